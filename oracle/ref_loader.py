@@ -1,0 +1,70 @@
+"""Import the *reference's own* ``model.py`` from /root/reference (build container
+only -- the GPU box has no /root/reference).  TEST INFRASTRUCTURE ONLY.
+
+Used by ``oracle/pin_against_reference.py`` and ``tests/golden/make_golden.py``.
+Both reference variants define top-level modules ``model`` and ``transforms``
+(code/dmcnet/model.py:12, code/dmcnet_GAN/model.py:12), so they are loaded one
+at a time under private names.  The only patch: ``torchvision.models.resnet18(
+pretrained=True)`` (code/dmcnet/model.py:305) would download weights -> it is
+wrapped to ``weights=None``.
+"""
+import contextlib
+import importlib.util
+import io
+import os
+import sys
+import warnings
+
+REFERENCE_ROOT = os.environ.get('DMC_REFERENCE_ROOT', '/root/reference')
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'code', 'dmcnet', 'model.py'))
+
+
+def load_reference_model_module(variant: str):
+    """variant in {'dmcnet', 'dmcnet_GAN'} -> the imported reference module."""
+    import torchvision
+    d = os.path.join(REFERENCE_ROOT, 'code', variant)
+    name = '_ref_%s_model' % variant
+    if name in sys.modules:
+        return sys.modules[name]
+    saved_path = list(sys.path)
+    saved_tf = sys.modules.pop('transforms', None)
+    sys.path.insert(0, d)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')          # SyntaxWarning: `is 'ContextNetwork'`
+            spec = importlib.util.spec_from_file_location(name, os.path.join(d, 'model.py'))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved_path
+        sys.modules.pop('transforms', None)
+        if saved_tf is not None:
+            sys.modules['transforms'] = saved_tf
+    sys.modules[name] = mod
+
+    orig = {}
+
+    class _TV:                                         # proxy seen by the reference as `torchvision`
+        def __getattr__(self, k):
+            return getattr(torchvision, k)
+
+    class _Models:
+        def __getattr__(self, k):
+            fn = getattr(torchvision.models, k)
+            if k.startswith('resnet'):
+                return lambda pretrained=False, **kw: fn(weights=None, **kw)
+            return fn
+
+    tv = _TV()
+    tv.__dict__['models'] = _Models()
+    mod.torchvision = tv
+    return mod
+
+
+def build_reference_model(variant: str, *args, **kwargs):
+    mod = load_reference_model_module(variant)
+    with contextlib.redirect_stdout(io.StringIO()):    # the ctor prints a banner
+        return mod.Model(*args, **kwargs)
