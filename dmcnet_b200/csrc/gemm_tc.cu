@@ -1,0 +1,437 @@
+// tcgen05 tensor-core kernels for the classifier / discriminator convolutions.
+//
+// A 3x3 convolution over the padded pixel-major layout [frames][Hp][Wp][C] is a
+// sum of "row-shifted" GEMMs: out[q][co] = sum_tap sum_ci act[q + shift(tap)][ci] *
+// w[tap][co][ci], where shift(tap) = dr*Wp + ds is a flat offset.  Border rows
+// produce garbage and are masked to zero in the epilogue, which keeps the zero
+// ring intact for the next layer.  Stride-2 convolutions read four parity
+// "phases" of the input, each stored in the OUTPUT geometry, so they use the
+// same kernel with a per-tap phase index (see phase_split in pixelwise.cu).
+//
+// Precision: operands are bf16 hi/lo pairs; each k-step issues hi*hi, lo*hi and
+// hi*lo MMAs into one fp32 TMEM accumulator (~2^-16 relative error).
+//
+//   tap_gemm_kernel  : D[P][N]  = sum_t A_ph(t)[q+s_t][K] * B_t[N][K]^T    (fprop, dgrad)
+//                      K-major operands, TMA 3-D tiled loads, 128 x BN tile per CTA.
+//   wgrad_gemm_kernel: dW_t[M][N] += sum_q G[q][M] * A_ph(t)[q+s_t][N]     (split-K, atomics)
+//                      MN-major operands (pixel index is K).
+#include "common.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace dmc {
+
+static constexpr int MAX_TAPS = 16;
+struct TapTable {
+  int ntaps;
+  int shift[MAX_TAPS];   // row shift applied to the A operand
+  int phase[MAX_TAPS];   // A phase (outer TMA coordinate)
+  int bsel[MAX_TAPS];    // which weight slice
+};
+
+// ------------------------------------------------------------------ tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  return g_encode;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], SWIZZLE_128B.
+static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint32_t box0, uint32_t box1) {
+  auto enc = get_encode();
+  if (!enc) {
+    dmc_set_error("cuTensorMapEncodeTiled entry point not available");
+    return DMC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(bf16), d0 * d1 * sizeof(bf16)};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dmc_set_error("cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu box=%u,%u", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0,
+                  box1);
+    return DMC_ERR_CUDA;
+  }
+  return DMC_OK;
+}
+
+// ------------------------------------------------------------------ fprop / dgrad
+template <int BN, int STAGES>
+struct TapGemmSmem {
+  static constexpr int A_BYTES = 128 * 128;        // 128 rows x 64 bf16
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+tap_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
+                int K, int Hp, int Wp) {
+  using S = TapGemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
+  // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full @ +16*STAGES, tmem slot after
+  const uint32_t tmem_full = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = tmem_full + 8;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long m0 = (long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int kblocks = K / 64;
+  const int iters = taps.ntaps * kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapAh);
+    tma_prefetch_desc(&mapAl);
+    tma_prefetch_desc(&mapBh);
+    tma_prefetch_desc(&mapBl);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
+      const int t = i / kblocks, kb = i - t * kblocks;
+      const uint32_t full = bar_base + 8 * s;
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+      mbar_expect_tx(full, S::STAGE_BYTES);
+      const int row = (int)(m0 + taps.shift[t]);
+      tma_load_3d(st, &mapAh, full, kb * 64, row, taps.phase[t]);
+      tma_load_3d(st + S::A_BYTES, &mapAl, full, kb * 64, row, taps.phase[t]);
+      tma_load_3d(st + 2 * S::A_BYTES, &mapBh, full, kb * 64, n0, taps.bsel[t]);
+      tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &mapBl, full, kb * 64, n0, taps.bsel[t]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ah = umma_desc_sw128(st + ks * 32, 16, 1024);
+        const uint64_t al = umma_desc_sw128(st + S::A_BYTES + ks * 32, 16, 1024);
+        const uint64_t bh = umma_desc_sw128(st + 2 * S::A_BYTES + ks * 32, 16, 1024);
+        const uint64_t bl = umma_desc_sw128(st + 2 * S::A_BYTES + S::B_BYTES + ks * 32, 16, 1024);
+        umma_bf16(tmem_d, al, bh, idesc, (i | ks) != 0);
+        umma_bf16(tmem_d, ah, bl, idesc, 1);
+        umma_bf16(tmem_d, ah, bh, idesc, 1);
+      }
+      umma_commit(bar_base + 8 * (STAGES + s));   // frees the smem slot when the MMAs retire
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> global (lane = output row)
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+  const long q = m0 + warp * 32 + lane;
+  const bool in_range = q < M;
+  const bool keep = in_range && (Hp == 0 || interior(q, Hp, Wp));
+  float* drow = D + q * (long)ldD + n0;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_wait();
+    if (in_range) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + c + j < N) {
+          float4 v;
+          v.x = keep ? __uint_as_float(r[j + 0]) : 0.f;
+          v.y = keep ? __uint_as_float(r[j + 1]) : 0.f;
+          v.z = keep ? __uint_as_float(r[j + 2]) : 0.f;
+          v.w = keep ? __uint_as_float(r[j + 3]) : 0.f;
+          *reinterpret_cast<float4*>(drow + c + j) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+}
+
+template <int BN, int STAGES>
+static int launch_tap_gemm(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
+                           const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
+                           int ldD, int K, int Hp, int Wp, cudaStream_t stream) {
+  using S = TapGemmSmem<BN, STAGES>;
+  auto kern = tap_gemm_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+        cudaSuccess)
+      return dmc_check_launch("tap_gemm smem attribute");
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, BN));
+  kern<<<grid, 128, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp);
+  return dmc_check_launch("tap_gemm_kernel");
+}
+
+// ------------------------------------------------------------------ wgrad (split-K)
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int BOX_BYTES = 64 * 128;       // 64 pixels x 64 channels bf16
+  static constexpr int G_BYTES = 2 * BOX_BYTES;    // M = 128 channels of dY
+  static constexpr int X_BYTES = (BN / 64) * BOX_BYTES;
+  static constexpr int STAGE_BYTES = 2 * G_BYTES + 2 * X_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
+                  const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+                  const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
+                  long P, int kb_per_split, int n_tiles) {
+  using S = WgradSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
+  const uint32_t tmem_full = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = tmem_full + 8;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.z;
+  const int mt = blockIdx.y / n_tiles, nt = blockIdx.y % n_tiles;
+  const int m0 = mt * 128, n0 = nt * BN;
+  const long kb_total = cdiv(P, 64);
+  const long kb0 = (long)blockIdx.x * kb_per_split;
+  long kb1 = kb0 + kb_per_split;
+  if (kb1 > kb_total) kb1 = kb_total;
+  const int iters = (int)(kb1 - kb0);
+  const int m_boxes = (Cout - m0) >= 128 ? 2 : 1;   // second 64-channel group may not exist
+  const uint32_t stage_tx = (uint32_t)(2 * m_boxes * S::BOX_BYTES + 2 * S::X_BYTES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapGh);
+    tma_prefetch_desc(&mapGl);
+    tma_prefetch_desc(&mapXh);
+    tma_prefetch_desc(&mapXl);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  if (iters <= 0) {   // uniform per CTA
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+    return;
+  }
+
+  if (warp == 0 && lane == 0) {
+    const int shift = taps.shift[t], phase = taps.phase[t];
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
+      const uint32_t full = bar_base + 8 * s;
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+      mbar_expect_tx(full, stage_tx);
+      const int row = (int)((kb0 + i) * 64);
+      for (int b = 0; b < m_boxes; ++b) {
+        tma_load_3d(st + b * S::BOX_BYTES, &mapGh, full, m0 + 64 * b, row, 0);
+        tma_load_3d(st + S::G_BYTES + b * S::BOX_BYTES, &mapGl, full, m0 + 64 * b, row, 0);
+      }
+#pragma unroll
+      for (int b = 0; b < BN / 64; ++b) {
+        tma_load_3d(st + 2 * S::G_BYTES + b * S::BOX_BYTES, &mapXh, full, n0 + 64 * b, row + shift,
+                    phase);
+        tma_load_3d(st + 2 * S::G_BYTES + S::X_BYTES + b * S::BOX_BYTES, &mapXl, full, n0 + 64 * b,
+                    row + shift, phase);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(BN, 1, 1);
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {     // 16 pixels per MMA = two 8-row swizzle atoms
+        const uint32_t koff = ks * 2048;
+        const uint64_t gh = umma_desc_sw128(st + koff, S::BOX_BYTES, 1024);
+        const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
+        const uint64_t xh = umma_desc_sw128(st + 2 * S::G_BYTES + koff, S::BOX_BYTES, 1024);
+        const uint64_t xl =
+            umma_desc_sw128(st + 2 * S::G_BYTES + S::X_BYTES + koff, S::BOX_BYTES, 1024);
+        umma_bf16(tmem_d, gl, xh, idesc, (i | ks) != 0);
+        umma_bf16(tmem_d, gh, xl, idesc, 1);
+        umma_bf16(tmem_d, gh, xh, idesc, 1);
+      }
+      umma_commit(bar_base + 8 * (STAGES + s));
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+  const int co = m0 + warp * 32 + lane;
+  float* wrow = dW + ((long)taps.bsel[t] * Cout + co) * Cin + n0;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_wait();
+    if (co < Cout) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + c + j < Cin) atomicAdd(wrow + c + j, __uint_as_float(r[j]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& mGh, const CUtensorMap& mGl, const CUtensorMap& mXh,
+                        const CUtensorMap& mXl, const TapTable& taps, float* dW, int Cout, int Cin,
+                        long P, int sm_count, cudaStream_t stream) {
+  using S = WgradSmem<BN, STAGES>;
+  auto kern = wgrad_gemm_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+        cudaSuccess)
+      return dmc_check_launch("wgrad smem attribute");
+    attr_set = true;
+  }
+  const int m_tiles = (int)cdiv(Cout, 128), n_tiles = (int)cdiv(Cin, BN);
+  const long kb_total = cdiv(P, 64);
+  const long tiles = (long)m_tiles * n_tiles * taps.ntaps;
+  long want_splits = cdiv((long)sm_count * 4, tiles);     // ~4 waves of CTAs
+  if (want_splits < 1) want_splits = 1;
+  long kb_per_split = cdiv(kb_total, want_splits);
+  if (kb_per_split < 8) kb_per_split = 8;
+  const long splits = cdiv(kb_total, kb_per_split);
+  dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)taps.ntaps);
+  kern<<<grid, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, Cout, Cin, P,
+                                        (int)kb_per_split, n_tiles);
+  return dmc_check_launch("wgrad_gemm_kernel");
+}
+
+static int fill_taps(TapTable& tt, int ntaps, const int* shift, const int* phase, const int* bsel) {
+  if (ntaps < 1 || ntaps > MAX_TAPS) return -1;
+  tt.ntaps = ntaps;
+  for (int i = 0; i < MAX_TAPS; ++i) {
+    tt.shift[i] = i < ntaps ? shift[i] : 0;
+    tt.phase[i] = i < ntaps ? phase[i] : 0;
+    tt.bsel[i] = i < ntaps ? bsel[i] : 0;
+  }
+  return 0;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+}  // namespace dmc
+
+using namespace dmc;
+
+// D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
+extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                               const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
+                               long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
+                               const int* phase, const int* bsel, void* stream) {
+  DMC_REQUIRE(K > 0 && K % 64 == 0, "tap_gemm: K=%d must be a positive multiple of 64", K);
+  DMC_REQUIRE(N > 0 && N % 32 == 0, "tap_gemm: N=%d must be a multiple of 32", N);
+  DMC_REQUIRE(ldD % 4 == 0 && ldD >= N, "tap_gemm: ldD=%d", ldD);
+  DMC_REQUIRE(M > 0 && a_rows > 0 && a_rows < (1L << 31), "tap_gemm: bad rows");
+  TapTable tt;
+  DMC_REQUIRE(fill_taps(tt, ntaps, shift, phase, bsel) == 0, "tap_gemm: ntaps=%d", ntaps);
+  for (int i = 0; i < ntaps; ++i)
+    DMC_REQUIRE(phase[i] >= 0 && phase[i] < a_phases && bsel[i] >= 0 && bsel[i] < b_slices,
+                "tap_gemm: tap %d out of range", i);
+  const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, 128))) return rc;
+  if ((rc = make_map_3d(&mAl, A_lo, K, a_rows, a_phases, 64, 128))) return rc;
+  if ((rc = make_map_3d(&mBh, B_hi, K, N, b_slices, 64, BN))) return rc;
+  if ((rc = make_map_3d(&mBl, B_lo, K, N, b_slices, 64, BN))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 128) return launch_tap_gemm<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
+  if (BN == 64) return launch_tap_gemm<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
+  return launch_tap_gemm<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
+}
+
+// dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW)
+extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
+                            const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
+                            const int* shift, const int* phase, const int* bsel, void* stream) {
+  DMC_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0, "wgrad: Cout=%d Cin=%d must be multiples of 64", Cout,
+              Cin);
+  DMC_REQUIRE(P > 0 && P < (1L << 31), "wgrad: bad P");
+  TapTable tt;
+  DMC_REQUIRE(fill_taps(tt, ntaps, shift, phase, bsel) == 0, "wgrad: ntaps=%d", ntaps);
+  for (int i = 0; i < ntaps; ++i)
+    DMC_REQUIRE(phase[i] >= 0 && phase[i] < x_phases, "wgrad: tap %d phase out of range", i);
+  const int BN = (Cin % 128 == 0) ? 128 : 64;
+  CUtensorMap mGh, mGl, mXh, mXl;
+  int rc;
+  if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, 64))) return rc;
+  if ((rc = make_map_3d(&mGl, G_lo, Cout, P, 1, 64, 64))) return rc;
+  if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, 64))) return rc;
+  if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, 64))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 128)
+    return launch_wgrad<128, 3>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
+  return launch_wgrad<64, 4>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
+}
