@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -14,7 +15,10 @@ void dmc_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
 int dmc_check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     dmc_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -41,3 +45,8 @@ extern "C" int dmc_device_arch(void) {
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   return major * 10 + minor;
 }
+
+// Number of kernel launches issued by this library since the last reset (every
+// launch site goes through dmc_check_launch exactly once).
+extern "C" long long dmc_launch_count(void) { return g_launches.load(); }
+extern "C" void dmc_reset_launch_count(void) { g_launches.store(0); }

@@ -1,0 +1,196 @@
+// Loss heads and small dense layers.
+//   linear_fwd / bwd        : classifier fc (512 -> num_class) and the
+//                             discriminator's adv_layer (25088 -> 2).
+//   ce_head                 : TSN segment consensus (mean of the logits over the
+//                             S segments of a clip, code/dmcnet/train.py:239-240),
+//                             cross-entropy (train.py:241), its gradient w.r.t. the
+//                             per-frame logits, and top-1 / top-5 hits
+//                             (train.py:411-424) in one launch.  With S = 1 and
+//                             C = 2 it is the adversarial CE (GAN/train.py:274,346).
+//   mse_head                : flow-reconstruction MSE (train.py:245) and its
+//                             gradient in one streaming pass.
+// All losses are reported as SUMS over the local shard plus a caller-provided
+// global normaliser, so that a sum all-reduce reproduces the global mean.
+#include "common.cuh"
+
+namespace dmc {
+
+__global__ void __launch_bounds__(128)
+linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                  const float* __restrict__ b, int K, int N, float* __restrict__ out) {
+  const int m = blockIdx.x, j = blockIdx.y;
+  const float* xp = x + (long)m * K;
+  const float* wp = w + (long)j * K;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) s = fmaf(xp[k], wp[k], s);
+  __shared__ float red[4];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) out[(long)m * N + j] = red[0] + red[1] + red[2] + red[3] + (b ? b[j] : 0.f);
+}
+
+// dx[m][k] = sum_j dy[m][j] * w[j][k]
+__global__ void linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                       int M, int K, int N, float* __restrict__ dx) {
+  const long total = (long)M * K;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long m = i / K;
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s = fmaf(dy[m * N + j], w[(long)j * K + k], s);
+    dx[i] = s;
+  }
+}
+
+// dw[j][k] = sum_m dy[m][j] * x[m][k];  db[j] = sum_m dy[m][j]
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                         int M, int K, int N, float* __restrict__ dw,
+                                         float* __restrict__ db) {
+  const long total = (long)N * K;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int j = (int)(i / K);
+    float s = 0.f, sb = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float d = dy[(long)m * N + j];
+      s = fmaf(d, x[(long)m * K + k], s);
+      sb += d;
+    }
+    dw[i] = s;
+    if (k == 0 && db) db[j] = sb;
+  }
+}
+
+// out_stats: [0] loss sum over clips, [1] top-1 hits, [2] top-5 hits  (fp32, overwritten)
+// consensus[b][c] written when non-null.  dlogits[n][c] = gscale * (softmax - onehot) / S.
+__global__ void __launch_bounds__(256)
+ce_head_kernel(const float* __restrict__ logits, int B, int S, int C,
+               const long long* __restrict__ target, float gscale, float* __restrict__ consensus,
+               float* __restrict__ dlogits, float* __restrict__ out_stats) {
+  __shared__ float s_loss[256], s_t1[256], s_t5[256];
+  float loss = 0.f, t1 = 0.f, t5 = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* lp = logits + (long)b * S * C;
+    const int tgt = (int)target[b];
+    const float invS = 1.f / (float)S;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float v = 0.f;
+      for (int s = 0; s < S; ++s) v += lp[s * C + c];
+      v *= invS;
+      mx = fmaxf(mx, v);
+    }
+    float den = 0.f, vt = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float v = 0.f;
+      for (int s = 0; s < S; ++s) v += lp[s * C + c];
+      v *= invS;
+      if (consensus) consensus[(long)b * C + c] = v;
+      den += expf(v - mx);
+      if (c == tgt) vt = v;
+    }
+    const float lse = mx + logf(den);
+    loss += lse - vt;
+    int rank = 0;
+    for (int c = 0; c < C; ++c) {
+      float v = 0.f;
+      for (int s = 0; s < S; ++s) v += lp[s * C + c];
+      v *= invS;
+      // torch.topk order: larger value first, lower index first among equals
+      if (v > vt || (v == vt && c < tgt)) ++rank;
+      if (dlogits) {
+        const float p = expf(v - lse);
+        const float g = gscale * invS * (p - (c == tgt ? 1.f : 0.f));
+        for (int s = 0; s < S; ++s) dlogits[((long)b * S + s) * C + c] = g;
+      }
+    }
+    t1 += rank < 1 ? 1.f : 0.f;
+    t5 += rank < 5 ? 1.f : 0.f;
+  }
+  s_loss[threadIdx.x] = loss;
+  s_t1[threadIdx.x] = t1;
+  s_t5[threadIdx.x] = t5;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b1 = 0, b5 = 0;
+    for (int i = 0; i < blockDim.x; ++i) { a += s_loss[i]; b1 += s_t1[i]; b5 += s_t5[i]; }
+    out_stats[0] = (float)a;
+    out_stats[1] = (float)b1;
+    out_stats[2] = (float)b5;
+  }
+}
+
+// loss_sum += sum (gen-flow)^2 (double);  dgen = gscale * (gen - flow)  (gscale = 2*lr_mse/numel)
+__global__ void __launch_bounds__(256)
+mse_head_kernel(const float* __restrict__ gen, const float* __restrict__ flow, long n4, float gscale,
+                float* __restrict__ dgen, double* __restrict__ loss_sum) {
+  float s = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(gen)[i];
+    const float4 b = reinterpret_cast<const float4*>(flow)[i];
+    const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    s += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    if (dgen)
+      reinterpret_cast<float4*>(dgen)[i] =
+          make_float4(gscale * d.x, gscale * d.y, gscale * d.z, gscale * d.w);
+  }
+  __shared__ double red[8];
+  double sd = warp_sum_d((double)s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) sd += red[i];
+    atomicAdd(loss_sum, sd);
+  }
+}
+
+}  // namespace dmc
+
+using namespace dmc;
+#define ST_(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int dmc_linear_fwd(const float* x, const float* w, const float* b, int M, int K, int N,
+                              float* out, void* stream) {
+  linear_fwd_kernel<<<dim3(M, N), 128, 0, ST_(stream)>>>(x, w, b, K, N, out);
+  return dmc_check_launch("linear_fwd_kernel");
+}
+
+extern "C" int dmc_linear_bwd(const float* dy, const float* x, const float* w, int M, int K, int N,
+                              float* dx, float* dw, float* db, void* stream) {
+  if (dx) {
+    long blocks = cdiv((long)M * K, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    linear_bwd_data_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(dy, w, M, K, N, dx);
+    int rc = dmc_check_launch("linear_bwd_data_kernel");
+    if (rc) return rc;
+  }
+  if (dw) {
+    long blocks = cdiv((long)N * K, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    linear_bwd_weight_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(dy, x, M, K, N, dw, db);
+    return dmc_check_launch("linear_bwd_weight_kernel");
+  }
+  return DMC_OK;
+}
+
+extern "C" int dmc_ce_head(const float* logits, int B, int S, int C, const long long* target,
+                           float gscale, float* consensus, float* dlogits, float* out_stats,
+                           void* stream) {
+  DMC_REQUIRE(B > 0 && S > 0 && C > 0, "ce_head: bad shape");
+  ce_head_kernel<<<1, 256, 0, ST_(stream)>>>(logits, B, S, C, target, gscale, consensus, dlogits,
+                                             out_stats);
+  return dmc_check_launch("ce_head_kernel");
+}
+
+extern "C" int dmc_mse_head(const float* gen, const float* flow, long numel, float gscale,
+                            float* dgen, double* loss_sum, void* stream) {
+  DMC_REQUIRE(numel % 4 == 0, "mse_head: numel must be a multiple of 4");
+  if (cudaMemsetAsync(loss_sum, 0, sizeof(double), ST_(stream)) != cudaSuccess)
+    return dmc_check_launch("mse_head memset");
+  long blocks = cdiv(numel / 4, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  mse_head_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, numel / 4, gscale, dgen, loss_sum);
+  return dmc_check_launch("mse_head_kernel");
+}

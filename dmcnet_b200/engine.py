@@ -1,0 +1,727 @@
+"""Device-side execution plan of the DMC-Net hot path.
+
+``DmcEngine`` owns every device buffer (flat parameter / gradient / Adam-moment
+buckets, activations, scratch) and sequences the C-ABI kernels for
+
+  * the generator  EstimatorDenseNetTiny   (code/dmcnet/model.py:172-194)
+  * the classifier ResNet-18 on the 2-channel DMC map (model.py:283-308)
+  * the discriminator blocks               (code/dmcnet_GAN/model.py:254-438)
+  * forward  = ``Model.forward``           (dmcnet/model.py:330-357, GAN :533-566)
+  * backward = what autograd does in the reference for
+    ``loss.backward()`` (dmcnet/train.py:264, GAN/train.py:300,369)
+
+PyTorch is used for memory, streams and (optionally) CUDA-graph capture only;
+no torch operator runs on the data path.  Layouts:
+
+  planar   fp32 [N][C][H][W]                    generator, discriminator, stem conv
+  pixel    [N][H+2][W+2][C] with a zero ring    classifier, as bf16 hi/lo planes
+           (activations, GEMM operands) or fp32 (raw conv outputs, gradients)
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+GEN_GROWTH = (8, 8, 6, 4, 2)          # code/dmcnet/model.py:175-183
+GEN_IN = 5
+BN_MOMENTUM = 0.1
+
+
+def disc_blocks(arch_d: str) -> List[Tuple[str, int, int, int, bool]]:
+    """(suffix, cin, cout, stride, has_bn) per block; code/dmcnet_GAN/model.py:254-438."""
+    if arch_d == 'Discriminator4':
+        return [('1', 2, 8, 2, False), ('2', 8, 16, 2, True), ('3', 16, 32, 2, True)]
+    extra = {'Discriminator': 0, 'Discriminator2': 1, 'Discriminator3': 2, 'Discriminator5': 4}[arch_d]
+    blocks, cin = [], 2
+    for stage, cout in enumerate((16, 32, 64, 128), start=1):
+        blocks.append((str(stage), cin, cout, 2, stage != 1))
+        for j in range(extra):
+            blocks.append(('%d_%d' % (stage, j + 2), cout, cout, 1, True))
+        cin = cout
+    return blocks
+
+
+class _Geo:
+    """Padded pixel-major geometry of one classifier stage."""
+
+    def __init__(self, frames: int, H: int, W: int):
+        self.frames, self.H, self.W = frames, H, W
+        self.Hp, self.Wp = H + 2, W + 2
+        self.P = frames * self.Hp * self.Wp
+        self.count = float(frames * H * W)
+
+
+def _taps_s1(Wp: int):
+    shift = [(r - 1) * Wp + (s - 1) for r in range(3) for s in range(3)]
+    return shift, [0] * 9, list(range(9))
+
+
+# stride-2 3x3: kernel row r reads input row 2*oh + r - 1 = phase (r+1)%2 at oh + (r==0 ? -1 : 0)
+_S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+
+
+def _taps_s2(Wq: int):
+    shift, phase, bsel = [], [], []
+    for r in range(3):
+        for s in range(3):
+            (ph, dr), (pw, ds) = _S2[r], _S2[s]
+            shift.append(dr * Wq + ds)
+            phase.append(ph * 2 + pw)
+            bsel.append(r * 3 + s)
+    return shift, phase, bsel
+
+
+class _ConvBN:
+    """One conv + BatchNorm unit of the classifier (pixel-major, tensor cores)."""
+
+    def __init__(self, eng: 'DmcEngine', name_conv: str, name_bn: str, cin: int, cout: int, ks: int,
+                 stride: int, geo_out: _Geo):
+        dev = eng.device
+        self.name_conv, self.name_bn = name_conv, name_bn
+        self.cin, self.cout, self.ks, self.stride, self.geo = cin, cout, ks, stride, geo_out
+        self.taps = ks * ks
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.W_hi = torch.zeros(self.taps, cout, cin, **bf)
+        self.W_lo = torch.zeros(self.taps, cout, cin, **bf)
+        self.Wt_hi = self.Wt_lo = None            # assigned by the owner (may be a shared stack)
+        self.Y = torch.zeros(geo_out.P, cout, **f32)
+        self.act_hi = torch.zeros(geo_out.P, cout, **bf)
+        self.act_lo = torch.zeros(geo_out.P, cout, **bf)
+        self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.sums2 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.scale = torch.zeros(cout, **f32)
+        self.shift = torch.zeros(cout, **f32)
+        self.mean = torch.zeros(cout, **f32)
+        self.invstd = torch.ones(cout, **f32)
+
+
+class DmcEngine:
+    def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
+                 arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
+                 width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
+        if height % 32 or width % 32:
+            raise ValueError('height/width must be multiples of 32')
+        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.num_class, self.S, self.N = num_class, num_segments, frames
+        self.gan, self.arch_d = gan, (arch_d if gan else None)
+        self.gen_flow_or_delta = gen_flow_or_delta
+        self.H, self.W = height, width
+        self.gemm_engine = gemm_engine
+        self._build_param_table()
+        self._alloc_generator()
+        self._alloc_classifier()
+        if self.gan:
+            self._alloc_discriminator()
+
+    # ------------------------------------------------------------------ parameters
+    def _param_specs(self) -> "OrderedDict[str, Tuple[int, ...]]":
+        C = self.num_class
+        specs: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+        specs['base_model.conv1.weight'] = (64, 2, 7, 7)
+        specs['base_model.bn1.weight'] = (64,)
+        specs['base_model.bn1.bias'] = (64,)
+        cin = 64
+        for li, (width, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+            for b in range(2):
+                q = 'base_model.layer%d.%d' % (li, b)
+                s = stride if b == 0 else 1
+                specs[q + '.conv1.weight'] = (width, cin, 3, 3)
+                specs[q + '.bn1.weight'] = (width,)
+                specs[q + '.bn1.bias'] = (width,)
+                specs[q + '.conv2.weight'] = (width, width, 3, 3)
+                specs[q + '.bn2.weight'] = (width,)
+                specs[q + '.bn2.bias'] = (width,)
+                if b == 0 and (s != 1 or cin != width):
+                    specs[q + '.downsample.0.weight'] = (width, cin, 1, 1)
+                    specs[q + '.downsample.1.weight'] = (width,)
+                    specs[q + '.downsample.1.bias'] = (width,)
+                cin = width
+        specs['base_model.fc.weight'] = (C, 512)
+        specs['base_model.fc.bias'] = (C,)
+        cin = GEN_IN
+        for k, g in enumerate(GEN_GROWTH):
+            specs['gen_flow_model.conv_%d.0.weight' % k] = (g, cin, 3, 3)
+            specs['gen_flow_model.conv_%d.0.bias' % k] = (g,)
+            cin += g
+        specs['gen_flow_model.predict_flow.weight'] = (2, cin, 3, 3)
+        specs['gen_flow_model.predict_flow.bias'] = (2,)
+        if self.gan:
+            for name, ci, co, stride, bn in disc_blocks(self.arch_d):
+                p = 'discriminator.discriminator_block_%s' % name
+                specs[p + '.0.weight'] = (co, ci, 3, 3)
+                specs[p + '.0.bias'] = (co,)
+                if bn:
+                    specs[p + '.3.weight'] = (co,)
+                    specs[p + '.3.bias'] = (co,)
+            fc_in = 32 * (self.H // 8) * (self.W // 8) if self.arch_d == 'Discriminator4' \
+                else 128 * (self.H // 16) * (self.W // 16)
+            specs['discriminator.adv_layer.weight'] = (2, fc_in)
+            specs['discriminator.adv_layer.bias'] = (2,)
+        return specs
+
+    def _build_param_table(self):
+        dev = self.device
+        self.specs = self._param_specs()
+        self.offsets: Dict[str, int] = {}
+        self.group_range: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for tag in ('base_model', 'gen_flow_model', 'discriminator'):
+            start = off
+            for k, shp in self.specs.items():
+                if not k.startswith(tag):
+                    continue
+                n = 1
+                for d in shp:
+                    n *= d
+                self.offsets[k] = off
+                off += (n + 63) // 64 * 64
+            self.group_range[tag] = (start, off)
+        self.total = off
+        z = lambda: torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        # BatchNorm buffers (state_dict entries that are not parameters)
+        self.buffers: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for k, shp in self.specs.items():
+            if k.endswith('.weight') and len(shp) == 1:        # a BatchNorm weight
+                base = k[:-len('.weight')]
+                self.buffers[base + '.running_mean'] = torch.zeros(shp, dtype=torch.float32, device=dev)
+                self.buffers[base + '.running_var'] = torch.ones(shp, dtype=torch.float32, device=dev)
+                self.buffers[base + '.num_batches_tracked'] = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def numel(self, key: str) -> int:
+        n = 1
+        for d in self.specs[key]:
+            n *= d
+        return n
+
+    def p(self, key: str) -> torch.Tensor:
+        o = self.offsets[key]
+        return self.params[o:o + self.numel(key)]
+
+    def g(self, key: str) -> torch.Tensor:
+        o = self.offsets[key]
+        return self.grads[o:o + self.numel(key)]
+
+    def param_view(self, key: str) -> torch.Tensor:
+        return self.p(key).view(self.specs[key])
+
+    def grad_view(self, key: str) -> torch.Tensor:
+        return self.g(key).view(self.specs[key])
+
+    def state_keys(self) -> List[str]:
+        """state_dict key order of the reference ``Model`` (torch module order)."""
+        keys: List[str] = []
+        for k in self.specs:
+            keys.append(k)
+            if k.endswith('.bias') and (k[:-len('.bias')] + '.running_mean') in self.buffers:
+                base = k[:-len('.bias')]
+                keys += [base + '.running_mean', base + '.running_var', base + '.num_batches_tracked']
+        return keys
+
+    def load_state(self, sd: Dict[str, torch.Tensor]) -> None:
+        for k in self.specs:
+            self.p(k).copy_(sd[k].detach().reshape(-1).to(self.device, torch.float32))
+        for k, b in self.buffers.items():
+            b.copy_(sd[k].detach().to(self.device))
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for k in self.state_keys():
+            out[k] = (self.param_view(k) if k in self.specs else self.buffers[k]).detach().clone()
+        return out
+
+    # ------------------------------------------------------------------ allocation
+    def _alloc_generator(self):
+        dev, N, H, W = self.device, self.N, self.H, self.W
+        self.gen_ctot = GEN_IN + sum(GEN_GROWTH)                      # 33
+        self.X = torch.zeros(N, self.gen_ctot, H, W, dtype=torch.float32, device=dev)
+        self.dX = torch.zeros(N, self.gen_ctot - GEN_IN, H, W, dtype=torch.float32, device=dev)
+        self.gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
+        self.d_gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
+        # channel offset of each layer's OUTPUT inside X: new channels are prepended
+        outs, off = [], self.gen_ctot - GEN_IN
+        for g in GEN_GROWTH:
+            off -= g
+            outs.append(off)
+        self.gen_out_off = outs                                          # [20, 12, 6, 2, 0]
+        self.gen_in_off = [o + g for o, g in zip(outs, GEN_GROWTH)]      # [28, 20, 12, 6, 2]
+        self.mv_off = self.gen_ctot - GEN_IN                             # 28
+
+    def _alloc_classifier(self):
+        dev, N = self.device, self.N
+        H2, W2 = self.H // 2, self.W // 2
+        f32 = dict(dtype=torch.float32, device=dev)
+        # stem (planar)
+        self.stem_Y = torch.zeros(N, 64, H2, W2, **f32)
+        self.stem_dZ = torch.zeros(N, 64, H2, W2, **f32)
+        self.stem = {k: torch.zeros(64, **f32) for k in ('scale', 'shift', 'mean', 'invstd')}
+        self.stem['sums'] = torch.zeros(2, 64, dtype=torch.float64, device=dev)
+        self.stem['sums2'] = torch.zeros(2, 64, dtype=torch.float64, device=dev)
+        g = _Geo(N, self.H // 4, self.W // 4)
+        self.geo0 = g
+        self.A0_hi = torch.zeros(g.P, 64, dtype=torch.bfloat16, device=dev)
+        self.A0_lo = torch.zeros(g.P, 64, dtype=torch.bfloat16, device=dev)
+        self.pool_idx = torch.zeros(N * (self.H // 4) * (self.W // 4) * 64, dtype=torch.uint8, device=dev)
+        # residual stages
+        self.blocks = []
+        cin, geo = 64, g
+        max_pc, max_w = 0, 0
+        for li, (width, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+            for b in range(2):
+                q = 'base_model.layer%d.%d' % (li, b)
+                s = stride if b == 0 else 1
+                geo_out = _Geo(N, geo.H // s, geo.W // s)
+                blk = {'name': q, 'stride': s, 'geo_in': geo, 'geo': geo_out, 'cin': cin, 'width': width}
+                blk['c1'] = _ConvBN(self, q + '.conv1', q + '.bn1', cin, width, 3, s, geo_out)
+                blk['c2'] = _ConvBN(self, q + '.conv2', q + '.bn2', width, width, 3, 1, geo_out)
+                bf = dict(dtype=torch.bfloat16, device=dev)
+                if s != 1 or cin != width:
+                    blk['ds'] = _ConvBN(self, q + '.downsample.0', q + '.downsample.1', cin, width, 1, s,
+                                        geo_out)
+                    # conv1 and downsample share one transposed-weight stack (dgrad B operand)
+                    wt_hi = torch.zeros(10, cin, width, **bf)
+                    wt_lo = torch.zeros(10, cin, width, **bf)
+                    blk['c1'].Wt_hi, blk['c1'].Wt_lo = wt_hi, wt_lo
+                    blk['ds'].Wt_hi, blk['ds'].Wt_lo = wt_hi[9:], wt_lo[9:]
+                    blk['xp_hi'] = torch.zeros(4, geo_out.P, cin, **bf)     # phase-split block input
+                    blk['xp_lo'] = torch.zeros(4, geo_out.P, cin, **bf)
+                    blk['dxp'] = torch.zeros(4, geo_out.P, cin, **f32)
+                else:
+                    blk['c1'].Wt_hi = torch.zeros(9, cin, width, **bf)
+                    blk['c1'].Wt_lo = torch.zeros(9, cin, width, **bf)
+                blk['c2'].Wt_hi = torch.zeros(9, width, width, **bf)
+                blk['c2'].Wt_lo = torch.zeros(9, width, width, **bf)
+                self.blocks.append(blk)
+                max_pc = max(max_pc, geo_out.P * width, geo.P * cin)
+                max_w = max(max_w, 9 * width * max(cin, width))
+                cin, geo = width, geo_out
+        self.geo_last = geo
+        # shared scratch
+        self.G_hi = torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)   # dY planes (x2: conv1|ds stack)
+        self.G_lo = torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)
+        self.gbuf = [torch.zeros(max_pc, **f32) for _ in range(5)]             # T1, T2a, Ra, T2b, Rb
+        self.dWs = torch.zeros(max_w, **f32)
+        self.pooled = torch.zeros(N, 512, **f32)
+        self.d_pooled = torch.zeros(N, 512, **f32)
+        self.logits = torch.zeros(N, self.num_class, **f32)
+        self.d_logits = torch.zeros(N, self.num_class, **f32)
+
+    def _alloc_discriminator(self):
+        dev, H, W = self.device, self.H, self.W
+        M = 2 * self.N
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.d_layers = []
+        h, w = H, W
+        for name, ci, co, stride, bn in disc_blocks(self.arch_d):
+            ho, wo = h // stride, w // stride
+            L = {'name': 'discriminator.discriminator_block_%s' % name, 'cin': ci, 'cout': co,
+                 'stride': stride, 'bn': bn, 'H': h, 'W': w, 'Ho': ho, 'Wo': wo}
+            L['A'] = torch.zeros(M, co, ho, wo, **f32)         # lrelu(conv)*mask
+            L['Z'] = torch.zeros(M, co, ho, wo, **f32) if bn else L['A']   # after BN (next input)
+            L['mask'] = torch.ones(M, co, **f32)
+            if bn:
+                for k in ('scale', 'shift', 'mean', 'invstd'):
+                    L[k] = torch.zeros(co, **f32)
+                L['sums'] = torch.zeros(2, co, dtype=torch.float64, device=dev)
+                L['sums2'] = torch.zeros(2, co, dtype=torch.float64, device=dev)
+            self.d_layers.append(L)
+            h, w = ho, wo
+        big = max(L['A'].numel() for L in self.d_layers)
+        self.d_in = torch.zeros(M, 2, H, W, **f32)
+        self.d_g = [torch.zeros(max(big, self.d_in.numel()), **f32) for _ in range(2)]
+        self.validity = torch.zeros(M, 2, **f32)
+        self.d_validity = torch.zeros(M, 2, **f32)
+        self.d_feat = torch.zeros(M, self.specs['discriminator.adv_layer.weight'][1], **f32)
+
+    # ------------------------------------------------------------------ generator
+    def _gen_forward(self, mv: torch.Tensor, res: torch.Tensor, n: int):
+        """EstimatorDenseNetTiny.forward (+ input_mv when gen_flow_or_delta == 1)."""
+        H, W = self.H, self.W
+        HW = H * W
+        X = self.X.view(-1)
+        ns = self.gen_ctot * HW
+        ops.copy_planar(mv, 2 * HW, X[self.mv_off * HW:], ns, 2 * HW, n)
+        ops.copy_planar(res, 3 * HW, X[(self.mv_off + 2) * HW:], ns, 3 * HW, n)
+        for k, g in enumerate(GEN_GROWTH):
+            cin = self.gen_ctot - self.gen_in_off[k]
+            ops.conv_fwd(X[self.gen_in_off[k] * HW:], ns, cin, H, W,
+                         self.p('gen_flow_model.conv_%d.0.weight' % k),
+                         self.p('gen_flow_model.conv_%d.0.bias' % k), g, 3, 1,
+                         X[self.gen_out_off[k] * HW:], ns, n, slope=0.1)
+        ops.conv_fwd(X, ns, self.gen_ctot, H, W, self.p('gen_flow_model.predict_flow.weight'),
+                     self.p('gen_flow_model.predict_flow.bias'), 2, 3, 1, self.gen_flow.view(-1),
+                     2 * HW, n, slope=1.0,
+                     add=(mv if self.gen_flow_or_delta == 1 else None), add_ns=2 * HW)
+
+    def _gen_backward(self, n: int):
+        """Gradients of all generator parameters from ``self.d_gen_flow``."""
+        H, W = self.H, self.W
+        HW = H * W
+        X, dX = self.X.view(-1), self.dX.view(-1)
+        ns, dns = self.gen_ctot * HW, (self.gen_ctot - GEN_IN) * HW
+        ngen = self.gen_ctot - GEN_IN                                   # 28 generated channels
+        dG = self.d_gen_flow.view(-1)
+        wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
+        ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dG, 2 * HW, 2, 3, 1, self.g(wk), self.g(bk), n)
+        ops.conv_dgrad(dG, 2 * HW, 2, self.p(wk), self.gen_ctot, ngen, 3, 1, dX, dns, H, W, n,
+                       accumulate=False)
+        for k in reversed(range(len(GEN_GROWTH))):
+            g = GEN_GROWTH[k]
+            oo, io = self.gen_out_off[k], self.gen_in_off[k]
+            cin = self.gen_ctot - io
+            wk, bk = 'gen_flow_model.conv_%d.0.weight' % k, 'gen_flow_model.conv_%d.0.bias' % k
+            # LeakyReLU(0.1) backward in place on this layer's slice of dX
+            ops.act_bwd_planar(dX[oo * HW:], dns, X[oo * HW:], ns, None, 0.1, g, HW, n, dX[oo * HW:], dns)
+            ops.conv_wgrad(X[io * HW:], ns, cin, H, W, dX[oo * HW:], dns, g, 3, 1, self.g(wk),
+                           self.g(bk), n)
+            if ngen - io > 0:
+                ops.conv_dgrad(dX[oo * HW:], dns, g, self.p(wk), cin, ngen - io, 3, 1, dX[io * HW:],
+                               dns, H, W, n, accumulate=True)
+
+    # ------------------------------------------------------------------ classifier
+    def _prep_weights(self):
+        """fp32 OIHW parameters -> bf16 hi/lo GEMM operands (fprop and transposed for dgrad)."""
+        for blk in self.blocks:
+            for key in ('c1', 'c2', 'ds'):
+                if key not in blk:
+                    continue
+                u = blk[key]
+                ops.weight_prep(self.p(u.name_conv + '.weight'), u.cout, u.cin, u.taps,
+                                u.W_hi, u.W_lo, u.Wt_hi, u.Wt_lo)
+
+    def _unit_bn(self, u: _ConvBN, train: bool):
+        """Batch statistics (train) or running statistics (eval) -> scale/shift of unit u."""
+        wk = u.name_bn
+        if train:
+            ops.bn_stats(u.Y, u.geo.P, u.cout, u.sums)
+            ops.bn_finalize(u.sums, u.geo.count, self.p(wk + '.weight'), self.p(wk + '.bias'),
+                            self.buffers[wk + '.running_mean'], self.buffers[wk + '.running_var'],
+                            self.buffers[wk + '.num_batches_tracked'], BN_MOMENTUM, 1e-5, u.cout,
+                            u.scale, u.shift, u.mean, u.invstd)
+        else:
+            ops.bn_eval_coeffs(self.p(wk + '.weight'), self.p(wk + '.bias'),
+                               self.buffers[wk + '.running_mean'], self.buffers[wk + '.running_var'],
+                               1e-5, u.cout, u.scale, u.shift)
+
+    def _conv_fwd(self, u: _ConvBN, a_hi, a_lo, a_phases: int):
+        geo = u.geo
+        if u.ks == 1:
+            shift, phase, bsel = [0], [0], [0]
+        elif u.stride == 1:
+            shift, phase, bsel = _taps_s1(geo.Wp)
+        else:
+            shift, phase, bsel = _taps_s2(geo.Wp)
+        ops.tap_gemm(a_hi, a_lo, u.W_hi, u.W_lo, u.Y, a_phases=a_phases, a_rows=geo.P, K=u.cin,
+                     b_slices=u.taps, N=u.cout, M=geo.P, ldD=u.cout, Hp=geo.Hp, Wp=geo.Wp,
+                     shift=shift, phase=phase, bsel=bsel, engine=self.gemm_engine)
+
+    def _cls_forward(self, x_planar: torch.Tensor, n: int, train: bool):
+        """ResNet-18 forward on a planar [n,2,H,W] input -> self.logits[:n]."""
+        H, W = self.H, self.W
+        if n != self.N:
+            raise RuntimeError('engine was built for %d frames, got %d' % (self.N, n))
+        self._prep_weights()
+        # stem: 7x7/2 conv (planar) -> BN -> ReLU -> maxpool -> pixel-major hi/lo
+        H2, W2 = H // 2, W // 2
+        ops.conv_fwd(x_planar, 2 * H * W, 2, H, W, self.p('base_model.conv1.weight'), None, 64, 7, 2,
+                     self.stem_Y.view(-1), 64 * H2 * W2, n)
+        st = self.stem
+        if train:
+            ops.bn_stats_planar(self.stem_Y, 64 * H2 * W2, 64, H2 * W2, n, st['sums'])
+            ops.bn_finalize(st['sums'], float(n * H2 * W2), self.p('base_model.bn1.weight'),
+                            self.p('base_model.bn1.bias'), self.buffers['base_model.bn1.running_mean'],
+                            self.buffers['base_model.bn1.running_var'],
+                            self.buffers['base_model.bn1.num_batches_tracked'], BN_MOMENTUM, 1e-5, 64,
+                            st['scale'], st['shift'], st['mean'], st['invstd'])
+        else:
+            ops.bn_eval_coeffs(self.p('base_model.bn1.weight'), self.p('base_model.bn1.bias'),
+                               self.buffers['base_model.bn1.running_mean'],
+                               self.buffers['base_model.bn1.running_var'], 1e-5, 64, st['scale'],
+                               st['shift'])
+        ops.stem_pool_fwd(self.stem_Y, st['scale'], st['shift'], n, 64, H2, W2, self.A0_hi, self.A0_lo,
+                          self.pool_idx)
+        x_hi, x_lo = self.A0_hi, self.A0_lo
+        for blk in self.blocks:
+            c1, c2, geo = blk['c1'], blk['c2'], blk['geo']
+            if 'ds' in blk:
+                gi = blk['geo_in']
+                ops.phase_split(x_hi, x_lo, n, gi.H, gi.W, blk['cin'], blk['xp_hi'], blk['xp_lo'])
+                self._conv_fwd(c1, blk['xp_hi'], blk['xp_lo'], 4)
+            else:
+                self._conv_fwd(c1, x_hi, x_lo, 1)
+            self._unit_bn(c1, train)
+            ops.bn_apply(c1.Y, c1.scale, c1.shift, geo.P, c1.cout, geo.Hp, geo.Wp, True, c1.act_hi,
+                         c1.act_lo)
+            self._conv_fwd(c2, c1.act_hi, c1.act_lo, 1)
+            self._unit_bn(c2, train)
+            if 'ds' in blk:
+                ds = blk['ds']
+                self._conv_fwd(ds, blk['xp_hi'], blk['xp_lo'], 4)
+                self._unit_bn(ds, train)
+                ops.bn_apply(c2.Y, c2.scale, c2.shift, geo.P, c2.cout, geo.Hp, geo.Wp, True, c2.act_hi,
+                             c2.act_lo, resY=ds.Y, res_scale=ds.scale, res_shift=ds.shift)
+            else:
+                ops.bn_apply(c2.Y, c2.scale, c2.shift, geo.P, c2.cout, geo.Hp, geo.Wp, True, c2.act_hi,
+                             c2.act_lo, res_hi=x_hi, res_lo=x_lo)
+            x_hi, x_lo = c2.act_hi, c2.act_lo
+        gl = self.geo_last
+        ops.avgpool(x_hi, x_lo, n, gl.Hp, gl.Wp, 512, self.pooled)
+        ops.linear_fwd(self.pooled, self.p('base_model.fc.weight'), self.p('base_model.fc.bias'), n,
+                       512, self.num_class, self.logits)
+
+    def _unit_bn_bwd(self, u: _ConvBN, g_a, g_b, act_hi, G_hi, G_lo, dz_out):
+        geo, wk = u.geo, u.name_bn
+        ops.bn_bwd_reduce(g_a, g_b, act_hi, u.Y, u.mean, u.invstd, geo.P, u.cout, geo.Hp, geo.Wp,
+                          u.sums2)
+        ops.bn_bwd_apply(g_a, g_b, act_hi, u.Y, u.mean, u.invstd, self.p(wk + '.weight'), u.sums2,
+                         geo.count, geo.P, u.cout, geo.Hp, geo.Wp, G_hi, G_lo, dz_out,
+                         self.g(wk + '.weight'), self.g(wk + '.bias'))
+
+    def _conv_wgrad(self, u: _ConvBN, G_hi, G_lo, x_hi, x_lo, x_phases: int):
+        geo = u.geo
+        if u.ks == 1:
+            shift, phase, bsel = [0], [0], [0]
+        elif u.stride == 1:
+            shift, phase, bsel = _taps_s1(geo.Wp)
+        else:
+            shift, phase, bsel = _taps_s2(geo.Wp)
+        nW = u.taps * u.cout * u.cin
+        dWs = self.dWs[:nW]
+        ops.memset_zero(dWs)
+        ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, dWs, P=geo.P, Cout=u.cout, x_phases=x_phases,
+                       Cin=u.cin, shift=shift, phase=phase, bsel=bsel, engine=self.gemm_engine)
+        ops.wgrad_unpack(dWs, self.g(u.name_conv + '.weight'), u.cout, u.cin, u.taps)
+
+    def _cls_backward(self, x_planar: torch.Tensor, n: int, need_wgrad: bool, need_input_grad: bool,
+                      d_input: Optional[torch.Tensor] = None):
+        """Backward of _cls_forward from self.d_logits.  need_wgrad=False skips every
+        weight gradient (GAN generator step: those grads are zeroed unused,
+        code/dmcnet_GAN/train.py:367-371)."""
+        C = self.num_class
+        gl = self.geo_last
+        ops.linear_bwd(self.d_logits, self.pooled, self.p('base_model.fc.weight'), n, 512, C,
+                       self.d_pooled, self.g('base_model.fc.weight') if need_wgrad else None,
+                       self.g('base_model.fc.bias') if need_wgrad else None)
+        T1, T2a, Ra, T2b, Rb = self.gbuf
+        g_a = T2a[:gl.P * 512]
+        ops.avgpool_bwd(self.d_pooled, n, gl.Hp, gl.Wp, 512, g_a)
+        g_b = None
+        flip = False       # which (T2, R) pair the CURRENT block writes
+        for bi in reversed(range(len(self.blocks))):
+            blk = self.blocks[bi]
+            c1, c2, geo, width, cin = blk['c1'], blk['c2'], blk['geo'], blk['width'], blk['cin']
+            T2, R = (T2b, Rb) if not flip else (T2a, Ra)
+            flip = not flip
+            x_hi, x_lo = (self.blocks[bi - 1]['c2'].act_hi, self.blocks[bi - 1]['c2'].act_lo) \
+                if bi > 0 else (self.A0_hi, self.A0_lo)
+            pc = geo.P * width
+            G_hi, G_lo = self.G_hi[:pc], self.G_lo[:pc]
+            has_ds = 'ds' in blk
+            # bn2 backward; the masked gradient dz also feeds the identity / downsample branch
+            self._unit_bn_bwd(c2, g_a, g_b, c2.act_hi, G_hi, G_lo, None if has_ds else R[:pc])
+            if getattr(self, 'debug_capture', False) and bi == len(self.blocks) - 1:
+                self.debug = {'g_a': g_a.clone(), 'sums2': c2.sums2.clone(), 'G': G_hi.float() + G_lo.float(),
+                              'dz': R[:pc].clone(), 'act': c2.act_hi.float() + c2.act_lo.float(),
+                              'Y': c2.Y.clone(), 'mean': c2.mean.clone(), 'invstd': c2.invstd.clone(),
+                              'd_pooled': self.d_pooled.clone()}
+            if need_wgrad:
+                self._conv_wgrad(c2, G_hi, G_lo, c1.act_hi, c1.act_lo, 1)
+            shift, phase, bsel = _taps_s1(geo.Wp)
+            ops.tap_gemm(G_hi, G_lo, c2.Wt_hi, c2.Wt_lo, T1[:pc], a_phases=1, a_rows=geo.P, K=width,
+                         b_slices=9, N=width, M=geo.P, ldD=width, Hp=geo.Hp, Wp=geo.Wp,
+                         shift=[-s for s in shift], phase=phase, bsel=bsel, engine=self.gemm_engine)
+            if has_ds:
+                ds = blk['ds']
+                Gp_hi, Gp_lo = self.G_hi[:2 * pc].view(2, pc), self.G_lo[:2 * pc].view(2, pc)
+                # downsample BN backward (same dz) -> slot 1 ; bn1 backward -> slot 0
+                self._unit_bn_bwd(ds, g_a, g_b, c2.act_hi, Gp_hi[1], Gp_lo[1], None)
+                self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, Gp_hi[0], Gp_lo[0], None)
+                if need_wgrad:
+                    self._conv_wgrad(c1, Gp_hi[0], Gp_lo[0], blk['xp_hi'], blk['xp_lo'], 4)
+                    self._conv_wgrad(ds, Gp_hi[1], Gp_lo[1], blk['xp_hi'], blk['xp_lo'], 4)
+                # dgrad into the four input phases; the 1x1 downsample joins phase (0,0)
+                fs, fp, fb = _taps_s2(geo.Wp)
+                for ph in range(4):
+                    sh = [-fs[t] for t in range(9) if fp[t] == ph]
+                    bs = [fb[t] for t in range(9) if fp[t] == ph]
+                    aph = [0] * len(sh)
+                    if ph == 0:
+                        sh, bs, aph = sh + [0], bs + [9], aph + [1]
+                    ops.tap_gemm(Gp_hi, Gp_lo, c1.Wt_hi, c1.Wt_lo, blk['dxp'][ph], a_phases=2,
+                                 a_rows=geo.P, K=width, b_slices=10, N=cin, M=geo.P, ldD=cin,
+                                 Hp=geo.Hp, Wp=geo.Wp, shift=sh, phase=aph, bsel=bs,
+                                 engine=self.gemm_engine)
+                gi = blk['geo_in']
+                g_a = T2[:gi.P * cin]
+                ops.phase_unsplit(blk['dxp'], n, gi.H, gi.W, cin, g_a)
+                g_b = None
+            else:
+                self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, G_hi, G_lo, None)
+                if need_wgrad:
+                    self._conv_wgrad(c1, G_hi, G_lo, x_hi, x_lo, 1)
+                g_a = T2[:pc]
+                ops.tap_gemm(G_hi, G_lo, c1.Wt_hi, c1.Wt_lo, g_a, a_phases=1, a_rows=geo.P, K=width,
+                             b_slices=9, N=cin, M=geo.P, ldD=cin, Hp=geo.Hp, Wp=geo.Wp,
+                             shift=[-s for s in shift], phase=phase, bsel=bsel,
+                             engine=self.gemm_engine)
+                g_b = R[:pc]
+        # stem backward
+        H, W = self.H, self.W
+        H2, W2 = H // 2, W // 2
+        st = self.stem
+        ops.stem_pool_bwd(g_a, g_b, self.pool_idx, self.stem_Y, st['scale'], st['shift'], n, 64, H2, W2,
+                          self.stem_dZ)
+        ns = 64 * H2 * W2
+        ops.bn_bwd_reduce_planar(self.stem_dZ, ns, self.stem_Y, ns, st['mean'], st['invstd'], 64,
+                                 H2 * W2, n, st['sums2'])
+        ops.bn_bwd_apply_planar(self.stem_dZ, ns, self.stem_Y, ns, st['mean'], st['invstd'],
+                                self.p('base_model.bn1.weight'), st['sums2'], float(n * H2 * W2), 64,
+                                H2 * W2, n, self.stem_dZ, ns, self.g('base_model.bn1.weight'),
+                                self.g('base_model.bn1.bias'))
+        if need_wgrad:
+            ops.conv_wgrad(x_planar, 2 * H * W, 2, H, W, self.stem_dZ, ns, 64, 7, 2,
+                           self.g('base_model.conv1.weight'), None, n)
+        if need_input_grad:
+            ops.conv_dgrad(self.stem_dZ, ns, 64, self.p('base_model.conv1.weight'), 2, 2, 7, 2,
+                           d_input.view(-1), 2 * H * W, H, W, n, accumulate=True)
+
+    # ------------------------------------------------------------------ discriminator
+    def _disc_forward(self, x: torch.Tensor, m: int, train: bool, use_masks: bool):
+        """Discriminator*.forward on planar x [m,2,H,W] -> self.validity[:m]."""
+        inp, in_c, h, w = x, 2, self.H, self.W
+        for L in self.d_layers:
+            p = L['name']
+            ops.conv_fwd(inp.view(-1), in_c * h * w, in_c, h, w, self.p(p + '.0.weight'),
+                         self.p(p + '.0.bias'), L['cout'], 3, L['stride'], L['A'].view(-1),
+                         L['cout'] * L['Ho'] * L['Wo'], m, slope=0.2,
+                         mask=(L['mask'] if (train and use_masks) else None))
+            hw = L['Ho'] * L['Wo']
+            if L['bn']:
+                ns = L['cout'] * hw
+                if train:
+                    ops.bn_stats_planar(L['A'], ns, L['cout'], hw, m, L['sums'])
+                    ops.bn_finalize(L['sums'], float(m * hw), self.p(p + '.3.weight'),
+                                    self.p(p + '.3.bias'), self.buffers[p + '.3.running_mean'],
+                                    self.buffers[p + '.3.running_var'],
+                                    self.buffers[p + '.3.num_batches_tracked'], BN_MOMENTUM, 0.8,
+                                    L['cout'], L['scale'], L['shift'], L['mean'], L['invstd'])
+                else:
+                    ops.bn_eval_coeffs(self.p(p + '.3.weight'), self.p(p + '.3.bias'),
+                                       self.buffers[p + '.3.running_mean'],
+                                       self.buffers[p + '.3.running_var'], 0.8, L['cout'], L['scale'],
+                                       L['shift'])
+                ops.bn_apply_planar(L['A'], ns, L['scale'], L['shift'], L['cout'], hw, m, False,
+                                    L['Z'], ns)
+            inp, in_c, h, w = L['Z'], L['cout'], L['Ho'], L['Wo']
+        K = self.specs['discriminator.adv_layer.weight'][1]
+        ops.linear_fwd(inp, self.p('discriminator.adv_layer.weight'),
+                       self.p('discriminator.adv_layer.bias'), m, K, 2, self.validity)
+
+    def _disc_backward(self, x: torch.Tensor, m: int, need_wgrad: bool, use_masks: bool,
+                       d_input: Optional[torch.Tensor], d_input_rows: int):
+        """Backward from self.d_validity[:m]; optionally accumulates d(loss)/d(x[:rows]) into d_input."""
+        K = self.specs['discriminator.adv_layer.weight'][1]
+        last = self.d_layers[-1]
+        ops.linear_bwd(self.d_validity, last['Z'], self.p('discriminator.adv_layer.weight'), m, K, 2,
+                       self.d_feat, self.g('discriminator.adv_layer.weight') if need_wgrad else None,
+                       self.g('discriminator.adv_layer.bias') if need_wgrad else None)
+        g = self.d_feat.view(-1)
+        for li in reversed(range(len(self.d_layers))):
+            L = self.d_layers[li]
+            p, co = L['name'], L['cout']
+            hw = L['Ho'] * L['Wo']
+            ns = co * hw
+            buf = self.d_g[li % 2]
+            if L['bn']:
+                ops.bn_bwd_reduce_planar(g, ns, L['A'], ns, L['mean'], L['invstd'], co, hw, m, L['sums2'])
+                ops.bn_bwd_apply_planar(g, ns, L['A'], ns, L['mean'], L['invstd'], self.p(p + '.3.weight'),
+                                        L['sums2'], float(m * hw), co, hw, m, buf, ns,
+                                        self.g(p + '.3.weight'), self.g(p + '.3.bias'))
+                g = buf
+            # LeakyReLU(0.2) + Dropout2d backward -> gradient of the conv pre-activation
+            ops.act_bwd_planar(g, ns, L['A'], ns, L['mask'] if use_masks else None, 0.2, co, hw, m,
+                               buf, ns)
+            g = buf
+            if li > 0:
+                prev = self.d_layers[li - 1]
+                inp, ci, h, w = prev['Z'], prev['cout'], prev['Ho'], prev['Wo']
+            else:
+                inp, ci, h, w = x, 2, self.H, self.W
+            if need_wgrad:
+                ops.conv_wgrad(inp.view(-1), ci * h * w, ci, h, w, g, ns, co, 3, L['stride'],
+                               self.g(p + '.0.weight'), self.g(p + '.0.bias'), m)
+            if li > 0:
+                nxt = self.d_g[(li - 1) % 2]
+                ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'], nxt,
+                               ci * h * w, h, w, m, accumulate=False)
+                g = nxt
+            elif d_input is not None:
+                ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'],
+                               d_input.view(-1), ci * h * w, h, w, d_input_rows, accumulate=True)
+
+    # ------------------------------------------------------------------ public passes
+    def forward(self, input_mv: torch.Tensor, input_residual: torch.Tensor,
+                input_flow: Optional[torch.Tensor] = None, *, train: bool = True,
+                masks: Optional[Sequence[torch.Tensor]] = None, use_dropout: bool = True):
+        """Model.forward.  Returns views of engine-owned outputs:
+        (logits [n,C], gen_flow [n,2,H,W]) or, for GAN, (logits, validity [m,2], gen_flow)."""
+        H, W = self.H, self.W
+        mv = input_mv.reshape(-1, 2, H, W)
+        res = input_residual.reshape(-1, 3, H, W)
+        n = mv.shape[0]
+        self._gen_forward(mv, res, n)
+        self._cls_forward(self.gen_flow, n, train)
+        if not self.gan:
+            return self.logits[:n], self.gen_flow[:n]
+        HW2 = 2 * H * W
+        ops.copy_planar(self.gen_flow, HW2, self.d_in.view(-1), HW2, HW2, n)     # "first fake then real"
+        m = n
+        if input_flow is not None:
+            flow = input_flow.reshape(-1, 2, H, W)
+            ops.copy_planar(flow, HW2, self.d_in.view(-1)[n * HW2:], HW2, HW2, n)
+            m = 2 * n
+        self._use_masks = bool(train and use_dropout)
+        if self._use_masks and not (isinstance(masks, str) and masks == 'preloaded'):
+            self.set_masks(masks if masks is not None else self.draw_dropout_masks(m), m)
+        self._disc_forward(self.d_in, m, train, self._use_masks)
+        self._m = m
+        return self.logits[:n], self.validity[:m], self.gen_flow[:n]
+
+    def set_masks(self, masks: Sequence[torch.Tensor], m: int):
+        """Stage Dropout2d masks ([m, C] per block) into the static device buffers."""
+        for L, mk in zip(self.d_layers, masks):
+            L['mask'][:m].copy_(mk.reshape(m, -1).to(torch.float32), non_blocking=True)
+
+    def draw_dropout_masks(self, m: int, generator: Optional[torch.Generator] = None):
+        """Dropout2d(0.25) feature masks drawn with the same ATen calls, shapes and
+        order as F.dropout2d inside the reference blocks (GAN/model.py:254-279)."""
+        out = []
+        for L in self.d_layers:
+            noise = torch.empty(m, L['cout'], 1, 1).bernoulli_(0.75, generator=generator).div_(0.75)
+            out.append(noise.view(m, L['cout']))
+        return out
+
+    def zero_grads(self):
+        ops.memset_zero(self.grads)
+
+    def backward(self, n: int, *, cls: bool = True, cls_wgrad: bool = True, gen_grad: bool = True,
+                 cls_to_gen: bool = False, disc: bool = False, disc_wgrad: bool = False,
+                 disc_to_gen: bool = False):
+        """Backward pass.  Inputs: self.d_logits (classifier), self.d_gen_flow (direct
+        gradient on the generated map, e.g. MSE; must be initialised -- zeros if none)
+        and self.d_validity (discriminator).  Flags select which parameter gradients are
+        produced (dead-work elimination)."""
+        if cls:
+            self._cls_backward(self.gen_flow, n, cls_wgrad, cls_to_gen, self.d_gen_flow)
+        if disc:
+            self._disc_backward(self.d_in, self._m, disc_wgrad, self._use_masks,
+                                self.d_gen_flow if disc_to_gen else None, n)
+        if gen_grad:
+            self._gen_backward(n)

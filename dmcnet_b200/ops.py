@@ -37,10 +37,32 @@ def _iarr(v: Sequence[int]):
     return (c_int * len(v))(*[int(x) for x in v])
 
 
+_hook = None          # profiling hook: callable(name, args) -> context manager, or None
+
+
+def set_call_hook(hook) -> None:
+    global _hook
+    _hook = hook
+
+
 def _call(name: str, *args) -> None:
     fn = getattr(_native.lib(), name)
     fn.restype = c_int
-    _native.check(fn(*args), name)
+    if _hook is None:
+        _native.check(fn(*args), name)
+    else:
+        with _hook(name, args):
+            _native.check(fn(*args), name)
+
+
+def launch_count() -> int:
+    fn = _native.lib().dmc_launch_count
+    fn.restype = ctypes.c_longlong
+    return int(fn())
+
+
+def reset_launch_count() -> None:
+    _native.lib().dmc_reset_launch_count()
 
 
 F32, BF16, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int64, torch.uint8, torch.float64
@@ -62,3 +84,176 @@ def wgrad_gemm(G_hi, G_lo, X_hi, X_lo, dW, *, P, Cout, x_phases, Cin, shift, pha
     _call(name, _ptr(G_hi, BF16), _ptr(G_lo, BF16), c_long(P), c_int(Cout), _ptr(X_hi, BF16),
           _ptr(X_lo, BF16), c_int(x_phases), c_int(Cin), _ptr(dW, F32), c_int(len(shift)),
           _iarr(shift), _iarr(phase), _iarr(bsel), _stream())
+
+
+# ---------------------------------------------------------------- pixel-major classifier helpers
+def memset_zero(t):
+    _call('dmc_memset_zero', _ptr(t), c_long(t.numel() * t.element_size()), _stream())
+
+
+def weight_prep(w, Cout, Cin, taps, W_hi, W_lo, Wt_hi=None, Wt_lo=None):
+    _call('dmc_weight_prep', _ptr(w, F32), c_int(Cout), c_int(Cin), c_int(taps), _ptr(W_hi, BF16),
+          _ptr(W_lo, BF16), _ptr(Wt_hi, BF16), _ptr(Wt_lo, BF16), _stream())
+
+
+def wgrad_unpack(dWs, grad, Cout, Cin, taps):
+    _call('dmc_wgrad_unpack', _ptr(dWs, F32), _ptr(grad, F32), c_int(Cout), c_int(Cin), c_int(taps),
+          _stream())
+
+
+def bn_stats(Y, P, C, sums):
+    _call('dmc_bn_stats', _ptr(Y, F32), c_long(P), c_int(C), _ptr(sums, F64), _stream())
+
+
+def bn_finalize(sums, count, gamma, beta, rmean, rvar, nbt, momentum, eps, C, scale, shift, mean,
+                invstd):
+    _call('dmc_bn_finalize', _ptr(sums, F64), c_double(count), _ptr(gamma, F32), _ptr(beta, F32),
+          _ptr(rmean, F32), _ptr(rvar, F32), _ptr(nbt, I64), c_float(momentum), c_float(eps),
+          c_int(C), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32), _ptr(invstd, F32), _stream())
+
+
+def bn_eval_coeffs(gamma, beta, rmean, rvar, eps, C, scale, shift):
+    _call('dmc_bn_eval_coeffs', _ptr(gamma, F32), _ptr(beta, F32), _ptr(rmean, F32), _ptr(rvar, F32),
+          c_float(eps), c_int(C), _ptr(scale, F32), _ptr(shift, F32), _stream())
+
+
+def bn_apply(Y, scale, shift, P, C, Hp, Wp, relu, out_hi, out_lo, res_hi=None, res_lo=None,
+             resY=None, res_scale=None, res_shift=None):
+    _call('dmc_bn_apply', _ptr(Y, F32), _ptr(scale, F32), _ptr(shift, F32), c_long(P), c_int(C),
+          c_int(Hp), c_int(Wp), c_int(1 if relu else 0), _ptr(res_hi, BF16), _ptr(res_lo, BF16),
+          _ptr(resY, F32), _ptr(res_scale, F32), _ptr(res_shift, F32), _ptr(out_hi, BF16),
+          _ptr(out_lo, BF16), _stream())
+
+
+def bn_bwd_reduce(g_a, g_b, act_hi, Y, mean, invstd, P, C, Hp, Wp, sums2):
+    _call('dmc_bn_bwd_reduce', _ptr(g_a, F32), _ptr(g_b, F32), _ptr(act_hi, BF16), _ptr(Y, F32),
+          _ptr(mean, F32), _ptr(invstd, F32), c_long(P), c_int(C), c_int(Hp), c_int(Wp),
+          _ptr(sums2, F64), _stream())
+
+
+def bn_bwd_apply(g_a, g_b, act_hi, Y, mean, invstd, gamma, sums2, count, P, C, Hp, Wp, G_hi, G_lo,
+                 dz_out, dgamma, dbeta):
+    _call('dmc_bn_bwd_apply', _ptr(g_a, F32), _ptr(g_b, F32), _ptr(act_hi, BF16), _ptr(Y, F32),
+          _ptr(mean, F32), _ptr(invstd, F32), _ptr(gamma, F32), _ptr(sums2, F64), c_double(count),
+          c_long(P), c_int(C), c_int(Hp), c_int(Wp), _ptr(G_hi, BF16), _ptr(G_lo, BF16),
+          _ptr(dz_out, F32), _ptr(dgamma, F32), _ptr(dbeta, F32), _stream())
+
+
+def phase_split(in_hi, in_lo, frames, H, W, C, out_hi, out_lo):
+    _call('dmc_phase_split', _ptr(in_hi, BF16), _ptr(in_lo, BF16), c_int(frames), c_int(H), c_int(W),
+          c_int(C), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _stream())
+
+
+def phase_unsplit(inp, frames, H, W, C, out):
+    _call('dmc_phase_unsplit', _ptr(inp, F32), c_int(frames), c_int(H), c_int(W), c_int(C),
+          _ptr(out, F32), _stream())
+
+
+def avgpool(hi, lo, frames, Hp, Wp, C, pooled):
+    _call('dmc_avgpool', _ptr(hi, BF16), _ptr(lo, BF16), c_int(frames), c_int(Hp), c_int(Wp),
+          c_int(C), _ptr(pooled, F32), _stream())
+
+
+def avgpool_bwd(dpooled, frames, Hp, Wp, C, dX):
+    _call('dmc_avgpool_bwd', _ptr(dpooled, F32), c_int(frames), c_int(Hp), c_int(Wp), c_int(C),
+          _ptr(dX, F32), _stream())
+
+
+def split_planes(X, P, C, Hp, Wp, hi, lo):
+    _call('dmc_split_planes', _ptr(X, F32), c_long(P), c_int(C), c_int(Hp), c_int(Wp), _ptr(hi, BF16),
+          _ptr(lo, BF16), _stream())
+
+
+# ---------------------------------------------------------------- planar (NCHW) small-channel layers
+def conv_fwd(inp, in_ns, Cin, H, W, w, bias, Cout, ks, stride, out, out_ns, N, slope=1.0, mask=None,
+             add=None, add_ns=0, accumulate=False):
+    _call('dmc_conv_fwd', _ptr(inp, F32), c_long(in_ns), c_int(Cin), c_int(H), c_int(W), _ptr(w, F32),
+          _ptr(bias, F32), c_int(Cout), c_int(ks), c_int(stride), _ptr(out, F32), c_long(out_ns),
+          c_float(slope), _ptr(mask, F32), _ptr(add, F32), c_long(add_ns),
+          c_int(1 if accumulate else 0), c_int(N), _stream())
+
+
+def conv_dgrad(dY, dy_ns, Cout, w, Cin, ci_count, ks, stride, dX, dx_ns, H, W, N, accumulate=False):
+    _call('dmc_conv_dgrad', _ptr(dY, F32), c_long(dy_ns), c_int(Cout), _ptr(w, F32), c_int(Cin),
+          c_int(ci_count), c_int(ks), c_int(stride), _ptr(dX, F32), c_long(dx_ns), c_int(H), c_int(W),
+          c_int(1 if accumulate else 0), c_int(N), _stream())
+
+
+def conv_wgrad(inp, in_ns, Cin, H, W, dY, dy_ns, Cout, ks, stride, dW, dbias, N):
+    _call('dmc_conv_wgrad', _ptr(inp, F32), c_long(in_ns), c_int(Cin), c_int(H), c_int(W),
+          _ptr(dY, F32), c_long(dy_ns), c_int(Cout), c_int(ks), c_int(stride), _ptr(dW, F32),
+          _ptr(dbias, F32), c_int(N), _stream())
+
+
+def act_bwd_planar(dA, da_ns, A, a_ns, mask, slope, C, HW, N, dPre, dp_ns):
+    _call('dmc_act_bwd_planar', _ptr(dA, F32), c_long(da_ns), _ptr(A, F32), c_long(a_ns),
+          _ptr(mask, F32), c_float(slope), c_int(C), c_long(HW), c_int(N), _ptr(dPre, F32),
+          c_long(dp_ns), _stream())
+
+
+def bn_stats_planar(X, x_ns, C, HW, N, sums):
+    _call('dmc_bn_stats_planar', _ptr(X, F32), c_long(x_ns), c_int(C), c_long(HW), c_int(N),
+          _ptr(sums, F64), _stream())
+
+
+def bn_apply_planar(X, x_ns, scale, shift, C, HW, N, relu, out, o_ns):
+    _call('dmc_bn_apply_planar', _ptr(X, F32), c_long(x_ns), _ptr(scale, F32), _ptr(shift, F32),
+          c_int(C), c_long(HW), c_int(N), c_int(1 if relu else 0), _ptr(out, F32), c_long(o_ns),
+          _stream())
+
+
+def bn_bwd_reduce_planar(dZ, dz_ns, X, x_ns, mean, invstd, C, HW, N, sums2):
+    _call('dmc_bn_bwd_reduce_planar', _ptr(dZ, F32), c_long(dz_ns), _ptr(X, F32), c_long(x_ns),
+          _ptr(mean, F32), _ptr(invstd, F32), c_int(C), c_long(HW), c_int(N), _ptr(sums2, F64),
+          _stream())
+
+
+def bn_bwd_apply_planar(dZ, dz_ns, X, x_ns, mean, invstd, gamma, sums2, count, C, HW, N, dX, dx_ns,
+                        dgamma, dbeta):
+    _call('dmc_bn_bwd_apply_planar', _ptr(dZ, F32), c_long(dz_ns), _ptr(X, F32), c_long(x_ns),
+          _ptr(mean, F32), _ptr(invstd, F32), _ptr(gamma, F32), _ptr(sums2, F64), c_double(count),
+          c_int(C), c_long(HW), c_int(N), _ptr(dX, F32), c_long(dx_ns), _ptr(dgamma, F32),
+          _ptr(dbeta, F32), _stream())
+
+
+def copy_planar(src, s_ns, dst, d_ns, count, N):
+    _call('dmc_copy_planar', _ptr(src, F32), c_long(s_ns), _ptr(dst, F32), c_long(d_ns),
+          c_long(count), c_int(N), _stream())
+
+
+# ---------------------------------------------------------------- stem, heads, optimizer
+def stem_pool_fwd(Y, scale, shift, N, C, H, W, out_hi, out_lo, idx):
+    _call('dmc_stem_pool_fwd', _ptr(Y, F32), _ptr(scale, F32), _ptr(shift, F32), c_int(N), c_int(C),
+          c_int(H), c_int(W), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8), _stream())
+
+
+def stem_pool_bwd(g_a, g_b, idx, Y, scale, shift, N, C, H, W, dZ):
+    _call('dmc_stem_pool_bwd', _ptr(g_a, F32), _ptr(g_b, F32), _ptr(idx, U8), _ptr(Y, F32),
+          _ptr(scale, F32), _ptr(shift, F32), c_int(N), c_int(C), c_int(H), c_int(W), _ptr(dZ, F32),
+          _stream())
+
+
+def linear_fwd(x, w, b, M, K, N, out):
+    _call('dmc_linear_fwd', _ptr(x, F32), _ptr(w, F32), _ptr(b, F32), c_int(M), c_int(K), c_int(N),
+          _ptr(out, F32), _stream())
+
+
+def linear_bwd(dy, x, w, M, K, N, dx, dw, db):
+    _call('dmc_linear_bwd', _ptr(dy, F32), _ptr(x, F32), _ptr(w, F32), c_int(M), c_int(K), c_int(N),
+          _ptr(dx, F32), _ptr(dw, F32), _ptr(db, F32), _stream())
+
+
+def ce_head(logits, B, S, C, target, gscale, consensus, dlogits, out_stats):
+    _call('dmc_ce_head', _ptr(logits, F32), c_int(B), c_int(S), c_int(C), _ptr(target, I64),
+          c_float(gscale), _ptr(consensus, F32), _ptr(dlogits, F32), _ptr(out_stats, F32), _stream())
+
+
+def mse_head(gen, flow, numel, gscale, dgen, loss_sum):
+    _call('dmc_mse_head', _ptr(gen, F32), _ptr(flow, F32), c_long(numel), c_float(gscale),
+          _ptr(dgen, F32), _ptr(loss_sum, F64), _stream())
+
+
+def adam_step(p, g, m, v, chunks, nchunks, hyper, step, beta1, beta2, eps, grad_scale=1.0):
+    _call('dmc_adam_step', _ptr(p, F32), _ptr(g, F32), _ptr(m, F32), _ptr(v, F32),
+          _ptr(chunks, torch.int32), c_int(nchunks), _ptr(hyper, F32), _ptr(step, torch.int32),
+          c_float(beta1), c_float(beta2), c_float(eps), c_float(grad_scale), _stream())

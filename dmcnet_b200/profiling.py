@@ -1,0 +1,120 @@
+"""Live per-kernel-family timing of a train step (CUDA events on the launch
+stream) and the roofline figures bench.py reports.
+
+Algorithmic work: a tap GEMM launch does
+2 * valid_pixels * N * K * ntaps FLOP where valid_pixels excludes the padding
+ring; the tensor-pipe peak is the measured cuBLAS bf16 figure in
+MEASURED_PEAKS.json (the bf16x3 split issues 3 MMAs per algorithmic MAC, so the
+ceiling of `frac` for these kernels is 1/3).
+"""
+from __future__ import annotations
+
+import contextlib
+import json
+import os
+from collections import defaultdict
+
+import torch
+
+from . import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'tensor_tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json: copy GB/s, cuBLAS bf16 sustained)'}
+    return {'hbm_gbs': 6650.0, 'tensor_tflops': 1590.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class FamilyTimer:
+    def __init__(self):
+        self.events = []            # (name, e0, e1, flops, bytes)
+
+    @contextlib.contextmanager
+    def __call__(self, name, args):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.events.append((name, e0, e1, _flops(name, args)))
+
+    def totals(self):
+        torch.cuda.synchronize()
+        ms, fl, cnt = defaultdict(float), defaultdict(float), defaultdict(int)
+        for name, e0, e1, f in self.events:
+            ms[name] += e0.elapsed_time(e1)
+            fl[name] += f
+            cnt[name] += 1
+        return ms, fl, cnt
+
+
+def _v(a):
+    return a.value if hasattr(a, 'value') else a
+
+
+def _flops(name, args):
+    """Algorithmic FLOPs of one call (0 for bandwidth kernels)."""
+    if name in ('dmc_tc_tap_gemm', 'dmc_simt_tap_gemm'):
+        K, N, M, Hp, Wp, ntaps = _v(args[4]), _v(args[8]), _v(args[10]), _v(args[12]), _v(args[13]), _v(args[14])
+        valid = M * ((Hp - 2) * (Wp - 2)) / float(Hp * Wp) if Hp else M
+        return 2.0 * valid * N * K * ntaps
+    if name in ('dmc_tc_wgrad', 'dmc_simt_wgrad'):
+        P, Cout, Cin, ntaps = _v(args[2]), _v(args[3]), _v(args[7]), _v(args[9])
+        return 2.0 * P * Cout * Cin * ntaps            # upper bound: ring rows are zero work
+    if name in ('dmc_conv_fwd',):
+        Cin, H, W, Cout, ks, stride, N = (_v(args[i]) for i in (2, 3, 4, 7, 8, 9, 17))
+        return 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * ks * ks
+    if name in ('dmc_conv_wgrad',):
+        Cin, H, W, Cout, ks, stride, N = (_v(args[i]) for i in (2, 3, 4, 7, 8, 9, 12))
+        return 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * ks * ks
+    if name in ('dmc_conv_dgrad',):
+        Cout, cic, ks, stride, H, W, N = (_v(args[i]) for i in (2, 5, 6, 7, 10, 11, 13))
+        return 2.0 * N * (H // stride) * (W // stride) * cic * Cout * ks * ks
+    return 0.0
+
+
+def measure_roofline(resident_step, per, steps, trainer):
+    """Run `steps` instrumented eager steps; return the dominant family's roofline
+    and the per-family time breakdown (ms per train step)."""
+    peaks = measured_peaks()
+    was_graph = trainer.use_graph
+    trainer.use_graph = False
+    timer = FamilyTimer()
+    resident_step()                                   # eager warm-up outside the hook
+    if per == 2:
+        resident_step()
+    ops.set_call_hook(timer)
+    try:
+        for _ in range(steps * per):
+            resident_step()
+    finally:
+        ops.set_call_hook(None)
+        trainer.use_graph = was_graph
+    ms, fl, cnt = timer.totals()
+    denom = float(steps * per)
+    breakdown = {k.replace('dmc_', ''): round(v / denom, 4) for k, v in sorted(ms.items(), key=lambda kv: -kv[1])}
+    top = max(ms, key=lambda k: ms[k])
+    gemm = 'dmc_tc_tap_gemm'
+    fam = gemm if gemm in ms else top
+    out = {'breakdown': breakdown, 'top_family': top.replace('dmc_', '')}
+    t_ms = ms[fam]
+    achieved = fl[fam] / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    out['roofline'] = {
+        'kernel': fam.replace('dmc_', '') + '_kernel', 'bound': 'tensor', 'achieved': achieved,
+        'peak': peaks['tensor_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'],
+        'traffic': None, 'launches_per_step': cnt[fam] / denom, 'avg_launch_ms': t_ms / max(cnt[fam], 1),
+        'share_of_step': t_ms / max(sum(ms.values()), 1e-9),
+        'peak_source': peaks['source'],
+        'note': 'algorithmic FLOPs (padding ring excluded); bf16x3 split issues 3 MMAs per MAC -> ceiling 1/3',
+    }
+    others = {}
+    for k in ms:
+        if fl[k] > 0 and k != fam:
+            others[k.replace('dmc_', '')] = {'tflops': fl[k] / (ms[k] * 1e-3) / 1e12, 'ms_per_step': ms[k] / denom}
+    out['roofline']['other_families'] = others
+    return out

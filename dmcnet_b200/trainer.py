@@ -1,0 +1,269 @@
+"""Fused DMC-Net train step (the product's fast path).
+
+``FusedTrainStep.step(input_flow, input_mv, input_residual, target)`` performs
+what one iteration of the reference loops does --
+code/dmcnet/train.py:221-266 (``gan=False``) and
+code/dmcnet_GAN/train.py:237-372 (``gan=True``: D-step on even iterations,
+G-step on odd ones) -- entirely with the library's kernels: forward, segment
+consensus + CE / MSE / adversarial-CE heads, backward, one gradient all-reduce
+(multi-GPU) and the per-tensor Adam of train.py:121-142 / :398-408.
+
+Data parallelism: one process per GPU, each with its own
+shard of clips; loss gradients are pre-scaled by the GLOBAL batch so that a
+plain sum all-reduce over the flat gradient bucket reproduces the reference's
+gradient; BatchNorm statistics stay per rank (= nn.DataParallel semantics).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .engine import DmcEngine
+
+
+@dataclass
+class HParams:
+    """Defaults = exp_my/hmdb51_gen_flow/split1/run.sh:12-35 and exp_my/hmdb51_gan/split1/run.sh:12-39."""
+    lr: float = 0.01
+    lr_cls: float = 1.0          # loss weights (code/dmcnet/train_options.py:69-73)
+    lr_mse: float = 10.0
+    lr_adv_g: float = 1.0
+    lr_adv_d: float = 0.01
+    lr_cls_mult: float = 0.01    # per-group lr multipliers (:74-75)
+    lr_mse_mult: float = 1.0
+    lr_d_mult: float = 1.0
+    weight_decay: float = 1e-4
+    lr_steps: Tuple[int, ...] = (20, 35, 45)
+    lr_decay: float = 0.1
+    num_segments: int = 3
+    eps: float = 1e-3            # Adam eps, code/dmcnet/train.py:137,142
+    betas: Tuple[float, float] = (0.9, 0.999)
+
+
+GROUPS = ('base_model', 'gen_flow_model', 'discriminator')
+
+
+class FusedTrainStep:
+    def __init__(self, engine: DmcEngine, hp: HParams, batch: int, *, world_size: int = 1,
+                 process_group=None, use_graph: bool = False):
+        self.eng, self.hp, self.B = engine, hp, batch
+        self.S = hp.num_segments
+        if batch * self.S != engine.N:
+            raise ValueError('engine was built for %d frames, need batch*segments = %d'
+                             % (engine.N, batch * self.S))
+        self.world = world_size
+        self.pg = process_group
+        self.use_graph = use_graph
+        dev = engine.device
+        H, W, n = engine.H, engine.W, engine.N
+        f32 = dict(dtype=torch.float32, device=dev)
+        # static inputs (graph-replayable)
+        self.in_flow = torch.zeros(n, 2, H, W, **f32)
+        self.in_mv = torch.zeros(n, 2, H, W, **f32)
+        self.in_res = torch.zeros(n, 3, H, W, **f32)
+        self.target = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.consensus = torch.zeros(batch, engine.num_class, **f32)
+        self.ce_stats = torch.zeros(4, **f32)
+        self.adv_stats = torch.zeros(4, **f32)
+        self.mse_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        if engine.gan:
+            self.adv_t_d = torch.cat((torch.zeros(n, dtype=torch.int64), torch.ones(n, dtype=torch.int64))).to(dev)
+            self.adv_t_g = torch.ones(n, dtype=torch.int64, device=dev)
+        self.iteration = 0
+        self._build_adam_tables()
+        self.set_epoch(0, epoch_thre=0)
+        self._graphs: Dict[str, object] = {}
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ optimizer tables
+    def _build_adam_tables(self):
+        eng, dev = self.eng, self.eng.device
+        self.tensor_keys: List[str] = list(eng.specs.keys())
+        self.tensor_group: List[int] = []
+        chunks = {g: [] for g in GROUPS}
+        for ti, k in enumerate(self.tensor_keys):
+            tag = next(g for g in GROUPS if k.startswith(g))
+            self.tensor_group.append(GROUPS.index(tag))
+            off, n = eng.offsets[k], eng.numel(k)
+            for c0 in range(0, n, 1024):
+                chunks[tag].append((off + c0, min(1024, n - c0), ti, 0))
+        self.chunks = {}
+        for g in GROUPS:
+            t = torch.tensor(chunks[g], dtype=torch.int32).reshape(-1, 4).contiguous().to(dev)
+            self.chunks[g] = (t, len(chunks[g]))
+        self.hyper = torch.zeros(len(self.tensor_keys), 2, dtype=torch.float32, device=dev)
+        self.steps = torch.zeros(len(GROUPS), dtype=torch.int32, device=dev)
+
+    def set_epoch(self, epoch: int, epoch_thre: int = 0):
+        """adjust_learning_rate (code/dmcnet/train.py:398-408).  dmcnet freezes the
+        classifier while epoch < epoch_thre (train.py:177,183); the GAN script
+        ignores epoch_thre (GAN/train.py:190)."""
+        hp = self.hp
+        self.freeze = (not self.eng.gan) and epoch < epoch_thre
+        decay = hp.lr_decay ** sum(epoch >= s for s in hp.lr_steps)
+        mults = (hp.lr_cls_mult, hp.lr_mse_mult, hp.lr_d_mult)
+        rows = []
+        for k, gi in zip(self.tensor_keys, self.tensor_group):
+            lr, wd = hp.lr * decay, hp.weight_decay
+            if gi == 0 and self.freeze:
+                lr, wd = 0.0, 0.0
+            rows.append((lr * mults[gi], wd * (0.0 if 'bias' in k else 1.0)))
+        self.hyper.copy_(torch.tensor(rows, dtype=torch.float32))
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ step pieces
+    def _adam(self, groups: Sequence[str]):
+        eng, hp = self.eng, self.hp
+        for g in groups:
+            t, n = self.chunks[g]
+            gi = GROUPS.index(g)
+            ops.adam_step(eng.params, eng.grads, eng.exp_avg, eng.exp_avg_sq, t, n, self.hyper.view(-1),
+                          self.steps[gi:gi + 1], hp.betas[0], hp.betas[1], hp.eps, 1.0)
+
+    def _allreduce(self, groups: Sequence[str]):
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        lo = min(self.eng.group_range[g][0] for g in groups)
+        hi = max(self.eng.group_range[g][1] for g in groups)
+        dist.all_reduce(self.eng.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _mode(self) -> str:
+        if not self.eng.gan:
+            return 'freeze' if self.freeze else 'full'
+        return 'D' if self.iteration % 2 == 0 else 'G'
+
+    def _fwd_bwd(self, mode: str):
+        """forward + heads + backward for one mode (graph-capturable: static buffers only)."""
+        eng, hp, B, S = self.eng, self.hp, self.B, self.S
+        n = B * S
+        Bg = B * self.world
+        numel_g = float(n * 2 * eng.H * eng.W * self.world)
+        eng.zero_grads()
+        if not eng.gan:
+            eng.forward(self.in_mv, self.in_res, train=True)
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+                        eng.d_logits, self.ce_stats)
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, 2.0 * hp.lr_mse / numel_g,
+                         eng.d_gen_flow, self.mse_sum)
+            eng.backward(n, cls=(mode == 'full'), cls_wgrad=True, gen_grad=True, cls_to_gen=False)
+        elif mode == 'D':
+            eng.forward(self.in_mv, self.in_res, self.in_flow, train=True, masks='preloaded')
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+                        eng.d_logits, self.ce_stats)
+            ops.ce_head(eng.validity, 2 * n, 1, 2, self.adv_t_d, hp.lr_adv_d / (2 * n * self.world), None,
+                        eng.d_validity, self.adv_stats)
+            # generator gradients are dead work in the D-step (GAN/train.py:297-302)
+            eng.backward(n, cls=True, cls_wgrad=True, gen_grad=False, cls_to_gen=False, disc=True,
+                         disc_wgrad=True, disc_to_gen=False)
+        else:
+            eng.forward(self.in_mv, self.in_res, None, train=True, masks='preloaded')
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+                        eng.d_logits, self.ce_stats)
+            ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, hp.lr_adv_g / (n * self.world), None,
+                        eng.d_validity, self.adv_stats)
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, 2.0 * hp.lr_mse / numel_g,
+                         eng.d_gen_flow, self.mse_sum)
+            # classifier / discriminator weight gradients are dead work in the G-step (:367-371)
+            eng.backward(n, cls=True, cls_wgrad=False, gen_grad=True, cls_to_gen=True, disc=True,
+                         disc_wgrad=False, disc_to_gen=True)
+
+    def _step_groups(self, mode: str) -> List[str]:
+        return {'full': ['base_model', 'gen_flow_model'], 'freeze': ['gen_flow_model'],
+                'D': ['base_model', 'discriminator'], 'G': ['gen_flow_model']}[mode]
+
+    def _run(self, mode: str, apply: bool):
+        groups = self._step_groups(mode)
+        if not self.use_graph:
+            c0 = ops.launch_count()
+            self._fwd_bwd(mode)
+            if apply:
+                self._allreduce(groups)
+                self._adam(groups)
+            self.launches_per_step = ops.launch_count() - c0
+            return
+        key = mode
+        if key not in self._graphs:
+            # warm-up eagerly once (sets kernel attributes, fills caches), restoring BN / step state
+            # is not needed: the eager run IS this step; later calls replay the captured graphs.
+            c0 = ops.launch_count()
+            self._fwd_bwd(mode)
+            if apply:
+                self._allreduce(groups)
+                self._adam(groups)
+            self.launches_per_step = ops.launch_count() - c0
+            torch.cuda.synchronize()
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self._graphs[key] = ('pending', ga, gb)
+            return
+        entry = self._graphs[key]
+        if entry[0] == 'pending':
+            _, ga, gb = entry
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(ga, stream=s):
+                    self._fwd_bwd(mode)
+                if apply:
+                    self._allreduce(groups)
+                with torch.cuda.graph(gb, stream=s):
+                    self._adam(groups)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graphs[key] = ('ready', ga, gb)
+            # capture does not execute: run the step now
+            ga.replay()
+            if apply:
+                self._allreduce(groups)
+                gb.replay()
+            return
+        _, ga, gb = entry
+        ga.replay()
+        if apply:
+            self._allreduce(groups)
+            gb.replay()
+
+    # ------------------------------------------------------------------ public API
+    def load_inputs(self, input_flow, input_mv, input_residual, target):
+        """Stage one batch (host or device tensors, CoviarDataSet layout
+        [B,S,c,H,W], code/dmcnet/dataset.py:278) into the static device buffers."""
+        H, W = self.eng.H, self.eng.W
+        self.in_flow.copy_(input_flow.reshape(-1, 2, H, W), non_blocking=True)
+        self.in_mv.copy_(input_mv.reshape(-1, 2, H, W), non_blocking=True)
+        self.in_res.copy_(input_residual.reshape(-1, 3, H, W), non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+
+    def step(self, input_flow, input_mv, input_residual, target,
+             masks: Optional[Sequence[torch.Tensor]] = None, apply: bool = True,
+             metrics: bool = True) -> Dict[str, float]:
+        eng = self.eng
+        self.load_inputs(input_flow, input_mv, input_residual, target)
+        mode = self._mode()
+        if eng.gan:
+            m = 2 * eng.N if mode == 'D' else eng.N
+            eng.set_masks(masks if masks is not None else eng.draw_dropout_masks(m), m)
+        self._run(mode, apply)
+        self.iteration += 1
+        return self.read_metrics(mode) if metrics else {}
+
+    def read_metrics(self, mode: str) -> Dict[str, float]:
+        """One small device->host read (the reference does five .data[0] syncs, train.py:251-255)."""
+        eng, hp, B = self.eng, self.hp, self.B
+        n = B * self.S
+        ce = self.ce_stats.cpu()
+        out = {'loss_cls': float(ce[0]) / B, 'prec1': float(ce[1]) * 100.0 / B,
+               'prec5': float(ce[2]) * 100.0 / B}
+        loss = out['loss_cls'] * hp.lr_cls
+        if mode in ('full', 'freeze', 'G'):
+            out['loss_mse'] = float(self.mse_sum.cpu()[0]) / float(n * 2 * eng.H * eng.W)
+            loss += out['loss_mse'] * hp.lr_mse
+        if mode in ('D', 'G'):
+            adv = self.adv_stats.cpu()
+            m = 2 * n if mode == 'D' else n
+            out['loss_adv'] = float(adv[0]) / m
+            out['acc_adv'] = float(adv[1]) * 100.0 / m
+            loss += out['loss_adv'] * (hp.lr_adv_d if mode == 'D' else hp.lr_adv_g)
+        out['loss'] = loss
+        return out
