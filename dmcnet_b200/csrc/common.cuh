@@ -14,6 +14,11 @@
 
 void dmc_set_error(const char* fmt, ...);
 int dmc_check_launch(const char* what);
+// Tiled TMA descriptor over an fp32 tensor of `rank` dims (dims[0] contiguous), no swizzle,
+// out-of-bounds elements read as zero.  Implemented in gemm_tc.cu.
+int dmc_make_f32_map(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_elems /*[rank-1], dims 1..*/,
+                     const unsigned int* box);
 
 #define DMC_REQUIRE(cond, ...)                                  \
   do {                                                          \
@@ -101,6 +106,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

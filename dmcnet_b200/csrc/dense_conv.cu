@@ -253,6 +253,339 @@ conv_wgrad_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int 
   }
 }
 
+// ------------------------------------------------------------------ 3x3 stride-1, register-tiled
+// Thread = PX consecutive output pixels of one row x COG output channels
+// (PX*COG accumulators); the input strip comes in as one 128-bit shared load
+// plus two neighbours per (channel, kernel row), weights as broadcast vector
+// loads -> ~1 shared-memory wavefront per 8 FMAs, i.e. FMA-pipe bound.
+template <int COG, int PX>
+struct FwdV2Cfg {
+  static constexpr int CK = 8;
+  static constexpr int SPR = 32 / PX;          // strips per tile row
+  static constexpr int TH = 128 / SPR;         // tile rows (16 for PX=4, 32 for PX=8)
+  static constexpr int PITCH = 40;             // 4 + 32 + 4 columns
+  static constexpr int COGP = (COG + 3) / 4 * 4;
+  static constexpr int BUF = CK * (TH + 2) * PITCH;   // floats per stage
+  static int smem_bytes(int Cin) { return 128 + 2 * BUF * 4 + Cin * 9 * COGP * 4 + 64; }
+};
+
+// Input tiles arrive by TMA (4-D tiled map over [N][C][H][W], zero fill outside the
+// image = the conv padding) into a two-stage ring; the weights of this output
+// group are staged once.
+template <int COG, int PX>
+__global__ void __launch_bounds__(128)
+conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int ckb, int H, int W,
+                      const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                      float* __restrict__ out, long out_ns, float slope,
+                      const float* __restrict__ mask, const float* __restrict__ add, long add_ns,
+                      int accumulate, int tiles_x) {
+  using C = FwdV2Cfg<COG, PX>;
+  constexpr int SPR = C::SPR, TH = C::TH, PITCH = C::PITCH, COGP = C::COGP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  float* buf = reinterpret_cast<float*>(smem_raw + (base_u32 - smem_u32(smem_raw)));
+  float* w_s = buf + 2 * C::BUF;                       // [Cin][9][COGP]
+  const uint32_t bar0 = base_u32 + (2 * C::BUF + Cin * 9 * COGP) * 4;
+  const int tid = threadIdx.x;
+  const int sx = tid % SPR, ty = tid / SPR;
+  const int th0 = (blockIdx.x / tiles_x) * TH, tw0 = (blockIdx.x % tiles_x) * 32;
+  const int co0 = blockIdx.y * COG;
+  const int n = blockIdx.z;
+  const int nch = (Cin + ckb - 1) / ckb;
+  const uint32_t stage_bytes = (uint32_t)(ckb * (TH + 2) * PITCH * 4);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&in_map);
+    mbar_expect_tx(bar0, stage_bytes);
+    tma_load_4d(base_u32, &in_map, bar0, tw0 - 4, th0 - 1, 0, n);
+  }
+  for (int i = tid; i < Cin * 9 * COGP; i += 128) {
+    const int g = i % COGP, t = (i / COGP) % 9, c = i / (COGP * 9);
+    float v = 0.f;
+    if (g < COG && co0 + g < Cout) v = w[((long)(co0 + g) * Cin + c) * 9 + t];
+    w_s[i] = v;
+  }
+  float acc[PX][COG];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int g = 0; g < COG; ++g) acc[p][g] = 0.f;
+  __syncthreads();
+
+  for (int k = 0; k < nch; ++k) {
+    if (tid == 0 && k + 1 < nch) {
+      const uint32_t b = bar0 + 8 * ((k + 1) & 1);
+      mbar_expect_tx(b, stage_bytes);
+      tma_load_4d(base_u32 + ((k + 1) & 1) * C::BUF * 4, &in_map, b, tw0 - 4, th0 - 1, (k + 1) * ckb, n);
+    }
+    mbar_wait(bar0 + 8 * (k & 1), (k >> 1) & 1);
+    const float* in_s = buf + (k & 1) * C::BUF;
+    const int c0 = k * ckb;
+    const int cmax = (Cin - c0) < ckb ? (Cin - c0) : ckb;
+#pragma unroll 1
+    for (int c = 0; c < cmax; ++c) {
+      const float* wc = w_s + (c0 + c) * 9 * COGP;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float* row = in_s + (c * (TH + 2) + ty + r) * PITCH + PX * sx + 4;
+        float v[PX + 2];
+        v[0] = row[-1];
+#pragma unroll
+        for (int q = 0; q < PX; q += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(row + q);
+          v[q + 1] = f.x; v[q + 2] = f.y; v[q + 3] = f.z; v[q + 4] = f.w;
+        }
+        v[PX + 1] = row[PX];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          float wv[COGP];
+#pragma unroll
+          for (int g4 = 0; g4 < COGP; g4 += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(wc + (r * 3 + s) * COGP + g4);
+            wv[g4] = f.x; wv[g4 + 1] = f.y; wv[g4 + 2] = f.z; wv[g4 + 3] = f.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int g = 0; g < COG; ++g) acc[p][g] = fmaf(v[p + s], wv[g], acc[p][g]);
+        }
+      }
+    }
+    __syncthreads();          // stage (k&1) may be refilled at the next iteration
+  }
+  const int oy = th0 + ty, ox = tw0 + PX * sx;
+  if (oy >= H || ox >= W) return;
+#pragma unroll
+  for (int g = 0; g < COG; ++g) {
+    const int co = co0 + g;
+    if (co >= Cout) break;
+    const float b = bias ? bias[co] : 0.f;
+    const float mk = mask ? mask[(long)n * Cout + co] : 1.f;
+    const long o = (long)n * out_ns + ((long)co * H + oy) * W + ox;
+    const long oa = (long)n * add_ns + ((long)co * H + oy) * W + ox;
+    float r[PX];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      float v = acc[p][g] + b;
+      v = v < 0.f ? v * slope : v;
+      r[p] = v * mk;
+    }
+    if (ox + PX <= W) {                       // W % 4 == 0 is required by the launcher
+#pragma unroll
+      for (int q = 0; q < PX; q += 4) {
+        float4 f = make_float4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+        if (add) {
+          const float4 a = *reinterpret_cast<const float4*>(add + oa + q);
+          f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
+        }
+        if (accumulate) {
+          const float4 a = *reinterpret_cast<const float4*>(out + o + q);
+          f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
+        }
+        *reinterpret_cast<float4*>(out + o + q) = f;
+      }
+    } else {
+      for (int p = 0; p < PX && ox + p < W; ++p) {
+        float v = r[p];
+        if (add) v += add[oa + p];
+        if (accumulate) v += out[o + p];
+        out[o + p] = v;
+      }
+    }
+  }
+}
+
+template <int COG, int PX>
+static int launch_fwd_v2(const float* in, long in_ns, int Cin, int H, int W, const float* w,
+                         const float* bias, int Cout, float* out, long out_ns, float slope,
+                         const float* mask, const float* add, long add_ns, int accumulate, int N,
+                         cudaStream_t st) {
+  using C = FwdV2Cfg<COG, PX>;
+  const int ckb = Cin < C::CK ? Cin : C::CK;
+  CUtensorMap map;
+  const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)Cin, (unsigned long long)N};
+  const unsigned long long strides[3] = {(unsigned long long)W, (unsigned long long)H * W,
+                                         (unsigned long long)in_ns};
+  const unsigned int box[4] = {(unsigned)C::PITCH, (unsigned)(C::TH + 2), (unsigned)ckb, 1u};
+  int rc = dmc_make_f32_map(&map, in, 4, dims, strides, box);
+  if (rc) return rc;
+  const int smem = C::smem_bytes(Cin);
+  auto kern = conv3x3_fwd_v2_kernel<COG, PX>;
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    const int want = smem > 100 * 1024 ? smem : 100 * 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want) != cudaSuccess)
+      return dmc_check_launch("conv3x3_fwd_v2 smem attribute");
+    attr_bytes = want;
+  }
+  const int tx32 = (int)cdiv(W, 32);
+  dim3 grid(tx32 * (unsigned)cdiv(H, C::TH), (unsigned)cdiv(Cout, COG), N);
+  kern<<<grid, 128, smem, st>>>(map, Cin, ckb, H, W, w, bias, Cout, out, out_ns, slope, mask, add,
+                                add_ns, accumulate, tx32);
+  return dmc_check_launch("conv3x3_fwd_v2_kernel");
+}
+
+// wT[ci][co][2-r][2-s] = w[co][ci][r][s] for ci < ci_count: turns the stride-1 data
+// gradient into a forward convolution of dY with wT.
+__global__ void weight_flip_kernel(const float* __restrict__ w, int Cout, int Cin, int ci_count,
+                                   float* __restrict__ wT) {
+  const int n = ci_count * Cout * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = i % 9, co = (i / 9) % Cout, ci = i / (9 * Cout);
+    wT[i] = w[((long)co * Cin + ci) * 9 + (8 - t)];
+  }
+}
+
+// 3x3 stride-1 weight gradient.  Warp = one input channel x COUT output channels
+// (9*COUT register accumulators kept across ALL tiles the CTA visits), lane = one
+// column of a 32 x 16 output tile, with a 3 x 3 register window sliding down the
+// rows: 3 + COUT shared loads per 9*COUT FMAs.  Tiles (input with halo, dY) arrive
+// by TMA into a two-stage ring.  One shuffle reduction + atomic flush per CTA.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map,
+                        int Cin, int Cout, int H, int W, float* __restrict__ dW,
+                        float* __restrict__ dbias, int N, int ci_groups, int xbox_c) {
+  constexpr int XP = 40, XR = 18, TR = 16;   // 4 + 32 + 4 columns: 16-byte aligned box start
+  constexpr int XBUF = 8 * XR * XP, DBUF = COUT * TR * 32, STAGE = XBUF + DBUF;   // floats
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const float* buf = reinterpret_cast<const float*>(smem_raw + (base_u32 - smem_u32(smem_raw)));
+  const uint32_t bar0 = base_u32 + 2 * STAGE * 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cig = blockIdx.y % ci_groups, cog = blockIdx.y / ci_groups;
+  const int ci = cig * 8 + warp, co0 = cog * COUT;
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + TR - 1) / TR;
+  const long items = (long)N * tiles_x * tiles_y;
+  const uint32_t stage_bytes = (uint32_t)(xbox_c * XR * XP + DBUF) * 4;
+  float acc[COUT][3][3];
+  float bs[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    bs[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) acc[c][r][s] = 0.f;
+  }
+#define DMC_WG_ISSUE(item_, stage_)                                                   \
+  {                                                                                   \
+    const long it_ = (item_);                                                         \
+    const int n_ = (int)(it_ / (tiles_x * tiles_y));                                  \
+    const int t_ = (int)(it_ % (tiles_x * tiles_y));                                  \
+    const int oh0_ = (t_ / tiles_x) * TR, ow0_ = (t_ % tiles_x) * 32;                 \
+    const uint32_t b_ = bar0 + 8 * (stage_);                                          \
+    const uint32_t dst_ = base_u32 + (stage_) * STAGE * 4;                            \
+    mbar_expect_tx(b_, stage_bytes);                                                  \
+    tma_load_4d(dst_, &x_map, b_, ow0_ - 4, oh0_ - 1, cig * 8, n_);                   \
+    tma_load_4d(dst_ + XBUF * 4, &dy_map, b_, ow0_, oh0_, co0, n_);                   \
+  }
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&x_map);
+    tma_prefetch_desc(&dy_map);
+    if ((long)blockIdx.x < items) DMC_WG_ISSUE(blockIdx.x, 0)
+  }
+  __syncthreads();
+  int k = 0;
+  for (long item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+    const long next = item + gridDim.x;
+    if (tid == 0 && next < items) DMC_WG_ISSUE(next, (k + 1) & 1)
+    mbar_wait(bar0 + 8 * (k & 1), (k >> 1) & 1);
+    if (ci < Cin) {
+      const float* xs = buf + (k & 1) * STAGE + warp * XR * XP + lane + 3;   // tile col 0 = x0 - 4
+      const float* ds = buf + (k & 1) * STAGE + XBUF + lane;
+      float w0[3], w1[3], w2[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) { w0[s] = xs[s]; w1[s] = xs[XP + s]; }
+#pragma unroll 4
+      for (int y = 0; y < TR; ++y) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) w2[s] = xs[(y + 2) * XP + s];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float d = ds[(c * TR + y) * 32];
+          bs[c] += d;
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            acc[c][0][s] = fmaf(d, w0[s], acc[c][0][s]);
+            acc[c][1][s] = fmaf(d, w1[s], acc[c][1][s]);
+            acc[c][2][s] = fmaf(d, w2[s], acc[c][2][s]);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { w0[s] = w1[s]; w1[s] = w2[s]; }
+      }
+    }
+    __syncthreads();
+  }
+  if (ci < Cin) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      const int co = co0 + c;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const float v = warp_sum(acc[c][r][s]);
+          if (lane == 0 && co < Cout) atomicAdd(dW + ((long)co * Cin + ci) * 9 + r * 3 + s, v);
+        }
+      if (dbias && ci == 0) {
+        const float v = warp_sum(bs[c]);
+        if (lane == 0 && co < Cout) atomicAdd(dbias + co, v);
+      }
+    }
+  }
+}
+
+#undef DMC_WG_ISSUE
+
+template <int COUT>
+static int launch_wgrad_v3(const float* in, long in_ns, int Cin, int H, int W, const float* dY,
+                           long dy_ns, int Cout, float* dW, float* dbias, int N, cudaStream_t st) {
+  CUtensorMap xm, dm;
+  {
+    const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
+                                        (unsigned long long)Cin, (unsigned long long)N};
+    const unsigned long long str[3] = {(unsigned long long)W, (unsigned long long)H * W,
+                                       (unsigned long long)in_ns};
+    const unsigned int box[4] = {40u, 18u, (unsigned)(Cin < 8 ? Cin : 8), 1u};
+    int rc = dmc_make_f32_map(&xm, in, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
+                                        (unsigned long long)Cout, (unsigned long long)N};
+    const unsigned long long str[3] = {(unsigned long long)W, (unsigned long long)H * W,
+                                       (unsigned long long)dy_ns};
+    const unsigned int box[4] = {32u, 16u, (unsigned)COUT, 1u};
+    int rc = dmc_make_f32_map(&dm, dY, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  constexpr int STAGE = 8 * 18 * 40 + COUT * 16 * 32;
+  const int smem = 128 + 2 * STAGE * 4 + 64;
+  auto kern = conv3x3_wgrad_v3_kernel<COUT>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return dmc_check_launch("conv3x3_wgrad_v3 smem attribute");
+    attr = true;
+  }
+  const int ci_groups = (int)cdiv(Cin, 8), co_groups = (int)cdiv(Cout, COUT);
+  const long items = (long)N * cdiv(W, 32) * cdiv(H, 16);
+  long gx = cdiv(148L * 3, (long)ci_groups * co_groups);
+  if (gx < 1) gx = 1;
+  if (gx > items) gx = items;
+  dim3 grid((unsigned)gx, (unsigned)(ci_groups * co_groups));
+  kern<<<grid, 256, smem, st>>>(xm, dm, Cin, Cout, H, W, dW, dbias, N, ci_groups, Cin < 8 ? Cin : 8);
+  return dmc_check_launch("conv3x3_wgrad_v3_kernel");
+}
+
 // ------------------------------------------------------------------ planar elementwise / BatchNorm
 // dPre = dA * mask[n][c] * (A > 0 ? 1 : slope)     (LeakyReLU + Dropout2d backward)
 __global__ void act_bwd_planar_kernel(const float* __restrict__ dA, long da_ns,
@@ -432,7 +765,16 @@ extern "C" int dmc_conv_fwd(const float* in, long in_ns, int Cin, int H, int W, 
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   const int tiles_x = (int)cdiv(Wo, 16), tiles_y = (int)cdiv(Ho, 16);
   cudaStream_t st = ST_(stream);
-  if (ks == 3 && stride == 1) {
+  if (ks == 3 && stride == 1 && W % 4 == 0 && in_ns % 4 == 0 && out_ns % 4 == 0 && add_ns % 4 == 0 &&
+      (H * W) % 4 == 0) {
+    if (Cout == 2)
+      return launch_fwd_v2<2, 8>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
+    if (Cout <= 4)
+      return launch_fwd_v2<4, 8>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
+    if (Cout == 6)
+      return launch_fwd_v2<6, 4>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
+    return launch_fwd_v2<8, 4>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
+  } else if (ks == 3 && stride == 1) {
     dim3 grid(tiles_x * tiles_y, (unsigned)cdiv(Cout, 8), N);
     conv_fwd_kernel<3, 1, 8, 8><<<grid, 256, 0, st>>>(in, in_ns, Cin, H, W, w, bias, Cout, out,
                                                       out_ns, Ho, Wo, slope, mask, add, add_ns,
@@ -488,6 +830,12 @@ extern "C" int dmc_conv_wgrad(const float* in, long in_ns, int Cin, int H, int W
   const int pad = ks / 2;
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   cudaStream_t st = ST_(stream);
+  if (ks == 3 && stride == 1 && W % 4 == 0 && in_ns % 4 == 0 && dy_ns % 4 == 0 && (H * W) % 4 == 0) {
+    if (Cout == 2) return launch_wgrad_v3<2>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, dW, dbias, N, st);
+    if (Cout <= 4) return launch_wgrad_v3<4>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, dW, dbias, N, st);
+    if (Cout == 6) return launch_wgrad_v3<6>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, dW, dbias, N, st);
+    return launch_wgrad_v3<8>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, dW, dbias, N, st);
+  }
   if (ks == 3 && stride == 1)
     return launch_wgrad<3, 1, 8, 32>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
   if (ks == 3)
@@ -553,4 +901,13 @@ extern "C" int dmc_copy_planar(const float* src, long s_ns, float* dst, long d_n
   const long total = count * N;
   copy_planar_kernel<<<ew_grid(total), 256, 0, ST_(stream)>>>(src, s_ns, dst, d_ns, count, total);
   return dmc_check_launch("copy_planar_kernel");
+}
+
+// wT[ci][co][3][3] (ci < ci_count) = spatially flipped, transposed w[co][ci][3][3]
+extern "C" int dmc_weight_flip(const float* w, int Cout, int Cin, int ci_count, float* wT,
+                               void* stream) {
+  DMC_REQUIRE(ci_count >= 1 && ci_count <= Cin, "weight_flip: ci_count=%d Cin=%d", ci_count, Cin);
+  const int n = ci_count * Cout * 9;
+  weight_flip_kernel<<<(int)cdiv(n, 256), 256, 0, ST_(stream)>>>(w, Cout, Cin, ci_count, wT);
+  return dmc_check_launch("weight_flip_kernel");
 }

@@ -69,6 +69,35 @@ static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
   return DMC_OK;
 }
 
+}  // namespace dmc
+
+int dmc_make_f32_map(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_elems, const unsigned int* box) {
+  auto enc = dmc::get_encode();
+  if (!enc) {
+    dmc_set_error("cuTensorMapEncodeTiled entry point not available");
+    return DMC_ERR_CUDA;
+  }
+  cuuint64_t d[5], strides[4];
+  cuuint32_t b[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    estr[i] = 1;
+    if (i < rank - 1) strides[i] = strides_elems[i] * sizeof(float);
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), d, strides, b,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dmc_set_error("cuTensorMapEncodeTiled(f32, rank %d) failed (%d)", rank, (int)r);
+    return DMC_ERR_CUDA;
+  }
+  return DMC_OK;
+}
+
+namespace dmc {
+
 // ------------------------------------------------------------------ fprop / dgrad
 template <int BN, int STAGES>
 struct TapGemmSmem {

@@ -253,6 +253,7 @@ class DmcEngine:
         self.gen_out_off = outs                                          # [20, 12, 6, 2, 0]
         self.gen_in_off = [o + g for o, g in zip(outs, GEN_GROWTH)]      # [28, 20, 12, 6, 2]
         self.mv_off = self.gen_ctot - GEN_IN                             # 28
+        self.wflip = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=dev)   # dgrad weight scratch
 
     def _alloc_classifier(self):
         dev, N = self.device, self.N
@@ -370,8 +371,7 @@ class DmcEngine:
         dG = self.d_gen_flow.view(-1)
         wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
         ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dG, 2 * HW, 2, 3, 1, self.g(wk), self.g(bk), n)
-        ops.conv_dgrad(dG, 2 * HW, 2, self.p(wk), self.gen_ctot, ngen, 3, 1, dX, dns, H, W, n,
-                       accumulate=False)
+        self._dgrad_s1(dG, 2 * HW, 2, wk, self.gen_ctot, ngen, dX, dns, H, W, n, False)
         for k in reversed(range(len(GEN_GROWTH))):
             g = GEN_GROWTH[k]
             oo, io = self.gen_out_off[k], self.gen_in_off[k]
@@ -382,8 +382,14 @@ class DmcEngine:
             ops.conv_wgrad(X[io * HW:], ns, cin, H, W, dX[oo * HW:], dns, g, 3, 1, self.g(wk),
                            self.g(bk), n)
             if ngen - io > 0:
-                ops.conv_dgrad(dX[oo * HW:], dns, g, self.p(wk), cin, ngen - io, 3, 1, dX[io * HW:],
-                               dns, H, W, n, accumulate=True)
+                self._dgrad_s1(dX[oo * HW:], dns, g, wk, cin, ngen - io, dX[io * HW:], dns, H, W, n, True)
+
+    def _dgrad_s1(self, dY, dy_ns, cout, wkey, cin, ci_count, dX, dx_ns, H, W, n, accumulate):
+        """3x3 stride-1 data gradient = forward convolution of dY with the flipped, transposed weight."""
+        wT = self.wflip[:ci_count * cout * 9]
+        ops.weight_flip(self.p(wkey), cout, cin, ci_count, wT)
+        ops.conv_fwd(dY, dy_ns, cout, H, W, wT, None, ci_count, 3, 1, dX, dx_ns, n, slope=1.0,
+                     accumulate=accumulate)
 
     # ------------------------------------------------------------------ classifier
     def _prep_weights(self):
@@ -659,8 +665,11 @@ class DmcEngine:
                                self.g(p + '.0.weight'), self.g(p + '.0.bias'), m)
             if li > 0:
                 nxt = self.d_g[(li - 1) % 2]
-                ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'], nxt,
-                               ci * h * w, h, w, m, accumulate=False)
+                if L['stride'] == 1:
+                    self._dgrad_s1(g, ns, co, p + '.0.weight', ci, ci, nxt, ci * h * w, h, w, m, False)
+                else:
+                    ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'], nxt,
+                                   ci * h * w, h, w, m, accumulate=False)
                 g = nxt
             elif d_input is not None:
                 ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'],

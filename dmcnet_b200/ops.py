@@ -7,6 +7,7 @@ must be CUDA, contiguous and of the stated dtype; violations raise.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -45,9 +46,20 @@ def set_call_hook(hook) -> None:
     _hook = hook
 
 
+_SYNC_DEBUG = bool(os.environ.get('DMC_SYNC_DEBUG'))
+
+
 def _call(name: str, *args) -> None:
     fn = getattr(_native.lib(), name)
     fn.restype = c_int
+    if _SYNC_DEBUG:
+        _native.check(fn(*args), name)
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError as e:
+            raise RuntimeError('kernel failure inside %s(%s): %s' % (
+                name, ', '.join(str(getattr(a, 'value', a)) for a in args), e)) from e
+        return
     if _hook is None:
         _native.check(fn(*args), name)
     else:
@@ -177,6 +189,11 @@ def conv_dgrad(dY, dy_ns, Cout, w, Cin, ci_count, ks, stride, dX, dx_ns, H, W, N
     _call('dmc_conv_dgrad', _ptr(dY, F32), c_long(dy_ns), c_int(Cout), _ptr(w, F32), c_int(Cin),
           c_int(ci_count), c_int(ks), c_int(stride), _ptr(dX, F32), c_long(dx_ns), c_int(H), c_int(W),
           c_int(1 if accumulate else 0), c_int(N), _stream())
+
+
+def weight_flip(w, Cout, Cin, ci_count, wT):
+    _call('dmc_weight_flip', _ptr(w, F32), c_int(Cout), c_int(Cin), c_int(ci_count), _ptr(wT, F32),
+          _stream())
 
 
 def conv_wgrad(inp, in_ns, Cin, H, W, dY, dy_ns, Cout, ks, stride, dW, dbias, N):
