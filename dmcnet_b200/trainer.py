@@ -46,6 +46,34 @@ class HParams:
 GROUPS = ('base_model', 'gen_flow_model', 'discriminator')
 
 
+def shard_range(rank: int, world: int, global_batch: int) -> Tuple[int, int]:
+    """Clips [lo, hi) of the global batch owned by `rank` (shard on clips, never on
+    frames: consensus groups the S frames of one clip)."""
+    if global_batch % world:
+        raise ValueError('global batch %d is not divisible by world size %d' % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def loss_grad_scales(hp: 'HParams', batch: int, world: int, frames: int, height: int, width: int):
+    """Per-rank gradient pre-scales that make a SUM all-reduce reproduce the
+    reference's global-mean losses: CE / B_global, 2*MSE / numel_global."""
+    return {'cls': hp.lr_cls / (batch * world),
+            'mse': 2.0 * hp.lr_mse / float(frames * 2 * height * width * world)}
+
+
+def allreduce_groups(flat: torch.Tensor, group_range: Dict[str, Tuple[int, int]],
+                     groups: Sequence[str], world: int, pg=None) -> Tuple[int, int]:
+    """ONE sum all-reduce over the contiguous slice of the flat gradient bucket that
+    covers the optimizers about to step.  Returns the [lo, hi) element range."""
+    lo = min(group_range[g][0] for g in groups)
+    hi = max(group_range[g][1] for g in groups)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=pg)
+    return lo, hi
+
+
 class FusedTrainStep:
     def __init__(self, engine: DmcEngine, hp: HParams, batch: int, *, world_size: int = 1,
                  process_group=None, use_graph: bool = False):
@@ -126,10 +154,7 @@ class FusedTrainStep:
     def _allreduce(self, groups: Sequence[str]):
         if self.world <= 1:
             return
-        import torch.distributed as dist
-        lo = min(self.eng.group_range[g][0] for g in groups)
-        hi = max(self.eng.group_range[g][1] for g in groups)
-        dist.all_reduce(self.eng.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        allreduce_groups(self.eng.grads, self.eng.group_range, groups, self.world, self.pg)
 
     def _mode(self) -> str:
         if not self.eng.gan:
@@ -140,19 +165,19 @@ class FusedTrainStep:
         """forward + heads + backward for one mode (graph-capturable: static buffers only)."""
         eng, hp, B, S = self.eng, self.hp, self.B, self.S
         n = B * S
-        Bg = B * self.world
-        numel_g = float(n * 2 * eng.H * eng.W * self.world)
+        sc = loss_grad_scales(hp, B, self.world, n, eng.H, eng.W)
+        g_cls, g_mse = sc['cls'], sc['mse']
         eng.zero_grads()
         if not eng.gan:
             eng.forward(self.in_mv, self.in_res, train=True)
-            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
                         eng.d_logits, self.ce_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, 2.0 * hp.lr_mse / numel_g,
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse,
                          eng.d_gen_flow, self.mse_sum)
             eng.backward(n, cls=(mode == 'full'), cls_wgrad=True, gen_grad=True, cls_to_gen=False)
         elif mode == 'D':
             eng.forward(self.in_mv, self.in_res, self.in_flow, train=True, masks='preloaded')
-            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
                         eng.d_logits, self.ce_stats)
             ops.ce_head(eng.validity, 2 * n, 1, 2, self.adv_t_d, hp.lr_adv_d / (2 * n * self.world), None,
                         eng.d_validity, self.adv_stats)
@@ -161,11 +186,11 @@ class FusedTrainStep:
                          disc_wgrad=True, disc_to_gen=False)
         else:
             eng.forward(self.in_mv, self.in_res, None, train=True, masks='preloaded')
-            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, hp.lr_cls / Bg, self.consensus,
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
                         eng.d_logits, self.ce_stats)
             ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, hp.lr_adv_g / (n * self.world), None,
                         eng.d_validity, self.adv_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, 2.0 * hp.lr_mse / numel_g,
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse,
                          eng.d_gen_flow, self.mse_sum)
             # classifier / discriminator weight gradients are dead work in the G-step (:367-371)
             eng.backward(n, cls=True, cls_wgrad=False, gen_grad=True, cls_to_gen=True, disc=True,

@@ -1,0 +1,110 @@
+"""CPU, world_size 2, gloo: the data-parallel host logic of FusedTrainStep.
+
+Each rank runs the ORACLE on its shard of clips with the trainer's gradient
+pre-scales (loss / global batch), packs the gradients into a flat bucket laid
+out like the engine's (classifier | generator | discriminator groups), and the
+trainer's single sum all-reduce must reproduce the gradient the reference
+computes on the gathered batch with per-replica BatchNorm (nn.DataParallel
+semantics, code/dmcnet/train.py:117)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from dmcnet_b200 import trainer as T
+from oracle import dmc_oracle as O
+
+HW = 32          # small frames keep the CPU test fast
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_grads(sd, flow, mv, res, target, lo, hi, scales):
+    """Oracle forward/backward on clips [lo,hi) with pre-scaled loss gradients."""
+    st = {k: (v.clone().requires_grad_(True) if not O.is_buffer(k) else v.clone()) for k, v in sd.items()}
+    out, gen = O.model_forward(st, mv[lo:hi], res[lo:hi], train=True)
+    out = out.view(-1, 3, out.shape[-1]).mean(1)
+    fl = flow[lo:hi].reshape(gen.shape)
+    # sum-form losses times the trainer's scales == d/dtheta of the global-mean losses
+    loss = F.cross_entropy(out, target[lo:hi], reduction='sum') * scales['cls'] \
+        + ((gen - fl) ** 2).sum() * (scales['mse'] / 2.0)
+    loss.backward()
+    return {k: v.grad for k, v in st.items() if not O.is_buffer(k)}
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    B = 4
+    sd = O.build_state(11, None, seed=1)
+    flow, mv, res, target = O.make_inputs(B, 3, 11, seed=0, hw=HW)
+    lo, hi = T.shard_range(rank, world, B)
+    hp = T.HParams()
+    scales = T.loss_grad_scales(hp, hi - lo, world, (hi - lo) * 3, HW, HW)
+    grads = _shard_grads(sd, flow, mv, res, target, lo, hi, scales)
+    # flat bucket with the engine's group layout
+    keys = list(grads.keys())
+    offs, off, group_range = {}, 0, {}
+    for tag in T.GROUPS:
+        start = off
+        for k in keys:
+            if k.startswith(tag):
+                offs[k] = off
+                off += (grads[k].numel() + 63) // 64 * 64
+        group_range[tag] = (start, off)
+    flat = torch.zeros(off)
+    for k in keys:
+        flat[offs[k]:offs[k] + grads[k].numel()] = grads[k].reshape(-1)
+    before_gen = flat[group_range['gen_flow_model'][0]:group_range['gen_flow_model'][1]].clone()
+    # classifier-only step group first: the generator slice must stay untouched
+    lo_e, hi_e = T.allreduce_groups(flat, group_range, ['base_model'], world)
+    assert (lo_e, hi_e) == group_range['base_model']
+    assert torch.equal(flat[group_range['gen_flow_model'][0]:group_range['gen_flow_model'][1]], before_gen)
+    T.allreduce_groups(flat, group_range, ['gen_flow_model'], world)
+    if rank == 0:
+        # reference gradient of the gathered batch with per-replica BN = sum of the shard gradients
+        tot = None
+        for r in range(world):
+            a, b = T.shard_range(r, world, B)
+            g = _shard_grads(sd, flow, mv, res, target, a, b,
+                             T.loss_grad_scales(hp, b - a, world, (b - a) * 3, HW, HW))
+            tot = g if tot is None else {k: tot[k] + g[k] for k in g}
+        worst = 0.0
+        for k in keys:
+            got = flat[offs[k]:offs[k] + tot[k].numel()].view_as(tot[k])
+            worst = max(worst, float((got - tot[k]).abs().max() / (tot[k].abs().max() + 1e-12)))
+        ret['worst'] = worst
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range():
+    assert T.shard_range(0, 8, 512) == (0, 64) and T.shard_range(7, 8, 512) == (448, 512)
+    with pytest.raises(ValueError):
+        T.shard_range(0, 3, 64)
+
+
+def test_loss_scales_reproduce_global_means():
+    hp = T.HParams()
+    s = T.loss_grad_scales(hp, 64, 8, 192, 224, 224)
+    assert s['cls'] == pytest.approx(hp.lr_cls / 512)
+    assert s['mse'] == pytest.approx(2 * hp.lr_mse / (512 * 3 * 2 * 224 * 224))
+
+
+def test_two_rank_gradient_allreduce_matches_reference_semantics():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret['worst'] < 1e-5, ret['worst']

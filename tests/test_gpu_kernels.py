@@ -1,0 +1,336 @@
+"""GPU: every kernel family against a plain PyTorch fp32 (CPU) reference of the
+same op on identical inputs, through the C-ABI.  Tolerances: 2e-5 for fp32
+CUDA-core kernels, 5e-5 for the bf16x3 tensor-core GEMMs (~2^-16 per product),
+relative to the largest reference magnitude."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from dmcnet_b200 import ops
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / (b.double().abs().max() + 1e-30))
+
+
+def split(x):
+    hi = x.to(torch.bfloat16)
+    return hi.contiguous(), (x - hi.float()).to(torch.bfloat16).contiguous()
+
+
+def to_pixel(x):      # [N,C,H,W] -> padded pixel-major [N*(H+2)*(W+2), C]
+    n, c, h, w = x.shape
+    p = torch.zeros(n, h + 2, w + 2, c)
+    p[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1)
+    return p.reshape(-1, c).contiguous()
+
+
+def from_pixel(flat, n, c, h, w):
+    return flat.reshape(n, h + 2, w + 2, c)[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------ planar small-channel convs
+CONV_CASES = [(2, 33, 2, 64, 64, 3, 1), (2, 5, 8, 64, 96, 3, 1), (1, 21, 6, 40, 36, 3, 1),
+              (2, 27, 4, 32, 64, 3, 1), (2, 16, 16, 56, 56, 3, 1), (2, 2, 16, 64, 64, 3, 2),
+              (2, 32, 64, 28, 28, 3, 2), (2, 2, 64, 64, 64, 7, 2), (1, 3, 8, 17, 20, 3, 1)]
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,W,ks,stride', CONV_CASES)
+def test_planar_conv_fwd_dgrad_wgrad(N, Cin, Cout, H, W, ks, stride):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, Cin, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(Cout, Cin, ks, ks, generator=g) * 0.2).requires_grad_(True)
+    b = torch.randn(Cout, generator=g, requires_grad=True)
+    mask = torch.empty(N, Cout).bernoulli_(0.75, generator=g) / 0.75
+    pad = ks // 2
+    pre = F.conv2d(x, w, b, stride, pad)
+    y = F.leaky_relu(pre, 0.2) * mask.view(N, Cout, 1, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    Ho, Wo = y.shape[-2:]
+    xd, wd, bd = x.detach().cuda(), w.detach().cuda(), b.detach().cuda()
+    yo = torch.full((N, Cout, Ho, Wo), float('nan'), device='cuda')
+    ops.conv_fwd(xd, Cin * H * W, Cin, H, W, wd, bd, Cout, ks, stride, yo, Cout * Ho * Wo, N, slope=0.2,
+                 mask=mask.cuda())
+    assert rel(yo, y.detach()) < 2e-5
+    dpre = torch.empty_like(yo)
+    ops.act_bwd_planar(dy.cuda(), Cout * Ho * Wo, yo, Cout * Ho * Wo, mask.cuda(), 0.2, Cout, Ho * Wo, N,
+                       dpre, Cout * Ho * Wo)
+    dW, dB = torch.zeros_like(wd), torch.zeros_like(bd)
+    ops.conv_wgrad(xd, Cin * H * W, Cin, H, W, dpre, Cout * Ho * Wo, Cout, ks, stride, dW, dB, N)
+    assert rel(dW, w.grad) < 2e-5 and rel(dB, b.grad) < 2e-5
+    dX = torch.full((N, Cin, H, W), float('nan'), device='cuda')
+    ops.conv_dgrad(dpre, Cout * Ho * Wo, Cout, wd, Cin, Cin, ks, stride, dX, Cin * H * W, H, W, N)
+    assert rel(dX, x.grad) < 2e-5
+    if ks == 3 and stride == 1:       # the engine's stride-1 path: forward conv with flipped weights
+        wT = torch.zeros(Cin * Cout * 9, device='cuda')
+        ops.weight_flip(wd, Cout, Cin, Cin, wT)
+        dX2 = torch.full((N, Cin, H, W), float('nan'), device='cuda')
+        ops.conv_fwd(dpre, Cout * Ho * Wo, Cout, H, W, wT, None, Cin, 3, 1, dX2, Cin * H * W, N)
+        assert rel(dX2, x.grad) < 2e-5
+
+
+def test_conv_fwd_channel_subrange_add_and_accumulate():
+    """Reads / writes channel sub-ranges of a wider buffer (the dense concat), '+ input_mv', and '+='."""
+    g = torch.Generator().manual_seed(1)
+    N, H, W = 2, 32, 32
+    buf = torch.randn(N, 10, H, W, generator=g)
+    w = torch.randn(3, 6, 3, 3, generator=g) * 0.3
+    b = torch.randn(3, generator=g)
+    add = torch.randn(N, 3, H, W, generator=g)
+    ref = buf.clone()
+    ref[:, 1:4] = ref[:, 1:4] + F.conv2d(buf[:, 4:10], w, b, 1, 1) + add
+    d = buf.cuda()
+    flat = d.view(-1)
+    ops.conv_fwd(flat[4 * H * W:], 10 * H * W, 6, H, W, w.cuda(), b.cuda(), 3, 3, 1, flat[1 * H * W:],
+                 10 * H * W, N, slope=1.0, add=add.cuda(), add_ns=3 * H * W, accumulate=True)
+    assert rel(d, ref) < 2e-5
+
+
+# ------------------------------------------------------------------ tensor-core tap GEMMs
+@pytest.mark.parametrize('engine', ['tc', 'simt'])
+@pytest.mark.parametrize('n,cin,cout,h,stride', [(3, 64, 64, 12, 1), (2, 128, 256, 8, 1), (2, 64, 128, 16, 2),
+                                                  (5, 256, 512, 14, 2)])
+def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
+    from dmcnet_b200.engine import _taps_s1, _taps_s2
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, cin, h, h, generator=g, requires_grad=True)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    ho = h // stride
+    Hp = Wp = ho + 2
+    P = n * Hp * Wp
+    W_hi = torch.zeros(9, cout, cin, dtype=torch.bfloat16, device='cuda')
+    W_lo, Wt_hi, Wt_lo = (torch.zeros_like(W_hi) for _ in range(3))
+    ops.weight_prep(w.detach().cuda().contiguous(), cout, cin, 9, W_hi, W_lo, Wt_hi.view(9, cin, cout),
+                    Wt_lo.view(9, cin, cout))
+    if stride == 1:
+        A = to_pixel(x.detach())[None]
+        shift, phase, bsel = _taps_s1(Wp)
+        phases = 1
+    else:
+        hi_, lo_ = split(to_pixel(x.detach()).cuda())
+        xp_hi = torch.zeros(4, P, cin, dtype=torch.bfloat16, device='cuda')
+        xp_lo = torch.zeros_like(xp_hi)
+        ops.phase_split(hi_, lo_, n, h, h, cin, xp_hi, xp_lo)
+        shift, phase, bsel = _taps_s2(Wp)
+        phases = 4
+    if stride == 1:
+        A_hi, A_lo = split(A.cuda())
+    else:
+        A_hi, A_lo = xp_hi, xp_lo
+    D = torch.full((P, cout), float('nan'), device='cuda')
+    ops.tap_gemm(A_hi, A_lo, W_hi, W_lo, D, a_phases=phases, a_rows=P, K=cin, b_slices=9, N=cout, M=P,
+                 ldD=cout, Hp=Hp, Wp=Wp, shift=shift, phase=phase, bsel=bsel, engine=engine)
+    assert rel(from_pixel(D, n, cout, ho, ho), y.detach()) < 5e-5
+    ring = D.view(n, Hp, Wp, cout).clone()
+    ring[:, 1:-1, 1:-1] = 0
+    assert float(ring.abs().max()) == 0.0                         # epilogue keeps the zero ring
+    # wgrad
+    G_hi, G_lo = split(to_pixel(dy).cuda())
+    dWs = torch.zeros(9, cout, cin, device='cuda')
+    ops.wgrad_gemm(G_hi, G_lo, A_hi, A_lo, dWs, P=P, Cout=cout, x_phases=phases, Cin=cin, shift=shift,
+                   phase=phase, bsel=bsel, engine=engine)
+    gw = torch.empty(cout, cin, 3, 3, device='cuda')
+    ops.wgrad_unpack(dWs, gw, cout, cin, 9)
+    assert rel(gw, w.grad) < 5e-5
+    # dgrad
+    if stride == 1:
+        dX = torch.full((P, cin), float('nan'), device='cuda')
+        ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dX, a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin, M=P,
+                     ldD=cin, Hp=Hp, Wp=Wp, shift=[-s for s in shift], phase=phase, bsel=bsel, engine=engine)
+        assert rel(from_pixel(dX, n, cin, h, h), x.grad) < 5e-5
+    else:
+        dxp = torch.zeros(4, P, cin, device='cuda')
+        for ph in range(4):
+            sh = [-shift[t] for t in range(9) if phase[t] == ph]
+            bs = [bsel[t] for t in range(9) if phase[t] == ph]
+            ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dxp[ph], a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin,
+                         M=P, ldD=cin, Hp=Hp, Wp=Wp, shift=sh, phase=[0] * len(sh), bsel=bs, engine=engine)
+        dX = torch.empty(n * (h + 2) * (h + 2), cin, device='cuda')
+        ops.phase_unsplit(dxp, n, h, h, cin, dX)
+        assert rel(from_pixel(dX, n, cin, h, h), x.grad) < 5e-5
+
+
+# ------------------------------------------------------------------ BatchNorm (pixel-major and planar)
+def test_pixel_bn_train_forward_backward_with_residual():
+    g = torch.Generator().manual_seed(3)
+    n, c, h = 4, 64, 10
+    y = (torch.randn(n, c, h, h, generator=g) * 2 + 0.5).requires_grad_(True)
+    res = torch.randn(n, c, h, h, generator=g).relu()
+    gamma = (torch.rand(c, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(c, generator=g, requires_grad=True)
+    rm, rv = torch.zeros(c), torch.ones(c)
+    out = F.relu(F.batch_norm(y, rm, rv, gamma, beta, True, 0.1, 1e-5) + res)
+    dout = torch.randn(out.shape, generator=g)
+    out.backward(dout)
+    Hp = h + 2
+    P = n * Hp * Hp
+    dev = dict(device='cuda')
+    Y = to_pixel(y.detach()).cuda()
+    sums = torch.zeros(2, c, dtype=torch.float64, **dev)
+    scale, shift, mean, invstd = (torch.zeros(c, **dev) for _ in range(4))
+    rmd, rvd = torch.zeros(c, **dev), torch.ones(c, **dev)
+    nbt = torch.zeros((), dtype=torch.int64, **dev)
+    ops.bn_stats(Y, P, c, sums)
+    ops.bn_finalize(sums, float(n * h * h), gamma.detach().cuda(), beta.detach().cuda(), rmd, rvd, nbt, 0.1,
+                    1e-5, c, scale, shift, mean, invstd)
+    assert rel(rmd, rm) < 1e-5 and rel(rvd, rv) < 1e-5 and int(nbt) == 1
+    r_hi, r_lo = split(to_pixel(res).cuda())
+    o_hi = torch.zeros(P, c, dtype=torch.bfloat16, **dev)
+    o_lo = torch.zeros_like(o_hi)
+    ops.bn_apply(Y, scale, shift, P, c, Hp, Hp, True, o_hi, o_lo, res_hi=r_hi, res_lo=r_lo)
+    got = from_pixel(o_hi.float() + o_lo.float(), n, c, h, h)
+    assert rel(got, out.detach()) < 2e-5
+    # backward
+    gA = to_pixel(dout).cuda()
+    sums2 = torch.zeros(2, c, dtype=torch.float64, **dev)
+    G_hi = torch.zeros(P, c, dtype=torch.bfloat16, **dev)
+    G_lo = torch.zeros_like(G_hi)
+    dz = torch.zeros(P, c, **dev)
+    dgam, dbet = torch.zeros(c, **dev), torch.zeros(c, **dev)
+    ops.bn_bwd_reduce(gA, None, o_hi, Y, mean, invstd, P, c, Hp, Hp, sums2)
+    ops.bn_bwd_apply(gA, None, o_hi, Y, mean, invstd, gamma.detach().cuda(), sums2, float(n * h * h), P, c,
+                     Hp, Hp, G_hi, G_lo, dz, dgam, dbet)
+    assert rel(from_pixel(G_hi.float() + G_lo.float(), n, c, h, h), y.grad) < 2e-5
+    assert rel(dgam, gamma.grad) < 2e-5 and rel(dbet, beta.grad) < 2e-5
+    assert rel(from_pixel(dz, n, c, h, h), dout * (out.detach() > 0)) < 1e-6
+
+
+def test_planar_bn_eps08_forward_backward():
+    """Discriminator BatchNorm2d(C, 0.8): the 0.8 is eps (code/dmcnet_GAN/model.py:264)."""
+    g = torch.Generator().manual_seed(4)
+    n, c, h = 6, 16, 14
+    x = torch.randn(n, c, h, h, generator=g, requires_grad=True)
+    gamma = (torch.rand(c, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(c, generator=g, requires_grad=True)
+    out = F.batch_norm(x, torch.zeros(c), torch.ones(c), gamma, beta, True, 0.1, 0.8)
+    dout = torch.randn(out.shape, generator=g)
+    out.backward(dout)
+    dev = dict(device='cuda')
+    X = x.detach().cuda()
+    sums = torch.zeros(2, c, dtype=torch.float64, **dev)
+    scale, shift, mean, invstd = (torch.zeros(c, **dev) for _ in range(4))
+    ops.bn_stats_planar(X, c * h * h, c, h * h, n, sums)
+    ops.bn_finalize(sums, float(n * h * h), gamma.detach().cuda(), beta.detach().cuda(), None, None, None,
+                    0.1, 0.8, c, scale, shift, mean, invstd)
+    Z = torch.empty_like(X)
+    ops.bn_apply_planar(X, c * h * h, scale, shift, c, h * h, n, False, Z, c * h * h)
+    assert rel(Z, out.detach()) < 2e-5
+    sums2 = torch.zeros(2, c, dtype=torch.float64, **dev)
+    dX = torch.empty_like(X)
+    dgam, dbet = torch.zeros(c, **dev), torch.zeros(c, **dev)
+    ops.bn_bwd_reduce_planar(dout.cuda(), c * h * h, X, c * h * h, mean, invstd, c, h * h, n, sums2)
+    ops.bn_bwd_apply_planar(dout.cuda(), c * h * h, X, c * h * h, mean, invstd, gamma.detach().cuda(), sums2,
+                            float(n * h * h), c, h * h, n, dX, c * h * h, dgam, dbet)
+    assert rel(dX, x.grad) < 2e-5 and rel(dgam, gamma.grad) < 2e-5 and rel(dbet, beta.grad) < 2e-5
+
+
+def test_stem_bn_relu_maxpool_forward_backward():
+    g = torch.Generator().manual_seed(5)
+    n, c, h = 3, 64, 32
+    y = torch.randn(n, c, h, h, generator=g, requires_grad=True)
+    scale = torch.rand(c, generator=g) + 0.5
+    shift = torch.randn(c, generator=g) * 0.3
+    a = F.relu(y * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1))
+    p = F.max_pool2d(a, 3, 2, 1)
+    dp = torch.randn(p.shape, generator=g)
+    (da,) = torch.autograd.grad(p, a, dp, retain_graph=True)
+    dz_ref = da * (a.detach() > 0)
+    hq = h // 2
+    dev = dict(device='cuda')
+    o_hi = torch.zeros(n * (hq + 2) * (hq + 2), c, dtype=torch.bfloat16, **dev)
+    o_lo = torch.zeros_like(o_hi)
+    idx = torch.zeros(n * hq * hq * c, dtype=torch.uint8, **dev)
+    Y = y.detach().cuda()
+    ops.stem_pool_fwd(Y, scale.cuda(), shift.cuda(), n, c, h, h, o_hi, o_lo, idx)
+    assert rel(from_pixel(o_hi.float() + o_lo.float(), n, c, hq, hq), p.detach()) < 2e-5
+    dZ = torch.empty_like(Y)
+    ops.stem_pool_bwd(to_pixel(dp).cuda(), None, idx, Y, scale.cuda(), shift.cuda(), n, c, h, h, dZ)
+    assert rel(dZ, dz_ref) < 1e-6
+
+
+# ------------------------------------------------------------------ heads and optimizer
+def test_ce_head_consensus_loss_grad_topk():
+    g = torch.Generator().manual_seed(6)
+    B, S, C = 16, 3, 51
+    logits = (torch.randn(B * S, C, generator=g) * 2).requires_grad_(True)
+    target = torch.randint(0, C, (B,), generator=g)
+    out = logits.view(B, S, C).mean(1)
+    loss = F.cross_entropy(out, target)
+    (loss * 0.7).backward()
+    dev = dict(device='cuda')
+    cons, dl, st = torch.zeros(B, C, **dev), torch.zeros(B * S, C, **dev), torch.zeros(4, **dev)
+    ops.ce_head(logits.detach().cuda(), B, S, C, target.cuda(), 0.7 / B, cons, dl, st)
+    st = st.cpu()
+    assert rel(cons, out.detach()) < 1e-6 and rel(dl, logits.grad) < 1e-5
+    assert abs(float(st[0]) / B - float(loss.detach())) < 1e-5
+    _, pred = out.topk(5, 1, True, True)
+    correct = pred.eq(target.view(-1, 1))
+    assert int(st[1]) == int(correct[:, :1].sum()) and int(st[2]) == int(correct.sum())
+
+
+def test_mse_head_and_linear():
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(6, 2, 32, 32, generator=g, requires_grad=True)
+    b = torch.randn(6, 2, 32, 32, generator=g)
+    loss = F.mse_loss(a, b)
+    (loss * 10).backward()
+    dev = dict(device='cuda')
+    dgen, s = torch.zeros_like(a, **dev), torch.zeros(1, dtype=torch.float64, **dev)
+    ops.mse_head(a.detach().cuda(), b.cuda(), a.numel(), 2.0 * 10 / a.numel(), dgen, s)
+    assert abs(float(s.cpu()[0]) / a.numel() - float(loss)) < 1e-6 and rel(dgen, a.grad) < 1e-6
+    x = torch.randn(12, 512, generator=g, requires_grad=True)
+    w = (torch.randn(51, 512, generator=g) * 0.05).requires_grad_(True)
+    bias = torch.randn(51, generator=g, requires_grad=True)
+    y = F.linear(x, w, bias)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    yo = torch.zeros(12, 51, **dev)
+    ops.linear_fwd(x.detach().cuda(), w.detach().cuda(), bias.detach().cuda(), 12, 512, 51, yo)
+    dx, dw, db = torch.zeros(12, 512, **dev), torch.zeros(51, 512, **dev), torch.zeros(51, **dev)
+    ops.linear_bwd(dy.cuda(), x.detach().cuda(), w.detach().cuda(), 12, 512, 51, dx, dw, db)
+    assert rel(yo, y.detach()) < 1e-5 and rel(dx, x.grad) < 1e-5 and rel(dw, w.grad) < 1e-5
+    assert rel(db, bias.grad) < 1e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    """torch.optim.Adam(eps=1e-3) with one param group per tensor (code/dmcnet/train.py:121-142)."""
+    g = torch.Generator().manual_seed(8)
+    shapes = [(64, 2, 7, 7), (64,), (51, 512), (5,), (1030,)]
+    lrs = [1e-4, 1e-4, 1e-2, 1e-2, 3e-3]
+    wds = [1e-4, 0.0, 1e-4, 0.0, 1e-4]
+    ps = [torch.randn(s, generator=g).requires_grad_(True) for s in shapes]
+    opt = torch.optim.Adam([{'params': [p], 'lr': lr, 'weight_decay': wd} for p, lr, wd in zip(ps, lrs, wds)],
+                           eps=1e-3)
+    offs, off = [], 0
+    for s in shapes:
+        offs.append(off)
+        off += (torch.Size(s).numel() + 63) // 64 * 64
+    dev = dict(device='cuda')
+    flat, gr, m, v = (torch.zeros(off, **dev) for _ in range(4))
+    chunks = []
+    for ti, (s, o) in enumerate(zip(shapes, offs)):
+        n = torch.Size(s).numel()
+        flat[o:o + n] = ps[ti].detach().reshape(-1).cuda()
+        for c0 in range(0, n, 1024):
+            chunks.append((o + c0, min(1024, n - c0), ti, 0))
+    ch = torch.tensor(chunks, dtype=torch.int32).cuda()
+    hyper = torch.tensor(list(zip(lrs, wds)), dtype=torch.float32).cuda()
+    step = torch.zeros(1, dtype=torch.int32, **dev)
+    for it in range(3):
+        for ti, p in enumerate(ps):
+            p.grad = torch.randn(p.shape, generator=g) * (10.0 ** (-it))
+            n = p.numel()
+            gr[offs[ti]:offs[ti] + n] = p.grad.reshape(-1).cuda()
+        opt.step()
+        ops.adam_step(flat, gr, m, v, ch, len(chunks), hyper.view(-1), step, 0.9, 0.999, 1e-3)
+        for ti, p in enumerate(ps):
+            n = p.numel()
+            assert rel(flat[offs[ti]:offs[ti] + n], p.detach().reshape(-1)) < 1e-6, (it, ti)
+    assert int(step) == 3

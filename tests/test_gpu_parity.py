@@ -1,0 +1,232 @@
+"""GPU: the product path against the CPU oracle (oracle/dmc_oracle.py, pinned to
+the reference's own model.py) and against the committed golden fixtures that
+were produced by the REFERENCE (tests/golden/make_golden.py).
+
+Tolerances
+  * forward outputs (logits, consensus, validity, gen_flow, losses): 1e-3 relative
+    (north-star bar; measured ~1e-5), argmax / prec@k exact;
+  * generator and discriminator gradients in steps where no classifier gradient
+    flows into them: 1e-4 relative (they are plain fp32 kernels);
+  * everything downstream of the ResNet-18 backward: the gradient is a
+    discontinuous function of the forward activations (ReLU / max-pool switches
+    times BatchNorm's mean-subtraction over tiny test batches), so ANY forward that
+    is not bit-identical -- ours carries ~1e-5 relative error from the bf16x3
+    tensor-core split -- moves a handful of switches and changes per-tensor
+    gradients by ~1e-2 in L2.  oracle-side evidence: rounding the oracle's own
+    activations to 2^-17 reproduces the same 1.3e-2 (DESIGN.md "Parity").  The
+    bar used here is per-tensor relative L2 <= 1.2e-1 and a median <= 5e-2 (measured: worst
+    6.6e-2, medians 1.5e-2 .. 3.1e-2), with the
+    kernels themselves checked to 1e-5 on identical inputs in test_gpu_kernels.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dmc_oracle as O          # noqa: E402  (checker only)
+from oracle.digest import digest_close      # noqa: E402
+
+if torch.cuda.is_available():
+    from dmcnet_b200.engine import DmcEngine
+    from dmcnet_b200.trainer import FusedTrainStep, HParams
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel2(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _run(num_class, arch_d, batch, steps=2, gemm='tc'):
+    gan = arch_d is not None
+    sd = O.build_state(num_class, arch_d, seed=1)
+    flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
+    ref = O.OracleTrainer(sd, O.HParams(), gan=gan, arch_d=arch_d)
+    eng = DmcEngine(num_class, 3, batch * 3, gan=gan, arch_d=arch_d, gemm_engine=gemm)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(), batch)
+    assert list(eng.state_keys()) == list(sd.keys())
+    for it in range(steps):
+        masks = None
+        if gan:
+            torch.manual_seed(100 + it)
+            masks = O.draw_dropout_masks(arch_d, batch * 3 * (2 if it % 2 == 0 else 1))
+        mo = ref.step(flow, mv, res, target, masks=masks)
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), masks=masks)
+        yield it, ref, eng, tr, mo, mg
+
+
+def _check_forward(ref, eng, tr, mo, mg, gan):
+    for k in mo:
+        if k in ('prec1', 'prec5', 'acc_adv'):
+            assert mg[k] == pytest.approx(mo[k], abs=1e-9), k          # integer counts: exact
+        else:
+            assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+    assert rel(eng.gen_flow, ref.last_gen_flow) < 1e-3
+    assert rel(tr.consensus, ref.last_output) < 1e-3
+    assert torch.equal(tr.consensus.argmax(1).cpu(), ref.last_output.argmax(1))
+    if gan:
+        m = ref.last_validity.shape[0]
+        assert rel(eng.validity[:m], ref.last_validity) < 1e-3
+
+
+def _check_grads(ref, eng, groups, tight_groups=()):
+    og = ref.grads()
+    l2 = []
+    for k in eng.specs:
+        if not any(k.startswith(g) for g in groups):
+            continue
+        if float(og[k].abs().max()) == 0.0:
+            continue
+        e = rel2(eng.grad_view(k), og[k])
+        if any(k.startswith(g) for g in tight_groups):
+            assert e < 1e-4, (k, e)
+        else:
+            assert e < 1.2e-1, (k, e)
+            l2.append(e)
+    if l2:
+        assert float(np.median(l2)) < 5e-2
+
+
+def test_dmcnet_two_train_steps_vs_oracle():
+    for it, ref, eng, tr, mo, mg in _run(51, None, 2):
+        _check_forward(ref, eng, tr, mo, mg, False)
+        if it == 0:
+            # generator sees only the MSE gradient (classifier input is detached, model.py:352)
+            _check_grads(ref, eng, ['base_model', 'gen_flow_model'], tight_groups=['gen_flow_model'])
+            osd, gsd = ref.state_dict(), eng.state_dict()
+            for k in osd:
+                if k.startswith('gen_flow_model') or k.endswith(('running_mean', 'running_var')):
+                    assert rel(gsd[k].float(), osd[k].float()) < 1e-3, k
+                if k.endswith('num_batches_tracked'):
+                    assert int(gsd[k]) == int(osd[k])
+
+
+def test_dmcnet_cuda_core_gemm_engine_agrees():
+    """Same step with the CUDA-core twins of the tensor-core GEMMs."""
+    for it, ref, eng, tr, mo, mg in _run(51, None, 1, steps=1, gemm='simt'):
+        _check_forward(ref, eng, tr, mo, mg, False)
+
+
+@pytest.mark.parametrize('num_class,arch_d,batch', [(101, 'Discriminator3', 2), (51, 'Discriminator', 1)])
+def test_gan_d_step_then_g_step_vs_oracle(num_class, arch_d, batch):
+    for it, ref, eng, tr, mo, mg in _run(num_class, arch_d, batch):
+        _check_forward(ref, eng, tr, mo, mg, True)
+        if it == 0:      # D-step: classifier + discriminator step; D grads do not depend on ResNet
+            _check_grads(ref, eng, ['base_model', 'discriminator'], tight_groups=['discriminator'])
+        else:            # G-step: generator gradient arrives through ResNet-18 and D
+            _check_grads(ref, eng, ['gen_flow_model'])
+
+
+def test_frozen_phase_steps_only_generator():
+    """epoch < epoch_thre: (loss_mse*lr_mse).backward(); only optimizer_gf steps (train.py:260-266)."""
+    sd = O.build_state(51, None, seed=1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    ref = O.OracleTrainer(sd, O.HParams())
+    ref.set_epoch(0, epoch_thre=5)
+    eng = DmcEngine(51, 3, 3)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(), 1)
+    tr.set_epoch(0, epoch_thre=5)
+    ref.step(flow, mv, res, target)
+    tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+    osd, gsd = ref.state_dict(), eng.state_dict()
+    for k in osd:
+        if k.startswith('base_model') and not O.is_buffer(k):
+            assert torch.equal(gsd[k].cpu(), sd[k]), k                  # untouched
+        if k.startswith('gen_flow_model'):
+            assert rel(gsd[k], osd[k]) < 1e-3, k
+
+
+def test_inference_config1_against_reference_golden(golden_dir):
+    """BASELINE config 1: single clip, eval-mode forward, scores = mean over segments
+    (code/dmcnet/test.py:139-151); fixture produced by the reference's model.py."""
+    g = np.load(os.path.join(golden_dir, 'infer_cfg1.npz'))
+    sd = O.build_state(51, None, seed=1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    eng = DmcEngine(51, 3, 3)
+    eng.load_state(sd)
+    logits, gen_flow = eng.forward(mv.cuda(), res.cuda(), train=False)
+    base_out = logits.cpu().numpy()
+    np.testing.assert_allclose(base_out, g['base_out'], rtol=1e-3, atol=1e-3 * np.abs(g['base_out']).max())
+    scores = base_out.reshape(1, 3, 51).mean(1)
+    assert np.array_equal(scores.argmax(1), g['argmax'])
+    digest_close(g['gen_flow'], gen_flow.cpu(), 1e-3, 'gen_flow')
+
+
+def test_train_step_against_reference_golden(golden_dir):
+    """Losses / outputs of two reference train steps (fixture from the reference Model)."""
+    g = np.load(os.path.join(golden_dir, 'train_dmcnet_b2.npz'))
+    for it, ref, eng, tr, mo, mg in _run(51, None, 2):
+        for k in ('loss', 'loss_cls', 'loss_mse'):
+            assert mg[k] == pytest.approx(float(g['s%d_%s' % (it, k)]), rel=1e-3)
+        np.testing.assert_allclose(tr.consensus.cpu().numpy(), g['s%d_output' % it], rtol=1e-3,
+                                   atol=1e-3 * np.abs(g['s%d_output' % it]).max())
+        digest_close(g['s%d_gen_flow' % it], eng.gen_flow.cpu(), 1e-3, 'gen_flow')
+
+
+def test_dropin_model_autograd_path_matches_fused_step():
+    """Model.forward + loss.backward() (reference-style loop) gives the same gradients as
+    FusedTrainStep on the same inputs (both use the same kernels)."""
+    import contextlib, io
+    from dmcnet_b200.model import Model
+    sd = O.build_state(51, None, seed=1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Model(51, 3, 'mv', base_model='resnet18', arch_estimator='DenseNetTiny', gen_flow_or_delta=1,
+                  use_databn=0)
+    m.load_state_dict(sd)
+    m.cuda().train()
+    out, gen_flow = m(mv.cuda(), res.cuda())
+    out = out.view(-1, 3, 51).mean(1)
+    loss = torch.nn.functional.cross_entropy(out, target.cuda()) * 1.0 + \
+        torch.nn.functional.mse_loss(gen_flow, flow.cuda().view(-1, 2, 224, 224)) * 10.0
+    loss.backward()
+    eng = DmcEngine(51, 3, 3)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(), 1)
+    mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), apply=False)
+    assert float(loss) == pytest.approx(mg['loss'], rel=1e-5)
+    named = dict(m.named_parameters())
+    for k in eng.specs:
+        assert named[k].grad is not None, k
+        assert rel2(named[k].grad, eng.grad_view(k)) < 1e-3, k
+    assert set(m.state_dict().keys()) == set(sd.keys())
+
+
+def test_full_size_properties_b64():
+    """BASELINE config 2 size (B=64): size-independent properties -- finite losses,
+    the MSE loss decreases under Adam, zero padding ring preserved, BN counters advance,
+    and a CUDA-graph replay reproduces the eager step bit for bit."""
+    B = 64
+    sd = O.build_state(51, None, seed=1)
+    g = torch.Generator().manual_seed(3)
+    flow = torch.randn(B, 3, 2, 224, 224, generator=g)
+    mv = torch.randn(B, 3, 2, 224, 224, generator=g)
+    res = torch.randn(B, 3, 3, 224, 224, generator=g)
+    target = torch.randint(0, 51, (B,), generator=g)
+    outs = {}
+    for graph in (False, True):
+        eng = DmcEngine(51, 3, B * 3)
+        eng.load_state(sd)
+        tr = FusedTrainStep(eng, HParams(), B, use_graph=graph)
+        ms = [tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda()) for _ in range(4)]
+        assert all(np.isfinite(m['loss']) for m in ms)
+        assert ms[-1]['loss_mse'] < ms[0]['loss_mse']
+        blk = eng.blocks[0]['c2']
+        ring = (blk.act_hi.float() + blk.act_lo.float()).view(B * 3, 58, 58, 64).clone()
+        ring[:, 1:-1, 1:-1] = 0
+        assert float(ring.abs().max()) == 0.0
+        assert int(eng.buffers['base_model.bn1.num_batches_tracked']) == 4
+        outs[graph] = (ms[-1]['loss'], eng.params.clone())
+        del eng, tr
+        torch.cuda.empty_cache()
+    assert outs[False][0] == pytest.approx(outs[True][0], rel=1e-5)
+    assert rel2(outs[True][1], outs[False][1]) < 1e-4       # atomics order differs; same maths

@@ -1,0 +1,137 @@
+"""CPU: host-side logic of the product path (no kernels are launched).
+
+* the drop-in Model constructs the reference's state_dict (keys, shapes, init RNG order),
+* the row-shifted "tap GEMM" formulation of 3x3 convolutions over the padded
+  pixel-major layout (stride 1, stride 2 through four phases, and their data
+  gradients) is checked in numpy against torch conv2d with the engine's own tap tables,
+* product code refuses to run on CPU tensors (no fallback).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dmcnet_b200 import engine as E
+from dmcnet_b200 import model as M
+from oracle import dmc_oracle as O
+
+
+@pytest.mark.parametrize('num_class,arch_d', [(51, None), (101, 'Discriminator3'), (51, 'Discriminator'),
+                                              (51, 'Discriminator4')])
+def test_model_state_matches_reference_constructor(num_class, arch_d):
+    a = M.build_state(num_class, arch_d, seed=1)
+    b = O.build_state(num_class, arch_d, seed=1)
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_model_api_surface():
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = M.Model(51, 3, 'mv', base_model='resnet18', arch_estimator='DenseNetTiny', use_databn=0,
+                    gen_flow_or_delta=1)
+        g = M.GANModel(51, 3, 'mv', base_model='resnet18', arch_estimator='DenseNetTiny', use_databn=1,
+                       arch_d='Discriminator3')
+        with pytest.raises(ValueError, match='Unknown base model'):
+            M.Model(51, 3, 'mv', base_model='vgg16')
+    assert m.crop_size == 224 and m.scale_size == 256 and m.num_segments == 3
+    names = [n for n, _ in g.named_parameters()]
+    assert any('base_model' in n for n in names) and any('gen_flow_model' in n for n in names)
+    assert any('discriminator' in n for n in names) and 'data_bn.weight' in names
+    assert not hasattr(m, 'discriminator')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m(torch.zeros(1, 3, 2, 224, 224), torch.zeros(1, 3, 3, 224, 224))
+
+
+def _pad_pixel_major(x):          # [N,C,H,W] -> [N*(H+2)*(W+2), C] with zero ring
+    n, c, h, w = x.shape
+    p = np.zeros((n, h + 2, w + 2, c), np.float64)
+    p[:, 1:-1, 1:-1, :] = x.transpose(0, 2, 3, 1)
+    return p.reshape(-1, c)
+
+
+def _tap_gemm(A, B, shift, phase, bsel, M_rows):
+    """numpy model of dmc_tc_tap_gemm: A [phases][rows][K], B [slices][N][K]."""
+    rows = A.shape[1]
+    out = np.zeros((M_rows, B.shape[1]))
+    q = np.arange(M_rows)
+    for s, p, b in zip(shift, phase, bsel):
+        idx = q + s
+        ok = (idx >= 0) & (idx < rows)
+        a = A[p][np.clip(idx, 0, rows - 1)] * ok[:, None]
+        out += a @ B[b].T
+    return out
+
+
+def _interior(n, h, w, c, flat):
+    return flat.reshape(n, h + 2, w + 2, c)[:, 1:-1, 1:-1, :].transpose(0, 3, 1, 2)
+
+
+def _phase_split(x):               # [N,C,H,W] -> [4][N*(H/2+2)*(W/2+2), C]
+    return np.stack([_pad_pixel_major(x[:, :, ph::2, pw::2]) for ph in (0, 1) for pw in (0, 1)])
+
+
+def test_tap_tables_stride1_and_stride2_match_conv2d():
+    rng = np.random.default_rng(0)
+    n, ci, co, h, w = 2, 5, 4, 8, 6
+    x = rng.standard_normal((n, ci, h, w))
+    wt = rng.standard_normal((co, ci, 3, 3))
+    Wg = wt.transpose(2, 3, 0, 1).reshape(9, co, ci)               # [tap][co][ci]
+    # stride 1
+    shift, phase, bsel = E._taps_s1(w + 2)
+    A = _pad_pixel_major(x)[None]
+    y = _interior(n, h, w, co, _tap_gemm(A, Wg, shift, phase, bsel, A.shape[1]))
+    ref = F.conv2d(torch.tensor(x), torch.tensor(wt), None, 1, 1).numpy()
+    np.testing.assert_allclose(y, ref, atol=1e-10)
+    # stride 2 through the four input phases stored in the OUTPUT geometry
+    shift, phase, bsel = E._taps_s2(w // 2 + 2)
+    A2 = _phase_split(x)
+    y2 = _interior(n, h // 2, w // 2, co, _tap_gemm(A2, Wg, shift, phase, bsel, A2.shape[1]))
+    ref2 = F.conv2d(torch.tensor(x), torch.tensor(wt), None, 2, 1).numpy()
+    np.testing.assert_allclose(y2, ref2, atol=1e-10)
+
+
+def test_tap_tables_data_gradients():
+    """dgrad = tap GEMM with negated shifts and transposed weights (stride 1), and one
+    GEMM per input phase with the matching tap subset (stride 2), as engine._cls_backward."""
+    rng = np.random.default_rng(1)
+    n, ci, co, h, w = 1, 3, 4, 6, 8
+    wt = rng.standard_normal((co, ci, 3, 3))
+    Wt = wt.transpose(2, 3, 1, 0).reshape(9, ci, co)               # [tap][ci][co]
+    x = torch.tensor(rng.standard_normal((n, ci, h, w)), requires_grad=True)
+    for stride in (1, 2):
+        y = F.conv2d(x, torch.tensor(wt), None, stride, 1)
+        dy = rng.standard_normal(tuple(y.shape))
+        (gx,) = torch.autograd.grad(y, x, torch.tensor(dy))
+        G = _pad_pixel_major(dy)[None]
+        ho, wo = h // stride, w // stride
+        if stride == 1:
+            shift, phase, bsel = E._taps_s1(w + 2)
+            dx = _interior(n, h, w, ci, _tap_gemm(G, Wt, [-s for s in shift], phase, bsel, G.shape[1]))
+        else:
+            fs, fp, fb = E._taps_s2(wo + 2)
+            dx = np.zeros((n, ci, h, w))
+            for ph in range(4):
+                sh = [-fs[t] for t in range(9) if fp[t] == ph]
+                bs = [fb[t] for t in range(9) if fp[t] == ph]
+                d = _interior(n, ho, wo, ci, _tap_gemm(G, Wt, sh, [0] * len(sh), bs, G.shape[1]))
+                dx[:, :, ph // 2::2, ph % 2::2] = d
+        np.testing.assert_allclose(dx, gx.numpy(), atol=1e-10)
+
+
+def test_generator_channel_layout():
+    """New channels are prepended (code/dmcnet/model.py:186-194): layer k reads a
+    contiguous channel range that ends with mv(2)+res(3)."""
+    outs, off = [], 28
+    for g in E.GEN_GROWTH:
+        off -= g
+        outs.append(off)
+    assert outs == [20, 12, 6, 2, 0]
+    cins = [33 - (o + g) for o, g in zip(outs, E.GEN_GROWTH)]
+    assert cins == [5, 13, 21, 27, 31]
+
+
+def test_disc_block_tables_match_oracle():
+    for a in ('Discriminator', 'Discriminator2', 'Discriminator3', 'Discriminator4', 'Discriminator5'):
+        assert E.disc_blocks(a) == O.disc_blocks(a)
