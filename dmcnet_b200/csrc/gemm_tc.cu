@@ -108,7 +108,7 @@ struct TapGemmSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                 const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
@@ -246,7 +246,7 @@ struct WgradSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
                   const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
@@ -437,8 +437,8 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   if ((rc = make_map_3d(&mBl, B_lo, K, N, b_slices, 64, BN))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 128) return launch_tap_gemm<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
-  if (BN == 64) return launch_tap_gemm<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
-  return launch_tap_gemm<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
+  if (BN == 64) return launch_tap_gemm<64, 2>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
+  return launch_tap_gemm<32, 2>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW)
@@ -462,5 +462,5 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 128)
     return launch_wgrad<128, 3>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
-  return launch_wgrad<64, 4>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
+  return launch_wgrad<64, 2>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
 }
