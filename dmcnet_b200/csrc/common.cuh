@@ -180,6 +180,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  // The base-offset field (bits 49-51) stays 0 even when the start address is only
+  // 128-byte (row) aligned: measured on B200, the MMA unit applies the 128B swizzle to the
+  // ABSOLUTE shared-memory address bits, exactly as TMA wrote them, so a descriptor may
+  // point at any row of a 1024-byte-aligned tile (setting the field corrupts the result).
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }

@@ -129,6 +129,10 @@ def bench_tap(frames, H, C, Cout, reps=5):
     Bh, Bl = split(B)
     D = torch.empty(P, Cout, device='cuda')
     shift = [(r - 1) * Wp + (s - 1) for r in range(3) for s in range(3)]
+    if os.environ.get('ZERO_SHIFT') == '1':
+        shift = [0, 8, 16, 24, 32, 40, 48, 56, 64]       # atom-aligned row offsets
+    if os.environ.get('ZERO_SHIFT') == '2':
+        shift = [0, 1, 2, 3, 4, 5, 6, 7, 9]              # small unaligned window
     kw = dict(a_phases=1, a_rows=P, K=C, b_slices=9, N=Cout, M=P, ldD=Cout, Hp=Hp, Wp=Wp,
               shift=shift, phase=[0] * 9, bsel=list(range(9)))
     for eng in ('tc',):
