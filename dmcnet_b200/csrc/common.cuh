@@ -204,9 +204,22 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int n, int a_mn_major, int b
 // Activations of the classifier live as [frames][Hp][Wp][C] with a one-pixel
 // zero ring (Hp = H+2, Wp = W+2); q is the flat padded pixel index.
 __host__ __device__ inline bool interior(long q, int Hp, int Wp) {
-  int wp = (int)(q % Wp);
-  int hp = (int)((q / Wp) % Hp);
-  return wp >= 1 && wp <= Wp - 2 && hp >= 1 && hp <= Hp - 2;
+  // q < 2^31 for every tensor this library builds: 32-bit unsigned division is ~5x cheaper
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp;
+  const unsigned row = uq / uw;
+  const unsigned wp = uq - row * uw;
+  const unsigned hp = row % uh;
+  return wp >= 1u && wp <= uw - 2u && hp >= 1u && hp <= uh - 2u;
 }
+
+// i -> (i / d, i % d) for 32-bit i; shift/mask when d is a power of two (channel counts)
+struct FastDiv {
+  unsigned d, shift, pow2;
+  __host__ __device__ explicit FastDiv(unsigned d_) : d(d_), shift(0), pow2((d_ & (d_ - 1)) == 0) {
+    while ((1u << shift) < d_) ++shift;
+  }
+  __host__ __device__ inline unsigned div(unsigned i) const { return pow2 ? (i >> shift) : (i / d); }
+  __host__ __device__ inline unsigned mod(unsigned i) const { return pow2 ? (i & (d - 1)) : (i % d); }
+};
 
 }  // namespace dmc

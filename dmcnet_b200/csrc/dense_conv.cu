@@ -278,7 +278,8 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
                       const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                       float* __restrict__ out, long out_ns, float slope,
                       const float* __restrict__ mask, const float* __restrict__ add, long add_ns,
-                      int accumulate, int tiles_x) {
+                      int accumulate, int tiles_x, const float* __restrict__ act_src, long act_ns,
+                      int act_c1, float act_slope) {
   using C = FwdV2Cfg<COG, PX>;
   constexpr int SPR = C::SPR, TH = C::TH, PITCH = C::PITCH, COGP = C::COGP;
   extern __shared__ uint8_t smem_raw[];
@@ -384,6 +385,12 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
           const float4 a = *reinterpret_cast<const float4*>(out + o + q);
           f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
         }
+        if (act_src && co < act_c1) {          // fused LeakyReLU backward on the finished slice
+          const float4 a = *reinterpret_cast<const float4*>(
+              act_src + (long)n * act_ns + ((long)co * H + oy) * W + ox + q);
+          f.x *= a.x > 0.f ? 1.f : act_slope; f.y *= a.y > 0.f ? 1.f : act_slope;
+          f.z *= a.z > 0.f ? 1.f : act_slope; f.w *= a.w > 0.f ? 1.f : act_slope;
+        }
         *reinterpret_cast<float4*>(out + o + q) = f;
       }
     } else {
@@ -391,6 +398,8 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
         float v = r[p];
         if (add) v += add[oa + p];
         if (accumulate) v += out[o + p];
+        if (act_src && co < act_c1)
+          v *= act_src[(long)n * act_ns + ((long)co * H + oy) * W + ox + p] > 0.f ? 1.f : act_slope;
         out[o + p] = v;
       }
     }
@@ -401,7 +410,8 @@ template <int COG, int PX>
 static int launch_fwd_v2(const float* in, long in_ns, int Cin, int H, int W, const float* w,
                          const float* bias, int Cout, float* out, long out_ns, float slope,
                          const float* mask, const float* add, long add_ns, int accumulate, int N,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* act_src = nullptr, long act_ns = 0,
+                         int act_c1 = 0, float act_slope = 1.f) {
   using C = FwdV2Cfg<COG, PX>;
   const int ckb = Cin < C::CK ? Cin : C::CK;
   CUtensorMap map;
@@ -424,7 +434,7 @@ static int launch_fwd_v2(const float* in, long in_ns, int Cin, int H, int W, con
   const int tx32 = (int)cdiv(W, 32);
   dim3 grid(tx32 * (unsigned)cdiv(H, C::TH), (unsigned)cdiv(Cout, COG), N);
   kern<<<grid, 128, smem, st>>>(map, Cin, ckb, H, W, w, bias, Cout, out, out_ns, slope, mask, add,
-                                add_ns, accumulate, tx32);
+                                add_ns, accumulate, tx32, act_src, act_ns, act_c1, act_slope);
   return dmc_check_launch("conv3x3_fwd_v2_kernel");
 }
 
@@ -910,4 +920,25 @@ extern "C" int dmc_weight_flip(const float* w, int Cout, int Cin, int ci_count, 
   const int n = ci_count * Cout * 9;
   weight_flip_kernel<<<(int)cdiv(n, 256), 256, 0, ST_(stream)>>>(w, Cout, Cin, ci_count, wT);
   return dmc_check_launch("weight_flip_kernel");
+}
+
+// 3x3 stride-1 data gradient expressed as a forward convolution of dY with the flipped,
+// transposed weight wT (dmc_weight_flip): dX[n][0:Cx] (+)= conv(dY, wT); output channels
+// [0, act_c1) are then multiplied by LeakyReLU'(act_src) -- the slice of the dense-concat
+// gradient that receives its last contribution here becomes the pre-activation gradient.
+extern "C" int dmc_conv3x3_dgrad_fused(const float* dY, long dy_ns, int Cy, int H, int W,
+                                       const float* wT, int Cx, float* dX, long dx_ns,
+                                       int accumulate, const float* act_src, long act_ns, int act_c1,
+                                       float act_slope, int N, void* stream) {
+  DMC_REQUIRE(W % 4 == 0 && dy_ns % 4 == 0 && dx_ns % 4 == 0 && act_ns % 4 == 0 && (H * W) % 4 == 0,
+              "conv3x3_dgrad_fused: W=%d and strides must be multiples of 4", W);
+  cudaStream_t st = ST_(stream);
+#define DMC_DG(COG, PX)                                                                             \
+  return launch_fwd_v2<COG, PX>(dY, dy_ns, Cy, H, W, wT, nullptr, Cx, dX, dx_ns, 1.f, nullptr, nullptr, \
+                                0, accumulate, N, st, act_src, act_ns, act_c1, act_slope)
+  if (Cx == 2) DMC_DG(2, 8);
+  if (Cx <= 4) DMC_DG(4, 8);
+  if (Cx == 6) DMC_DG(6, 4);
+  DMC_DG(8, 4);
+#undef DMC_DG
 }

@@ -11,8 +11,9 @@
 // Precision: operands are bf16 hi/lo pairs; each k-step issues hi*hi, lo*hi and
 // hi*lo MMAs into one fp32 TMEM accumulator (~2^-16 relative error).
 //
-//   tap_gemm_kernel  : D[P][N]  = sum_t A_ph(t)[q+s_t][K] * B_t[N][K]^T    (fprop, dgrad)
-//                      K-major operands, TMA 3-D tiled loads, 128 x BN tile per CTA.
+//   tap_gemm_ws_kernel: D[P][N] = sum_t A_ph(t)[q+s_t][K] * B_t[N][K]^T    (fprop, dgrad)
+//                      K-major operands, TMA 3-D tiled loads, persistent warp-specialised
+//                      CTAs (128 x BN tiles, two TMEM accumulators).
 //   wgrad_gemm_kernel: dW_t[M][N] += sum_q G[q][M] * A_ph(t)[q+s_t][N]     (split-K, atomics)
 //                      MN-major operands (pixel index is K).
 #include "common.cuh"
@@ -98,143 +99,6 @@ int dmc_make_f32_map(CUtensorMap* m, const void* base, int rank, const unsigned 
 }
 
 namespace dmc {
-
-// ------------------------------------------------------------------ fprop / dgrad
-template <int BN, int STAGES>
-struct TapGemmSmem {
-  static constexpr int A_BYTES = 128 * 128;        // 128 rows x 64 bf16
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(128)
-tap_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
-                const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
-                int K, int Hp, int Wp) {
-  using S = TapGemmSmem<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
-  // barriers: full[s] @ +8s, empty[s] @ +8(STAGES+s), tmem_full @ +16*STAGES, tmem slot after
-  const uint32_t tmem_full = bar_base + 16 * STAGES;
-  const uint32_t tmem_slot = tmem_full + 8;
-  uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long m0 = (long)blockIdx.x * 128;
-  const int n0 = blockIdx.y * BN;
-  const int kblocks = K / 64;
-  const int iters = taps.ntaps * kblocks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, 1);
-      mbar_init(bar_base + 8 * (STAGES + s), 1);
-    }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&mapAh);
-    tma_prefetch_desc(&mapAl);
-    tma_prefetch_desc(&mapBh);
-    tma_prefetch_desc(&mapBl);
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot_ptr;
-
-  if (warp == 0 && lane == 0) {
-    // ---- TMA producer
-    for (int i = 0; i < iters; ++i) {
-      const int s = i % STAGES;
-      if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
-      const int t = i / kblocks, kb = i - t * kblocks;
-      const uint32_t full = bar_base + 8 * s;
-      const uint32_t st = smem_base + s * S::STAGE_BYTES;
-      mbar_expect_tx(full, S::STAGE_BYTES);
-      const int row = (int)(m0 + taps.shift[t]);
-      tma_load_3d(st, &mapAh, full, kb * 64, row, taps.phase[t]);
-      tma_load_3d(st + S::A_BYTES, &mapAl, full, kb * 64, row, taps.phase[t]);
-      tma_load_3d(st + 2 * S::A_BYTES, &mapBh, full, kb * 64, n0, taps.bsel[t]);
-      tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &mapBl, full, kb * 64, n0, taps.bsel[t]);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---- MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
-    for (int i = 0; i < iters; ++i) {
-      const int s = i % STAGES;
-      mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
-      tc_fence_after();
-      const uint32_t st = smem_base + s * S::STAGE_BYTES;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t ah = umma_desc_sw128(st + ks * 32, 16, 1024);
-        const uint64_t al = umma_desc_sw128(st + S::A_BYTES + ks * 32, 16, 1024);
-        const uint64_t bh = umma_desc_sw128(st + 2 * S::A_BYTES + ks * 32, 16, 1024);
-        const uint64_t bl = umma_desc_sw128(st + 2 * S::A_BYTES + S::B_BYTES + ks * 32, 16, 1024);
-        umma_bf16(tmem_d, al, bh, idesc, (i | ks) != 0);
-        umma_bf16(tmem_d, ah, bl, idesc, 1);
-        umma_bf16(tmem_d, ah, bh, idesc, 1);
-      }
-      umma_commit(bar_base + 8 * (STAGES + s));   // frees the smem slot when the MMAs retire
-    }
-    umma_commit(tmem_full);
-  }
-  __syncwarp();
-
-  // ---- epilogue: TMEM -> registers -> global (lane = output row)
-  mbar_wait(tmem_full, 0);
-  tc_fence_after();
-  const long q = m0 + warp * 32 + lane;
-  const bool in_range = q < M;
-  const bool keep = in_range && (Hp == 0 || interior(q, Hp, Wp));
-  float* drow = D + q * (long)ldD + n0;
-#pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c, r);
-    tmem_ld_wait();
-    if (in_range) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (n0 + c + j < N) {
-          float4 v;
-          v.x = keep ? __uint_as_float(r[j + 0]) : 0.f;
-          v.y = keep ? __uint_as_float(r[j + 1]) : 0.f;
-          v.z = keep ? __uint_as_float(r[j + 2]) : 0.f;
-          v.w = keep ? __uint_as_float(r[j + 3]) : 0.f;
-          *reinterpret_cast<float4*>(drow + c + j) = v;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
-}
-
-template <int BN, int STAGES>
-static int launch_tap_gemm(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
-                           const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
-                           int ldD, int K, int Hp, int Wp, cudaStream_t stream) {
-  using S = TapGemmSmem<BN, STAGES>;
-  auto kern = tap_gemm_kernel<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
-        cudaSuccess)
-      return dmc_check_launch("tap_gemm smem attribute");
-    attr_set = true;
-  }
-  dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, BN));
-  kern<<<grid, 128, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp);
-  return dmc_check_launch("tap_gemm_kernel");
-}
 
 static int sm_count();
 
@@ -420,277 +284,6 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
                                                   tiles_m, tiles_n);
   return dmc_check_launch("tap_gemm_ws_kernel");
-}
-
-// ------------------------------------------------------------------ window kernel (operand reuse across taps)
-// The nine taps of a 3x3 convolution read row-shifted views of the SAME
-// activation rows.  Instead of nine 128-row TMA loads per k-block, this kernel
-// loads ONE window of 128 + (max shift - min shift) rows per (phase group,
-// k-block) and points the UMMA A descriptor at row offset (shift - min shift)
-// inside it (SWIZZLE_128B rows are 128 B, so a row offset is a plain address
-// offset plus the descriptor's base-offset field).  A traffic drops from 9 tiles
-// to ~1.9 (56x56) .. 1.2 (7x7) tiles per k-block; weights stream through their
-// own ring.  Same persistent warp-specialised skeleton as tap_gemm_ws_kernel.
-struct WinGroups {
-  int ngroups;
-  int phase[4];
-  int win_lo[4];      // smallest shift of the group (window start = m0 + win_lo)
-  int t_begin[5];     // taps of group g are [t_begin[g], t_begin[g+1]) in the sorted table below
-  int shift[MAX_TAPS];
-  int bsel[MAX_TAPS];
-};
-
-template <int BN>
-struct TapGemmWinSmem {
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int BSTAGE_BYTES = 2 * B_BYTES;
-  static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
-  static int win_bytes(int win_rows) { return ((win_rows * 128 + 1023) / 1024) * 1024; }   // one plane
-  static int total(int win_rows, int bstages) {
-    return 2 * 2 * win_bytes(win_rows) + bstages * BSTAGE_BYTES + EPI_BYTES + 1024 + 256;
-  }
-};
-
-template <int BN>
-__global__ void __launch_bounds__(224, 1)
-tap_gemm_win_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
-                    const __grid_constant__ WinGroups grp, float* __restrict__ D, long M, int N, int ldD,
-                    int K, int Hp, int Wp, int tiles_m, int tiles_n, int win_rows, int bstages) {
-  using S = TapGemmWinSmem<BN>;
-  constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t wplane = (uint32_t)(((win_rows * 128 + 1023) / 1024) * 1024);
-  const uint32_t win_base = smem_base;                                  // [2 stages][hi, lo]
-  const uint32_t b_base = smem_base + 4 * wplane;                       // [bstages][hi, lo]
-  float* epi = reinterpret_cast<float*>(smem_gen + 4 * wplane + bstages * S::BSTAGE_BYTES);
-  const uint32_t bar_base = b_base + bstages * S::BSTAGE_BYTES + S::EPI_BYTES;
-  const uint32_t bar_afull = bar_base, bar_aempty = bar_base + 16;
-  const uint32_t bar_bfull = bar_base + 32, bar_bempty = bar_bfull + 8 * 8;   // up to 8 B stages
-  const uint32_t bar_tfull = bar_bempty + 8 * 8, bar_tempty = bar_tfull + 16;
-  const uint32_t tmem_slot = bar_tempty + 16;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = K / 64;
-  const int total_tiles = tiles_m * tiles_n;
-  const uint32_t win_tx = (uint32_t)(2 * win_rows * 128);
-
-  if (threadIdx.x == 0) {
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_afull + 8 * a, 1);
-      mbar_init(bar_aempty + 8 * a, 1);
-      mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
-    }
-    for (int s = 0; s < bstages; ++s) {
-      mbar_init(bar_bfull + 8 * s, 1);
-      mbar_init(bar_bempty + 8 * s, 1);
-    }
-    fence_barrier_init();
-    tma_prefetch_desc(&mapAh);
-    tma_prefetch_desc(&mapAl);
-    tma_prefetch_desc(&mapBh);
-    tma_prefetch_desc(&mapBl);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {                                  // ---- activation-window producer
-      uint32_t wa = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long m0 = (long)(tile % tiles_m) * 128;
-        for (int g = 0; g < grp.ngroups; ++g) {
-          for (int kb = 0; kb < kblocks; ++kb, ++wa) {
-            const uint32_t a = wa & 1, aph = (wa >> 1) & 1;
-            mbar_wait(bar_aempty + 8 * a, aph ^ 1);
-            const uint32_t af = bar_afull + 8 * a;
-            mbar_expect_tx(af, win_tx);
-            const int row = (int)(m0 + grp.win_lo[g]);
-            tma_load_3d(win_base + (2 * a) * wplane, &mapAh, af, kb * 64, row, grp.phase[g]);
-            tma_load_3d(win_base + (2 * a + 1) * wplane, &mapAl, af, kb * 64, row, grp.phase[g]);
-          }
-        }
-      }
-    }
-  } else if (warp == 6) {
-    if (lane == 0) {                                  // ---- weight-tile producer
-      uint32_t bi = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile / tiles_m) * BN;
-        for (int g = 0; g < grp.ngroups; ++g) {
-          for (int kb = 0; kb < kblocks; ++kb) {
-            for (int t = grp.t_begin[g]; t < grp.t_begin[g + 1]; ++t, ++bi) {
-              const uint32_t s = bi % bstages, ph = (bi / bstages) & 1;
-              mbar_wait(bar_bempty + 8 * s, ph ^ 1);
-              const uint32_t bf = bar_bfull + 8 * s;
-              mbar_expect_tx(bf, S::BSTAGE_BYTES);
-              const uint32_t st = b_base + s * S::BSTAGE_BYTES;
-              tma_load_3d(st, &mapBh, bf, kb * 64, n0, grp.bsel[t]);
-              tma_load_3d(st + S::B_BYTES, &mapBl, bf, kb * 64, n0, grp.bsel[t]);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
-      uint32_t wa = 0, bi = 0, j = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-        const uint32_t acs = j & 1, acph = (j >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acs, acph ^ 1);
-        tc_fence_after();
-        const uint32_t acc = tmem_d + acs * BN;
-        uint32_t first = 1;
-        for (int g = 0; g < grp.ngroups; ++g) {
-          for (int kb = 0; kb < kblocks; ++kb, ++wa) {
-            const uint32_t a = wa & 1, aph = (wa >> 1) & 1;
-            mbar_wait(bar_afull + 8 * a, aph);
-            tc_fence_after();
-            const uint32_t wh = win_base + (2 * a) * wplane, wl = wh + wplane;
-            for (int t = grp.t_begin[g]; t < grp.t_begin[g + 1]; ++t, ++bi) {
-              const uint32_t s = bi % bstages, ph = (bi / bstages) & 1;
-              mbar_wait(bar_bfull + 8 * s, ph);
-              tc_fence_after();
-              const uint32_t st = b_base + s * S::BSTAGE_BYTES;
-              const uint32_t roff = (uint32_t)(grp.shift[t] - grp.win_lo[g]) * 128u;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ah = umma_desc_sw128(wh + roff + ks * 32, 16, 1024);
-                const uint64_t al = umma_desc_sw128(wl + roff + ks * 32, 16, 1024);
-                const uint64_t bh = umma_desc_sw128(st + ks * 32, 16, 1024);
-                const uint64_t bl = umma_desc_sw128(st + S::B_BYTES + ks * 32, 16, 1024);
-                umma_bf16(acc, al, bh, idesc, first ? 0u : 1u);
-                first = 0;
-                umma_bf16(acc, ah, bl, idesc, 1);
-                umma_bf16(acc, ah, bh, idesc, 1);
-              }
-              umma_commit(bar_bempty + 8 * s);
-            }
-            umma_commit(bar_aempty + 8 * a);
-          }
-        }
-        umma_commit(bar_tfull + 8 * acs);
-      }
-    }
-  } else {                                            // ---- epilogue warps 2..5
-    const int wq = warp & 3;
-    float* stage = epi + wq * 32 * S::EPI_PITCH;
-    uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-      const long m0 = (long)(tile % tiles_m) * 128;
-      const int n0 = (tile / tiles_m) * BN;
-      const uint32_t a = j & 1, aph = (j >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * a, aph);
-      tc_fence_after();
-      const long q = m0 + wq * 32 + lane;
-      const bool keep = q < M && (Hp == 0 || interior(q, Hp, Wp));
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_d + a * BN + ((uint32_t)(wq * 32) << 16) + c, r);
-        tmem_ld_wait();
-        if (c + 32 >= BN) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float4 v;
-          v.x = keep ? __uint_as_float(r[4 * g + 0]) : 0.f;
-          v.y = keep ? __uint_as_float(r[4 * g + 1]) : 0.f;
-          v.z = keep ? __uint_as_float(r[4 * g + 2]) : 0.f;
-          v.w = keep ? __uint_as_float(r[4 * g + 3]) : 0.f;
-          *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
-        }
-        __syncwarp();
-        if (n0 + c < N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
-            const long gq = m0 + wq * 32 + row;
-            if (gq < M) {
-              const float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
-              *reinterpret_cast<float4*>(D + gq * (long)ldD + n0 + c + c4) = v;
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
-// Groups the taps by A phase and computes each group's window.  Returns the window
-// height in rows (128 + largest shift span) or -1 when the table has too many phases.
-static int build_groups(WinGroups& g, int ntaps, const int* shift, const int* phase, const int* bsel) {
-  g.ngroups = 0;
-  int pos = 0, span = 0;
-  bool used[MAX_TAPS] = {false};
-  for (int i = 0; i < ntaps; ++i) {
-    if (used[i]) continue;
-    if (g.ngroups == 4) return -1;
-    const int gi = g.ngroups++;
-    g.phase[gi] = phase[i];
-    g.t_begin[gi] = pos;
-    int lo = shift[i], hi = shift[i];
-    for (int j = i; j < ntaps; ++j) {
-      if (used[j] || phase[j] != phase[i]) continue;
-      used[j] = true;
-      g.shift[pos] = shift[j];
-      g.bsel[pos] = bsel[j];
-      ++pos;
-      lo = shift[j] < lo ? shift[j] : lo;
-      hi = shift[j] > hi ? shift[j] : hi;
-    }
-    g.win_lo[gi] = lo;
-    span = (hi - lo) > span ? (hi - lo) : span;
-  }
-  for (int gi = g.ngroups; gi <= 4; ++gi) g.t_begin[gi] = pos;
-  for (int gi = g.ngroups; gi < 4; ++gi) { g.phase[gi] = 0; g.win_lo[gi] = 0; }
-  for (int i = pos; i < MAX_TAPS; ++i) { g.shift[i] = 0; g.bsel[i] = 0; }
-  return 128 + span;
-}
-
-template <int BN>
-static int launch_tap_gemm_win(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
-                               const CUtensorMap& mBh, const CUtensorMap& mBl, const WinGroups& grp,
-                               int win_rows, float* D, long M, int N, int ldD, int Hp, int Wp, int sms,
-                               cudaStream_t stream) {
-  using S = TapGemmWinSmem<BN>;
-  int bstages = 4;
-  while (bstages > 2 && S::total(win_rows, bstages) > 227 * 1024) --bstages;
-  if (S::total(win_rows, bstages) > 227 * 1024) return 1;          // caller falls back
-  CUtensorMap mAh, mAl;
-  int rc;
-  if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, win_rows))) return rc;
-  if ((rc = make_map_3d(&mAl, A_lo, K, a_rows, a_phases, 64, win_rows))) return rc;
-  auto kern = tap_gemm_win_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
-      return dmc_check_launch("tap_gemm_win smem attribute");
-    attr_set = true;
-  }
-  const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(N, BN);
-  long grid = (long)tiles_m * tiles_n;
-  if (grid > sms) grid = sms;
-  kern<<<(unsigned)grid, 224, S::total(win_rows, bstages), stream>>>(
-      mAh, mAl, mBh, mBl, grp, D, M, N, ldD, K, Hp, Wp, tiles_m, tiles_n, win_rows, bstages);
-  return dmc_check_launch("tap_gemm_win_kernel");
 }
 
 // ------------------------------------------------------------------ wgrad (split-K)
@@ -894,23 +487,7 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   if ((rc = make_map_3d(&mBh, B_hi, K, N, b_slices, 64, BN))) return rc;
   if ((rc = make_map_3d(&mBl, B_lo, K, N, b_slices, 64, BN))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const bool legacy = getenv("DMC_GEMM_LEGACY") != nullptr;   // debug aid: non-persistent kernel
-  if (legacy) {
-    if (BN == 128) return launch_tap_gemm<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
-    if (BN == 64) return launch_tap_gemm<64, 2>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
-    return launch_tap_gemm<32, 2>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, st);
-  }
   const int sms = sm_count();
-  static const bool no_window = getenv("DMC_GEMM_NO_WINDOW") != nullptr;   // debug aid
-  WinGroups grp;
-  const int win_rows = build_groups(grp, ntaps, shift, phase, bsel);
-  if (!no_window && win_rows > 128 && win_rows <= 256 && BN >= 64) {
-    int wrc = BN == 128 ? launch_tap_gemm_win<128>(A_hi, A_lo, a_phases, a_rows, K, mBh, mBl, grp,
-                                                   win_rows, D, M, N, ldD, Hp, Wp, sms, st)
-                        : launch_tap_gemm_win<64>(A_hi, A_lo, a_phases, a_rows, K, mBh, mBl, grp,
-                                                  win_rows, D, M, N, ldD, Hp, Wp, sms, st);
-    if (wrc <= 0) return wrc;          // 0 = launched, <0 = error, 1 = does not fit -> fall through
-  }
   if (BN == 128)
     return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, st);
   if (BN == 64)

@@ -85,19 +85,25 @@ __device__ __forceinline__ void channel_reduce2(long P, int C, double* __restric
   const int r = threadIdx.x / c4n;
   float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   double d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0};
+  const unsigned step = gridDim.x * rows_per_iter;
+  const unsigned uP = (unsigned)P;
+  unsigned q = blockIdx.x * rows_per_iter + r;
   int n = 0;
-  if (r < rows_per_iter) {
-    for (long q = (long)blockIdx.x * rows_per_iter + r; q < P; q += (long)gridDim.x * rows_per_iter) {
-      f(q, c4 * 4, s0, s1);
-      if (++n == 64) {   // flush fp32 partials to double regularly
+  // four independent rows per trip keep enough loads in flight to stream HBM
+  for (; q + 3u * step < uP; q += 4u * step) {
+    f(q, c4 * 4, s0, s1);
+    f(q + step, c4 * 4, s0, s1);
+    f(q + 2u * step, c4 * 4, s0, s1);
+    f(q + 3u * step, c4 * 4, s0, s1);
+    if (++n == 16) {                           // flush fp32 partials to double regularly
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          d0[i] += s0[i]; d1[i] += s1[i]; s0[i] = 0.f; s1[i] = 0.f;
-        }
-        n = 0;
+      for (int i = 0; i < 4; ++i) {
+        d0[i] += s0[i]; d1[i] += s1[i]; s0[i] = 0.f; s1[i] = 0.f;
       }
+      n = 0;
     }
   }
+  for (; q < uP; q += step) f(q, c4 * 4, s0, s1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; }
   extern __shared__ double red[];              // [2][blockDim.x][4]
@@ -126,10 +132,10 @@ __device__ __forceinline__ void channel_reduce2(long P, int C, double* __restric
 }
 
 // sums[0][c] = sum_q Y[q][c], sums[1][c] = sum_q Y[q][c]^2  (border rows are zero).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_stats_kernel(const float* __restrict__ Y, long P, int C, double* __restrict__ sums) {
-  channel_reduce2(P, C, sums, sums + C, [&](long q, int c, float (&s0)[4], float (&s1)[4]) {
-    const float4 v = *reinterpret_cast<const float4*>(Y + q * C + c);
+  channel_reduce2(P, C, sums, sums + C, [&](unsigned q, int c, float (&s0)[4], float (&s1)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(Y + (long)q * C + c);
     s0[0] += v.x; s0[1] += v.y; s0[2] += v.z; s0[3] += v.w;
     s1[0] += v.x * v.x; s1[1] += v.y * v.y; s1[2] += v.z * v.z; s1[3] += v.w * v.w;
   });
@@ -185,12 +191,12 @@ bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
                 const float* __restrict__ resY, const float* __restrict__ res_scale,
                 const float* __restrict__ res_shift, bf16* __restrict__ out_hi,
                 bf16* __restrict__ out_lo) {
-  const int c4n = C / 4;
-  const long n = P * c4n;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const long q = i / c4n;
-    const int c = (int)(i % c4n) * 4;
-    const long off = q * C + c;
+  const FastDiv fd((unsigned)(C / 4));
+  const unsigned n = (unsigned)(P * (C / 4));
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned q = fd.div(i);
+    const int c = (int)fd.mod(i) * 4;
+    const long off = (long)q * C + c;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (interior(q, Hp, Wp)) {
       const float4 y = *reinterpret_cast<const float4*>(Y + off);
@@ -237,14 +243,14 @@ __device__ __forceinline__ void load_dz(const float* g_a, const float* g_b, cons
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b,
                      const bf16* __restrict__ act_hi, const float* __restrict__ Y,
                      const float* __restrict__ mean, const float* __restrict__ invstd, long P, int C,
                      int Hp, int Wp, double* __restrict__ sums2) {
-  channel_reduce2(P, C, sums2, sums2 + C, [&](long q, int c, float (&s0)[4], float (&s1)[4]) {
+  channel_reduce2(P, C, sums2, sums2 + C, [&](unsigned q, int c, float (&s0)[4], float (&s1)[4]) {
     if (!interior(q, Hp, Wp)) return;
-    const long off = q * C + c;
+    const long off = (long)q * C + c;
     float dz[4];
     load_dz(g_a, g_b, act_hi, off, dz);
     const float4 y = *reinterpret_cast<const float4*>(Y + off);
@@ -266,33 +272,44 @@ bn_bwd_apply_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b
                     const float* __restrict__ gamma, const double* __restrict__ sums2, double count,
                     long P, int C, int Hp, int Wp, bf16* __restrict__ G_hi, bf16* __restrict__ G_lo,
                     float* __restrict__ dz_out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  // dY = A*dz + B*y + K per channel:  A = gamma*invstd, B = -A*invstd*mean(dz*xhat),
+  // K = -A*mean(dz) - B*mean
+  extern __shared__ __align__(16) float coef[];            // [3][C]
+  float* cA = coef;
+  float* cB = coef + C;
+  float* cK = coef + 2 * C;
+  const double inv_count = 1.0 / count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = gamma[c] * invstd[c];
+    const float m1 = (float)(sums2[c] * inv_count), m2 = (float)(sums2[C + c] * inv_count);
+    const float b = -a * invstd[c] * m2;
+    cA[c] = a;
+    cB[c] = b;
+    cK[c] = -a * m1 - b * mean[c];
+    if (blockIdx.x == 0 && dgamma) {
       dbeta[c] = (float)sums2[c];
       dgamma[c] = (float)sums2[C + c];
     }
   }
-  const int c4n = C / 4;
-  const long n = P * c4n;
-  const float inv_count = (float)(1.0 / count);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const long q = i / c4n;
-    const int c = (int)(i % c4n) * 4;
-    const long off = q * C + c;
+  __syncthreads();
+  const FastDiv fd((unsigned)(C / 4));
+  const unsigned n = (unsigned)(P * (C / 4));
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned q = fd.div(i);
+    const int c = (int)fd.mod(i) * 4;
+    const long off = (long)q * C + c;
     float dy[4] = {0.f, 0.f, 0.f, 0.f};
     float dz[4] = {0.f, 0.f, 0.f, 0.f};
     if (interior(q, Hp, Wp)) {
       load_dz(g_a, g_b, act_hi, off, dz);
       const float4 y = *reinterpret_cast<const float4*>(Y + off);
-      const float yv[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float is = invstd[c + k];
-        const float xhat = (yv[k] - mean[c + k]) * is;
-        const float m1 = (float)sums2[c + k] * inv_count;
-        const float m2 = (float)sums2[C + c + k] * inv_count;
-        dy[k] = gamma[c + k] * is * (dz[k] - m1 - xhat * m2);
-      }
+      const float4 a = *reinterpret_cast<const float4*>(cA + c);
+      const float4 b = *reinterpret_cast<const float4*>(cB + c);
+      const float4 k = *reinterpret_cast<const float4*>(cK + c);
+      dy[0] = fmaf(a.x, dz[0], fmaf(b.x, y.x, k.x));
+      dy[1] = fmaf(a.y, dz[1], fmaf(b.y, y.y, k.y));
+      dy[2] = fmaf(a.z, dz[2], fmaf(b.z, y.z, k.z));
+      dy[3] = fmaf(a.w, dz[3], fmaf(b.w, y.w, k.w));
     }
     store_split4(G_hi, G_lo, off, dy);
     if (dz_out) *reinterpret_cast<float4*>(dz_out + off) = make_float4(dz[0], dz[1], dz[2], dz[3]);
@@ -383,11 +400,11 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dpooled, int frames
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ X, long P, int C, int Hp, int Wp,
                     bf16* __restrict__ hi, bf16* __restrict__ lo) {
-  const int c4n = C / 4;
-  const long n = P * c4n;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const long q = i / c4n;
-    const long off = q * C + (i % c4n) * 4;
+  const FastDiv fd((unsigned)(C / 4));
+  const unsigned n = (unsigned)(P * (C / 4));
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned q = fd.div(i);
+    const long off = (long)q * C + fd.mod(i) * 4;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (Hp == 0 || interior(q, Hp, Wp)) {
       const float4 v = *reinterpret_cast<const float4*>(X + off);
@@ -439,8 +456,8 @@ extern "C" int dmc_bn_stats(const float* Y, long P, int C, double* sums, void* s
     return dmc_check_launch("bn_stats memset");
   const int threads = reduce_block(C);
   const int rows = threads / (C / 4);
-  int blocks = (int)cdiv(P, (long)rows * 32);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int blocks = (int)cdiv(P, (long)rows * 16);
+  if (blocks > 148 * 4) blocks = 148 * 4;      // 4 resident blocks per SM: the kernel is latency-bound
   if (blocks < 1) blocks = 1;
   bn_stats_kernel<<<blocks, threads, sizeof(double) * 8 * threads, ST(stream)>>>(Y, P, C, sums);
   return dmc_check_launch("bn_stats_kernel");
@@ -484,8 +501,8 @@ extern "C" int dmc_bn_bwd_reduce(const float* g_a, const float* g_b, const void*
     return dmc_check_launch("bn_bwd_reduce memset");
   const int threads = reduce_block(C);
   const int rows = threads / (C / 4);
-  int blocks = (int)cdiv(P, (long)rows * 32);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int blocks = (int)cdiv(P, (long)rows * 16);
+  if (blocks > 148 * 4) blocks = 148 * 4;      // 4 resident blocks per SM: the kernel is latency-bound
   if (blocks < 1) blocks = 1;
   bn_bwd_reduce_kernel<<<blocks, threads, sizeof(double) * 8 * threads, ST(stream)>>>(
       g_a, g_b, (const bf16*)act_hi, Y, mean, invstd, P, C, Hp, Wp, sums2);
@@ -498,7 +515,7 @@ extern "C" int dmc_bn_bwd_apply(const float* g_a, const float* g_b, const void* 
                                 int Hp, int Wp, void* G_hi, void* G_lo, float* dz_out, float* dgamma,
                                 float* dbeta, void* stream) {
   DMC_REQUIRE(C % 4 == 0, "bn_bwd_apply: C=%d", C);
-  bn_bwd_apply_kernel<<<grid_for(P * (C / 4), 256), 256, 0, ST(stream)>>>(
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 4), 256), 256, 3 * C * sizeof(float), ST(stream)>>>(
       g_a, g_b, (const bf16*)act_hi, Y, mean, invstd, gamma, sums2, count, P, C, Hp, Wp, (bf16*)G_hi,
       (bf16*)G_lo, dz_out, dgamma, dbeta);
   return dmc_check_launch("bn_bwd_apply_kernel");

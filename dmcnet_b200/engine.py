@@ -371,25 +371,34 @@ class DmcEngine:
         dG = self.d_gen_flow.view(-1)
         wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
         ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dG, 2 * HW, 2, 3, 1, self.g(wk), self.g(bk), n)
-        self._dgrad_s1(dG, 2 * HW, 2, wk, self.gen_ctot, ngen, dX, dns, H, W, n, False)
+        # Each dgrad writes channels [io, 28) of dX; the FIRST slice it writes (the previous
+        # layer's outputs) receives its last contribution there, so LeakyReLU(0.1)' is fused
+        # into that launch and the slice leaves as the pre-activation gradient.
+        self._dgrad_s1(dG, 2 * HW, 2, wk, self.gen_ctot, ngen, dX, dns, H, W, n, False,
+                       act=(X, ns, GEN_GROWTH[-1], 0.1))
         for k in reversed(range(len(GEN_GROWTH))):
             g = GEN_GROWTH[k]
             oo, io = self.gen_out_off[k], self.gen_in_off[k]
             cin = self.gen_ctot - io
             wk, bk = 'gen_flow_model.conv_%d.0.weight' % k, 'gen_flow_model.conv_%d.0.bias' % k
-            # LeakyReLU(0.1) backward in place on this layer's slice of dX
-            ops.act_bwd_planar(dX[oo * HW:], dns, X[oo * HW:], ns, None, 0.1, g, HW, n, dX[oo * HW:], dns)
             ops.conv_wgrad(X[io * HW:], ns, cin, H, W, dX[oo * HW:], dns, g, 3, 1, self.g(wk),
                            self.g(bk), n)
             if ngen - io > 0:
-                self._dgrad_s1(dX[oo * HW:], dns, g, wk, cin, ngen - io, dX[io * HW:], dns, H, W, n, True)
+                self._dgrad_s1(dX[oo * HW:], dns, g, wk, cin, ngen - io, dX[io * HW:], dns, H, W, n, True,
+                               act=(X[io * HW:], ns, GEN_GROWTH[k - 1], 0.1))
 
-    def _dgrad_s1(self, dY, dy_ns, cout, wkey, cin, ci_count, dX, dx_ns, H, W, n, accumulate):
-        """3x3 stride-1 data gradient = forward convolution of dY with the flipped, transposed weight."""
+    def _dgrad_s1(self, dY, dy_ns, cout, wkey, cin, ci_count, dX, dx_ns, H, W, n, accumulate, act=None):
+        """3x3 stride-1 data gradient = forward convolution of dY with the flipped, transposed weight;
+        act = (tensor, stride, channels, slope) fuses LeakyReLU' on the first `channels` outputs."""
         wT = self.wflip[:ci_count * cout * 9]
         ops.weight_flip(self.p(wkey), cout, cin, ci_count, wT)
-        ops.conv_fwd(dY, dy_ns, cout, H, W, wT, None, ci_count, 3, 1, dX, dx_ns, n, slope=1.0,
-                     accumulate=accumulate)
+        if act is None:          # plain path (also covers widths that are not multiples of 4)
+            ops.conv_fwd(dY, dy_ns, cout, H, W, wT, None, ci_count, 3, 1, dX, dx_ns, n, slope=1.0,
+                         accumulate=accumulate)
+            return
+        a_src, a_ns, a_c1, a_slope = act
+        ops.conv3x3_dgrad_fused(dY, dy_ns, cout, H, W, wT, ci_count, dX, dx_ns, n, accumulate=accumulate,
+                                act_src=a_src, act_ns=a_ns, act_c1=a_c1, act_slope=a_slope)
 
     # ------------------------------------------------------------------ classifier
     def _prep_weights(self):

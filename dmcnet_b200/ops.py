@@ -196,6 +196,13 @@ def weight_flip(w, Cout, Cin, ci_count, wT):
           _stream())
 
 
+def conv3x3_dgrad_fused(dY, dy_ns, Cy, H, W, wT, Cx, dX, dx_ns, N, accumulate=False, act_src=None,
+                        act_ns=0, act_c1=0, act_slope=1.0):
+    _call('dmc_conv3x3_dgrad_fused', _ptr(dY, F32), c_long(dy_ns), c_int(Cy), c_int(H), c_int(W),
+          _ptr(wT, F32), c_int(Cx), _ptr(dX, F32), c_long(dx_ns), c_int(1 if accumulate else 0),
+          _ptr(act_src, F32), c_long(act_ns), c_int(act_c1), c_float(act_slope), c_int(N), _stream())
+
+
 def conv_wgrad(inp, in_ns, Cin, H, W, dY, dy_ns, Cout, ks, stride, dW, dbias, N):
     _call('dmc_conv_wgrad', _ptr(inp, F32), c_long(in_ns), c_int(Cin), c_int(H), c_int(W),
           _ptr(dY, F32), c_long(dy_ns), c_int(Cout), c_int(ks), c_int(stride), _ptr(dW, F32),
