@@ -76,7 +76,7 @@ def allreduce_groups(flat: torch.Tensor, group_range: Dict[str, Tuple[int, int]]
 
 class FusedTrainStep:
     def __init__(self, engine: DmcEngine, hp: HParams, batch: int, *, world_size: int = 1,
-                 process_group=None, use_graph: bool = False):
+                 process_group=None, use_graph: bool = False, pipelined: bool = False):
         self.eng, self.hp, self.B = engine, hp, batch
         self.S = hp.num_segments
         if batch * self.S != engine.N:
@@ -105,6 +105,20 @@ class FusedTrainStep:
         self.set_epoch(0, epoch_thre=0)
         self._graphs: Dict[str, object] = {}
         self.launches_per_step = 0
+        # pipelined input staging: H2D of batch k+1 overlaps the compute of batch k
+        self.pipelined = pipelined
+        if pipelined:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            mk = lambda t: [torch.zeros_like(t) for _ in range(2)]
+            self._stg = {'flow': mk(self.in_flow), 'mv': mk(self.in_mv), 'res': mk(self.in_res),
+                         'target': mk(self.target)}
+            self._ev_h2d = [torch.cuda.Event() for _ in range(2)]
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]
+            self._ev_done = [torch.cuda.Event() for _ in range(2)]
+            self._host_stats = [torch.zeros(16, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._dev_stats = torch.zeros(16, dtype=torch.float64, device=dev)
+            self._pending = None          # (slot, mode) of the step whose metrics are still in flight
+            self._k = 0
 
     # ------------------------------------------------------------------ optimizer tables
     def _build_adam_tables(self):
@@ -273,19 +287,76 @@ class FusedTrainStep:
         self.iteration += 1
         return self.read_metrics(mode) if metrics else {}
 
+    # ------------------------------------------------------------------ pipelined API
+    def step_pipelined(self, input_flow, input_mv, input_residual, target,
+                       masks: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, float]:
+        """Same work as ``step`` but asynchronous: the host->device copy of THIS batch runs on a
+        copy stream and the call returns the metrics of the PREVIOUS step (``{}`` on the first
+        call; ``flush()`` returns the last), so the next batch's copy overlaps this step's
+        compute.  Host tensors should be pinned."""
+        if not self.pipelined:
+            raise RuntimeError('construct FusedTrainStep(..., pipelined=True)')
+        eng, H, W = self.eng, self.eng.H, self.eng.W
+        s = self._k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_free[s])
+            self._stg['flow'][s].copy_(input_flow.reshape(-1, 2, H, W), non_blocking=True)
+            self._stg['mv'][s].copy_(input_mv.reshape(-1, 2, H, W), non_blocking=True)
+            self._stg['res'][s].copy_(input_residual.reshape(-1, 3, H, W), non_blocking=True)
+            self._stg['target'][s].copy_(target, non_blocking=True)
+            self._ev_h2d[s].record(self._copy_stream)
+        main.wait_event(self._ev_h2d[s])
+        self.in_flow.copy_(self._stg['flow'][s], non_blocking=True)
+        self.in_mv.copy_(self._stg['mv'][s], non_blocking=True)
+        self.in_res.copy_(self._stg['res'][s], non_blocking=True)
+        self.target.copy_(self._stg['target'][s], non_blocking=True)
+        self._ev_free[s].record(main)
+        mode = self._mode()
+        if eng.gan:
+            m = 2 * eng.N if mode == 'D' else eng.N
+            eng.set_masks(masks if masks is not None else eng.draw_dropout_masks(m), m)
+        self._run(mode, True)
+        self.iteration += 1
+        # stats -> pinned host memory, asynchronously
+        self._dev_stats[0:4].copy_(self.ce_stats)
+        self._dev_stats[4:8].copy_(self.adv_stats)
+        self._dev_stats[8:9].copy_(self.mse_sum)
+        self._host_stats[s].copy_(self._dev_stats, non_blocking=True)
+        self._ev_done[s].record(main)
+        prev, self._pending = self._pending, (s, mode)
+        self._k += 1
+        return self._collect(prev) if prev is not None else {}
+
+    def flush(self) -> Dict[str, float]:
+        """Metrics of the last pipelined step (blocks until it finished)."""
+        prev, self._pending = self._pending, None
+        return self._collect(prev) if prev is not None else {}
+
+    def _collect(self, pending) -> Dict[str, float]:
+        s, mode = pending
+        self._ev_done[s].synchronize()
+        h = self._host_stats[s]
+        return self._metrics_from(mode, [float(h[i]) for i in range(0, 4)], float(h[8]),
+                                  [float(h[i]) for i in range(4, 8)])
+
     def read_metrics(self, mode: str) -> Dict[str, float]:
         """One small device->host read (the reference does five .data[0] syncs, train.py:251-255)."""
+        ce = self.ce_stats.cpu().tolist()
+        mse = float(self.mse_sum.cpu()[0]) if mode in ('full', 'freeze', 'G') else 0.0
+        adv = self.adv_stats.cpu().tolist() if mode in ('D', 'G') else [0.0] * 4
+        return self._metrics_from(mode, ce, mse, adv)
+
+    def _metrics_from(self, mode: str, ce, mse_sum: float, adv) -> Dict[str, float]:
         eng, hp, B = self.eng, self.hp, self.B
         n = B * self.S
-        ce = self.ce_stats.cpu()
         out = {'loss_cls': float(ce[0]) / B, 'prec1': float(ce[1]) * 100.0 / B,
                'prec5': float(ce[2]) * 100.0 / B}
         loss = out['loss_cls'] * hp.lr_cls
         if mode in ('full', 'freeze', 'G'):
-            out['loss_mse'] = float(self.mse_sum.cpu()[0]) / float(n * 2 * eng.H * eng.W)
+            out['loss_mse'] = mse_sum / float(n * 2 * eng.H * eng.W)
             loss += out['loss_mse'] * hp.lr_mse
         if mode in ('D', 'G'):
-            adv = self.adv_stats.cpu()
             m = 2 * n if mode == 'D' else n
             out['loss_adv'] = float(adv[0]) / m
             out['acc_adv'] = float(adv[1]) * 100.0 / m

@@ -230,3 +230,26 @@ def test_full_size_properties_b64():
         torch.cuda.empty_cache()
     assert outs[False][0] == pytest.approx(outs[True][0], rel=1e-5)
     assert rel2(outs[True][1], outs[False][1]) < 1e-4       # atomics order differs; same maths
+
+
+def test_pipelined_step_matches_blocking_step():
+    """step_pipelined (async H2D on a copy stream, metrics one step late) == step."""
+    sd = O.build_state(51, None, seed=1)
+    batches = [O.make_inputs(1, 3, 51, seed=s) for s in range(3)]
+    res = {}
+    for pipelined in (False, True):
+        eng = DmcEngine(51, 3, 3)
+        eng.load_state(sd)
+        tr = FusedTrainStep(eng, HParams(), 1, pipelined=pipelined)
+        ms = []
+        for flow, mv, r, t in batches:
+            args = (flow.pin_memory(), mv.pin_memory(), r.pin_memory(), t.pin_memory())
+            ms.append(tr.step_pipelined(*args) if pipelined else tr.step(*args))
+        if pipelined:
+            assert ms[0] == {}
+            ms = ms[1:] + [tr.flush()]
+        res[pipelined] = (ms, eng.params.clone())
+    for a, b in zip(res[False][0], res[True][0]):
+        for k in a:
+            assert b[k] == pytest.approx(a[k], rel=1e-5, abs=1e-7), k
+    assert rel2(res[True][1], res[False][1]) < 1e-4
