@@ -150,7 +150,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     cfg = CONFIGS[args.config]
     B, S, H, W = args.batch, 3, 224, 224
     per = 2 if cfg['gan'] else 1                      # GAN: one "step" = D-step + G-step pair / 2
@@ -239,10 +241,10 @@ def main():
     d2h = 16 * 8                                     # one pinned 16-double stats record per step
 
     # ---------------- roofline of the dominant kernel family (instrumented eager pass)
-    roof = None
-    if rank == 0:
-        from dmcnet_b200.profiling import measure_roofline
-        roof = measure_roofline(resident_step, per, min(args.steps, 3), tr)
+    # every rank runs it (the steps contain the gradient all-reduce); rank 0 reports
+    from dmcnet_b200.profiling import measure_roofline
+    roof = measure_roofline(resident_step, per, min(args.steps, 3), tr)
+    barrier()
 
     if rank != 0:
         if world > 1:

@@ -244,11 +244,11 @@ class FusedTrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                with torch.cuda.graph(ga, stream=s):
+                with torch.cuda.graph(ga, stream=s, capture_error_mode='thread_local'):
                     self._fwd_bwd(mode)
                 if apply:
                     self._allreduce(groups)
-                with torch.cuda.graph(gb, stream=s):
+                with torch.cuda.graph(gb, stream=s, capture_error_mode='thread_local'):
                     self._adam(groups)
             torch.cuda.current_stream().wait_stream(s)
             self._graphs[key] = ('ready', ga, gb)
