@@ -121,10 +121,27 @@ def run_reference(args):
         'e2e': {'value': rate, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else printed by libraries
+    (NCCL banner, torchrun notices) was redirected to stderr by protect_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -275,7 +292,7 @@ def main():
         line['cpu_baseline'] = {'value': rate, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
                                 'sample': '2 timed + 1 warm-up steps of B=%d clips (x3 segments) of the same '
                                           'workload, torch CPU fp32, oracle restatement' % args.cpu_sample_batch}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
