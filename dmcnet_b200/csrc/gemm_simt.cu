@@ -79,7 +79,8 @@ simt_tap_gemm_kernel(const bf16* __restrict__ Ah, const bf16* __restrict__ Al, l
 __global__ void __launch_bounds__(256)
 simt_wgrad_kernel(const bf16* __restrict__ Gh, const bf16* __restrict__ Gl, long P, int Cout,
                   const bf16* __restrict__ Xh, const bf16* __restrict__ Xl, int Cin,
-                  float* __restrict__ dW, SimtTaps taps, int n_tiles, long rows_per_split) {
+                  float* __restrict__ dW, SimtTaps taps, int n_tiles, long rows_per_split,
+                  int oihw_taps) {
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -109,7 +110,8 @@ simt_wgrad_kernel(const bf16* __restrict__ Gh, const bf16* __restrict__ Gl, long
     tile_fma(As, Bs, acc, ty, tx);
     __syncthreads();
   }
-  float* w = dW + (long)taps.bsel[t] * Cout * Cin;
+  float* w = dW + (oihw_taps ? (long)taps.bsel[t] : (long)taps.bsel[t] * Cout * Cin);
+  const int wstep = oihw_taps ? oihw_taps : 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int co = m0 + ty * 4 + i;
@@ -117,7 +119,7 @@ simt_wgrad_kernel(const bf16* __restrict__ Gh, const bf16* __restrict__ Gl, long
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ci = n0 + tx * 4 + j;
-      if (ci < Cin) atomicAdd(w + (long)co * Cin + ci, acc[i][j]);
+      if (ci < Cin) atomicAdd(w + ((long)co * Cin + ci) * wstep, acc[i][j]);
     }
   }
 }
@@ -155,7 +157,8 @@ extern "C" int dmc_simt_tap_gemm(const void* A_hi, const void* A_lo, int a_phase
 
 extern "C" int dmc_simt_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
                               const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
-                              const int* shift, const int* phase, const int* bsel, void* stream) {
+                              const int* shift, const int* phase, const int* bsel, int oihw_taps,
+                              void* stream) {
   DMC_REQUIRE(ntaps >= 1 && ntaps <= 16, "simt_wgrad: ntaps=%d", ntaps);
   for (int i = 0; i < ntaps; ++i)
     DMC_REQUIRE(phase[i] >= 0 && phase[i] < x_phases, "simt_wgrad: tap %d phase out of range", i);
@@ -170,6 +173,6 @@ extern "C" int dmc_simt_wgrad(const void* G_hi, const void* G_lo, long P, int Co
   dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)ntaps);
   simt_wgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const bf16*)G_hi, (const bf16*)G_lo, P, Cout, (const bf16*)X_hi, (const bf16*)X_lo, Cin, dW, tt,
-      n_tiles, rows);
+      n_tiles, rows, oihw_taps);
   return dmc_check_launch("simt_wgrad_kernel");
 }

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
                   const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
-                  long P, int kb_per_split, int n_tiles) {
+                  long P, int kb_per_split, int n_tiles, int oihw_taps) {
   using S = WgradSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -395,7 +395,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   mbar_wait(tmem_full, 0);
   tc_fence_after();
   const int co = m0 + warp * 32 + lane;
-  float* wrow = dW + ((long)taps.bsel[t] * Cout + co) * Cin + n0;
+  // output layout: [slice][Cout][Cin] (oihw_taps == 0) or the OIHW gradient itself,
+  // dW[co][ci][tap] with oihw_taps taps per filter (no repacking pass afterwards)
+  const long wbase = oihw_taps ? ((long)co * Cin + n0) * oihw_taps + taps.bsel[t]
+                               : ((long)taps.bsel[t] * Cout + co) * Cin + n0;
+  const int wstep = oihw_taps ? oihw_taps : 1;
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
     uint32_t r[32];
@@ -404,7 +408,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
     if (co < Cout) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + c + j < Cin) atomicAdd(wrow + c + j, __uint_as_float(r[j]));
+        if (n0 + c + j < Cin) atomicAdd(dW + wbase + (long)(c + j) * wstep, __uint_as_float(r[j]));
     }
   }
   tc_fence_before();
@@ -415,7 +419,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
 template <int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap& mGh, const CUtensorMap& mGl, const CUtensorMap& mXh,
                         const CUtensorMap& mXl, const TapTable& taps, float* dW, int Cout, int Cin,
-                        long P, int sm_count, cudaStream_t stream) {
+                        long P, int sm_count, int oihw_taps, cudaStream_t stream) {
   using S = WgradSmem<BN, STAGES>;
   auto kern = wgrad_gemm_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -435,7 +439,7 @@ static int launch_wgrad(const CUtensorMap& mGh, const CUtensorMap& mGl, const CU
   const long splits = cdiv(kb_total, kb_per_split);
   dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)taps.ntaps);
   kern<<<grid, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, Cout, Cin, P,
-                                        (int)kb_per_split, n_tiles);
+                                        (int)kb_per_split, n_tiles, oihw_taps);
   return dmc_check_launch("wgrad_gemm_kernel");
 }
 
@@ -495,10 +499,12 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, st);
 }
 
-// dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW)
+// dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).
+// oihw_taps > 0 writes the OIHW gradient directly instead: dW[co][ci][bsel_t], oihw_taps per filter.
 extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
                             const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
-                            const int* shift, const int* phase, const int* bsel, void* stream) {
+                            const int* shift, const int* phase, const int* bsel, int oihw_taps,
+                            void* stream) {
   DMC_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0, "wgrad: Cout=%d Cin=%d must be multiples of 64", Cout,
               Cin);
   DMC_REQUIRE(P > 0 && P < (1L << 31), "wgrad: bad P");
@@ -515,6 +521,6 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, 64))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (BN == 128)
-    return launch_wgrad<128, 3>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
-  return launch_wgrad<64, 2>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), st);
+    return launch_wgrad<128, 3>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), oihw_taps, st);
+  return launch_wgrad<64, 2>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), oihw_taps, st);
 }

@@ -61,6 +61,41 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
+// All conv weights of the classifier in ONE launch: a chunk table maps 1024-element chunks
+// of the [tap][co][ci] enumeration to (tensor, destination planes).
+struct PrepChunk {
+  long long w_off;             // element offset of the OIHW tensor inside the parameter bucket
+  long long Wh, Wl, Th, Tl;    // destination addresses (bf16), Th/Tl may be 0
+  int Cout, Cin, taps, start;  // start = first element of this chunk
+};
+
+__global__ void __launch_bounds__(256)
+weight_prep_multi_kernel(const float* __restrict__ params, const PrepChunk* __restrict__ chunks) {
+  const PrepChunk ch = chunks[blockIdx.x];
+  const float* w = params + ch.w_off;
+  bf16* Wh = reinterpret_cast<bf16*>(ch.Wh);
+  bf16* Wl = reinterpret_cast<bf16*>(ch.Wl);
+  bf16* Th = reinterpret_cast<bf16*>(ch.Th);
+  bf16* Tl = reinterpret_cast<bf16*>(ch.Tl);
+  const int n = ch.Cout * ch.Cin * ch.taps;
+  const int end = ch.start + 1024 < n ? ch.start + 1024 : n;
+  for (int i = ch.start + threadIdx.x; i < end; i += 256) {
+    const int ci = i % ch.Cin;
+    const int co = (i / ch.Cin) % ch.Cout;
+    const int t = i / (ch.Cin * ch.Cout);
+    const float v = w[((long)co * ch.Cin + ci) * ch.taps + t];
+    bf16 h, l;
+    split_bf16(v, h, l);
+    Wh[i] = h;
+    Wl[i] = l;
+    if (Th) {
+      const long j = ((long)t * ch.Cin + ci) * ch.Cout + co;
+      Th[j] = h;
+      Tl[j] = l;
+    }
+  }
+}
+
 // [tap][Cout][Cin] fp32 (wgrad accumulator) -> OIHW gradient.
 __global__ void wgrad_unpack_kernel(const float* __restrict__ dWs, float* __restrict__ g, int Cout,
                                     int Cin, int taps) {
@@ -441,6 +476,15 @@ extern "C" int dmc_weight_prep(const float* w_oihw, int Cout, int Cin, int taps,
   weight_prep_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(
       w_oihw, Cout, Cin, taps, (bf16*)W_hi, (bf16*)W_lo, (bf16*)Wt_hi, (bf16*)Wt_lo);
   return dmc_check_launch("weight_prep_kernel");
+}
+
+// chunks: device array of PrepChunk {int64 w_off, Wh, Wl, Th, Tl; int32 Cout, Cin, taps, start}
+extern "C" int dmc_weight_prep_multi(const float* params, const void* chunks, int nchunks,
+                                     void* stream) {
+  if (nchunks <= 0) return DMC_OK;
+  weight_prep_multi_kernel<<<nchunks, 256, 0, ST(stream)>>>(params,
+                                                            reinterpret_cast<const PrepChunk*>(chunks));
+  return dmc_check_launch("weight_prep_multi_kernel");
 }
 
 extern "C" int dmc_wgrad_unpack(const float* dWs, float* grad_oihw, int Cout, int Cin, int taps,

@@ -308,7 +308,6 @@ class DmcEngine:
         self.G_hi = torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)   # dY planes (x2: conv1|ds stack)
         self.G_lo = torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)
         self.gbuf = [torch.zeros(max_pc, **f32) for _ in range(5)]             # T1, T2a, Ra, T2b, Rb
-        self.dWs = torch.zeros(max_w, **f32)
         self.pooled = torch.zeros(N, 512, **f32)
         self.d_pooled = torch.zeros(N, 512, **f32)
         self.logits = torch.zeros(N, self.num_class, **f32)
@@ -402,14 +401,22 @@ class DmcEngine:
 
     # ------------------------------------------------------------------ classifier
     def _prep_weights(self):
-        """fp32 OIHW parameters -> bf16 hi/lo GEMM operands (fprop and transposed for dgrad)."""
-        for blk in self.blocks:
-            for key in ('c1', 'c2', 'ds'):
-                if key not in blk:
-                    continue
-                u = blk[key]
-                ops.weight_prep(self.p(u.name_conv + '.weight'), u.cout, u.cin, u.taps,
-                                u.W_hi, u.W_lo, u.Wt_hi, u.Wt_lo)
+        """fp32 OIHW parameters -> bf16 hi/lo GEMM operands (fprop and transposed for dgrad),
+        every classifier conv in one launch."""
+        if getattr(self, '_prep_chunks', None) is None:
+            rows = []
+            for blk in self.blocks:
+                for key in ('c1', 'c2', 'ds'):
+                    if key not in blk:
+                        continue
+                    u = blk[key]
+                    n = u.cout * u.cin * u.taps
+                    for start in range(0, n, 1024):
+                        rows.append([self.offsets[u.name_conv + '.weight'], u.W_hi.data_ptr(),
+                                     u.W_lo.data_ptr(), u.Wt_hi.data_ptr(), u.Wt_lo.data_ptr(),
+                                     u.cout | (u.cin << 32), u.taps | (start << 32)])
+            self._prep_chunks = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        ops.weight_prep_multi(self.params, self._prep_chunks, self._prep_chunks.shape[0])
 
     def _unit_bn(self, u: _ConvBN, train: bool):
         """Batch statistics (train) or running statistics (eval) -> scale/shift of unit u."""
@@ -507,12 +514,10 @@ class DmcEngine:
             shift, phase, bsel = _taps_s1(geo.Wp)
         else:
             shift, phase, bsel = _taps_s2(geo.Wp)
-        nW = u.taps * u.cout * u.cin
-        dWs = self.dWs[:nW]
-        ops.memset_zero(dWs)
-        ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, dWs, P=geo.P, Cout=u.cout, x_phases=x_phases,
-                       Cin=u.cin, shift=shift, phase=phase, bsel=bsel, engine=self.gemm_engine)
-        ops.wgrad_unpack(dWs, self.g(u.name_conv + '.weight'), u.cout, u.cin, u.taps)
+        # the split-K epilogue accumulates straight into the (zeroed) OIHW gradient bucket
+        ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, self.g(u.name_conv + '.weight'), P=geo.P, Cout=u.cout,
+                       x_phases=x_phases, Cin=u.cin, shift=shift, phase=phase, bsel=bsel,
+                       engine=self.gemm_engine, oihw_taps=u.taps)
 
     def _cls_backward(self, x_planar: torch.Tensor, n: int, need_wgrad: bool, need_input_grad: bool,
                       d_input: Optional[torch.Tensor] = None):

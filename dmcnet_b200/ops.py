@@ -91,11 +91,11 @@ def tap_gemm(A_hi, A_lo, B_hi, B_lo, D, *, a_phases, a_rows, K, b_slices, N, M, 
 
 
 def wgrad_gemm(G_hi, G_lo, X_hi, X_lo, dW, *, P, Cout, x_phases, Cin, shift, phase, bsel,
-               engine='tc'):
+               engine='tc', oihw_taps=0):
     name = 'dmc_tc_wgrad' if engine == 'tc' else 'dmc_simt_wgrad'
     _call(name, _ptr(G_hi, BF16), _ptr(G_lo, BF16), c_long(P), c_int(Cout), _ptr(X_hi, BF16),
           _ptr(X_lo, BF16), c_int(x_phases), c_int(Cin), _ptr(dW, F32), c_int(len(shift)),
-          _iarr(shift), _iarr(phase), _iarr(bsel), _stream())
+          _iarr(shift), _iarr(phase), _iarr(bsel), c_int(oihw_taps), _stream())
 
 
 # ---------------------------------------------------------------- pixel-major classifier helpers
@@ -106,6 +106,10 @@ def memset_zero(t):
 def weight_prep(w, Cout, Cin, taps, W_hi, W_lo, Wt_hi=None, Wt_lo=None):
     _call('dmc_weight_prep', _ptr(w, F32), c_int(Cout), c_int(Cin), c_int(taps), _ptr(W_hi, BF16),
           _ptr(W_lo, BF16), _ptr(Wt_hi, BF16), _ptr(Wt_lo, BF16), _stream())
+
+
+def weight_prep_multi(params, chunks, nchunks):
+    _call('dmc_weight_prep_multi', _ptr(params, F32), _ptr(chunks, I64), c_int(nchunks), _stream())
 
 
 def wgrad_unpack(dWs, grad, Cout, Cin, taps):
