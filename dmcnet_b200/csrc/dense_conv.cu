@@ -942,3 +942,63 @@ extern "C" int dmc_conv3x3_dgrad_fused(const float* dY, long dy_ns, int Cy, int 
   DMC_DG(8, 4);
 #undef DMC_DG
 }
+
+// ------------------------------------------------------------------ dense-block data gradient
+// Gradient buffer layout [dOut(c_out) | new_{L-1} | ... | new_0]: the gradient of slice k is ONE
+// forward convolution over all channels in front of it (every later layer's pre-activation
+// gradient), with a weight tensor assembled from the flipped weights of those layers:
+//   Wc_k[ci'][c'][t] = w_j[co_j][(x_k + ci') - in_off_j][8 - t],  c' <-> (layer j, output co_j).
+struct DenseSeg {
+  int c0, cnt;        // channels [c0, c0+cnt) of the gradient buffer belong to layer j
+  int w_off;          // offset of w_j (OIHW) in the parameter bucket
+  int cin_j;          // input channels of layer j
+  int ci_off;         // x_k - in_off_j: where slice k starts inside layer j's input
+};
+struct DenseSlice {
+  int out_off;        // offset of Wc_k in the output buffer
+  int gk, cin_s, nseg;
+  DenseSeg seg[6];
+};
+struct DenseTable {
+  int nslices;
+  DenseSlice sl[6];
+};
+
+__global__ void dense_dgrad_weights_kernel(const float* __restrict__ params, DenseTable tab,
+                                           float* __restrict__ out) {
+  const DenseSlice& sl = tab.sl[blockIdx.x];
+  const int n = sl.gk * sl.cin_s * 9;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = i % 9, c = (i / 9) % sl.cin_s, ci = i / (9 * sl.cin_s);
+    float v = 0.f;
+    for (int g = 0; g < sl.nseg; ++g) {
+      const DenseSeg& sg = sl.seg[g];
+      if (c >= sg.c0 && c < sg.c0 + sg.cnt)
+        v = params[sg.w_off + ((long)(c - sg.c0) * sg.cin_j + sg.ci_off + ci) * 9 + (8 - t)];
+    }
+    out[sl.out_off + i] = v;
+  }
+}
+
+// table: int32 array [1 + nslices * (4 + 6*5)] = {nslices, per slice: out_off, gk, cin_s, nseg,
+// 6 x (c0, cnt, w_off, cin_j, ci_off)} (host memory).
+extern "C" int dmc_dense_dgrad_weights(const float* params, const int* table, float* out,
+                                       void* stream) {
+  DenseTable tab;
+  tab.nslices = table[0];
+  DMC_REQUIRE(tab.nslices >= 1 && tab.nslices <= 6, "dense_dgrad_weights: nslices=%d", tab.nslices);
+  const int* p = table + 1;
+  for (int k = 0; k < tab.nslices; ++k) {
+    DenseSlice& sl = tab.sl[k];
+    sl.out_off = p[0]; sl.gk = p[1]; sl.cin_s = p[2]; sl.nseg = p[3];
+    DMC_REQUIRE(sl.nseg >= 1 && sl.nseg <= 6, "dense_dgrad_weights: nseg=%d", sl.nseg);
+    for (int g = 0; g < 6; ++g) {
+      const int* q = p + 4 + 5 * g;
+      sl.seg[g].c0 = q[0]; sl.seg[g].cnt = q[1]; sl.seg[g].w_off = q[2];
+      sl.seg[g].cin_j = q[3]; sl.seg[g].ci_off = q[4];
+    }
+    p += 4 + 30;
+  }
+  dense_dgrad_weights_kernel<<<tab.nslices, 256, 0, ST_(stream)>>>(params, tab, out);
+  return dmc_check_launch("dense_dgrad_weights_kernel");
+}

@@ -124,16 +124,18 @@ ce_head_kernel(const float* __restrict__ logits, int B, int S, int C,
 // loss_sum += sum (gen-flow)^2 (double);  dgen = gscale * (gen - flow)  (gscale = 2*lr_mse/numel)
 __global__ void __launch_bounds__(256)
 mse_head_kernel(const float* __restrict__ gen, const float* __restrict__ flow, long n4, float gscale,
-                float* __restrict__ dgen, double* __restrict__ loss_sum) {
+                float* __restrict__ dgen, long frame4, long dgen_ns4, double* __restrict__ loss_sum) {
   float s = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(gen)[i];
     const float4 b = reinterpret_cast<const float4*>(flow)[i];
     const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
     s += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-    if (dgen)
-      reinterpret_cast<float4*>(dgen)[i] =
+    if (dgen) {      // dgen may be a channel slice of a wider buffer: per-frame stride dgen_ns4
+      const long o = frame4 == dgen_ns4 ? i : (i / frame4) * dgen_ns4 + (i % frame4);
+      reinterpret_cast<float4*>(dgen)[o] =
           make_float4(gscale * d.x, gscale * d.y, gscale * d.z, gscale * d.w);
+    }
   }
   __shared__ double red[8];
   double sd = warp_sum_d((double)s);
@@ -183,14 +185,18 @@ extern "C" int dmc_ce_head(const float* logits, int B, int S, int C, const long 
   return dmc_check_launch("ce_head_kernel");
 }
 
+// dgen[n][0:frame_elems] (per-frame stride dgen_ns elements) = gscale * (gen - flow)
 extern "C" int dmc_mse_head(const float* gen, const float* flow, long numel, float gscale,
-                            float* dgen, double* loss_sum, void* stream) {
-  DMC_REQUIRE(numel % 4 == 0, "mse_head: numel must be a multiple of 4");
+                            float* dgen, long frame_elems, long dgen_ns, double* loss_sum,
+                            void* stream) {
+  DMC_REQUIRE(numel % 4 == 0 && frame_elems % 4 == 0 && dgen_ns % 4 == 0 && frame_elems > 0,
+              "mse_head: sizes must be multiples of 4");
   if (cudaMemsetAsync(loss_sum, 0, sizeof(double), ST_(stream)) != cudaSuccess)
     return dmc_check_launch("mse_head memset");
   long blocks = cdiv(numel / 4, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  mse_head_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, numel / 4, gscale, dgen, loss_sum);
+  mse_head_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, numel / 4, gscale, dgen,
+                                                        frame_elems / 4, dgen_ns / 4, loss_sum);
   return dmc_check_launch("mse_head_kernel");
 }

@@ -242,9 +242,11 @@ class DmcEngine:
         dev, N, H, W = self.device, self.N, self.H, self.W
         self.gen_ctot = GEN_IN + sum(GEN_GROWTH)                      # 33
         self.X = torch.zeros(N, self.gen_ctot, H, W, dtype=torch.float32, device=dev)
-        self.dX = torch.zeros(N, self.gen_ctot - GEN_IN, H, W, dtype=torch.float32, device=dev)
+        # gradient buffer of the dense block: [d gen_flow (2) | new4 new3 new2 new1 new0 (28)];
+        # the gradient of one slice is a single convolution over ALL channels in front of it
+        self.dD = torch.zeros(N, 2 + self.gen_ctot - GEN_IN, H, W, dtype=torch.float32, device=dev)
+        self.d_gen_flow = self.dD[:, 0:2]                         # strided view (frame stride 30*H*W)
         self.gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
-        self.d_gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
         # channel offset of each layer's OUTPUT inside X: new channels are prepended
         outs, off = [], self.gen_ctot - GEN_IN
         for g in GEN_GROWTH:
@@ -254,6 +256,26 @@ class DmcEngine:
         self.gen_in_off = [o + g for o, g in zip(outs, GEN_GROWTH)]      # [28, 20, 12, 6, 2]
         self.mv_off = self.gen_ctot - GEN_IN                             # 28
         self.wflip = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=dev)   # dgrad weight scratch
+        # combined (flipped, transposed) dgrad weights of the generator slices, see _gen_backward
+        table, off = [len(GEN_GROWTH)], 0
+        self.gen_wc_off = []
+        L = len(GEN_GROWTH)
+        for k in reversed(range(L)):                    # slices new4 .. new0
+            gk, xk = GEN_GROWTH[k], self.gen_out_off[k]
+            cin_s = 2 + xk
+            segs = [(0, 2, self.offsets['gen_flow_model.predict_flow.weight'], self.gen_ctot, xk)]
+            for j in range(L - 1, k, -1):               # later dense layers j > k
+                segs.append((2 + self.gen_out_off[j], GEN_GROWTH[j],
+                             self.offsets['gen_flow_model.conv_%d.0.weight' % j],
+                             self.gen_ctot - self.gen_in_off[j], xk - self.gen_in_off[j]))
+            row = [off, gk, cin_s, len(segs)]
+            for g in range(6):
+                row += list(segs[g]) if g < len(segs) else [0, 0, 0, 0, 0]
+            table += row
+            self.gen_wc_off.append(off)
+            off += gk * cin_s * 9
+        self.gen_wc_table = table
+        self.gen_wc = torch.zeros(off, dtype=torch.float32, device=dev)
 
     def _alloc_classifier(self):
         dev, N = self.device, self.N
@@ -361,30 +383,27 @@ class DmcEngine:
                      add=(mv if self.gen_flow_or_delta == 1 else None), add_ns=2 * HW)
 
     def _gen_backward(self, n: int):
-        """Gradients of all generator parameters from ``self.d_gen_flow``."""
+        """Gradients of all generator parameters from ``self.d_gen_flow`` (= dD[:, 0:2])."""
         H, W = self.H, self.W
         HW = H * W
-        X, dX = self.X.view(-1), self.dX.view(-1)
-        ns, dns = self.gen_ctot * HW, (self.gen_ctot - GEN_IN) * HW
-        ngen = self.gen_ctot - GEN_IN                                   # 28 generated channels
-        dG = self.d_gen_flow.view(-1)
+        X, dD = self.X.view(-1), self.dD.view(-1)
+        ns, dns = self.gen_ctot * HW, self.dD.shape[1] * HW
+        L = len(GEN_GROWTH)
+        ops.dense_dgrad_weights(self.params, self.gen_wc_table, self.gen_wc)
         wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
-        ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dG, 2 * HW, 2, 3, 1, self.g(wk), self.g(bk), n)
-        # Each dgrad writes channels [io, 28) of dX; the FIRST slice it writes (the previous
-        # layer's outputs) receives its last contribution there, so LeakyReLU(0.1)' is fused
-        # into that launch and the slice leaves as the pre-activation gradient.
-        self._dgrad_s1(dG, 2 * HW, 2, wk, self.gen_ctot, ngen, dX, dns, H, W, n, False,
-                       act=(X, ns, GEN_GROWTH[-1], 0.1))
-        for k in reversed(range(len(GEN_GROWTH))):
+        ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dD, dns, 2, 3, 1, self.g(wk), self.g(bk), n)
+        for idx, k in enumerate(reversed(range(L))):
             g = GEN_GROWTH[k]
             oo, io = self.gen_out_off[k], self.gen_in_off[k]
-            cin = self.gen_ctot - io
+            cin_s = 2 + oo                                   # d gen_flow + every later slice
+            wc = self.gen_wc[self.gen_wc_off[idx]:self.gen_wc_off[idx] + g * cin_s * 9]
+            # slice gradient in ONE launch (no read-modify-write), LeakyReLU(0.1)' fused
+            ops.conv3x3_dgrad_fused(dD, dns, cin_s, H, W, wc, g, dD[(2 + oo) * HW:], dns, n,
+                                    accumulate=False, act_src=X[oo * HW:], act_ns=ns, act_c1=g,
+                                    act_slope=0.1)
             wk, bk = 'gen_flow_model.conv_%d.0.weight' % k, 'gen_flow_model.conv_%d.0.bias' % k
-            ops.conv_wgrad(X[io * HW:], ns, cin, H, W, dX[oo * HW:], dns, g, 3, 1, self.g(wk),
-                           self.g(bk), n)
-            if ngen - io > 0:
-                self._dgrad_s1(dX[oo * HW:], dns, g, wk, cin, ngen - io, dX[io * HW:], dns, H, W, n, True,
-                               act=(X[io * HW:], ns, GEN_GROWTH[k - 1], 0.1))
+            ops.conv_wgrad(X[io * HW:], ns, self.gen_ctot - io, H, W, dD[(2 + oo) * HW:], dns, g, 3, 1,
+                           self.g(wk), self.g(bk), n)
 
     def _dgrad_s1(self, dY, dy_ns, cout, wkey, cin, ci_count, dX, dx_ns, H, W, n, accumulate, act=None):
         """3x3 stride-1 data gradient = forward convolution of dY with the flipped, transposed weight;
@@ -610,7 +629,7 @@ class DmcEngine:
                            self.g('base_model.conv1.weight'), None, n)
         if need_input_grad:
             ops.conv_dgrad(self.stem_dZ, ns, 64, self.p('base_model.conv1.weight'), 2, 2, 7, 2,
-                           d_input.view(-1), 2 * H * W, H, W, n, accumulate=True)
+                           self.dD.view(-1), self.dD.shape[1] * H * W, H, W, n, accumulate=True)
 
     # ------------------------------------------------------------------ discriminator
     def _disc_forward(self, x: torch.Tensor, m: int, train: bool, use_masks: bool):
@@ -687,7 +706,8 @@ class DmcEngine:
                 g = nxt
             elif d_input is not None:
                 ops.conv_dgrad(g, ns, co, self.p(p + '.0.weight'), ci, ci, 3, L['stride'],
-                               d_input.view(-1), ci * h * w, h, w, d_input_rows, accumulate=True)
+                               self.dD.view(-1), self.dD.shape[1] * h * w, h, w, d_input_rows,
+                               accumulate=True)
 
     # ------------------------------------------------------------------ public passes
     def forward(self, input_mv: torch.Tensor, input_residual: torch.Tensor,

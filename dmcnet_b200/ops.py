@@ -276,9 +276,15 @@ def ce_head(logits, B, S, C, target, gscale, consensus, dlogits, out_stats):
           c_float(gscale), _ptr(consensus, F32), _ptr(dlogits, F32), _ptr(out_stats, F32), _stream())
 
 
-def mse_head(gen, flow, numel, gscale, dgen, loss_sum):
+def mse_head(gen, flow, numel, gscale, dgen, loss_sum, frame_elems=None, dgen_ns=None):
+    fe = frame_elems if frame_elems is not None else numel
     _call('dmc_mse_head', _ptr(gen, F32), _ptr(flow, F32), c_long(numel), c_float(gscale),
-          _ptr(dgen, F32), _ptr(loss_sum, F64), _stream())
+          _ptr(dgen, F32), c_long(fe), c_long(dgen_ns if dgen_ns is not None else fe),
+          _ptr(loss_sum, F64), _stream())
+
+
+def dense_dgrad_weights(params, table, out):
+    _call('dmc_dense_dgrad_weights', _ptr(params, F32), _iarr(table), _ptr(out, F32), _stream())
 
 
 def adam_step(p, g, m, v, chunks, nchunks, hyper, step, beta1, beta2, eps, grad_scale=1.0):

@@ -186,8 +186,8 @@ class FusedTrainStep:
             eng.forward(self.in_mv, self.in_res, train=True)
             ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
                         eng.d_logits, self.ce_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse,
-                         eng.d_gen_flow, self.mse_sum)
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse, eng.dD, self.mse_sum,
+                         frame_elems=2 * eng.H * eng.W, dgen_ns=eng.dD.shape[1] * eng.H * eng.W)
             eng.backward(n, cls=(mode == 'full'), cls_wgrad=True, gen_grad=True, cls_to_gen=False)
         elif mode == 'D':
             eng.forward(self.in_mv, self.in_res, self.in_flow, train=True, masks='preloaded')
@@ -204,8 +204,8 @@ class FusedTrainStep:
                         eng.d_logits, self.ce_stats)
             ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, hp.lr_adv_g / (n * self.world), None,
                         eng.d_validity, self.adv_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse,
-                         eng.d_gen_flow, self.mse_sum)
+            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse, eng.dD, self.mse_sum,
+                         frame_elems=2 * eng.H * eng.W, dgen_ns=eng.dD.shape[1] * eng.H * eng.W)
             # classifier / discriminator weight gradients are dead work in the G-step (:367-371)
             eng.backward(n, cls=True, cls_wgrad=False, gen_grad=True, cls_to_gen=True, disc=True,
                          disc_wgrad=False, disc_to_gen=True)
