@@ -8,7 +8,10 @@
 
 namespace dmc {
 
-// grid (Hq, N); Y [N][C][H][W] -> hi/lo [N][Hq+2][Wq+2][C] interior, idx [N][Hq][Wq][C]
+// grid (Hq, N); Y [N][C][H][W] -> hi/lo [N][Hq+2][Wq+2][C] interior, idx [N][Hq][Wq][C].
+// One warp streams one (channel, input row) at a time with 128-bit loads (no per-element
+// index arithmetic); the pooled row is then produced channel-fastest so the pixel-major
+// stores coalesce.
 __global__ void __launch_bounds__(256)
 stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
                      const float* __restrict__ shift, int C, int H, int W, bf16* __restrict__ out_hi,
@@ -17,17 +20,26 @@ stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scal
   extern __shared__ float rows[];              // [CG][3][W+1]
   const int Hq = H / 2, Wq = W / 2;
   const int ph = blockIdx.x, n = blockIdx.y;
-  const int WP = W + 1;
+  const int WP = W + 1, W4 = W / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int cg = 0; cg < C; cg += CG) {
-    for (int i = threadIdx.x; i < CG * 3 * W; i += blockDim.x) {
-      const int w = i % W, r = (i / W) % 3, c = i / (3 * W);
+    for (int cr = warp; cr < CG * 3; cr += nwarps) {
+      const int c = cr / 3, r = cr - 3 * c;
       const int h = 2 * ph - 1 + r;
-      float v = -1.f;                          // marks "outside the image"
+      float* dst = rows + cr * WP;
       if (h >= 0 && h < H) {
-        const float y = Y[(((long)n * C + cg + c) * H + h) * W + w];
-        v = fmaxf(fmaf(y, scale[cg + c], shift[cg + c]), 0.f);
+        const float sc = scale[cg + c], sh = shift[cg + c];
+        const float4* src = reinterpret_cast<const float4*>(Y + (((long)n * C + cg + c) * H + h) * W);
+        for (int j = lane; j < W4; j += 32) {
+          const float4 v = src[j];
+          dst[4 * j + 0] = fmaxf(fmaf(v.x, sc, sh), 0.f);
+          dst[4 * j + 1] = fmaxf(fmaf(v.y, sc, sh), 0.f);
+          dst[4 * j + 2] = fmaxf(fmaf(v.z, sc, sh), 0.f);
+          dst[4 * j + 3] = fmaxf(fmaf(v.w, sc, sh), 0.f);
+        }
+      } else {
+        for (int j = lane; j < W; j += 32) dst[j] = -1.f;     // marks "outside the image"
       }
-      rows[(c * 3 + r) * WP + w] = v;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Wq * CG; i += blockDim.x) {
@@ -37,11 +49,11 @@ stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scal
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int w = 2 * pw - 1 + s;
+        for (int s3 = 0; s3 < 3; ++s3) {
+          const int w = 2 * pw - 1 + s3;
           if (w < 0 || w >= W) continue;
           const float v = rows[(c * 3 + r) * WP + w];
-          if (v > best) { best = v; bi = r * 3 + s; }
+          if (v > best) { best = v; bi = r * 3 + s3; }
         }
       const long o = (((long)n * (Hq + 2) + ph + 1) * (Wq + 2) + pw + 1) * C + cg + c;
       bf16 h, l;
@@ -54,18 +66,19 @@ stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scal
   }
 }
 
-// grid (H, N); dZ[n][c][h][w] = relu'(bn(Y)) * sum_{windows whose argmax is (h,w)} dA[...]
+// grid (H, N); dZ[n][c][h][w] = relu'(bn(Y)) * sum_{windows whose argmax is (h,w)} dA[...].
+// The pooled gradient rows are staged channel-transposed once; every warp then streams one
+// channel row of Y / dZ with 128-bit accesses.
 __global__ void __launch_bounds__(256)
 stem_pool_bwd_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b,
                      const unsigned char* __restrict__ idx, const float* __restrict__ Y,
                      const float* __restrict__ scale, const float* __restrict__ shift, int C, int H,
                      int W, float* __restrict__ dZ) {
   extern __shared__ float sm[];                // g [2][C][Wq+1] floats, then idx bytes [2][C][Wq+1]
-  const int Hq = H / 2, Wq = W / 2, WQP = Wq + 1;
+  const int Hq = H / 2, Wq = W / 2, WQP = Wq + 1, W4 = W / 4;
   const int h = blockIdx.x, n = blockIdx.y;
   float* g_s = sm;
   unsigned char* i_s = reinterpret_cast<unsigned char*>(sm + 2 * C * WQP);
-  // candidate pooled rows: 2*ph-1 <= h <= 2*ph+1
   const int ph_lo = h / 2;                      // h even -> {h/2}; h odd -> {(h-1)/2, (h+1)/2}
   const int nph = (h & 1) ? 2 : 1;
   for (int i = threadIdx.x; i < nph * Wq * C; i += blockDim.x) {
@@ -83,26 +96,38 @@ stem_pool_bwd_kernel(const float* __restrict__ g_a, const float* __restrict__ g_
     i_s[(k * C + c) * WQP + pw] = id;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-    const int w = i % W, c = i / W;
-    const long o = (((long)n * C + c) * H + h) * W + w;
-    const float a = fmaf(Y[o], scale[c], shift[c]);
-    float acc = 0.f;
-    if (a > 0.f) {
-      const int pw_lo = w / 2, npw = (w & 1) ? 2 : 1;
-      for (int k = 0; k < nph; ++k) {
-        const int ph = ph_lo + k;
-        if (ph >= Hq) continue;
-        const int r = h - (2 * ph - 1);
-        for (int j = 0; j < npw; ++j) {
-          const int pw = pw_lo + j;
-          if (pw >= Wq) continue;
-          const int s = w - (2 * pw - 1);
-          if (i_s[(k * C + c) * WQP + pw] == r * 3 + s) acc += g_s[(k * C + c) * WQP + pw];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    const float sc = scale[c], sh = shift[c];
+    const long base = (((long)n * C + c) * H + h) * W;
+    const float4* ysrc = reinterpret_cast<const float4*>(Y + base);
+    float4* zdst = reinterpret_cast<float4*>(dZ + base);
+    for (int j = lane; j < W4; j += 32) {
+      const float4 y = ysrc[j];
+      const float yv[4] = {y.x, y.y, y.z, y.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int w = 4 * j + e;
+        float acc = 0.f;
+        if (fmaf(yv[e], sc, sh) > 0.f) {
+          const int pw_lo = w / 2, npw = (w & 1) ? 2 : 1;
+          for (int k = 0; k < nph; ++k) {
+            const int ph = ph_lo + k;
+            if (ph >= Hq) continue;
+            const int r = h - (2 * ph - 1);
+            for (int q = 0; q < npw; ++q) {
+              const int pw = pw_lo + q;
+              if (pw >= Wq) continue;
+              const int s3 = w - (2 * pw - 1);
+              if (i_s[(k * C + c) * WQP + pw] == r * 3 + s3) acc += g_s[(k * C + c) * WQP + pw];
+            }
+          }
         }
+        o[e] = acc;
       }
+      zdst[j] = make_float4(o[0], o[1], o[2], o[3]);
     }
-    dZ[o] = acc;
   }
 }
 
@@ -113,7 +138,7 @@ using namespace dmc;
 extern "C" int dmc_stem_pool_fwd(const float* Y, const float* scale, const float* shift, int N, int C,
                                  int H, int W, void* out_hi, void* out_lo, unsigned char* idx,
                                  void* stream) {
-  DMC_REQUIRE(C % 32 == 0 && H % 2 == 0 && W % 2 == 0, "stem_pool_fwd: C=%d H=%d W=%d", C, H, W);
+  DMC_REQUIRE(C % 32 == 0 && H % 2 == 0 && W % 4 == 0, "stem_pool_fwd: C=%d H=%d W=%d", C, H, W);
   const int smem = 32 * 3 * (W + 1) * (int)sizeof(float);
   DMC_REQUIRE(smem <= 48 * 1024, "stem_pool_fwd: W=%d too wide", W);
   stem_pool_fwd_kernel<<<dim3(H / 2, N), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -124,6 +149,7 @@ extern "C" int dmc_stem_pool_fwd(const float* Y, const float* scale, const float
 extern "C" int dmc_stem_pool_bwd(const float* g_a, const float* g_b, const unsigned char* idx,
                                  const float* Y, const float* scale, const float* shift, int N, int C,
                                  int H, int W, float* dZ, void* stream) {
+  DMC_REQUIRE(W % 4 == 0, "stem_pool_bwd: W=%d must be a multiple of 4", W);
   const int WQP = W / 2 + 1;
   const int smem = 2 * C * WQP * (int)sizeof(float) + 2 * C * WQP;
   DMC_REQUIRE(smem <= 48 * 1024, "stem_pool_bwd: smem %d", smem);
