@@ -308,11 +308,14 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
     if (g < COG && co0 + g < Cout) v = w[((long)(co0 + g) * Cin + c) * 9 + t];
     w_s[i] = v;
   }
-  float acc[PX][COG];
+  // accumulators are output-channel PAIRS: Blackwell's fp32 pipe reaches its peak only
+  // through the packed FFMA2 form (two FMAs per lane per issue slot)
+  static_assert(COG % 2 == 0, "COG must be even");
+  float2 acc[PX][COG / 2];
 #pragma unroll
   for (int p = 0; p < PX; ++p)
 #pragma unroll
-    for (int g = 0; g < COG; ++g) acc[p][g] = 0.f;
+    for (int g = 0; g < COG / 2; ++g) acc[p][g] = make_float2(0.f, 0.f);
   __syncthreads();
 
   for (int k = 0; k < nch; ++k) {
@@ -339,18 +342,22 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
           v[q + 1] = f.x; v[q + 2] = f.y; v[q + 3] = f.z; v[q + 4] = f.w;
         }
         v[PX + 1] = row[PX];
+        float2 vv[PX + 2];
+#pragma unroll
+        for (int q = 0; q < PX + 2; ++q) vv[q] = make_float2(v[q], v[q]);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          float wv[COGP];
+          float2 wv[COGP / 2];
 #pragma unroll
           for (int g4 = 0; g4 < COGP; g4 += 4) {
             const float4 f = *reinterpret_cast<const float4*>(wc + (r * 3 + s) * COGP + g4);
-            wv[g4] = f.x; wv[g4 + 1] = f.y; wv[g4 + 2] = f.z; wv[g4 + 3] = f.w;
+            wv[g4 / 2] = make_float2(f.x, f.y);
+            wv[g4 / 2 + 1] = make_float2(f.z, f.w);
           }
 #pragma unroll
           for (int p = 0; p < PX; ++p)
 #pragma unroll
-            for (int g = 0; g < COG; ++g) acc[p][g] = fmaf(v[p + s], wv[g], acc[p][g]);
+            for (int g = 0; g < COG / 2; ++g) acc[p][g] = __ffma2_rn(vv[p + s], wv[g], acc[p][g]);
         }
       }
     }
@@ -369,7 +376,7 @@ conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
     float r[PX];
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
-      float v = acc[p][g] + b;
+      float v = ((g & 1) ? acc[p][g / 2].y : acc[p][g / 2].x) + b;
       v = v < 0.f ? v * slope : v;
       r[p] = v * mk;
     }
@@ -471,15 +478,16 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
   const int tiles_x = (W + 31) / 32, tiles_y = (H + TR - 1) / TR;
   const long items = (long)N * tiles_x * tiles_y;
   const uint32_t stage_bytes = (uint32_t)(xbox_c * XR * XP + DBUF) * 4;
-  float acc[COUT][3][3];
-  float bs[COUT];
+  static_assert(COUT % 2 == 0, "COUT must be even");
+  float2 acc[COUT / 2][3][3];       // output-channel pairs -> packed FFMA2
+  float2 bs[COUT / 2];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) {
-    bs[c] = 0.f;
+  for (int c = 0; c < COUT / 2; ++c) {
+    bs[c] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) acc[c][r][s] = 0.f;
+      for (int s = 0; s < 3; ++s) acc[c][r][s] = make_float2(0.f, 0.f);
   }
 #define DMC_WG_ISSUE(item_, stage_)                                                   \
   {                                                                                   \
@@ -510,22 +518,28 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
     if (ci < Cin) {
       const float* xs = buf + (k & 1) * STAGE + warp * XR * XP + lane + 3;   // tile col 0 = x0 - 4
       const float* ds = buf + (k & 1) * STAGE + XBUF + lane;
-      float w0[3], w1[3], w2[3];
+      float2 w0[3], w1[3], w2[3];   // window values broadcast into both halves
 #pragma unroll
-      for (int s = 0; s < 3; ++s) { w0[s] = xs[s]; w1[s] = xs[XP + s]; }
+      for (int s = 0; s < 3; ++s) {
+        w0[s] = make_float2(xs[s], xs[s]);
+        w1[s] = make_float2(xs[XP + s], xs[XP + s]);
+      }
 #pragma unroll 4
       for (int y = 0; y < TR; ++y) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) w2[s] = xs[(y + 2) * XP + s];
+        for (int s = 0; s < 3; ++s) {
+          const float t = xs[(y + 2) * XP + s];
+          w2[s] = make_float2(t, t);
+        }
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-          const float d = ds[(c * TR + y) * 32];
-          bs[c] += d;
+        for (int c = 0; c < COUT / 2; ++c) {
+          const float2 d = make_float2(ds[((2 * c) * TR + y) * 32], ds[((2 * c + 1) * TR + y) * 32]);
+          bs[c] = __fadd2_rn(bs[c], d);
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            acc[c][0][s] = fmaf(d, w0[s], acc[c][0][s]);
-            acc[c][1][s] = fmaf(d, w1[s], acc[c][1][s]);
-            acc[c][2][s] = fmaf(d, w2[s], acc[c][2][s]);
+            acc[c][0][s] = __ffma2_rn(d, w0[s], acc[c][0][s]);
+            acc[c][1][s] = __ffma2_rn(d, w1[s], acc[c][1][s]);
+            acc[c][2][s] = __ffma2_rn(d, w2[s], acc[c][2][s]);
           }
         }
 #pragma unroll
@@ -542,11 +556,11 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const float v = warp_sum(acc[c][r][s]);
+          const float v = warp_sum((c & 1) ? acc[c / 2][r][s].y : acc[c / 2][r][s].x);
           if (lane == 0 && co < Cout) atomicAdd(dW + ((long)co * Cin + ci) * 9 + r * 3 + s, v);
         }
       if (dbias && ci == 0) {
-        const float v = warp_sum(bs[c]);
+        const float v = warp_sum((c & 1) ? bs[c / 2].y : bs[c / 2].x);
         if (lane == 0 && co < Cout) atomicAdd(dbias + co, v);
       }
     }
