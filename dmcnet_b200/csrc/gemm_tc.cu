@@ -286,23 +286,29 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
-// ------------------------------------------------------------------ wgrad (split-K)
-template <int BN, int STAGES>
+// ------------------------------------------------------------------ wgrad (split-K, tap groups)
+// One CTA accumulates TG taps of one (128 x BN) weight tile over its pixel range: the dY
+// operand (M side) is loaded ONCE per k-block and multiplied with TG row-shifted activation
+// tiles into TG TMEM accumulators, instead of being re-read by nine single-tap CTAs.
+template <int BN, int TG, int BKP, int STAGES>
 struct WgradSmem {
-  static constexpr int BOX_BYTES = 64 * 128;       // 64 pixels x 64 channels bf16
-  static constexpr int G_BYTES = 2 * BOX_BYTES;    // M = 128 channels of dY
-  static constexpr int X_BYTES = (BN / 64) * BOX_BYTES;
-  static constexpr int STAGE_BYTES = 2 * G_BYTES + 2 * X_BYTES;
+  static constexpr int BOX_BYTES = BKP * 128;      // BKP pixels x 64 channels bf16
+  static constexpr int G_BYTES = 2 * BOX_BYTES;    // M = 128 channels of dY (one plane)
+  static constexpr int X_BYTES = (BN / 64) * BOX_BYTES;   // one tap, one plane
+  static constexpr int STAGE_BYTES = 2 * G_BYTES + TG * 2 * X_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = (TG * BN) <= 32 ? 32 : (TG * BN) <= 64 ? 64 : (TG * BN) <= 128 ? 128
+                                        : (TG * BN) <= 256 ? 256 : 512;
 };
 
-template <int BN, int STAGES>
+template <int BN, int TG, int BKP, int STAGES>
 __global__ void __launch_bounds__(128)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
                   const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
                   long P, int kb_per_split, int n_tiles, int oihw_taps) {
-  using S = WgradSmem<BN, STAGES>;
+  using S = WgradSmem<BN, TG, BKP, STAGES>;
+  static_assert(TG * BN <= 512, "tap group does not fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
@@ -312,16 +318,17 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.z;
+  const int t0 = blockIdx.z * TG;
+  const int nt_g = (taps.ntaps - t0) < TG ? (taps.ntaps - t0) : TG;     // taps in this group
   const int mt = blockIdx.y / n_tiles, nt = blockIdx.y % n_tiles;
   const int m0 = mt * 128, n0 = nt * BN;
-  const long kb_total = cdiv(P, 64);
+  const long kb_total = cdiv(P, BKP);
   const long kb0 = (long)blockIdx.x * kb_per_split;
   long kb1 = kb0 + kb_per_split;
   if (kb1 > kb_total) kb1 = kb_total;
   const int iters = (int)(kb1 - kb0);
   const int m_boxes = (Cout - m0) >= 128 ? 2 : 1;   // second 64-channel group may not exist
-  const uint32_t stage_tx = (uint32_t)(2 * m_boxes * S::BOX_BYTES + 2 * S::X_BYTES);
+  const uint32_t stage_tx = (uint32_t)(2 * m_boxes * S::BOX_BYTES + nt_g * 2 * S::X_BYTES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -335,36 +342,37 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
     tma_prefetch_desc(&mapXh);
     tma_prefetch_desc(&mapXl);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_ptr;
   if (iters <= 0) {   // uniform per CTA
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+    if (warp == 2) tmem_dealloc(tmem_d, S::TMEM_COLS);
     return;
   }
 
   if (warp == 0 && lane == 0) {
-    const int shift = taps.shift[t], phase = taps.phase[t];
     for (int i = 0; i < iters; ++i) {
       const int s = i % STAGES;
       if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
       const uint32_t full = bar_base + 8 * s;
       const uint32_t st = smem_base + s * S::STAGE_BYTES;
       mbar_expect_tx(full, stage_tx);
-      const int row = (int)((kb0 + i) * 64);
+      const int row = (int)((kb0 + i) * BKP);
       for (int b = 0; b < m_boxes; ++b) {
         tma_load_3d(st + b * S::BOX_BYTES, &mapGh, full, m0 + 64 * b, row, 0);
         tma_load_3d(st + S::G_BYTES + b * S::BOX_BYTES, &mapGl, full, m0 + 64 * b, row, 0);
       }
+      for (int g = 0; g < nt_g; ++g) {
+        const uint32_t xs = st + 2 * S::G_BYTES + g * 2 * S::X_BYTES;
+        const int xrow = row + taps.shift[t0 + g], ph = taps.phase[t0 + g];
 #pragma unroll
-      for (int b = 0; b < BN / 64; ++b) {
-        tma_load_3d(st + 2 * S::G_BYTES + b * S::BOX_BYTES, &mapXh, full, n0 + 64 * b, row + shift,
-                    phase);
-        tma_load_3d(st + 2 * S::G_BYTES + S::X_BYTES + b * S::BOX_BYTES, &mapXl, full, n0 + 64 * b,
-                    row + shift, phase);
+        for (int b = 0; b < BN / 64; ++b) {
+          tma_load_3d(xs + b * S::BOX_BYTES, &mapXh, full, n0 + 64 * b, xrow, ph);
+          tma_load_3d(xs + S::X_BYTES + b * S::BOX_BYTES, &mapXl, full, n0 + 64 * b, xrow, ph);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -374,17 +382,20 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
       mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
       tc_fence_after();
       const uint32_t st = smem_base + s * S::STAGE_BYTES;
+      for (int g = 0; g < nt_g; ++g) {
+        const uint32_t xs = st + 2 * S::G_BYTES + g * 2 * S::X_BYTES;
+        const uint32_t acc = tmem_d + g * BN;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {     // 16 pixels per MMA = two 8-row swizzle atoms
-        const uint32_t koff = ks * 2048;
-        const uint64_t gh = umma_desc_sw128(st + koff, S::BOX_BYTES, 1024);
-        const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
-        const uint64_t xh = umma_desc_sw128(st + 2 * S::G_BYTES + koff, S::BOX_BYTES, 1024);
-        const uint64_t xl =
-            umma_desc_sw128(st + 2 * S::G_BYTES + S::X_BYTES + koff, S::BOX_BYTES, 1024);
-        umma_bf16(tmem_d, gl, xh, idesc, (i | ks) != 0);
-        umma_bf16(tmem_d, gh, xl, idesc, 1);
-        umma_bf16(tmem_d, gh, xh, idesc, 1);
+        for (int ks = 0; ks < BKP / 16; ++ks) {   // 16 pixels per MMA = two 8-row swizzle atoms
+          const uint32_t koff = ks * 2048;
+          const uint64_t gh = umma_desc_sw128(st + koff, S::BOX_BYTES, 1024);
+          const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
+          const uint64_t xh = umma_desc_sw128(xs + koff, S::BOX_BYTES, 1024);
+          const uint64_t xl = umma_desc_sw128(xs + S::X_BYTES + koff, S::BOX_BYTES, 1024);
+          umma_bf16(acc, gl, xh, idesc, (i | ks) != 0);
+          umma_bf16(acc, gh, xl, idesc, 1);
+          umma_bf16(acc, gh, xh, idesc, 1);
+        }
       }
       umma_commit(bar_base + 8 * (STAGES + s));
     }
@@ -395,33 +406,42 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   mbar_wait(tmem_full, 0);
   tc_fence_after();
   const int co = m0 + warp * 32 + lane;
-  // output layout: [slice][Cout][Cin] (oihw_taps == 0) or the OIHW gradient itself,
-  // dW[co][ci][tap] with oihw_taps taps per filter (no repacking pass afterwards)
-  const long wbase = oihw_taps ? ((long)co * Cin + n0) * oihw_taps + taps.bsel[t]
-                               : ((long)taps.bsel[t] * Cout + co) * Cin + n0;
   const int wstep = oihw_taps ? oihw_taps : 1;
+  for (int g = 0; g < nt_g; ++g) {
+    // output layout: [slice][Cout][Cin] (oihw_taps == 0) or the OIHW gradient itself,
+    // dW[co][ci][tap] with oihw_taps taps per filter (no repacking pass afterwards)
+    const int bsel = taps.bsel[t0 + g];
+    const long wbase = oihw_taps ? ((long)co * Cin + n0) * oihw_taps + bsel
+                                 : ((long)bsel * Cout + co) * Cin + n0;
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c, r);
-    tmem_ld_wait();
-    if (co < Cout) {
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * BN + c, r);
+      tmem_ld_wait();
+      if (co < Cout) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + c + j < Cin) atomicAdd(dW + wbase + (long)(c + j) * wstep, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < Cin) atomicAdd(dW + wbase + (long)(c + j) * wstep, __uint_as_float(r[j]));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
-template <int BN, int STAGES>
-static int launch_wgrad(const CUtensorMap& mGh, const CUtensorMap& mGl, const CUtensorMap& mXh,
-                        const CUtensorMap& mXl, const TapTable& taps, float* dW, int Cout, int Cin,
-                        long P, int sm_count, int oihw_taps, cudaStream_t stream) {
-  using S = WgradSmem<BN, STAGES>;
-  auto kern = wgrad_gemm_kernel<BN, STAGES>;
+template <int BN, int TG, int BKP, int STAGES>
+static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, const void* X_lo,
+                        int x_phases, const TapTable& taps, float* dW, int Cout, int Cin, long P,
+                        int sm_count, int oihw_taps, cudaStream_t stream) {
+  using S = WgradSmem<BN, TG, BKP, STAGES>;
+  CUtensorMap mGh, mGl, mXh, mXl;
+  int rc;
+  if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mGl, G_lo, Cout, P, 1, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, BKP))) return rc;
+  auto kern = wgrad_gemm_kernel<BN, TG, BKP, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
@@ -430,14 +450,15 @@ static int launch_wgrad(const CUtensorMap& mGh, const CUtensorMap& mGl, const CU
     attr_set = true;
   }
   const int m_tiles = (int)cdiv(Cout, 128), n_tiles = (int)cdiv(Cin, BN);
-  const long kb_total = cdiv(P, 64);
-  const long tiles = (long)m_tiles * n_tiles * taps.ntaps;
-  long want_splits = cdiv((long)sm_count * 4, tiles);     // ~4 waves of CTAs
+  const int groups = (int)cdiv(taps.ntaps, TG);
+  const long kb_total = cdiv(P, BKP);
+  const long tiles = (long)m_tiles * n_tiles * groups;
+  long want_splits = cdiv((long)sm_count * (TG > 1 ? 2 : 4), tiles);
   if (want_splits < 1) want_splits = 1;
   long kb_per_split = cdiv(kb_total, want_splits);
   if (kb_per_split < 8) kb_per_split = 8;
   const long splits = cdiv(kb_total, kb_per_split);
-  dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)taps.ntaps);
+  dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)groups);
   kern<<<grid, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, Cout, Cin, P,
                                         (int)kb_per_split, n_tiles, oihw_taps);
   return dmc_check_launch("wgrad_gemm_kernel");
@@ -512,15 +533,13 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   DMC_REQUIRE(fill_taps(tt, ntaps, shift, phase, bsel) == 0, "wgrad: ntaps=%d", ntaps);
   for (int i = 0; i < ntaps; ++i)
     DMC_REQUIRE(phase[i] >= 0 && phase[i] < x_phases, "wgrad: tap %d phase out of range", i);
-  const int BN = (Cin % 128 == 0) ? 128 : 64;
-  CUtensorMap mGh, mGl, mXh, mXl;
-  int rc;
-  if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, 64))) return rc;
-  if ((rc = make_map_3d(&mGl, G_lo, Cout, P, 1, 64, 64))) return rc;
-  if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, 64))) return rc;
-  if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, 64))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 128)
-    return launch_wgrad<128, 3>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), oihw_taps, st);
-  return launch_wgrad<64, 2>(mGh, mGl, mXh, mXl, tt, dW, Cout, Cin, P, sm_count(), oihw_taps, st);
+  // taps are grouped so that consecutive taps share a CTA: they must read the same phase-independent
+  // dY tile (always true) -- the activation tile is per tap.
+  if (Cin % 128 == 0)       // wide tiles are MMA/latency-bound: one tap per CTA, more CTAs in flight
+    return launch_wgrad<128, 1, 64, 3>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P,
+                                       sm_count(), oihw_taps, st);
+  return launch_wgrad<64, 5, 64, 2>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P, sm_count(),
+                                    oihw_taps, st);
 }
+
