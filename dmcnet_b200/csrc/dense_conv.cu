@@ -637,10 +637,18 @@ bn_stats_planar_kernel(const float* __restrict__ X, long x_ns, int C, long HW, i
   for (int n = blockIdx.y; n < N; n += gridDim.y) {
     const float* p = X + (long)n * x_ns + (long)c * HW;
     float a = 0.f, b = 0.f;
-    for (long i = threadIdx.x; i < HW; i += blockDim.x) {
-      const float v = p[i];
-      a += v;
-      b += v * v;
+    if ((HW & 3) == 0) {
+      for (long i = threadIdx.x * 4; i < HW; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        a += (v.x + v.y) + (v.z + v.w);
+        b += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      for (long i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float v = p[i];
+        a += v;
+        b += v * v;
+      }
     }
     s0 += a;
     s1 += b;
@@ -657,18 +665,29 @@ bn_stats_planar_kernel(const float* __restrict__ X, long x_ns, int C, long HW, i
   }
 }
 
-// out = [relu](X*scale + shift), planar
-__global__ void bn_apply_planar_kernel(const float* __restrict__ X, long x_ns,
-                                       const float* __restrict__ scale,
-                                       const float* __restrict__ shift, int C, long HW, long total,
-                                       int relu, float* __restrict__ out, long o_ns) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long chw = (long)C * HW;
-    const long n = i / chw, r = i % chw;
-    const int c = (int)(r / HW);
-    float v = fmaf(X[n * x_ns + r], scale[c], shift[c]);
-    if (relu) v = fmaxf(v, 0.f);
-    out[n * o_ns + r] = v;
+// out = [relu](X*scale + shift), planar.  grid (chunks, C, N): one (image, channel) plane per
+// block row, 128-bit accesses, no per-element index arithmetic.
+__global__ void __launch_bounds__(256)
+bn_apply_planar_kernel(const float* __restrict__ X, long x_ns, const float* __restrict__ scale,
+                       const float* __restrict__ shift, long HW, int relu, float* __restrict__ out,
+                       long o_ns) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float sc = scale[c], sh = shift[c];
+  const float* xp = X + (long)n * x_ns + (long)c * HW;
+  float* op = out + (long)n * o_ns + (long)c * HW;
+  const long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4, step = (long)gridDim.x * blockDim.x * 4;
+  if ((HW & 3) == 0) {
+    for (long i = i0; i < HW; i += step) {
+      float4 v = *reinterpret_cast<const float4*>(xp + i);
+      v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      *reinterpret_cast<float4*>(op + i) = v;
+    }
+  } else {
+    for (long i = i0 / 4; i < HW; i += step / 4) {
+      float v = fmaf(xp[i], sc, sh);
+      op[i] = relu ? fmaxf(v, 0.f) : v;
+    }
   }
 }
 
@@ -685,10 +704,19 @@ bn_bwd_reduce_planar_kernel(const float* __restrict__ dZ, long dz_ns, const floa
     const float* g = dZ + (long)n * dz_ns + (long)c * HW;
     const float* p = X + (long)n * x_ns + (long)c * HW;
     float a = 0.f, b = 0.f;
-    for (long i = threadIdx.x; i < HW; i += blockDim.x) {
-      const float d = g[i];
-      a += d;
-      b += d * (p[i] - m) * is;
+    if ((HW & 3) == 0) {
+      for (long i = threadIdx.x * 4; i < HW; i += blockDim.x * 4) {
+        const float4 d = *reinterpret_cast<const float4*>(g + i);
+        const float4 x = *reinterpret_cast<const float4*>(p + i);
+        a += (d.x + d.y) + (d.z + d.w);
+        b += (d.x * (x.x - m) + d.y * (x.y - m) + d.z * (x.z - m) + d.w * (x.w - m)) * is;
+      }
+    } else {
+      for (long i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float d = g[i];
+        a += d;
+        b += d * (p[i] - m) * is;
+      }
     }
     s0 += a;
     s1 += b;
@@ -705,30 +733,39 @@ bn_bwd_reduce_planar_kernel(const float* __restrict__ dZ, long dz_ns, const floa
   }
 }
 
-// dX = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)); block 0 writes dgamma/dbeta
-__global__ void bn_bwd_apply_planar_kernel(const float* __restrict__ dZ, long dz_ns,
-                                           const float* __restrict__ X, long x_ns,
-                                           const float* __restrict__ mean,
-                                           const float* __restrict__ invstd,
-                                           const float* __restrict__ gamma,
-                                           const double* __restrict__ sums2, double count, int C,
-                                           long HW, long total, float* __restrict__ dX, long dx_ns,
-                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] = (float)sums2[c];
-      dgamma[c] = (float)sums2[C + c];
-    }
+// dX = gamma*invstd*(dZ - mean(dZ) - xhat*mean(dZ*xhat)) = A*dZ + B*X + K per channel;
+// grid (chunks, C, N); block (0, c, 0) writes dgamma[c] / dbeta[c].
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_planar_kernel(const float* __restrict__ dZ, long dz_ns, const float* __restrict__ X,
+                           long x_ns, const float* __restrict__ mean, const float* __restrict__ invstd,
+                           const float* __restrict__ gamma, const double* __restrict__ sums2,
+                           double count, int C, long HW, float* __restrict__ dX, long dx_ns,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const double inv_count = 1.0 / count;
+  const float a = gamma[c] * invstd[c];
+  const float m1 = (float)(sums2[c] * inv_count), m2 = (float)(sums2[C + c] * inv_count);
+  const float b = -a * invstd[c] * m2;
+  const float k = -a * m1 - b * mean[c];
+  if (blockIdx.x == 0 && n == 0 && threadIdx.x == 0 && dgamma) {
+    dbeta[c] = (float)sums2[c];
+    dgamma[c] = (float)sums2[C + c];
   }
-  const float inv_count = (float)(1.0 / count);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long chw = (long)C * HW;
-    const long n = i / chw, r = i % chw;
-    const int c = (int)(r / HW);
-    const float is = invstd[c];
-    const float xhat = (X[n * x_ns + r] - mean[c]) * is;
-    const float m1 = (float)sums2[c] * inv_count, m2 = (float)sums2[C + c] * inv_count;
-    dX[n * dx_ns + r] = gamma[c] * is * (dZ[n * dz_ns + r] - m1 - xhat * m2);
+  const float* zp = dZ + (long)n * dz_ns + (long)c * HW;
+  const float* xp = X + (long)n * x_ns + (long)c * HW;
+  float* op = dX + (long)n * dx_ns + (long)c * HW;
+  const long i0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4, step = (long)gridDim.x * blockDim.x * 4;
+  if ((HW & 3) == 0) {
+    for (long i = i0; i < HW; i += step) {
+      const float4 z = *reinterpret_cast<const float4*>(zp + i);
+      const float4 x = *reinterpret_cast<const float4*>(xp + i);
+      float4 o;
+      o.x = fmaf(a, z.x, fmaf(b, x.x, k)); o.y = fmaf(a, z.y, fmaf(b, x.y, k));
+      o.z = fmaf(a, z.z, fmaf(b, x.z, k)); o.w = fmaf(a, z.w, fmaf(b, x.w, k));
+      *reinterpret_cast<float4*>(op + i) = o;
+    }
+  } else {
+    for (long i = i0 / 4; i < HW; i += step / 4) op[i] = fmaf(a, zp[i], fmaf(b, xp[i], k));
   }
 }
 
@@ -890,9 +927,9 @@ extern "C" int dmc_bn_stats_planar(const float* X, long x_ns, int C, long HW, in
 extern "C" int dmc_bn_apply_planar(const float* X, long x_ns, const float* scale, const float* shift,
                                    int C, long HW, int N, int relu, float* out, long o_ns,
                                    void* stream) {
-  const long total = (long)N * C * HW;
-  bn_apply_planar_kernel<<<ew_grid(total), 256, 0, ST_(stream)>>>(X, x_ns, scale, shift, C, HW,
-                                                                  total, relu, out, o_ns);
+  const int chunks = (int)cdiv(HW, 256 * 4 * 4) < 1 ? 1 : (int)cdiv(HW, 256 * 4 * 4);
+  bn_apply_planar_kernel<<<dim3(chunks, C, N), 256, 0, ST_(stream)>>>(X, x_ns, scale, shift, HW, relu,
+                                                                      out, o_ns);
   return dmc_check_launch("bn_apply_planar_kernel");
 }
 
@@ -914,9 +951,9 @@ extern "C" int dmc_bn_bwd_apply_planar(const float* dZ, long dz_ns, const float*
                                        const double* sums2, double count, int C, long HW, int N,
                                        float* dX, long dx_ns, float* dgamma, float* dbeta,
                                        void* stream) {
-  const long total = (long)N * C * HW;
-  bn_bwd_apply_planar_kernel<<<ew_grid(total), 256, 0, ST_(stream)>>>(
-      dZ, dz_ns, X, x_ns, mean, invstd, gamma, sums2, count, C, HW, total, dX, dx_ns, dgamma, dbeta);
+  const int chunks = (int)cdiv(HW, 256 * 4 * 4) < 1 ? 1 : (int)cdiv(HW, 256 * 4 * 4);
+  bn_bwd_apply_planar_kernel<<<dim3(chunks, C, N), 256, 0, ST_(stream)>>>(
+      dZ, dz_ns, X, x_ns, mean, invstd, gamma, sums2, count, C, HW, dX, dx_ns, dgamma, dbeta);
   return dmc_check_launch("bn_bwd_apply_planar_kernel");
 }
 
