@@ -33,7 +33,8 @@ __device__ __forceinline__ void tile_fma(const float (*As)[68], const float (*Bs
 __global__ void __launch_bounds__(256)
 simt_tap_gemm_kernel(const bf16* __restrict__ Ah, const bf16* __restrict__ Al, long a_rows, int K,
                      const bf16* __restrict__ Bh, const bf16* __restrict__ Bl, int N,
-                     float* __restrict__ D, long M, int ldD, int Hp, int Wp, SimtTaps taps) {
+                     float* __restrict__ D, long M, int ldD, int Hp, int Wp, SimtTaps taps,
+                     double* __restrict__ stats) {
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -71,7 +72,14 @@ simt_tap_gemm_kernel(const bf16* __restrict__ Ah, const bf16* __restrict__ Al, l
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < N) D[q * ldD + n] = keep ? acc[i][j] : 0.f;
+      if (n < N) {
+        const float v = keep ? acc[i][j] : 0.f;
+        D[q * ldD + n] = v;
+        if (stats && keep) {
+          atomicAdd(stats + n, (double)v);
+          atomicAdd(stats + N + n, (double)v * v);
+        }
+      }
     }
   }
 }
@@ -140,7 +148,7 @@ using namespace dmc;
 extern "C" int dmc_simt_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                                  const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
                                  long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
-                                 const int* phase, const int* bsel, void* stream) {
+                                 const int* phase, const int* bsel, double* stats, void* stream) {
   DMC_REQUIRE(ntaps >= 1 && ntaps <= 16, "simt_tap_gemm: ntaps=%d", ntaps);
   DMC_REQUIRE(K > 0 && N > 0 && M > 0 && ldD >= N, "simt_tap_gemm: bad shape");
   for (int i = 0; i < ntaps; ++i)
@@ -151,7 +159,7 @@ extern "C" int dmc_simt_tap_gemm(const void* A_hi, const void* A_lo, int a_phase
   dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64));
   simt_tap_gemm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const bf16*)A_hi, (const bf16*)A_lo, a_rows, K, (const bf16*)B_hi, (const bf16*)B_lo, N, D, M,
-      ldD, Hp, Wp, tt);
+      ldD, Hp, Wp, tt, stats);
   return dmc_check_launch("simt_tap_gemm_kernel");
 }
 

@@ -115,7 +115,8 @@ struct TapGemmWsSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int EPI_PITCH = 36;                         // floats; STS.128 conflict-free
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int RED_BYTES = 4 * 2 * BN * 4;             // per-warp column sums (BN statistics)
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + RED_BYTES + 1024 + 256;
 };
 
 template <int BN, int STAGES>
@@ -123,14 +124,15 @@ __global__ void __launch_bounds__(192, 1)
 tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
-                   int K, int Hp, int Wp, int tiles_m, int tiles_n) {
+                   int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats) {
   using S = TapGemmWsSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(smem_gen + STAGES * S::STAGE_BYTES);
-  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::EPI_BYTES;
+  float* red = reinterpret_cast<float*>(smem_gen + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::RED_BYTES;
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * STAGES;
   const uint32_t bar_tfull = bar_base + 16 * STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
@@ -216,21 +218,51 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int wq = warp & 3;
     float* stage = epi + wq * 32 * S::EPI_PITCH;
+    // fused BatchNorm statistics: lane = one column of each 32-column chunk; partial sums
+    // stay in registers while the CTA walks tiles of the same output-channel block
+    constexpr int NCH = BN / 32;
+    float cs[NCH], css[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { cs[i] = 0.f; css[i] = 0.f; }
+    int stat_n0 = -1;
+    auto flush_stats = [&](int n0f) {
+      // combine the four epilogue warps in shared memory, then one double atomic per column
+      float* mine = red + wq * 2 * BN;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        mine[i * 32 + lane] = cs[i];
+        mine[BN + i * 32 + lane] = css[i];
+        cs[i] = 0.f;
+        css[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = wq * 32 + lane; c < 2 * BN; c += 128) {
+        const float v = red[c] + red[2 * BN + c] + red[4 * BN + c] + red[6 * BN + c];
+        const int col = c < BN ? c : c - BN;
+        if (n0f + col < N) atomicAdd(stats + (c < BN ? 0 : N) + n0f + col, (double)v);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const long m0 = (long)(tile % tiles_m) * 128;
       const int n0 = (tile / tiles_m) * BN;
+      if (stats && stat_n0 != n0) {
+        if (stat_n0 >= 0) flush_stats(stat_n0);
+        stat_n0 = n0;
+      }
       const uint32_t a = j & 1, aph = (j >> 1) & 1;
       mbar_wait(bar_tfull + 8 * a, aph);
       tc_fence_after();
       const long q = m0 + wq * 32 + lane;
       const bool keep = q < M && (Hp == 0 || interior(q, Hp, Wp));
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = ci * 32;
         uint32_t r[32];
         tmem_ld32(tmem_d + a * BN + ((uint32_t)(wq * 32) << 16) + c, r);
         tmem_ld_wait();
-        if (c + 32 >= BN) {                       // accumulator fully read: hand it back to the MMA warp
+        if (ci == NCH - 1) {                      // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
@@ -245,6 +277,17 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
         }
         __syncwarp();
+        if (stats) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int row = 0; row < 32; ++row) {
+            const float v = stage[row * S::EPI_PITCH + lane];
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+          }
+          cs[ci] += s1;
+          css[ci] += s2;
+        }
         if (n0 + c < N) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -259,6 +302,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         __syncwarp();
       }
     }
+    if (stats && stat_n0 >= 0) flush_stats(stat_n0);
   }
   tc_fence_before();
   __syncthreads();
@@ -268,7 +312,8 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
 template <int BN, int STAGES>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
-                              int ldD, int K, int Hp, int Wp, int sms, cudaStream_t stream) {
+                              int ldD, int K, int Hp, int Wp, int sms, double* stats,
+                              cudaStream_t stream) {
   using S = TapGemmWsSmem<BN, STAGES>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -282,7 +327,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n);
+                                                  tiles_m, tiles_n, stats);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -491,10 +536,12 @@ static int sm_count() {
 using namespace dmc;
 
 // D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
+// stats (nullable, zeroed by the caller): double [2][N], += per-column sum and sum of squares of D
+// (the BatchNorm batch statistics of a convolution output, fused into the epilogue).
 extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                                const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
                                long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
-                               const int* phase, const int* bsel, void* stream) {
+                               const int* phase, const int* bsel, double* stats, void* stream) {
   DMC_REQUIRE(K > 0 && K % 64 == 0, "tap_gemm: K=%d must be a positive multiple of 64", K);
   DMC_REQUIRE(N > 0 && N % 32 == 0, "tap_gemm: N=%d must be a multiple of 32", N);
   DMC_REQUIRE(ldD % 4 == 0 && ldD >= N, "tap_gemm: ldD=%d", ldD);
@@ -514,10 +561,10 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
   if (BN == 64)
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, st);
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).

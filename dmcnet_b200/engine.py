@@ -92,7 +92,7 @@ class _ConvBN:
         self.Y = torch.zeros(geo_out.P, cout, **f32)
         self.act_hi = torch.zeros(geo_out.P, cout, **bf)
         self.act_lo = torch.zeros(geo_out.P, cout, **bf)
-        self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.sums = eng._alloc_sums(cout)          # zeroed in one memset per forward
         self.sums2 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
         self.scale = torch.zeros(cout, **f32)
         self.shift = torch.zeros(cout, **f32)
@@ -119,6 +119,18 @@ class DmcEngine:
         self._alloc_classifier()
         if self.gan:
             self._alloc_discriminator()
+
+    def _alloc_sums(self, cout: int) -> torch.Tensor:
+        """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
+        if not hasattr(self, '_sums_pool'):
+            self._sums_pool = torch.zeros(20 * 2 * 512, dtype=torch.float64, device=self.device)
+            self._sums_used = 0
+        n = 2 * cout
+        if self._sums_used + n > self._sums_pool.numel():
+            raise RuntimeError('BN statistics pool exhausted')
+        v = self._sums_pool[self._sums_used:self._sums_used + n].view(2, cout)
+        self._sums_used += n
+        return v
 
     # ------------------------------------------------------------------ parameters
     def _param_specs(self) -> "OrderedDict[str, Tuple[int, ...]]":
@@ -440,8 +452,7 @@ class DmcEngine:
     def _unit_bn(self, u: _ConvBN, train: bool):
         """Batch statistics (train) or running statistics (eval) -> scale/shift of unit u."""
         wk = u.name_bn
-        if train:
-            ops.bn_stats(u.Y, u.geo.P, u.cout, u.sums)
+        if train:        # batch statistics were accumulated by the conv's GEMM epilogue
             ops.bn_finalize(u.sums, u.geo.count, self.p(wk + '.weight'), self.p(wk + '.bias'),
                             self.buffers[wk + '.running_mean'], self.buffers[wk + '.running_var'],
                             self.buffers[wk + '.num_batches_tracked'], BN_MOMENTUM, 1e-5, u.cout,
@@ -451,7 +462,7 @@ class DmcEngine:
                                self.buffers[wk + '.running_mean'], self.buffers[wk + '.running_var'],
                                1e-5, u.cout, u.scale, u.shift)
 
-    def _conv_fwd(self, u: _ConvBN, a_hi, a_lo, a_phases: int):
+    def _conv_fwd(self, u: _ConvBN, a_hi, a_lo, a_phases: int, train: bool = False):
         geo = u.geo
         if u.ks == 1:
             shift, phase, bsel = [0], [0], [0]
@@ -461,7 +472,8 @@ class DmcEngine:
             shift, phase, bsel = _taps_s2(geo.Wp)
         ops.tap_gemm(a_hi, a_lo, u.W_hi, u.W_lo, u.Y, a_phases=a_phases, a_rows=geo.P, K=u.cin,
                      b_slices=u.taps, N=u.cout, M=geo.P, ldD=u.cout, Hp=geo.Hp, Wp=geo.Wp,
-                     shift=shift, phase=phase, bsel=bsel, engine=self.gemm_engine)
+                     shift=shift, phase=phase, bsel=bsel, engine=self.gemm_engine,
+                     stats=(u.sums if train else None))
 
     def _cls_forward(self, x_planar: torch.Tensor, n: int, train: bool):
         """ResNet-18 forward on a planar [n,2,H,W] input -> self.logits[:n]."""
@@ -469,6 +481,8 @@ class DmcEngine:
         if n != self.N:
             raise RuntimeError('engine was built for %d frames, got %d' % (self.N, n))
         self._prep_weights()
+        if train:
+            ops.memset_zero(self._sums_pool[:self._sums_used])
         # stem: 7x7/2 conv (planar) -> BN -> ReLU -> maxpool -> pixel-major hi/lo
         H2, W2 = H // 2, W // 2
         ops.conv_fwd(x_planar, 2 * H * W, 2, H, W, self.p('base_model.conv1.weight'), None, 64, 7, 2,
@@ -494,17 +508,17 @@ class DmcEngine:
             if 'ds' in blk:
                 gi = blk['geo_in']
                 ops.phase_split(x_hi, x_lo, n, gi.H, gi.W, blk['cin'], blk['xp_hi'], blk['xp_lo'])
-                self._conv_fwd(c1, blk['xp_hi'], blk['xp_lo'], 4)
+                self._conv_fwd(c1, blk['xp_hi'], blk['xp_lo'], 4, train)
             else:
-                self._conv_fwd(c1, x_hi, x_lo, 1)
+                self._conv_fwd(c1, x_hi, x_lo, 1, train)
             self._unit_bn(c1, train)
             ops.bn_apply(c1.Y, c1.scale, c1.shift, geo.P, c1.cout, geo.Hp, geo.Wp, True, c1.act_hi,
                          c1.act_lo)
-            self._conv_fwd(c2, c1.act_hi, c1.act_lo, 1)
+            self._conv_fwd(c2, c1.act_hi, c1.act_lo, 1, train)
             self._unit_bn(c2, train)
             if 'ds' in blk:
                 ds = blk['ds']
-                self._conv_fwd(ds, blk['xp_hi'], blk['xp_lo'], 4)
+                self._conv_fwd(ds, blk['xp_hi'], blk['xp_lo'], 4, train)
                 self._unit_bn(ds, train)
                 ops.bn_apply(c2.Y, c2.scale, c2.shift, geo.P, c2.cout, geo.Hp, geo.Wp, True, c2.act_hi,
                              c2.act_lo, resY=ds.Y, res_scale=ds.scale, res_shift=ds.shift)

@@ -82,12 +82,12 @@ F32, BF16, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int64, torch.uint
 
 # ---------------------------------------------------------------- tap GEMMs
 def tap_gemm(A_hi, A_lo, B_hi, B_lo, D, *, a_phases, a_rows, K, b_slices, N, M, ldD, Hp, Wp,
-             shift, phase, bsel, engine='tc'):
+             shift, phase, bsel, engine='tc', stats=None):
     name = 'dmc_tc_tap_gemm' if engine == 'tc' else 'dmc_simt_tap_gemm'
     _call(name, _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(a_phases), c_long(a_rows), c_int(K),
           _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M),
           c_int(ldD), c_int(Hp), c_int(Wp), c_int(len(shift)), _iarr(shift), _iarr(phase),
-          _iarr(bsel), _stream())
+          _iarr(bsel), _ptr(stats, F64), _stream())
 
 
 def wgrad_gemm(G_hi, G_lo, X_hi, X_lo, dW, *, P, Cout, x_phases, Cin, shift, phase, bsel,

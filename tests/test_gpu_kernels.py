@@ -125,9 +125,14 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
     else:
         A_hi, A_lo = xp_hi, xp_lo
     D = torch.full((P, cout), float('nan'), device='cuda')
+    stats = torch.zeros(2, cout, dtype=torch.float64, device='cuda')
     ops.tap_gemm(A_hi, A_lo, W_hi, W_lo, D, a_phases=phases, a_rows=P, K=cin, b_slices=9, N=cout, M=P,
-                 ldD=cout, Hp=Hp, Wp=Wp, shift=shift, phase=phase, bsel=bsel, engine=engine)
+                 ldD=cout, Hp=Hp, Wp=Wp, shift=shift, phase=phase, bsel=bsel, engine=engine, stats=stats)
     assert rel(from_pixel(D, n, cout, ho, ho), y.detach()) < 5e-5
+    # fused BatchNorm batch statistics (per-channel sum and sum of squares of the conv output)
+    yd = y.detach().double()
+    assert rel(stats[0], yd.sum((0, 2, 3))) < 5e-5 * (n * ho * ho) ** 0.5
+    assert rel(stats[1], (yd * yd).sum((0, 2, 3))) < 5e-5
     ring = D.view(n, Hp, Wp, cout).clone()
     ring[:, 1:-1, 1:-1] = 0
     assert float(ring.abs().max()) == 0.0                         # epilogue keeps the zero ring
