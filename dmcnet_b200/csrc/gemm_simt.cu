@@ -148,8 +148,12 @@ using namespace dmc;
 extern "C" int dmc_simt_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                                  const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
                                  long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
-                                 const int* phase, const int* bsel, double* stats, void* stream) {
+                                 const int* phase, const int* bsel, double* stats, const float* bw_Y,
+                                 const void* bw_act_hi, const float* bw_gb, const float* bw_mean,
+                                 const float* bw_invstd, void* stream) {
   DMC_REQUIRE(ntaps >= 1 && ntaps <= 16, "simt_tap_gemm: ntaps=%d", ntaps);
+  DMC_REQUIRE(bw_Y == nullptr, "simt_tap_gemm: the fused BN-backward epilogue exists only in the tensor-core kernel");
+  (void)bw_act_hi; (void)bw_gb; (void)bw_mean; (void)bw_invstd;
   DMC_REQUIRE(K > 0 && N > 0 && M > 0 && ldD >= N, "simt_tap_gemm: bad shape");
   for (int i = 0; i < ntaps; ++i)
     DMC_REQUIRE(phase[i] >= 0 && phase[i] < a_phases && bsel[i] >= 0 && bsel[i] < b_slices,

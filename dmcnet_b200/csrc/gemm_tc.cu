@@ -108,6 +108,19 @@ static int sm_count();
 // thread each), warps 2..5 = epilogue.  Two fp32 accumulators live in TMEM, so
 // the epilogue of tile j (tcgen05.ld -> ring mask -> shared-memory transpose ->
 // 128-byte coalesced global stores) overlaps the MMAs of tile j+1.
+// Optional fused BatchNorm-backward reduction in the epilogue of a data-gradient GEMM: the tile
+// D = dX (gradient w.r.t. the activation a = relu(bn(Y) [+ residual])) is turned into
+//   dz = (D + gb) * [act > 0]            (written instead of D)
+// and sums[0][c] += sum dz, sums[1][c] += sum dz * (Y - mean) * invstd are accumulated, which is
+// everything the BN backward needs besides one more elementwise pass.
+struct BwFuse {
+  const float* Y;        // raw conv output of the BN being differentiated, [M][N]; null = off
+  const bf16* act_hi;    // hi plane of the activation (ReLU mask)
+  const float* gb;       // second gradient source (residual branch) or null
+  const float* mean;
+  const float* invstd;
+};
+
 template <int BN, int STAGES>
 struct TapGemmWsSmem {
   static constexpr int A_BYTES = 128 * 128;
@@ -124,7 +137,8 @@ __global__ void __launch_bounds__(192, 1)
 tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
-                   int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats) {
+                   int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
+                   const BwFuse bw) {
   using S = TapGemmWsSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -221,19 +235,41 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     // fused BatchNorm statistics: lane = one column of each 32-column chunk; partial sums
     // stay in registers while the CTA walks tiles of the same output-channel block
     constexpr int NCH = BN / 32;
-    float cs[NCH], css[NCH];
+    float cs[NCH], css[NCH];          // forward statistics: lane = column of the chunk
+    float bs1[NCH][4], bs2[NCH][4];   // fused BN backward: lane owns 4 columns ((lane & 7) * 4 ..)
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) { cs[i] = 0.f; css[i] = 0.f; }
+    for (int i = 0; i < NCH; ++i) {
+      cs[i] = 0.f; css[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { bs1[i][k] = 0.f; bs2[i][k] = 0.f; }
+    }
+    const bool bwd = bw.Y != nullptr;
     int stat_n0 = -1;
     auto flush_stats = [&](int n0f) {
       // combine the four epilogue warps in shared memory, then one double atomic per column
       float* mine = red + wq * 2 * BN;
+      if (bwd) {
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        mine[i * 32 + lane] = cs[i];
-        mine[BN + i * 32 + lane] = css[i];
-        cs[i] = 0.f;
-        css[i] = 0.f;
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float a = bs1[i][k], b = bs2[i][k];
+            a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+            if (lane < 8) {
+              mine[i * 32 + lane * 4 + k] = a;
+              mine[BN + i * 32 + lane * 4 + k] = b;
+            }
+            bs1[i][k] = 0.f; bs2[i][k] = 0.f;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          mine[i * 32 + lane] = cs[i];
+          mine[BN + i * 32 + lane] = css[i];
+          cs[i] = 0.f;
+          css[i] = 0.f;
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = wq * 32 + lane; c < 2 * BN; c += 128) {
@@ -277,7 +313,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
         }
         __syncwarp();
-        if (stats) {
+        if (stats && !bwd) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
           for (int row = 0; row < 32; ++row) {
@@ -289,13 +325,66 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           css[ci] += s2;
         }
         if (n0 + c < N) {
+          const int c4 = (lane & 7) * 4;
+          float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu;
+          if (bwd) {
+            mu = *reinterpret_cast<const float4*>(bw.mean + n0 + c + c4);
+            is = *reinterpret_cast<const float4*>(bw.invstd + n0 + c + c4);
+          }
+          if (!bwd) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
-            const long gq = m0 + wq * 32 + row;
-            if (gq < M) {
-              const float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
-              *reinterpret_cast<float4*>(D + gq * (long)ldD + n0 + c + c4) = v;
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);
+              const long gq = m0 + wq * 32 + row;
+              if (gq < M) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
+                *reinterpret_cast<float4*>(D + gq * (long)ldD + n0 + c + c4) = v;
+              }
+            }
+          } else {
+            // two batches of four rows: all global loads of a batch are issued before any use,
+            // so the epilogue warp keeps 12 independent requests in flight
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              float4 yv[4], gv[4];
+              uint2 hv[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int row = (hb * 4 + ii) * 4 + (lane >> 3);
+                const long gq = m0 + wq * 32 + row;
+                const long off = gq * (long)ldD + n0 + c + c4;
+                yv[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+                gv[ii] = yv[ii];
+                hv[ii] = make_uint2(0u, 0u);
+                if (gq < M) {
+                  yv[ii] = __ldg(reinterpret_cast<const float4*>(bw.Y + off));
+                  hv[ii] = __ldg(reinterpret_cast<const uint2*>(bw.act_hi + off));
+                  if (bw.gb) gv[ii] = __ldg(reinterpret_cast<const float4*>(bw.gb + off));
+                }
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int row = (hb * 4 + ii) * 4 + (lane >> 3);
+                const long gq = m0 + wq * 32 + row;
+                if (gq < M) {
+                  float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
+                  const long off = gq * (long)ldD + n0 + c + c4;
+                  v.x += gv[ii].x; v.y += gv[ii].y; v.z += gv[ii].z; v.w += gv[ii].w;
+                  const uint2 hraw = hv[ii];
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  v.x = ((hraw.x & 0x8000u) == 0 && (hraw.x & 0x7fffu) != 0) ? v.x : 0.f;
+                  v.y = ((hraw.x & 0x80000000u) == 0 && (hraw.x & 0x7fff0000u) != 0) ? v.y : 0.f;
+                  v.z = ((hraw.y & 0x8000u) == 0 && (hraw.y & 0x7fffu) != 0) ? v.z : 0.f;
+                  v.w = ((hraw.y & 0x80000000u) == 0 && (hraw.y & 0x7fff0000u) != 0) ? v.w : 0.f;
+                  const float4 y = yv[ii];
+                  bs1[ci][0] += v.x; bs1[ci][1] += v.y; bs1[ci][2] += v.z; bs1[ci][3] += v.w;
+                  bs2[ci][0] = fmaf(v.x, (y.x - mu.x) * is.x, bs2[ci][0]);
+                  bs2[ci][1] = fmaf(v.y, (y.y - mu.y) * is.y, bs2[ci][1]);
+                  bs2[ci][2] = fmaf(v.z, (y.z - mu.z) * is.z, bs2[ci][2]);
+                  bs2[ci][3] = fmaf(v.w, (y.w - mu.w) * is.w, bs2[ci][3]);
+                  *reinterpret_cast<float4*>(D + off) = v;
+                }
+              }
             }
           }
         }
@@ -313,7 +402,7 @@ template <int BN, int STAGES>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
-                              cudaStream_t stream) {
+                              const BwFuse& bw, cudaStream_t stream) {
   using S = TapGemmWsSmem<BN, STAGES>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -327,7 +416,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n, stats);
+                                                  tiles_m, tiles_n, stats, bw);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -538,10 +627,18 @@ using namespace dmc;
 // D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
 // stats (nullable, zeroed by the caller): double [2][N], += per-column sum and sum of squares of D
 // (the BatchNorm batch statistics of a convolution output, fused into the epilogue).
+// bw_Y != null switches the epilogue to the fused BatchNorm-backward reduction (see BwFuse):
+// D receives dz = (D + bw_gb) * [bw_act_hi > 0] and stats[0]/[1] += sum dz / sum dz * xhat.
 extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                                const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
                                long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
-                               const int* phase, const int* bsel, double* stats, void* stream) {
+                               const int* phase, const int* bsel, double* stats, const float* bw_Y,
+                               const void* bw_act_hi, const float* bw_gb, const float* bw_mean,
+                               const float* bw_invstd, void* stream) {
+  DMC_REQUIRE(bw_Y == nullptr || (stats && bw_act_hi && bw_mean && bw_invstd && ldD == N),
+              "tap_gemm: fused BN backward needs stats, act, mean, invstd and ldD == N");
+  BwFuse bw;
+  bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
   DMC_REQUIRE(K > 0 && K % 64 == 0, "tap_gemm: K=%d must be a positive multiple of 64", K);
   DMC_REQUIRE(N > 0 && N % 32 == 0, "tap_gemm: N=%d must be a multiple of 32", N);
   DMC_REQUIRE(ldD % 4 == 0 && ldD >= N, "tap_gemm: ldD=%d", ldD);
@@ -561,10 +658,10 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
   if (BN == 64)
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).

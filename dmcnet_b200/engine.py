@@ -93,7 +93,7 @@ class _ConvBN:
         self.act_hi = torch.zeros(geo_out.P, cout, **bf)
         self.act_lo = torch.zeros(geo_out.P, cout, **bf)
         self.sums = eng._alloc_sums(cout)          # zeroed in one memset per forward
-        self.sums2 = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.sums2 = eng._alloc_sums(cout, bwd=True)   # zeroed in one memset per backward
         self.scale = torch.zeros(cout, **f32)
         self.shift = torch.zeros(cout, **f32)
         self.mean = torch.zeros(cout, **f32)
@@ -120,16 +120,22 @@ class DmcEngine:
         if self.gan:
             self._alloc_discriminator()
 
-    def _alloc_sums(self, cout: int) -> torch.Tensor:
+    def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
         if not hasattr(self, '_sums_pool'):
             self._sums_pool = torch.zeros(20 * 2 * 512, dtype=torch.float64, device=self.device)
+            self._sums2_pool = torch.zeros(20 * 2 * 512, dtype=torch.float64, device=self.device)
             self._sums_used = 0
+            self._sums2_used = 0
         n = 2 * cout
-        if self._sums_used + n > self._sums_pool.numel():
+        pool, used = (self._sums2_pool, self._sums2_used) if bwd else (self._sums_pool, self._sums_used)
+        if used + n > pool.numel():
             raise RuntimeError('BN statistics pool exhausted')
-        v = self._sums_pool[self._sums_used:self._sums_used + n].view(2, cout)
-        self._sums_used += n
+        v = pool[used:used + n].view(2, cout)
+        if bwd:
+            self._sums2_used += n
+        else:
+            self._sums_used += n
         return v
 
     # ------------------------------------------------------------------ parameters
@@ -539,6 +545,13 @@ class DmcEngine:
                          geo.count, geo.P, u.cout, geo.Hp, geo.Wp, G_hi, G_lo, dz_out,
                          self.g(wk + '.weight'), self.g(wk + '.bias'))
 
+    def _bn_bwd_apply_only(self, u: _ConvBN, dz, G_hi, G_lo):
+        """BN backward when dz (masked gradient) and u.sums2 were produced by a fused GEMM epilogue."""
+        geo, wk = u.geo, u.name_bn
+        ops.bn_bwd_apply(dz, None, None, u.Y, u.mean, u.invstd, self.p(wk + '.weight'), u.sums2, geo.count,
+                         geo.P, u.cout, geo.Hp, geo.Wp, G_hi, G_lo, None, self.g(wk + '.weight'),
+                         self.g(wk + '.bias'))
+
     def _conv_wgrad(self, u: _ConvBN, G_hi, G_lo, x_hi, x_lo, x_phases: int):
         geo = u.geo
         if u.ks == 1:
@@ -563,9 +576,13 @@ class DmcEngine:
                        self.d_pooled, self.g('base_model.fc.weight') if need_wgrad else None,
                        self.g('base_model.fc.bias') if need_wgrad else None)
         T1, T2a, Ra, T2b, Rb = self.gbuf
+        fuse = self.gemm_engine == 'tc'         # fused BN-backward epilogue exists in the tcgen05 kernel
+        ops.memset_zero(self._sums2_pool[:self._sums2_used])
         g_a = T2a[:gl.P * 512]
         ops.avgpool_bwd(self.d_pooled, n, gl.Hp, gl.Wp, 512, g_a)
         g_b = None
+        g_is_dz = False    # True: g_a already holds dz = relu'(x_out) * (sum of gradients) of THIS block's
+                           # output and c2.sums2 was accumulated by the GEMM epilogue that produced it
         flip = False       # which (T2, R) pair the CURRENT block writes
         for bi in reversed(range(len(self.blocks))):
             blk = self.blocks[bi]
@@ -577,25 +594,34 @@ class DmcEngine:
             pc = geo.P * width
             G_hi, G_lo = self.G_hi[:pc], self.G_lo[:pc]
             has_ds = 'ds' in blk
-            # bn2 backward; the masked gradient dz also feeds the identity / downsample branch
-            self._unit_bn_bwd(c2, g_a, g_b, c2.act_hi, G_hi, G_lo, None if has_ds else R[:pc])
-            if getattr(self, 'debug_capture', False) and bi == len(self.blocks) - 1:
-                self.debug = {'g_a': g_a.clone(), 'sums2': c2.sums2.clone(), 'G': G_hi.float() + G_lo.float(),
-                              'dz': R[:pc].clone(), 'act': c2.act_hi.float() + c2.act_lo.float(),
-                              'Y': c2.Y.clone(), 'mean': c2.mean.clone(), 'invstd': c2.invstd.clone(),
-                              'd_pooled': self.d_pooled.clone()}
+            # ---- bn2 backward (dz also feeds the identity / downsample branch)
+            if g_is_dz:
+                dz = g_a                                       # masked + summed already, sums2 ready
+                self._bn_bwd_apply_only(c2, dz, G_hi, G_lo)
+            else:
+                dz = None if has_ds else R[:pc]
+                self._unit_bn_bwd(c2, g_a, g_b, c2.act_hi, G_hi, G_lo, dz)
             if need_wgrad:
                 self._conv_wgrad(c2, G_hi, G_lo, c1.act_hi, c1.act_lo, 1)
+            # ---- conv2 dgrad -> dz1 (bn1's ReLU mask and both reductions fused into the epilogue)
             shift, phase, bsel = _taps_s1(geo.Wp)
+            bw1 = (c1.Y, c1.act_hi, None, c1.mean, c1.invstd) if fuse else None
             ops.tap_gemm(G_hi, G_lo, c2.Wt_hi, c2.Wt_lo, T1[:pc], a_phases=1, a_rows=geo.P, K=width,
                          b_slices=9, N=width, M=geo.P, ldD=width, Hp=geo.Hp, Wp=geo.Wp,
-                         shift=[-s for s in shift], phase=phase, bsel=bsel, engine=self.gemm_engine)
+                         shift=[-s for s in shift], phase=phase, bsel=bsel, engine=self.gemm_engine,
+                         stats=(c1.sums2 if fuse else None), bw=bw1)
             if has_ds:
                 ds = blk['ds']
                 Gp_hi, Gp_lo = self.G_hi[:2 * pc].view(2, pc), self.G_lo[:2 * pc].view(2, pc)
-                # downsample BN backward (same dz) -> slot 1 ; bn1 backward -> slot 0
-                self._unit_bn_bwd(ds, g_a, g_b, c2.act_hi, Gp_hi[1], Gp_lo[1], None)
-                self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, Gp_hi[0], Gp_lo[0], None)
+                # downsample BN backward (same dz as bn2) -> slot 1 ; bn1 backward -> slot 0
+                if g_is_dz:
+                    self._unit_bn_bwd(ds, g_a, None, None, Gp_hi[1], Gp_lo[1], None)
+                else:
+                    self._unit_bn_bwd(ds, g_a, g_b, c2.act_hi, Gp_hi[1], Gp_lo[1], None)
+                if fuse:
+                    self._bn_bwd_apply_only(c1, T1[:pc], Gp_hi[0], Gp_lo[0])
+                else:
+                    self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, Gp_hi[0], Gp_lo[0], None)
                 if need_wgrad:
                     self._conv_wgrad(c1, Gp_hi[0], Gp_lo[0], blk['xp_hi'], blk['xp_lo'], 4)
                     self._conv_wgrad(ds, Gp_hi[1], Gp_lo[1], blk['xp_hi'], blk['xp_lo'], 4)
@@ -614,17 +640,30 @@ class DmcEngine:
                 gi = blk['geo_in']
                 g_a = T2[:gi.P * cin]
                 ops.phase_unsplit(blk['dxp'], n, gi.H, gi.W, cin, g_a)
-                g_b = None
+                g_b, g_is_dz = None, False
             else:
-                self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, G_hi, G_lo, None)
+                if fuse:
+                    self._bn_bwd_apply_only(c1, T1[:pc], G_hi, G_lo)
+                else:
+                    self._unit_bn_bwd(c1, T1[:pc], None, c1.act_hi, G_hi, G_lo, None)
                 if need_wgrad:
                     self._conv_wgrad(c1, G_hi, G_lo, x_hi, x_lo, 1)
+                res = dz if dz is not None else None       # gradient of the identity branch
                 g_a = T2[:pc]
-                ops.tap_gemm(G_hi, G_lo, c1.Wt_hi, c1.Wt_lo, g_a, a_phases=1, a_rows=geo.P, K=width,
-                             b_slices=9, N=cin, M=geo.P, ldD=cin, Hp=geo.Hp, Wp=geo.Wp,
-                             shift=[-s for s in shift], phase=phase, bsel=bsel,
-                             engine=self.gemm_engine)
-                g_b = R[:pc]
+                if fuse and bi > 0:
+                    # conv1 dgrad: the epilogue adds the identity-branch gradient, applies the ReLU mask of
+                    # the PREVIOUS block's output and reduces for its bn2 -> g_a is that block's dz
+                    pb = self.blocks[bi - 1]['c2']
+                    ops.tap_gemm(G_hi, G_lo, c1.Wt_hi, c1.Wt_lo, g_a, a_phases=1, a_rows=geo.P, K=width,
+                                 b_slices=9, N=cin, M=geo.P, ldD=cin, Hp=geo.Hp, Wp=geo.Wp,
+                                 shift=[-s for s in shift], phase=phase, bsel=bsel, engine=self.gemm_engine,
+                                 stats=pb.sums2, bw=(pb.Y, pb.act_hi, res, pb.mean, pb.invstd))
+                    g_b, g_is_dz = None, True
+                else:
+                    ops.tap_gemm(G_hi, G_lo, c1.Wt_hi, c1.Wt_lo, g_a, a_phases=1, a_rows=geo.P, K=width,
+                                 b_slices=9, N=cin, M=geo.P, ldD=cin, Hp=geo.Hp, Wp=geo.Wp,
+                                 shift=[-s for s in shift], phase=phase, bsel=bsel, engine=self.gemm_engine)
+                    g_b, g_is_dz = res, False
         # stem backward
         H, W = self.H, self.W
         H2, W2 = H // 2, W // 2

@@ -82,12 +82,15 @@ F32, BF16, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int64, torch.uint
 
 # ---------------------------------------------------------------- tap GEMMs
 def tap_gemm(A_hi, A_lo, B_hi, B_lo, D, *, a_phases, a_rows, K, b_slices, N, M, ldD, Hp, Wp,
-             shift, phase, bsel, engine='tc', stats=None):
+             shift, phase, bsel, engine='tc', stats=None, bw=None):
+    """bw = (Y, act_hi, gb_or_None, mean, invstd): fused BatchNorm-backward reduction (tc engine)."""
+    bY, bact, bgb, bmean, binv = bw if bw is not None else (None, None, None, None, None)
     name = 'dmc_tc_tap_gemm' if engine == 'tc' else 'dmc_simt_tap_gemm'
     _call(name, _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(a_phases), c_long(a_rows), c_int(K),
           _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M),
           c_int(ldD), c_int(Hp), c_int(Wp), c_int(len(shift)), _iarr(shift), _iarr(phase),
-          _iarr(bsel), _ptr(stats, F64), _stream())
+          _iarr(bsel), _ptr(stats, F64), _ptr(bY, F32), _ptr(bact, BF16), _ptr(bgb, F32),
+          _ptr(bmean, F32), _ptr(binv, F32), _stream())
 
 
 def wgrad_gemm(G_hi, G_lo, X_hi, X_lo, dW, *, P, Cout, x_phases, Cin, shift, phase, bsel,
