@@ -78,6 +78,16 @@ def _flops(name, args):
     return 0.0
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_tap_gemm_traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r01_tap_gemm_traffic.json')
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f).get('dram_bytes_per_launch_avg')
+    return None
+
+
 def measure_roofline(resident_step, per, steps, trainer):
     """Run `steps` instrumented eager steps; return the dominant family's roofline
     and the per-family time breakdown (ms per train step)."""
@@ -107,10 +117,11 @@ def measure_roofline(resident_step, per, steps, trainer):
     out['roofline'] = {
         'kernel': fam.replace('dmc_', '') + '_kernel', 'bound': 'tensor', 'achieved': achieved,
         'peak': peaks['tensor_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_tflops'],
-        'traffic': None, 'launches_per_step': cnt[fam] / denom, 'avg_launch_ms': t_ms / max(cnt[fam], 1),
+        'traffic': measured_traffic(), 'launches_per_step': cnt[fam] / denom, 'avg_launch_ms': t_ms / max(cnt[fam], 1),
         'share_of_step': t_ms / max(sum(ms.values()), 1e-9),
         'peak_source': peaks['source'],
-        'note': 'algorithmic FLOPs (padding ring excluded); bf16x3 split issues 3 MMAs per MAC -> ceiling 1/3',
+        'note': 'algorithmic FLOPs (padding ring excluded); bf16x3 split issues 3 MMAs per MAC -> ceiling 1/3; '
+                'traffic = DRAM bytes per launch (bytes) from the committed ncu capture',
     }
     others = {}
     for k in ms:
