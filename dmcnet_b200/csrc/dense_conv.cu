@@ -36,9 +36,10 @@ conv_fwd_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int W,
   const int n = blockIdx.z;
   const int ih0 = th0 * ST - PAD, iw0 = tw0 * ST - PAD;
   const float* inp = in + (long)n * in_ns;
-  float acc[COG];
+  static_assert(COG % 2 == 0, "COG must be even");
+  float2 acc[COG / 2];               // output-channel pairs -> packed FFMA2
 #pragma unroll
-  for (int g = 0; g < COG; ++g) acc[g] = 0.f;
+  for (int g = 0; g < COG / 2; ++g) acc[g] = make_float2(0.f, 0.f);
 
   for (int c0 = 0; c0 < Cin; c0 += CK) {
     for (int i = tid; i < CK * IT * IT; i += 256) {
@@ -63,8 +64,10 @@ conv_fwd_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int W,
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
           const float v = in_s[c][ty * ST + r][tx * ST + s];
+          const float2 vv = make_float2(v, v);
+          const float2* wp = reinterpret_cast<const float2*>(&w_s[c][r * KS + s][0]);
 #pragma unroll
-          for (int g = 0; g < COG; ++g) acc[g] = fmaf(v, w_s[c][r * KS + s][g], acc[g]);
+          for (int g = 0; g < COG / 2; ++g) acc[g] = __ffma2_rn(vv, wp[g], acc[g]);
         }
     }
     __syncthreads();
@@ -75,7 +78,7 @@ conv_fwd_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int W,
   for (int g = 0; g < COG; ++g) {
     const int co = co0 + g;
     if (co >= Cout) break;
-    float v = acc[g] + (bias ? bias[co] : 0.f);
+    float v = ((g & 1) ? acc[g / 2].y : acc[g / 2].x) + (bias ? bias[co] : 0.f);
     v = v < 0.f ? v * slope : v;
     if (mask) v *= mask[(long)n * Cout + co];
     const long o = (long)n * out_ns + ((long)co * Ho + oh) * Wo + ow;
@@ -785,6 +788,126 @@ static int ew_grid(long total) {
   return (int)b;
 }
 
+// Stride-2 variant: moving one output pixel to the right shifts the input window by exactly
+// one float2, so the window and the accumulators are kept as column PAIRS and every update
+// is a packed FFMA2 (KS padded to the next even width; the pad column is discarded).
+template <int KS, int COC, int CIC>
+__global__ void __launch_bounds__(COC * CIC)
+conv_wgrad_s2_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int W,
+                     const float* __restrict__ dY, long dy_ns, int Cout, int Ho, int Wo,
+                     float* __restrict__ dW, float* __restrict__ dbias, int N, int ci_groups) {
+  constexpr int PAD = KS / 2;
+  constexpr int TO = 8;                          // output tile side
+  constexpr int IT = (TO - 1) * 2 + KS;          // input tile side
+  constexpr int ITP = IT + (IT & 1);             // even row pitch -> 8-byte aligned pairs
+  constexpr int ICH = ITP * IT;                  // = 2 * odd for KS = 3, 7 -> conflict-free LDS.64
+  constexpr int DCH = (TO * TO) | 1;
+  constexpr int NP = (KS + 1) / 2;               // column pairs per window row
+  constexpr int NT = COC * CIC;
+  extern __shared__ __align__(16) float smem[];
+  float* in_s = smem;                            // [CIC][ICH]
+  float* dy_s = smem + CIC * ICH;                // [COC][DCH]
+  const int tid = threadIdx.x;
+  const int lco = tid / CIC, lci = tid % CIC;
+  const int co0 = (blockIdx.y / ci_groups) * COC, ci0 = (blockIdx.y % ci_groups) * CIC;
+  const int co = co0 + lco, ci = ci0 + lci;
+  const int tiles_x = (Wo + TO - 1) / TO, tiles_y = (Ho + TO - 1) / TO;
+  const long items = (long)N * tiles_x * tiles_y;
+  float2 acc[KS][NP];
+#pragma unroll
+  for (int r = 0; r < KS; ++r)
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc[r][j] = make_float2(0.f, 0.f);
+  float bsum = 0.f;
+
+  for (long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int n = (int)(item / (tiles_x * tiles_y));
+    const int t = (int)(item % (tiles_x * tiles_y));
+    const int oh0 = (t / tiles_x) * TO, ow0 = (t % tiles_x) * TO;
+    const int ih0 = oh0 * 2 - PAD, iw0 = ow0 * 2 - PAD;
+    const float* inp = in + (long)n * in_ns;
+    const float* dyp = dY + (long)n * dy_ns;
+    for (int i = tid; i < CIC * IT * ITP; i += NT) {
+      const int c = i / (IT * ITP), r = (i / ITP) % IT, s3 = i % ITP;
+      const int ih = ih0 + r, iw = iw0 + s3;
+      float v = 0.f;
+      if (s3 < IT && ci0 + c < Cin && ih >= 0 && ih < H && iw >= 0 && iw < W)
+        v = inp[((long)(ci0 + c) * H + ih) * W + iw];
+      in_s[c * ICH + r * ITP + s3] = v;
+    }
+    for (int i = tid; i < COC * TO * TO; i += NT) {
+      const int c = i / (TO * TO), r = (i / TO) % TO, s3 = i % TO;
+      const int oh = oh0 + r, ow = ow0 + s3;
+      float v = 0.f;
+      if (co0 + c < Cout && oh < Ho && ow < Wo) v = dyp[((long)(co0 + c) * Ho + oh) * Wo + ow];
+      dy_s[c * DCH + r * TO + s3] = v;
+    }
+    __syncthreads();
+    const float* ip = in_s + lci * ICH;
+    const float* dp = dy_s + lco * DCH;
+#pragma unroll 1
+    for (int y = 0; y < TO; ++y) {
+      float2 win[KS][NP];
+#pragma unroll
+      for (int r = 0; r < KS; ++r)
+#pragma unroll
+        for (int j = 0; j + 1 < NP; ++j)
+          win[r][j + 1] = *reinterpret_cast<const float2*>(ip + (y * 2 + r) * ITP + 2 * j);
+#pragma unroll
+      for (int x = 0; x < TO; ++x) {
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+#pragma unroll
+          for (int j = 0; j + 1 < NP; ++j) win[r][j] = win[r][j + 1];
+          win[r][NP - 1] = *reinterpret_cast<const float2*>(ip + (y * 2 + r) * ITP + 2 * x + 2 * (NP - 1));
+        }
+        const float d = dp[y * TO + x];
+        bsum += d;
+        const float2 dd = make_float2(d, d);
+#pragma unroll
+        for (int r = 0; r < KS; ++r)
+#pragma unroll
+          for (int j = 0; j < NP; ++j) acc[r][j] = __ffma2_rn(dd, win[r][j], acc[r][j]);
+      }
+    }
+    __syncthreads();
+  }
+  if (co < Cout && ci < Cin) {
+    float* wp = dW + ((long)co * Cin + ci) * (KS * KS);
+#pragma unroll
+    for (int r = 0; r < KS; ++r)
+#pragma unroll
+      for (int s3 = 0; s3 < KS; ++s3)
+        atomicAdd(wp + r * KS + s3, (s3 & 1) ? acc[r][s3 / 2].y : acc[r][s3 / 2].x);
+    if (dbias && ci == 0) atomicAdd(dbias + co, bsum);
+  }
+}
+
+template <int KS, int COC, int CIC>
+static int launch_wgrad_s2(const float* in, long in_ns, int Cin, int H, int W, const float* dY,
+                           long dy_ns, int Cout, int Ho, int Wo, float* dW, float* dbias, int N,
+                           cudaStream_t st) {
+  constexpr int TO = 8, IT = (TO - 1) * 2 + KS, ITP = IT + (IT & 1);
+  constexpr int ICH = ITP * IT, DCH = (TO * TO) | 1;
+  const int smem = (CIC * ICH + COC * DCH) * (int)sizeof(float);
+  auto kern = conv_wgrad_s2_kernel<KS, COC, CIC>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return dmc_check_launch("conv_wgrad_s2 smem attribute");
+    attr = true;
+  }
+  const int co_groups = (int)cdiv(Cout, COC), ci_groups = (int)cdiv(Cin, CIC);
+  const long items = (long)N * cdiv(Wo, TO) * cdiv(Ho, TO);
+  long gx = cdiv(148L * 4, (long)co_groups * ci_groups);
+  if (gx < 1) gx = 1;
+  if (gx > items) gx = items;
+  dim3 grid((unsigned)gx, (unsigned)(co_groups * ci_groups));
+  kern<<<grid, COC * CIC, smem, st>>>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N,
+                                      ci_groups);
+  return dmc_check_launch("conv_wgrad_s2_kernel");
+}
+
 template <int KS, int ST, int COC, int CIC>
 static int launch_wgrad(const float* in, long in_ns, int Cin, int H, int W, const float* dY,
                         long dy_ns, int Cout, int Ho, int Wo, float* dW, float* dbias, int N,
@@ -900,8 +1023,8 @@ extern "C" int dmc_conv_wgrad(const float* in, long in_ns, int Cin, int H, int W
   if (ks == 3 && stride == 1)
     return launch_wgrad<3, 1, 8, 32>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
   if (ks == 3)
-    return launch_wgrad<3, 2, 8, 32>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
-  return launch_wgrad<7, 2, 64, 2>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
+    return launch_wgrad_s2<3, 8, 32>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
+  return launch_wgrad_s2<7, 64, 2>(in, in_ns, Cin, H, W, dY, dy_ns, Cout, Ho, Wo, dW, dbias, N, st);
 }
 
 extern "C" int dmc_act_bwd_planar(const float* dA, long da_ns, const float* A, long a_ns,
