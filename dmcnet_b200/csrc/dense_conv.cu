@@ -257,195 +257,258 @@ conv_wgrad_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int 
 }
 
 // ------------------------------------------------------------------ 3x3 stride-1, register-tiled
-// Thread = PX consecutive output pixels of one row x COG output channels
-// (PX*COG accumulators); the input strip comes in as one 128-bit shared load
-// plus two neighbours per (channel, kernel row), weights as broadcast vector
-// loads -> ~1 shared-memory wavefront per 8 FMAs, i.e. FMA-pipe bound.
-template <int COG, int PX>
-struct FwdV2Cfg {
-  static constexpr int CK = 8;
-  static constexpr int SPR = 32 / PX;          // strips per tile row
-  static constexpr int TH = 128 / SPR;         // tile rows (16 for PX=4, 32 for PX=8)
-  static constexpr int PITCH = 40;             // 4 + 32 + 4 columns
-  static constexpr int COGP = (COG + 3) / 4 * 4;
-  static constexpr int BUF = CK * (TH + 2) * PITCH;   // floats per stage
-  static int smem_bytes(int Cin) { return 128 + 2 * BUF * 4 + Cin * 9 * COGP * 4 + 64; }
+// Measured on B200 (tools/ubench/pipes.cu): the SM retires 1 shared-memory wavefront and
+// 128 fp32 FMAs per clock; FFMA2 has the same FMA rate as FFMA but needs half the issue
+// slots; a shuffle costs one wavefront; a 128-bit load whose lanes are 32 bytes apart is
+// 2-way bank conflicted, halo loads 4 floats apart 4- to 8-way.  So the kernel is built
+// to spend < 1 wavefront per 4 FFMA2:
+//   * thread = 4 consecutive pixels x R rows x COG output channels; the 8 lanes of a
+//     quarter-warp read one tile row as consecutive 128-bit words (conflict free),
+//   * the left/right halo pixel comes from the neighbour lane by shuffle; only the two
+//     edge lanes of a row touch shared memory for it,
+//   * each input row is loaded once and feeds the (up to) three output rows it overlaps,
+//   * the 9*COG weights of the current input channel live in registers.
+// Tile = 32 x 32 output pixels; block = 8/R warps; input rows arrive by TMA (4-D tiled
+// map, zero fill = conv padding) into a two-stage ring of CK channels.
+template <int COG, int R, int CK, int NS>
+struct FwdV3Cfg {
+  static constexpr int TH = 32, PITCH = 40, ROWS = TH + 2;
+  static constexpr int NT = 32 * (8 / R);
+  static constexpr int WPC = (9 * COG + 3) / 4 * 4;            // weight floats per input channel
+  static constexpr int BUF = (CK * ROWS * PITCH + 31) / 32 * 32;   // floats per stage (128-byte multiple)
+  static int smem_bytes(int Cin) { return 128 + NS * BUF * 4 + Cin * WPC * 4 + 8 * NS + 64; }
 };
 
-// Input tiles arrive by TMA (4-D tiled map over [N][C][H][W], zero fill outside the
-// image = the conv padding) into a two-stage ring; the weights of this output
-// group are staged once.
-template <int COG, int PX>
-__global__ void __launch_bounds__(128)
-conv3x3_fwd_v2_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int ckb, int H, int W,
+// grid.x CTAs walk the (frame, tile) list with a fixed stride (one tile each when grid.x ==
+// number of tiles) while the NS-stage TMA ring keeps running across tile boundaries; the
+// weights of this CTA's output-channel group (grid.y) are staged once.
+template <int COG, int R, int CK, int NS>
+__global__ void __launch_bounds__(32 * (8 / R))
+conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int ckb, int H, int W,
                       const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                       float* __restrict__ out, long out_ns, float slope,
                       const float* __restrict__ mask, const float* __restrict__ add, long add_ns,
-                      int accumulate, int tiles_x, const float* __restrict__ act_src, long act_ns,
-                      int act_c1, float act_slope) {
-  using C = FwdV2Cfg<COG, PX>;
-  constexpr int SPR = C::SPR, TH = C::TH, PITCH = C::PITCH, COGP = C::COGP;
+                      int accumulate, int tiles_x, int tiles_img, int total_tiles,
+                      const float* __restrict__ act_src, long act_ns, int act_c1, float act_slope) {
+  using C = FwdV3Cfg<COG, R, CK, NS>;
+  constexpr int PITCH = C::PITCH, ROWS = C::ROWS, WPC = C::WPC, NT = C::NT;
+  static_assert(COG % 2 == 0 && (R == 2 || R == 4), "COG even, R in {2,4}");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
   float* buf = reinterpret_cast<float*>(smem_raw + (base_u32 - smem_u32(smem_raw)));
-  float* w_s = buf + 2 * C::BUF;                       // [Cin][9][COGP]
-  const uint32_t bar0 = base_u32 + (2 * C::BUF + Cin * 9 * COGP) * 4;
-  const int tid = threadIdx.x;
-  const int sx = tid % SPR, ty = tid / SPR;
-  const int th0 = (blockIdx.x / tiles_x) * TH, tw0 = (blockIdx.x % tiles_x) * 32;
+  float* w_s = buf + NS * C::BUF;                      // [Cin][WPC]: tap-major, channel pairs
+  const uint32_t bar0 = base_u32 + (NS * C::BUF + Cin * WPC) * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sx = lane & 7;                             // 4-pixel strip within the 32-wide tile row
+  const int y0 = (warp * 4 + (lane >> 3)) * R;         // first output row of this thread in the tile
   const int co0 = blockIdx.y * COG;
-  const int n = blockIdx.z;
   const int nch = (Cin + ckb - 1) / ckb;
-  const uint32_t stage_bytes = (uint32_t)(ckb * (TH + 2) * PITCH * 4);
+  const uint32_t stage_bytes = (uint32_t)(ckb * ROWS * PITCH * 4);
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_steps = my_tiles * nch;
+
+  // producer state (thread 0): next (tile, channel block) to request and its ring slot
+  int p_left = total_steps, p_k = 0, p_sl = 0, p_n = 0, p_th0 = 0, p_tw0 = 0, p_tile = blockIdx.x;
+  auto locate = [&]() {
+    p_n = p_tile / tiles_img;
+    const int t = p_tile - p_n * tiles_img;
+    p_th0 = (t / tiles_x) * C::TH;
+    p_tw0 = (t % tiles_x) * 32;
+  };
+  auto issue = [&]() {                                 // thread 0 only
+    mbar_expect_tx(bar0 + 8 * p_sl, stage_bytes);
+    tma_load_4d(base_u32 + p_sl * C::BUF * 4, &in_map, bar0 + 8 * p_sl, p_tw0 - 4, p_th0 - 1, p_k * ckb, p_n);
+    --p_left;
+    if (++p_sl == NS) p_sl = 0;
+    if (++p_k == nch) {
+      p_k = 0;
+      p_tile += gridDim.x;
+      if (p_left > 0) locate();
+    }
+  };
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(bar0 + 8 * i, 1);
     fence_barrier_init();
     tma_prefetch_desc(&in_map);
-    mbar_expect_tx(bar0, stage_bytes);
-    tma_load_4d(base_u32, &in_map, bar0, tw0 - 4, th0 - 1, 0, n);
+    locate();
+    for (int i = 0; i < NS - 1 && p_left > 0; ++i) issue();
   }
-  for (int i = tid; i < Cin * 9 * COGP; i += 128) {
-    const int g = i % COGP, t = (i / COGP) % 9, c = i / (COGP * 9);
-    float v = 0.f;
-    if (g < COG && co0 + g < Cout) v = w[((long)(co0 + g) * Cin + c) * 9 + t];
-    w_s[i] = v;
+  // weights of this output group: thread = one (channel, output) filter, 9 taps
+  for (int i = tid; i < Cin * COG; i += NT) {
+    const int c = i / COG, g = i - c * COG;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = 0.f;
+    if (co0 + g < Cout) {
+      const float* wp = w + ((long)(co0 + g) * Cin + c) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = wp[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w_s[c * WPC + t * COG + g] = v[t];
   }
-  // accumulators are output-channel PAIRS: Blackwell's fp32 pipe reaches its peak only
-  // through the packed FFMA2 form (two FMAs per lane per issue slot)
-  static_assert(COG % 2 == 0, "COG must be even");
-  float2 acc[PX][COG / 2];
+  if (WPC > 9 * COG)
+    for (int c = tid; c < Cin; c += NT)
+      for (int j = 9 * COG; j < WPC; ++j) w_s[c * WPC + j] = 0.f;
+  float2 acc[R][4][COG / 2];
 #pragma unroll
-  for (int p = 0; p < PX; ++p)
+  for (int y = 0; y < R; ++y)
 #pragma unroll
-    for (int g = 0; g < COG / 2; ++g) acc[p][g] = make_float2(0.f, 0.f);
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int g = 0; g < COG / 2; ++g) acc[y][p][g] = make_float2(0.f, 0.f);
   __syncthreads();
 
-  for (int k = 0; k < nch; ++k) {
-    if (tid == 0 && k + 1 < nch) {
-      const uint32_t b = bar0 + 8 * ((k + 1) & 1);
-      mbar_expect_tx(b, stage_bytes);
-      tma_load_4d(base_u32 + ((k + 1) & 1) * C::BUF * 4, &in_map, b, tw0 - 4, th0 - 1, (k + 1) * ckb, n);
-    }
-    mbar_wait(bar0 + 8 * (k & 1), (k >> 1) & 1);
-    const float* in_s = buf + (k & 1) * C::BUF;
+  // edge lanes fetch the one halo pixel the shuffle cannot provide
+  const bool edge = sx == 0 || sx == 7;
+  const int edge_off = sx == 0 ? -1 : 4;
+  const int thr_off = y0 * PITCH + 4 + 4 * sx;
+
+  int k = 0, ti = 0, sl = 0;
+  uint32_t ph = 0;
+#pragma unroll 1
+  for (int step = 0; step < total_steps; ++step) {
+    if (tid == 0 && p_left > 0) issue();
+    mbar_wait(bar0 + 8 * sl, ph);
+    const float* in_s = buf + sl * C::BUF + thr_off;
     const int c0 = k * ckb;
     const int cmax = (Cin - c0) < ckb ? (Cin - c0) : ckb;
 #pragma unroll 1
     for (int c = 0; c < cmax; ++c) {
-      const float* wc = w_s + (c0 + c) * 9 * COGP;
+      float wr[WPC];
+      {
+        const float4* wp = reinterpret_cast<const float4*>(w_s + (c0 + c) * WPC);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float* row = in_s + (c * (TH + 2) + ty + r) * PITCH + PX * sx + 4;
-        float v[PX + 2];
-        v[0] = row[-1];
-#pragma unroll
-        for (int q = 0; q < PX; q += 4) {
-          const float4 f = *reinterpret_cast<const float4*>(row + q);
-          v[q + 1] = f.x; v[q + 2] = f.y; v[q + 3] = f.z; v[q + 4] = f.w;
+        for (int j = 0; j < WPC / 4; ++j) {
+          const float4 f = wp[j];
+          wr[4 * j] = f.x; wr[4 * j + 1] = f.y; wr[4 * j + 2] = f.z; wr[4 * j + 3] = f.w;
         }
-        v[PX + 1] = row[PX];
-        float2 vv[PX + 2];
+      }
+      const float* cp = in_s + c * (ROWS * PITCH);
 #pragma unroll
-        for (int q = 0; q < PX + 2; ++q) vv[q] = make_float2(v[q], v[q]);
+      for (int rr = 0; rr < R + 2; ++rr) {             // input row y0 - 1 + rr of the image tile
+        const float* row = cp + rr * PITCH;
+        const float4 f = *reinterpret_cast<const float4*>(row);
+        float e = 0.f;
+        if (edge) e = row[edge_off];
+        float left = __shfl_up_sync(0xffffffffu, f.w, 1);
+        float right = __shfl_down_sync(0xffffffffu, f.x, 1);
+        if (sx == 0) left = e;
+        if (sx == 7) right = e;
+        const float v[6] = {left, f.x, f.y, f.z, f.w, right};
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          float2 wv[COGP / 2];
+        for (int r = 0; r < 3; ++r) {
+          const int y = rr - r;                        // output row fed through kernel row r
+          if (y < 0 || y >= R) continue;
 #pragma unroll
-          for (int g4 = 0; g4 < COGP; g4 += 4) {
-            const float4 f = *reinterpret_cast<const float4*>(wc + (r * 3 + s) * COGP + g4);
-            wv[g4 / 2] = make_float2(f.x, f.y);
-            wv[g4 / 2 + 1] = make_float2(f.z, f.w);
+          for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+            for (int g = 0; g < COG / 2; ++g) {
+              const float2 wv = make_float2(wr[(r * 3 + s3) * COG + 2 * g], wr[(r * 3 + s3) * COG + 2 * g + 1]);
+#pragma unroll
+              for (int p = 0; p < 4; ++p)              // FFMA2 with a scalar-broadcast operand
+                acc[y][p][g] = __ffma2_rn(make_float2(v[p + s3], v[p + s3]), wv, acc[y][p][g]);
+            }
+        }
+      }
+    }
+    __syncthreads();          // this stage may be refilled at the next iteration
+    if (++sl == NS) { sl = 0; ph ^= 1u; }
+    if (++k < nch) continue;
+    k = 0;
+    // ---- tile finished: epilogue, then clear the accumulators
+    const int tile = blockIdx.x + ti * gridDim.x;
+    ++ti;
+    const int n = tile / tiles_img, t = tile - n * tiles_img;
+    const int th0 = (t / tiles_x) * C::TH, tw0 = (t % tiles_x) * 32;
+    const int ox = tw0 + 4 * sx;
+    const long hw = (long)H * W;
+    const long pix = (long)(th0 + y0) * W + ox;
+    float bs[COG], mk[COG];
+#pragma unroll
+    for (int g = 0; g < COG; ++g) {
+      const bool ok = co0 + g < Cout;
+      bs[g] = (bias && ok) ? bias[co0 + g] : 0.f;
+      mk[g] = (mask && ok) ? mask[(long)n * Cout + co0 + g] : 1.f;
+    }
+#pragma unroll
+    for (int y = 0; y < R; ++y) {
+      const bool row_ok = th0 + y0 + y < H && ox < W;
+#pragma unroll
+      for (int g = 0; g < COG; ++g) {
+        const int co = co0 + g;
+        if (co < Cout && row_ok) {
+          const long cpix = co * hw + pix + (long)y * W;
+          float rv[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float v = ((g & 1) ? acc[y][p][g / 2].y : acc[y][p][g / 2].x) + bs[g];
+            v = v < 0.f ? v * slope : v;
+            rv[p] = v * mk[g];
           }
-#pragma unroll
-          for (int p = 0; p < PX; ++p)
-#pragma unroll
-            for (int g = 0; g < COG / 2; ++g) acc[p][g] = __ffma2_rn(vv[p + s], wv[g], acc[p][g]);
+          float4 f = make_float4(rv[0], rv[1], rv[2], rv[3]);   // W % 4 == 0 is required by the launcher
+          if (add) {
+            const float4 a = *reinterpret_cast<const float4*>(add + (long)n * add_ns + cpix);
+            f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
+          }
+          float* op = out + (long)n * out_ns + cpix;
+          if (accumulate) {
+            const float4 a = *reinterpret_cast<const float4*>(op);
+            f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
+          }
+          if (act_src && co < act_c1) {            // fused LeakyReLU backward on the finished slice
+            const float4 a = *reinterpret_cast<const float4*>(act_src + (long)n * act_ns + cpix);
+            f.x *= a.x > 0.f ? 1.f : act_slope; f.y *= a.y > 0.f ? 1.f : act_slope;
+            f.z *= a.z > 0.f ? 1.f : act_slope; f.w *= a.w > 0.f ? 1.f : act_slope;
+          }
+          *reinterpret_cast<float4*>(op) = f;
         }
       }
-    }
-    __syncthreads();          // stage (k&1) may be refilled at the next iteration
-  }
-  const int oy = th0 + ty, ox = tw0 + PX * sx;
-  if (oy >= H || ox >= W) return;
 #pragma unroll
-  for (int g = 0; g < COG; ++g) {
-    const int co = co0 + g;
-    if (co >= Cout) break;
-    const float b = bias ? bias[co] : 0.f;
-    const float mk = mask ? mask[(long)n * Cout + co] : 1.f;
-    const long o = (long)n * out_ns + ((long)co * H + oy) * W + ox;
-    const long oa = (long)n * add_ns + ((long)co * H + oy) * W + ox;
-    float r[PX];
+      for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      float v = ((g & 1) ? acc[p][g / 2].y : acc[p][g / 2].x) + b;
-      v = v < 0.f ? v * slope : v;
-      r[p] = v * mk;
-    }
-    if (ox + PX <= W) {                       // W % 4 == 0 is required by the launcher
-#pragma unroll
-      for (int q = 0; q < PX; q += 4) {
-        float4 f = make_float4(r[q], r[q + 1], r[q + 2], r[q + 3]);
-        if (add) {
-          const float4 a = *reinterpret_cast<const float4*>(add + oa + q);
-          f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
-        }
-        if (accumulate) {
-          const float4 a = *reinterpret_cast<const float4*>(out + o + q);
-          f.x += a.x; f.y += a.y; f.z += a.z; f.w += a.w;
-        }
-        if (act_src && co < act_c1) {          // fused LeakyReLU backward on the finished slice
-          const float4 a = *reinterpret_cast<const float4*>(
-              act_src + (long)n * act_ns + ((long)co * H + oy) * W + ox + q);
-          f.x *= a.x > 0.f ? 1.f : act_slope; f.y *= a.y > 0.f ? 1.f : act_slope;
-          f.z *= a.z > 0.f ? 1.f : act_slope; f.w *= a.w > 0.f ? 1.f : act_slope;
-        }
-        *reinterpret_cast<float4*>(out + o + q) = f;
-      }
-    } else {
-      for (int p = 0; p < PX && ox + p < W; ++p) {
-        float v = r[p];
-        if (add) v += add[oa + p];
-        if (accumulate) v += out[o + p];
-        if (act_src && co < act_c1)
-          v *= act_src[(long)n * act_ns + ((long)co * H + oy) * W + ox + p] > 0.f ? 1.f : act_slope;
-        out[o + p] = v;
-      }
+        for (int g = 0; g < COG / 2; ++g) acc[y][p][g] = make_float2(0.f, 0.f);
     }
   }
 }
 
-template <int COG, int PX>
-static int launch_fwd_v2(const float* in, long in_ns, int Cin, int H, int W, const float* w,
+template <int COG, int R, int CK, int NS>
+static int launch_fwd_v3(const float* in, long in_ns, int Cin, int H, int W, const float* w,
                          const float* bias, int Cout, float* out, long out_ns, float slope,
                          const float* mask, const float* add, long add_ns, int accumulate, int N,
                          cudaStream_t st, const float* act_src = nullptr, long act_ns = 0,
                          int act_c1 = 0, float act_slope = 1.f) {
-  using C = FwdV2Cfg<COG, PX>;
-  const int ckb = Cin < C::CK ? Cin : C::CK;
+  using C = FwdV3Cfg<COG, R, CK, NS>;
+  const int ckb = Cin < CK ? Cin : CK;
   CUtensorMap map;
   const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
                                       (unsigned long long)Cin, (unsigned long long)N};
   const unsigned long long strides[3] = {(unsigned long long)W, (unsigned long long)H * W,
                                          (unsigned long long)in_ns};
-  const unsigned int box[4] = {(unsigned)C::PITCH, (unsigned)(C::TH + 2), (unsigned)ckb, 1u};
+  const unsigned int box[4] = {(unsigned)C::PITCH, (unsigned)C::ROWS, (unsigned)ckb, 1u};
   int rc = dmc_make_f32_map(&map, in, 4, dims, strides, box);
   if (rc) return rc;
   const int smem = C::smem_bytes(Cin);
-  auto kern = conv3x3_fwd_v2_kernel<COG, PX>;
+  auto kern = conv3x3_fwd_v3_kernel<COG, R, CK, NS>;
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
-    const int want = smem > 100 * 1024 ? smem : 100 * 1024;
+    const int want = smem > 64 * 1024 ? smem : 64 * 1024;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want) != cudaSuccess)
-      return dmc_check_launch("conv3x3_fwd_v2 smem attribute");
+      return dmc_check_launch("conv3x3_fwd_v3 smem attribute");
     attr_bytes = want;
   }
-  const int tx32 = (int)cdiv(W, 32);
-  dim3 grid(tx32 * (unsigned)cdiv(H, C::TH), (unsigned)cdiv(Cout, COG), N);
-  kern<<<grid, 128, smem, st>>>(map, Cin, ckb, H, W, w, bias, Cout, out, out_ns, slope, mask, add,
-                                add_ns, accumulate, tx32, act_src, act_ns, act_c1, act_slope);
-  return dmc_check_launch("conv3x3_fwd_v2_kernel");
+  const int tx32 = (int)cdiv(W, 32), tiles_img = tx32 * (int)cdiv(H, C::TH);
+  const long total = (long)tiles_img * N;
+  const int groups = (int)cdiv(Cout, COG);
+  // One CTA per tile measured ~10% faster than a persistent grid of 148*occ CTAs here (the
+  // hardware scheduler staggers the CTAs' prologues/epilogues); the kernel handles both.
+  const long gx = total;
+  dim3 grid((unsigned)gx, (unsigned)groups);
+  kern<<<grid, C::NT, smem, st>>>(map, Cin, ckb, H, W, w, bias, Cout, out, out_ns, slope, mask, add,
+                                  add_ns, accumulate, tx32, tiles_img, (int)total, act_src, act_ns,
+                                  act_c1, act_slope);
+  return dmc_check_launch("conv3x3_fwd_v3_kernel");
 }
 
 // wT[ci][co][2-r][2-s] = w[co][ci][r][s] for ci < ci_count: turns the stride-1 data
@@ -951,13 +1014,12 @@ extern "C" int dmc_conv_fwd(const float* in, long in_ns, int Cin, int H, int W, 
   cudaStream_t st = ST_(stream);
   if (ks == 3 && stride == 1 && W % 4 == 0 && in_ns % 4 == 0 && out_ns % 4 == 0 && add_ns % 4 == 0 &&
       (H * W) % 4 == 0) {
-    if (Cout == 2)
-      return launch_fwd_v2<2, 8>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
-    if (Cout <= 4)
-      return launch_fwd_v2<4, 8>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
-    if (Cout == 6)
-      return launch_fwd_v2<6, 4>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
-    return launch_fwd_v2<8, 4>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st);
+#define DMC_FW(COG, R) \
+  return launch_fwd_v3<COG, R, 2, 2>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, mask, add, add_ns, accumulate, N, st)
+    if (Cout == 2) DMC_FW(2, 4);
+    if (Cout == 6) DMC_FW(6, 2);
+    DMC_FW(4, 4);
+#undef DMC_FW
   } else if (ks == 3 && stride == 1) {
     dim3 grid(tiles_x * tiles_y, (unsigned)cdiv(Cout, 8), N);
     conv_fwd_kernel<3, 1, 8, 8><<<grid, 256, 0, st>>>(in, in_ns, Cin, H, W, w, bias, Cout, out,
@@ -1107,13 +1169,12 @@ extern "C" int dmc_conv3x3_dgrad_fused(const float* dY, long dy_ns, int Cy, int 
   DMC_REQUIRE(W % 4 == 0 && dy_ns % 4 == 0 && dx_ns % 4 == 0 && act_ns % 4 == 0 && (H * W) % 4 == 0,
               "conv3x3_dgrad_fused: W=%d and strides must be multiples of 4", W);
   cudaStream_t st = ST_(stream);
-#define DMC_DG(COG, PX)                                                                             \
-  return launch_fwd_v2<COG, PX>(dY, dy_ns, Cy, H, W, wT, nullptr, Cx, dX, dx_ns, 1.f, nullptr, nullptr, \
-                                0, accumulate, N, st, act_src, act_ns, act_c1, act_slope)
-  if (Cx == 2) DMC_DG(2, 8);
-  if (Cx <= 4) DMC_DG(4, 8);
-  if (Cx == 6) DMC_DG(6, 4);
-  DMC_DG(8, 4);
+#define DMC_DG(COG, R)                                                                              \
+  return launch_fwd_v3<COG, R, 2, 2>(dY, dy_ns, Cy, H, W, wT, nullptr, Cx, dX, dx_ns, 1.f, nullptr, nullptr, \
+                                     0, accumulate, N, st, act_src, act_ns, act_c1, act_slope)
+  if (Cx == 2) DMC_DG(2, 4);
+  if (Cx == 6) DMC_DG(6, 2);
+  DMC_DG(4, 4);
 #undef DMC_DG
 }
 
