@@ -47,7 +47,7 @@ simt_tap_gemm_kernel(const bf16* __restrict__ Ah, const bf16* __restrict__ Al, l
     const long arow = m0 + lr + taps.shift[t];
     const bool a_ok = arow >= 0 && arow < a_rows;
     const bf16* ah = Ah + ((long)taps.phase[t] * a_rows + (a_ok ? arow : 0)) * K;
-    const bf16* al = Al + ((long)taps.phase[t] * a_rows + (a_ok ? arow : 0)) * K;
+    const bf16* al = Al ? Al + ((long)taps.phase[t] * a_rows + (a_ok ? arow : 0)) * K : nullptr;
     const int brow = n0 + lr;
     const bool b_ok = brow < N;
     const bf16* bh = Bh + ((long)taps.bsel[t] * N + (b_ok ? brow : 0)) * K;
@@ -56,7 +56,7 @@ simt_tap_gemm_kernel(const bf16* __restrict__ Ah, const bf16* __restrict__ Al, l
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + lk + j;
-        As[lk + j][lr] = (a_ok && k < K) ? join_bf16(ah[k], al[k]) : 0.f;
+        As[lk + j][lr] = (a_ok && k < K) ? (al ? join_bf16(ah[k], al[k]) : __bfloat162float(ah[k])) : 0.f;
         Bs[lk + j][lr] = (b_ok && k < K) ? join_bf16(bh[k], bl[k]) : 0.f;
       }
       __syncthreads();
@@ -111,7 +111,9 @@ simt_wgrad_kernel(const bf16* __restrict__ Gh, const bf16* __restrict__ Gl, long
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = m0 + lc + j, ci = n0 + lc + j;
-      As[lk][lc + j] = (g_ok && co < Cout) ? join_bf16(Gh[gq * Cout + co], Gl[gq * Cout + co]) : 0.f;
+      As[lk][lc + j] = (g_ok && co < Cout)
+                           ? (Gl ? join_bf16(Gh[gq * Cout + co], Gl[gq * Cout + co]) : __bfloat162float(Gh[gq * Cout + co]))
+                           : 0.f;
       Bs[lk][lc + j] = (x_ok && ci < Cin) ? join_bf16(xh[xq * Cin + ci], xl[xq * Cin + ci]) : 0.f;
     }
     __syncthreads();

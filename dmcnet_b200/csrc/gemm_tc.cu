@@ -138,7 +138,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
-                   const BwFuse bw) {
+                   const BwFuse bw, int a_lo_on) {
   using S = TapGemmWsSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -190,10 +190,10 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           const int t = i / kblocks, kb = i - t * kblocks;
           const uint32_t full = bar_full + 8 * s;
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
-          mbar_expect_tx(full, S::STAGE_BYTES);
+          mbar_expect_tx(full, a_lo_on ? S::STAGE_BYTES : S::STAGE_BYTES - S::A_BYTES);
           const int row = (int)(m0 + taps.shift[t]);
           tma_load_3d(st, &mapAh, full, kb * 64, row, taps.phase[t]);
-          tma_load_3d(st + S::A_BYTES, &mapAl, full, kb * 64, row, taps.phase[t]);
+          if (a_lo_on) tma_load_3d(st + S::A_BYTES, &mapAl, full, kb * 64, row, taps.phase[t]);
           tma_load_3d(st + 2 * S::A_BYTES, &mapBh, full, kb * 64, n0, taps.bsel[t]);
           tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &mapBl, full, kb * 64, n0, taps.bsel[t]);
         }
@@ -219,8 +219,8 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
             const uint64_t al = umma_desc_sw128(st + S::A_BYTES + ks * 32, 16, 1024);
             const uint64_t bh = umma_desc_sw128(st + 2 * S::A_BYTES + ks * 32, 16, 1024);
             const uint64_t bl = umma_desc_sw128(st + 2 * S::A_BYTES + S::B_BYTES + ks * 32, 16, 1024);
-            umma_bf16(acc, al, bh, idesc, (i | ks) != 0);
-            umma_bf16(acc, ah, bl, idesc, 1);
+            if (a_lo_on) umma_bf16(acc, al, bh, idesc, (i | ks) != 0);
+            umma_bf16(acc, ah, bl, idesc, a_lo_on ? 1u : (uint32_t)((i | ks) != 0));
             umma_bf16(acc, ah, bh, idesc, 1);
           }
           umma_commit(bar_empty + 8 * s);
@@ -402,7 +402,7 @@ template <int BN, int STAGES>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
-                              const BwFuse& bw, cudaStream_t stream) {
+                              const BwFuse& bw, int a_lo_on, cudaStream_t stream) {
   using S = TapGemmWsSmem<BN, STAGES>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -416,7 +416,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n, stats, bw);
+                                                  tiles_m, tiles_n, stats, bw, a_lo_on);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(128)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
                   const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
-                  long P, int kb_per_split, int n_tiles, int oihw_taps) {
+                  long P, int kb_per_split, int n_tiles, int oihw_taps, int g_lo_on) {
   using S = WgradSmem<BN, TG, BKP, STAGES>;
   static_assert(TG * BN <= 512, "tap group does not fit TMEM");
   extern __shared__ uint8_t smem_raw[];
@@ -462,7 +462,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   if (kb1 > kb_total) kb1 = kb_total;
   const int iters = (int)(kb1 - kb0);
   const int m_boxes = (Cout - m0) >= 128 ? 2 : 1;   // second 64-channel group may not exist
-  const uint32_t stage_tx = (uint32_t)(2 * m_boxes * S::BOX_BYTES + nt_g * 2 * S::X_BYTES);
+  const uint32_t stage_tx = (uint32_t)((g_lo_on ? 2 : 1) * m_boxes * S::BOX_BYTES + nt_g * 2 * S::X_BYTES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -497,7 +497,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
       const int row = (int)((kb0 + i) * BKP);
       for (int b = 0; b < m_boxes; ++b) {
         tma_load_3d(st + b * S::BOX_BYTES, &mapGh, full, m0 + 64 * b, row, 0);
-        tma_load_3d(st + S::G_BYTES + b * S::BOX_BYTES, &mapGl, full, m0 + 64 * b, row, 0);
+        if (g_lo_on) tma_load_3d(st + S::G_BYTES + b * S::BOX_BYTES, &mapGl, full, m0 + 64 * b, row, 0);
       }
       for (int g = 0; g < nt_g; ++g) {
         const uint32_t xs = st + 2 * S::G_BYTES + g * 2 * S::X_BYTES;
@@ -526,8 +526,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
           const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
           const uint64_t xh = umma_desc_sw128(xs + koff, S::BOX_BYTES, 1024);
           const uint64_t xl = umma_desc_sw128(xs + S::X_BYTES + koff, S::BOX_BYTES, 1024);
-          umma_bf16(acc, gl, xh, idesc, (i | ks) != 0);
-          umma_bf16(acc, gh, xl, idesc, 1);
+          if (g_lo_on) umma_bf16(acc, gl, xh, idesc, (i | ks) != 0);
+          umma_bf16(acc, gh, xl, idesc, g_lo_on ? 1u : (uint32_t)((i | ks) != 0));
           umma_bf16(acc, gh, xh, idesc, 1);
         }
       }
@@ -572,7 +572,8 @@ static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, co
   CUtensorMap mGh, mGl, mXh, mXl;
   int rc;
   if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mGl, G_lo, Cout, P, 1, 64, BKP))) return rc;
+  const int g_lo_on = G_lo != nullptr;     // G_lo == NULL: dY is used at bf16 precision
+  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, Cout, P, 1, 64, BKP))) return rc;
   if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, BKP))) return rc;
   if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, BKP))) return rc;
   auto kern = wgrad_gemm_kernel<BN, TG, BKP, STAGES>;
@@ -594,7 +595,7 @@ static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, co
   const long splits = cdiv(kb_total, kb_per_split);
   dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)groups);
   kern<<<grid, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, Cout, Cin, P,
-                                        (int)kb_per_split, n_tiles, oihw_taps);
+                                        (int)kb_per_split, n_tiles, oihw_taps, g_lo_on);
   return dmc_check_launch("wgrad_gemm_kernel");
 }
 
@@ -629,6 +630,7 @@ using namespace dmc;
 // (the BatchNorm batch statistics of a convolution output, fused into the epilogue).
 // bw_Y != null switches the epilogue to the fused BatchNorm-backward reduction (see BwFuse):
 // D receives dz = (D + bw_gb) * [bw_act_hi > 0] and stats[0]/[1] += sum dz / sum dz * xhat.
+// A_lo == NULL: A is taken at bf16 precision (A_hi only, two MMAs per k-step instead of three).
 extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                                const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
                                long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
@@ -652,20 +654,22 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, 128))) return rc;
-  if ((rc = make_map_3d(&mAl, A_lo, K, a_rows, a_phases, 64, 128))) return rc;
+  const int a_lo_on = A_lo != nullptr;     // A_lo == NULL: A is used at bf16 precision (two MMAs per k-step)
+  if ((rc = make_map_3d(&mAl, a_lo_on ? A_lo : A_hi, K, a_rows, a_phases, 64, 128))) return rc;
   if ((rc = make_map_3d(&mBh, B_hi, K, N, b_slices, 64, BN))) return rc;
   if ((rc = make_map_3d(&mBl, B_lo, K, N, b_slices, 64, BN))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
   if (BN == 64)
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).
 // oihw_taps > 0 writes the OIHW gradient directly instead: dW[co][ci][bsel_t], oihw_taps per filter.
+// G_lo == NULL: dY is taken at bf16 precision (G_hi only).
 extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
                             const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
                             const int* shift, const int* phase, const int* bsel, int oihw_taps,

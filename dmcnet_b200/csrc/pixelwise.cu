@@ -27,7 +27,7 @@ __device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, long off, const
 #pragma unroll
   for (int i = 0; i < 4; ++i) split_bf16(x[i], h.v[i], l.v[i]);
   *reinterpret_cast<bf16x4*>(hi + off) = h;
-  *reinterpret_cast<bf16x4*>(lo + off) = l;
+  if (lo) *reinterpret_cast<bf16x4*>(lo + off) = l;    // lo == NULL: bf16 (round-to-nearest) only
 }
 __device__ __forceinline__ void load_join4(const bf16* hi, const bf16* lo, long off, float (&x)[4]) {
   const bf16x4 h = *reinterpret_cast<const bf16x4*>(hi + off);

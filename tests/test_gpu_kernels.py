@@ -150,6 +150,20 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
         ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dX, a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin, M=P,
                      ldD=cin, Hp=Hp, Wp=Wp, shift=[-s for s in shift], phase=phase, bsel=bsel, engine=engine)
         assert rel(from_pixel(dX, n, cin, h, h), x.grad) < 5e-5
+        # lo plane of the gradient omitted (NULL): the kernels must then equal the exact result
+        # for dY rounded to bf16 -- the engine's opt-in grad_bf16 mode
+        dy_r = dy.to(torch.bfloat16).float()
+        y2 = F.conv2d(x, w, None, stride, 1)
+        gx_r, gw_r = torch.autograd.grad(y2, (x, w), dy_r)
+        dX.fill_(float('nan'))
+        ops.tap_gemm(G_hi, None, Wt_hi, Wt_lo, dX, a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin, M=P,
+                     ldD=cin, Hp=Hp, Wp=Wp, shift=[-s for s in shift], phase=phase, bsel=bsel, engine=engine)
+        assert rel(from_pixel(dX, n, cin, h, h), gx_r) < 5e-5
+        dWs.zero_()
+        ops.wgrad_gemm(G_hi, None, A_hi, A_lo, dWs, P=P, Cout=cout, x_phases=phases, Cin=cin, shift=shift,
+                       phase=phase, bsel=bsel, engine=engine)
+        ops.wgrad_unpack(dWs, gw, cout, cin, 9)
+        assert rel(gw, gw_r) < 5e-5
     else:
         dxp = torch.zeros(4, P, cin, device='cuda')
         for ph in range(4):
