@@ -172,7 +172,8 @@ extern "C" int dmc_simt_tap_gemm(const void* A_hi, const void* A_lo, int a_phase
 extern "C" int dmc_simt_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
                               const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
                               const int* shift, const int* phase, const int* bsel, int oihw_taps,
-                              void* stream) {
+                              float* workspace, long workspace_floats, void* stream) {
+  (void)workspace; (void)workspace_floats;      // the CUDA-core twin always accumulates atomically
   DMC_REQUIRE(ntaps >= 1 && ntaps <= 16, "simt_wgrad: ntaps=%d", ntaps);
   for (int i = 0; i < ntaps; ++i)
     DMC_REQUIRE(phase[i] >= 0 && phase[i] < x_phases, "simt_wgrad: tap %d phase out of range", i);

@@ -440,7 +440,8 @@ __global__ void __launch_bounds__(128)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
                   const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
                   const __grid_constant__ TapTable taps, float* __restrict__ dW, int Cout, int Cin,
-                  long P, int kb_per_split, int n_tiles, int oihw_taps, int g_lo_on) {
+                  long P, int kb_per_split, int n_tiles, int oihw_taps, int g_lo_on,
+                  float* __restrict__ ws) {
   using S = WgradSmem<BN, TG, BKP, STAGES>;
   static_assert(TG * BN <= 512, "tap group does not fit TMEM");
   extern __shared__ uint8_t smem_raw[];
@@ -542,6 +543,27 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   const int co = m0 + warp * 32 + lane;
   const int wstep = oihw_taps ? oihw_taps : 1;
   for (int g = 0; g < nt_g; ++g) {
+    if (ws) {
+      // split-K partial tile -> workspace [split][tap][Cout][Cin] with plain 128-bit stores (each
+      // lane owns 128 contiguous bytes of its row); wgrad_reduce_kernel sums the splits in a
+      // fixed order.  No atomics: deterministic, and ~4x cheaper than scattered 4-byte REDs.
+      float* wrow = ws + (((long)blockIdx.x * taps.ntaps + (t0 + g)) * Cout + co) * Cin + n0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * BN + c, r);
+        tmem_ld_wait();
+        if (co < Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (n0 + c + j < Cin)
+              *reinterpret_cast<float4*>(wrow + c + j) =
+                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                              __uint_as_float(r[j + 3]));
+        }
+      }
+      continue;
+    }
     // output layout: [slice][Cout][Cin] (oihw_taps == 0) or the OIHW gradient itself,
     // dW[co][ci][tap] with oihw_taps taps per filter (no repacking pass afterwards)
     const int bsel = taps.bsel[t0 + g];
@@ -564,10 +586,68 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
+// dW (+)= sum over splits of the workspace partials.  Block = 32 consecutive (co, ci) filters x
+// SL split lanes (one warp each); a thread sums its splits for every tap of its filter, the
+// lanes are combined through shared memory in a fixed order, and lane-warp 0 writes the
+// filter's taps (contiguous in OIHW).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, const __grid_constant__ TapTable taps,
+                    int Cout, int Cin, int oihw_taps, float* __restrict__ dW) {
+  extern __shared__ float part[];                 // [SL][MAX_TAPS][32]
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5, SL = blockDim.x >> 5;
+  const long filters = (long)Cout * Cin;
+  const long f = (long)blockIdx.x * 32 + lane;
+  const int ntaps = taps.ntaps;
+  float acc[MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < MAX_TAPS; ++t) acc[t] = 0.f;
+  if (f < filters) {
+    for (int sp = sl; sp < splits; sp += SL) {
+      const float* p = ws + (long)sp * ntaps * filters + f;
+#pragma unroll
+      for (int t = 0; t < MAX_TAPS; ++t)
+        if (t < ntaps) acc[t] += p[(long)t * filters];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MAX_TAPS; ++t) part[(sl * MAX_TAPS + t) * 32 + lane] = acc[t];
+  __syncthreads();
+  if (sl == 0 && f < filters) {
+    for (int k = 1; k < SL; ++k)
+#pragma unroll
+      for (int t = 0; t < MAX_TAPS; ++t) acc[t] += part[(k * MAX_TAPS + t) * 32 + lane];
+    const int co = (int)(f / Cin), ci = (int)(f % Cin);
+#pragma unroll
+    for (int t = 0; t < MAX_TAPS; ++t)
+      if (t < ntaps) {
+        const int bsel = taps.bsel[t];
+        float* o = oihw_taps ? dW + f * oihw_taps + bsel : dW + ((long)bsel * Cout + co) * Cin + ci;
+        *o += acc[t];
+      }
+  }
+}
+
+template <int TG>
+static void wgrad_plan(int BN, int BKP, int Cout, int Cin, int ntaps, long P, int sm_count,
+                       long* kb_per_split, long* splits) {
+  const int m_tiles = (int)cdiv(Cout, 128), n_tiles = (int)cdiv(Cin, BN);
+  const int groups = (int)cdiv(ntaps, TG);
+  const long kb_total = cdiv(P, BKP);
+  const long tiles = (long)m_tiles * n_tiles * groups;
+  // whole waves: these CTAs are resident one or two per SM, so the CTA count must not spill
+  // a few CTAs into an extra round
+  long want_splits = ((long)sm_count * (TG > 1 ? 2 : 4)) / tiles;
+  if (want_splits < 1) want_splits = 1;
+  long kbs = cdiv(kb_total, want_splits);
+  if (kbs < 8) kbs = 8;
+  *kb_per_split = kbs;
+  *splits = cdiv(kb_total, kbs);
+}
+
 template <int BN, int TG, int BKP, int STAGES>
 static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, const void* X_lo,
                         int x_phases, const TapTable& taps, float* dW, int Cout, int Cin, long P,
-                        int sm_count, int oihw_taps, cudaStream_t stream) {
+                        int sm_count, int oihw_taps, float* ws, long ws_floats, cudaStream_t stream) {
   using S = WgradSmem<BN, TG, BKP, STAGES>;
   CUtensorMap mGh, mGl, mXh, mXl;
   int rc;
@@ -586,17 +666,22 @@ static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, co
   }
   const int m_tiles = (int)cdiv(Cout, 128), n_tiles = (int)cdiv(Cin, BN);
   const int groups = (int)cdiv(taps.ntaps, TG);
-  const long kb_total = cdiv(P, BKP);
-  const long tiles = (long)m_tiles * n_tiles * groups;
-  long want_splits = cdiv((long)sm_count * (TG > 1 ? 2 : 4), tiles);
-  if (want_splits < 1) want_splits = 1;
-  long kb_per_split = cdiv(kb_total, want_splits);
-  if (kb_per_split < 8) kb_per_split = 8;
-  const long splits = cdiv(kb_total, kb_per_split);
+  long kb_per_split, splits;
+  wgrad_plan<TG>(BN, BKP, Cout, Cin, taps.ntaps, P, sm_count, &kb_per_split, &splits);
+  const long per_split = (long)taps.ntaps * Cout * Cin;
+  if (ws) DMC_REQUIRE(ws_floats >= splits * per_split, "wgrad: workspace %ld floats < %ld needed", ws_floats,
+                      splits * per_split);
   dim3 grid((unsigned)splits, (unsigned)(m_tiles * n_tiles), (unsigned)groups);
   kern<<<grid, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, Cout, Cin, P,
-                                        (int)kb_per_split, n_tiles, oihw_taps, g_lo_on);
-  return dmc_check_launch("wgrad_gemm_kernel");
+                                        (int)kb_per_split, n_tiles, oihw_taps, g_lo_on, ws);
+  if ((rc = dmc_check_launch("wgrad_gemm_kernel"))) return rc;
+  if (ws) {
+    const int SL = splits >= 8 ? 8 : (splits >= 4 ? 4 : (splits >= 2 ? 2 : 1));
+    wgrad_reduce_kernel<<<(unsigned)cdiv((long)Cout * Cin, 32), 32 * SL, SL * MAX_TAPS * 32 * sizeof(float),
+                          stream>>>(ws, (int)splits, taps, Cout, Cin, oihw_taps, dW);
+    return dmc_check_launch("wgrad_reduce_kernel");
+  }
+  return DMC_OK;
 }
 
 static int fill_taps(TapTable& tt, int ntaps, const int* shift, const int* phase, const int* bsel) {
@@ -670,10 +755,12 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).
 // oihw_taps > 0 writes the OIHW gradient directly instead: dW[co][ci][bsel_t], oihw_taps per filter.
 // G_lo == NULL: dY is taken at bf16 precision (G_hi only).
+// workspace != NULL (>= dmc_tc_wgrad_workspace() floats): split-K partial tiles go to the workspace
+// with plain stores and a second kernel sums them in a fixed order (deterministic, no atomics).
 extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
                             const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
                             const int* shift, const int* phase, const int* bsel, int oihw_taps,
-                            void* stream) {
+                            float* workspace, long workspace_floats, void* stream) {
   DMC_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0, "wgrad: Cout=%d Cin=%d must be multiples of 64", Cout,
               Cin);
   DMC_REQUIRE(P > 0 && P < (1L << 31), "wgrad: bad P");
@@ -684,10 +771,20 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // taps are grouped so that consecutive taps share a CTA: they must read the same phase-independent
   // dY tile (always true) -- the activation tile is per tap.
-  if (Cin % 128 == 0)       // wide tiles are MMA/latency-bound: one tap per CTA, more CTAs in flight
-    return launch_wgrad<128, 1, 64, 3>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P,
-                                       sm_count(), oihw_taps, st);
+  if (Cin % 128 == 0)       // wide tiles: one tap per CTA, two CTAs per SM (32-pixel k-blocks)
+    return launch_wgrad<128, 1, 32, 3>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P,
+                                       sm_count(), oihw_taps, workspace, workspace_floats, st);
   return launch_wgrad<64, 5, 64, 2>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P, sm_count(),
-                                    oihw_taps, st);
+                                    oihw_taps, workspace, workspace_floats, st);
 }
 
+// Floats of split-K workspace dmc_tc_wgrad needs for this shape (0 is never returned; passing
+// workspace == NULL selects the atomic-accumulation epilogue instead).
+extern "C" long dmc_tc_wgrad_workspace(long P, int Cout, int Cin, int ntaps) {
+  long kbs, splits;
+  if (Cin % 128 == 0)
+    wgrad_plan<1>(128, 32, Cout, Cin, ntaps, P, sm_count(), &kbs, &splits);
+  else
+    wgrad_plan<5>(64, 64, Cout, Cin, ntaps, P, sm_count(), &kbs, &splits);
+  return splits * (long)ntaps * Cout * Cin;
+}

@@ -355,6 +355,16 @@ class DmcEngine:
         self.G_hi = torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)   # dY planes (x2: conv1|ds stack)
         self.G_lo = None if self.grad_bf16 else torch.zeros(2 * max_pc, dtype=torch.bfloat16, device=dev)
         self.gbuf = [torch.zeros(max_pc, **f32) for _ in range(5)]             # T1, T2a, Ra, T2b, Rb
+        # split-K workspace of the weight-gradient GEMM (deterministic reduction instead of atomics)
+        self.wgrad_ws = None
+        if self.gemm_engine == 'tc':
+            need = 0
+            for blk in self.blocks:
+                for key in ('c1', 'c2', 'ds'):
+                    if key in blk:
+                        u = blk[key]
+                        need = max(need, ops.wgrad_workspace_floats(u.geo.P, u.cout, u.cin, u.taps))
+            self.wgrad_ws = torch.empty(need, **f32)
         self.pooled = torch.zeros(N, 512, **f32)
         self.d_pooled = torch.zeros(N, 512, **f32)
         self.logits = torch.zeros(N, self.num_class, **f32)
@@ -570,7 +580,7 @@ class DmcEngine:
         # the split-K epilogue accumulates straight into the (zeroed) OIHW gradient bucket
         ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, self.g(u.name_conv + '.weight'), P=geo.P, Cout=u.cout,
                        x_phases=x_phases, Cin=u.cin, shift=shift, phase=phase, bsel=bsel,
-                       engine=self.gemm_engine, oihw_taps=u.taps)
+                       engine=self.gemm_engine, oihw_taps=u.taps, workspace=self.wgrad_ws)
 
     def _cls_backward(self, x_planar: torch.Tensor, n: int, need_wgrad: bool, need_input_grad: bool,
                       d_input: Optional[torch.Tensor] = None):

@@ -94,11 +94,19 @@ def tap_gemm(A_hi, A_lo, B_hi, B_lo, D, *, a_phases, a_rows, K, b_slices, N, M, 
 
 
 def wgrad_gemm(G_hi, G_lo, X_hi, X_lo, dW, *, P, Cout, x_phases, Cin, shift, phase, bsel,
-               engine='tc', oihw_taps=0):
+               engine='tc', oihw_taps=0, workspace=None):
     name = 'dmc_tc_wgrad' if engine == 'tc' else 'dmc_simt_wgrad'
     _call(name, _ptr(G_hi, BF16), _ptr(G_lo, BF16), c_long(P), c_int(Cout), _ptr(X_hi, BF16),
           _ptr(X_lo, BF16), c_int(x_phases), c_int(Cin), _ptr(dW, F32), c_int(len(shift)),
-          _iarr(shift), _iarr(phase), _iarr(bsel), c_int(oihw_taps), _stream())
+          _iarr(shift), _iarr(phase), _iarr(bsel), c_int(oihw_taps), _ptr(workspace, F32),
+          c_long(0 if workspace is None else workspace.numel()), _stream())
+
+
+def wgrad_workspace_floats(P, Cout, Cin, ntaps):
+    """Split-K workspace (floats) the tensor-core wgrad needs for this shape."""
+    fn = _native.lib().dmc_tc_wgrad_workspace
+    fn.restype = c_long
+    return int(fn(c_long(P), c_int(Cout), c_int(Cin), c_int(ntaps)))
 
 
 # ---------------------------------------------------------------- pixel-major classifier helpers

@@ -144,6 +144,17 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
     gw = torch.empty(cout, cin, 3, 3, device='cuda')
     ops.wgrad_unpack(dWs, gw, cout, cin, 9)
     assert rel(gw, w.grad) < 5e-5
+    if engine == 'tc':
+        # workspace path: partial tiles + fixed-order reduction straight into OIHW; bit-reproducible
+        ws = torch.empty(ops.wgrad_workspace_floats(P, cout, cin, 9), device='cuda')
+        runs = []
+        for _ in range(2):
+            gw2 = torch.zeros(cout, cin, 3, 3, device='cuda')
+            ops.wgrad_gemm(G_hi, G_lo, A_hi, A_lo, gw2, P=P, Cout=cout, x_phases=phases, Cin=cin, shift=shift,
+                           phase=phase, bsel=bsel, engine=engine, oihw_taps=9, workspace=ws)
+            runs.append(gw2)
+        assert rel(runs[0], w.grad) < 5e-5
+        assert torch.equal(runs[0], runs[1])
     # dgrad
     if stride == 1:
         dX = torch.full((P, cin), float('nan'), device='cuda')
