@@ -308,6 +308,11 @@ class DmcEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         # stem (planar)
         self.stem_Y = torch.zeros(N, 64, H2, W2, **f32)
+        # stem conv on the tensor cores (im2col built in shared memory) when the shape allows
+        self.stem_tc = (self.gemm_engine == 'tc' and self.W % 8 == 0 and 8 <= self.W <= 256
+                        and self.H % 2 == 0)
+        self.stem_wb = torch.zeros(128 * 128, dtype=torch.bfloat16, device=dev)
+        self.stem_ws = torch.empty(ops.stem_wgrad_workspace_floats(), **f32) if self.stem_tc else None
         self.stem_dZ = torch.zeros(N, 64, H2, W2, **f32)
         self.stem = {k: torch.zeros(64, **f32) for k in ('scale', 'shift', 'mean', 'invstd')}
         self.stem['sums'] = torch.zeros(2, 64, dtype=torch.float64, device=dev)
@@ -508,8 +513,12 @@ class DmcEngine:
             ops.memset_zero(self._sums_pool[:self._sums_used])
         # stem: 7x7/2 conv (planar) -> BN -> ReLU -> maxpool -> pixel-major hi/lo
         H2, W2 = H // 2, W // 2
-        ops.conv_fwd(x_planar, 2 * H * W, 2, H, W, self.p('base_model.conv1.weight'), None, 64, 7, 2,
-                     self.stem_Y.view(-1), 64 * H2 * W2, n)
+        if self.stem_tc:
+            ops.stem_conv_tc_fwd(x_planar, 2 * H * W, H, W, self.p('base_model.conv1.weight'), self.stem_wb,
+                                 self.stem_Y.view(-1), 64 * H2 * W2, n)
+        else:
+            ops.conv_fwd(x_planar, 2 * H * W, 2, H, W, self.p('base_model.conv1.weight'), None, 64, 7, 2,
+                         self.stem_Y.view(-1), 64 * H2 * W2, n)
         st = self.stem
         if train:
             ops.bn_stats_planar(self.stem_Y, 64 * H2 * W2, 64, H2 * W2, n, st['sums'])
@@ -697,8 +706,12 @@ class DmcEngine:
                                 H2 * W2, n, self.stem_dZ, ns, self.g('base_model.bn1.weight'),
                                 self.g('base_model.bn1.bias'))
         if need_wgrad:
-            ops.conv_wgrad(x_planar, 2 * H * W, 2, H, W, self.stem_dZ, ns, 64, 7, 2,
-                           self.g('base_model.conv1.weight'), None, n)
+            if self.stem_tc:
+                ops.stem_conv_tc_wgrad(x_planar, 2 * H * W, H, W, self.stem_dZ.view(-1), ns,
+                                       self.g('base_model.conv1.weight'), self.stem_ws, n)
+            else:
+                ops.conv_wgrad(x_planar, 2 * H * W, 2, H, W, self.stem_dZ, ns, 64, 7, 2,
+                               self.g('base_model.conv1.weight'), None, n)
         if need_input_grad:
             ops.conv_dgrad(self.stem_dZ, ns, 64, self.p('base_model.conv1.weight'), 2, 2, 7, 2,
                            self.dD.view(-1), self.dD.shape[1] * H * W, H, W, n, accumulate=True)

@@ -261,6 +261,24 @@ def copy_planar(src, s_ns, dst, d_ns, count, N):
 
 
 # ---------------------------------------------------------------- stem, heads, optimizer
+def stem_conv_tc_fwd(x, in_ns, H, W, w, wb, Y, y_ns, N):
+    """Stem 7x7/2 conv (2 -> 64 channels) on the tensor cores; wb = 128*128 bf16 scratch."""
+    _call('dmc_stem_conv_tc_fwd', _ptr(x, F32), c_long(in_ns), c_int(H), c_int(W), _ptr(w, F32),
+          _ptr(wb, BF16), _ptr(Y, F32), c_long(y_ns), c_int(N), _stream())
+
+
+def stem_conv_tc_wgrad(x, in_ns, H, W, dP, dp_ns, dW, ws, N):
+    """dW[64][2][7][7] += stem conv weight gradient (tensor cores); ws from stem_wgrad_workspace_floats()."""
+    _call('dmc_stem_conv_tc_wgrad', _ptr(x, F32), c_long(in_ns), c_int(H), c_int(W), _ptr(dP, F32),
+          c_long(dp_ns), _ptr(dW, F32), _ptr(ws, F32), c_int(N), _stream())
+
+
+def stem_wgrad_workspace_floats():
+    fn = _native.lib().dmc_stem_conv_tc_wgrad_workspace
+    fn.restype = c_long
+    return int(fn())
+
+
 def stem_pool_fwd(Y, scale, shift, N, C, H, W, out_hi, out_lo, idx):
     _call('dmc_stem_pool_fwd', _ptr(Y, F32), _ptr(scale, F32), _ptr(shift, F32), c_int(N), c_int(C),
           c_int(H), c_int(W), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8), _stream())

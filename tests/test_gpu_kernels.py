@@ -261,6 +261,31 @@ def test_planar_bn_eps08_forward_backward():
     assert rel(dX, x.grad) < 2e-5 and rel(dgam, gamma.grad) < 2e-5 and rel(dbet, beta.grad) < 2e-5
 
 
+@pytest.mark.parametrize('N,H,W', [(2, 64, 64), (3, 224, 224), (1, 40, 48)])
+def test_stem_conv_tensor_core_forward_and_wgrad(N, H, W):
+    """7x7/2 stem conv through the im2col-in-shared-memory tcgen05 kernel vs torch fp32."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 2, H, W, generator=g)
+    w = torch.randn(64, 2, 7, 7, generator=g) * 0.1
+    y = F.conv2d(x, w, None, 2, 3)
+    Y = torch.full((N, 64, H // 2, W // 2), float('nan'), device='cuda')
+    wb = torch.zeros(128 * 128, dtype=torch.bfloat16, device='cuda')
+    ops.stem_conv_tc_fwd(x.cuda(), 2 * H * W, H, W, w.cuda(), wb, Y, 64 * (H // 2) * (W // 2), N)
+    assert rel(Y, y) < 2e-5
+    # weight gradient through the same im2col tiles (deterministic: workspace + fixed-order reduce)
+    wr = w.clone().requires_grad_(True)
+    dy = torch.randn(y.shape, generator=g)
+    F.conv2d(x, wr, None, 2, 3).backward(dy)
+    ws = torch.empty(ops.stem_wgrad_workspace_floats(), device='cuda')
+    runs = []
+    for _ in range(2):
+        dW = torch.zeros(64, 2, 7, 7, device='cuda')
+        ops.stem_conv_tc_wgrad(x.cuda(), 2 * H * W, H, W, dy.cuda(), 64 * (H // 2) * (W // 2), dW, ws, N)
+        runs.append(dW)
+    assert rel(runs[0], wr.grad) < 2e-5
+    assert torch.equal(runs[0], runs[1])
+
+
 def test_stem_bn_relu_maxpool_forward_backward():
     g = torch.Generator().manual_seed(5)
     n, c, h = 3, 64, 32

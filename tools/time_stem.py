@@ -28,10 +28,18 @@ def main():
     t = timeit(lambda: ops.conv_fwd(x, 2 * H * W, 2, H, W, w, None, C, 7, 2, Y, C * Ho * Wo, N, slope=1.0))
     fma = 2 * 49 * C * N * Ho * Wo
     print('stem conv fwd   %7.1f us  FMA %4.1f%%  write %5.0f GB/s' % (t * 1e6, 100 * fma / t / FMA_PEAK, Y.numel() * 4 / t / 1e9))
+    wb = torch.zeros(128 * 128, dtype=torch.bfloat16, device='cuda')
+    Y2 = torch.empty_like(Y)
+    t = timeit(lambda: ops.stem_conv_tc_fwd(x, 2 * H * W, H, W, w, wb, Y2, C * Ho * Wo, N))
+    print('stem conv fwd TC %6.1f us  write %5.0f GB/s  max|diff| vs simt %.2e' % (t * 1e6, Y.numel() * 4 / t / 1e9, float((Y2 - Y).abs().max())))
     dW = torch.zeros_like(w)
     dZ = torch.randn_like(Y)
     t = timeit(lambda: ops.conv_wgrad(x, 2 * H * W, 2, H, W, dZ, C * Ho * Wo, C, 7, 2, dW, None, N))
     print('stem conv wgrad %7.1f us  FMA %4.1f%%  read  %5.0f GB/s' % (t * 1e6, 100 * fma / t / FMA_PEAK, dZ.numel() * 4 / t / 1e9))
+    ws = torch.empty(ops.stem_wgrad_workspace_floats(), device='cuda')
+    dW2 = torch.zeros_like(w)
+    t = timeit(lambda: ops.stem_conv_tc_wgrad(x, 2 * H * W, H, W, dZ, C * Ho * Wo, dW2, ws, N))
+    print('stem conv wgrad TC %5.1f us  read  %5.0f GB/s' % (t * 1e6, dZ.numel() * 4 / t / 1e9))
     scale = torch.rand(C, device='cuda') + 0.5
     shift = torch.randn(C, device='cuda') * 0.1
     a_hi = torch.zeros(N, Hq + 2, Wq + 2, C, dtype=torch.bfloat16, device='cuda')
