@@ -586,6 +586,149 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------ wgrad, 64 x 64 layers
+// With Cout = 64 the generic kernel fills only half of the M = 128 MMA rows.  Here the roles
+// are swapped and two taps share one MMA: A (M side) = [X(tap 2p) ; X(tap 2p+1)] (2 x 64 input
+// channels, each box loaded at its own row shift), B (N side) = dY (64 output channels,
+// loaded once per k-block), so D_p[128][64] holds dW^T of both taps.  One CTA accumulates all
+// taps (ceil(ntaps/2) TMEM accumulators of 64 columns) over its pixel range.
+template <int BKP, int STAGES>
+struct Wgrad64Smem {
+  static constexpr int BOX_BYTES = BKP * 128;                  // BKP pixels x 64 channels bf16
+  static constexpr int G_BYTES = BOX_BYTES;                    // one plane of dY
+  static constexpr int XP_BYTES = 2 * BOX_BYTES;               // one plane of a tap pair
+  static constexpr int MAX_PAIRS = 5;
+  static constexpr int STAGE_BYTES = 2 * G_BYTES + MAX_PAIRS * 2 * XP_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BKP, int STAGES>
+__global__ void __launch_bounds__(128)
+wgrad64_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant__ CUtensorMap mapGl,
+               const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
+               const __grid_constant__ TapTable taps, float* __restrict__ dW, long P, int kb_per_split,
+               int oihw_taps, int g_lo_on, float* __restrict__ ws) {
+  using S = Wgrad64Smem<BKP, STAGES>;
+  constexpr int Cout = 64, Cin = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
+  const uint32_t tmem_full = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = tmem_full + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = taps.ntaps, npairs = (ntaps + 1) / 2;
+  const long kb_total = cdiv(P, BKP);
+  const long kb0 = (long)blockIdx.x * kb_per_split;
+  long kb1 = kb0 + kb_per_split;
+  if (kb1 > kb_total) kb1 = kb_total;
+  const int iters = (int)(kb1 - kb0);
+  const uint32_t stage_tx = (uint32_t)((g_lo_on ? 2 : 1) * S::G_BYTES + ntaps * 2 * S::BOX_BYTES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapGh);
+    tma_prefetch_desc(&mapGl);
+    tma_prefetch_desc(&mapXh);
+    tma_prefetch_desc(&mapXl);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  if (iters <= 0) {   // uniform per CTA (never happens: every split owns >= 1 k-block)
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_d, 512);
+    return;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
+      const uint32_t full = bar_base + 8 * s;
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+      mbar_expect_tx(full, stage_tx);
+      const int row = (int)((kb0 + i) * BKP);
+      tma_load_3d(st, &mapGh, full, 0, row, 0);
+      if (g_lo_on) tma_load_3d(st + S::G_BYTES, &mapGl, full, 0, row, 0);
+      for (int t = 0; t < ntaps; ++t) {
+        // pair p = t/2, box b = t%2 inside the pair's M = 128 tile; planes hi | lo per pair
+        const uint32_t xs = st + 2 * S::G_BYTES + (t >> 1) * 2 * S::XP_BYTES + (t & 1) * S::BOX_BYTES;
+        const int xrow = row + taps.shift[t], ph = taps.phase[t];
+        tma_load_3d(xs, &mapXh, full, 0, xrow, ph);
+        tma_load_3d(xs + S::XP_BYTES, &mapXl, full, 0, xrow, ph);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(64, 1, 1);
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_base + s * S::STAGE_BYTES;
+      for (int p = 0; p < npairs; ++p) {
+        const uint32_t xs = st + 2 * S::G_BYTES + p * 2 * S::XP_BYTES;
+        const uint32_t acc = tmem_d + p * 64;
+#pragma unroll
+        for (int ks = 0; ks < BKP / 16; ++ks) {   // 16 pixels per MMA = two 8-row swizzle atoms
+          const uint32_t koff = ks * 2048;
+          const uint64_t xh = umma_desc_sw128(xs + koff, S::BOX_BYTES, 1024);
+          const uint64_t xl = umma_desc_sw128(xs + S::XP_BYTES + koff, S::BOX_BYTES, 1024);
+          const uint64_t gh = umma_desc_sw128(st + koff, S::BOX_BYTES, 1024);
+          const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
+          umma_bf16(acc, xl, gh, idesc, (i | ks) != 0);
+          if (g_lo_on) umma_bf16(acc, xh, gl, idesc, 1);
+          umma_bf16(acc, xh, gh, idesc, 1);
+        }
+      }
+      umma_commit(bar_base + 8 * (STAGES + s));
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+  // thread = row m of every pair tile: tap 2p + (m >= 64), input channel m & 63; columns = co
+  const int m = warp * 32 + lane;
+  const int ci = m & 63;
+  for (int p = 0; p < npairs; ++p) {
+    const int t = 2 * p + (m >> 6);
+    const bool ok = t < ntaps;
+    const int bsel = ok ? taps.bsel[t] : 0;
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + p * 64 + c, r);
+      tmem_ld_wait();
+      if (!ok) continue;
+      if (ws) {       // [split][tap][Cout][Cin]: lanes = consecutive ci -> coalesced
+        float* o = ws + (((long)blockIdx.x * ntaps + t) * Cout + c) * Cin + ci;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[(long)j * Cin] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = c + j;
+          float* o = oihw_taps ? dW + ((long)co * Cin + ci) * oihw_taps + bsel
+                               : dW + ((long)bsel * Cout + co) * Cin + ci;
+          atomicAdd(o, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_d, 512);
+}
+
 // dW (+)= sum over splits of the workspace partials.  Block = 32 consecutive (co, ci) filters x
 // SL split lanes (one warp each); a thread sums its splits for every tap of its filter, the
 // lanes are combined through shared memory in a fixed order, and lane-warp 0 writes the
@@ -684,6 +827,50 @@ static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, co
   return DMC_OK;
 }
 
+static void wgrad64_plan(int BKP, long P, int sm_count, long* kb_per_split, long* splits) {
+  const long kb_total = cdiv(P, BKP);
+  long kbs = cdiv(kb_total, (long)sm_count * 2);      // one CTA per SM resident, two rounds
+  if (kbs < 8) kbs = 8;
+  *kb_per_split = kbs;
+  *splits = cdiv(kb_total, kbs);
+}
+
+template <int BKP, int STAGES>
+static int launch_wgrad64(const void* G_hi, const void* G_lo, const void* X_hi, const void* X_lo,
+                          int x_phases, const TapTable& taps, float* dW, long P, int sm_count,
+                          int oihw_taps, float* ws, long ws_floats, cudaStream_t stream) {
+  using S = Wgrad64Smem<BKP, STAGES>;
+  CUtensorMap mGh, mGl, mXh, mXl;
+  int rc;
+  const int g_lo_on = G_lo != nullptr;
+  if ((rc = make_map_3d(&mGh, G_hi, 64, P, 1, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, 64, P, 1, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mXh, X_hi, 64, P, x_phases, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mXl, X_lo, 64, P, x_phases, 64, BKP))) return rc;
+  auto kern = wgrad64_kernel<BKP, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+      return dmc_check_launch("wgrad64 smem attribute");
+    attr_set = true;
+  }
+  long kb_per_split, splits;
+  wgrad64_plan(BKP, P, sm_count, &kb_per_split, &splits);
+  const long per_split = (long)taps.ntaps * 64 * 64;
+  if (ws) DMC_REQUIRE(ws_floats >= splits * per_split, "wgrad: workspace %ld floats < %ld needed", ws_floats,
+                      splits * per_split);
+  kern<<<(unsigned)splits, 128, S::TOTAL, stream>>>(mGh, mGl, mXh, mXl, taps, dW, P, (int)kb_per_split,
+                                                    oihw_taps, g_lo_on, ws);
+  if ((rc = dmc_check_launch("wgrad64_kernel"))) return rc;
+  if (ws) {
+    const int SL = splits >= 8 ? 8 : (splits >= 4 ? 4 : (splits >= 2 ? 2 : 1));
+    wgrad_reduce_kernel<<<(unsigned)cdiv(64L * 64, 32), 32 * SL, SL * MAX_TAPS * 32 * sizeof(float),
+                          stream>>>(ws, (int)splits, taps, 64, 64, oihw_taps, dW);
+    return dmc_check_launch("wgrad_reduce_kernel");
+  }
+  return DMC_OK;
+}
+
 static int fill_taps(TapTable& tt, int ntaps, const int* shift, const int* phase, const int* bsel) {
   if (ntaps < 1 || ntaps > MAX_TAPS) return -1;
   tt.ntaps = ntaps;
@@ -771,6 +958,9 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // taps are grouped so that consecutive taps share a CTA: they must read the same phase-independent
   // dY tile (always true) -- the activation tile is per tap.
+  if (Cout == 64 && Cin == 64 && ntaps <= 10)      // layer1: two taps per M = 128 MMA
+    return launch_wgrad64<32, 2>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, P, sm_count(), oihw_taps,
+                                 workspace, workspace_floats, st);
   if (Cin % 128 == 0)       // wide tiles: one tap per CTA, two CTAs per SM (32-pixel k-blocks)
     return launch_wgrad<128, 1, 32, 3>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P,
                                        sm_count(), oihw_taps, workspace, workspace_floats, st);
@@ -782,7 +972,9 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
 // workspace == NULL selects the atomic-accumulation epilogue instead).
 extern "C" long dmc_tc_wgrad_workspace(long P, int Cout, int Cin, int ntaps) {
   long kbs, splits;
-  if (Cin % 128 == 0)
+  if (Cout == 64 && Cin == 64 && ntaps <= 10)
+    wgrad64_plan(32, P, sm_count(), &kbs, &splits);
+  else if (Cin % 128 == 0)
     wgrad_plan<1>(128, 32, Cout, Cin, ntaps, P, sm_count(), &kbs, &splits);
   else
     wgrad_plan<5>(64, 64, Cout, Cin, ntaps, P, sm_count(), &kbs, &splits);
