@@ -531,7 +531,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map,
                         int Cin, int Cout, int H, int W, float* __restrict__ dW,
-                        float* __restrict__ dbias, int N, int ci_groups, int xbox_c) {
+                        float* __restrict__ dbias, int N, int ci_groups, int xbox_c, int cpg) {
   constexpr int XP = 40, XR = 18, TR = 16;   // 4 + 32 + 4 columns: 16-byte aligned box start
   constexpr int XBUF = 8 * XR * XP, DBUF = COUT * TR * 32, STAGE = XBUF + DBUF;   // floats
   extern __shared__ uint8_t smem_raw[];
@@ -540,7 +540,9 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
   const uint32_t bar0 = base_u32 + 2 * STAGE * 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cig = blockIdx.y % ci_groups, cog = blockIdx.y / ci_groups;
-  const int ci = cig * 8 + warp, co0 = cog * COUT;
+  // input channels are dealt evenly to the groups (cpg <= 8 per CTA, one per warp): 33 channels
+  // run as 7+7+7+6+6 instead of 8+8+8+8+1
+  const int ci = warp < cpg ? cig * cpg + warp : Cin, co0 = cog * COUT;
   const int tiles_x = (W + 31) / 32, tiles_y = (H + TR - 1) / TR;
   const long items = (long)N * tiles_x * tiles_y;
   const uint32_t stage_bytes = (uint32_t)(xbox_c * XR * XP + DBUF) * 4;
@@ -564,7 +566,7 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
     const uint32_t b_ = bar0 + 8 * (stage_);                                          \
     const uint32_t dst_ = base_u32 + (stage_) * STAGE * 4;                            \
     mbar_expect_tx(b_, stage_bytes);                                                  \
-    tma_load_4d(dst_, &x_map, b_, ow0_ - 4, oh0_ - 1, cig * 8, n_);                   \
+    tma_load_4d(dst_, &x_map, b_, ow0_ - 4, oh0_ - 1, cig * cpg, n_);                 \
     tma_load_4d(dst_ + XBUF * 4, &dy_map, b_, ow0_, oh0_, co0, n_);                   \
   }
   if (tid == 0) {
@@ -672,7 +674,8 @@ static int launch_wgrad_v3(const float* in, long in_ns, int Cin, int H, int W, c
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
   dim3 grid((unsigned)gx, (unsigned)(ci_groups * co_groups));
-  kern<<<grid, 256, smem, st>>>(xm, dm, Cin, Cout, H, W, dW, dbias, N, ci_groups, Cin < 8 ? Cin : 8);
+  const int cpg = (int)cdiv(Cin, ci_groups);
+  kern<<<grid, 256, smem, st>>>(xm, dm, Cin, Cout, H, W, dW, dbias, N, ci_groups, Cin < 8 ? Cin : 8, cpg);
   return dmc_check_launch("conv3x3_wgrad_v3_kernel");
 }
 

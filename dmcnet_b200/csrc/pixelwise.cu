@@ -61,37 +61,49 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
-// All conv weights of the classifier in ONE launch: a chunk table maps 1024-element chunks
-// of the [tap][co][ci] enumeration to (tensor, destination planes).
+// All conv weights of the classifier in ONE launch: a chunk table maps 32 x 32 (co, ci) tiles
+// to (tensor, destination planes).  A CTA reads its tile's taps as 32 contiguous runs of the
+// OIHW tensor into shared memory and writes both operand layouts with the fastest index on
+// the lanes ([tap][co][ci]: ci, [tap][ci][co]: co), so every global access is a full run.
 struct PrepChunk {
   long long w_off;             // element offset of the OIHW tensor inside the parameter bucket
   long long Wh, Wl, Th, Tl;    // destination addresses (bf16), Th/Tl may be 0
-  int Cout, Cin, taps, start;  // start = first element of this chunk
+  int Cout, Cin, taps, start;  // start = tile index: (co tile) * (Cin / 32) + (ci tile)
 };
 
 __global__ void __launch_bounds__(256)
 weight_prep_multi_kernel(const float* __restrict__ params, const PrepChunk* __restrict__ chunks) {
+  __shared__ float tile[32][32 * 9 + 1];
   const PrepChunk ch = chunks[blockIdx.x];
+  const int taps = ch.taps, Cin = ch.Cin, Cout = ch.Cout;
+  const int tiles_ci = Cin / 32;
+  const int co0 = (ch.start / tiles_ci) * 32, ci0 = (ch.start % tiles_ci) * 32;
   const float* w = params + ch.w_off;
   bf16* Wh = reinterpret_cast<bf16*>(ch.Wh);
   bf16* Wl = reinterpret_cast<bf16*>(ch.Wl);
   bf16* Th = reinterpret_cast<bf16*>(ch.Th);
   bf16* Tl = reinterpret_cast<bf16*>(ch.Tl);
-  const int n = ch.Cout * ch.Cin * ch.taps;
-  const int end = ch.start + 1024 < n ? ch.start + 1024 : n;
-  for (int i = ch.start + threadIdx.x; i < end; i += 256) {
-    const int ci = i % ch.Cin;
-    const int co = (i / ch.Cin) % ch.Cout;
-    const int t = i / (ch.Cin * ch.Cout);
-    const float v = w[((long)co * ch.Cin + ci) * ch.taps + t];
-    bf16 h, l;
-    split_bf16(v, h, l);
-    Wh[i] = h;
-    Wl[i] = l;
-    if (Th) {
-      const long j = ((long)t * ch.Cin + ci) * ch.Cout + co;
-      Th[j] = h;
-      Tl[j] = l;
+  const int run = 32 * taps;                       // contiguous floats per output channel
+  for (int i = threadIdx.x; i < 32 * run; i += 256) {
+    const int co = i / run, r = i - co * run;
+    tile[co][r] = w[((long)(co0 + co) * Cin + ci0) * taps + r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < taps * 1024; i += 256) {
+    const int x = i & 31, y = (i >> 5) & 31, t = i >> 10;
+    {   // [tap][co][ci]: x = ci
+      bf16 h, l;
+      split_bf16(tile[y][x * taps + t], h, l);
+      const long o = ((long)t * Cout + co0 + y) * Cin + ci0 + x;
+      Wh[o] = h;
+      Wl[o] = l;
+    }
+    if (Th) {   // [tap][ci][co]: x = co
+      bf16 h, l;
+      split_bf16(tile[x][y * taps + t], h, l);
+      const long o = ((long)t * Cin + ci0 + y) * Cout + co0 + x;
+      Th[o] = h;
+      Tl[o] = l;
     }
   }
 }
@@ -478,7 +490,8 @@ extern "C" int dmc_weight_prep(const float* w_oihw, int Cout, int Cin, int taps,
   return dmc_check_launch("weight_prep_kernel");
 }
 
-// chunks: device array of PrepChunk {int64 w_off, Wh, Wl, Th, Tl; int32 Cout, Cin, taps, start}
+// chunks: device array of PrepChunk {int64 w_off, Wh, Wl, Th, Tl; int32 Cout, Cin, taps, tile}, one per
+// 32 x 32 (co, ci) tile: tile = (co / 32) * (Cin / 32) + ci / 32; Cout and Cin multiples of 32, taps <= 9
 extern "C" int dmc_weight_prep_multi(const float* params, const void* chunks, int nchunks,
                                      void* stream) {
   if (nchunks <= 0) return DMC_OK;

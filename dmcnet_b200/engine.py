@@ -469,11 +469,11 @@ class DmcEngine:
                     if key not in blk:
                         continue
                     u = blk[key]
-                    n = u.cout * u.cin * u.taps
-                    for start in range(0, n, 1024):
+                    assert u.cout % 32 == 0 and u.cin % 32 == 0 and u.taps <= 9
+                    for tile in range((u.cout // 32) * (u.cin // 32)):       # 32 x 32 (co, ci) tiles
                         rows.append([self.offsets[u.name_conv + '.weight'], u.W_hi.data_ptr(),
                                      u.W_lo.data_ptr(), u.Wt_hi.data_ptr(), u.Wt_lo.data_ptr(),
-                                     u.cout | (u.cin << 32), u.taps | (start << 32)])
+                                     u.cout | (u.cin << 32), u.taps | (tile << 32)])
             self._prep_chunks = torch.tensor(rows, dtype=torch.int64).to(self.device)
         ops.weight_prep_multi(self.params, self._prep_chunks, self._prep_chunks.shape[0])
 
