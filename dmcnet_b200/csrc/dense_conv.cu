@@ -533,7 +533,8 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
                         int Cin, int Cout, int H, int W, float* __restrict__ dW,
                         float* __restrict__ dbias, int N, int ci_groups, int xbox_c, int cpg) {
   constexpr int XP = 40, XR = 18, TR = 16;   // 4 + 32 + 4 columns: 16-byte aligned box start
-  constexpr int XBUF = 8 * XR * XP, DBUF = COUT * TR * 32, STAGE = XBUF + DBUF;   // floats
+  constexpr int DBUF = COUT * TR * 32;
+  const int XBUF = (xbox_c * XR * XP + 31) & ~31, STAGE = XBUF + DBUF;   // floats; the CTA has xbox_c warps
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
   const float* buf = reinterpret_cast<const float*>(smem_raw + (base_u32 - smem_u32(smem_raw)));
@@ -586,32 +587,30 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
     if (ci < Cin) {
       const float* xs = buf + (k & 1) * STAGE + warp * XR * XP + lane + 3;   // tile col 0 = x0 - 4
       const float* ds = buf + (k & 1) * STAGE + XBUF + lane;
-      float2 w0[3], w1[3], w2[3];   // window values broadcast into both halves
+      // 3 x 3 scalar window, rows rotate through three register slots (rows fully unrolled, so
+      // the slot index is static and no register is ever moved); FFMA2 broadcasts the scalar
+      float xw[3][3];
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        w0[s] = make_float2(xs[s], xs[s]);
-        w1[s] = make_float2(xs[XP + s], xs[XP + s]);
+        xw[0][s] = xs[s];
+        xw[1][s] = xs[XP + s];
       }
-#pragma unroll 4
+#pragma unroll
       for (int y = 0; y < TR; ++y) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const float t = xs[(y + 2) * XP + s];
-          w2[s] = make_float2(t, t);
-        }
+        for (int s = 0; s < 3; ++s) xw[(y + 2) % 3][s] = xs[(y + 2) * XP + s];
 #pragma unroll
         for (int c = 0; c < COUT / 2; ++c) {
           const float2 d = make_float2(ds[((2 * c) * TR + y) * 32], ds[((2 * c + 1) * TR + y) * 32]);
           bs[c] = __fadd2_rn(bs[c], d);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            acc[c][0][s] = __ffma2_rn(d, w0[s], acc[c][0][s]);
-            acc[c][1][s] = __ffma2_rn(d, w1[s], acc[c][1][s]);
-            acc[c][2][s] = __ffma2_rn(d, w2[s], acc[c][2][s]);
-          }
-        }
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) { w0[s] = w1[s]; w1[s] = w2[s]; }
+            for (int s = 0; s < 3; ++s) {
+              const float v = xw[(y + r) % 3][s];
+              acc[c][r][s] = __ffma2_rn(make_float2(v, v), d, acc[c][r][s]);
+            }
+        }
       }
     }
     __syncthreads();
@@ -640,13 +639,17 @@ conv3x3_wgrad_v3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_
 template <int COUT>
 static int launch_wgrad_v3(const float* in, long in_ns, int Cin, int H, int W, const float* dY,
                            long dy_ns, int Cout, float* dW, float* dbias, int N, cudaStream_t st) {
+  // input channels are dealt evenly to ceil(Cin/8) groups; a CTA has one warp per channel of its
+  // group (5..8 warps) and stages exactly those channels
+  const int ci_groups = (int)cdiv(Cin, 8), co_groups = (int)cdiv(Cout, COUT);
+  const int cpg = (int)cdiv(Cin, ci_groups);
   CUtensorMap xm, dm;
   {
     const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
                                         (unsigned long long)Cin, (unsigned long long)N};
     const unsigned long long str[3] = {(unsigned long long)W, (unsigned long long)H * W,
                                        (unsigned long long)in_ns};
-    const unsigned int box[4] = {40u, 18u, (unsigned)(Cin < 8 ? Cin : 8), 1u};
+    const unsigned int box[4] = {40u, 18u, (unsigned)cpg, 1u};
     int rc = dmc_make_f32_map(&xm, in, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -659,23 +662,26 @@ static int launch_wgrad_v3(const float* in, long in_ns, int Cin, int H, int W, c
     int rc = dmc_make_f32_map(&dm, dY, 4, dims, str, box);
     if (rc) return rc;
   }
-  constexpr int STAGE = 8 * 18 * 40 + COUT * 16 * 32;
+  const int STAGE = ((cpg * 18 * 40 + 31) & ~31) + COUT * 16 * 32;
   const int smem = 128 + 2 * STAGE * 4 + 64;
   auto kern = conv3x3_wgrad_v3_kernel<COUT>;
-  static bool attr = false;
-  if (!attr) {
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return dmc_check_launch("conv3x3_wgrad_v3 smem attribute");
-    attr = true;
+    attr_bytes = smem;
   }
-  const int ci_groups = (int)cdiv(Cin, 8), co_groups = (int)cdiv(Cout, COUT);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * cpg, smem) != cudaSuccess || occ < 1)
+    return dmc_check_launch("conv3x3_wgrad_v3 occupancy");
   const long items = (long)N * cdiv(W, 32) * cdiv(H, 16);
-  long gx = cdiv(148L * 3, (long)ci_groups * co_groups);
+  // a few more CTAs than are resident: measured faster than an exact fit (shorter item lists
+  // even out the tail)
+  long gx = cdiv(148L * (occ > 3 ? occ : 3), (long)ci_groups * co_groups);
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
   dim3 grid((unsigned)gx, (unsigned)(ci_groups * co_groups));
-  const int cpg = (int)cdiv(Cin, ci_groups);
-  kern<<<grid, 256, smem, st>>>(xm, dm, Cin, Cout, H, W, dW, dbias, N, ci_groups, Cin < 8 ? Cin : 8, cpg);
+  kern<<<grid, 32 * cpg, smem, st>>>(xm, dm, Cin, Cout, H, W, dW, dbias, N, ci_groups, cpg, cpg);
   return dmc_check_launch("conv3x3_wgrad_v3_kernel");
 }
 
