@@ -50,3 +50,6 @@ extern "C" int dmc_device_arch(void) {
 // launch site goes through dmc_check_launch exactly once).
 extern "C" long long dmc_launch_count(void) { return g_launches.load(); }
 extern "C" void dmc_reset_launch_count(void) { g_launches.store(0); }
+
+// 0: shared zero ring (row 0 / column 0 only), 1: private ring on every side (see common.cuh).
+extern "C" int dmc_layout_pad_hi(void) { return DMC_PAD_HI; }

@@ -201,15 +201,22 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int n, int a_mn_major, int b
 }
 
 // ---------------------------------------------------------------- padded pixel-major geometry
-// Activations of the classifier live as [frames][Hp][Wp][C] with a one-pixel
-// zero ring (Hp = H+2, Wp = W+2); q is the flat padded pixel index.
+// Activations of the classifier live as [frames][Hp][Wp][C]; q is the flat padded pixel index.
+// The zero ring is SHARED: row 0 and column 0 of every frame are zero, and the bottom / right
+// neighbours of the last row / column are the next frame's row 0 / the next row's column 0
+// (reads past the last frame are TMA out-of-bounds zero fill).  Hp = H + 1 + DMC_PAD_HI,
+// Wp = W + 1 + DMC_PAD_HI; DMC_PAD_HI = 1 would restore a private ring on every side
+// (81 instead of 64 rows per 7x7 frame, 256 instead of 225 per 14x14 frame).
+#define DMC_PAD_HI 0
+__host__ __device__ inline int dmc_padded(int h) { return h + 1 + DMC_PAD_HI; }
+__host__ __device__ inline int dmc_unpadded(int hp) { return hp - 1 - DMC_PAD_HI; }
 __host__ __device__ inline bool interior(long q, int Hp, int Wp) {
   // q < 2^31 for every tensor this library builds: 32-bit unsigned division is ~5x cheaper
   const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp;
   const unsigned row = uq / uw;
   const unsigned wp = uq - row * uw;
   const unsigned hp = row % uh;
-  return wp >= 1u && wp <= uw - 2u && hp >= 1u && hp <= uh - 2u;
+  return wp >= 1u && wp + DMC_PAD_HI < uw && hp >= 1u && hp + DMC_PAD_HI < uh;
 }
 
 // i -> (i / d, i % d) for 32-bit i; shift/mask when d is a power of two (channel counts)

@@ -369,7 +369,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b
 __global__ void __launch_bounds__(256)
 phase_split_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int frames, int H,
                    int W, int C, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
-  const int Hq = H / 2 + 2, Wq = W / 2 + 2, c8n = C / 8;
+  const int Hq = dmc_padded(H / 2), Wq = dmc_padded(W / 2), c8n = C / 8;
   const long Pq = (long)frames * Hq * Wq;
   const long n = 4 * Pq * c8n;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -380,9 +380,9 @@ phase_split_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_l
     const int f = (int)(r % frames);
     const int ph = (int)(r / frames);
     uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-    if (hq >= 1 && hq <= Hq - 2 && wq >= 1 && wq <= Wq - 2) {
+    if (hq >= 1 && hq <= H / 2 && wq >= 1 && wq <= W / 2) {
       const int h = 2 * (hq - 1) + (ph >> 1) + 1, w = 2 * (wq - 1) + (ph & 1) + 1;
-      const long src = (((long)f * (H + 2) + h) * (W + 2) + w) * C + c;
+      const long src = (((long)f * dmc_padded(H) + h) * dmc_padded(W) + w) * C + c;
       vh = *reinterpret_cast<const uint4*>(in_hi + src);
       vl = *reinterpret_cast<const uint4*>(in_lo + src);
     }
@@ -396,7 +396,7 @@ phase_split_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_l
 __global__ void __launch_bounds__(256)
 phase_unsplit_kernel(const float* __restrict__ in, int frames, int H, int W, int C,
                      float* __restrict__ out) {
-  const int Hq = H / 2 + 2, Wq = W / 2 + 2, Hp = H + 2, Wp = W + 2, c4n = C / 4;
+  const int Hq = dmc_padded(H / 2), Wq = dmc_padded(W / 2), Hp = dmc_padded(H), Wp = dmc_padded(W), c4n = C / 4;
   const long n = (long)frames * Hp * Wp * c4n;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
@@ -405,7 +405,7 @@ phase_unsplit_kernel(const float* __restrict__ in, int frames, int H, int W, int
     const int hp = (int)(r % Hp);
     const int f = (int)(r / Hp);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (hp >= 1 && hp <= Hp - 2 && wp >= 1 && wp <= Wp - 2) {
+    if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) {
       const int h = hp - 1, w = wp - 1;
       const int ph = (h & 1) * 2 + (w & 1);
       const long src = ((((long)ph * frames + f) * Hq + (h >> 1) + 1) * Wq + (w >> 1) + 1) * C + c;
@@ -419,11 +419,12 @@ phase_unsplit_kernel(const float* __restrict__ in, int frames, int H, int W, int
 __global__ void avgpool_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int frames,
                                int Hp, int Wp, int C, float* __restrict__ pooled) {
   const int f = blockIdx.x;
-  const float inv = 1.f / (float)((Hp - 2) * (Wp - 2));
+  const int H = dmc_unpadded(Hp), W = dmc_unpadded(Wp);
+  const float inv = 1.f / (float)(H * W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int h = 1; h <= Hp - 2; ++h)
-      for (int w = 1; w <= Wp - 2; ++w) {
+    for (int h = 1; h <= H; ++h)
+      for (int w = 1; w <= W; ++w) {
         const long off = (((long)f * Hp + h) * Wp + w) * C + c;
         s += join_bf16(hi[off], lo[off]);
       }
@@ -434,7 +435,7 @@ __global__ void avgpool_kernel(const bf16* __restrict__ hi, const bf16* __restri
 __global__ void avgpool_bwd_kernel(const float* __restrict__ dpooled, int frames, int Hp, int Wp,
                                    int C, float* __restrict__ dX) {
   const long n = (long)frames * Hp * Wp * C;
-  const float inv = 1.f / (float)((Hp - 2) * (Wp - 2));
+  const float inv = 1.f / (float)(dmc_unpadded(Hp) * dmc_unpadded(Wp));
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long q = i / C;
@@ -581,7 +582,7 @@ extern "C" int dmc_bn_bwd_apply(const float* g_a, const float* g_b, const void* 
 extern "C" int dmc_phase_split(const void* in_hi, const void* in_lo, int frames, int H, int W, int C,
                                void* out_hi, void* out_lo, void* stream) {
   DMC_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "phase_split: H=%d W=%d C=%d", H, W, C);
-  const long n = 4L * frames * (H / 2 + 2) * (W / 2 + 2) * (C / 8);
+  const long n = 4L * frames * dmc_padded(H / 2) * dmc_padded(W / 2) * (C / 8);
   phase_split_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(
       (const bf16*)in_hi, (const bf16*)in_lo, frames, H, W, C, (bf16*)out_hi, (bf16*)out_lo);
   return dmc_check_launch("phase_split_kernel");
@@ -590,7 +591,7 @@ extern "C" int dmc_phase_split(const void* in_hi, const void* in_lo, int frames,
 extern "C" int dmc_phase_unsplit(const float* in, int frames, int H, int W, int C, float* out,
                                  void* stream) {
   DMC_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "phase_unsplit: H=%d W=%d C=%d", H, W, C);
-  const long n = (long)frames * (H + 2) * (W + 2) * (C / 4);
+  const long n = (long)frames * dmc_padded(H) * dmc_padded(W) * (C / 4);
   phase_unsplit_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(in, frames, H, W, C, out);
   return dmc_check_launch("phase_unsplit_kernel");
 }

@@ -8,7 +8,8 @@
 
 namespace dmc {
 
-// grid (Hq, N); Y [N][C][H][W] -> hi/lo [N][Hq+2][Wq+2][C] interior, idx [N][Hq][Wq][C].
+// grid (Hq, N); Y [N][C][H][W] -> hi/lo padded pixel-major [N][Hq+1][Wq+1][C] interior (common.cuh),
+// idx [N][Hq][Wq][C].
 // One warp streams one (channel, input row) at a time with 128-bit loads (no per-element
 // index arithmetic); the pooled row is then produced channel-fastest so the pixel-major
 // stores coalesce.
@@ -55,7 +56,7 @@ stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scal
           const float v = rows[(c * 3 + r) * WP + w];
           if (v > best) { best = v; bi = r * 3 + s3; }
         }
-      const long o = (((long)n * (Hq + 2) + ph + 1) * (Wq + 2) + pw + 1) * C + cg + c;
+      const long o = (((long)n * dmc_padded(Hq) + ph + 1) * dmc_padded(Wq) + pw + 1) * C + cg + c;
       bf16 h, l;
       split_bf16(best, h, l);
       out_hi[o] = h;
@@ -107,7 +108,7 @@ stem_pool_bwd_kernel(const float* __restrict__ g_a, const float* __restrict__ g_
           pww[u] = 2 * ((ii / CG) % nw) + wp;
           kk[u] = i < cnt ? 2 * (ii / (CG * nw)) + kp : -1;
           const int ph = ph0 + (kk[u] < 0 ? kp : kk[u]);
-          const long o = (((long)n * (Hq + 2) + ph + 1) * (Wq + 2) + pww[u] + 1) * C + cg + cc[u];
+          const long o = (((long)n * dmc_padded(Hq) + ph + 1) * dmc_padded(Wq) + pww[u] + 1) * C + cg + cc[u];
           g[u] = g_a[o];
           if (g_b) g[u] += g_b[o];
           id[u] = idx[(((long)n * Hq + ph) * Wq + pww[u]) * C + cg + cc[u]];

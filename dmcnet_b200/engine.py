@@ -50,7 +50,7 @@ class _Geo:
 
     def __init__(self, frames: int, H: int, W: int):
         self.frames, self.H, self.W = frames, H, W
-        self.Hp, self.Wp = H + 2, W + 2
+        self.Hp, self.Wp = ops.padded(H), ops.padded(W)     # shared zero ring: row 0 / column 0
         self.P = frames * self.Hp * self.Wp
         self.count = float(frames * H * W)
 

@@ -41,6 +41,16 @@ def _iarr(v: Sequence[int]):
 _hook = None          # profiling hook: callable(name, args) -> context manager, or None
 
 
+def pad_hi() -> int:
+    """High-side padding of the pixel-major layout (0: shared zero ring, see csrc/common.cuh)."""
+    return int(_native.lib().dmc_layout_pad_hi())
+
+
+def padded(h: int) -> int:
+    """Padded extent of a pixel-major dimension of h pixels."""
+    return h + 1 + pad_hi()
+
+
 def set_call_hook(hook) -> None:
     global _hook
     _hook = hook

@@ -61,7 +61,8 @@ def _flops(name, args):
     """Algorithmic FLOPs of one call (0 for bandwidth kernels)."""
     if name in ('dmc_tc_tap_gemm', 'dmc_simt_tap_gemm'):
         K, N, M, Hp, Wp, ntaps = _v(args[4]), _v(args[8]), _v(args[10]), _v(args[12]), _v(args[13]), _v(args[14])
-        valid = M * ((Hp - 2) * (Wp - 2)) / float(Hp * Wp) if Hp else M
+        ph = ops.pad_hi()
+        valid = M * ((Hp - 1 - ph) * (Wp - 1 - ph)) / float(Hp * Wp) if Hp else M
         return 2.0 * valid * N * K * ntaps
     if name in ('dmc_tc_wgrad', 'dmc_simt_wgrad'):
         P, Cout, Cin, ntaps = _v(args[2]), _v(args[3]), _v(args[7]), _v(args[9])

@@ -23,13 +23,13 @@ def split(x):
 
 def to_pixel(x):      # [N,C,H,W] -> padded pixel-major [N*(H+2)*(W+2), C]
     n, c, h, w = x.shape
-    p = torch.zeros(n, h + 2, w + 2, c)
-    p[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1)
+    p = torch.zeros(n, ops.padded(h), ops.padded(w), c)
+    p[:, 1:h + 1, 1:w + 1, :] = x.permute(0, 2, 3, 1)
     return p.reshape(-1, c).contiguous()
 
 
 def from_pixel(flat, n, c, h, w):
-    return flat.reshape(n, h + 2, w + 2, c)[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+    return flat.reshape(n, ops.padded(h), ops.padded(w), c)[:, 1:h + 1, 1:w + 1, :].permute(0, 3, 1, 2)
 
 
 # ------------------------------------------------------------------ planar small-channel convs
@@ -103,7 +103,7 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy)
     ho = h // stride
-    Hp = Wp = ho + 2
+    Hp = Wp = ops.padded(ho)
     P = n * Hp * Wp
     W_hi = torch.zeros(9, cout, cin, dtype=torch.bfloat16, device='cuda')
     W_lo, Wt_hi, Wt_lo = (torch.zeros_like(W_hi) for _ in range(3))
@@ -134,7 +134,7 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
     assert rel(stats[0], yd.sum((0, 2, 3))) < 5e-5 * (n * ho * ho) ** 0.5
     assert rel(stats[1], (yd * yd).sum((0, 2, 3))) < 5e-5
     ring = D.view(n, Hp, Wp, cout).clone()
-    ring[:, 1:-1, 1:-1] = 0
+    ring[:, 1:ho + 1, 1:ho + 1] = 0
     assert float(ring.abs().max()) == 0.0                         # epilogue keeps the zero ring
     # wgrad
     G_hi, G_lo = split(to_pixel(dy).cuda())
@@ -182,7 +182,7 @@ def test_tap_gemm_conv_fprop_dgrad_wgrad(engine, n, cin, cout, h, stride):
             bs = [bsel[t] for t in range(9) if phase[t] == ph]
             ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dxp[ph], a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin,
                          M=P, ldD=cin, Hp=Hp, Wp=Wp, shift=sh, phase=[0] * len(sh), bsel=bs, engine=engine)
-        dX = torch.empty(n * (h + 2) * (h + 2), cin, device='cuda')
+        dX = torch.empty(n * ops.padded(h) * ops.padded(h), cin, device='cuda')
         ops.phase_unsplit(dxp, n, h, h, cin, dX)
         assert rel(from_pixel(dX, n, cin, h, h), x.grad) < 5e-5
 
@@ -199,7 +199,7 @@ def test_pixel_bn_train_forward_backward_with_residual():
     out = F.relu(F.batch_norm(y, rm, rv, gamma, beta, True, 0.1, 1e-5) + res)
     dout = torch.randn(out.shape, generator=g)
     out.backward(dout)
-    Hp = h + 2
+    Hp = ops.padded(h)
     P = n * Hp * Hp
     dev = dict(device='cuda')
     Y = to_pixel(y.detach()).cuda()
@@ -299,7 +299,7 @@ def test_stem_bn_relu_maxpool_forward_backward():
     dz_ref = da * (a.detach() > 0)
     hq = h // 2
     dev = dict(device='cuda')
-    o_hi = torch.zeros(n * (hq + 2) * (hq + 2), c, dtype=torch.bfloat16, **dev)
+    o_hi = torch.zeros(n * ops.padded(hq) * ops.padded(hq), c, dtype=torch.bfloat16, **dev)
     o_lo = torch.zeros_like(o_hi)
     idx = torch.zeros(n * hq * hq * c, dtype=torch.uint8, **dev)
     Y = y.detach().cuda()

@@ -240,8 +240,9 @@ def test_full_size_properties_b64():
         assert all(np.isfinite(m['loss']) for m in ms)
         assert ms[-1]['loss_mse'] < ms[0]['loss_mse']
         blk = eng.blocks[0]['c2']
-        ring = (blk.act_hi.float() + blk.act_lo.float()).view(B * 3, 58, 58, 64).clone()
-        ring[:, 1:-1, 1:-1] = 0
+        hp = blk.geo.Hp
+        ring = (blk.act_hi.float() + blk.act_lo.float()).view(B * 3, hp, hp, 64).clone()
+        ring[:, 1:57, 1:57] = 0
         assert float(ring.abs().max()) == 0.0
         assert int(eng.buffers['base_model.bn1.num_batches_tracked']) == 4
         outs[graph] = (ms[-1]['loss'], eng.params.clone())

@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from dmcnet_b200 import engine as E
+from dmcnet_b200 import ops
 from dmcnet_b200 import model as M
 from oracle import dmc_oracle as O
 
@@ -44,10 +45,10 @@ def test_model_api_surface():
         m(torch.zeros(1, 3, 2, 224, 224), torch.zeros(1, 3, 3, 224, 224))
 
 
-def _pad_pixel_major(x):          # [N,C,H,W] -> [N*(H+2)*(W+2), C] with zero ring
+def _pad_pixel_major(x):          # [N,C,H,W] -> [N*Hp*Wp, C] with the (shared) zero ring
     n, c, h, w = x.shape
-    p = np.zeros((n, h + 2, w + 2, c), np.float64)
-    p[:, 1:-1, 1:-1, :] = x.transpose(0, 2, 3, 1)
+    p = np.zeros((n, ops.padded(h), ops.padded(w), c), np.float64)
+    p[:, 1:h + 1, 1:w + 1, :] = x.transpose(0, 2, 3, 1)
     return p.reshape(-1, c)
 
 
@@ -65,7 +66,7 @@ def _tap_gemm(A, B, shift, phase, bsel, M_rows):
 
 
 def _interior(n, h, w, c, flat):
-    return flat.reshape(n, h + 2, w + 2, c)[:, 1:-1, 1:-1, :].transpose(0, 3, 1, 2)
+    return flat.reshape(n, ops.padded(h), ops.padded(w), c)[:, 1:h + 1, 1:w + 1, :].transpose(0, 3, 1, 2)
 
 
 def _phase_split(x):               # [N,C,H,W] -> [4][N*(H/2+2)*(W/2+2), C]
@@ -79,13 +80,13 @@ def test_tap_tables_stride1_and_stride2_match_conv2d():
     wt = rng.standard_normal((co, ci, 3, 3))
     Wg = wt.transpose(2, 3, 0, 1).reshape(9, co, ci)               # [tap][co][ci]
     # stride 1
-    shift, phase, bsel = E._taps_s1(w + 2)
+    shift, phase, bsel = E._taps_s1(ops.padded(w))
     A = _pad_pixel_major(x)[None]
     y = _interior(n, h, w, co, _tap_gemm(A, Wg, shift, phase, bsel, A.shape[1]))
     ref = F.conv2d(torch.tensor(x), torch.tensor(wt), None, 1, 1).numpy()
     np.testing.assert_allclose(y, ref, atol=1e-10)
     # stride 2 through the four input phases stored in the OUTPUT geometry
-    shift, phase, bsel = E._taps_s2(w // 2 + 2)
+    shift, phase, bsel = E._taps_s2(ops.padded(w // 2))
     A2 = _phase_split(x)
     y2 = _interior(n, h // 2, w // 2, co, _tap_gemm(A2, Wg, shift, phase, bsel, A2.shape[1]))
     ref2 = F.conv2d(torch.tensor(x), torch.tensor(wt), None, 2, 1).numpy()
@@ -107,10 +108,10 @@ def test_tap_tables_data_gradients():
         G = _pad_pixel_major(dy)[None]
         ho, wo = h // stride, w // stride
         if stride == 1:
-            shift, phase, bsel = E._taps_s1(w + 2)
+            shift, phase, bsel = E._taps_s1(ops.padded(w))
             dx = _interior(n, h, w, ci, _tap_gemm(G, Wt, [-s for s in shift], phase, bsel, G.shape[1]))
         else:
-            fs, fp, fb = E._taps_s2(wo + 2)
+            fs, fp, fb = E._taps_s2(ops.padded(wo))
             dx = np.zeros((n, ci, h, w))
             for ph in range(4):
                 sh = [-fs[t] for t in range(9) if fp[t] == ph]

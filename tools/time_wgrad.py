@@ -8,7 +8,7 @@ from dmcnet_b200.engine import _taps_s1
 N = 192
 def main():
     for c, h in ((64, 56), (128, 28), (256, 14), (512, 7)):
-        Hp = h + 2
+        Hp = ops.padded(h)
         P = N * Hp * Hp
         G = torch.randn(P, c, device='cuda')
         X = torch.randn(P, c, device='cuda')
