@@ -782,7 +782,7 @@ static void wgrad_plan(int BN, int BKP, int Cout, int Cin, int ntaps, long P, in
   long want_splits = ((long)sm_count * (TG > 1 ? 2 : 4)) / tiles;
   if (want_splits < 1) want_splits = 1;
   long kbs = cdiv(kb_total, want_splits);
-  if (kbs < 8) kbs = 8;
+  if (kbs < 16) kbs = 16;     // shorter pixel ranges are all prologue + epilogue (1x1 downsample layers)
   *kb_per_split = kbs;
   *splits = cdiv(kb_total, kbs);
 }
@@ -830,7 +830,7 @@ static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, co
 static void wgrad64_plan(int BKP, long P, int sm_count, long* kb_per_split, long* splits) {
   const long kb_total = cdiv(P, BKP);
   long kbs = cdiv(kb_total, (long)sm_count * 2);      // one CTA per SM resident, two rounds
-  if (kbs < 8) kbs = 8;
+  if (kbs < 16) kbs = 16;     // shorter pixel ranges are all prologue + epilogue (1x1 downsample layers)
   *kb_per_split = kbs;
   *splits = cdiv(kb_total, kbs);
 }

@@ -344,6 +344,13 @@ stem_conv_tc_wgrad_kernel(const float* __restrict__ in, long in_ns, int H, int W
       if (px < Wo) gv[c] = *reinterpret_cast<const float4*>(src + 4 * c);   // Wo % 4 == 0
     }
   };
+  // L2 prefetch of a later gradient row: the register prefetch above keeps only one row
+  // (32 KB per SM) in flight, which at DRAM latency caps the kernel near 1.5 TB/s
+  auto grad_prefetch = [&](int n, int y) {
+    const float* src = dP + (long)n * dp_ns + ((long)gco * Ho + y) * Wo + ghalf * 64;
+    if (ghalf * 64 < Wo) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    if (ghalf * 64 + 32 < Wo) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 32));
+  };
   auto grad_store = [&](uint8_t* G) {                  // 8 chunks (8 pixels each) of row gco, hi and lo
 #pragma unroll
     for (int c8 = 0; c8 < 8; ++c8) {
@@ -392,6 +399,12 @@ stem_conv_tc_wgrad_kernel(const float* __restrict__ in, long in_ns, int H, int W
       grad_store(G);
       fence_proxy_async();
       if (it + 1 < rows) grad_load(n1, y1);
+      if (it + 4 < rows) {                             // row it+4: three steps before its register load
+        int n4 = n2, y4 = y2;
+        advance(n4, y4);
+        advance(n4, y4);
+        grad_prefetch(n4, y4);
+      }
     }
     tc_fence_before();
     __syncthreads();

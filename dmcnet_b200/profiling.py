@@ -107,6 +107,12 @@ def measure_roofline(resident_step, per, steps, trainer):
         ops.set_call_hook(None)
         trainer.use_graph = was_graph
     ms, fl, cnt = timer.totals()
+    if os.environ.get('DMC_DUMP_CALLS'):            # per-call times of one family, in launch order
+        fam_dump = os.environ['DMC_DUMP_CALLS']
+        import sys
+        for name, e0, e1, f in timer.events:
+            if fam_dump in name:
+                print('CALL %s %.1f us %.1f GFLOP' % (name, e0.elapsed_time(e1) * 1e3, f / 1e9), file=sys.stderr)
     denom = float(steps * per)
     breakdown = {k.replace('dmc_', ''): round(v / denom, 4) for k, v in sorted(ms.items(), key=lambda kv: -kv[1])}
     top = max(ms, key=lambda k: ms[k])
