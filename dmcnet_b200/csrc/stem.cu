@@ -24,22 +24,45 @@ stem_pool_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ scal
   const int WP = W + 1, W4 = W / 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int cg = 0; cg < C; cg += CG) {
-    for (int cr = warp; cr < CG * 3; cr += nwarps) {
-      const int c = cr / 3, r = cr - 3 * c;
-      const int h = 2 * ph - 1 + r;
-      float* dst = rows + cr * WP;
-      if (h >= 0 && h < H) {
-        const float sc = scale[cg + c], sh = shift[cg + c];
-        const float4* src = reinterpret_cast<const float4*>(Y + (((long)n * C + cg + c) * H + h) * W);
-        for (int j = lane; j < W4; j += 32) {
-          const float4 v = src[j];
-          dst[4 * j + 0] = fmaxf(fmaf(v.x, sc, sh), 0.f);
-          dst[4 * j + 1] = fmaxf(fmaf(v.y, sc, sh), 0.f);
-          dst[4 * j + 2] = fmaxf(fmaf(v.z, sc, sh), 0.f);
-          dst[4 * j + 3] = fmaxf(fmaf(v.w, sc, sh), 0.f);
+    // four (channel, row) strips per warp in flight: the loads are issued before the first use
+    for (int cr0 = warp; cr0 < CG * 3; cr0 += 4 * nwarps) {
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cr = cr0 + u * nwarps;
+        const int c = cr / 3, r = cr - 3 * c;
+        const int h = 2 * ph - 1 + r;
+        ok[u] = cr < CG * 3 && h >= 0 && h < H && lane < W4;
+        if (ok[u])
+          v[u] = reinterpret_cast<const float4*>(Y + (((long)n * C + cg + c) * H + h) * W)[lane];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cr = cr0 + u * nwarps;
+        if (cr >= CG * 3) break;
+        const int c = cr / 3, r = cr - 3 * c;
+        const int h = 2 * ph - 1 + r;
+        float* dst = rows + cr * WP;
+        if (h >= 0 && h < H) {
+          if (ok[u]) {
+            const float sc = scale[cg + c], sh = shift[cg + c];
+            dst[4 * lane + 0] = fmaxf(fmaf(v[u].x, sc, sh), 0.f);
+            dst[4 * lane + 1] = fmaxf(fmaf(v[u].y, sc, sh), 0.f);
+            dst[4 * lane + 2] = fmaxf(fmaf(v[u].z, sc, sh), 0.f);
+            dst[4 * lane + 3] = fmaxf(fmaf(v[u].w, sc, sh), 0.f);
+          }
+          for (int j = lane + 32; j < W4; j += 32) {      // rows wider than 128 pixels
+            const float sc = scale[cg + c], sh = shift[cg + c];
+            const float4 t = reinterpret_cast<const float4*>(Y + (((long)n * C + cg + c) * H + h) * W)[j];
+            dst[4 * j + 0] = fmaxf(fmaf(t.x, sc, sh), 0.f);
+            dst[4 * j + 1] = fmaxf(fmaf(t.y, sc, sh), 0.f);
+            dst[4 * j + 2] = fmaxf(fmaf(t.z, sc, sh), 0.f);
+            dst[4 * j + 3] = fmaxf(fmaf(t.w, sc, sh), 0.f);
+          }
+        } else {
+          for (int j = lane; j < W; j += 32) dst[j] = -1.f;     // marks "outside the image"
         }
-      } else {
-        for (int j = lane; j < W; j += 32) dst[j] = -1.f;     // marks "outside the image"
       }
     }
     __syncthreads();
