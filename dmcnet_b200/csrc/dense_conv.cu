@@ -270,11 +270,14 @@ conv_wgrad_kernel(const float* __restrict__ in, long in_ns, int Cin, int H, int 
 //   * the 9*COG weights of the current input channel live in registers.
 // Tile = 32 x 32 output pixels; block = 8/R warps; input rows arrive by TMA (4-D tiled
 // map, zero fill = conv padding) into a two-stage ring of CK channels.
-template <int COG, int R, int CK, int NS>
+// T0 / TN restrict the kernel to the taps [T0, T0 + TN) of every kernel row and column: the
+// space-to-depth form of a stride-2 conv only has weights at taps {0,1} (forward) or {1,2}
+// (its flipped data gradient), so 4 instead of 9 taps are computed (dense_conv.cu, space-to-depth).
+template <int COG, int R, int CK, int NS, int T0 = 0, int TN = 3>
 struct FwdV3Cfg {
   static constexpr int TH = 32, PITCH = 40, ROWS = TH + 2;
   static constexpr int NT = 32 * (8 / R);
-  static constexpr int WPC = (9 * COG + 3) / 4 * 4;            // weight floats per input channel
+  static constexpr int WPC = (TN * TN * COG + 3) / 4 * 4;      // weight floats per input channel
   static constexpr int BUF = (CK * ROWS * PITCH + 31) / 32 * 32;   // floats per stage (128-byte multiple)
   static int smem_bytes(int Cin) { return 128 + NS * BUF * 4 + Cin * WPC * 4 + 8 * NS + 64; }
 };
@@ -282,7 +285,7 @@ struct FwdV3Cfg {
 // grid.x CTAs walk the (frame, tile) list with a fixed stride (one tile each when grid.x ==
 // number of tiles) while the NS-stage TMA ring keeps running across tile boundaries; the
 // weights of this CTA's output-channel group (grid.y) are staged once.
-template <int COG, int R, int CK, int NS>
+template <int COG, int R, int CK, int NS, int T0, int TN>
 __global__ void __launch_bounds__(32 * (8 / R))
 conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int ckb, int H, int W,
                       const float* __restrict__ w, const float* __restrict__ bias, int Cout,
@@ -290,8 +293,9 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
                       const float* __restrict__ mask, const float* __restrict__ add, long add_ns,
                       int accumulate, int tiles_x, int tiles_img, int total_tiles,
                       const float* __restrict__ act_src, long act_ns, int act_c1, float act_slope) {
-  using C = FwdV3Cfg<COG, R, CK, NS>;
+  using C = FwdV3Cfg<COG, R, CK, NS, T0, TN>;
   constexpr int PITCH = C::PITCH, ROWS = C::ROWS, WPC = C::WPC, NT = C::NT;
+  static_assert(T0 >= 0 && TN >= 1 && T0 + TN <= 3, "tap range");
   static_assert(COG % 2 == 0 && (R == 2 || R == 4), "COG even, R in {2,4}");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -334,7 +338,7 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
     locate();
     for (int i = 0; i < NS - 1 && p_left > 0; ++i) issue();
   }
-  // weights of this output group: thread = one (channel, output) filter, 9 taps
+  // weights of this output group: thread = one (channel, output) filter; taps [T0, T0+TN)^2
   for (int i = tid; i < Cin * COG; i += NT) {
     const int c = i / COG, g = i - c * COG;
     float v[9];
@@ -346,11 +350,14 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
       for (int t = 0; t < 9; ++t) v[t] = wp[t];
     }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) w_s[c * WPC + t * COG + g] = v[t];
+    for (int tr = 0; tr < TN; ++tr)
+#pragma unroll
+      for (int ts = 0; ts < TN; ++ts)
+        w_s[c * WPC + (tr * TN + ts) * COG + g] = v[(tr + T0) * 3 + ts + T0];
   }
-  if (WPC > 9 * COG)
+  if (WPC > TN * TN * COG)
     for (int c = tid; c < Cin; c += NT)
-      for (int j = 9 * COG; j < WPC; ++j) w_s[c * WPC + j] = 0.f;
+      for (int j = TN * TN * COG; j < WPC; ++j) w_s[c * WPC + j] = 0.f;
   float2 acc[R][4][COG / 2];
 #pragma unroll
   for (int y = 0; y < R; ++y)
@@ -387,7 +394,7 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
       }
       const float* cp = in_s + c * (ROWS * PITCH);
 #pragma unroll
-      for (int rr = 0; rr < R + 2; ++rr) {             // input row y0 - 1 + rr of the image tile
+      for (int rr = T0; rr < T0 + R + TN - 1; ++rr) {  // input row y0 - 1 + rr of the image tile
         const float* row = cp + rr * PITCH;
         const float4 f = *reinterpret_cast<const float4*>(row);
         float e = 0.f;
@@ -398,14 +405,15 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
         if (sx == 7) right = e;
         const float v[6] = {left, f.x, f.y, f.z, f.w, right};
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int r = T0; r < T0 + TN; ++r) {
           const int y = rr - r;                        // output row fed through kernel row r
           if (y < 0 || y >= R) continue;
 #pragma unroll
-          for (int s3 = 0; s3 < 3; ++s3)
+          for (int s3 = T0; s3 < T0 + TN; ++s3)
 #pragma unroll
             for (int g = 0; g < COG / 2; ++g) {
-              const float2 wv = make_float2(wr[(r * 3 + s3) * COG + 2 * g], wr[(r * 3 + s3) * COG + 2 * g + 1]);
+              const int wi = ((r - T0) * TN + (s3 - T0)) * COG + 2 * g;
+              const float2 wv = make_float2(wr[wi], wr[wi + 1]);
 #pragma unroll
               for (int p = 0; p < 4; ++p)              // FFMA2 with a scalar-broadcast operand
                 acc[y][p][g] = __ffma2_rn(make_float2(v[p + s3], v[p + s3]), wv, acc[y][p][g]);
@@ -473,13 +481,13 @@ conv3x3_fwd_v3_kernel(const __grid_constant__ CUtensorMap in_map, int Cin, int c
   }
 }
 
-template <int COG, int R, int CK, int NS>
+template <int COG, int R, int CK, int NS, int T0 = 0, int TN = 3>
 static int launch_fwd_v3(const float* in, long in_ns, int Cin, int H, int W, const float* w,
                          const float* bias, int Cout, float* out, long out_ns, float slope,
                          const float* mask, const float* add, long add_ns, int accumulate, int N,
                          cudaStream_t st, const float* act_src = nullptr, long act_ns = 0,
                          int act_c1 = 0, float act_slope = 1.f) {
-  using C = FwdV3Cfg<COG, R, CK, NS>;
+  using C = FwdV3Cfg<COG, R, CK, NS, T0, TN>;
   const int ckb = Cin < CK ? Cin : CK;
   CUtensorMap map;
   const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H,
@@ -490,7 +498,7 @@ static int launch_fwd_v3(const float* in, long in_ns, int Cin, int H, int W, con
   int rc = dmc_make_f32_map(&map, in, 4, dims, strides, box);
   if (rc) return rc;
   const int smem = C::smem_bytes(Cin);
-  auto kern = conv3x3_fwd_v3_kernel<COG, R, CK, NS>;
+  auto kern = conv3x3_fwd_v3_kernel<COG, R, CK, NS, T0, TN>;
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
     const int want = smem > 64 * 1024 ? smem : 64 * 1024;
@@ -858,6 +866,79 @@ static int ew_grid(long total) {
   if (b > 148L * 16) b = 148L * 16;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+// ------------------------------------------------------------------ 3x3 stride-2 via space-to-depth
+// A 3x3 stride-2 pad-1 convolution equals a 3x3 stride-1 pad-1 convolution of the space-to-depth
+// input S[(pr,pc,ci)][i][j] = in[ci][2i+pr][2j+pc] with the weight
+//   W3[co][(pr,pc,ci)][a][b] = w[co][ci][r(pr,a)][s(pc,b)],   r(1,0)=0, r(0,1)=1, r(1,1)=2, else 0
+// (kernel row r reads input row 2y+r-1 = phase pr at i = y + a - 1).  The backward pass of the
+// stride-2 discriminator layers runs on S through the fast stride-1 kernels: the weight
+// gradient of W3 is gathered back into OIHW, the data gradient of S is re-interleaved.
+__device__ __forceinline__ int s2_tap(int p, int a) {      // kernel index for (phase, window position)
+  return p == 0 ? (a == 1 ? 1 : -1) : (a == 0 ? 0 : (a == 1 ? 2 : -1));
+}
+
+// S[n][p*C + c][H/2][W/2] <- in[n][c][H][W];  W % 8 == 0
+__global__ void s2d_planar_kernel(const float* __restrict__ in, long in_ns, int C, int H, int W,
+                                  float* __restrict__ out, long out_ns, long total8) {
+  const int W8 = W / 8, Ho = H / 2, Wo = W / 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % W8);
+    long r = i / W8;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const long n = r / C;
+    const float4* src = reinterpret_cast<const float4*>(in + n * in_ns + ((long)c * H + h) * W + 8 * j);
+    const float4 a = src[0], b = src[1];
+    const int pr = h & 1;
+    float* o0 = out + n * out_ns + (((long)(pr * 2 + 0) * C + c) * Ho + (h >> 1)) * Wo + 4 * j;
+    float* o1 = out + n * out_ns + (((long)(pr * 2 + 1) * C + c) * Ho + (h >> 1)) * Wo + 4 * j;
+    *reinterpret_cast<float4*>(o0) = make_float4(a.x, a.z, b.x, b.z);
+    *reinterpret_cast<float4*>(o1) = make_float4(a.y, a.w, b.y, b.w);
+  }
+}
+
+// out[n][c][H][W] (+)= S[n][p*C + c][H/2][W/2]
+__global__ void d2s_planar_kernel(const float* __restrict__ S, long s_ns, int C, int H, int W,
+                                  float* __restrict__ out, long out_ns, long total8, int accumulate) {
+  const int W8 = W / 8, Ho = H / 2, Wo = W / 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % W8);
+    long r = i / W8;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const long n = r / C;
+    const int pr = h & 1;
+    const float4 e = *reinterpret_cast<const float4*>(
+        S + n * s_ns + (((long)(pr * 2 + 0) * C + c) * Ho + (h >> 1)) * Wo + 4 * j);
+    const float4 o = *reinterpret_cast<const float4*>(
+        S + n * s_ns + (((long)(pr * 2 + 1) * C + c) * Ho + (h >> 1)) * Wo + 4 * j);
+    float4* dst = reinterpret_cast<float4*>(out + n * out_ns + ((long)c * H + h) * W + 8 * j);
+    float4 a = make_float4(e.x, o.x, e.y, o.y), b = make_float4(e.z, o.z, e.w, o.w);
+    if (accumulate) {
+      const float4 pa = dst[0], pb = dst[1];
+      a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+      b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+    }
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// mode 0: W3[co][p*Cin + ci][a][b] = w[co][ci][r][s] (zero where no tap);  mode 1: dW[co][ci][r][s] += dW3[...]
+__global__ void s2_weight_map_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout,
+                                     int Cin, int mode) {
+  const int n = Cout * 4 * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = i % 9, pc_ci = (i / 9) % (4 * Cin), co = i / (9 * 4 * Cin);
+    const int p = pc_ci / Cin, ci = pc_ci % Cin;
+    const int r = s2_tap(p >> 1, t / 3), s3 = s2_tap(p & 1, t % 3);
+    const bool ok = r >= 0 && s3 >= 0;
+    const long o = ((long)co * Cin + ci) * 9 + r * 3 + s3;
+    if (mode == 0) dst[i] = ok ? src[o] : 0.f;
+    else if (ok) dst[o] += src[i];                // every OIHW element has exactly one source
+  }
 }
 
 // Stride-2 variant: moving one output pixel to the right shifts the input window by exactly
@@ -1246,3 +1327,55 @@ extern "C" int dmc_dense_dgrad_weights(const float* params, const int* table, fl
   dense_dgrad_weights_kernel<<<tab.nslices, 256, 0, ST_(stream)>>>(params, tab, out);
   return dmc_check_launch("dense_dgrad_weights_kernel");
 }
+
+// Space-to-depth of a planar tensor: S[n][(pr*2+pc)*C + c][H/2][W/2] = in[n][c][2i+pr][2j+pc]; W % 8 == 0.
+extern "C" int dmc_s2d_planar(const float* in, long in_ns, int C, int H, int W, float* S, long s_ns,
+                              int N, void* stream) {
+  DMC_REQUIRE(W % 8 == 0 && H % 2 == 0 && in_ns % 4 == 0 && s_ns % 4 == 0, "s2d_planar: H=%d W=%d", H, W);
+  const long total8 = (long)N * C * H * (W / 8);
+  s2d_planar_kernel<<<ew_grid(total8), 256, 0, ST_(stream)>>>(in, in_ns, C, H, W, S, s_ns, total8);
+  return dmc_check_launch("s2d_planar_kernel");
+}
+
+// Inverse of dmc_s2d_planar: out[n][c][H][W] (+)= S[n][(pr*2+pc)*C + c][H/2][W/2].
+extern "C" int dmc_d2s_planar(const float* S, long s_ns, int C, int H, int W, float* out, long out_ns,
+                              int accumulate, int N, void* stream) {
+  DMC_REQUIRE(W % 8 == 0 && H % 2 == 0 && out_ns % 4 == 0 && s_ns % 4 == 0, "d2s_planar: H=%d W=%d", H, W);
+  const long total8 = (long)N * C * H * (W / 8);
+  d2s_planar_kernel<<<ew_grid(total8), 256, 0, ST_(stream)>>>(S, s_ns, C, H, W, out, out_ns, total8,
+                                                               accumulate);
+  return dmc_check_launch("d2s_planar_kernel");
+}
+
+// Weight of the stride-1 convolution on the space-to-depth input that equals a 3x3 stride-2 conv:
+// W3[Cout][4*Cin][3][3] from w[Cout][Cin][3][3] (to_s2d = 1), or the gather of its gradient back:
+// w_or_dw[Cout][Cin][3][3] += W3 (to_s2d = 0).
+extern "C" int dmc_s2_weight_map(const float* src, float* dst, int Cout, int Cin, int to_s2d,
+                                 void* stream) {
+  const int n = Cout * 4 * Cin * 9;
+  s2_weight_map_kernel<<<(int)cdiv(n, 256), 256, 0, ST_(stream)>>>(src, dst, Cout, Cin, to_s2d ? 0 : 1);
+  return dmc_check_launch("s2_weight_map_kernel");
+}
+
+// 3x3 stride-1 pad-1 convolution restricted to the taps [t0, t0 + 2) of every kernel row and
+// column of w (OIHW 3x3; the other taps are taken as zero): t0 = 0 is the forward and t0 = 1 the
+// flipped data gradient of a stride-2 conv in space-to-depth form.  Same epilogue as dmc_conv_fwd.
+extern "C" int dmc_conv3x3_taps2(const float* in, long in_ns, int Cin, int H, int W, const float* w,
+                                 const float* bias, int Cout, int t0, float* out, long out_ns,
+                                 float slope, const float* mask, int N, void* stream) {
+  DMC_REQUIRE(t0 == 0 || t0 == 1, "conv3x3_taps2: t0=%d", t0);
+  DMC_REQUIRE(W % 4 == 0 && in_ns % 4 == 0 && out_ns % 4 == 0 && (H * W) % 4 == 0,
+              "conv3x3_taps2: W=%d and strides must be multiples of 4", W);
+  cudaStream_t st = ST_(stream);
+#define DMC_T2(COG, R, T0)                                                                          \
+  return launch_fwd_v3<COG, R, 2, 2, T0, 2>(in, in_ns, Cin, H, W, w, bias, Cout, out, out_ns, slope, \
+                                            mask, nullptr, 0, 0, N, st)
+  if (t0 == 0) {
+    if (Cout == 2) DMC_T2(2, 4, 0);
+    DMC_T2(4, 4, 0);
+  }
+  if (Cout == 2) DMC_T2(2, 4, 1);
+  DMC_T2(4, 4, 1);
+#undef DMC_T2
+}
+

@@ -398,6 +398,18 @@ class DmcEngine:
         big = max(L['A'].numel() for L in self.d_layers)
         self.d_in = torch.zeros(M, 2, H, W, **f32)
         self.d_g = [torch.zeros(max(big, self.d_in.numel()), **f32) for _ in range(2)]
+        # stride-2 layers whose output width is a multiple of 4 run their backward on the
+        # space-to-depth input through the stride-1 kernels (csrc/dense_conv.cu, "via space-to-depth")
+        s2 = [L for L in self.d_layers if L['stride'] == 2 and L['Wo'] % 4 == 0 and L['H'] % 2 == 0]
+        for L in s2:
+            L['s2d'] = True
+        if s2:
+            n_in = max(M * L['cin'] * L['H'] * L['W'] for L in s2)
+            n_w = max(L['cout'] * 4 * L['cin'] * 9 for L in s2)
+            self.d_s2d = torch.zeros(n_in, **f32)          # S = space-to-depth(layer input)
+            self.d_ds = torch.zeros(n_in, **f32)           # dS
+            self.d_w3 = torch.zeros(n_w, **f32)            # W3 / flipped W3 / dW3
+            self.d_w3t = torch.zeros(n_w, **f32)
         self.validity = torch.zeros(M, 2, **f32)
         self.d_validity = torch.zeros(M, 2, **f32)
         self.d_feat = torch.zeros(M, self.specs['discriminator.adv_layer.weight'][1], **f32)
@@ -722,10 +734,20 @@ class DmcEngine:
         inp, in_c, h, w = x, 2, self.H, self.W
         for L in self.d_layers:
             p = L['name']
-            ops.conv_fwd(inp.view(-1), in_c * h * w, in_c, h, w, self.p(p + '.0.weight'),
-                         self.p(p + '.0.bias'), L['cout'], 3, L['stride'], L['A'].view(-1),
-                         L['cout'] * L['Ho'] * L['Wo'], m, slope=0.2,
-                         mask=(L['mask'] if (train and use_masks) else None))
+            mk = L['mask'] if (train and use_masks) else None
+            if L.get('s2d', False):
+                # stride-2 layer as a 2x2-tap stride-1 conv on the space-to-depth input
+                s_ns, c4 = in_c * h * w, 4 * in_c
+                W3 = self.d_w3[:L['cout'] * c4 * 9]
+                ops.s2d_planar(inp.view(-1), s_ns, in_c, h, w, self.d_s2d, s_ns, m)
+                ops.s2_weight_map(self.p(p + '.0.weight'), W3, L['cout'], in_c, True)
+                ops.conv3x3_taps2(self.d_s2d, s_ns, c4, L['Ho'], L['Wo'], W3, self.p(p + '.0.bias'),
+                                  L['cout'], 0, L['A'].view(-1), L['cout'] * L['Ho'] * L['Wo'], m,
+                                  slope=0.2, mask=mk)
+            else:
+                ops.conv_fwd(inp.view(-1), in_c * h * w, in_c, h, w, self.p(p + '.0.weight'),
+                             self.p(p + '.0.bias'), L['cout'], 3, L['stride'], L['A'].view(-1),
+                             L['cout'] * L['Ho'] * L['Wo'], m, slope=0.2, mask=mk)
             hw = L['Ho'] * L['Wo']
             if L['bn']:
                 ns = L['cout'] * hw
@@ -778,10 +800,35 @@ class DmcEngine:
                 inp, ci, h, w = prev['Z'], prev['cout'], prev['Ho'], prev['Wo']
             else:
                 inp, ci, h, w = x, 2, self.H, self.W
+            s2d = L.get('s2d', False)
+            c4, s_ns = 4 * ci, ci * h * w                     # S: [m][4ci][Ho][Wo], same size as the input
             if need_wgrad:
-                ops.conv_wgrad(inp.view(-1), ci * h * w, ci, h, w, g, ns, co, 3, L['stride'],
-                               self.g(p + '.0.weight'), self.g(p + '.0.bias'), m)
-            if li > 0:
+                if s2d:
+                    S, dW3 = self.d_s2d, self.d_w3[:co * c4 * 9]
+                    ops.s2d_planar(inp.view(-1), s_ns, ci, h, w, S, s_ns, m)
+                    ops.memset_zero(dW3)
+                    ops.conv_wgrad(S, s_ns, c4, L['Ho'], L['Wo'], g, ns, co, 3, 1, dW3,
+                                   self.g(p + '.0.bias'), m)
+                    ops.s2_weight_map(dW3, self.g(p + '.0.weight'), co, ci, False)
+                else:
+                    ops.conv_wgrad(inp.view(-1), ci * h * w, ci, h, w, g, ns, co, 3, L['stride'],
+                                   self.g(p + '.0.weight'), self.g(p + '.0.bias'), m)
+            want_dx = li > 0 or d_input is not None
+            rows = m if li > 0 else d_input_rows
+            if want_dx and s2d:
+                # dS = conv3x3/1(dPre, flip(W3)); dX = depth-to-space(dS)
+                W3, W3t = self.d_w3[:co * c4 * 9], self.d_w3t[:co * c4 * 9]
+                ops.s2_weight_map(self.p(p + '.0.weight'), W3, co, ci, True)
+                ops.weight_flip(W3, co, c4, c4, W3t)
+                ops.conv3x3_taps2(g, ns, co, L['Ho'], L['Wo'], W3t, None, c4, 1, self.d_ds, s_ns, rows)
+                if li > 0:
+                    nxt = self.d_g[(li - 1) % 2]
+                    ops.d2s_planar(self.d_ds, s_ns, ci, h, w, nxt, ci * h * w, rows)
+                    g = nxt
+                else:
+                    ops.d2s_planar(self.d_ds, s_ns, ci, h, w, self.dD.view(-1), self.dD.shape[1] * h * w,
+                                   rows, accumulate=True)
+            elif li > 0:
                 nxt = self.d_g[(li - 1) % 2]
                 if L['stride'] == 1:
                     self._dgrad_s1(g, ns, co, p + '.0.weight', ci, ci, nxt, ci * h * w, h, w, m, False)

@@ -289,6 +289,28 @@ def stem_wgrad_workspace_floats():
     return int(fn())
 
 
+def conv3x3_taps2(x, in_ns, Cin, H, W, w, bias, Cout, t0, out, out_ns, N, slope=1.0, mask=None):
+    """3x3/1 conv using only the taps [t0, t0+2)^2 of w (space-to-depth form of a stride-2 conv)."""
+    _call('dmc_conv3x3_taps2', _ptr(x, F32), c_long(in_ns), c_int(Cin), c_int(H), c_int(W), _ptr(w, F32),
+          _ptr(bias, F32), c_int(Cout), c_int(t0), _ptr(out, F32), c_long(out_ns), c_float(slope),
+          _ptr(mask, F32), c_int(N), _stream())
+
+
+def s2d_planar(x, in_ns, C, H, W, S, s_ns, N):
+    _call('dmc_s2d_planar', _ptr(x, F32), c_long(in_ns), c_int(C), c_int(H), c_int(W), _ptr(S, F32),
+          c_long(s_ns), c_int(N), _stream())
+
+
+def d2s_planar(S, s_ns, C, H, W, out, out_ns, N, accumulate=False):
+    _call('dmc_d2s_planar', _ptr(S, F32), c_long(s_ns), c_int(C), c_int(H), c_int(W), _ptr(out, F32),
+          c_long(out_ns), c_int(1 if accumulate else 0), c_int(N), _stream())
+
+
+def s2_weight_map(src, dst, Cout, Cin, to_s2d):
+    _call('dmc_s2_weight_map', _ptr(src, F32), _ptr(dst, F32), c_int(Cout), c_int(Cin),
+          c_int(1 if to_s2d else 0), _stream())
+
+
 def stem_pool_fwd(Y, scale, shift, N, C, H, W, out_hi, out_lo, idx):
     _call('dmc_stem_pool_fwd', _ptr(Y, F32), _ptr(scale, F32), _ptr(shift, F32), c_int(N), c_int(C),
           c_int(H), c_int(W), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8), _stream())

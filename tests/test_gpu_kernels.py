@@ -90,6 +90,50 @@ def test_conv_fwd_channel_subrange_add_and_accumulate():
     assert rel(d, ref) < 2e-5
 
 
+def test_stride2_backward_through_space_to_depth():
+    """s2d / d2s / weight maps (the discriminator's stride-2 backward path) vs torch autograd of the
+    stride-2 conv itself."""
+    g = torch.Generator().manual_seed(7)
+    N, ci, co, H, W = 3, 4, 8, 32, 48
+    x = torch.randn(N, ci, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(co, ci, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    y = F.conv2d(x, w, None, 2, 1)
+    dy = torch.randn(y.shape, generator=g)
+    gx, gw = torch.autograd.grad(y, (x, w), dy)
+    Ho, Wo, c4 = H // 2, W // 2, 4 * ci
+    xd, wd, dyd = x.detach().cuda(), w.detach().cuda(), dy.cuda()
+    S = torch.full((N, c4, Ho, Wo), float('nan'), device='cuda')
+    ops.s2d_planar(xd, ci * H * W, ci, H, W, S, ci * H * W, N)
+    ref_S = torch.cat([x.detach()[:, :, pr::2, pc::2] for pr in (0, 1) for pc in (0, 1)], 1)
+    assert torch.equal(S.cpu(), ref_S)
+    # weight gradient: stride-1 wgrad on S, gathered back into OIHW (accumulating)
+    dW3 = torch.zeros(co, c4, 3, 3, device='cuda')
+    ops.conv_wgrad(S, ci * H * W, c4, Ho, Wo, dyd, co * Ho * Wo, co, 3, 1, dW3, None, N)
+    dW = torch.ones(co, ci, 3, 3, device='cuda')
+    ops.s2_weight_map(dW3, dW, co, ci, False)
+    assert rel(dW - 1.0, gw) < 2e-5
+    # data gradient: conv of dY with the flipped space-to-depth weight, then depth-to-space
+    W3 = torch.full((co, c4, 3, 3), float('nan'), device='cuda')
+    ops.s2_weight_map(wd, W3, co, ci, True)
+    W3t = torch.zeros(c4 * co * 9, device='cuda')
+    ops.weight_flip(W3, co, c4, c4, W3t)
+    # forward through the 2x2-tap kernel (taps {0,1}), with bias / LeakyReLU / channel mask epilogue
+    b = torch.randn(co, generator=g)
+    mask = torch.empty(N, co).bernoulli_(0.75, generator=g) / 0.75
+    ref_y = F.leaky_relu(y.detach() + b.view(1, co, 1, 1), 0.2) * mask.view(N, co, 1, 1)
+    Yo = torch.full((N, co, Ho, Wo), float('nan'), device='cuda')
+    ops.conv3x3_taps2(S, ci * H * W, c4, Ho, Wo, W3, b.cuda(), co, 0, Yo, co * Ho * Wo, N, slope=0.2,
+                      mask=mask.cuda())
+    assert rel(Yo, ref_y) < 2e-5
+    dS = torch.full((N, c4, Ho, Wo), float('nan'), device='cuda')
+    ops.conv3x3_taps2(dyd, co * Ho * Wo, co, Ho, Wo, W3t, None, c4, 1, dS, ci * H * W, N)
+    dX = torch.ones(N, ci, H, W, device='cuda')
+    ops.d2s_planar(dS, ci * H * W, ci, H, W, dX, ci * H * W, N, accumulate=True)
+    assert rel(dX - 1.0, gx) < 2e-5
+    ops.d2s_planar(dS, ci * H * W, ci, H, W, dX, ci * H * W, N)
+    assert rel(dX, gx) < 2e-5
+
+
 # ------------------------------------------------------------------ tensor-core tap GEMMs
 @pytest.mark.parametrize('engine', ['tc', 'simt'])
 @pytest.mark.parametrize('n,cin,cout,h,stride', [(3, 64, 64, 12, 1), (2, 128, 256, 8, 1), (2, 64, 128, 16, 2),

@@ -136,3 +136,57 @@ def test_generator_channel_layout():
 def test_disc_block_tables_match_oracle():
     for a in ('Discriminator', 'Discriminator2', 'Discriminator3', 'Discriminator4', 'Discriminator5'):
         assert E.disc_blocks(a) == O.disc_blocks(a)
+
+
+def _s2_tap(p, a):                 # mirrors s2_tap() in csrc/dense_conv.cu
+    return (1 if a == 1 else -1) if p == 0 else (0 if a == 0 else (2 if a == 1 else -1))
+
+
+def _s2d(x):                       # [N,C,H,W] -> [N,4C,H/2,W/2], channel = (pr*2+pc)*C + c
+    return torch.cat([x[:, :, pr::2, pc::2] for pr in (0, 1) for pc in (0, 1)], 1)
+
+
+def _s2_weight(w):                 # [Co,Ci,3,3] -> [Co,4Ci,3,3]
+    co, ci = w.shape[:2]
+    w3 = torch.zeros(co, 4 * ci, 3, 3, dtype=w.dtype)
+    for p in range(4):
+        for a in range(3):
+            for b in range(3):
+                r, s_ = _s2_tap(p >> 1, a), _s2_tap(p & 1, b)
+                if r >= 0 and s_ >= 0:
+                    w3[:, p * ci:(p + 1) * ci, a, b] = w[:, :, r, s_]
+    return w3
+
+
+def test_stride2_conv_equals_stride1_conv_on_space_to_depth():
+    """The identity behind the discriminator's stride-2 backward (engine._disc_backward):
+    conv3x3/2(x, w) == conv3x3/1(s2d(x), W3), and the gradients map back by gather / depth-to-space."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 8, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(5, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, None, 2, 1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    gx, gw = torch.autograd.grad(y, (x, w), dy)
+    S = _s2d(x.detach()).requires_grad_(True)
+    W3 = _s2_weight(w.detach()).requires_grad_(True)
+    y3 = F.conv2d(S, W3, None, 1, 1)
+    assert torch.allclose(y3, y.detach(), atol=1e-12)
+    gS, gW3 = torch.autograd.grad(y3, (S, W3), dy)
+    # weight gradient: every OIHW element has exactly one source in W3
+    gw_back = torch.zeros_like(gw)
+    hits = torch.zeros(3, 3)
+    for p in range(4):
+        for a in range(3):
+            for b in range(3):
+                r, s_ = _s2_tap(p >> 1, a), _s2_tap(p & 1, b)
+                if r >= 0 and s_ >= 0:
+                    gw_back[:, :, r, s_] += gW3[:, p * 3:(p + 1) * 3, a, b]
+                    hits[r, s_] += 1
+    assert torch.equal(hits, torch.ones(3, 3))
+    assert torch.allclose(gw_back, gw, atol=1e-12)
+    # data gradient: depth-to-space of dS
+    gx_back = torch.zeros_like(gx)
+    for p in range(4):
+        gx_back[:, :, p >> 1::2, p & 1::2] = gS[:, p * 3:(p + 1) * 3]
+    assert torch.allclose(gx_back, gx, atol=1e-12)
+
