@@ -190,3 +190,30 @@ def test_stride2_conv_equals_stride1_conv_on_space_to_depth():
         gx_back[:, :, p >> 1::2, p & 1::2] = gS[:, p * 3:(p + 1) * 3]
     assert torch.allclose(gx_back, gx, atol=1e-12)
 
+
+def test_stem_im2col_operand_layout():
+    """Operand layout of the tensor-core stem conv (csrc/stem_tc.cu): K = 128 = 8 kernel rows x
+    2 channels x 8 columns, k = r*16 + ci*8 + s; the 16-byte chunk (r, ci) of output pixel (y, x)
+    is the 8 consecutive input pixels of row 2y+r-3 starting at column 2x-3; the weight operand is
+    zero at r = 7 and s = 7.  A @ Wb^T must equal the 7x7 stride-2 pad-3 convolution."""
+    rng = np.random.default_rng(3)
+    n, H, W = 1, 12, 16
+    x = rng.standard_normal((n, 2, H, W))
+    w = rng.standard_normal((64, 2, 7, 7))
+    Ho, Wo = H // 2, W // 2
+    xp = np.zeros((n, 2, H + 8, W + 8))                 # staging: image column c lives at c + 3
+    xp[:, :, 3:3 + H, 3:3 + W] = x
+    A = np.zeros((n, Ho, Wo, 128))
+    for y in range(Ho):
+        for xo in range(Wo):
+            for r in range(7):
+                for ci in range(2):
+                    A[0, y, xo, r * 16 + ci * 8:r * 16 + ci * 8 + 8] = xp[0, ci, 2 * y + r, 2 * xo:2 * xo + 8]
+    Wb = np.zeros((64, 128))
+    for r in range(7):
+        for ci in range(2):
+            Wb[:, r * 16 + ci * 8:r * 16 + ci * 8 + 7] = w[:, ci, r, :]
+    y_gemm = (A.reshape(-1, 128) @ Wb.T).reshape(n, Ho, Wo, 64).transpose(0, 3, 1, 2)
+    ref = F.conv2d(torch.tensor(x), torch.tensor(w), None, 2, 3).numpy()
+    np.testing.assert_allclose(y_gemm, ref, atol=1e-10)
+
