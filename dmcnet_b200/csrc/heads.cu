@@ -147,6 +147,57 @@ mse_head_kernel(const float* __restrict__ gen, const float* __restrict__ flow, l
   }
 }
 
+// Flow-reconstruction criterion chosen by --loss-mse (code/dmcnet/train.py:166-172):
+// KIND 0 MSELoss, 1 SmoothL1Loss (beta = 1), 2 L1Loss, all with mean reduction.
+//   value  f(d): d^2 | (|d| < 1 ? d^2/2 : |d| - 1/2) | |d|
+//   slope f'(d): 2d  | clamp(d, -1, 1)               | sign(d)  (0 at d = 0, as ATen)
+// loss_sum += sum f(gen-flow) (double);  dgen = gscale * f'(gen-flow), gscale = lr_mse / numel_global.
+template <int KIND>
+__device__ __forceinline__ void flow_loss_term(float d, float& val, float& slope) {
+  if (KIND == 0) {
+    val = d * d;
+    slope = 2.f * d;
+  } else if (KIND == 1) {
+    const float a = fabsf(d);
+    val = a < 1.f ? 0.5f * d * d : a - 0.5f;
+    slope = fminf(fmaxf(d, -1.f), 1.f);
+  } else {
+    val = fabsf(d);
+    slope = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+flow_loss_head_kernel(const float* __restrict__ gen, const float* __restrict__ flow, long n4,
+                      float gscale, float* __restrict__ dgen, long frame4, long dgen_ns4,
+                      double* __restrict__ loss_sum) {
+  float s = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(gen)[i];
+    const float4 b = reinterpret_cast<const float4*>(flow)[i];
+    float4 v, g;
+    flow_loss_term<KIND>(a.x - b.x, v.x, g.x);
+    flow_loss_term<KIND>(a.y - b.y, v.y, g.y);
+    flow_loss_term<KIND>(a.z - b.z, v.z, g.z);
+    flow_loss_term<KIND>(a.w - b.w, v.w, g.w);
+    s += (v.x + v.y) + (v.z + v.w);
+    if (dgen) {      // dgen may be a channel slice of a wider buffer: per-frame stride dgen_ns4
+      const long o = frame4 == dgen_ns4 ? i : (i / frame4) * dgen_ns4 + (i % frame4);
+      reinterpret_cast<float4*>(dgen)[o] =
+          make_float4(gscale * g.x, gscale * g.y, gscale * g.z, gscale * g.w);
+    }
+  }
+  __shared__ double red[8];
+  double sd = warp_sum_d((double)s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) sd += red[i];
+    atomicAdd(loss_sum, sd);
+  }
+}
+
 }  // namespace dmc
 
 using namespace dmc;
@@ -199,4 +250,29 @@ extern "C" int dmc_mse_head(const float* gen, const float* flow, long numel, flo
   mse_head_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, numel / 4, gscale, dgen,
                                                         frame_elems / 4, dgen_ns / 4, loss_sum);
   return dmc_check_launch("mse_head_kernel");
+}
+
+// Flow-reconstruction loss of --loss-mse (code/dmcnet/train.py:166-172, :245): kind 0 = MSELoss,
+// 1 = SmoothL1Loss, 2 = L1Loss.  loss_sum (double, overwritten) = sum of the per-element loss;
+// dgen[n][0:frame_elems] (per-frame stride dgen_ns elements; may be NULL) = gscale * dloss/dgen with
+// gscale = weight / (global element count), i.e. the mean reduction is the caller's normaliser.
+extern "C" int dmc_flow_loss_head(int kind, const float* gen, const float* flow, long numel,
+                                  float gscale, float* dgen, long frame_elems, long dgen_ns,
+                                  double* loss_sum, void* stream) {
+  DMC_REQUIRE(kind >= 0 && kind <= 2, "flow_loss_head: kind must be 0 (MSE), 1 (SmoothL1) or 2 (L1)");
+  DMC_REQUIRE(numel % 4 == 0 && frame_elems % 4 == 0 && dgen_ns % 4 == 0 && frame_elems > 0,
+              "flow_loss_head: sizes must be multiples of 4");
+  if (cudaMemsetAsync(loss_sum, 0, sizeof(double), ST_(stream)) != cudaSuccess)
+    return dmc_check_launch("flow_loss_head memset");
+  long blocks = cdiv(numel / 4, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  const long n4 = numel / 4, f4 = frame_elems / 4, d4 = dgen_ns / 4;
+  if (kind == 0)
+    flow_loss_head_kernel<0><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, n4, gscale, dgen, f4, d4, loss_sum);
+  else if (kind == 1)
+    flow_loss_head_kernel<1><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, n4, gscale, dgen, f4, d4, loss_sum);
+  else
+    flow_loss_head_kernel<2><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, n4, gscale, dgen, f4, d4, loss_sum);
+  return dmc_check_launch("flow_loss_head_kernel");
 }

@@ -344,6 +344,14 @@ def mse_head(gen, flow, numel, gscale, dgen, loss_sum, frame_elems=None, dgen_ns
           _ptr(loss_sum, F64), _stream())
 
 
+def flow_loss_head(kind, gen, flow, numel, gscale, dgen, loss_sum, frame_elems=None, dgen_ns=None):
+    """kind 0 MSELoss / 1 SmoothL1Loss / 2 L1Loss (code/dmcnet/train.py:166-172)."""
+    fe = frame_elems if frame_elems is not None else numel
+    _call('dmc_flow_loss_head', c_int(kind), _ptr(gen, F32), _ptr(flow, F32), c_long(numel),
+          c_float(gscale), _ptr(dgen, F32), c_long(fe), c_long(dgen_ns if dgen_ns is not None else fe),
+          _ptr(loss_sum, F64), _stream())
+
+
 def dense_dgrad_weights(params, table, out):
     _call('dmc_dense_dgrad_weights', _ptr(params, F32), _iarr(table), _ptr(out, F32), _stream())
 

@@ -41,9 +41,21 @@ class HParams:
     num_segments: int = 3
     eps: float = 1e-3            # Adam eps, code/dmcnet/train.py:137,142
     betas: Tuple[float, float] = (0.9, 0.999)
+    loss_mse: str = 'MSELoss'    # --loss-mse (train_options.py:71): MSELoss | SmoothL1Loss | L1
 
 
 GROUPS = ('base_model', 'gen_flow_model', 'discriminator')
+FLOW_LOSS_KINDS = {'MSELoss': 0, 'SmoothL1Loss': 1, 'L1': 2}
+
+
+def flow_loss_kind(name: str) -> int:
+    """criterion_mse selection of code/dmcnet/train.py:166-172.  The reference leaves the
+    criterion undefined for any other string (NameError at the first iteration); here the
+    same mistake is reported when the step is built."""
+    if name not in FLOW_LOSS_KINDS:
+        raise NameError("name 'criterion_mse' is not defined (--loss-mse %r; expected one of %s)"
+                        % (name, ', '.join(FLOW_LOSS_KINDS)))
+    return FLOW_LOSS_KINDS[name]
 
 
 def shard_range(rank: int, world: int, global_batch: int) -> Tuple[int, int]:
@@ -57,9 +69,12 @@ def shard_range(rank: int, world: int, global_batch: int) -> Tuple[int, int]:
 
 def loss_grad_scales(hp: 'HParams', batch: int, world: int, frames: int, height: int, width: int):
     """Per-rank gradient pre-scales that make a SUM all-reduce reproduce the
-    reference's global-mean losses: CE / B_global, 2*MSE / numel_global."""
-    return {'cls': hp.lr_cls / (batch * world),
-            'mse': 2.0 * hp.lr_mse / float(frames * 2 * height * width * world)}
+    reference's global-mean losses: CE / B_global, 2*MSE / numel_global ('flow' is the same
+    normaliser without the factor 2 of d(d^2): the kernel of dmc_flow_loss_head applies the
+    criterion's own slope)."""
+    numel = float(frames * 2 * height * width * world)
+    return {'cls': hp.lr_cls / (batch * world), 'mse': 2.0 * hp.lr_mse / numel,
+            'flow': hp.lr_mse / numel}
 
 
 def allreduce_groups(flat: torch.Tensor, group_range: Dict[str, Tuple[int, int]],
@@ -101,6 +116,7 @@ class FusedTrainStep:
             self.adv_t_d = torch.cat((torch.zeros(n, dtype=torch.int64), torch.ones(n, dtype=torch.int64))).to(dev)
             self.adv_t_g = torch.ones(n, dtype=torch.int64, device=dev)
         self.iteration = 0
+        self.flow_kind = flow_loss_kind(hp.loss_mse)
         self._build_adam_tables()
         self.set_epoch(0, epoch_thre=0)
         self._graphs: Dict[str, object] = {}
@@ -180,14 +196,13 @@ class FusedTrainStep:
         eng, hp, B, S = self.eng, self.hp, self.B, self.S
         n = B * S
         sc = loss_grad_scales(hp, B, self.world, n, eng.H, eng.W)
-        g_cls, g_mse = sc['cls'], sc['mse']
+        g_cls = sc['cls']
         eng.zero_grads()
         if not eng.gan:
             eng.forward(self.in_mv, self.in_res, train=True)
             ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
                         eng.d_logits, self.ce_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse, eng.dD, self.mse_sum,
-                         frame_elems=2 * eng.H * eng.W, dgen_ns=eng.dD.shape[1] * eng.H * eng.W)
+            self._flow_head(sc)
             eng.backward(n, cls=(mode == 'full'), cls_wgrad=True, gen_grad=True, cls_to_gen=False)
         elif mode == 'D':
             eng.forward(self.in_mv, self.in_res, self.in_flow, train=True, masks='preloaded')
@@ -204,11 +219,23 @@ class FusedTrainStep:
                         eng.d_logits, self.ce_stats)
             ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, hp.lr_adv_g / (n * self.world), None,
                         eng.d_validity, self.adv_stats)
-            ops.mse_head(eng.gen_flow, self.in_flow, n * 2 * eng.H * eng.W, g_mse, eng.dD, self.mse_sum,
-                         frame_elems=2 * eng.H * eng.W, dgen_ns=eng.dD.shape[1] * eng.H * eng.W)
+            self._flow_head(sc)
             # classifier / discriminator weight gradients are dead work in the G-step (:367-371)
             eng.backward(n, cls=True, cls_wgrad=False, gen_grad=True, cls_to_gen=True, disc=True,
                          disc_wgrad=False, disc_to_gen=True)
+
+    def _flow_head(self, sc):
+        """criterion_mse(gen_flow, input_flow) and its gradient into the generator's
+        gradient buffer (code/dmcnet/train.py:245; GAN/train.py:350)."""
+        eng = self.eng
+        numel, frame = eng.N * 2 * eng.H * eng.W, 2 * eng.H * eng.W
+        dgen_ns = eng.dD.shape[1] * eng.H * eng.W
+        if self.flow_kind == 0:
+            ops.mse_head(eng.gen_flow, self.in_flow, numel, sc['mse'], eng.dD, self.mse_sum,
+                         frame_elems=frame, dgen_ns=dgen_ns)
+        else:
+            ops.flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, numel, sc['flow'], eng.dD,
+                               self.mse_sum, frame_elems=frame, dgen_ns=dgen_ns)
 
     def _step_groups(self, mode: str) -> List[str]:
         return {'full': ['base_model', 'gen_flow_model'], 'freeze': ['gen_flow_model'],

@@ -281,6 +281,19 @@ class HParams:
     num_segments: int = 3
     eps: float = 1e-3            # Adam eps, code/dmcnet/train.py:137,142
     betas: Tuple[float, float] = (0.9, 0.999)
+    loss_mse: str = 'MSELoss'    # --loss-mse (train_options.py:71): MSELoss | SmoothL1Loss | L1
+
+
+def flow_criterion(name: str):
+    """criterion_mse of code/dmcnet/train.py:166-172 (GAN/train.py:179-185).  Any other
+    string leaves criterion_mse undefined in the reference (NameError at the first use)."""
+    if name == 'MSELoss':
+        return torch.nn.MSELoss()
+    if name == 'SmoothL1Loss':
+        return torch.nn.SmoothL1Loss()
+    if name == 'L1':
+        return torch.nn.L1Loss()
+    raise NameError("name 'criterion_mse' is not defined")
 
 
 def accuracy(output: Tensor, target: Tensor, topk=(1,)) -> List[float]:
@@ -324,6 +337,7 @@ class OracleTrainer:
         self.opt_gf = mk(groups['gen_flow_model'])
         self.opt_d = mk(groups['discriminator']) if gan else None
         self.iteration = 0
+        self.criterion_mse = flow_criterion(hp.loss_mse)
         self.set_epoch(0, epoch_thre=0)
 
     def set_epoch(self, epoch: int, epoch_thre: int = 0):
@@ -365,7 +379,7 @@ class OracleTrainer:
             output, gen_flow = model_forward(self.st, input_mv, input_residual, train=True)
             output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)   # :239-240
             loss_cls = ce(output, target)                                     # :241
-            loss_mse = F.mse_loss(gen_flow, flow)                             # :245
+            loss_mse = self.criterion_mse(gen_flow, flow)                             # :245
             loss = loss_cls * hp.lr_cls + loss_mse * hp.lr_mse                # :248
             self._zero()
             if self.freeze:                                                   # :260-265
@@ -402,7 +416,7 @@ class OracleTrainer:
                 output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)
                 loss_cls = ce(output, target)
                 loss_adv = ce(validity, valid)                                # :346
-                loss_mse = F.mse_loss(gen_flow, flow)                         # :350
+                loss_mse = self.criterion_mse(gen_flow, flow)                         # :350
                 loss = loss_cls * hp.lr_cls + loss_adv * hp.lr_adv_g + loss_mse * hp.lr_mse
                 self._zero()
                 loss.backward()
