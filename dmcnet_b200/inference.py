@@ -1,0 +1,177 @@
+"""Video-level scoring (the deployment side of the same kernels).
+
+Mirrors the protocol of code/dmcnet/test.py:88-198 (GAN flavour
+code/dmcnet_GAN/test.py): one video = ``test_segments x test_crops`` frames
+(25 x 10 = 250 in the shipped recipe), eval-mode forward (BatchNorm running
+statistics, no dropout, no discriminator), class scores = mean of the LOGITS over
+all frames of the video (test.py:147-148), accuracy = argmax against the label
+(test.py:173-179), and the ``--save-scores`` ``.npz`` consumed by
+code/dmcnet/combine.py:35-56 (``scores`` = one ``(scores[1,C], label)`` pair per
+video in sorted-name order, ``labels``, ``names``).
+
+The forward runs on ``DmcEngine`` (hand-written kernels only); the mean over the
+frames of a video, the video-level cross-entropy and the top-1/top-5 hits come from
+the same ``ce_head`` launch the train step uses (S = frames per video).  There is
+no CPU path: ``VideoScorer`` needs a CUDA device and the built library.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+# ------------------------------------------------------------------ host logic (no device work)
+def strip_module_prefix(state: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+    """Checkpoints are saved from the nn.DataParallel wrapper; test.py:84 drops the first
+    dotted component of every key (``module.base_model...`` -> ``base_model...``)."""
+    return OrderedDict((k.split('.', 1)[1] if '.' in k else '', v) for k, v in state.items())
+
+
+def plan_launches(frames_per_video: int, max_frames: Optional[int]) -> Tuple[int, int]:
+    """(frames per engine launch, launches per video).  The engine runs a fixed frame count,
+    so a video is cut into equal parts: the largest divisor of ``frames_per_video`` that
+    does not exceed ``max_frames`` (None = the whole video in one launch)."""
+    if frames_per_video <= 0:
+        raise ValueError('a video needs at least one frame')
+    if max_frames is None or max_frames >= frames_per_video:
+        return frames_per_video, 1
+    if max_frames <= 0:
+        raise ValueError('max_frames must be positive')
+    per = max(d for d in range(1, max_frames + 1) if frames_per_video % d == 0)
+    return per, frames_per_video // per
+
+
+def check_crops(test_crops: int) -> int:
+    """test.py:88-98: only the centre crop or GroupOverSample's 10 crops exist."""
+    if test_crops not in (1, 10):
+        raise ValueError('Only 1 and 10 crops are supported, but got {}.'.format(test_crops))
+    return test_crops
+
+
+def video_accuracy(output: Sequence[Tuple[np.ndarray, int]]) -> float:
+    """Per-cent of videos whose argmax score equals the label (test.py:173-179)."""
+    if not output:
+        raise ValueError('no videos were scored')
+    hits = sum(int(np.argmax(s)) == int(l) for s, l in output)
+    return 100.0 * hits / len(output)
+
+
+def ordered_for_save(output: Sequence[Tuple[np.ndarray, int]], names: Sequence[str]):
+    """Sorted-name order of the saved file (test.py:183-195).  Returns (scores, labels, names)
+    with ``scores`` an object array [n, 2]: column 0 the [1, C] float32 scores, column 1 the
+    label -- the element layout combine.py indexes as ``score[0][0]`` / ``score[1]``."""
+    if len(output) != len(names):
+        raise ValueError('%d scored videos but %d names' % (len(output), len(names)))
+    if len(set(names)) != len(names):
+        raise ValueError('video names must be unique (they key the saved order)')
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    scores = np.empty((len(order), 2), dtype=object)
+    for row, i in enumerate(order):
+        scores[row, 0] = np.asarray(output[i][0], dtype=np.float32).reshape(1, -1)
+        scores[row, 1] = int(output[i][1])
+    labels = np.array([int(output[i][1]) for i in order], dtype=np.int64)
+    return scores, labels, np.array([names[i] for i in order])
+
+
+def save_scores(path: str, output: Sequence[Tuple[np.ndarray, int]], names: Sequence[str]) -> None:
+    """``--save-scores`` (test.py:181-198)."""
+    scores, labels, ordered = ordered_for_save(output, names)
+    np.savez(path, scores=scores, labels=labels, names=ordered)
+
+
+def load_scores(path: str):
+    """(scores [n, C] float32, labels [n], names [n]) of a file written by ``save_scores`` or by the
+    reference's test.py (object arrays: ``allow_pickle``)."""
+    with np.load(path, allow_pickle=True) as z:
+        scores = np.stack([np.asarray(s[0], dtype=np.float32)[0] for s in z['scores']])
+        labels = np.array([int(s[1]) for s in z['scores']], dtype=np.int64)
+        return scores, labels, np.array(z['names'])
+
+
+def combine_scores(files: Sequence[str], weights: Sequence[float]) -> Tuple[float, int]:
+    """Late fusion of per-stream score files (code/dmcnet/combine.py:35-56): weighted sum of
+    the video scores, argmax accuracy as a fraction, and the video count."""
+    if len(files) != len(weights) or not files:
+        raise ValueError('one weight per score file')
+    total, ref_labels = None, None
+    for f, w in zip(files, weights):
+        s, l, _ = load_scores(f)
+        if ref_labels is None:
+            total, ref_labels = w * s, l
+        else:
+            assert np.array_equal(l, ref_labels), 'score files disagree on the labels'
+            total = total + w * s
+    return float(np.mean(np.argmax(total, axis=1) == ref_labels)), len(ref_labels)
+
+
+# ------------------------------------------------------------------ device path
+class VideoScorer:
+    """``forward_video`` of test.py:139-151 on the B200 engine.
+
+    state:   state_dict of a trained ``Model`` (``module.`` prefix already stripped; keys of a
+             discriminator or ``data_bn`` are ignored, as ``load_state_dict(strict=False)`` does)
+    """
+
+    def __init__(self, state: Dict[str, torch.Tensor], num_class: int, test_segments: int = 25,
+                 test_crops: int = 10, *, gen_flow_or_delta: int = 1, height: int = 224,
+                 width: int = 224, max_frames_per_launch: Optional[int] = None,
+                 device: Optional[torch.device] = None):
+        from .engine import DmcEngine
+        self.num_class = num_class
+        self.segments, self.crops = test_segments, check_crops(test_crops)
+        self.frames = test_segments * test_crops
+        self.per_launch, self.launches = plan_launches(self.frames, max_frames_per_launch)
+        self.eng = DmcEngine(num_class, test_segments, self.per_launch, gan=False,
+                             gen_flow_or_delta=gen_flow_or_delta, height=height, width=width,
+                             device=device)
+        missing = [k for k in list(self.eng.specs) + list(self.eng.buffers) if k not in state]
+        if missing:
+            raise KeyError('state_dict lacks %d tensors of the scoring path, e.g. %s'
+                           % (len(missing), missing[0]))
+        self.eng.load_state(state)
+        dev = self.eng.device
+        self.H, self.W = height, width
+        self._logits = torch.zeros(self.frames, num_class, dtype=torch.float32, device=dev)
+        self._scores = torch.zeros(1, num_class, dtype=torch.float32, device=dev)
+        self._stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._label = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def forward_video(self, input_mv: torch.Tensor, input_residual: torch.Tensor,
+                      label: int = 0) -> np.ndarray:
+        """[1, frames, 2, H, W] / [1, frames, 3, H, W] (one DataLoader item, batch_size=1 as in
+        test.py:119) -> scores [1, num_class] (numpy, like ``scores.data.cpu().numpy()``)."""
+        from . import ops
+        H, W = self.H, self.W
+        mv = input_mv.reshape(-1, 2, H, W)
+        res = input_residual.reshape(-1, 3, H, W)
+        if mv.shape[0] != self.frames or res.shape[0] != self.frames:
+            raise ValueError('expected %d frames per video (test_segments x test_crops), got %d / %d'
+                             % (self.frames, mv.shape[0], res.shape[0]))
+        dev = self.eng.device
+        mv = mv.to(dev, torch.float32, non_blocking=True).contiguous()
+        res = res.to(dev, torch.float32, non_blocking=True).contiguous()
+        n = self.per_launch
+        for j in range(self.launches):
+            logits, _ = self.eng.forward(mv[j * n:(j + 1) * n], res[j * n:(j + 1) * n], train=False)
+            self._logits[j * n:(j + 1) * n].copy_(logits)
+        self._label.fill_(int(label))
+        # mean over every frame of the video + video-level CE / top-k in one launch
+        ops.ce_head(self._logits, 1, self.frames, self.num_class, self._label, 0.0, self._scores, None,
+                    self._stats)
+        return self._scores.cpu().numpy().copy()
+
+    def last_stats(self) -> Dict[str, float]:
+        """Cross-entropy and top-1 / top-5 hit of the last scored video against its label."""
+        s = self._stats.cpu().tolist()
+        return {'loss': s[0], 'top1': s[1], 'top5': s[2]}
+
+    def evaluate(self, samples: Iterable) -> List[Tuple[np.ndarray, int]]:
+        """The loop of test.py:155-171 over ``(input_flow, input_mv, input_residual, label)`` items."""
+        output = []
+        for _flow, mv, res, label in samples:
+            lab = int(label[0]) if hasattr(label, '__len__') else int(label)
+            output.append((self.forward_video(mv, res, lab), lab))
+        return output

@@ -75,3 +75,44 @@ def test_train_step_with_alternative_flow_criterion(loss_mse):
     for k, v in ref.state_dict().items():
         if k.startswith('gen_flow_model'):
             assert rel(new[k], v) < tol_p, k
+
+
+# ------------------------------------------------------------------ video-level scoring (test.py protocol)
+@pytest.mark.parametrize('max_frames', [None, 3])
+def test_video_scorer_vs_oracle_protocol(max_frames, monkeypatch):
+    """2 videos x (3 segments x 2 'crops') frames, eval-mode forward, mean of the logits over the
+    6 frames of a video (code/dmcnet/test.py:139-151); whole video per launch and 2 launches."""
+    from dmcnet_b200 import inference as I
+    from oracle import video_protocol as V
+    monkeypatch.setattr(I, 'check_crops', lambda c: c)       # 2 crops keep the CPU oracle quick
+    num_class, segs, crops = 51, 3, 2
+    sd = O.build_state(num_class, 'Discriminator', seed=1)   # a GAN checkpoint: D keys are ignored
+    # non-trivial running statistics, as after training
+    g = torch.Generator().manual_seed(5)
+    for k in sd:
+        if k.endswith('running_mean'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    scorer = I.VideoScorer(sd, num_class, segs, crops, max_frames_per_launch=max_frames)
+    assert scorer.launches == (1 if max_frames is None else 2)
+    out, ref = [], []
+    for v in range(2):
+        flow, mv, res, target = O.make_inputs(2, 3, num_class, seed=10 + v)   # [2,3,c,H,W] = 6 frames
+        mv, res = mv.reshape(1, 6, 2, 224, 224), res.reshape(1, 6, 3, 224, 224)
+        label = int(target[0])
+        s = scorer.forward_video(mv, res, label)
+        r = V.forward_video(sd, mv, res, segs, crops)
+        assert s.shape == r.shape == (1, num_class)
+        np.testing.assert_allclose(s, r, rtol=1e-3, atol=1e-3 * np.abs(r).max())
+        assert int(s.argmax()) == int(r.argmax())
+        st = scorer.last_stats()
+        assert st['loss'] == pytest.approx(float(F.cross_entropy(torch.from_numpy(r), target[:1])), rel=1e-3)
+        assert st['top1'] == float(int(r.argmax()) == label)
+        out.append((s, label)); ref.append((r, label))
+    assert I.video_accuracy(out) == V.accuracy(ref)
+    # the engine's running statistics are read, never updated, in eval mode
+    new = scorer.eng.state_dict()
+    for k in new:
+        if 'running' in k or 'num_batches' in k:
+            assert torch.equal(new[k].cpu(), sd[k].to(new[k].dtype)), k
