@@ -1,0 +1,150 @@
+// Input stage of the train / test step: the CoviarDataSet sample arithmetic
+// (code/dmcnet/dataset.py:215-263) on the device, so a batch crosses PCIe as the uint8
+// [N][H][W][7] stacks the augmentation produces (7 B/pixel) instead of three fp32 tensors
+// (28 B/pixel).
+//   unpack_normalize_u8  : split the interleaved stack (channels 0-1 optical flow, 2-3 motion
+//                          vectors, 4-6 residual; dataset.py:210,222-224) into the planar fp32
+//                          tensors Model.forward takes and normalise them,
+//                          (v/255 - 0.5)/mean(std) for flow and mv, (v/255 - 0.5)/std_c for the
+//                          residual (dataset.py:251-263).
+//   flow_block_mean_u8   : the "blocky" flow target of --flow_ds_factor (dataset.py:226-246 with
+//                          upsample_interp = False): mean over factor x factor blocks (zero padded
+//                          at the bottom/right edge, as skimage.measure.block_reduce), repeated back
+//                          to full size, then normalised like the flow above.
+// Both are HBM streams (7 B read + 28 B written per pixel).  The arithmetic is bit-exact with the
+// reference: the same IEEE fp32 operations in the same order (two divisions and a subtraction per
+// value; the block mean is an exact integer sum divided in double and rounded once to fp32, which is
+// what numpy's float64 mean followed by .float() gives).
+#include "common.cuh"
+
+namespace dmc {
+
+__device__ __forceinline__ float normalize_u8(float v, float divisor) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), 0.5f), divisor);
+}
+
+// One thread = 4 consecutive pixels = 28 bytes = 7 aligned 32-bit words in, 7 float4 out.
+__global__ void __launch_bounds__(256)
+unpack_normalize_u8_kernel(const unsigned int* __restrict__ frames, long groups, int hw4,
+                           float div_motion, float div_r0, float div_r1, float div_r2,
+                           float* __restrict__ flow, float* __restrict__ mv, float* __restrict__ res) {
+  const float divs[7] = {div_motion, div_motion, div_motion, div_motion, div_r0, div_r1, div_r2};
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups;
+       g += (long)gridDim.x * blockDim.x) {
+    unsigned int w[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = __ldg(frames + g * 7 + k);
+    const long n = g / hw4;              // frame
+    const long p4 = g - n * hw4;         // float4 index inside a plane
+    float out[7][4];
+#pragma unroll
+    for (int b = 0; b < 28; ++b) {
+      const unsigned int byte = (w[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      out[b % 7][b / 7] = normalize_u8((float)byte, divs[b % 7]);
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      float* base;
+      if (c < 2) {
+        if (flow == nullptr) continue;
+        base = flow + ((n * 2 + c) * hw4 + p4) * 4;
+      } else if (c < 4) {
+        base = mv + ((n * 2 + (c - 2)) * hw4 + p4) * 4;
+      } else {
+        base = res + ((n * 3 + (c - 4)) * hw4 + p4) * 4;
+      }
+      *reinterpret_cast<float4*>(base) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+    }
+  }
+}
+
+constexpr int kMaxBlockCols = 256;
+
+// One CTA = one row of blocks of one frame: `rows` image rows x W pixels x 2 flow channels.
+__global__ void __launch_bounds__(256)
+flow_block_mean_u8_kernel(const unsigned char* __restrict__ frames, int H, int W, int f,
+                          float div_motion, float* __restrict__ flow) {
+  __shared__ int s_sum[2 * kMaxBlockCols];
+  __shared__ float s_val[2 * kMaxBlockCols];
+  const int by = blockIdx.x, n = blockIdx.y;
+  const int nbx = (W + f - 1) / f;
+  const int y0 = by * f;
+  const int rows = min(f, H - y0);
+  for (int i = threadIdx.x; i < 2 * nbx; i += blockDim.x) s_sum[i] = 0;
+  __syncthreads();
+  // work item = (image row r, block column bx, channel c): an exact integer sum of <= f bytes
+  const int items = rows * nbx * 2;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int c = it & 1;
+    const int bx = (it >> 1) % nbx;
+    const int r = (it >> 1) / nbx;
+    const int x0 = bx * f, xe = min(x0 + f, W);
+    const unsigned char* p = frames + (((long)n * H + y0 + r) * W + x0) * 7 + c;
+    int s = 0;
+    for (int x = x0; x < xe; ++x, p += 7) s += (int)__ldg(p);
+    atomicAdd(&s_sum[c * nbx + bx], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * nbx; i += blockDim.x) {
+    // zero padded blocks still divide by f*f (block_reduce pads with cval = 0)
+    const float mean = (float)((double)s_sum[i] / (double)(f * f));
+    s_val[i] = normalize_u8(mean, div_motion);
+  }
+  __syncthreads();
+  const int per_c = rows * W;
+  for (int idx = threadIdx.x; idx < 2 * per_c; idx += blockDim.x) {
+    const int c = idx / per_c;
+    const int rem = idx - c * per_c;
+    const int r = rem / W;
+    const int x = rem - r * W;
+    flow[(((long)n * 2 + c) * H + y0 + r) * W + x] = s_val[c * nbx + x / f];
+  }
+}
+
+}  // namespace dmc
+
+using namespace dmc;
+#define ST_(s) reinterpret_cast<cudaStream_t>(s)
+
+// frames: uint8 [N][H][W][7] (flow x,y | mv x,y | residual r,g,b), 4-byte aligned, H*W a multiple of 4.
+// flow / mv: fp32 [N][2][H][W], res: fp32 [N][3][H][W], contiguous and 16-byte aligned; flow may be
+// NULL (then only mv and res are produced -- use dmc_flow_block_mean_u8 for the flow target).
+// div_motion = mean(std) (flow and mv), div_r* = std of the three residual channels
+// (code/dmcnet/dataset.py:109-112, :251-263).
+extern "C" int dmc_unpack_normalize_u8(const unsigned char* frames, int N, int H, int W,
+                                       float div_motion, float div_r0, float div_r1, float div_r2,
+                                       float* flow, float* mv, float* res, void* stream) {
+  DMC_REQUIRE(N > 0 && H > 0 && W > 0, "unpack_normalize_u8: bad shape");
+  DMC_REQUIRE(((long)H * W) % 4 == 0, "unpack_normalize_u8: H*W must be a multiple of 4");
+  DMC_REQUIRE(frames && mv && res, "unpack_normalize_u8: null pointer");
+  DMC_REQUIRE((reinterpret_cast<size_t>(frames) & 3) == 0, "unpack_normalize_u8: frames must be 4-byte aligned");
+  DMC_REQUIRE(((reinterpret_cast<size_t>(flow) | reinterpret_cast<size_t>(mv) |
+                reinterpret_cast<size_t>(res)) & 15) == 0,
+              "unpack_normalize_u8: outputs must be 16-byte aligned");
+  DMC_REQUIRE(div_motion != 0.f && div_r0 != 0.f && div_r1 != 0.f && div_r2 != 0.f,
+              "unpack_normalize_u8: zero divisor");
+  const int hw4 = (int)(((long)H * W) / 4);
+  const long groups = (long)N * hw4;
+  long blocks = cdiv(groups, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_normalize_u8_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(
+      reinterpret_cast<const unsigned int*>(frames), groups, hw4, div_motion, div_r0, div_r1, div_r2,
+      flow, mv, res);
+  return dmc_check_launch("unpack_normalize_u8_kernel");
+}
+
+// flow: fp32 [N][2][H][W] = normalised factor x factor block means of channels 0-1 of `frames`
+// (uint8 [N][H][W][7]), each mean repeated over its block (code/dmcnet/dataset.py:226-246,
+// upsample_interp = False).  factor >= 1; ceil(W / factor) <= 256.
+extern "C" int dmc_flow_block_mean_u8(const unsigned char* frames, int N, int H, int W, int factor,
+                                      float div_motion, float* flow, void* stream) {
+  DMC_REQUIRE(N > 0 && H > 0 && W > 0 && factor >= 1, "flow_block_mean_u8: bad shape");
+  DMC_REQUIRE(frames && flow, "flow_block_mean_u8: null pointer");
+  DMC_REQUIRE(div_motion != 0.f, "flow_block_mean_u8: zero divisor");
+  const int nbx = (W + factor - 1) / factor, nby = (H + factor - 1) / factor;
+  DMC_REQUIRE(nbx <= kMaxBlockCols, "flow_block_mean_u8: more than 256 blocks per row");
+  DMC_REQUIRE(N <= 65535, "flow_block_mean_u8: more than 65535 frames per call");
+  DMC_REQUIRE((long)factor * factor * 255 < 2147483647L, "flow_block_mean_u8: factor too large");
+  flow_block_mean_u8_kernel<<<dim3(nby, N), 256, 0, ST_(stream)>>>(frames, H, W, factor, div_motion, flow);
+  return dmc_check_launch("flow_block_mean_u8_kernel");
+}

@@ -352,6 +352,20 @@ def flow_loss_head(kind, gen, flow, numel, gscale, dgen, loss_sum, frame_elems=N
           _ptr(loss_sum, F64), _stream())
 
 
+def unpack_normalize_u8(frames, N, H, W, div_motion, div_res, flow, mv, res):
+    """uint8 [N][H][W][7] -> planar fp32 flow (optional) / mv / residual, normalised as
+    code/dmcnet/dataset.py:251-263.  div_res = the three residual std values."""
+    _call('dmc_unpack_normalize_u8', _ptr(frames, U8), c_int(N), c_int(H), c_int(W), c_float(div_motion),
+          c_float(div_res[0]), c_float(div_res[1]), c_float(div_res[2]), _ptr(flow, F32), _ptr(mv, F32),
+          _ptr(res, F32), _stream())
+
+
+def flow_block_mean_u8(frames, N, H, W, factor, div_motion, flow):
+    """Block-mean ("blocky") flow target of --flow_ds_factor (code/dmcnet/dataset.py:226-246)."""
+    _call('dmc_flow_block_mean_u8', _ptr(frames, U8), c_int(N), c_int(H), c_int(W), c_int(factor),
+          c_float(div_motion), _ptr(flow, F32), _stream())
+
+
 def dense_dgrad_weights(params, table, out):
     _call('dmc_dense_dgrad_weights', _ptr(params, F32), _iarr(table), _ptr(out, F32), _stream())
 

@@ -120,6 +120,7 @@ class FusedTrainStep:
         self._build_adam_tables()
         self.set_epoch(0, epoch_thre=0)
         self._graphs: Dict[str, object] = {}
+        self._u8_stages: Dict[int, object] = {}
         self.launches_per_step = 0
         # pipelined input staging: H2D of batch k+1 overlaps the compute of batch k
         self.pipelined = pipelined
@@ -301,11 +302,34 @@ class FusedTrainStep:
         self.in_res.copy_(input_residual.reshape(-1, 3, H, W), non_blocking=True)
         self.target.copy_(target, non_blocking=True)
 
+    def load_inputs_u8(self, frames_u8, target, flow_ds_factor: int = 0):
+        """Stage one batch given as the uint8 stack [B,S,H,W,7] the augmentation produces
+        (flow | mv | residual channels, code/dmcnet/dataset.py:210): split, block-mean flow
+        target (--flow_ds_factor) and normalisation run on the device (input_stage.py), so the
+        host->device copy is 7 B/pixel instead of 28."""
+        from .input_stage import U8InputStage
+        st = self._u8_stages.get(flow_ds_factor)
+        if st is None:
+            st = U8InputStage(self.eng.N, self.eng.H, self.eng.W, flow_ds_factor=flow_ds_factor,
+                              device=self.eng.device)
+            self._u8_stages[flow_ds_factor] = st
+        st(frames_u8, self.in_flow, self.in_mv, self.in_res)
+        self.target.copy_(target, non_blocking=True)
+
+    def step_u8(self, frames_u8, target, masks: Optional[Sequence[torch.Tensor]] = None,
+                flow_ds_factor: int = 0, apply: bool = True, metrics: bool = True) -> Dict[str, float]:
+        """``step`` fed with the uint8 sample stack (see ``load_inputs_u8``)."""
+        return self.step(None, None, None, target, masks=masks, apply=apply, metrics=metrics,
+                         _u8=(frames_u8, flow_ds_factor))
+
     def step(self, input_flow, input_mv, input_residual, target,
              masks: Optional[Sequence[torch.Tensor]] = None, apply: bool = True,
-             metrics: bool = True) -> Dict[str, float]:
+             metrics: bool = True, _u8=None) -> Dict[str, float]:
         eng = self.eng
-        self.load_inputs(input_flow, input_mv, input_residual, target)
+        if _u8 is not None:
+            self.load_inputs_u8(_u8[0], target, _u8[1])
+        else:
+            self.load_inputs(input_flow, input_mv, input_residual, target)
         mode = self._mode()
         if eng.gan:
             m = 2 * eng.N if mode == 'D' else eng.N

@@ -103,3 +103,89 @@ def test_video_scorer_refuses_to_run_without_a_gpu():
         pytest.skip('CPU-only check')
     with pytest.raises(RuntimeError, match='CUDA'):
         I.VideoScorer({}, 51, 3, 1)
+
+
+# ------------------------------------------------------------------ uint8 input stage
+def _golden_cases(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, 'input_pipe.npz'))
+    names = sorted({k.split('.')[0] for k in z.files})
+    assert len(names) == 4
+    for n in names:
+        yield n, z[n + '.frames'], int(z[n + '.factor']), z[n + '.flow'], z[n + '.mv'], z[n + '.res']
+
+
+def test_input_oracle_pinned_against_reference_dataset():
+    from oracle import ref_loader as R
+    if not R.reference_available():
+        pytest.skip('/root/reference not present')
+    from oracle.pin_input_pipe import pin
+    assert pin(write=False, verbose=False) == 2 * 4 * 3
+
+
+def test_input_oracle_reproduces_reference_golden(golden_dir):
+    """tests/golden/input_pipe.npz holds outputs of the reference's own dataset.py."""
+    from oracle import input_pipe as P
+    for name, frames, factor, flow, mv, res in _golden_cases(golden_dir):
+        o_flow, o_mv, o_res = P.sample_from_frames(list(frames), factor)
+        assert np.array_equal(o_flow.numpy(), flow), name
+        assert np.array_equal(o_mv.numpy(), mv), name
+        assert np.array_equal(o_res.numpy(), res), name
+
+
+def _kernel_model_unpack(frames, div_motion, div_res):
+    """numpy model of unpack_normalize_u8_kernel: thread g reads words 7g..7g+6 of the byte
+    stream, byte b of its 28 is pixel b // 7, channel b % 7."""
+    S, H, W, _ = frames.shape
+    words = np.frombuffer(frames.tobytes(), dtype='<u4')
+    groups = S * H * W // 4
+    w = words.reshape(groups, 7)
+    out = np.zeros((7, groups, 4), np.float32)
+    divs = np.array([div_motion] * 4 + list(div_res), np.float32)
+    for b in range(28):
+        byte = (w[:, b >> 2] >> np.uint32(8 * (b & 3))) & np.uint32(0xff)
+        v = byte.astype(np.float32) / np.float32(255.0)
+        out[b % 7, :, b // 7] = (v - np.float32(0.5)) / divs[b % 7]
+    planes = out.reshape(7, S, H * W)                      # group g = frame n, float4 p4 -> contiguous
+    split = lambda lo, hi: planes[lo:hi].transpose(1, 0, 2).reshape(S, hi - lo, H, W)
+    return split(0, 2), split(2, 4), split(4, 7)
+
+
+def _kernel_model_block_mean(frames, f, div_motion):
+    """numpy model of flow_block_mean_u8_kernel (integer block sums, one double division)."""
+    S, H, W, _ = frames.shape
+    out = np.zeros((S, 2, H, W), np.float32)
+    for by in range(-(-H // f)):
+        for bx in range(-(-W // f)):
+            blk = frames[:, by * f:min(H, by * f + f), bx * f:min(W, bx * f + f), 0:2].astype(np.int64)
+            mean = (blk.sum(axis=(1, 2)).astype(np.float64) / np.float64(f * f)).astype(np.float32)   # [S,2]
+            val = (mean / np.float32(255.0) - np.float32(0.5)) / np.float32(div_motion)
+            out[:, :, by * f:by * f + f, bx * f:bx * f + f] = val[:, :, None, None]
+    return out
+
+
+def test_input_kernels_index_arithmetic_model_is_bit_exact(golden_dir):
+    from dmcnet_b200.input_stage import normalisation_divisors
+    div_motion, div_res = normalisation_divisors()
+    std = torch.from_numpy(np.array([0.229, 0.224, 0.225]).reshape((1, 3, 1, 1))).float()   # dataset.py:111
+    assert div_motion == float(torch.mean(std)) and list(div_res) == [float(v) for v in std.reshape(-1)]
+    for name, frames, factor, flow, mv, res in _golden_cases(golden_dir):
+        k_flow, k_mv, k_res = _kernel_model_unpack(frames, div_motion, div_res)
+        assert np.array_equal(k_mv, mv) and np.array_equal(k_res, res), name
+        if factor == 0:
+            assert np.array_equal(k_flow, flow), name
+        else:
+            assert np.array_equal(_kernel_model_block_mean(frames, factor, div_motion), flow), name
+
+
+def test_input_stage_argument_checks():
+    from dmcnet_b200 import input_stage as S
+    with pytest.raises(TypeError):
+        S.check_stack(torch.zeros(2, 8, 8, 7), 2, 8, 8)
+    with pytest.raises(ValueError, match='trailing'):
+        S.check_stack(torch.zeros(2, 7, 8, 8, dtype=torch.uint8), 2, 8, 8)
+    with pytest.raises(ValueError, match='frames'):
+        S.check_stack(torch.zeros(3, 8, 8, 7, dtype=torch.uint8), 2, 8, 8)
+    S.check_stack(torch.zeros(1, 2, 8, 8, 7, dtype=torch.uint8), 2, 8, 8)
+    with pytest.raises(NotImplementedError, match='interp'):
+        S.U8InputStage(2, 8, 8, upsample_interp=True)

@@ -116,3 +116,63 @@ def test_video_scorer_vs_oracle_protocol(max_frames, monkeypatch):
     for k in new:
         if 'running' in k or 'num_batches' in k:
             assert torch.equal(new[k].cpu(), sd[k].to(new[k].dtype)), k
+
+
+# ------------------------------------------------------------------ uint8 input stage
+def test_input_stage_kernels_bit_exact_vs_reference_golden(golden_dir):
+    """tests/golden/input_pipe.npz: outputs of the reference's own dataset.py (oracle/pin_input_pipe.py)."""
+    import os
+    from dmcnet_b200.input_stage import U8InputStage
+    z = np.load(os.path.join(golden_dir, 'input_pipe.npz'))
+    for name in sorted({k.split('.')[0] for k in z.files}):
+        frames, factor = z[name + '.frames'], int(z[name + '.factor'])
+        S, H, W, _ = frames.shape
+        stage = U8InputStage(S, H, W, flow_ds_factor=factor)
+        flow, mv, res = stage(torch.from_numpy(frames))
+        torch.cuda.synchronize()
+        assert np.array_equal(flow.cpu().numpy(), z[name + '.flow']), name
+        assert np.array_equal(mv.cpu().numpy(), z[name + '.mv']), name
+        assert np.array_equal(res.cpu().numpy(), z[name + '.res']), name
+
+
+@pytest.mark.parametrize('factor', [0, 16, 3])
+def test_input_stage_full_size_vs_oracle(factor):
+    from dmcnet_b200.input_stage import U8InputStage
+    from oracle import input_pipe as P
+    frames = P.synthetic_frames(6, 224, 224, seed=factor)
+    o_flow, o_mv, o_res = P.sample_from_frames(list(frames), factor)
+    stage = U8InputStage(6, 224, 224, flow_ds_factor=factor)
+    host = torch.from_numpy(frames).reshape(2, 3, 224, 224, 7).pin_memory()      # [B,S,H,W,7]
+    flow, mv, res = stage(host)
+    torch.cuda.synchronize()
+    assert torch.equal(flow.cpu(), o_flow) and torch.equal(mv.cpu(), o_mv) and torch.equal(res.cpu(), o_res)
+    assert stage.h2d_bytes == 6 * 224 * 224 * 7
+
+
+def test_step_from_uint8_stack_equals_step_from_float_tensors():
+    from oracle import input_pipe as P
+    batch, num_class = 2, 51
+    frames = P.synthetic_frames(batch * 3, 224, 224, seed=4)
+    flow, mv, res = P.sample_from_frames(list(frames), 16)
+    target = torch.tensor([3, 40])
+    sd = O.build_state(num_class, None, seed=1)
+    out = []
+    for use_u8 in (False, True):
+        eng = DmcEngine(num_class, 3, batch * 3)
+        eng.load_state(sd)
+        tr = FusedTrainStep(eng, HParams(), batch)
+        if use_u8:
+            m = tr.step_u8(torch.from_numpy(frames).reshape(batch, 3, 224, 224, 7), target.cuda(),
+                           flow_ds_factor=16)
+        else:
+            m = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+        out.append((m, eng.gen_flow.cpu().clone(), tr.consensus.cpu().clone()))
+    (ma, ga, ca), (mb, gb, cb) = out
+    assert torch.equal(ga, gb)                 # identical inputs -> identical generator output
+    assert rel(ca, cb) < 1e-5                  # BatchNorm channel sums use fp32 atomics: last-bit noise
+    for k in ('loss_cls', 'loss_mse', 'prec1', 'prec5'):
+        assert ma[k] == pytest.approx(mb[k], rel=1e-6), k
+    ref = O.OracleTrainer(sd, O.HParams(), gan=False)
+    mo = ref.step(flow, mv, res, target)
+    for k in ('loss', 'loss_cls', 'loss_mse'):
+        assert mb[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
