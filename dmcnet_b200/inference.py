@@ -3,7 +3,7 @@
 Mirrors the protocol of code/dmcnet/test.py:88-198 (GAN flavour
 code/dmcnet_GAN/test.py): one video = ``test_segments x test_crops`` frames
 (25 x 10 = 250 in the shipped recipe), eval-mode forward (BatchNorm running
-statistics, no dropout, no discriminator), class scores = mean of the LOGITS over
+statistics, no dropout; the discriminator only on request), class scores = mean of the LOGITS over
 all frames of the video (test.py:147-148), accuracy = argmax against the label
 (test.py:173-179), and the ``--save-scores`` ``.npz`` consumed by
 code/dmcnet/combine.py:35-56 (``scores`` = one ``(scores[1,C], label)`` pair per
@@ -51,32 +51,49 @@ def check_crops(test_crops: int) -> int:
     return test_crops
 
 
-def video_accuracy(output: Sequence[Tuple[np.ndarray, int]]) -> float:
+def video_accuracy(output: Sequence[tuple]) -> float:
     """Per-cent of videos whose argmax score equals the label (test.py:173-179)."""
     if not output:
         raise ValueError('no videos were scored')
-    hits = sum(int(np.argmax(s)) == int(l) for s, l in output)
+    hits = sum(int(np.argmax(o[0])) == int(o[1]) for o in output)
     return 100.0 * hits / len(output)
 
 
-def ordered_for_save(output: Sequence[Tuple[np.ndarray, int]], names: Sequence[str]):
+def adversarial_accuracy(output: Sequence[tuple]) -> float:
+    """'Accuracy adv G' of code/dmcnet_GAN/test.py:125,131-133: np.argmax over the FLATTENED
+    [frames, 2] validity logits of each video, summed and divided by the video count (the
+    reference prints this figure as is; it is not bounded by 100)."""
+    if not output:
+        raise ValueError('no videos were scored')
+    return 100.0 * float(sum(int(np.argmax(o[2])) for o in output)) / len(output)
+
+
+def ordered_for_save(output: Sequence[tuple], names: Sequence[str]):
     """Sorted-name order of the saved file (test.py:183-195).  Returns (scores, labels, names)
     with ``scores`` an object array [n, 2]: column 0 the [1, C] float32 scores, column 1 the
-    label -- the element layout combine.py indexes as ``score[0][0]`` / ``score[1]``."""
+    label -- the element layout combine.py indexes as ``score[0][0]`` / ``score[1]``.  The GAN
+    script appends the per-frame discriminator logits as a third element
+    (code/dmcnet_GAN/test.py:116): 3-tuples give an [n, 3] array with that column."""
     if len(output) != len(names):
         raise ValueError('%d scored videos but %d names' % (len(output), len(names)))
     if len(set(names)) != len(names):
         raise ValueError('video names must be unique (they key the saved order)')
+    width = {len(o) for o in output}
+    if len(width) > 1 or not width <= {2, 3}:
+        raise ValueError('every entry must be (scores, label) or (scores, label, validity)')
+    cols = width.pop() if width else 2
     order = sorted(range(len(names)), key=lambda i: names[i])
-    scores = np.empty((len(order), 2), dtype=object)
+    scores = np.empty((len(order), cols), dtype=object)
     for row, i in enumerate(order):
         scores[row, 0] = np.asarray(output[i][0], dtype=np.float32).reshape(1, -1)
         scores[row, 1] = int(output[i][1])
+        if cols == 3:
+            scores[row, 2] = np.asarray(output[i][2], dtype=np.float32)
     labels = np.array([int(output[i][1]) for i in order], dtype=np.int64)
     return scores, labels, np.array([names[i] for i in order])
 
 
-def save_scores(path: str, output: Sequence[Tuple[np.ndarray, int]], names: Sequence[str]) -> None:
+def save_scores(path: str, output: Sequence[tuple], names: Sequence[str]) -> None:
     """``--save-scores`` (test.py:181-198)."""
     scores, labels, ordered = ordered_for_save(output, names)
     np.savez(path, scores=scores, labels=labels, names=ordered)
@@ -118,15 +135,18 @@ class VideoScorer:
     def __init__(self, state: Dict[str, torch.Tensor], num_class: int, test_segments: int = 25,
                  test_crops: int = 10, *, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, max_frames_per_launch: Optional[int] = None,
-                 device: Optional[torch.device] = None):
+                 arch_d: Optional[str] = None, device: Optional[torch.device] = None):
         from .engine import DmcEngine
         self.num_class = num_class
+        self.arch_d = arch_d
         self.segments, self.crops = test_segments, check_crops(test_crops)
         self.frames = test_segments * test_crops
         self.per_launch, self.launches = plan_launches(self.frames, max_frames_per_launch)
-        self.eng = DmcEngine(num_class, test_segments, self.per_launch, gan=False,
-                             gen_flow_or_delta=gen_flow_or_delta, height=height, width=width,
-                             device=device)
+        # arch_d: also run the discriminator on the generated map (code/dmcnet_GAN/test.py:91,
+        # validity [frames, 2] per video); the class scores do not depend on it
+        self.eng = DmcEngine(num_class, test_segments, self.per_launch, gan=arch_d is not None,
+                             arch_d=arch_d, gen_flow_or_delta=gen_flow_or_delta, height=height,
+                             width=width, device=device)
         missing = [k for k in list(self.eng.specs) + list(self.eng.buffers) if k not in state]
         if missing:
             raise KeyError('state_dict lacks %d tensors of the scoring path, e.g. %s'
@@ -135,6 +155,7 @@ class VideoScorer:
         dev = self.eng.device
         self.H, self.W = height, width
         self._logits = torch.zeros(self.frames, num_class, dtype=torch.float32, device=dev)
+        self._validity = torch.zeros(self.frames, 2, dtype=torch.float32, device=dev)
         self._scores = torch.zeros(1, num_class, dtype=torch.float32, device=dev)
         self._stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self._label = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -155,23 +176,33 @@ class VideoScorer:
         res = res.to(dev, torch.float32, non_blocking=True).contiguous()
         n = self.per_launch
         for j in range(self.launches):
-            logits, _ = self.eng.forward(mv[j * n:(j + 1) * n], res[j * n:(j + 1) * n], train=False)
-            self._logits[j * n:(j + 1) * n].copy_(logits)
+            out = self.eng.forward(mv[j * n:(j + 1) * n], res[j * n:(j + 1) * n], train=False)
+            self._logits[j * n:(j + 1) * n].copy_(out[0])
+            if self.arch_d is not None:
+                self._validity[j * n:(j + 1) * n].copy_(out[1])
         self._label.fill_(int(label))
         # mean over every frame of the video + video-level CE / top-k in one launch
         ops.ce_head(self._logits, 1, self.frames, self.num_class, self._label, 0.0, self._scores, None,
                     self._stats)
         return self._scores.cpu().numpy().copy()
 
+    def last_validity(self) -> np.ndarray:
+        """Discriminator logits [frames, 2] of the last scored video (needs ``arch_d``); the third
+        element of the GAN script's output tuples (code/dmcnet_GAN/test.py:97,116)."""
+        if self.arch_d is None:
+            raise RuntimeError('VideoScorer was built without arch_d: no discriminator was run')
+        return self._validity.cpu().numpy().copy()
+
     def last_stats(self) -> Dict[str, float]:
         """Cross-entropy and top-1 / top-5 hit of the last scored video against its label."""
         s = self._stats.cpu().tolist()
         return {'loss': s[0], 'top1': s[1], 'top5': s[2]}
 
-    def evaluate(self, samples: Iterable) -> List[Tuple[np.ndarray, int]]:
+    def evaluate(self, samples: Iterable) -> List[tuple]:
         """The loop of test.py:155-171 over ``(input_flow, input_mv, input_residual, label)`` items."""
         output = []
         for _flow, mv, res, label in samples:
             lab = int(label[0]) if hasattr(label, '__len__') else int(label)
-            output.append((self.forward_video(mv, res, lab), lab))
+            scores = self.forward_video(mv, res, lab)
+            output.append((scores, lab) if self.arch_d is None else (scores, lab, self.last_validity()))
         return output

@@ -28,6 +28,17 @@ def forward_video(state: Dict[str, torch.Tensor], input_mv: torch.Tensor, input_
     return torch.mean(scores, dim=1).numpy().copy()
 
 
+def forward_video_gan(state: Dict[str, torch.Tensor], input_mv: torch.Tensor, input_residual: torch.Tensor,
+                      test_segments: int, test_crops: int, arch_d: str):
+    """code/dmcnet_GAN/test.py:86-98: (scores [1,C], validity [frames,2])."""
+    st = {k: v.detach() for k, v in state.items()}
+    with torch.no_grad():
+        scores, validity, _ = O.model_forward(st, input_mv, input_residual, None, gan=True, arch_d=arch_d,
+                                              train=False)
+    scores = scores.view((-1, test_segments * test_crops) + tuple(scores.shape[1:]))
+    return torch.mean(scores, dim=1).numpy().copy(), validity.numpy().copy()
+
+
 def accuracy(output: Sequence[Tuple[np.ndarray, int]]) -> float:
     """test.py:173-179."""
     video_pred = [np.argmax(x[0]) for x in output]

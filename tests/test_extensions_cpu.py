@@ -189,3 +189,53 @@ def test_input_stage_argument_checks():
     S.check_stack(torch.zeros(1, 2, 8, 8, 7, dtype=torch.uint8), 2, 8, 8)
     with pytest.raises(NotImplementedError, match='interp'):
         S.U8InputStage(2, 8, 8, upsample_interp=True)
+
+
+def test_score_reader_and_fusion_on_files_written_by_the_reference(golden_dir, tmp_path):
+    """tests/golden/score_files.npz: every 30th video of the score files the reference ships
+    (exp_my/hmdb51_*/split1, written by its own test.py), with the accuracy combine.py's formula
+    gives (tests/golden/make_score_fixture.py)."""
+    import os
+    from dmcnet_b200 import inference as I
+    z = np.load(os.path.join(golden_dir, 'score_files.npz'), allow_pickle=True)
+    files = []
+    for k in z['order']:
+        p = str(tmp_path / ('%s.npz' % k))
+        np.savez(p, scores=z[k + '.scores'], labels=z[k + '.labels'], names=z[k + '.names'])
+        files.append(p)
+    acc, n = I.combine_scores(files, list(z['weights']))
+    assert n == 51 and acc == pytest.approx(float(z['accuracy_subset'][0]), abs=1e-12)
+    # write -> read round trip of a reference file, both flavours (the GAN file has a validity column)
+    for k in ('mv', 'dmc_gan'):
+        cols = z[k + '.scores'].shape[1]
+        assert cols == (3 if k == 'dmc_gan' else 2)
+        names = list(z[k + '.names'])
+        output = [tuple(row) for row in z[k + '.scores']]
+        p = str(tmp_path / ('again_%s.npz' % k))
+        I.save_scores(p, output[::-1], names[::-1])                      # any input order
+        w = np.load(p, allow_pickle=True)
+        assert list(w['names']) == sorted(names) and w['scores'].shape == (51, cols)
+        for a, b in zip(w['scores'], z[k + '.scores'][np.argsort(names, kind='stable')]):
+            assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+            if cols == 3:
+                assert np.array_equal(a[2], b[2]) and a[2].shape == (25, 2)
+        assert I.video_accuracy(output) == pytest.approx(
+            100.0 * np.mean([int(np.argmax(o[0])) == int(o[1]) for o in output]))
+    adv = I.adversarial_accuracy([tuple(row) for row in z['dmc_gan.scores']])
+    assert adv == pytest.approx(100.0 * np.mean([np.argmax(r[2]) for r in z['dmc_gan.scores']]))
+
+
+def test_full_reference_score_files_reproduce_the_published_fusion_accuracy():
+    import os
+    from dmcnet_b200 import inference as I
+    root = '/root/reference/exp_my'
+    if not os.path.isdir(root):
+        pytest.skip('/root/reference not present')
+    expect = {1: 0.6405, 2: 0.6131, 3: 0.6007}                              # SURVEY.md section 6
+    for split, want in expect.items():
+        files = [root + '/hmdb51_coviar/iframe/split%d/iframe_score_model_best.npz' % split,
+                 root + '/hmdb51_coviar/mv/split%d/mv_score_model_best.npz' % split,
+                 root + '/hmdb51_coviar/residual/split%d/residual_score_model_best.npz' % split,
+                 root + '/hmdb51_gan/split%d/mv_score_model_best.npz' % split]
+        acc, n = I.combine_scores(files, [2.0, 1.0, 1.0, 1.0])
+        assert n == 1530 and acc == pytest.approx(want, abs=5e-5)

@@ -176,3 +176,29 @@ def test_step_from_uint8_stack_equals_step_from_float_tensors():
     mo = ref.step(flow, mv, res, target)
     for k in ('loss', 'loss_cls', 'loss_mse'):
         assert mb[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+
+
+def test_video_scorer_gan_flavour_returns_validity(monkeypatch):
+    """code/dmcnet_GAN/test.py: the eval-mode discriminator (Dropout2d off, BatchNorm(eps 0.8) on
+    running statistics) scores the generated map of every frame."""
+    from dmcnet_b200 import inference as I
+    from oracle import video_protocol as V
+    monkeypatch.setattr(I, 'check_crops', lambda c: c)
+    num_class, segs, crops, arch_d = 51, 3, 2, 'Discriminator3'
+    sd = O.build_state(num_class, arch_d, seed=1)
+    g = torch.Generator().manual_seed(6)
+    for k in sd:
+        if k.endswith('running_mean'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    scorer = I.VideoScorer(sd, num_class, segs, crops, arch_d=arch_d)
+    flow, mv, res, target = O.make_inputs(2, 3, num_class, seed=12)
+    mv, res = mv.reshape(1, 6, 2, 224, 224), res.reshape(1, 6, 3, 224, 224)
+    out = scorer.evaluate([(None, mv, res, target[:1])])
+    (s, lab, val), = out
+    r, rv = V.forward_video_gan(sd, mv, res, segs, crops, arch_d)
+    assert lab == int(target[0]) and val.shape == rv.shape == (6, 2)
+    np.testing.assert_allclose(s, r, rtol=1e-3, atol=1e-3 * np.abs(r).max())
+    np.testing.assert_allclose(val, rv, rtol=1e-3, atol=1e-3 * np.abs(rv).max())
+    assert I.adversarial_accuracy(out) == 100.0 * float(np.argmax(rv))
