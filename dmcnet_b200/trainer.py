@@ -173,6 +173,54 @@ class FusedTrainStep:
         self.hyper.copy_(torch.tensor(rows, dtype=torch.float32))
         self._graphs = {}
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def _hyper_rows(self) -> Dict[str, Tuple[float, float]]:
+        rows = self.hyper.cpu().tolist()
+        return {k: (rows[i][0], rows[i][1]) for i, k in enumerate(self.tensor_keys)}
+
+    def checkpoint(self, epoch: int, arch: str = 'resnet18', best_prec1: float = 0.0) -> dict:
+        """The dict the reference passes to ``save_checkpoint`` (code/dmcnet/train.py:190-201; GAN
+        code/dmcnet_GAN/train.py:203-215): ``module.``-prefixed state_dict and one
+        ``torch.optim.Adam.state_dict()`` per optimizer (one param group per tensor), built from
+        the flat buckets -- loadable by the reference's ``--resume`` and by ``resume`` below."""
+        from . import checkpoint as C
+        hp, eng = self.hp, self.eng
+        steps = self.steps.cpu().tolist()
+        rows = self._hyper_rows()
+        mults = (hp.lr_cls_mult, hp.lr_mse_mult, hp.lr_d_mult)
+        out = {'epoch': int(epoch), 'arch': arch,
+               'state_dict': C.add_module_prefix({k: v.cpu() for k, v in eng.state_dict().items()}),
+               'best_prec1': best_prec1}
+        for gi, tag in enumerate(GROUPS):
+            if tag == 'discriminator' and not eng.gan:
+                continue
+            out[C.OPTIMIZER_KEYS[tag]] = C.adam_state_to_torch(eng, tag, int(steps[gi]), rows, mults[gi],
+                                                               hp.betas, hp.eps)
+        return out
+
+    def resume(self, ckpt: dict) -> Tuple[int, float]:
+        """``--resume`` (code/dmcnet/train.py:145-163): model, optimizer moments and step counts.
+        Returns (start_epoch, best_prec1); call ``set_epoch`` with the epoch about to run."""
+        from . import checkpoint as C
+        eng = self.eng
+        eng.load_state(C.strip_first_component(ckpt['state_dict']))       # strict, as train.py:151
+        steps = self.steps.cpu().tolist()
+        for gi, tag in enumerate(GROUPS):
+            key = C.OPTIMIZER_KEYS[tag]
+            if key in ckpt and (tag != 'discriminator' or eng.gan):
+                steps[gi] = C.adam_state_from_torch(eng, tag, ckpt[key])
+        self.steps.copy_(torch.tensor(steps, dtype=torch.int32))
+        return int(ckpt['epoch']), ckpt['best_prec1']
+
+    def warm_start(self, state_dict: Dict[str, torch.Tensor]) -> Tuple[List[str], List[str]]:
+        """``--weights`` (code/dmcnet/train.py:64-68): drop the first key component, then
+        ``load_state_dict(strict=False)``.  Returns (missing_keys, unexpected_keys)."""
+        from . import checkpoint as C
+        cur = self.eng.state_dict()
+        merged, missing, unexpected = C.merge_non_strict(cur, C.strip_first_component(state_dict))
+        self.eng.load_state(merged)
+        return missing, unexpected
+
     # ------------------------------------------------------------------ step pieces
     def _adam(self, groups: Sequence[str]):
         eng, hp = self.eng, self.hp

@@ -239,3 +239,95 @@ def test_full_reference_score_files_reproduce_the_published_fusion_accuracy():
                  root + '/hmdb51_gan/split%d/mv_score_model_best.npz' % split]
         acc, n = I.combine_scores(files, [2.0, 1.0, 1.0, 1.0])
         assert n == 1530 and acc == pytest.approx(want, abs=5e-5)
+
+
+# ------------------------------------------------------------------ checkpoint / resume format
+class _Bucket:
+    """CPU stand-in for the engine's flat parameter table (specs / offsets / moment buckets)."""
+
+    def __init__(self, state):
+        from collections import OrderedDict
+        self.specs = OrderedDict((k, tuple(v.shape)) for k, v in state.items() if not O.is_buffer(k))
+        self.offsets, off = {}, 0
+        for tag in ('base_model', 'gen_flow_model', 'discriminator'):
+            for k, shp in self.specs.items():
+                if k.startswith(tag):
+                    self.offsets[k] = off
+                    off += (int(np.prod(shp)) + 63) // 64 * 64
+        self.exp_avg, self.exp_avg_sq = torch.zeros(off), torch.zeros(off)
+
+
+def test_optimizer_state_round_trips_through_the_torch_adam_format():
+    """The reference checkpoints torch.optim.Adam.state_dict() of one-group-per-tensor optimizers
+    (code/dmcnet_GAN/train.py:122-153, :203-215).  Oracle optimizers after real steps -> flat
+    buckets -> torch format again: identical, and loadable by a fresh torch Adam."""
+    from dmcnet_b200 import checkpoint as C
+    arch_d = 'Discriminator'
+    sd = O.build_state(51, arch_d, seed=1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    ref = O.OracleTrainer(sd, O.HParams(), gan=True, arch_d=arch_d)
+    for it in range(2):                                              # D-step then G-step
+        torch.manual_seed(100 + it)
+        ref.step(flow, mv, res, target, masks=O.draw_dropout_masks(arch_d, 3 * (2 if it % 2 == 0 else 1)))
+    bucket = _Bucket(sd)
+    hp = O.HParams()
+    for tag, opt, mult in (('base_model', ref.opt_cls, hp.lr_cls_mult), ('gen_flow_model', ref.opt_gf, hp.lr_mse_mult),
+                           ('discriminator', ref.opt_d, hp.lr_d_mult)):
+        want = opt.state_dict()
+        step = C.adam_state_from_torch(bucket, tag, want)
+        assert step == 1                                             # each optimizer stepped once
+        keys = C.group_keys(bucket.specs, tag)
+        assert len(keys) == len(want['param_groups']) == {'base_model': 62, 'gen_flow_model': 12,
+                                                          'discriminator': 16}[tag]
+        rows = {k: (g['lr'], g['weight_decay']) for k, g in zip(keys, want['param_groups'])}
+        got = C.adam_state_to_torch(bucket, tag, step, rows, mult, hp.betas, hp.eps)
+        assert sorted(got['state']) == sorted(want['state'])
+        for i in want['state']:
+            assert float(got['state'][i]['step']) == float(want['state'][i]['step'])
+            assert torch.equal(got['state'][i]['exp_avg'], want['state'][i]['exp_avg'])
+            assert torch.equal(got['state'][i]['exp_avg_sq'], want['state'][i]['exp_avg_sq'])
+        for g, w in zip(got['param_groups'], want['param_groups']):
+            for f in ('lr', 'betas', 'eps', 'weight_decay', 'amsgrad', 'lr_mult', 'decay_mult', 'params'):
+                assert g[f] == w[f] or tuple(g[f]) == tuple(w[f]), (tag, f)
+        # a fresh optimizer wired as the reference's accepts the produced dict and reproduces it
+        params = [{'params': torch.zeros(bucket.specs[k], requires_grad=True), 'lr': hp.lr, 'lr_mult': mult,
+                   'decay_mult': 0.0 if 'bias' in k else 1.0} for k in keys]
+        fresh = torch.optim.Adam(params, weight_decay=hp.weight_decay, eps=hp.eps)
+        fresh.load_state_dict(got)
+        again = fresh.state_dict()
+        assert torch.equal(again['state'][0]['exp_avg'], want['state'][0]['exp_avg'])
+        assert [g['lr'] for g in again['param_groups']] == [g['lr'] for g in want['param_groups']]
+    # a never-stepped optimizer has no state entries
+    assert C.adam_state_to_torch(bucket, 'gen_flow_model', 0, rows_all(bucket), 1.0)['state'] == {}
+    with pytest.raises(ValueError, match='parameters'):
+        C.adam_state_from_torch(bucket, 'gen_flow_model', ref.opt_cls.state_dict())
+
+
+def rows_all(bucket):
+    return {k: (0.01, 1e-4) for k in bucket.specs}
+
+
+def test_checkpoint_file_names_prefix_handling_and_warm_start(tmp_path):
+    from dmcnet_b200 import checkpoint as C
+    assert C.checkpoint_names('exp/run1/hmdb51', 'MV') == ('exp/run1/hmdb51_mv_checkpoint.pth.tar',
+                                                          'exp/run1/hmdb51_mv_model_best.pth.tar')   # train.py:372-377
+    sd = O.build_state(51, None, seed=1)
+    wrapped = C.add_module_prefix(sd)
+    assert all(k.startswith('module.') for k in wrapped)
+    assert list(C.strip_first_component(wrapped)) == list(sd)
+    state = {'epoch': 3, 'arch': 'resnet18', 'state_dict': wrapped, 'best_prec1': 12.5}
+    path = C.save_checkpoint(state, True, str(tmp_path / 'm'), 'mv')
+    best = C.checkpoint_names(str(tmp_path / 'm'), 'mv')[1]
+    a, b = C.load_checkpoint(path), C.load_checkpoint(best)
+    assert a['epoch'] == b['epoch'] == 3 and torch.equal(a['state_dict']['module.base_model.fc.bias'],
+                                                         sd['base_model.fc.bias'])
+    # --weights: stage-2 (GAN) model warm-started from a stage-1 checkpoint (no discriminator keys)
+    gan = O.build_state(51, 'Discriminator3', seed=2)
+    merged, missing, unexpected = C.merge_non_strict(gan, C.strip_first_component(wrapped))
+    assert all(k.startswith('discriminator') for k in missing) and unexpected == []
+    assert torch.equal(merged['base_model.conv1.weight'], sd['base_model.conv1.weight'])
+    assert torch.equal(merged['discriminator.adv_layer.bias'], gan['discriminator.adv_layer.bias'])
+    bad = dict(sd)
+    bad['base_model.fc.weight'] = torch.zeros(101, 512)
+    with pytest.raises(RuntimeError, match='size mismatch'):
+        C.merge_non_strict(gan, bad)
