@@ -386,6 +386,27 @@ class FusedTrainStep:
         self.iteration += 1
         return self.read_metrics(mode) if metrics else {}
 
+    def validate_batch(self, input_flow, input_mv, input_residual, target) -> Dict[str, float]:
+        """One iteration of ``validate`` (code/dmcnet/train.py:296-347; GAN
+        code/dmcnet_GAN/train.py:414-459): eval-mode forward (BatchNorm running statistics, no
+        dropout), consensus + CE + top-k, the flow criterion and -- GAN -- the adversarial CE of the
+        generated maps against "valid".  No gradients, no parameter or statistic is modified."""
+        eng, hp, B, n = self.eng, self.hp, self.B, self.eng.N
+        self.load_inputs(input_flow, input_mv, input_residual, target)
+        eng.forward(self.in_mv, self.in_res, None, train=False)
+        ops.ce_head(eng.logits, B, self.S, eng.num_class, self.target, 0.0, self.consensus, None,
+                    self.ce_stats)
+        numel, frame = n * 2 * eng.H * eng.W, 2 * eng.H * eng.W
+        if self.flow_kind == 0:
+            ops.mse_head(eng.gen_flow, self.in_flow, numel, 0.0, None, self.mse_sum, frame_elems=frame,
+                         dgen_ns=frame)
+        else:
+            ops.flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, numel, 0.0, None, self.mse_sum,
+                               frame_elems=frame, dgen_ns=frame)
+        if eng.gan:
+            ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, 0.0, None, None, self.adv_stats)
+        return self.read_metrics('G' if eng.gan else 'full')
+
     # ------------------------------------------------------------------ pipelined API
     def step_pipelined(self, input_flow, input_mv, input_residual, target,
                        masks: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, float]:

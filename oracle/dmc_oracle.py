@@ -434,6 +434,37 @@ class OracleTrainer:
         return out
 
 
+def validate_batch(state: Dict[str, Tensor], hp: HParams, input_flow: Tensor, input_mv: Tensor,
+                   input_residual: Tensor, target: Tensor, *, gan: bool = False,
+                   arch_d: Optional[str] = None) -> Dict[str, float]:
+    """One iteration of ``validate``: code/dmcnet/train.py:309-347 (``gan=False``) and
+    code/dmcnet_GAN/train.py:417-459 (``gan=True``; it reports no total loss, the sum below is
+    the G-step weighting of :355 for convenience)."""
+    S = hp.num_segments
+    st = {k: v.detach() for k, v in state.items()}
+    flow = input_flow.reshape((-1,) + tuple(input_mv.shape[-3:]))
+    crit = flow_criterion(hp.loss_mse)
+    out: Dict[str, float] = {}
+    with torch.no_grad():
+        if not gan:
+            output, gen_flow = model_forward(st, input_mv, input_residual, train=False)
+        else:
+            output, validity, gen_flow = model_forward(st, input_mv, input_residual, None, gan=True,
+                                                       arch_d=arch_d, train=False)
+        output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)
+        loss_cls = F.cross_entropy(output, target)
+        loss_mse = crit(gen_flow, flow)
+        loss = loss_cls * hp.lr_cls + loss_mse * hp.lr_mse
+        if gan:
+            valid = torch.cat([target.clone().fill_(1)] * S, 0)                 # GAN/train.py:442
+            loss_adv = F.cross_entropy(validity, valid)
+            loss = loss + loss_adv * hp.lr_adv_g
+            out.update(loss_adv=float(loss_adv), acc_adv=accuracy(validity, valid)[0])
+    prec1, prec5 = accuracy(output, target, topk=(1, 5))
+    out.update(loss=float(loss), loss_cls=float(loss_cls), loss_mse=float(loss_mse), prec1=prec1, prec5=prec5)
+    return out
+
+
 def infer_video_scores(state: Dict[str, Tensor], input_mv: Tensor, input_residual: Tensor,
                        segments: int) -> Tensor:
     """Inference flavour (BASELINE config 1): code/dmcnet/test.py:139-151 --

@@ -331,3 +331,59 @@ def test_checkpoint_file_names_prefix_handling_and_warm_start(tmp_path):
     bad['base_model.fc.weight'] = torch.zeros(101, 512)
     with pytest.raises(RuntimeError, match='size mismatch'):
         C.merge_non_strict(gan, bad)
+
+
+# ------------------------------------------------------------------ epoch driver (host logic)
+class _FakeStep:
+    """Records what the epoch driver asks of the fused step."""
+
+    def __init__(self, precs):
+        self.calls, self.precs, self.epoch = [], list(precs), None
+
+    def set_epoch(self, epoch, epoch_thre=0):
+        self.calls.append(('set_epoch', epoch, epoch_thre))
+        self.epoch = epoch
+
+    def step(self, flow, mv, res, target):
+        self.calls.append(('step', self.epoch))
+        return {'loss': 2.0, 'loss_cls': 1.0, 'loss_mse': 0.1, 'prec1': 50.0, 'prec5': 100.0}
+
+    def validate_batch(self, flow, mv, res, target):
+        self.calls.append(('val', self.epoch))
+        return {'loss': 1.0, 'loss_cls': 1.0, 'loss_mse': 0.0, 'prec1': self.precs[self.epoch], 'prec5': 100.0}
+
+    def checkpoint(self, epoch, arch, best_prec1):
+        self.calls.append(('ckpt', epoch, best_prec1))
+        return {'epoch': epoch, 'arch': arch, 'state_dict': {}, 'best_prec1': best_prec1}
+
+
+def test_epoch_driver_follows_the_reference_schedule(tmp_path):
+    """main() of code/dmcnet/train.py:173-201: set lr per epoch, validate when epoch % eval_freq == 0
+    or on the last epoch, save when best or epoch % SAVE_FREQ == 0, 'epoch' stored as epoch + 1."""
+    import os
+    from dmcnet_b200 import loop as L
+    from dmcnet_b200 import checkpoint as C
+    batch = (None, None, None, torch.zeros(4, dtype=torch.int64))
+    step = _FakeStep(precs=[10.0, 0.0, 30.0, 0.0, 20.0, 25.0])
+    lines = []
+    best = L.fit(step, [batch] * 3, [batch] * 2, epochs=6, eval_freq=2, epoch_thre=1,
+                 model_prefix=str(tmp_path / 'hmdb51'), representation='mv', log=lines.append)
+    assert best == 30.0
+    assert [c for c in step.calls if c[0] == 'set_epoch'] == [('set_epoch', e, 1) for e in range(6)]
+    assert [c[1] for c in step.calls if c[0] == 'val'] == [0, 0, 2, 2, 4, 4, 5, 5]       # epochs 0, 2, 4 and the last
+    # epoch 0: best (10 > 0) and 0 % 40 == 0; epoch 2: best (30); epochs 4, 5: neither
+    assert [c for c in step.calls if c[0] == 'ckpt'] == [('ckpt', 1, 10.0), ('ckpt', 3, 30.0)]
+    ck, best_file = C.checkpoint_names(str(tmp_path / 'hmdb51'), 'mv')
+    assert C.load_checkpoint(ck)['epoch'] == 3 and C.load_checkpoint(best_file)['best_prec1'] == 30.0
+    assert lines[0] == 'current epoch freeze?: True' and 'current epoch freeze?: False' in lines
+    assert sum(l.startswith('Testing Results: Prec@1') for l in lines) == 4
+    m = L.AverageMeter()
+    m.update(2.0, 3); m.update(4.0, 1)
+    assert (m.val, m.sum, m.count, m.avg) == (4.0, 10.0, 4, 2.5)                          # train.py:380-395
+    # GAN: D-step and G-step metrics are averaged separately
+    class _Gan(_FakeStep):
+        def step(self, flow, mv, res, target):
+            self.k = getattr(self, 'k', 0) + 1
+            return {'loss': 1.0, 'loss_adv': 0.5} if self.k % 2 else {'loss': 3.0, 'loss_adv': 0.7, 'loss_mse': 0.2}
+    avg = L.train_epoch(_Gan([]), [batch] * 4, 0, gan=True, log=lines.append)
+    assert avg['D_loss'] == 1.0 and avg['G_loss'] == 3.0 and avg['G_loss_mse'] == pytest.approx(0.2) and 'D_loss_mse' not in avg

@@ -290,3 +290,63 @@ def test_gan_stage_warm_starts_from_a_stage1_checkpoint():
     for k in now:
         want = gan_sd[k] if k.startswith('discriminator') else stage1[k]
         assert torch.equal(now[k].cpu(), want.to(now[k].dtype)), k
+
+
+# ------------------------------------------------------------------ validate() and the epoch driver
+@pytest.mark.parametrize('arch_d,loss_mse', [(None, 'MSELoss'), (None, 'SmoothL1Loss'), ('Discriminator', 'MSELoss')])
+def test_validate_batch_vs_oracle(arch_d, loss_mse):
+    """validate() of code/dmcnet/train.py:296-347 / code/dmcnet_GAN/train.py:403-459: eval-mode batch,
+    nothing is updated."""
+    gan = arch_d is not None
+    batch, num_class = 2, 51
+    sd = O.build_state(num_class, arch_d, seed=1)
+    g = torch.Generator().manual_seed(8)
+    for k in sd:
+        if k.endswith('running_mean'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=3)
+    mo = O.validate_batch(sd, O.HParams(loss_mse=loss_mse), flow, mv, res, target, gan=gan, arch_d=arch_d)
+    eng = DmcEngine(num_class, 3, batch * 3, gan=gan, arch_d=arch_d)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(loss_mse=loss_mse), batch)
+    before = eng.state_dict()
+    mg = tr.validate_batch(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+    assert set(mg) == set(mo)
+    for k in mo:
+        if k in ('prec1', 'prec5', 'acc_adv'):
+            assert mg[k] == pytest.approx(mo[k], abs=1e-9), k
+        else:
+            assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+    after = eng.state_dict()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    assert tr.steps.cpu().tolist() == [0, 0, 0]
+
+
+def test_epoch_driver_on_the_engine(tmp_path):
+    """fit(): two epochs of two batches, validation, checkpoint in the reference format, resume."""
+    from dmcnet_b200 import loop as L
+    from dmcnet_b200 import checkpoint as C
+    batch, num_class = 1, 51
+    sd = O.build_state(num_class, None, seed=1)
+    data = [O.make_inputs(batch, 3, num_class, seed=s) for s in (0, 1)]
+    eng = DmcEngine(num_class, 3, batch * 3)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(lr_steps=(1,)), batch)
+    lines = []
+    best = L.fit(tr, data, data[:1], epochs=2, eval_freq=1, epoch_thre=1, model_prefix=str(tmp_path / 'x'),
+                 log=lines.append)
+    assert tr.steps.cpu().tolist() == [2, 4, 0]          # epoch 0 frozen: only the generator stepped
+    assert 0.0 <= best <= 100.0 and any(l.startswith('Testing Results') for l in lines)
+    ck = C.load_checkpoint(C.checkpoint_names(str(tmp_path / 'x'), 'mv')[0])
+    if ck['epoch'] == 1:       # saved after epoch 0 (0 % SAVE_FREQ == 0); epoch 1 did not improve Prec@1
+        assert float(ck['optimizer_gf']['state'][0]['step']) == 2.0
+        assert ck['optimizer_cls']['state'] == {} and ck['optimizer_cls']['param_groups'][0]['lr'] == 0.0
+    else:                      # epoch 1 was the best so far and overwrote the file
+        assert ck['epoch'] == 2 and ck['best_prec1'] == best
+        assert float(ck['optimizer_gf']['state'][0]['step']) == 4.0
+        assert float(ck['optimizer_cls']['state'][0]['step']) == 2.0
+    # epoch 1 ran at the decayed rate (lr_steps=(1,)): lr * lr_decay * lr_mse_mult
+    assert float(tr.hyper[len(C.group_keys(eng.specs, 'base_model')), 0]) == pytest.approx(0.01 * 0.1)
