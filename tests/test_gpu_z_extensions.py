@@ -234,14 +234,19 @@ def test_checkpoint_resumes_on_the_oracle_and_back(tmp_path):
     assert len(ck['optimizer_cls']['param_groups']) == 62 and len(ck['optimizer_gf']['param_groups']) == 12
     assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0
 
-    # (1) the oracle (torch.optim.Adam) resumes from our file
-    ref = O.OracleTrainer(C.strip_first_component(ck['state_dict']), O.HParams(), gan=False)
-    ref.opt_cls.load_state_dict(ck['optimizer_cls'])
-    ref.opt_gf.load_state_dict(ck['optimizer_gf'])
+    # (1) the oracle (torch.optim.Adam) resumes from our file.  torch's load_state_dict keeps the
+    # tensors it is given (no copy) and Adam then updates them in place, so the oracle gets its own
+    # read of the file
+    ck_for_oracle = C.load_checkpoint(path)
+    ref = O.OracleTrainer(C.strip_first_component(ck_for_oracle['state_dict']), O.HParams(), gan=False)
+    ref.opt_cls.load_state_dict(ck_for_oracle['optimizer_cls'])
+    ref.opt_gf.load_state_dict(ck_for_oracle['optimizer_gf'])
     mo = ref.step(flow, mv, res, target)
+    assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0          # our copy is untouched
     # (2) a fresh engine resumes from the same file
     eng2, tr2 = engine_trainer(state={k: torch.zeros_like(v) if v.is_floating_point() else v for k, v in sd.items()})
     assert tr2.resume(ck) == (1, 3.0)
+    assert tr2.steps.cpu().tolist() == [1, 1, 0]
     m2 = tr2.step(*dev(flow, mv, res, target))
     # (3) the original engine simply continues
     m1 = tr.step(*dev(flow, mv, res, target))
