@@ -256,8 +256,8 @@ def test_checkpoint_resumes_on_the_oracle_and_back(tmp_path):
     after_o = ref.state_dict()
     a1, a2 = eng.state_dict(), eng2.state_dict()
     for k in a1:
-        if k.startswith('gen_flow_model'):                     # plain fp32 path: tight
-            assert rel(a2[k], a1[k]) < 1e-5, k
+        if k.startswith('gen_flow_model'):     # same state, same batch: only fp32-atomic ordering differs
+            assert rel(a2[k], a1[k]) < 1e-4, k
             assert rel(a2[k], after_o[k]) < 1e-3, k
     st = ref.opt_gf.state_dict()['state'][0]
     ck2 = tr2.checkpoint(epoch=2)
