@@ -104,7 +104,7 @@ class DmcEngine:
     def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
-                 grad_bf16: bool = False):
+                 grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -113,6 +113,12 @@ class DmcEngine:
         self.num_class, self.S, self.N = num_class, num_segments, frames
         self.gan, self.arch_d = gan, (arch_d if gan else None)
         self.gen_flow_or_delta = gen_flow_or_delta
+        # channels added by each of the five dense layers: (8,8,6,4,2) = EstimatorDenseNetTiny, the
+        # shipped recipe; (32,32,24,16,8) = ...Small and (128,128,96,64,32) = EstimatorDenseNet share
+        # the structure (code/dmcnet/model.py:122-194) and the kernels
+        self.gen_growth = tuple(int(g) for g in gen_growth)
+        if len(self.gen_growth) != 5 or min(self.gen_growth) < 1:
+            raise ValueError('gen_growth must list the widths of the five dense layers')
         self.H, self.W = height, width
         self.gemm_engine = gemm_engine
         # grad_bf16=True: the backward GEMMs (data and weight gradients of the ResNet convs) read
@@ -171,7 +177,7 @@ class DmcEngine:
         specs['base_model.fc.weight'] = (C, 512)
         specs['base_model.fc.bias'] = (C,)
         cin = GEN_IN
-        for k, g in enumerate(GEN_GROWTH):
+        for k, g in enumerate(self.gen_growth):
             specs['gen_flow_model.conv_%d.0.weight' % k] = (g, cin, 3, 3)
             specs['gen_flow_model.conv_%d.0.bias' % k] = (g,)
             cin += g
@@ -265,7 +271,7 @@ class DmcEngine:
     # ------------------------------------------------------------------ allocation
     def _alloc_generator(self):
         dev, N, H, W = self.device, self.N, self.H, self.W
-        self.gen_ctot = GEN_IN + sum(GEN_GROWTH)                      # 33
+        self.gen_ctot = GEN_IN + sum(self.gen_growth)                      # 33
         self.X = torch.zeros(N, self.gen_ctot, H, W, dtype=torch.float32, device=dev)
         # gradient buffer of the dense block: [d gen_flow (2) | new4 new3 new2 new1 new0 (28)];
         # the gradient of one slice is a single convolution over ALL channels in front of it
@@ -274,23 +280,23 @@ class DmcEngine:
         self.gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
         # channel offset of each layer's OUTPUT inside X: new channels are prepended
         outs, off = [], self.gen_ctot - GEN_IN
-        for g in GEN_GROWTH:
+        for g in self.gen_growth:
             off -= g
             outs.append(off)
         self.gen_out_off = outs                                          # [20, 12, 6, 2, 0]
-        self.gen_in_off = [o + g for o, g in zip(outs, GEN_GROWTH)]      # [28, 20, 12, 6, 2]
+        self.gen_in_off = [o + g for o, g in zip(outs, self.gen_growth)]      # [28, 20, 12, 6, 2]
         self.mv_off = self.gen_ctot - GEN_IN                             # 28
         self.wflip = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=dev)   # dgrad weight scratch
         # combined (flipped, transposed) dgrad weights of the generator slices, see _gen_backward
-        table, off = [len(GEN_GROWTH)], 0
+        table, off = [len(self.gen_growth)], 0
         self.gen_wc_off = []
-        L = len(GEN_GROWTH)
+        L = len(self.gen_growth)
         for k in reversed(range(L)):                    # slices new4 .. new0
-            gk, xk = GEN_GROWTH[k], self.gen_out_off[k]
+            gk, xk = self.gen_growth[k], self.gen_out_off[k]
             cin_s = 2 + xk
             segs = [(0, 2, self.offsets['gen_flow_model.predict_flow.weight'], self.gen_ctot, xk)]
             for j in range(L - 1, k, -1):               # later dense layers j > k
-                segs.append((2 + self.gen_out_off[j], GEN_GROWTH[j],
+                segs.append((2 + self.gen_out_off[j], self.gen_growth[j],
                              self.offsets['gen_flow_model.conv_%d.0.weight' % j],
                              self.gen_ctot - self.gen_in_off[j], xk - self.gen_in_off[j]))
             row = [off, gk, cin_s, len(segs)]
@@ -423,7 +429,7 @@ class DmcEngine:
         ns = self.gen_ctot * HW
         ops.copy_planar(mv, 2 * HW, X[self.mv_off * HW:], ns, 2 * HW, n)
         ops.copy_planar(res, 3 * HW, X[(self.mv_off + 2) * HW:], ns, 3 * HW, n)
-        for k, g in enumerate(GEN_GROWTH):
+        for k, g in enumerate(self.gen_growth):
             cin = self.gen_ctot - self.gen_in_off[k]
             ops.conv_fwd(X[self.gen_in_off[k] * HW:], ns, cin, H, W,
                          self.p('gen_flow_model.conv_%d.0.weight' % k),
@@ -440,12 +446,12 @@ class DmcEngine:
         HW = H * W
         X, dD = self.X.view(-1), self.dD.view(-1)
         ns, dns = self.gen_ctot * HW, self.dD.shape[1] * HW
-        L = len(GEN_GROWTH)
+        L = len(self.gen_growth)
         ops.dense_dgrad_weights(self.params, self.gen_wc_table, self.gen_wc)
         wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
         ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dD, dns, 2, 3, 1, self.g(wk), self.g(bk), n)
         for idx, k in enumerate(reversed(range(L))):
-            g = GEN_GROWTH[k]
+            g = self.gen_growth[k]
             oo, io = self.gen_out_off[k], self.gen_in_off[k]
             cin_s = 2 + oo                                   # d gen_flow + every later slice
             wc = self.gen_wc[self.gen_wc_off[idx]:self.gen_wc_off[idx] + g * cin_s * 9]

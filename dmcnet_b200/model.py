@@ -46,20 +46,95 @@ def predict_flow(in_planes):
     return nn.Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1, bias=True)
 
 
-class EstimatorDenseNetTiny(nn.Module):
-    """Parameter container with the reference's names (code/dmcnet/model.py:172-194).
-    The computation is done by the fused engine, not by these torch modules."""
+# growth of the dense estimators (new channels per layer): code/dmcnet/model.py:122-194
+DENSE_GROWTH = {'DenseNetTiny': GEN_GROWTH, 'DenseNetSmall': (32, 32, 24, 16, 8),
+                'DenseNet': (128, 128, 96, 64, 32)}
 
-    def __init__(self, ch_in):
+
+class _EstimatorShell(nn.Module):
+    """Generators are parameter containers with the reference's names; the computation is done
+    by the fused engine, never by torch modules (no PyTorch fallback)."""
+
+    def forward(self, x):  # pragma: no cover
+        raise NotImplementedError('%s runs inside dmcnet_b200.engine.DmcEngine' % type(self).__name__)
+
+
+class EstimatorDense(_EstimatorShell):
+    """EstimatorDenseNet / ...Small / ...Tiny (code/dmcnet/model.py:122-194): five dense-connected
+    3x3 convs ``conv_k`` then ``predict_flow``; only the growth table differs."""
+
+    def __init__(self, ch_in, growth=GEN_GROWTH):
         super().__init__()
         cin = ch_in
-        for k, g in enumerate(GEN_GROWTH):
+        for k, g in enumerate(growth):
             setattr(self, 'conv_%d' % k, conv(cin, g))
             cin += g
         self.predict_flow = predict_flow(cin)
 
-    def forward(self, x):  # pragma: no cover - the product path never calls torch convs
-        raise NotImplementedError('EstimatorDenseNetTiny runs inside dmcnet_b200.engine.DmcEngine')
+
+class EstimatorDenseNetTiny(EstimatorDense):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, DENSE_GROWTH['DenseNetTiny'])
+
+
+class EstimatorDenseNetTinyEarlyFusion(_EstimatorShell):
+    """...EarlyFusionSum / ...EarlyFusionStack (code/dmcnet/model.py:197-250): separate first convs
+    for the motion vectors and the residual, summed (8 channels) or stacked (16)."""
+
+    def __init__(self, ch_in, stack):
+        super().__init__()
+        self.conv_0_mv = conv(2, 8)
+        self.conv_0_r = conv(3, 8)
+        dd = 16 if stack else 8
+        for k, g in zip((1, 2, 3, 4), (8, 6, 4, 2)):
+            setattr(self, 'conv_%d' % k, conv(dd, g))
+            dd += g
+        self.predict_flow = predict_flow(dd)
+
+
+def conv_dilation(in_planes, out_planes, dilation):
+    """code/dmcnet/model.py:31-42 with batch_norm=True (the only way Model builds it, :312-314)."""
+    return nn.Sequential(
+        nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=1, dilation=dilation, padding=dilation,
+                  bias=False),
+        nn.BatchNorm2d(out_planes), nn.LeakyReLU(0.1, inplace=True))
+
+
+class ContextNetwork(_EstimatorShell):
+    """ContextNetwork / ContextNetworkAtt (code/dmcnet/model.py:45-104): dilated 3x3 conv + BN +
+    LeakyReLU(0.1) stack 5-32-128-128-96-64-32(-2); dilation 16 of the fifth layer drops to 1 when
+    the generator runs on a down-sampled input; ``att`` splits the head into flow and attention."""
+
+    def __init__(self, ch_in, gen_flow_ds_factor=0, att=False):
+        super().__init__()
+        widths = (32, 128, 128, 96, 64, 32) + (() if att else (2,))
+        dil = (1, 2, 4, 8, 16 if gen_flow_ds_factor == 0 else 1, 1, 1)
+        layers, cin = [], ch_in
+        for w, d in zip(widths, dil):
+            layers.append(conv_dilation(cin, w, d))
+            cin = w
+        self.conv_context = nn.Sequential(*layers)
+        if att:
+            self.predict_flow = conv_dilation(32, 2, 1)
+            self.predict_att = nn.Sequential(conv_dilation(32, 2, 1), nn.ReLU(inplace=True))
+
+
+def build_estimator(arch_estimator, ch_in, gen_flow_ds_factor=0, att=0):
+    """The selection of code/dmcnet/model.py:310-325 (GAN: code/dmcnet_GAN/model.py:501-517).  The
+    dmcnet variant tests ``arch_estimator is 'ContextNetwork'`` (identity, :311), which only holds
+    for the default argument; equality is used here, as the GAN variant does.  An unknown string
+    returns None: the attribute stays undefined, as in the reference."""
+    if arch_estimator == 'ContextNetwork':
+        if att not in (0, 1):
+            return None
+        return ContextNetwork(ch_in, gen_flow_ds_factor, att=bool(att))
+    if arch_estimator in DENSE_GROWTH:
+        return EstimatorDense(ch_in, DENSE_GROWTH[arch_estimator])
+    if arch_estimator == 'DenseNetTinyEarlyFusionSum':
+        return EstimatorDenseNetTinyEarlyFusion(ch_in, stack=False)
+    if arch_estimator == 'DenseNetTinyEarlyFusionStack':
+        return EstimatorDenseNetTinyEarlyFusion(ch_in, stack=True)
+    return None
 
 
 def discriminator_block(in_filters, out_filters, stride, bn):
@@ -167,15 +242,17 @@ Initializing model:
             self._input_size = 224
         else:
             raise ValueError('Unknown base model: {}'.format(base_model))
-        ch_in = 5 * self.new_length
-        if self.arch_estimator == 'DenseNetTiny':
-            self.gen_flow_model = EstimatorDenseNetTiny(ch_in)
+        gen = build_estimator(self.arch_estimator, 5, self.gen_flow_ds_factor, self.att)
+        if gen is not None:
+            self.gen_flow_model = gen
         if self.arch_d is not None and self.arch_d in DISCRIMINATORS:
             self.discriminator = _Discriminator(self.arch_d)
 
     def _prepare_tsn(self, num_class):
         feature_dim = self.base_model.fc.in_features
         self.base_model.fc = nn.Linear(feature_dim, num_class)
+        if self.gen_flow_ds_factor != 0:                     # parameter-free (model.py:326-327)
+            self.downsample = nn.AvgPool2d(self.gen_flow_ds_factor, stride=self.gen_flow_ds_factor)
         if self._representation in ('mv', 'flow'):
             self.base_model.conv1 = nn.Conv2d(2 * self.new_length, 64, kernel_size=(7, 7), stride=(2, 2),
                                               padding=(3, 3), bias=False)
@@ -186,15 +263,18 @@ Initializing model:
 
     # -- engine plumbing
     def _native_supported(self) -> bool:
-        return (self._base_name == 'resnet18' and self.arch_estimator == 'DenseNetTiny'
+        return (self._base_name == 'resnet18' and self.arch_estimator in DENSE_GROWTH
                 and self._representation == 'mv' and self.new_length == 1 and self.att == 0
                 and self.gen_flow_ds_factor == 0)
 
     def _engine_for(self, input_mv) -> DmcEngine:
+        if not hasattr(self, 'gen_flow_model'):
+            raise AttributeError("'%s' object has no attribute 'gen_flow_model'" % type(self).__name__)
         if not self._native_supported():
             raise NotImplementedError(
-                'dmcnet_b200 runs base_model=resnet18, arch_estimator=DenseNetTiny, representation=mv '
-                'natively; this configuration has no kernels (and there is no PyTorch fallback)')
+                'dmcnet_b200 runs base_model=resnet18, arch_estimator=DenseNetTiny (also DenseNetSmall / '
+                'DenseNet, same kernels), representation=mv, att=0, gen_flow_ds_factor=0 natively; this '
+                'configuration has no kernels (and there is no PyTorch fallback)')
         if not input_mv.is_cuda:
             raise RuntimeError('dmcnet_b200: inputs must be CUDA tensors (no CPU path exists)')
         H, W = input_mv.shape[-2], input_mv.shape[-1]
@@ -204,7 +284,7 @@ Initializing model:
             gan = getattr(self, 'discriminator', None) is not None
             eng = DmcEngine(self._num_class, self.num_segments, n, gan=gan, arch_d=self.arch_d,
                             gen_flow_or_delta=self.gen_flow_or_delta, height=H, width=W,
-                            device=input_mv.device)
+                            device=input_mv.device, gen_growth=DENSE_GROWTH[self.arch_estimator])
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith('data_bn')}
             eng.load_state(sd)
             # parameters and buffers become views of the engine's storage
@@ -269,12 +349,12 @@ class GANModel(DmcModel):
                          gen_flow_or_delta, gen_flow_ds_factor, arch_estimator, arch_d, att)
 
 
-def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int] = 1
-                ) -> "OrderedDict[str, torch.Tensor]":
+def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int] = 1,
+                arch_estimator: str = 'DenseNetTiny') -> "OrderedDict[str, torch.Tensor]":
     """state_dict of a freshly constructed Model (random init under ``seed``)."""
     if seed is not None:
         torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
-        m = DmcModel(num_class, 3, 'mv', base_model='resnet18', arch_estimator='DenseNetTiny',
+        m = DmcModel(num_class, 3, 'mv', base_model='resnet18', arch_estimator=arch_estimator,
                      gen_flow_or_delta=1, use_databn=0, arch_d=arch_d)
     return OrderedDict((k, v.detach().clone()) for k, v in m.state_dict().items())

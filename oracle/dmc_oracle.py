@@ -41,6 +41,9 @@ Tensor = torch.Tensor
 # predict_flow -> 2).  Each conv sees cat(new_k-1, ..., new_0, mv, res).
 GEN_TINY_GROWTH = (8, 8, 6, 4, 2)
 GEN_CH_IN = 5
+# EstimatorDenseNetSmall (:147-169) and EstimatorDenseNet (:122-144): same structure, wider layers
+DENSE_GROWTH = {'DenseNetTiny': GEN_TINY_GROWTH, 'DenseNetSmall': (32, 32, 24, 16, 8),
+                'DenseNet': (128, 128, 96, 64, 32)}
 
 # ResNet-18 = torchvision BasicBlock x (2,2,2,2), widths 64..512
 RESNET18_STAGES = ((64, 1), (128, 2), (256, 2), (512, 2))
@@ -74,8 +77,8 @@ def disc_fc_in(arch_d: str) -> int:
 # parameter construction  (same RNG consumption order as the reference ctor)
 # --------------------------------------------------------------------------
 
-def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int] = 1
-                ) -> "OrderedDict[str, Tensor]":
+def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int] = 1,
+                arch_estimator: str = 'DenseNetTiny') -> "OrderedDict[str, Tensor]":
     """state_dict of ``Model(num_class, S, 'mv', 'resnet18', arch_estimator=
     'DenseNetTiny'[, arch_d=...], use_databn=0)`` with random init.
 
@@ -92,7 +95,7 @@ def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int
     base = torchvision.models.resnet18(weights=None)
     gen = OrderedDict()
     cin = GEN_CH_IN
-    for k, g in enumerate(GEN_TINY_GROWTH):
+    for k, g in enumerate(DENSE_GROWTH[arch_estimator]):
         gen['conv_%d.0' % k] = nn.Conv2d(cin, g, 3, 1, 1, bias=True)      # model.py:111-115
         cin += g
     gen['predict_flow'] = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)           # model.py:118-119

@@ -387,3 +387,97 @@ def test_epoch_driver_follows_the_reference_schedule(tmp_path):
             return {'loss': 1.0, 'loss_adv': 0.5} if self.k % 2 else {'loss': 3.0, 'loss_adv': 0.7, 'loss_mse': 0.2}
     avg = L.train_epoch(_Gan([]), [batch] * 4, 0, gan=True, log=lines.append)
     assert avg['D_loss'] == 1.0 and avg['G_loss'] == 3.0 and avg['G_loss_mse'] == pytest.approx(0.2) and 'D_loss_mse' not in avg
+
+
+# ------------------------------------------------------------------ generator choices (constructors)
+GEN_CASES = [('ContextNetwork', 0, 0), ('ContextNetwork', 1, 0), ('ContextNetwork', 0, 4), ('ContextNetwork', 1, 4),
+             ('DenseNet', 0, 0), ('DenseNetSmall', 0, 0), ('DenseNetTiny', 0, 0),
+             ('DenseNetTinyEarlyFusionSum', 0, 0), ('DenseNetTinyEarlyFusionStack', 0, 0)]
+
+
+def _our_model(arch, att, ds, gan=False):
+    import contextlib, io
+    from dmcnet_b200 import model as M
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if gan:
+            return M.GANModel(51, 3, 'mv', base_model='resnet18', arch_estimator=arch, att=att,
+                              gen_flow_ds_factor=ds, use_databn=0, gen_flow_or_delta=1, arch_d='Discriminator')
+        return M.Model(51, 3, 'mv', base_model='resnet18', arch_estimator=arch, att=att,
+                       gen_flow_ds_factor=ds, use_databn=0, gen_flow_or_delta=1)
+
+
+@pytest.mark.parametrize('arch,att,ds', GEN_CASES)
+def test_every_generator_choice_constructs_the_reference_state(arch, att, ds, golden_dir):
+    """state_dict keys / shapes / init values of gen_flow_model for every --arch_estimator
+    (code/dmcnet/model.py:310-325) against the reference constructor's (fixture:
+    tests/golden/make_generator_states.py; live comparison of the WHOLE state_dict when
+    /root/reference is present).  Only the dense estimators have kernels; the others construct
+    (checkpoints load, optimizers can be wired) and refuse to run."""
+    import os
+    from oracle.digest import digest
+    z = np.load(os.path.join(golden_dir, 'generator_states.npz'))
+    tag = '%s.att%d.ds%d' % (arch, att, ds)
+    m = _our_model(arch, att, ds)
+    sd = m.state_dict()
+    keys = [k for k in sd if k.startswith('gen_flow_model')]
+    assert keys == list(z[tag + '.keys'])
+    assert [','.join(map(str, sd[k].shape)) for k in keys] == list(z[tag + '.shapes'])
+    for k, d in zip(keys, z[tag + '.digests']):
+        assert np.array_equal(digest(sd[k].float()), d), k
+    n_params = sum(p.numel() for n, p in m.named_parameters() if n.startswith('gen_flow_model'))
+    assert n_params == int(z[tag + '.params'])
+    assert hasattr(m, 'downsample') == (ds != 0)
+    from oracle import ref_loader as R
+    if R.reference_available():
+        torch.manual_seed(1)
+        ref = R.build_reference_model('dmcnet', 51, 3, 'mv', base_model='resnet18', arch_estimator=arch,
+                                      att=att, gen_flow_ds_factor=ds, use_databn=0, gen_flow_or_delta=1)
+        rsd = ref.state_dict()
+        assert list(rsd) == list(sd)
+        for k in rsd:
+            assert torch.equal(rsd[k], sd[k]), k
+    if arch != 'DenseNetTiny':
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            m(torch.zeros(1, 3, 2, 224, 224), torch.zeros(1, 3, 3, 224, 224))
+
+
+def test_gan_model_with_other_generators_matches_reference_and_unknown_names_stay_undefined():
+    from oracle import ref_loader as R
+    m = _our_model('DenseNetSmall', 0, 0, gan=True)
+    if R.reference_available():
+        torch.manual_seed(1)
+        ref = R.build_reference_model('dmcnet_GAN', 51, 3, 'mv', base_model='resnet18', arch_estimator='DenseNetSmall',
+                                      att=0, gen_flow_ds_factor=0, use_databn=0, gen_flow_or_delta=1,
+                                      arch_d='Discriminator')
+        rsd, sd = ref.state_dict(), m.state_dict()
+        assert list(rsd) == list(sd) and all(torch.equal(rsd[k], sd[k]) for k in rsd)
+    bad = _our_model('NoSuchEstimator', 0, 0)
+    assert not hasattr(bad, 'gen_flow_model')                          # model.py:310-325: silently undefined
+    with pytest.raises((AttributeError, NotImplementedError)):
+        bad(torch.zeros(1, 3, 2, 224, 224), torch.zeros(1, 3, 3, 224, 224))
+
+
+@pytest.mark.parametrize('arch', ['DenseNetSmall', 'DenseNet'])
+def test_oracle_with_wider_dense_estimators_pinned_against_reference(arch):
+    """EstimatorDenseNetSmall / EstimatorDenseNet (code/dmcnet/model.py:122-169) share the dense
+    structure of the Tiny variant: the oracle's state and forward are bit-identical to the
+    reference Model's for them too."""
+    from oracle import ref_loader as R
+    from dmcnet_b200 import model as M
+    sd = O.build_state(51, None, seed=1, arch_estimator=arch)
+    ours = M.build_state(51, None, seed=1, arch_estimator=arch)
+    assert list(sd) == list(ours) and all(torch.equal(sd[k], ours[k]) for k in sd)
+    if not R.reference_available():
+        pytest.skip('/root/reference not present')
+    torch.manual_seed(1)
+    ref = R.build_reference_model('dmcnet', 51, 3, 'mv', base_model='resnet18', arch_estimator=arch,
+                                  use_databn=0, gen_flow_or_delta=1)
+    rsd = ref.state_dict()
+    assert list(rsd) == list(sd) and all(torch.equal(rsd[k], sd[k]) for k in rsd)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    ref.eval()
+    with torch.no_grad():
+        r_out, r_gen = ref(mv, res)
+        o_out, o_gen = O.model_forward({k: v.clone() for k, v in sd.items()}, mv, res, train=False)
+    assert torch.equal(r_out, o_out) and torch.equal(r_gen, o_gen)

@@ -217,3 +217,71 @@ def test_stem_im2col_operand_layout():
     ref = F.conv2d(torch.tensor(x), torch.tensor(w), None, 2, 3).numpy()
     np.testing.assert_allclose(y_gemm, ref, atol=1e-10)
 
+
+
+def _cpu_engine_tables(growth, H=16, W=16, N=2):
+    """The engine's parameter table and generator plan built on the CPU (no kernels): the host
+    logic under test is the channel layout and the combined-weight table of _alloc_generator."""
+    e = object.__new__(E.DmcEngine)
+    e.device = torch.device('cpu')
+    e.num_class, e.S, e.N = 51, 3, N
+    e.gan, e.arch_d, e.gen_flow_or_delta, e.H, e.W = False, None, 1, H, W
+    e.gen_growth = tuple(growth)
+    e._build_param_table()
+    e._alloc_generator()
+    return e
+
+
+@pytest.mark.parametrize('growth', [(8, 8, 6, 4, 2), (32, 32, 24, 16, 8), (12, 4, 8, 2, 6)])
+def test_dense_block_gradient_plan_matches_autograd(growth):
+    """Backward plan of the dense generator (engine._gen_backward): the gradient of dense slice k is
+    ONE 3x3 convolution over [d gen_flow | d new_{L-1} .. d new_{k+1}] with weights gathered from the
+    flipped weights of every later layer (numpy model of dense_dgrad_weights_kernel driven by the
+    engine's own table), times LeakyReLU'.  Checked against torch autograd for the Tiny table, the
+    DenseNetSmall table and an irregular one."""
+    e = _cpu_engine_tables(growth)
+    N, H, W, L = e.N, e.H, e.W, len(growth)
+    g = torch.Generator().manual_seed(sum(growth))
+    e.params.copy_(torch.randn(e.params.shape, generator=g) * 0.1)
+    x = torch.randn(N, 5, H, W, generator=g)
+    # reference: EstimatorDense forward (code/dmcnet/model.py:186-194) with autograd
+    pre, cur = [], x
+    for k in range(L):
+        w = e.param_view('gen_flow_model.conv_%d.0.weight' % k).clone().requires_grad_(True)
+        z = F.conv2d(cur, w, e.param_view('gen_flow_model.conv_%d.0.bias' % k), 1, 1)
+        z.retain_grad()
+        pre.append(z)
+        cur = torch.cat((F.leaky_relu(z, 0.1), cur), 1)
+    out = F.conv2d(cur, e.param_view('gen_flow_model.predict_flow.weight'),
+                   e.param_view('gen_flow_model.predict_flow.bias'), 1, 1)
+    R = torch.randn(out.shape, generator=g)
+    (out * R).sum().backward()
+    # the engine's buffers: X = [new_{L-1} .. new_0 | mv res], dD = [d gen_flow | d new_{L-1} .. d new_0]
+    X = cur.detach()
+    assert X.shape[1] == e.gen_ctot
+    for k in range(L):
+        oo = e.gen_out_off[k]
+        assert torch.equal(X[:, oo:oo + growth[k]], F.leaky_relu(pre[k].detach(), 0.1))
+    dD = torch.zeros(e.dD.shape)
+    dD[:, 0:2] = R
+    tab = e.gen_wc_table
+    assert tab[0] == L
+    params = e.params.numpy()
+    for idx, k in enumerate(reversed(range(L))):
+        row = tab[1 + idx * 34: 1 + (idx + 1) * 34]
+        out_off, gk, cin_s, nseg = row[:4]
+        assert (out_off, gk, cin_s) == (e.gen_wc_off[idx], growth[k], 2 + e.gen_out_off[k])
+        wc = np.zeros((gk, cin_s, 9), np.float32)
+        for s in range(nseg):
+            c0, cnt, w_off, cin_j, ci_off = row[4 + 5 * s: 9 + 5 * s]
+            for c in range(c0, c0 + cnt):
+                for ci in range(gk):
+                    base = w_off + ((c - c0) * cin_j + ci_off + ci) * 9
+                    wc[ci, c, :] = params[base:base + 9][::-1]
+        d_post = F.conv2d(dD[:, :cin_s], torch.from_numpy(wc).view(gk, cin_s, 3, 3), None, 1, 1)
+        oo = e.gen_out_off[k]
+        act = X[:, oo:oo + gk]
+        d_pre = d_post * torch.where(act > 0, torch.ones(()), torch.full((), 0.1))
+        dD[:, 2 + oo:2 + oo + gk] = d_pre
+        ref = pre[k].grad
+        assert float((d_pre - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), (growth, k)
