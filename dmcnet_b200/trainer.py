@@ -203,7 +203,10 @@ class FusedTrainStep:
         Returns (start_epoch, best_prec1); call ``set_epoch`` with the epoch about to run."""
         from . import checkpoint as C
         eng = self.eng
-        eng.load_state(C.strip_first_component(ckpt['state_dict']))       # strict, as train.py:151
+        state = ckpt['state_dict']
+        if all(k.startswith('module.') for k in state):                   # saved from nn.DataParallel
+            state = C.strip_first_component(state)
+        eng.load_state(state)                                             # strict, as train.py:151
         steps = self.steps.cpu().tolist()
         for gi, tag in enumerate(GROUPS):
             key = C.OPTIMIZER_KEYS[tag]
@@ -367,17 +370,18 @@ class FusedTrainStep:
     def step_u8(self, frames_u8, target, masks: Optional[Sequence[torch.Tensor]] = None,
                 flow_ds_factor: int = 0, apply: bool = True, metrics: bool = True) -> Dict[str, float]:
         """``step`` fed with the uint8 sample stack (see ``load_inputs_u8``)."""
-        return self.step(None, None, None, target, masks=masks, apply=apply, metrics=metrics,
-                         _u8=(frames_u8, flow_ds_factor))
+        self.load_inputs_u8(frames_u8, target, flow_ds_factor)
+        return self._step_staged(masks, apply, metrics)
 
     def step(self, input_flow, input_mv, input_residual, target,
              masks: Optional[Sequence[torch.Tensor]] = None, apply: bool = True,
-             metrics: bool = True, _u8=None) -> Dict[str, float]:
+             metrics: bool = True) -> Dict[str, float]:
+        self.load_inputs(input_flow, input_mv, input_residual, target)
+        return self._step_staged(masks, apply, metrics)
+
+    def _step_staged(self, masks, apply: bool, metrics: bool) -> Dict[str, float]:
+        """One iteration on the batch already in the static input buffers."""
         eng = self.eng
-        if _u8 is not None:
-            self.load_inputs_u8(_u8[0], target, _u8[1])
-        else:
-            self.load_inputs(input_flow, input_mv, input_residual, target)
         mode = self._mode()
         if eng.gan:
             m = 2 * eng.N if mode == 'D' else eng.N
