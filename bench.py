@@ -152,6 +152,9 @@ def main():
     ap.add_argument('--cpu-sample-batch', type=int, default=4)
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--input', default='fp32', choices=['fp32', 'u8'],
+                    help="host format of the e2e leg: three normalised fp32 tensors (default, the measured "
+                         "path) or the uint8 [B,S,H,W,7] sample stack normalised on the device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
@@ -237,8 +240,19 @@ def main():
     # FusedTrainStep.step_pipelined: every step copies ITS batch from pinned host memory
     # (on a copy stream, overlapping the previous step's compute) and reads back the metrics
     # of the step that just finished; flush() inside the timed region collects the last one.
+    stack_u8 = None
+    if args.input == 'u8':
+        # the same sample values as one interleaved uint8 stack (flow | mv | residual channels)
+        denorm = lambda t, d: torch.round((t * d + 0.5) * 255.0).clamp_(0, 255)
+        stack_u8 = torch.cat((denorm(flow, std.mean()), denorm(mv, std.mean()),
+                              denorm(res, std.view(1, 1, 3, 1, 1))), 2).permute(0, 1, 3, 4, 2)
+        stack_u8 = stack_u8.to(torch.uint8).contiguous().pin_memory()
+
     def e2e_step():
-        return tr.step_pipelined(flow, mv, res, target, masks=(masks_d if tr._mode() == 'D' else masks_g))
+        mk = masks_d if tr._mode() == 'D' else masks_g
+        if stack_u8 is not None:
+            return tr.step_pipelined_u8(stack_u8, target, masks=mk)
+        return tr.step_pipelined(flow, mv, res, target, masks=mk)
     for _ in range(2 * per):
         e2e_step()
     tr.flush()
@@ -255,6 +269,8 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = (flow.numel() + mv.numel() + res.numel()) * 4 + target.numel() * 8
+    if stack_u8 is not None:
+        h2d = stack_u8.numel() + target.numel() * 8
     d2h = 16 * 8                                     # one pinned 16-double stats record per step
 
     # ---------------- roofline of the dominant kernel family (instrumented eager pass)
@@ -276,7 +292,7 @@ def main():
         'config': {'workload': cfg['workload'], 'clips_per_gpu': B, 'global_batch': clips, 'segments': S,
                    'parallelism': 'dp%d' % world,
                    'l2_policy': 'inputs+activations per step (>2 GB) far exceed the 126 MB L2',
-                   'cuda_graph': bool(tr.use_graph)},
+                   'cuda_graph': bool(tr.use_graph), 'e2e_input': args.input},
         'e2e': {'value': clips / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
         'gpu_launches': int(launches),

@@ -452,6 +452,52 @@ class FusedTrainStep:
         self._k += 1
         return self._collect(prev) if prev is not None else {}
 
+    def step_pipelined_u8(self, frames_u8, target, masks: Optional[Sequence[torch.Tensor]] = None,
+                          flow_ds_factor: int = 0) -> Dict[str, float]:
+        """``step_pipelined`` fed with the uint8 sample stack [B,S,H,W,7] (``load_inputs_u8``): the
+        copy stream moves 7 B/pixel, the split / block-mean / normalisation kernels run on the main
+        stream in front of the step.  (Kept separate from ``step_pipelined`` so the measured fp32
+        path is untouched; not yet timed on a GPU.)"""
+        if not self.pipelined:
+            raise RuntimeError('construct FusedTrainStep(..., pipelined=True)')
+        from .input_stage import check_stack, normalisation_divisors
+        eng, H, W, n = self.eng, self.eng.H, self.eng.W, self.eng.N
+        check_stack(frames_u8, n, H, W)
+        if '_u8' not in self._stg:
+            self._stg['_u8'] = [torch.empty(n, H, W, 7, dtype=torch.uint8, device=eng.device) for _ in range(2)]
+            self._u8_divs = normalisation_divisors()
+        s = self._k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_free[s])
+            self._stg['_u8'][s].copy_(frames_u8.reshape(n, H, W, 7), non_blocking=True)
+            self._stg['target'][s].copy_(target, non_blocking=True)
+            self._ev_h2d[s].record(self._copy_stream)
+        main.wait_event(self._ev_h2d[s])
+        div_motion, div_res = self._u8_divs
+        stack = self._stg['_u8'][s]
+        if flow_ds_factor == 0:
+            ops.unpack_normalize_u8(stack, n, H, W, div_motion, div_res, self.in_flow, self.in_mv, self.in_res)
+        else:
+            ops.unpack_normalize_u8(stack, n, H, W, div_motion, div_res, None, self.in_mv, self.in_res)
+            ops.flow_block_mean_u8(stack, n, H, W, flow_ds_factor, div_motion, self.in_flow)
+        self.target.copy_(self._stg['target'][s], non_blocking=True)
+        self._ev_free[s].record(main)
+        mode = self._mode()
+        if eng.gan:
+            m = 2 * eng.N if mode == 'D' else eng.N
+            eng.set_masks(masks if masks is not None else eng.draw_dropout_masks(m), m)
+        self._run(mode, True)
+        self.iteration += 1
+        self._dev_stats[0:4].copy_(self.ce_stats)
+        self._dev_stats[4:8].copy_(self.adv_stats)
+        self._dev_stats[8:9].copy_(self.mse_sum)
+        self._host_stats[s].copy_(self._dev_stats, non_blocking=True)
+        self._ev_done[s].record(main)
+        prev, self._pending = self._pending, (s, mode)
+        self._k += 1
+        return self._collect(prev) if prev is not None else {}
+
     def flush(self) -> Dict[str, float]:
         """Metrics of the last pipelined step (blocks until it finished)."""
         prev, self._pending = self._pending, None

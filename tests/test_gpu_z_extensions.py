@@ -387,3 +387,36 @@ def test_wider_dense_estimators_train_step_vs_oracle(arch, batch):
     for k in eng.specs:
         if k.startswith('gen_flow_model'):
             assert rel2(eng.grad_view(k), og[k]) < 1e-4, k
+
+
+@pytest.mark.skipif(not _os.environ.get('DMC_RUN_UNVERIFIED'),
+                    reason='path not yet executed on a GPU; set DMC_RUN_UNVERIFIED=1 to run it')
+def test_pipelined_uint8_step_matches_blocking_step():
+    """step_pipelined_u8 (copy stream moves the uint8 stack, kernels normalise in front of the step)
+    against step_u8 on the same batches."""
+    from oracle import input_pipe as P
+    batch, num_class = 2, 51
+    sd = O.build_state(num_class, None, seed=1)
+    stacks = [torch.from_numpy(P.synthetic_frames(batch * 3, 224, 224, seed=s)).reshape(batch, 3, 224, 224, 7)
+              .pin_memory() for s in (1, 2, 3)]
+    target = torch.tensor([5, 17]).pin_memory()
+    runs = []
+    for pipelined in (False, True):
+        eng = DmcEngine(num_class, 3, batch * 3)
+        eng.load_state(sd)
+        tr = FusedTrainStep(eng, HParams(), batch, pipelined=pipelined)
+        ms = []
+        for st in stacks:
+            if pipelined:
+                m = tr.step_pipelined_u8(st, target, flow_ds_factor=16)
+                if m:
+                    ms.append(m)
+            else:
+                ms.append(tr.step_u8(st, target.cuda(), flow_ds_factor=16))
+        if pipelined:
+            ms.append(tr.flush())
+        runs.append(ms)
+    assert len(runs[0]) == len(runs[1]) == 3
+    for a, b in zip(*runs):
+        for k in ('loss', 'loss_cls', 'loss_mse', 'prec1'):
+            assert b[k] == pytest.approx(a[k], rel=1e-4, abs=1e-6), k
