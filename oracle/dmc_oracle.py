@@ -45,6 +45,17 @@ GEN_CH_IN = 5
 DENSE_GROWTH = {'DenseNetTiny': GEN_TINY_GROWTH, 'DenseNetSmall': (32, 32, 24, 16, 8),
                 'DenseNet': (128, 128, 96, 64, 32)}
 
+# ContextNetwork / ContextNetworkAtt: code/dmcnet/model.py:45-104.  (cout, dilation) per layer; the
+# fifth dilation is 16 at full resolution and 1 when gen_flow_ds_factor != 0.
+def context_layers(att: int, gen_flow_ds_factor: int) -> List[Tuple[int, int]]:
+    d5 = 16 if gen_flow_ds_factor == 0 else 1
+    layers = [(32, 1), (128, 2), (128, 4), (96, 8), (64, d5), (32, 1)]
+    return layers if att else layers + [(2, 1)]
+
+
+# ...TinyEarlyFusionSum / ...Stack: code/dmcnet/model.py:197-250
+EARLY_FUSION = {'DenseNetTinyEarlyFusionSum': False, 'DenseNetTinyEarlyFusionStack': True}
+
 # ResNet-18 = torchvision BasicBlock x (2,2,2,2), widths 64..512
 RESNET18_STAGES = ((64, 1), (128, 2), (256, 2), (512, 2))
 
@@ -78,7 +89,8 @@ def disc_fc_in(arch_d: str) -> int:
 # --------------------------------------------------------------------------
 
 def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int] = 1,
-                arch_estimator: str = 'DenseNetTiny') -> "OrderedDict[str, Tensor]":
+                arch_estimator: str = 'DenseNetTiny', att: int = 0, gen_flow_ds_factor: int = 0
+                ) -> "OrderedDict[str, Tensor]":
     """state_dict of ``Model(num_class, S, 'mv', 'resnet18', arch_estimator=
     'DenseNetTiny'[, arch_d=...], use_databn=0)`` with random init.
 
@@ -95,10 +107,31 @@ def build_state(num_class: int, arch_d: Optional[str] = None, seed: Optional[int
     base = torchvision.models.resnet18(weights=None)
     gen = OrderedDict()
     cin = GEN_CH_IN
-    for k, g in enumerate(DENSE_GROWTH[arch_estimator]):
-        gen['conv_%d.0' % k] = nn.Conv2d(cin, g, 3, 1, 1, bias=True)      # model.py:111-115
-        cin += g
-    gen['predict_flow'] = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)           # model.py:118-119
+    if arch_estimator in DENSE_GROWTH:
+        for k, g in enumerate(DENSE_GROWTH[arch_estimator]):
+            gen['conv_%d.0' % k] = nn.Conv2d(cin, g, 3, 1, 1, bias=True)      # model.py:111-115
+            cin += g
+        gen['predict_flow'] = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)           # model.py:118-119
+    elif arch_estimator in EARLY_FUSION:                                      # model.py:197-250
+        gen['conv_0_mv.0'] = nn.Conv2d(2, 8, 3, 1, 1, bias=True)
+        gen['conv_0_r.0'] = nn.Conv2d(3, 8, 3, 1, 1, bias=True)
+        cin = 16 if EARLY_FUSION[arch_estimator] else 8
+        for k, g in zip((1, 2, 3, 4), (8, 6, 4, 2)):
+            gen['conv_%d.0' % k] = nn.Conv2d(cin, g, 3, 1, 1, bias=True)
+            cin += g
+        gen['predict_flow'] = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)
+    elif arch_estimator == 'ContextNetwork':                                  # model.py:31-104
+        def block(prefix, ci, co, d):
+            gen[prefix + '.0'] = nn.Conv2d(ci, co, 3, 1, d, d, bias=False)
+            gen[prefix + '.1'] = nn.BatchNorm2d(co)
+        for i, (co, d) in enumerate(context_layers(att, gen_flow_ds_factor)):
+            block('conv_context.%d' % i, cin, co, d)
+            cin = co
+        if att:
+            block('predict_flow', 32, 2, 1)
+            block('predict_att.0', 32, 2, 1)
+    else:
+        raise ValueError('unknown arch_estimator %r' % (arch_estimator,))
     disc = OrderedDict()
     if arch_d is not None:
         for name, ci, co, stride, bn in disc_blocks(arch_d):
@@ -182,6 +215,33 @@ def gen_tiny_forward(st: Dict[str, Tensor], x: Tensor) -> Tensor:
     return F.conv2d(x, st[p + '.weight'], st[p + '.bias'], 1, 1)
 
 
+def early_fusion_forward(st: Dict[str, Tensor], x: Tensor, stack: bool) -> Tensor:
+    """EstimatorDenseNetTinyEarlyFusionSum / ...Stack.forward, code/dmcnet/model.py:212-222, :240-250."""
+    q = 'gen_flow_model.'
+    lr = lambda t: F.leaky_relu(t, 0.1)
+    x_mv = lr(F.conv2d(x[:, :2], st[q + 'conv_0_mv.0.weight'], st[q + 'conv_0_mv.0.bias'], 1, 1))
+    x_r = lr(F.conv2d(x[:, 2:], st[q + 'conv_0_r.0.weight'], st[q + 'conv_0_r.0.bias'], 1, 1))
+    x = torch.cat((x_mv, x_r), 1) if stack else x_mv + x_r
+    for k in (1, 2, 3, 4):
+        p = q + 'conv_%d.0' % k
+        x = torch.cat((lr(F.conv2d(x, st[p + '.weight'], st[p + '.bias'], 1, 1)), x), 1)
+    return F.conv2d(x, st[q + 'predict_flow.weight'], st[q + 'predict_flow.bias'], 1, 1)
+
+
+def context_forward(st: Dict[str, Tensor], x: Tensor, att: int, gen_flow_ds_factor: int, train: bool):
+    """ContextNetwork.forward (code/dmcnet/model.py:69-71) / ContextNetworkAtt.forward (:99-102):
+    every layer is dilated Conv3x3(bias=False) -> BatchNorm2d(eps 1e-5) -> LeakyReLU(0.1), the
+    output layers included; the attention head adds a ReLU."""
+    def block(x, prefix, d):
+        x = F.conv2d(x, st[prefix + '.0.weight'], None, 1, d, d)
+        return F.leaky_relu(_bn(x, st, prefix + '.1', train, 1e-5), 0.1)
+    for i, (_, d) in enumerate(context_layers(att, gen_flow_ds_factor)):
+        x = block(x, 'gen_flow_model.conv_context.%d' % i, d)
+    if not att:
+        return x
+    return block(x, 'gen_flow_model.predict_flow', 1), F.relu(block(x, 'gen_flow_model.predict_att.0', 1))
+
+
 def resnet18_forward(st: Dict[str, Tensor], x: Tensor, train: bool, prefix: str = 'base_model'
                      ) -> Tensor:
     """torchvision resnet18 forward with the 2-channel conv1 and num_class fc of
@@ -241,17 +301,36 @@ def disc_forward(st: Dict[str, Tensor], x: Tensor, arch_d: str, train: bool,
 def model_forward(st: Dict[str, Tensor], input_mv: Tensor, input_residual: Tensor,
                   input_flow: Optional[Tensor] = None, *, gan: bool = False,
                   arch_d: Optional[str] = None, train: bool = True,
-                  gen_flow_or_delta: int = 1, masks: Optional[Sequence[Tensor]] = None):
-    """Model.forward.  dmcnet: code/dmcnet/model.py:330-357 -> (base_out, gen_flow);
-    GAN: code/dmcnet_GAN/model.py:533-566 -> (base_out, validity, gen_flow)."""
+                  gen_flow_or_delta: int = 1, masks: Optional[Sequence[Tensor]] = None,
+                  arch_estimator: str = 'DenseNetTiny', att: int = 0, gen_flow_ds_factor: int = 0):
+    """Model.forward.  dmcnet: code/dmcnet/model.py:330-357 -> (base_out, gen_flow[, att_flow]);
+    GAN: code/dmcnet_GAN/model.py:533-566 -> (base_out, validity, gen_flow[, att_flow]).
+    ``att_flow`` is returned only for ContextNetwork with att == 1."""
     mv = input_mv.reshape((-1,) + tuple(input_mv.shape[-3:]))
     res = input_residual.reshape((-1,) + tuple(input_residual.shape[-3:]))
-    gen_flow = gen_tiny_forward(st, torch.cat((mv, res), 1))
+    if gen_flow_ds_factor != 0:                                              # model.py:335-337
+        mv = F.avg_pool2d(mv, gen_flow_ds_factor, gen_flow_ds_factor)
+        res = F.avg_pool2d(res, gen_flow_ds_factor, gen_flow_ds_factor)
+    x = torch.cat((mv, res), 1)
+    att_flow = None
+    if arch_estimator in DENSE_GROWTH:
+        gen_flow = gen_tiny_forward(st, x)
+    elif arch_estimator in EARLY_FUSION:
+        gen_flow = early_fusion_forward(st, x, EARLY_FUSION[arch_estimator])
+    elif arch_estimator == 'ContextNetwork' and att == 1:
+        gen_flow, att_flow = context_forward(st, x, 1, gen_flow_ds_factor, train)
+    elif arch_estimator == 'ContextNetwork':
+        gen_flow = context_forward(st, x, 0, gen_flow_ds_factor, train)
+    else:
+        raise AttributeError("'Model' object has no attribute 'gen_flow_model'")     # model.py:310-325
     if gen_flow_or_delta == 1:
         gen_flow = torch.add(gen_flow, mv)
+    if gen_flow_ds_factor != 0:                                              # model.py:347-348 (a TILING)
+        gen_flow = gen_flow.repeat(1, 1, gen_flow_ds_factor, gen_flow_ds_factor)
+    extra = () if att_flow is None else (att_flow,)
     if not gan:
         base_out = resnet18_forward(st, gen_flow.detach(), train)           # model.py:352
-        return base_out, gen_flow
+        return (base_out, gen_flow) + extra
     if input_flow is not None:
         flow = input_flow.reshape((-1,) + tuple(input_flow.shape[-3:]))
         d_in = torch.cat((gen_flow, flow), 0)                                # "first fake then real"
@@ -259,7 +338,7 @@ def model_forward(st: Dict[str, Tensor], input_mv: Tensor, input_residual: Tenso
         d_in = gen_flow
     base_out = resnet18_forward(st, gen_flow, train)                         # GAN/model.py:560
     validity = disc_forward(st, d_in, arch_d, train, masks)                  # :561
-    return base_out, validity, gen_flow
+    return (base_out, validity, gen_flow) + extra
 
 
 # --------------------------------------------------------------------------
@@ -315,8 +394,12 @@ class OracleTrainer:
     ``adjust_learning_rate`` (train.py:398-408)."""
 
     def __init__(self, state: Dict[str, Tensor], hp: HParams, *, gan: bool = False,
-                 arch_d: Optional[str] = None):
+                 arch_d: Optional[str] = None, arch_estimator: str = 'DenseNetTiny', att: int = 0,
+                 gen_flow_ds_factor: int = 0):
         self.hp, self.gan, self.arch_d = hp, gan, arch_d
+        # generator choice (--arch_estimator / --att / --gen_flow_ds_factor, train.py:53-60)
+        self.gen_kw = dict(arch_estimator=arch_estimator, att=att, gen_flow_ds_factor=gen_flow_ds_factor)
+        self.att = int(att == 1 and arch_estimator == 'ContextNetwork')
         self.st: Dict[str, Tensor] = OrderedDict()
         for k, v in state.items():
             t = v.detach().clone()
@@ -372,6 +455,13 @@ class OracleTrainer:
     def state_dict(self) -> Dict[str, Tensor]:
         return OrderedDict((k, v.detach().clone()) for k, v in self.st.items())
 
+    def _flow_loss(self, gen_flow: Tensor, flow: Tensor, att_flow) -> Tensor:
+        """code/dmcnet/train.py:244-247 (GAN/train.py:349-352): with pixel attention both the
+        generated and the target flow are weighted by the attention map."""
+        if self.att:
+            return self.criterion_mse(att_flow[0] * gen_flow, att_flow[0] * flow)
+        return self.criterion_mse(gen_flow, flow)
+
     def step(self, input_flow: Tensor, input_mv: Tensor, input_residual: Tensor, target: Tensor,
              masks: Optional[Sequence[Tensor]] = None, apply: bool = True) -> Dict[str, float]:
         hp, S = self.hp, self.hp.num_segments
@@ -379,10 +469,11 @@ class OracleTrainer:
         flow = input_flow.reshape((-1,) + tuple(input_mv.shape[-3:]))         # train.py:230
         out: Dict[str, float] = {}
         if not self.gan:
-            output, gen_flow = model_forward(self.st, input_mv, input_residual, train=True)
+            output, gen_flow, *att_flow = model_forward(self.st, input_mv, input_residual, train=True,
+                                                        **self.gen_kw)
             output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)   # :239-240
             loss_cls = ce(output, target)                                     # :241
-            loss_mse = self.criterion_mse(gen_flow, flow)                             # :245
+            loss_mse = self._flow_loss(gen_flow, flow, att_flow)              # :244-247
             loss = loss_cls * hp.lr_cls + loss_mse * hp.lr_mse                # :248
             self._zero()
             if self.freeze:                                                   # :260-265
@@ -398,9 +489,9 @@ class OracleTrainer:
             valid = torch.ones(target.shape[0] * S, dtype=torch.int64)        # GAN/train.py:253-256
             fake = torch.zeros_like(valid)
             if self.iteration % 2 == 0:                                       # D-step :261-302
-                output, validity, gen_flow = model_forward(
+                output, validity, gen_flow, *att_flow = model_forward(
                     self.st, input_mv, input_residual, flow, gan=True, arch_d=self.arch_d,
-                    train=True, masks=masks)
+                    train=True, masks=masks, **self.gen_kw)
                 output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)
                 loss_cls = ce(output, target)
                 adv_t = torch.cat((fake, valid), 0)
@@ -413,13 +504,13 @@ class OracleTrainer:
                     self.opt_d.step()
                 out.update(acc_adv=accuracy(validity.detach(), adv_t)[0])
             else:                                                             # G-step :331-371
-                output, validity, gen_flow = model_forward(
+                output, validity, gen_flow, *att_flow = model_forward(
                     self.st, input_mv, input_residual, None, gan=True, arch_d=self.arch_d,
-                    train=True, masks=masks)
+                    train=True, masks=masks, **self.gen_kw)
                 output = output.view((-1, S) + tuple(output.shape[1:])).mean(dim=1)
                 loss_cls = ce(output, target)
                 loss_adv = ce(validity, valid)                                # :346
-                loss_mse = self.criterion_mse(gen_flow, flow)                         # :350
+                loss_mse = self._flow_loss(gen_flow, flow, att_flow)          # :349-352
                 loss = loss_cls * hp.lr_cls + loss_adv * hp.lr_adv_g + loss_mse * hp.lr_mse
                 self._zero()
                 loss.backward()

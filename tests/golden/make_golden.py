@@ -27,9 +27,9 @@ from oracle.pin_against_reference import ref_optimizers  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build(variant, num_class, arch_d):
+def build(variant, num_class, arch_d, arch_estimator='DenseNetTiny'):
     torch.manual_seed(1)
-    kw = dict(base_model='resnet18', arch_estimator='DenseNetTiny', gen_flow_or_delta=1, use_databn=0)
+    kw = dict(base_model='resnet18', arch_estimator=arch_estimator, gen_flow_or_delta=1, use_databn=0)
     if variant == 'dmcnet_GAN':
         kw['arch_d'] = arch_d
     return R.build_reference_model(variant, num_class, 3, 'mv', **kw)
@@ -48,9 +48,9 @@ def golden_infer():
              init_state=np.stack([digest(v.float()) for v in ref.state_dict().values()]))
 
 
-def golden_train(variant, num_class, arch_d, batch, name, steps=2):
+def golden_train(variant, num_class, arch_d, batch, name, steps=2, arch_estimator='DenseNetTiny'):
     gan = variant == 'dmcnet_GAN'
-    ref = build(variant, num_class, arch_d).train()
+    ref = build(variant, num_class, arch_d, arch_estimator).train()
     hp = O.HParams()
     flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
     fl = flow.view((-1,) + tuple(mv.shape[-3:]))
@@ -117,6 +117,8 @@ def main():
     golden_train('dmcnet', 51, None, 2, 'train_dmcnet_b2.npz')
     golden_train('dmcnet_GAN', 101, 'Discriminator3', 2, 'train_gan_d3_b2.npz')
     golden_train('dmcnet_GAN', 51, 'Discriminator', 1, 'train_gan_d_b1.npz')
+    # the default generator: fixture for the kernels of the next round
+    golden_train('dmcnet', 51, None, 1, 'train_context_b1.npz', arch_estimator='ContextNetwork')
     print('golden fixtures written to', HERE)
 
 

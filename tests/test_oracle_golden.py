@@ -28,17 +28,18 @@ def test_infer_cfg1(golden_dir):
     digest_close(g['gen_flow'], gen_flow, RTOL, 'gen_flow')
 
 
-@pytest.mark.parametrize('name,num_class,arch_d,batch', [
-    ('train_dmcnet_b2.npz', 51, None, 2),
-    ('train_gan_d3_b2.npz', 101, 'Discriminator3', 2),
-    ('train_gan_d_b1.npz', 51, 'Discriminator', 1),
+@pytest.mark.parametrize('name,num_class,arch_d,batch,arch_estimator', [
+    ('train_dmcnet_b2.npz', 51, None, 2, 'DenseNetTiny'),
+    ('train_gan_d3_b2.npz', 101, 'Discriminator3', 2, 'DenseNetTiny'),
+    ('train_gan_d_b1.npz', 51, 'Discriminator', 1, 'DenseNetTiny'),
+    ('train_context_b1.npz', 51, None, 1, 'ContextNetwork'),
 ])
-def test_train_steps(golden_dir, name, num_class, arch_d, batch):
+def test_train_steps(golden_dir, name, num_class, arch_d, batch, arch_estimator):
     g = np.load(os.path.join(golden_dir, name))
     gan = arch_d is not None
-    sd = O.build_state(num_class, arch_d, seed=1)
+    sd = O.build_state(num_class, arch_d, seed=1, arch_estimator=arch_estimator)
     assert list(sd.keys()) == list(g['keys'])
-    tr = O.OracleTrainer(sd, O.HParams(), gan=gan, arch_d=arch_d)
+    tr = O.OracleTrainer(sd, O.HParams(), gan=gan, arch_d=arch_d, arch_estimator=arch_estimator)
     flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
     pkeys = list(g['param_keys'])
     for it in range(2):
