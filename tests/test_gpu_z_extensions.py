@@ -208,78 +208,7 @@ def test_video_scorer_gan_flavour_returns_validity(monkeypatch):
     assert I.adversarial_accuracy(out) == 100.0 * float(np.argmax(val))
 
 
-# ------------------------------------------------------------------ checkpoint / resume interop
-def test_checkpoint_resumes_on_the_oracle_and_back(tmp_path):
-    """One step here -> checkpoint in the reference's format (code/dmcnet/train.py:190-201) ->
-    torch optimizers wired as train.py:121-142 load it and take step 2; the engine resumed from the
-    same file takes step 2 as well.  Then the other direction: an oracle-written checkpoint."""
-    from dmcnet_b200 import checkpoint as C
-    batch, num_class = 2, 51
-    sd = O.build_state(num_class, None, seed=1)
-    flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
-    dev = lambda *ts: [t.cuda() for t in ts]
-
-    def engine_trainer(state=None):
-        eng = DmcEngine(num_class, 3, batch * 3)
-        eng.load_state(state if state is not None else sd)
-        return eng, FusedTrainStep(eng, HParams(), batch)
-
-    eng, tr = engine_trainer()
-    tr.step(*dev(flow, mv, res, target))
-    ck = tr.checkpoint(epoch=1, best_prec1=3.0)
-    path = C.save_checkpoint(ck, False, str(tmp_path / 'hmdb51'), 'mv')
-    ck = C.load_checkpoint(path)
-    assert set(ck) == {'epoch', 'arch', 'state_dict', 'best_prec1', 'optimizer_cls', 'optimizer_gf'}
-    assert all(k.startswith('module.') for k in ck['state_dict'])
-    assert len(ck['optimizer_cls']['param_groups']) == 62 and len(ck['optimizer_gf']['param_groups']) == 12
-    assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0
-
-    # (1) the oracle (torch.optim.Adam) resumes from our file.  torch's load_state_dict keeps the
-    # tensors it is given (no copy) and Adam then updates them in place, so the oracle gets its own
-    # read of the file
-    ck_for_oracle = C.load_checkpoint(path)
-    ref = O.OracleTrainer(C.strip_first_component(ck_for_oracle['state_dict']), O.HParams(), gan=False)
-    ref.opt_cls.load_state_dict(ck_for_oracle['optimizer_cls'])
-    ref.opt_gf.load_state_dict(ck_for_oracle['optimizer_gf'])
-    mo = ref.step(flow, mv, res, target)
-    assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0          # our copy is untouched
-    # (2) a fresh engine resumes from the same file
-    eng2, tr2 = engine_trainer(state={k: torch.zeros_like(v) if v.is_floating_point() else v for k, v in sd.items()})
-    assert tr2.resume(ck) == (1, 3.0)
-    assert tr2.steps.cpu().tolist() == [1, 1, 0]
-    m2 = tr2.step(*dev(flow, mv, res, target))
-    # (3) the original engine simply continues
-    m1 = tr.step(*dev(flow, mv, res, target))
-    for k in ('loss', 'loss_cls', 'loss_mse'):
-        assert m2[k] == pytest.approx(m1[k], rel=1e-5), k
-        assert m2[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
-    after_o = ref.state_dict()
-    a1, a2 = eng.state_dict(), eng2.state_dict()
-    for k in a1:
-        if k.startswith('gen_flow_model'):     # same state, same batch: only fp32-atomic ordering differs
-            assert rel(a2[k], a1[k]) < 1e-4, k
-            assert rel(a2[k], after_o[k]) < 1e-3, k
-    st = ref.opt_gf.state_dict()['state'][0]
-    ck2 = tr2.checkpoint(epoch=2)
-    assert float(ck2['optimizer_gf']['state'][0]['step']) == float(st['step']) == 2.0
-    assert rel(ck2['optimizer_gf']['state'][0]['exp_avg'], st['exp_avg']) < 1e-3
-
-    # (4) oracle-written checkpoint (the reference's own layout) -> engine
-    ck_o = {'epoch': 2, 'arch': 'resnet18', 'state_dict': C.add_module_prefix(after_o), 'best_prec1': 0.0,
-            'optimizer_cls': ref.opt_cls.state_dict(), 'optimizer_gf': ref.opt_gf.state_dict()}
-    eng3, tr3 = engine_trainer()
-    tr3.resume(ck_o)
-    assert tr3.steps.cpu().tolist()[:2] == [2, 2]
-    m3 = tr3.step(*dev(flow, mv, res, target))
-    mo3 = ref.step(flow, mv, res, target)
-    for k in ('loss', 'loss_cls', 'loss_mse'):
-        assert m3[k] == pytest.approx(mo3[k], rel=1e-3, abs=1e-6), k
-    o3, e3 = ref.state_dict(), eng3.state_dict()
-    for k in e3:
-        if k.startswith('gen_flow_model'):
-            assert rel(e3[k], o3[k]) < 1e-3, k
-
-
+# ------------------------------------------------------------------ checkpoint / resume
 def test_gan_stage_warm_starts_from_a_stage1_checkpoint():
     """--weights (code/dmcnet_GAN/train.py:64-68): strict=False after stripping the prefix; the
     discriminator keeps its initialisation."""
@@ -355,6 +284,79 @@ def test_epoch_driver_on_the_engine(tmp_path):
         assert float(ck['optimizer_cls']['state'][0]['step']) == 2.0
     # epoch 1 ran at the decayed rate (lr_steps=(1,)): lr * lr_decay * lr_mse_mult
     assert float(tr.hyper[len(C.group_keys(eng.specs, 'base_model')), 0]) == pytest.approx(0.01 * 0.1)
+
+
+# ------------------------------------------------------------------ checkpoint / resume interop (GPU <-> torch.optim.Adam)
+def test_checkpoint_resumes_on_the_oracle_and_back(tmp_path):
+    """One step here -> checkpoint in the reference's format (code/dmcnet/train.py:190-201) ->
+    torch optimizers wired as train.py:121-142 load it and take step 2; the engine resumed from the
+    same file takes step 2 as well.  Then the other direction: an oracle-written checkpoint."""
+    from dmcnet_b200 import checkpoint as C
+    batch, num_class = 2, 51
+    sd = O.build_state(num_class, None, seed=1)
+    flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
+    dev = lambda *ts: [t.cuda() for t in ts]
+
+    def engine_trainer(state=None):
+        eng = DmcEngine(num_class, 3, batch * 3)
+        eng.load_state(state if state is not None else sd)
+        return eng, FusedTrainStep(eng, HParams(), batch)
+
+    eng, tr = engine_trainer()
+    tr.step(*dev(flow, mv, res, target))
+    ck = tr.checkpoint(epoch=1, best_prec1=3.0)
+    path = C.save_checkpoint(ck, False, str(tmp_path / 'hmdb51'), 'mv')
+    ck = C.load_checkpoint(path)
+    assert set(ck) == {'epoch', 'arch', 'state_dict', 'best_prec1', 'optimizer_cls', 'optimizer_gf'}
+    assert all(k.startswith('module.') for k in ck['state_dict'])
+    assert len(ck['optimizer_cls']['param_groups']) == 62 and len(ck['optimizer_gf']['param_groups']) == 12
+    assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0
+
+    # (1) the oracle (torch.optim.Adam) resumes from our file.  torch's load_state_dict keeps the
+    # tensors it is given (no copy) and Adam then updates them in place, so the oracle gets its own
+    # read of the file
+    ck_for_oracle = C.load_checkpoint(path)
+    ref = O.OracleTrainer(C.strip_first_component(ck_for_oracle['state_dict']), O.HParams(), gan=False)
+    ref.opt_cls.load_state_dict(ck_for_oracle['optimizer_cls'])
+    ref.opt_gf.load_state_dict(ck_for_oracle['optimizer_gf'])
+    mo = ref.step(flow, mv, res, target)
+    assert float(ck['optimizer_gf']['state'][0]['step']) == 1.0          # our copy is untouched
+    # (2) a fresh engine resumes from the same file
+    eng2, tr2 = engine_trainer(state={k: torch.zeros_like(v) if v.is_floating_point() else v for k, v in sd.items()})
+    assert tr2.resume(ck) == (1, 3.0)
+    assert tr2.steps.cpu().tolist() == [1, 1, 0]
+    m2 = tr2.step(*dev(flow, mv, res, target))
+    # (3) the original engine simply continues
+    m1 = tr.step(*dev(flow, mv, res, target))
+    for k in ('loss', 'loss_cls', 'loss_mse'):
+        assert m2[k] == pytest.approx(m1[k], rel=1e-5), k
+        assert m2[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+    after_o = ref.state_dict()
+    a1, a2 = eng.state_dict(), eng2.state_dict()
+    for k in a1:
+        if k.startswith('gen_flow_model'):     # same state, same batch: only fp32-atomic ordering differs
+            assert rel(a2[k], a1[k]) < 1e-4, k
+            assert rel(a2[k], after_o[k]) < 1e-3, k
+    st = ref.opt_gf.state_dict()['state'][0]
+    ck2 = tr2.checkpoint(epoch=2)
+    assert float(ck2['optimizer_gf']['state'][0]['step']) == float(st['step']) == 2.0
+    assert rel(ck2['optimizer_gf']['state'][0]['exp_avg'], st['exp_avg']) < 1e-3
+
+    # (4) oracle-written checkpoint (the reference's own layout) -> engine
+    ck_o = {'epoch': 2, 'arch': 'resnet18', 'state_dict': C.add_module_prefix(after_o), 'best_prec1': 0.0,
+            'optimizer_cls': ref.opt_cls.state_dict(), 'optimizer_gf': ref.opt_gf.state_dict()}
+    eng3, tr3 = engine_trainer()
+    tr3.resume(ck_o)
+    assert tr3.steps.cpu().tolist()[:2] == [2, 2]
+    m3 = tr3.step(*dev(flow, mv, res, target))
+    mo3 = ref.step(flow, mv, res, target)
+    for k in ('loss', 'loss_cls', 'loss_mse'):
+        assert m3[k] == pytest.approx(mo3[k], rel=1e-3, abs=1e-6), k
+    o3, e3 = ref.state_dict(), eng3.state_dict()
+    for k in e3:
+        if k.startswith('gen_flow_model'):
+            assert rel(e3[k], o3[k]) < 1e-3, k
+
 
 
 # ------------------------------------------------------------------ wider dense estimators (opt-in)
