@@ -1,4 +1,7 @@
-"""Drop-in replacement for code/dmcnet/model.py: put this directory on sys.path
-ahead of the reference's so that ``from model import Model`` (code/dmcnet/
-train.py:21, test.py) resolves here.  See INTEGRATION.md."""
-from dmcnet_b200.model import Model, EstimatorDenseNetTiny, conv, predict_flow  # noqa: F401
+"""Drop-in replacement for code/dmcnet/model.py (``from model import Model``,
+code/dmcnet/train.py:21, test.py:14).  Every public name of the reference module is
+provided with the same signature; see INTEGRATION.md."""
+from dmcnet_b200.model import (Model, ContextNetwork, ContextNetworkAtt, EstimatorDenseNet,  # noqa: F401
+                               EstimatorDenseNetSmall, EstimatorDenseNetTiny,
+                               EstimatorDenseNetTinyEarlyFusionSum, EstimatorDenseNetTinyEarlyFusionStack,
+                               Flatten, conv, conv_dilation, predict_flow)

@@ -77,11 +77,21 @@ class EstimatorDenseNetTiny(EstimatorDense):
         super().__init__(ch_in, DENSE_GROWTH['DenseNetTiny'])
 
 
-class EstimatorDenseNetTinyEarlyFusion(_EstimatorShell):
+class EstimatorDenseNetSmall(EstimatorDense):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, DENSE_GROWTH['DenseNetSmall'])
+
+
+class EstimatorDenseNet(EstimatorDense):
+    def __init__(self, ch_in):
+        super().__init__(ch_in, DENSE_GROWTH['DenseNet'])
+
+
+class _EarlyFusion(_EstimatorShell):
     """...EarlyFusionSum / ...EarlyFusionStack (code/dmcnet/model.py:197-250): separate first convs
     for the motion vectors and the residual, summed (8 channels) or stacked (16)."""
 
-    def __init__(self, ch_in, stack):
+    def __init__(self, stack):
         super().__init__()
         self.conv_0_mv = conv(2, 8)
         self.conv_0_r = conv(3, 8)
@@ -92,31 +102,64 @@ class EstimatorDenseNetTinyEarlyFusion(_EstimatorShell):
         self.predict_flow = predict_flow(dd)
 
 
-def conv_dilation(in_planes, out_planes, dilation):
-    """code/dmcnet/model.py:31-42 with batch_norm=True (the only way Model builds it, :312-314)."""
+class EstimatorDenseNetTinyEarlyFusionSum(_EarlyFusion):
+    def __init__(self, ch_in):                 # ch_in is unused by the reference too (model.py:198-201)
+        super().__init__(stack=False)
+
+
+class EstimatorDenseNetTinyEarlyFusionStack(_EarlyFusion):
+    def __init__(self, ch_in):
+        super().__init__(stack=True)
+
+
+class Flatten(nn.Module):
+    """code/dmcnet/model.py:20-28."""
+
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+def conv_dilation(batch_norm, in_planes, out_planes, kernel_size=3, stride=1, dilation=1):
+    """code/dmcnet/model.py:31-42."""
+    pad = ((kernel_size - 1) * dilation) // 2
+    if batch_norm:
+        return nn.Sequential(
+            nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, dilation=dilation,
+                      padding=pad, bias=False),
+            nn.BatchNorm2d(out_planes), nn.LeakyReLU(0.1, inplace=True))
     return nn.Sequential(
-        nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=1, dilation=dilation, padding=dilation,
-                  bias=False),
-        nn.BatchNorm2d(out_planes), nn.LeakyReLU(0.1, inplace=True))
+        nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, dilation=dilation,
+                  padding=pad, bias=True),
+        nn.LeakyReLU(0.1, inplace=True))
 
 
-class ContextNetwork(_EstimatorShell):
+class _Context(_EstimatorShell):
     """ContextNetwork / ContextNetworkAtt (code/dmcnet/model.py:45-104): dilated 3x3 conv + BN +
     LeakyReLU(0.1) stack 5-32-128-128-96-64-32(-2); dilation 16 of the fifth layer drops to 1 when
     the generator runs on a down-sampled input; ``att`` splits the head into flow and attention."""
 
-    def __init__(self, ch_in, gen_flow_ds_factor=0, att=False):
+    def __init__(self, ch_in, batch_norm, gen_flow_ds_factor, att):
         super().__init__()
         widths = (32, 128, 128, 96, 64, 32) + (() if att else (2,))
         dil = (1, 2, 4, 8, 16 if gen_flow_ds_factor == 0 else 1, 1, 1)
         layers, cin = [], ch_in
         for w, d in zip(widths, dil):
-            layers.append(conv_dilation(cin, w, d))
+            layers.append(conv_dilation(batch_norm, cin, w, 3, 1, d))
             cin = w
         self.conv_context = nn.Sequential(*layers)
         if att:
-            self.predict_flow = conv_dilation(32, 2, 1)
-            self.predict_att = nn.Sequential(conv_dilation(32, 2, 1), nn.ReLU(inplace=True))
+            self.predict_flow = conv_dilation(batch_norm, 32, 2, 3, 1, 1)
+            self.predict_att = nn.Sequential(conv_dilation(batch_norm, 32, 2, 3, 1, 1), nn.ReLU(inplace=True))
+
+
+class ContextNetwork(_Context):
+    def __init__(self, ch_in, batch_norm=True, gen_flow_ds_factor=0):
+        super().__init__(ch_in, batch_norm, gen_flow_ds_factor, att=False)
+
+
+class ContextNetworkAtt(_Context):
+    def __init__(self, ch_in, batch_norm=True, gen_flow_ds_factor=0):
+        super().__init__(ch_in, batch_norm, gen_flow_ds_factor, att=True)
 
 
 def build_estimator(arch_estimator, ch_in, gen_flow_ds_factor=0, att=0):
@@ -125,19 +168,21 @@ def build_estimator(arch_estimator, ch_in, gen_flow_ds_factor=0, att=0):
     for the default argument; equality is used here, as the GAN variant does.  An unknown string
     returns None: the attribute stays undefined, as in the reference."""
     if arch_estimator == 'ContextNetwork':
-        if att not in (0, 1):
-            return None
-        return ContextNetwork(ch_in, gen_flow_ds_factor, att=bool(att))
-    if arch_estimator in DENSE_GROWTH:
-        return EstimatorDense(ch_in, DENSE_GROWTH[arch_estimator])
-    if arch_estimator == 'DenseNetTinyEarlyFusionSum':
-        return EstimatorDenseNetTinyEarlyFusion(ch_in, stack=False)
-    if arch_estimator == 'DenseNetTinyEarlyFusionStack':
-        return EstimatorDenseNetTinyEarlyFusion(ch_in, stack=True)
+        if att == 0:
+            return ContextNetwork(ch_in, True, gen_flow_ds_factor)
+        if att == 1:
+            return ContextNetworkAtt(ch_in, True, gen_flow_ds_factor)
+        return None
+    named = {'DenseNet': EstimatorDenseNet, 'DenseNetSmall': EstimatorDenseNetSmall,
+             'DenseNetTiny': EstimatorDenseNetTiny,
+             'DenseNetTinyEarlyFusionSum': EstimatorDenseNetTinyEarlyFusionSum,
+             'DenseNetTinyEarlyFusionStack': EstimatorDenseNetTinyEarlyFusionStack}
+    if arch_estimator in named:
+        return named[arch_estimator](ch_in)
     return None
 
 
-def discriminator_block(in_filters, out_filters, stride, bn):
+def _disc_block(in_filters, out_filters, stride, bn):
     """Conv(bias) -> LeakyReLU(0.2) -> Dropout2d(0.25) -> BatchNorm2d(out, eps=0.8)
     (code/dmcnet_GAN/model.py:254-279; the reference builds and discards a bn-less
     block first, which consumes one extra Conv2d init from the RNG)."""
@@ -149,19 +194,44 @@ def discriminator_block(in_filters, out_filters, stride, bn):
     return nn.Sequential(*layers)
 
 
+def discriminator_block(in_filters, out_filters, bn=True):
+    """Stride-2 block, code/dmcnet_GAN/model.py:254-265."""
+    return _disc_block(in_filters, out_filters, 2, bn)
+
+
+def discriminator_block2(in_filters, out_filters, bn=True):
+    """Stride-1 block, code/dmcnet_GAN/model.py:268-279."""
+    return _disc_block(in_filters, out_filters, 1, bn)
+
+
 class _Discriminator(nn.Module):
     """Discriminator / Discriminator2..5 parameter container (GAN/model.py:282-438)."""
 
     def __init__(self, arch_d, height=224, width=224):
         super().__init__()
         for name, ci, co, stride, bn in disc_blocks(arch_d):
-            setattr(self, 'discriminator_block_%s' % name, discriminator_block(ci, co, stride, bn))
+            setattr(self, 'discriminator_block_%s' % name, _disc_block(ci, co, stride, bn))
         fc_in = 32 * (height // 8) * (width // 8) if arch_d == 'Discriminator4' \
             else 128 * (height // 16) * (width // 16)
         self.adv_layer = nn.Linear(fc_in, 2)
 
     def forward(self, x):  # pragma: no cover
         raise NotImplementedError('the discriminator runs inside dmcnet_b200.engine.DmcEngine')
+
+
+def _named_discriminator(arch_d, doc):
+    def __init__(self, ch_in):
+        if ch_in != 2:
+            raise NotImplementedError('the discriminators take the 2-channel flow map (GAN/model.py:519-529)')
+        _Discriminator.__init__(self, arch_d)
+    return type(arch_d, (_Discriminator,), {'__init__': __init__, '__doc__': doc})
+
+
+Discriminator = _named_discriminator('Discriminator', 'code/dmcnet_GAN/model.py:282-300')
+Discriminator2 = _named_discriminator('Discriminator2', 'code/dmcnet_GAN/model.py:303-329')
+Discriminator3 = _named_discriminator('Discriminator3', 'code/dmcnet_GAN/model.py:332-366')
+Discriminator4 = _named_discriminator('Discriminator4', 'code/dmcnet_GAN/model.py:369-385')
+Discriminator5 = _named_discriminator('Discriminator5', 'code/dmcnet_GAN/model.py:388-438')
 
 
 DISCRIMINATORS = ('Discriminator', 'Discriminator2', 'Discriminator3', 'Discriminator4', 'Discriminator5')
@@ -246,7 +316,7 @@ Initializing model:
         if gen is not None:
             self.gen_flow_model = gen
         if self.arch_d is not None and self.arch_d in DISCRIMINATORS:
-            self.discriminator = _Discriminator(self.arch_d)
+            self.discriminator = globals()[self.arch_d](2)
 
     def _prepare_tsn(self, num_class):
         feature_dim = self.base_model.fc.in_features

@@ -481,3 +481,50 @@ def test_oracle_with_wider_dense_estimators_pinned_against_reference(arch):
         r_out, r_gen = ref(mv, res)
         o_out, o_gen = O.model_forward({k: v.clone() for k, v in sd.items()}, mv, res, train=False)
     assert torch.equal(r_out, o_out) and torch.equal(r_gen, o_gen)
+
+
+def test_dropin_modules_export_every_public_name_of_the_reference_with_its_signature():
+    """``from model import X`` for every class / helper of code/dmcnet/model.py and
+    code/dmcnet_GAN/model.py; with /root/reference present each one is constructed with the
+    reference's own arguments under the same seed and its state_dict compared bit for bit."""
+    import importlib.util, inspect, os
+    from oracle import ref_loader as R
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mods = {}
+    for variant in ('dmcnet', 'dmcnet_GAN'):
+        spec = importlib.util.spec_from_file_location('_dropin_%s' % variant,
+                                                      os.path.join(root, 'dmcnet_b200', 'dropin', variant, 'model.py'))
+        mods[variant] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[variant])
+    cases = [('ContextNetwork', (5, True, 0)), ('ContextNetwork', (5, True, 4)), ('ContextNetwork', (5, False, 0)),
+             ('ContextNetworkAtt', (5, True, 0)), ('EstimatorDenseNet', (5,)), ('EstimatorDenseNetSmall', (5,)),
+             ('EstimatorDenseNetTiny', (5,)), ('EstimatorDenseNetTinyEarlyFusionSum', (5,)),
+             ('EstimatorDenseNetTinyEarlyFusionStack', (5,)), ('conv', (5, 8)), ('predict_flow', (33,)),
+             ('conv_dilation', (True, 5, 32, 3, 1, 2)), ('conv_dilation', (False, 5, 32, 3, 1, 2))]
+    gan_cases = cases + [('Discriminator%s' % n, (2,)) for n in ('', '2', '3', '4', '5')] + \
+        [('discriminator_block', (2, 16, False)), ('discriminator_block', (16, 32, True)),
+         ('discriminator_block2', (16, 16, True))]
+    for variant, todo in (('dmcnet', cases), ('dmcnet_GAN', gan_cases)):
+        ours = mods[variant]
+        ref = R.load_reference_model_module(variant) if R.reference_available() else None
+        assert inspect.isclass(ours.Model) and issubclass(ours.Flatten, torch.nn.Module)
+        assert ours.Flatten()(torch.zeros(2, 3, 4)).shape == (2, 12)
+        for name, args in todo:
+            assert hasattr(ours, name), (variant, name)
+            torch.manual_seed(7)
+            a = getattr(ours, name)(*args)
+            if ref is None:
+                continue
+            torch.manual_seed(7)
+            b = getattr(ref, name)(*args)
+            sa, sb = a.state_dict(), b.state_dict()
+            assert list(sa) == list(sb), (variant, name)
+            assert all(torch.equal(sa[k], sb[k]) for k in sa), (variant, name)
+            assert type(a).__name__ == type(b).__name__
+            pa = list(inspect.signature(getattr(ours, name)).parameters)
+            pb = list(inspect.signature(getattr(ref, name)).parameters)
+            assert pa == pb, (variant, name, pa, pb)
+        if ref is not None:
+            pa = inspect.signature(ours.Model.__init__).parameters
+            pb = inspect.signature(ref.Model.__init__).parameters
+            assert list(pa) == list(pb) and all(pa[k].default == pb[k].default for k in pa), variant
