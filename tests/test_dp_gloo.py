@@ -108,3 +108,67 @@ def test_two_rank_gradient_allreduce_matches_reference_semantics():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret['worst'] < 1e-5, ret['worst']
+
+
+# ---------------------------------------------------------------- the real FusedTrainStep, two ranks
+def _trainer_worker(rank, world, port, ret):
+    """Each rank: FusedTrainStep(world_size=2) on a simulated engine (tests/sim_engine.py) fed with
+    its shard of clips; the step's own all-reduce + Adam must leave every rank with the parameters
+    that ONE Adam step on the summed shard gradients gives (the reference: nn.DataParallel gathers
+    the outputs, takes global-mean losses, reduces the replica gradients, steps once)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _pytest.monkeypatch import MonkeyPatch
+    from sim_engine import SimEngine, patch_ops
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    mp_ = MonkeyPatch()
+    patch_ops(mp_)
+    try:
+        B, C = 4, 11
+        sd = O.build_state(C, None, seed=1)
+        flow, mv, res, target = O.make_inputs(B, 3, C, seed=0, hw=HW)
+        lo, hi = T.shard_range(rank, world, B)
+        eng = SimEngine(C, 3, (hi - lo) * 3, height=HW, width=HW)
+        eng.load_state(sd)
+        hp = T.HParams()
+        tr = T.FusedTrainStep(eng, hp, hi - lo, world_size=world)
+        m = tr.step(flow[lo:hi], mv[lo:hi], res[lo:hi], target[lo:hi])
+        mine = {k: eng.param_view(k).clone() for k in eng.specs}
+        # every rank holds the same parameters after the step
+        flat = torch.cat([v.reshape(-1) for v in mine.values()])
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        same = bool(torch.equal(flat, other))
+        if rank == 0:
+            tot = None
+            for r in range(world):
+                a, b = T.shard_range(r, world, B)
+                g = _shard_grads(sd, flow, mv, res, target, a, b,
+                                 T.loss_grad_scales(hp, b - a, world, (b - a) * 3, HW, HW))
+                tot = g if tot is None else {k: tot[k] + g[k] for k in g}
+            ref = O.OracleTrainer(sd, O.HParams(), gan=False)
+            ref._zero()
+            for k, v in ref.st.items():
+                if not O.is_buffer(k):
+                    v.grad = tot[k].clone()
+            ref.opt_cls.step()
+            ref.opt_gf.step()
+            worst = max(float((mine[k] - ref.st[k].detach()).abs().max() / (ref.st[k].detach().abs().max() + 1e-12))
+                        for k in mine)
+            ret['worst'], ret['loss_cls'] = worst, m['loss_cls']
+        ret['same_%d' % rank] = same
+        dist.barrier()
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def test_two_rank_fused_step_matches_one_adam_step_on_the_summed_gradients():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_trainer_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret['same_0'] and ret['same_1']
+        assert ret['worst'] < 2e-5, ret['worst']
