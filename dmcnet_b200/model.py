@@ -389,11 +389,11 @@ Initializing model:
         """code/dmcnet/model.py:369-378 (needs the reference's transforms module on sys.path)."""
         import torchvision
         from transforms import GroupMultiScaleCrop, GroupRandomHorizontalFlip
-        scales = [1, .875, .75] if self._representation in ['mv', 'residual'] else [1, .875, .75, .66]
+        scales = [1, .875, .75] if self._representation in ['mv', 'residual', 'flow'] else [1, .875, .75, .66]
         print('Augmentation scales:', scales)
         return torchvision.transforms.Compose(
             [GroupMultiScaleCrop(self._input_size, scales),
-             GroupRandomHorizontalFlip(is_mv=(self._representation == 'mv'))])
+             GroupRandomHorizontalFlip()])
 
 
 class Model(DmcModel):

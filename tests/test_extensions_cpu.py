@@ -528,3 +528,33 @@ def test_dropin_modules_export_every_public_name_of_the_reference_with_its_signa
             pa = inspect.signature(ours.Model.__init__).parameters
             pb = inspect.signature(ref.Model.__init__).parameters
             assert list(pa) == list(pb) and all(pa[k].default == pb[k].default for k in pa), variant
+
+
+def test_get_augmentation_composes_the_reference_transforms():
+    """Model.get_augmentation (code/dmcnet/model.py:369-378) with the reference's own transforms
+    module: multi-scale crop to 224 then the random flip that negates the x components."""
+    import os, random, sys
+    from oracle import ref_loader as R
+    if not R.reference_available():
+        pytest.skip('/root/reference not present')
+    d = os.path.join(R.REFERENCE_ROOT, 'code', 'dmcnet')
+    saved = sys.modules.pop('transforms', None)
+    sys.path.insert(0, d)
+    try:
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()) as out:
+            aug = _our_model('DenseNetTiny', 0, 0).get_augmentation()
+        assert 'Augmentation scales: [1, 0.875, 0.75]' in out.getvalue()
+        names = [type(t).__name__ for t in aug.transforms]
+        assert names == ['GroupMultiScaleCrop', 'GroupRandomHorizontalFlip']
+        assert aug.transforms[0].scales == [1, .875, .75] and aug.transforms[0].input_size == [224, 224]
+        random.seed(3)
+        rng = np.random.default_rng(0)
+        group = [rng.integers(0, 256, (256, 340, 7), dtype=np.uint8) for _ in range(3)]
+        res = aug(group)
+        assert len(res) == 3 and all(r.shape == (224, 224, 7) for r in res)
+    finally:
+        sys.path.remove(d)
+        sys.modules.pop('transforms', None)
+        if saved is not None:
+            sys.modules['transforms'] = saved
