@@ -101,6 +101,100 @@ flow_block_mean_u8_kernel(const unsigned char* __restrict__ frames, int H, int W
   }
 }
 
+// ---- the same two stages with GroupRandomHorizontalFlip folded in (code/dmcnet/transforms.py:47-58).
+// A flipped frame is mirrored left-right and its x components (channel 0 = flow x, channel 2 = mv x)
+// become 256 - v: the reference computes (v - 128) * (-1) + 128 in int32, so v = 0 gives 256 -- a value
+// a uint8 stack cannot hold, which is why the flip has to happen here and not on the host.
+__global__ void __launch_bounds__(256)
+unpack_normalize_flip_u8_kernel(const unsigned int* __restrict__ frames,
+                                const unsigned char* __restrict__ flip, long groups, int hw4, int w4,
+                                float div_motion, float div_r0, float div_r1, float div_r2,
+                                float* __restrict__ flow, float* __restrict__ mv, float* __restrict__ res) {
+  const float divs[7] = {div_motion, div_motion, div_motion, div_motion, div_r0, div_r1, div_r2};
+  for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups;
+       g += (long)gridDim.x * blockDim.x) {
+    const long n = g / hw4;
+    const long p4 = g - n * hw4;
+    const bool f = flip[n] != 0;
+    long src = g;
+    if (f) {                               // the mirrored 4 pixels are another aligned group of the row
+      const long row = p4 / w4, cg = p4 - row * w4;
+      src = n * hw4 + row * w4 + (w4 - 1 - cg);
+    }
+    unsigned int w[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = __ldg(frames + src * 7 + k);
+    float out[7][4];
+#pragma unroll
+    for (int b = 0; b < 28; ++b) {
+      const unsigned int byte = (w[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      const int c = b % 7, p = b / 7;
+      float v = (float)byte;
+      if (f && (c == 0 || c == 2)) v = 256.0f - v;      // exact in fp32
+      const float r = normalize_u8(v, divs[c]);
+      if (f) out[c][3 - p] = r; else out[c][p] = r;
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      float* base;
+      if (c < 2) {
+        if (flow == nullptr) continue;
+        base = flow + ((n * 2 + c) * hw4 + p4) * 4;
+      } else if (c < 4) {
+        base = mv + ((n * 2 + (c - 2)) * hw4 + p4) * 4;
+      } else {
+        base = res + ((n * 3 + (c - 4)) * hw4 + p4) * 4;
+      }
+      *reinterpret_cast<float4*>(base) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+    }
+  }
+}
+
+// Block means of a flipped frame: the flip precedes block_reduce in the reference
+// (dataset.py:215 then :226-246), so block bx of the output is block nbx-1-bx of the stored frame
+// (W must be a multiple of f for the blocks to coincide) and channel 0 averages 256 - v.
+__global__ void __launch_bounds__(256)
+flow_block_mean_flip_u8_kernel(const unsigned char* __restrict__ frames,
+                               const unsigned char* __restrict__ flip, int H, int W, int f,
+                               float div_motion, float* __restrict__ flow) {
+  __shared__ int s_sum[2 * kMaxBlockCols];
+  __shared__ float s_val[2 * kMaxBlockCols];
+  const int by = blockIdx.x, n = blockIdx.y;
+  const bool fl = flip[n] != 0;
+  const int nbx = W / f;                      // host guarantees W % f == 0
+  const int y0 = by * f;
+  const int rows = min(f, H - y0);
+  for (int i = threadIdx.x; i < 2 * nbx; i += blockDim.x) s_sum[i] = 0;
+  __syncthreads();
+  const int items = rows * nbx * 2;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int c = it & 1;
+    const int bx = (it >> 1) % nbx;
+    const int r = (it >> 1) / nbx;
+    const unsigned char* p = frames + (((long)n * H + y0 + r) * W + bx * f) * 7 + c;
+    int s = 0;
+    for (int x = 0; x < f; ++x, p += 7) s += (int)__ldg(p);
+    atomicAdd(&s_sum[c * nbx + bx], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * nbx; i += blockDim.x) {
+    const int c = i / nbx, bx = i - c * nbx;
+    int s = s_sum[c * nbx + (fl ? nbx - 1 - bx : bx)];
+    if (fl && c == 0) s = 256 * rows * f - s;            // sum of (256 - v) over the valid pixels
+    const float mean = (float)((double)s / (double)(f * f));
+    s_val[i] = normalize_u8(mean, div_motion);
+  }
+  __syncthreads();
+  const int per_c = rows * W;
+  for (int idx = threadIdx.x; idx < 2 * per_c; idx += blockDim.x) {
+    const int c = idx / per_c;
+    const int rem = idx - c * per_c;
+    const int r = rem / W;
+    const int x = rem - r * W;
+    flow[(((long)n * 2 + c) * H + y0 + r) * W + x] = s_val[c * nbx + x / f];
+  }
+}
+
 }  // namespace dmc
 
 using namespace dmc;
@@ -147,4 +241,48 @@ extern "C" int dmc_flow_block_mean_u8(const unsigned char* frames, int N, int H,
   DMC_REQUIRE((long)factor * factor * 255 < 2147483647L, "flow_block_mean_u8: factor too large");
   flow_block_mean_u8_kernel<<<dim3(nby, N), 256, 0, ST_(stream)>>>(frames, H, W, factor, div_motion, flow);
   return dmc_check_launch("flow_block_mean_u8_kernel");
+}
+
+// dmc_unpack_normalize_u8 with GroupRandomHorizontalFlip (code/dmcnet/transforms.py:47-58) folded in:
+// flip[n] != 0 mirrors frame n left-right and replaces its x components (channels 0 and 2) by 256 - v
+// before the normalisation.  flip: uint8 [N] on the device.  W must be a multiple of 4.
+extern "C" int dmc_unpack_normalize_flip_u8(const unsigned char* frames, const unsigned char* flip,
+                                            int N, int H, int W, float div_motion, float div_r0,
+                                            float div_r1, float div_r2, float* flow, float* mv,
+                                            float* res, void* stream) {
+  DMC_REQUIRE(N > 0 && H > 0 && W > 0, "unpack_normalize_flip_u8: bad shape");
+  DMC_REQUIRE(W % 4 == 0, "unpack_normalize_flip_u8: W must be a multiple of 4");
+  DMC_REQUIRE(frames && flip && mv && res, "unpack_normalize_flip_u8: null pointer");
+  DMC_REQUIRE((reinterpret_cast<size_t>(frames) & 3) == 0, "unpack_normalize_flip_u8: frames must be 4-byte aligned");
+  DMC_REQUIRE(((reinterpret_cast<size_t>(flow) | reinterpret_cast<size_t>(mv) |
+                reinterpret_cast<size_t>(res)) & 15) == 0,
+              "unpack_normalize_flip_u8: outputs must be 16-byte aligned");
+  DMC_REQUIRE(div_motion != 0.f && div_r0 != 0.f && div_r1 != 0.f && div_r2 != 0.f,
+              "unpack_normalize_flip_u8: zero divisor");
+  const int w4 = W / 4, hw4 = H * w4;
+  const long groups = (long)N * hw4;
+  long blocks = cdiv(groups, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_normalize_flip_u8_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(
+      reinterpret_cast<const unsigned int*>(frames), flip, groups, hw4, w4, div_motion, div_r0, div_r1,
+      div_r2, flow, mv, res);
+  return dmc_check_launch("unpack_normalize_flip_u8_kernel");
+}
+
+// dmc_flow_block_mean_u8 for frames that may be flipped (flip: uint8 [N] on the device): the flip
+// precedes the block mean in the reference, so W must be a multiple of factor.
+extern "C" int dmc_flow_block_mean_flip_u8(const unsigned char* frames, const unsigned char* flip,
+                                           int N, int H, int W, int factor, float div_motion,
+                                           float* flow, void* stream) {
+  DMC_REQUIRE(N > 0 && H > 0 && W > 0 && factor >= 1, "flow_block_mean_flip_u8: bad shape");
+  DMC_REQUIRE(frames && flip && flow, "flow_block_mean_flip_u8: null pointer");
+  DMC_REQUIRE(div_motion != 0.f, "flow_block_mean_flip_u8: zero divisor");
+  DMC_REQUIRE(W % factor == 0, "flow_block_mean_flip_u8: W must be a multiple of factor");
+  const int nbx = W / factor, nby = (H + factor - 1) / factor;
+  DMC_REQUIRE(nbx <= kMaxBlockCols, "flow_block_mean_flip_u8: more than 256 blocks per row");
+  DMC_REQUIRE(N <= 65535, "flow_block_mean_flip_u8: more than 65535 frames per call");
+  DMC_REQUIRE((long)factor * factor * 256 < 2147483647L, "flow_block_mean_flip_u8: factor too large");
+  flow_block_mean_flip_u8_kernel<<<dim3(nby, N), 256, 0, ST_(stream)>>>(frames, flip, H, W, factor,
+                                                                         div_motion, flow);
+  return dmc_check_launch("flow_block_mean_flip_u8_kernel");
 }

@@ -59,9 +59,26 @@ class U8InputStage:
     def h2d_bytes(self) -> int:
         return self._stack.numel()
 
+    def _flip_flags(self, flip) -> torch.Tensor:
+        """Per-frame uint8 flags on the device from per-clip or per-frame booleans: the reference
+        draws ONE flip decision per sample, i.e. for all segments of a clip (transforms.py:48-49)."""
+        f = torch.as_tensor(flip).reshape(-1).to(torch.uint8)
+        if f.numel() == 0 or self.N % f.numel():
+            raise ValueError('flip has %d entries for %d frames' % (f.numel(), self.N))
+        f = f.repeat_interleave(self.N // f.numel())
+        if self.W % 4 or (self.factor and self.W % self.factor):
+            raise ValueError('flipping on the device needs a width that is a multiple of 4 and of '
+                             'flow_ds_factor (so mirrored pixel groups / blocks coincide)')
+        return f.to(self.device, non_blocking=True).contiguous()
+
     def __call__(self, frames_u8: torch.Tensor, out_flow: Optional[torch.Tensor] = None,
-                 out_mv: Optional[torch.Tensor] = None, out_res: Optional[torch.Tensor] = None):
+                 out_mv: Optional[torch.Tensor] = None, out_res: Optional[torch.Tensor] = None,
+                 flip=None):
         """frames_u8: uint8 [..., H, W, 7] (host, ideally pinned, or device) holding N frames.
+        flip: optional booleans, one per clip (or per frame): the random horizontal flip of
+        GroupRandomHorizontalFlip (code/dmcnet/transforms.py:47-58) applied on the device -- mirrored
+        frame, x components of flow and mv become 256 - v (a value a uint8 stack cannot carry, so the
+        host must NOT pre-flip).
         Returns (input_flow [N,2,H,W], input_mv [N,2,H,W], input_residual [N,3,H,W]) fp32 on the
         device, written into the given tensors when provided."""
         N, H, W = self.N, self.H, self.W
@@ -74,6 +91,14 @@ class U8InputStage:
             if t.numel() != N * c * H * W:
                 raise ValueError('output tensor has %d elements, expected %d' % (t.numel(), N * c * H * W))
         self._stack.copy_(frames_u8.reshape(N, H, W, 7), non_blocking=True)
+        if flip is not None:
+            ff = self._flip_flags(flip)
+            with_flow = out_flow if self.factor == 0 else None
+            ops.unpack_normalize_flip_u8(self._stack, ff, N, H, W, self.div_motion, self.div_res, with_flow,
+                                         out_mv, out_res)
+            if self.factor:
+                ops.flow_block_mean_flip_u8(self._stack, ff, N, H, W, self.factor, self.div_motion, out_flow)
+            return out_flow, out_mv, out_res
         if self.factor == 0:
             ops.unpack_normalize_u8(self._stack, N, H, W, self.div_motion, self.div_res, out_flow, out_mv,
                                     out_res)

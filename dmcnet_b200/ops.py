@@ -366,6 +366,19 @@ def flow_block_mean_u8(frames, N, H, W, factor, div_motion, flow):
           c_float(div_motion), _ptr(flow, F32), _stream())
 
 
+def unpack_normalize_flip_u8(frames, flip, N, H, W, div_motion, div_res, flow, mv, res):
+    """unpack_normalize_u8 with the random horizontal flip of code/dmcnet/transforms.py:47-58 folded
+    in; flip: uint8 [N] on the device (non-zero = mirrored frame, x components 256 - v)."""
+    _call('dmc_unpack_normalize_flip_u8', _ptr(frames, U8), _ptr(flip, U8), c_int(N), c_int(H), c_int(W),
+          c_float(div_motion), c_float(div_res[0]), c_float(div_res[1]), c_float(div_res[2]),
+          _ptr(flow, F32), _ptr(mv, F32), _ptr(res, F32), _stream())
+
+
+def flow_block_mean_flip_u8(frames, flip, N, H, W, factor, div_motion, flow):
+    _call('dmc_flow_block_mean_flip_u8', _ptr(frames, U8), _ptr(flip, U8), c_int(N), c_int(H), c_int(W),
+          c_int(factor), c_float(div_motion), _ptr(flow, F32), _stream())
+
+
 def dense_dgrad_weights(params, table, out):
     _call('dmc_dense_dgrad_weights', _ptr(params, F32), _iarr(table), _ptr(out, F32), _stream())
 

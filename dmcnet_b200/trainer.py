@@ -353,7 +353,7 @@ class FusedTrainStep:
         self.in_res.copy_(input_residual.reshape(-1, 3, H, W), non_blocking=True)
         self.target.copy_(target, non_blocking=True)
 
-    def load_inputs_u8(self, frames_u8, target, flow_ds_factor: int = 0):
+    def load_inputs_u8(self, frames_u8, target, flow_ds_factor: int = 0, flip=None):
         """Stage one batch given as the uint8 stack [B,S,H,W,7] the augmentation produces
         (flow | mv | residual channels, code/dmcnet/dataset.py:210): split, block-mean flow
         target (--flow_ds_factor) and normalisation run on the device (input_stage.py), so the
@@ -364,13 +364,14 @@ class FusedTrainStep:
             st = U8InputStage(self.eng.N, self.eng.H, self.eng.W, flow_ds_factor=flow_ds_factor,
                               device=self.eng.device)
             self._u8_stages[flow_ds_factor] = st
-        st(frames_u8, self.in_flow, self.in_mv, self.in_res)
+        st(frames_u8, self.in_flow, self.in_mv, self.in_res, flip=flip)
         self.target.copy_(target, non_blocking=True)
 
     def step_u8(self, frames_u8, target, masks: Optional[Sequence[torch.Tensor]] = None,
-                flow_ds_factor: int = 0, apply: bool = True, metrics: bool = True) -> Dict[str, float]:
-        """``step`` fed with the uint8 sample stack (see ``load_inputs_u8``)."""
-        self.load_inputs_u8(frames_u8, target, flow_ds_factor)
+                flow_ds_factor: int = 0, apply: bool = True, metrics: bool = True, flip=None) -> Dict[str, float]:
+        """``step`` fed with the uint8 sample stack (see ``load_inputs_u8``); ``flip``: one boolean
+        per clip, the random horizontal flip applied on the device (``U8InputStage``)."""
+        self.load_inputs_u8(frames_u8, target, flow_ds_factor, flip)
         return self._step_staged(masks, apply, metrics)
 
     def step(self, input_flow, input_mv, input_residual, target,

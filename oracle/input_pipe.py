@@ -36,6 +36,19 @@ def block_reduce(image: np.ndarray, block_size: Sequence[int], func=np.mean, cva
     return func(blocked, axis=tuple(range(1, 2 * image.ndim, 2)))
 
 
+def flip_group(img_group: Sequence[np.ndarray]):
+    """The flipped branch of GroupRandomHorizontalFlip.__call__ (code/dmcnet/transforms.py:49-57):
+    mirror, then negate the x components of flow (channel 0) and mv (channel 2) around 128 in int32.
+    Note v = 0 -> 256: the result no longer fits uint8."""
+    ret = [img[:, ::-1, :].astype(np.int32) for img in img_group]
+    for i in range(len(ret)):
+        ret[i][:, :, :4] -= 128
+        ret[i][..., 0] *= (-1)
+        ret[i][..., 2] *= (-1)
+        ret[i][:, :, :4] += 128
+    return ret
+
+
 def sample_from_frames(frames: Sequence[np.ndarray], flow_ds_factor: int = 0
                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """dataset.py:215-263 for representation == 'mv', upsample_interp == False.

@@ -34,8 +34,11 @@ from oracle import input_pipe as P                      # noqa: E402
 from oracle import ref_loader as R                      # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'input_pipe.npz')
-CASES = [('s3_64x64_f0', 3, 64, 64, 0), ('s3_64x64_f16', 3, 64, 64, 16), ('s2_40x36_f16', 2, 40, 36, 16),
-         ('s2_32x48_f8', 2, 32, 48, 8)]
+CASES = [('s3_64x64_f0', 3, 64, 64, 0, False), ('s3_64x64_f16', 3, 64, 64, 16, False),
+         ('s2_40x36_f16', 2, 40, 36, 16, False), ('s2_32x48_f8', 2, 32, 48, 8, False),
+         # GroupRandomHorizontalFlip of the reference's transforms.py forced to flip
+         ('s3_64x64_f0_flip', 3, 64, 64, 0, True), ('s3_64x64_f16_flip', 3, 64, 64, 16, True),
+         ('s2_40x48_f8_flip', 2, 40, 48, 8, True)]
 
 
 def _load_reference_dataset(variant: str, decoded):
@@ -72,9 +75,21 @@ def _load_reference_dataset(variant: str, decoded):
     return mod
 
 
-def reference_sample(variant: str, segments: int, height: int, width: int, factor: int, seed: int):
+def _reference_flip(variant: str):
+    """The reference's own GroupRandomHorizontalFlip (code/<variant>/transforms.py:47-58)."""
+    d = os.path.join(R.REFERENCE_ROOT, 'code', variant)
+    spec = importlib.util.spec_from_file_location('_ref_%s_transforms' % variant, os.path.join(d, 'transforms.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_sample(variant: str, segments: int, height: int, width: int, factor: int, seed: int,
+                     flip: bool = False):
     """Run the reference's CoviarDataSet on synthetic decoded data.
-    Returns (frames uint8 [S,H,W,7] as the reference assembled them, flow, mv, residual)."""
+    Returns (frames uint8 [S,H,W,7] as the reference assembled them, flow, mv, residual).
+    flip: the dataset's transform is the reference's GroupRandomHorizontalFlip with its coin forced
+    to 'flip' (random.random -> 0.0 for that call)."""
     from PIL import Image
     rng = np.random.default_rng(seed)
     num_frames, gop = 40, 12
@@ -88,6 +103,7 @@ def reference_sample(variant: str, segments: int, height: int, width: int, facto
         for idx in range(1, num_frames + 1):
             for ax in 'xy':
                 img = np.clip(np.round(128 + 30 * rng.standard_normal((height, width))), 0, 255).astype(np.uint8)
+                img[0, :4], img[1, :4] = 0, 255              # extremes (0 becomes 256 under the flip)
                 Image.fromarray(img, mode='L').save(os.path.join(flow_dir, 'flow_%s_%05d.jpg' % (ax, idx)),
                                                     format='PNG')
             open(os.path.join(flow_dir, 'img_%05d.jpg' % idx), 'wb').close()   # /3 in dataset.py:127
@@ -95,15 +111,25 @@ def reference_sample(variant: str, segments: int, height: int, width: int, facto
             for p in range(gop):
                 # raw decoder output: signed, beyond +-128 in places so the clip at :200-208 is exercised
                 decoded[(g, p, 1)] = np.round(40 * rng.standard_normal((height, width, 2))).astype(np.int32)
+                decoded[(g, p, 1)][2, :4], decoded[(g, p, 1)][3, :4] = -200, 200      # clip to 0 / 255
                 decoded[(g, p, 2)] = np.round(60 * rng.standard_normal((height, width, 3))).astype(np.int32)
         lst = os.path.join(tmp, 'list.txt')
         with open(lst, 'w') as f:
             f.write('%s.avi 0 7\n' % vid)
         mod = _load_reference_dataset(variant, decoded)
 
-        def transform(frames):                       # identity; records what the reference assembled
+        tmod = _reference_flip(variant) if flip else None
+
+        def transform(frames):                       # records what the reference assembled
             captured.append(np.array(frames))
-            return frames
+            if not flip:
+                return frames
+            saved = tmod.random.random
+            tmod.random.random = lambda: 0.0
+            try:
+                return tmod.GroupRandomHorizontalFlip()(frames)
+            finally:
+                tmod.random.random = saved
         kw = dict(mv_minmaxnorm=0) if variant == 'dmcnet_GAN' else {}
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):
@@ -120,10 +146,14 @@ def pin(write: bool = False, verbose: bool = True) -> int:
     """Number of compared tensors (raises on any bit difference)."""
     store, count = {}, 0
     for variant in ('dmcnet', 'dmcnet_GAN'):
-        for name, S, H, W, factor in CASES:
-            frames, flow, mv, res = reference_sample(variant, S, H, W, factor, seed=len(name) + S + factor)
+        for name, S, H, W, factor, flip in CASES:
+            frames, flow, mv, res = reference_sample(variant, S, H, W, factor, seed=len(name) + S + factor,
+                                                     flip=flip)
             assert frames.dtype == np.uint8 and frames.shape == (S, H, W, 7)
-            o_flow, o_mv, o_res = P.sample_from_frames(list(frames), factor)
+            if flip:
+                assert (frames[..., 0] == 0).any() and (frames[..., 2] == 0).any()   # v = 0 -> 256: beyond uint8
+            group = P.flip_group(list(frames)) if flip else list(frames)
+            o_flow, o_mv, o_res = P.sample_from_frames(group, factor)
             for tag, a, b in (('flow', o_flow, flow), ('mv', o_mv, mv), ('res', o_res, res)):
                 assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape, (variant, name, tag)
                 assert torch.equal(a, b), (variant, name, tag, float((a - b).abs().max()))
@@ -133,6 +163,7 @@ def pin(write: bool = False, verbose: bool = True) -> int:
                 store[name + '.flow'], store[name + '.mv'] = flow.numpy(), mv.numpy()
                 store[name + '.res'] = res.numpy()
                 store[name + '.factor'] = np.int64(factor)
+                store[name + '.flip'] = np.bool_(flip)
             if verbose:
                 print('pinned %-11s %-14s flow/mv/res bit-identical' % (variant, name))
     if write:

@@ -106,13 +106,14 @@ def test_video_scorer_refuses_to_run_without_a_gpu():
 
 
 # ------------------------------------------------------------------ uint8 input stage
-def _golden_cases(golden_dir):
+def _golden_cases(golden_dir, flipped=False):
     import os
     z = np.load(os.path.join(golden_dir, 'input_pipe.npz'))
     names = sorted({k.split('.')[0] for k in z.files})
-    assert len(names) == 4
+    assert len(names) == 7
     for n in names:
-        yield n, z[n + '.frames'], int(z[n + '.factor']), z[n + '.flow'], z[n + '.mv'], z[n + '.res']
+        if bool(z[n + '.flip']) == flipped:
+            yield n, z[n + '.frames'], int(z[n + '.factor']), z[n + '.flow'], z[n + '.mv'], z[n + '.res']
 
 
 def test_input_oracle_pinned_against_reference_dataset():
@@ -120,17 +121,22 @@ def test_input_oracle_pinned_against_reference_dataset():
     if not R.reference_available():
         pytest.skip('/root/reference not present')
     from oracle.pin_input_pipe import pin
-    assert pin(write=False, verbose=False) == 2 * 4 * 3
+    assert pin(write=False, verbose=False) == 2 * 7 * 3
 
 
 def test_input_oracle_reproduces_reference_golden(golden_dir):
     """tests/golden/input_pipe.npz holds outputs of the reference's own dataset.py."""
     from oracle import input_pipe as P
-    for name, frames, factor, flow, mv, res in _golden_cases(golden_dir):
-        o_flow, o_mv, o_res = P.sample_from_frames(list(frames), factor)
-        assert np.array_equal(o_flow.numpy(), flow), name
-        assert np.array_equal(o_mv.numpy(), mv), name
-        assert np.array_equal(o_res.numpy(), res), name
+    for flipped in (False, True):
+        n_cases = 0
+        for name, frames, factor, flow, mv, res in _golden_cases(golden_dir, flipped):
+            group = P.flip_group(list(frames)) if flipped else list(frames)
+            o_flow, o_mv, o_res = P.sample_from_frames(group, factor)
+            assert np.array_equal(o_flow.numpy(), flow), name
+            assert np.array_equal(o_mv.numpy(), mv), name
+            assert np.array_equal(o_res.numpy(), res), name
+            n_cases += 1
+        assert n_cases == (3 if flipped else 4)
 
 
 def _kernel_model_unpack(frames, div_motion, div_res):
@@ -162,6 +168,62 @@ def _kernel_model_block_mean(frames, f, div_motion):
             val = (mean / np.float32(255.0) - np.float32(0.5)) / np.float32(div_motion)
             out[:, :, by * f:by * f + f, bx * f:bx * f + f] = val[:, :, None, None]
     return out
+
+
+def _kernel_model_unpack_flip(frames, div_motion, div_res):
+    """numpy model of unpack_normalize_flip_u8_kernel with every frame flipped: output group cg of a
+    row reads source group w4-1-cg, pixel order inside the group reversed, channels 0 and 2 -> 256 - v."""
+    S, H, W, _ = frames.shape
+    w4 = W // 4
+    words = np.frombuffer(frames.tobytes(), dtype='<u4').reshape(S, H, w4, 7)
+    src = words[:, :, ::-1, :]                                   # src = row*w4 + (w4-1-cg)
+    out = np.zeros((7, S, H, w4, 4), np.float32)
+    divs = np.array([div_motion] * 4 + list(div_res), np.float32)
+    for b in range(28):
+        byte = ((src[..., b >> 2] >> np.uint32(8 * (b & 3))) & np.uint32(0xff)).astype(np.float32)
+        c, p = b % 7, b // 7
+        v = np.float32(256.0) - byte if c in (0, 2) else byte
+        out[c, ..., 3 - p] = (v / np.float32(255.0) - np.float32(0.5)) / divs[c]
+    planes = out.reshape(7, S, H, W)
+    split = lambda lo, hi: planes[lo:hi].transpose(1, 0, 2, 3)
+    return split(0, 2), split(2, 4), split(4, 7)
+
+
+def _kernel_model_block_mean_flip(frames, f, div_motion):
+    """numpy model of flow_block_mean_flip_u8_kernel with every frame flipped."""
+    S, H, W, _ = frames.shape
+    nbx = W // f
+    out = np.zeros((S, 2, H, W), np.float32)
+    for by in range(-(-H // f)):
+        rows = min(f, H - by * f)
+        for bx in range(nbx):
+            sb = nbx - 1 - bx
+            blk = frames[:, by * f:by * f + rows, sb * f:sb * f + f, 0:2].astype(np.int64)
+            s = blk.sum(axis=(1, 2))
+            s[:, 0] = 256 * rows * f - s[:, 0]
+            mean = (s.astype(np.float64) / np.float64(f * f)).astype(np.float32)
+            val = (mean / np.float32(255.0) - np.float32(0.5)) / np.float32(div_motion)
+            out[:, :, by * f:by * f + f, bx * f:bx * f + f] = val[:, :, None, None]
+    return out
+
+
+def test_input_kernels_flip_model_is_bit_exact(golden_dir):
+    """The flipped entry points against outputs of the reference's GroupRandomHorizontalFlip +
+    dataset.py (fixture cases *_flip; they contain v = 0 -> 256)."""
+    from dmcnet_b200.input_stage import normalisation_divisors
+    div_motion, div_res = normalisation_divisors()
+    n_cases = 0
+    for name, frames, factor, flow, mv, res in _golden_cases(golden_dir, flipped=True):
+        assert (frames[..., 0] == 0).any()
+        k_flow, k_mv, k_res = _kernel_model_unpack_flip(frames, div_motion, div_res)
+        assert np.array_equal(k_mv, mv) and np.array_equal(k_res, res), name
+        if factor == 0:
+            assert np.array_equal(k_flow, flow), name
+            assert flow.max() > (255 / 255.0 - 0.5) / div_motion          # the 256 is really there
+        else:
+            assert np.array_equal(_kernel_model_block_mean_flip(frames, factor, div_motion), flow), name
+        n_cases += 1
+    assert n_cases == 3
 
 
 def test_input_kernels_index_arithmetic_model_is_bit_exact(golden_dir):
