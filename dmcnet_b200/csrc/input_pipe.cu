@@ -195,6 +195,43 @@ flow_block_mean_flip_u8_kernel(const unsigned char* __restrict__ frames,
   }
 }
 
+// ---- crop + bilinear resize of the uint8 stacks (GroupMultiScaleCrop / GroupScale + GroupCenterCrop /
+// GroupOverSample of code/dmcnet/transforms.py:36-44, :60-114, :122-140: numpy crop, then
+// cv2.resize(..., INTER_LINEAR) per channel).  OpenCV's 8-bit linear resize is fixed point: 11-bit
+// coefficients, horizontal pass D = S[x0]*a0 + S[x1]*a1, vertical pass
+// ((b0*(D0>>4))>>16) + ((b1*(D1>>4))>>16) + 2) >> 2.  The host builds the index / coefficient tables
+// (float arithmetic as OpenCV, input_stage.resize_tables; source indices already include the crop
+// offset), so the kernel is pure integer arithmetic and bit-exact by construction.
+// tab: int32 [ntab][4*Wo + 4*Ho] = {x0[Wo], x1[Wo], a0[Wo], a1[Wo], y0[Ho], y1[Ho], b0[Ho], b1[Ho]};
+// frame n uses table n / frames_per_tab (one crop per clip).
+__global__ void __launch_bounds__(256)
+crop_resize_u8_kernel(const unsigned char* __restrict__ src, int Hs, int Ws,
+                      const int* __restrict__ tab, int frames_per_tab,
+                      unsigned char* __restrict__ out, int Ho, int Wo, long total) {
+  const int tstride = 4 * (Wo + Ho);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const long n = idx / ((long)Ho * Wo);
+    const int r = (int)(idx - n * (long)Ho * Wo);
+    const int dy = r / Wo, dx = r - dy * Wo;
+    const int* tx = tab + (n / frames_per_tab) * tstride;
+    const int* ty = tx + 4 * Wo;
+    const int x0 = __ldg(tx + dx), x1 = __ldg(tx + Wo + dx);
+    const int a0 = __ldg(tx + 2 * Wo + dx), a1 = __ldg(tx + 3 * Wo + dx);
+    const int y0 = __ldg(ty + dy), y1 = __ldg(ty + Ho + dy);
+    const int b0 = __ldg(ty + 2 * Ho + dy), b1 = __ldg(ty + 3 * Ho + dy);
+    const unsigned char* r0 = src + ((n * Hs + y0) * Ws) * 7;
+    const unsigned char* r1 = src + ((n * Hs + y1) * Ws) * 7;
+    unsigned char* o = out + idx * 7;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      const int d0 = (int)__ldg(r0 + x0 * 7 + c) * a0 + (int)__ldg(r0 + x1 * 7 + c) * a1;
+      const int d1 = (int)__ldg(r1 + x0 * 7 + c) * a0 + (int)__ldg(r1 + x1 * 7 + c) * a1;
+      o[c] = (unsigned char)((((b0 * (d0 >> 4)) >> 16) + ((b1 * (d1 >> 4)) >> 16) + 2) >> 2);
+    }
+  }
+}
+
 }  // namespace dmc
 
 using namespace dmc;
@@ -285,4 +322,21 @@ extern "C" int dmc_flow_block_mean_flip_u8(const unsigned char* frames, const un
   flow_block_mean_flip_u8_kernel<<<dim3(nby, N), 256, 0, ST_(stream)>>>(frames, flip, H, W, factor,
                                                                          div_motion, flow);
   return dmc_check_launch("flow_block_mean_flip_u8_kernel");
+}
+
+// out: uint8 [N][Ho][Wo][7] = crop + cv2.resize(INTER_LINEAR) of src uint8 [N][Hs][Ws][7]
+// (code/dmcnet/transforms.py:122-140; also GroupScale / GroupCenterCrop / GroupOverSample windows).
+// tab: device int32 [ntab][4*Wo + 4*Ho] built by the host (see the kernel comment); frame n uses table
+// n / frames_per_tab.  Every index in the tables must lie inside the source frame.
+extern "C" int dmc_crop_resize_u8(const unsigned char* src, int N, int Hs, int Ws, const int* tab,
+                                  int frames_per_tab, unsigned char* out, int Ho, int Wo, void* stream) {
+  DMC_REQUIRE(N > 0 && Hs > 0 && Ws > 0 && Ho > 0 && Wo > 0 && frames_per_tab > 0,
+              "crop_resize_u8: bad shape");
+  DMC_REQUIRE(src && tab && out, "crop_resize_u8: null pointer");
+  const long total = (long)N * Ho * Wo;
+  long blocks = cdiv(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  crop_resize_u8_kernel<<<(int)blocks, 256, 0, ST_(stream)>>>(src, Hs, Ws, tab, frames_per_tab, out, Ho,
+                                                               Wo, total);
+  return dmc_check_launch("crop_resize_u8_kernel");
 }

@@ -13,8 +13,10 @@ There is no CPU path: the stage needs a CUDA device and the built library.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import random as _random
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import ops
@@ -106,3 +108,116 @@ class U8InputStage:
             ops.unpack_normalize_u8(self._stack, N, H, W, self.div_motion, self.div_res, None, out_mv, out_res)
             ops.flow_block_mean_u8(self._stack, N, H, W, self.factor, self.div_motion, out_flow)
         return out_flow, out_mv, out_res
+
+
+# ------------------------------------------------------------------ crop + resize (transforms.py)
+INTER_RESIZE_COEF_SCALE = 2048          # OpenCV's 11-bit fixed point of the 8-bit linear resize
+
+
+def resize_tables(src_len: int, dst_len: int, horizontal: bool, offset: int = 0, frame_len: Optional[int] = None):
+    """Index / coefficient tables of ``cv2.resize(..., INTER_LINEAR)`` on uint8 along one axis, the way
+    OpenCV computes them (double for the position, float for the fraction, coefficients rounded to 11
+    bits).  The horizontal pass resets the fraction at the borders; the vertical pass only clamps the
+    two row indices.  Returns int32 arrays (i0, i1, a0, a1); indices are shifted by ``offset`` (the
+    crop origin inside a frame of ``frame_len`` pixels)."""
+    scale = 1.0 / (dst_len / src_len)
+    i0 = np.zeros(dst_len, np.int32)
+    i1 = np.zeros(dst_len, np.int32)
+    a0 = np.zeros(dst_len, np.int32)
+    a1 = np.zeros(dst_len, np.int32)
+    for d in range(dst_len):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if horizontal:
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= src_len - 1:
+                f, s = np.float32(0), src_len - 1
+        i0[d] = min(max(s, 0), src_len - 1) + offset
+        i1[d] = min(max(s + 1, 0), src_len - 1) + offset
+        a0[d] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(INTER_RESIZE_COEF_SCALE))))
+        a1[d] = int(np.rint(np.float32(f * np.float32(INTER_RESIZE_COEF_SCALE))))
+    if frame_len is not None and (i0.min() < 0 or i1.max() >= frame_len):
+        raise ValueError('crop [%d, %d) leaves the frame of %d pixels' % (offset, offset + src_len, frame_len))
+    return i0, i1, a0, a1
+
+
+def crop_tables(row0: int, col0: int, rows: int, cols: int, out_h: int, out_w: int,
+                frame_h: Optional[int] = None, frame_w: Optional[int] = None) -> np.ndarray:
+    """One table row of ``dmc_crop_resize_u8``: ``img[row0:row0+rows, col0:col0+cols]`` resized to
+    (out_h, out_w).  Layout {x0, x1, a0, a1 [out_w] | y0, y1, b0, b1 [out_h]}."""
+    x = resize_tables(cols, out_w, True, col0, frame_w)
+    y = resize_tables(rows, out_h, False, row0, frame_h)
+    return np.concatenate(list(x) + list(y)).astype(np.int32)
+
+
+def scaled_crop_tables(frame_h: int, frame_w: int, scale_h: int, scale_w: int, row0: int, col0: int,
+                       out_h: int, out_w: int) -> np.ndarray:
+    """GroupScale to (scale_h, scale_w) followed by the crop window [row0:row0+out_h, col0:col0+out_w]
+    of the scaled frame (GroupCenterCrop / one GroupOverSample window, transforms.py:36-44, :78-114):
+    the window's rows of the full-frame resize tables."""
+    x = [t[col0:col0 + out_w] for t in resize_tables(frame_w, scale_w, True)]
+    y = [t[row0:row0 + out_h] for t in resize_tables(frame_h, scale_h, False)]
+    if len(x[0]) != out_w or len(y[0]) != out_h:
+        raise ValueError('crop window leaves the scaled frame')
+    return np.concatenate(x + y).astype(np.int32)
+
+
+def multi_scale_crop_pairs(im_rows: int, im_cols: int, input_size: Sequence[int], scales: Sequence[float],
+                           max_distort: int = 1) -> List[Tuple[int, int]]:
+    """Candidate (crop_rows, crop_cols) of GroupMultiScaleCrop._sample_crop_size
+    (code/dmcnet/transforms.py:142-157; the reference calls the row extent 'w')."""
+    base = min(im_rows, im_cols)
+    sizes = [int(base * x) for x in scales]
+    crop_h = [input_size[1] if abs(x - input_size[1]) < 3 else x for x in sizes]
+    crop_w = [input_size[0] if abs(x - input_size[0]) < 3 else x for x in sizes]
+    return [(w, h) for i, h in enumerate(crop_h) for j, w in enumerate(crop_w) if abs(i - j) <= max_distort]
+
+
+def sample_multi_scale_crop(im_rows: int, im_cols: int, input_size: Sequence[int] = (224, 224),
+                            scales: Sequence[float] = (1, .875, .75), max_distort: int = 1,
+                            rng=_random) -> Tuple[int, int, int, int]:
+    """(row0, col0, rows, cols) drawn with the reference's calls to ``random`` in the reference's order
+    (``choice`` of the pair, then ``randint`` for each offset; transforms.py:159-163, fix_crop=False)."""
+    rows, cols = rng.choice(multi_scale_crop_pairs(im_rows, im_cols, list(input_size), list(scales), max_distort))
+    row0 = rng.randint(0, im_rows - rows)
+    col0 = rng.randint(0, im_cols - cols)
+    return row0, col0, rows, cols
+
+
+def oversample_offsets(scaled_rows: int, scaled_cols: int, crop_rows: int, crop_cols: int) -> List[Tuple[int, int]]:
+    """The five (row0, col0) windows of GroupOverSample (fill_fix_offset(False, ...),
+    transforms.py:171-181): corners and centre."""
+    rs, cs = (scaled_rows - crop_rows) // 4, (scaled_cols - crop_cols) // 4
+    return [(0, 0), (4 * rs, 0), (0, 4 * cs), (4 * rs, 4 * cs), (2 * rs, 2 * cs)]
+
+
+class CropResizeStage:
+    """Crop + resize of decoded uint8 stacks on the device: ``src`` [N, Hs, Ws, 7] -> [N, out_h, out_w, 7],
+    one crop per clip, bit-identical to numpy slicing + ``cv2.resize(INTER_LINEAR)`` (installed
+    OpenCV 4.x semantics).  Feed the result to ``U8InputStage`` (flip, split, normalise)."""
+
+    def __init__(self, frames: int, src_h: int, src_w: int, out_h: int = 224, out_w: int = 224,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
+        self.N, self.Hs, self.Ws, self.Ho, self.Wo = frames, src_h, src_w, out_h, out_w
+        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self._src = torch.empty(frames, src_h, src_w, 7, dtype=torch.uint8, device=self.device)
+        self.out = torch.empty(frames, out_h, out_w, 7, dtype=torch.uint8, device=self.device)
+
+    def __call__(self, src_u8: torch.Tensor, tables: np.ndarray) -> torch.Tensor:
+        """tables: int32 [clips, 4*out_w + 4*out_h] from ``crop_tables`` / ``scaled_crop_tables``."""
+        check_stack(src_u8, self.N, self.Hs, self.Ws)
+        tab = np.ascontiguousarray(np.asarray(tables, dtype=np.int32).reshape(-1, 4 * (self.Wo + self.Ho)))
+        if self.N % tab.shape[0]:
+            raise ValueError('%d tables for %d frames' % (tab.shape[0], self.N))
+        xs, ys = tab[:, :2 * self.Wo], tab[:, 4 * self.Wo:4 * self.Wo + 2 * self.Ho]
+        if xs.min() < 0 or xs.max() >= self.Ws or ys.min() < 0 or ys.max() >= self.Hs:
+            raise ValueError('table indices leave the %dx%d source frame' % (self.Hs, self.Ws))
+        self._src.copy_(src_u8.reshape(self.N, self.Hs, self.Ws, 7), non_blocking=True)
+        dtab = torch.from_numpy(tab).to(self.device)
+        ops.crop_resize_u8(self._src, self.N, self.Hs, self.Ws, dtab, self.N // tab.shape[0], self.out,
+                           self.Ho, self.Wo)
+        return self.out

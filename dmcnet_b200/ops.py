@@ -379,6 +379,13 @@ def flow_block_mean_flip_u8(frames, flip, N, H, W, factor, div_motion, flow):
           c_int(factor), c_float(div_motion), _ptr(flow, F32), _stream())
 
 
+def crop_resize_u8(src, N, Hs, Ws, tab, frames_per_tab, out, Ho, Wo):
+    """Crop + cv2-compatible bilinear resize of uint8 [N][Hs][Ws][7] stacks from host-built tables
+    (code/dmcnet/transforms.py:122-140)."""
+    _call('dmc_crop_resize_u8', _ptr(src, U8), c_int(N), c_int(Hs), c_int(Ws), _ptr(tab, torch.int32),
+          c_int(frames_per_tab), _ptr(out, U8), c_int(Ho), c_int(Wo), _stream())
+
+
 def dense_dgrad_weights(params, table, out):
     _call('dmc_dense_dgrad_weights', _ptr(params, F32), _iarr(table), _ptr(out, F32), _stream())
 

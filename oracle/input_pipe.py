@@ -36,6 +36,68 @@ def block_reduce(image: np.ndarray, block_size: Sequence[int], func=np.mean, cva
     return func(blocked, axis=tuple(range(1, 2 * image.ndim, 2)))
 
 
+def resize_linear_u8(src: np.ndarray, dsize: Tuple[int, int]) -> np.ndarray:
+    """``cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR)`` for uint8 ``src`` [H, W] or [H, W, C],
+    dsize = (width, height).  Third-party arithmetic absent from /root/reference (OpenCV, version
+    unpinned by the reference): its published algorithm is restated -- positions in double, fractions
+    in float, 11-bit coefficients (cvRound), horizontal pass with the fraction reset at the borders,
+    vertical pass with clamped row indices, fixed-point combine
+    ((b0*(D0>>4))>>16) + ((b1*(D1>>4))>>16) + 2 >> 2 -- and pinned bit for bit against the installed
+    cv2 (tests/test_extensions_cpu.py); same size returns a copy."""
+    if src.ndim == 3:
+        return np.stack([resize_linear_u8(src[..., c], dsize) for c in range(src.shape[2])], axis=2)
+    dw, dh = dsize
+    sh, sw = src.shape
+
+    def axis(ssize, dsize_, horizontal):
+        scale = 1.0 / (dsize_ / ssize)
+        i0, i1, a = np.zeros(dsize_, np.int64), np.zeros(dsize_, np.int64), np.zeros((dsize_, 2), np.int32)
+        for d in range(dsize_):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = np.float32(f - np.float32(s))
+            if horizontal:
+                if s < 0:
+                    f, s = np.float32(0), 0
+                if s >= ssize - 1:
+                    f, s = np.float32(0), ssize - 1
+            i0[d], i1[d] = min(max(s, 0), ssize - 1), min(max(s + 1, 0), ssize - 1)
+            a[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+            a[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+        return i0, i1, a
+    x0, x1, xa = axis(sw, dw, True)
+    y0, y1, ya = axis(sh, dh, False)
+    s32 = src.astype(np.int32)
+    rows = s32[:, x0] * xa[:, 0] + s32[:, x1] * xa[:, 1]
+    d0, d1 = rows[y0], rows[y1]
+    b0, b1 = ya[:, 0:1], ya[:, 1:2]
+    return ((((b0 * (d0 >> 4)) >> 16) + ((b1 * (d1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+
+
+def resize_group(img_group: Sequence[np.ndarray], size: Tuple[int, int]):
+    """The resize of GroupMultiScaleCrop / GroupScale (code/dmcnet/transforms.py:60-76, :131-138):
+    flow and mv channel by channel (resize_mv, :116-118), the residual as one 3-channel image."""
+    return [np.concatenate((resize_linear_u8(img[:, :, :4], size), resize_linear_u8(img[:, :, 4:], size)), axis=2)
+            for img in img_group]
+
+
+def multi_scale_crop(img_group: Sequence[np.ndarray], crop_w: int, crop_h: int, offset_w: int, offset_h: int,
+                     input_size=(224, 224)):
+    """GroupMultiScaleCrop.__call__ for an already sampled crop (transforms.py:124-140); the reference
+    names the ROW extent / offset 'w'."""
+    crops = [img[offset_w:offset_w + crop_w, offset_h:offset_h + crop_h] for img in img_group]
+    return resize_group(crops, (input_size[0], input_size[1]))
+
+
+def scale_center_crop(img_group: Sequence[np.ndarray], scale_size: int = 256, crop_size: int = 224):
+    """GroupScale(scale_size) then GroupCenterCrop(crop_size): transforms.py:36-44, :60-76
+    (the validation / 1-crop test transform, code/dmcnet/train.py:98-101)."""
+    scaled = resize_group(img_group, (scale_size, scale_size))
+    h, w, _ = scaled[0].shape
+    hs, ws = (h - crop_size) // 2, (w - crop_size) // 2
+    return [img[hs:hs + crop_size, ws:ws + crop_size] for img in scaled]
+
+
 def flip_group(img_group: Sequence[np.ndarray]):
     """The flipped branch of GroupRandomHorizontalFlip.__call__ (code/dmcnet/transforms.py:49-57):
     mirror, then negate the x components of flow (channel 0) and mv (channel 2) around 128 in int32.

@@ -620,3 +620,89 @@ def test_get_augmentation_composes_the_reference_transforms():
         sys.modules.pop('transforms', None)
         if saved is not None:
             sys.modules['transforms'] = saved
+
+
+# ------------------------------------------------------------------ crop + resize (transforms.py)
+def _ref_transforms():
+    import importlib.util, os
+    from oracle import ref_loader as R
+    if not R.reference_available():
+        pytest.skip('/root/reference not present')
+    spec = importlib.util.spec_from_file_location(
+        '_ref_transforms_for_tests', os.path.join(R.REFERENCE_ROOT, 'code', 'dmcnet', 'transforms.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _crop_resize_kernel_model(src, tab, out_h, out_w):
+    """numpy model of crop_resize_u8_kernel: src [N,Hs,Ws,7] uint8, one table for all frames."""
+    x0, x1, a0, a1 = (tab[i * out_w:(i + 1) * out_w] for i in range(4))
+    ty = tab[4 * out_w:]
+    y0, y1, b0, b1 = (ty[i * out_h:(i + 1) * out_h] for i in range(4))
+    s = src.astype(np.int32)
+    d0 = s[:, y0][:, :, x0] * a0[None, None, :, None] + s[:, y0][:, :, x1] * a1[None, None, :, None]
+    d1 = s[:, y1][:, :, x0] * a0[None, None, :, None] + s[:, y1][:, :, x1] * a1[None, None, :, None]
+    bb0, bb1 = b0[None, :, None, None], b1[None, :, None, None]
+    return ((((bb0 * (d0 >> 4)) >> 16) + ((bb1 * (d1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+
+
+def test_resize_restatement_is_bit_exact_against_installed_opencv():
+    cv2 = pytest.importorskip('cv2')
+    from oracle import input_pipe as P
+    rng = np.random.default_rng(0)
+    for (sh, sw) in [(256, 256), (192, 192), (192, 224), (256, 224), (224, 192), (340, 256), (255, 191), (193, 257),
+                     (224, 224), (170, 300), (256, 340)]:
+        for dsize in [(224, 224), (256, 256), (224, 256)]:
+            src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+            assert np.array_equal(P.resize_linear_u8(src, dsize), cv2.resize(src, dsize, interpolation=cv2.INTER_LINEAR)), \
+                ((sh, sw), dsize)
+    src = rng.integers(0, 256, (192, 256, 3), dtype=np.uint8)
+    assert np.array_equal(P.resize_linear_u8(src, (224, 224)), cv2.resize(src, (224, 224), interpolation=cv2.INTER_LINEAR))
+
+
+def test_crop_resize_oracle_tables_and_kernel_model_against_reference_transforms():
+    """GroupMultiScaleCrop (train), GroupScale + GroupCenterCrop (validation) and GroupOverSample's
+    windows (10-crop test) of the reference's transforms.py, executed with the same ``random`` draws,
+    against the oracle restatement and against a numpy model of the kernel driven by the product's
+    host-built tables."""
+    import random
+    import torchvision
+    T_ref = _ref_transforms()
+    from oracle import input_pipe as P
+    from dmcnet_b200 import input_stage as S
+    rng = np.random.default_rng(1)
+    group = [rng.integers(0, 256, (256, 340, 7), dtype=np.uint8) for _ in range(3)]
+    src = np.stack(group)
+    # train: multi-scale crop, several draws (all crop sizes 256 / 224 / 192 and distortions occur)
+    seen = set()
+    for seed in range(12):
+        random.seed(seed)
+        want = T_ref.GroupMultiScaleCrop(224, [1, .875, .75])(group)
+        random.seed(seed)
+        row0, col0, rows, cols = S.sample_multi_scale_crop(256, 340, (224, 224), (1, .875, .75))
+        seen.add((rows, cols))
+        got = P.multi_scale_crop(group, rows, cols, row0, col0)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), seed
+        tab = S.crop_tables(row0, col0, rows, cols, 224, 224, 256, 340)
+        assert np.array_equal(_crop_resize_kernel_model(src, tab, 224, 224), np.stack(want)), seed
+    assert len(seen) >= 4
+    # validation: scale to 256 x 256 then centre crop (train.py:98-101)
+    val = torchvision.transforms.Compose([T_ref.GroupScale(256), T_ref.GroupCenterCrop(224)])(group)
+    assert all(np.array_equal(a, b) for a, b in zip(P.scale_center_crop(group, 256, 224), val))
+    tab = S.scaled_crop_tables(256, 340, 256, 256, 16, 16, 224, 224)
+    assert np.array_equal(_crop_resize_kernel_model(src, tab, 224, 224), np.stack(val))
+    # 10-crop test: five windows of the scaled frame, each also flipped (odd entries; the flip is
+    # the device-side flag of the input stage)
+    over = T_ref.GroupOverSample(224, 256)(group)
+    offsets = S.oversample_offsets(256, 256, 224, 224)
+    assert len(over) == 5 * 3 * 2
+    for wi, (r0, c0) in enumerate(offsets):
+        tab = S.scaled_crop_tables(256, 340, 256, 256, r0, c0, 224, 224)
+        got = _crop_resize_kernel_model(src, tab, 224, 224)
+        for fi in range(3):
+            plain, flipped = over[(wi * 3 + fi) * 2], over[(wi * 3 + fi) * 2 + 1]
+            assert np.array_equal(got[fi], plain), (wi, fi)
+            assert np.array_equal(P.flip_group([got[fi]])[0], flipped), (wi, fi)
+    with pytest.raises(ValueError, match='leaves the frame'):
+        S.crop_tables(100, 0, 192, 192, 224, 224, 256, 340)

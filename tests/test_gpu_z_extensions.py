@@ -456,3 +456,41 @@ def test_input_stage_flip_bit_exact_vs_reference_golden(golden_dir):
     got = U8InputStage(6, 224, 224, flow_ds_factor=16)(torch.from_numpy(frames), flip=[False, True])
     torch.cuda.synchronize()
     assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+
+
+@pytest.mark.skipif(not _os.environ.get('DMC_RUN_UNVERIFIED'),
+                    reason='path not yet executed on a GPU; set DMC_RUN_UNVERIFIED=1 to run it')
+def test_crop_resize_flip_normalise_chain_bit_exact_vs_oracle():
+    """Decoded uint8 frames -> GroupMultiScaleCrop -> GroupRandomHorizontalFlip -> CoviarDataSet sample
+    arithmetic, all on the device (crop_resize_u8 + the flip entry points), against the oracle chain
+    (pinned on the reference's transforms.py / dataset.py and the installed cv2)."""
+    import random
+    from dmcnet_b200 import input_stage as S
+    from oracle import input_pipe as P
+    rng = np.random.default_rng(2)
+    clips, segs, Hs, Ws = 2, 3, 256, 340
+    src = rng.integers(0, 256, (clips * segs, Hs, Ws, 7), dtype=np.uint8)
+    src[0, :8, :8, 0] = 0                                   # 0 -> 256 under the flip
+    random.seed(5)
+    crops = [S.sample_multi_scale_crop(Hs, Ws) for _ in range(clips)]
+    flips = [True, False]
+    tabs = np.stack([S.crop_tables(r0, c0, rows, cols, 224, 224, Hs, Ws) for r0, c0, rows, cols in crops])
+    stage = S.CropResizeStage(clips * segs, Hs, Ws)
+    cropped = stage(torch.from_numpy(src), tabs)
+    want_u8, want = [], []
+    for ci, ((r0, c0, rows, cols), fl) in enumerate(zip(crops, flips)):
+        group = P.multi_scale_crop(list(src[ci * segs:(ci + 1) * segs]), rows, cols, r0, c0)
+        want_u8.append(np.stack(group))
+        want.append(P.sample_from_frames(P.flip_group(group) if fl else group, 16))
+    torch.cuda.synchronize()
+    assert np.array_equal(cropped.cpu().numpy(), np.concatenate(want_u8))
+    flow, mv, res = S.U8InputStage(clips * segs, 224, 224, flow_ds_factor=16)(cropped, flip=flips)
+    torch.cuda.synchronize()
+    for got, idx in ((flow, 0), (mv, 1), (res, 2)):
+        assert torch.equal(got.cpu(), torch.cat([w[idx] for w in want]))
+    # validation transform: GroupScale(256) + GroupCenterCrop(224) as one table
+    tab = S.scaled_crop_tables(Hs, Ws, 256, 256, 16, 16, 224, 224)
+    val = stage(torch.from_numpy(src), tab[None])
+    torch.cuda.synchronize()
+    want_val = np.concatenate([np.stack(P.scale_center_crop(list(src[i:i + 1]))) for i in range(clips * segs)])
+    assert np.array_equal(val.cpu().numpy(), want_val)
