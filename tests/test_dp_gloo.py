@@ -172,3 +172,80 @@ def test_two_rank_fused_step_matches_one_adam_step_on_the_summed_gradients():
         mp.spawn(_trainer_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret['same_0'] and ret['same_1']
         assert ret['worst'] < 2e-5, ret['worst']
+
+
+# ---------------------------------------------------------------- dmcnet_GAN, two ranks (BASELINE config 4)
+def _gan_worker(rank, world, port, ret):
+    """D-step then G-step of dmcnet_GAN with one clip per rank: per-rank BatchNorm and Dropout2d
+    masks, adversarial / CE / MSE gradients pre-scaled by the GLOBAL batch, one all-reduce over the
+    stepped groups -- against the oracle run shard by shard (its shard-mean gradients / world, summed)
+    followed by one step of the torch optimizers the reference would step."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _pytest.monkeypatch import MonkeyPatch
+    from sim_engine import SimEngine, patch_ops
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(4)
+    mp_ = MonkeyPatch()
+    patch_ops(mp_)
+    try:
+        B, C, arch_d = 2, 51, 'Discriminator'
+        sd = O.build_state(C, arch_d, seed=1)
+        flow, mv, res, target = O.make_inputs(B, 3, C, seed=0)
+
+        def masks_for(r, it):
+            g = torch.Generator().manual_seed(1000 + 10 * r + it)
+            return O.draw_dropout_masks(arch_d, 3 * (2 if it == 0 else 1), generator=g)
+
+        lo, hi = T.shard_range(rank, world, B)
+        eng = SimEngine(C, 3, 3, gan=True, arch_d=arch_d)
+        eng.load_state(sd)
+        tr = T.FusedTrainStep(eng, T.HParams(), 1, world_size=world)
+        state = sd
+        worst = 0.0
+        for it in range(2):
+            tr.step(flow[lo:hi], mv[lo:hi], res[lo:hi], target[lo:hi], masks=masks_for(rank, it))
+            if rank == 0:
+                total = None
+                for r in range(world):
+                    a, b = T.shard_range(r, world, B)
+                    shard = O.OracleTrainer(state, O.HParams(), gan=True, arch_d=arch_d)
+                    shard.iteration = it
+                    shard.step(flow[a:b], mv[a:b], res[a:b], target[a:b], masks=masks_for(r, it), apply=False)
+                    g = {k: v / world for k, v in shard.grads().items()}
+                    total = g if total is None else {k: total[k] + g[k] for k in g}
+                ref = O.OracleTrainer(state, O.HParams(), gan=True, arch_d=arch_d)
+                if it == 1:                       # Adam moments / step counts of the D-step carry over
+                    ref.opt_cls.load_state_dict(prev['cls']); ref.opt_d.load_state_dict(prev['d'])
+                ref._zero()
+                for k, v in ref.st.items():
+                    if not O.is_buffer(k):
+                        v.grad = total[k].clone()
+                for opt in ((ref.opt_cls, ref.opt_d) if it == 0 else (ref.opt_gf,)):
+                    opt.step()
+                prev = {'cls': ref.opt_cls.state_dict(), 'd': ref.opt_d.state_dict()}
+                for k in eng.specs:
+                    # 1e-8 absolute: BatchNorm biases start at 0, so after one step the parameter IS the
+                    # Adam update of a ~1e-6 gradient whose fp32 cancellation noise is ~1e-4 relative
+                    err = float((eng.param_view(k) - ref.st[k].detach()).abs().max())
+                    worst = max(worst, max(0.0, err - 1e-8) / (float(ref.st[k].detach().abs().max()) + 1e-12))
+                # the next iteration starts from rank 0's state on the reference side (parameters are
+                # identical on every rank; BatchNorm buffers are per rank and do not enter the gradients)
+                state = eng.state_dict()
+        if rank == 0:
+            ret['worst'] = worst
+            ret['steps'] = tr.steps.tolist()
+        dist.barrier()
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def test_two_rank_gan_d_and_g_steps_match_the_summed_shard_gradients():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gan_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret['steps'] == [1, 1, 1]
+        assert ret['worst'] < 5e-5, ret['worst']
