@@ -105,12 +105,23 @@ flow_block_mean_u8_kernel(const unsigned char* __restrict__ frames, int H, int W
 // A flipped frame is mirrored left-right and its x components (channel 0 = flow x, channel 2 = mv x)
 // become 256 - v: the reference computes (v - 128) * (-1) + 128 in int32, so v = 0 gives 256 -- a value
 // a uint8 stack cannot hold, which is why the flip has to happen here and not on the host.
+// Arithmetic: a value has only 257 possible inputs (0..255, and 256 for a negated x component), so each
+// CTA first tabulates normalize_u8 for the four divisors (motion, residual r/g/b) in shared memory --
+// the same function on the same fp32 input, hence the same bits -- and the per-pixel work is 28 LDS
+// instead of 56 IEEE divisions (the plain kernel above is ALU-bound on those divisions, DESIGN.md
+// section 10).
 __global__ void __launch_bounds__(256)
 unpack_normalize_flip_u8_kernel(const unsigned int* __restrict__ frames,
                                 const unsigned char* __restrict__ flip, long groups, int hw4, int w4,
                                 float div_motion, float div_r0, float div_r1, float div_r2,
                                 float* __restrict__ flow, float* __restrict__ mv, float* __restrict__ res) {
-  const float divs[7] = {div_motion, div_motion, div_motion, div_motion, div_r0, div_r1, div_r2};
+  __shared__ float lut[4][257];
+  for (int i = threadIdx.x; i < 4 * 257; i += blockDim.x) {
+    const int k = i / 257, v = i - k * 257;
+    const float d = k == 0 ? div_motion : (k == 1 ? div_r0 : (k == 2 ? div_r1 : div_r2));
+    lut[k][v] = normalize_u8((float)v, d);
+  }
+  __syncthreads();
   for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups;
        g += (long)gridDim.x * blockDim.x) {
     const long n = g / hw4;
@@ -127,11 +138,10 @@ unpack_normalize_flip_u8_kernel(const unsigned int* __restrict__ frames,
     float out[7][4];
 #pragma unroll
     for (int b = 0; b < 28; ++b) {
-      const unsigned int byte = (w[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      int v = (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu);
       const int c = b % 7, p = b / 7;
-      float v = (float)byte;
-      if (f && (c == 0 || c == 2)) v = 256.0f - v;      // exact in fp32
-      const float r = normalize_u8(v, divs[c]);
+      if (f && (c == 0 || c == 2)) v = 256 - v;
+      const float r = lut[c < 4 ? 0 : c - 3][v];
       if (f) out[c][3 - p] = r; else out[c][p] = r;
     }
 #pragma unroll
