@@ -186,6 +186,46 @@ class VideoScorer:
                     self._stats)
         return self._scores.cpu().numpy().copy()
 
+    def forward_video_u8(self, decoded_u8: torch.Tensor, label: int = 0, scale_size: int = 256) -> np.ndarray:
+        """The test transform on the device as well: ``decoded_u8`` is the uint8 stack
+        [test_segments, Hs, Ws, 7] of the decoded frames (flow | mv | residual channels,
+        code/dmcnet/dataset.py:210); with 10 crops it goes through GroupOverSample(crop, scale)
+        (five windows of the frame scaled to scale_size x scale_size, each also flipped,
+        code/dmcnet/transforms.py:78-114), with 1 crop through GroupScale + GroupCenterCrop
+        (test.py:88-98); then the sample arithmetic of dataset.py:215-263 and ``forward_video``.
+        The frame ORDER differs from the reference's list (window, segment, flip), which the mean
+        over all frames does not see."""
+        from . import input_stage as S
+        segs, H, W = self.segments, self.H, self.W
+        if decoded_u8.dim() != 4 or decoded_u8.shape[0] != segs or decoded_u8.shape[-1] != 7:
+            raise ValueError('expected a uint8 stack [%d, Hs, Ws, 7], got %s' % (segs, tuple(decoded_u8.shape)))
+        Hs, Ws = int(decoded_u8.shape[1]), int(decoded_u8.shape[2])
+        key = (Hs, Ws, scale_size)
+        if getattr(self, '_u8_key', None) != key:
+            dev = self.eng.device
+            self._crop = S.CropResizeStage(segs, Hs, Ws, H, W, device=dev)
+            self._norm = S.U8InputStage(segs, H, W, device=dev)
+            if self.crops == 10:
+                wins = S.oversample_offsets(scale_size, scale_size, H, W)
+            else:
+                wins = [((scale_size - H) // 2, (scale_size - W) // 2)]
+            self._tabs = [S.scaled_crop_tables(Hs, Ws, scale_size, scale_size, r0, c0, H, W)[None] for r0, c0 in wins]
+            f32 = dict(dtype=torch.float32, device=dev)
+            self._mv_all = torch.empty(self.frames, 2, H, W, **f32)
+            self._res_all = torch.empty(self.frames, 3, H, W, **f32)
+            self._flow_tmp = torch.empty(segs, 2, H, W, **f32)
+            self._u8_key = key
+        k = 0
+        for tab in self._tabs:
+            stack = self._crop(decoded_u8, tab)
+            for flipped in ((False, True) if self.crops == 10 else (False,)):
+                sl = slice(k * segs, (k + 1) * segs)
+                self._norm(stack, self._flow_tmp, self._mv_all[sl], self._res_all[sl],
+                           flip=[True] if flipped else None)
+                k += 1
+        assert k * segs == self.frames
+        return self.forward_video(self._mv_all, self._res_all, label)
+
     def last_validity(self) -> np.ndarray:
         """Discriminator logits [frames, 2] of the last scored video (needs ``arch_d``); the third
         element of the GAN script's output tuples (code/dmcnet_GAN/test.py:97,116)."""

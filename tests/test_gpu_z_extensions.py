@@ -494,3 +494,30 @@ def test_crop_resize_flip_normalise_chain_bit_exact_vs_oracle():
     torch.cuda.synchronize()
     want_val = np.concatenate([np.stack(P.scale_center_crop(list(src[i:i + 1]))) for i in range(clips * segs)])
     assert np.array_equal(val.cpu().numpy(), want_val)
+
+
+@pytest.mark.skipif(not _os.environ.get('DMC_RUN_UNVERIFIED'),
+                    reason='path not yet executed on a GPU; set DMC_RUN_UNVERIFIED=1 to run it')
+def test_video_scorer_from_decoded_uint8_frames_ten_crops():
+    """test.py with --test-crops 10 from the decoded stacks: GroupOverSample on the device, then the
+    eval forward and the mean over 3 segments x 10 crops, against the oracle chain."""
+    from dmcnet_b200 import inference as I
+    from dmcnet_b200 import input_stage as S
+    from oracle import input_pipe as P, video_protocol as V
+    num_class, segs = 51, 3
+    sd = O.build_state(num_class, None, seed=1)
+    rng = np.random.default_rng(3)
+    decoded = rng.integers(0, 256, (segs, 256, 340, 7), dtype=np.uint8)
+    scorer = I.VideoScorer(sd, num_class, segs, 10)
+    s = scorer.forward_video_u8(torch.from_numpy(decoded), label=4)
+    # oracle: GroupScale(256) -> five windows -> [crop, flipped crop] -> sample arithmetic
+    scaled = P.resize_group(list(decoded), (256, 256))
+    frames = []
+    for r0, c0 in S.oversample_offsets(256, 256, 224, 224):
+        crops = [img[r0:r0 + 224, c0:c0 + 224] for img in scaled]
+        frames += [P.sample_from_frames(crops, 0), P.sample_from_frames(P.flip_group(crops), 0)]
+    mv = torch.cat([f[1] for f in frames]).unsqueeze(0)
+    res = torch.cat([f[2] for f in frames]).unsqueeze(0)
+    r = V.forward_video(sd, mv, res, segs, 10)
+    np.testing.assert_allclose(s, r, rtol=1e-3, atol=1e-3 * np.abs(r).max())
+    assert int(s.argmax()) == int(r.argmax())
