@@ -216,6 +216,7 @@ class VideoScorer:
             self._flow_tmp = torch.empty(segs, 2, H, W, **f32)
             self._u8_key = key
         k = 0
+        decoded_u8 = decoded_u8.to(self.eng.device, non_blocking=True)       # one host->device copy
         for tab in self._tabs:
             stack = self._crop(decoded_u8, tab)
             for flipped in ((False, True) if self.crops == 10 else (False,)):
