@@ -7,8 +7,12 @@ CPU restatement of the video-level testing protocol around ``Model.forward``:
   * late fusion          code/dmcnet/combine.py:35-56
 The model forward itself is ``oracle.dmc_oracle.model_forward`` (pinned against the
 reference's model.py).  test.py cannot be imported here (``async=True`` is a
-SyntaxError on Python >= 3.7, SURVEY.md section 8c), so these few lines are restated;
-parity for them is pinned by construction only (they are list/array bookkeeping).
+SyntaxError on Python >= 3.7), so these few lines are restated.
+Pins: the score-file layout and the fusion formula are checked against files the reference's
+own test.py wrote (exp_my/*/split*/*_score_model_best.npz; fixture tests/golden/score_files.npz,
+and the published 64.05 / 61.31 / 60.07 % on the full files); ``forward_video`` and ``accuracy``
+are a view + mean / argmax over the pinned forward -- for those two lines themselves: parity
+unpinned (no reference output exists without trained weights and videos).
 """
 from typing import Dict, List, Sequence, Tuple
 
