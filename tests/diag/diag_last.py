@@ -1,7 +1,7 @@
 """GPU debug: last residual block's BN backward vs a CPU torch emulation."""
 import os, sys
 import torch, torch.nn.functional as F
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import dmc_oracle as O
 from dmcnet_b200.engine import DmcEngine

@@ -1,6 +1,6 @@
 """GPU diagnostics: FusedTrainStep vs the CPU oracle, per-tensor error report.
 
-    python tools/diag_step.py [dmcnet|gan_d3|gan_d] [batch] [tc|simt]
+    python tests/diag/diag_step.py [dmcnet|gan_d3|gan_d] [batch] [tc|simt]
 """
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import dmc_oracle as O          # noqa: E402  (checker only)
 from dmcnet_b200.engine import DmcEngine    # noqa: E402
