@@ -40,3 +40,19 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(RuntimeError, match='no CPU/PyTorch fallback'):
         _native.lib()
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under dmcnet_b200/, examples/ or tools/ may import it
+    (bench.py's CPU baseline legs and __graft_entry__.smoke() are the two sanctioned exceptions)."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for pat in ('dmcnet_b200/**/*.py', 'examples/*.py', 'tools/*.py'):
+        for path in glob.glob(os.path.join(root, pat), recursive=True):
+            text = open(path).read()
+            if re.search(r'^\s*(from|import)\s+oracle\b', text, re.M):
+                offenders.append(os.path.relpath(path, root))
+    assert offenders == []
