@@ -56,3 +56,35 @@ def test_product_code_never_touches_the_oracle():
             if re.search(r'^\s*(from|import)\s+oracle\b', text, re.M):
                 offenders.append(os.path.relpath(path, root))
     assert offenders == []
+
+
+def test_argument_errors_are_reported_without_touching_the_device(lib):
+    """Entry points validate their arguments before any CUDA call: -1 and a message from
+    dmc_last_error(), never an exception or a launch (include/dmc_b200.h conventions)."""
+    vp, ci, cl, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+    null, junk = vp(0), vp(4096)           # never dereferenced: every call below fails validation first
+    lib.dmc_flow_loss_head.restype = ci
+    assert lib.dmc_flow_loss_head(ci(7), junk, junk, cl(16), cf(1.0), null, cl(16), cl(16), junk, null) == -1
+    assert 'kind' in _native.last_error()
+    assert lib.dmc_flow_loss_head(ci(1), junk, junk, cl(18), cf(1.0), null, cl(18), cl(18), junk, null) == -1
+    assert 'multiples of 4' in _native.last_error()
+    lib.dmc_unpack_normalize_u8.restype = ci
+    args = (cf(0.226), cf(0.229), cf(0.224), cf(0.225), null, junk, junk, null)
+    assert lib.dmc_unpack_normalize_u8(junk, ci(1), ci(3), ci(3), *args) == -1
+    assert 'multiple of 4' in _native.last_error()
+    assert lib.dmc_unpack_normalize_u8(vp(4098), ci(1), ci(4), ci(4), *args) == -1
+    assert 'aligned' in _native.last_error()
+    lib.dmc_unpack_normalize_flip_u8.restype = ci
+    assert lib.dmc_unpack_normalize_flip_u8(junk, null, ci(1), ci(4), ci(4), *args) == -1
+    assert 'null pointer' in _native.last_error()
+    lib.dmc_flow_block_mean_u8.restype = ci
+    assert lib.dmc_flow_block_mean_u8(junk, ci(1), ci(8), ci(8), ci(0), cf(0.226), junk, null) == -1
+    lib.dmc_flow_block_mean_flip_u8.restype = ci
+    assert lib.dmc_flow_block_mean_flip_u8(junk, junk, ci(1), ci(8), ci(10), ci(4), cf(0.226), junk, null) == -1
+    assert 'multiple of factor' in _native.last_error()
+    lib.dmc_crop_resize_u8.restype = ci
+    assert lib.dmc_crop_resize_u8(junk, ci(1), ci(8), ci(8), null, ci(1), junk, ci(4), ci(4), null) == -1
+    assert 'null pointer' in _native.last_error()
+    assert lib.dmc_crop_resize_u8(junk, ci(1), ci(8), ci(8), junk, ci(0), junk, ci(4), ci(4), null) == -1
+    lib.dmc_mse_head.restype = ci
+    assert lib.dmc_mse_head(junk, junk, cl(10), cf(1.0), null, cl(10), cl(10), junk, null) == -1
