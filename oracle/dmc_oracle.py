@@ -242,24 +242,36 @@ def context_forward(st: Dict[str, Tensor], x: Tensor, att: int, gen_flow_ds_fact
     return block(x, 'gen_flow_model.predict_flow', 1), F.relu(block(x, 'gen_flow_model.predict_att.0', 1))
 
 
+# Sensitivity experiments (tests/test_grad_sensitivity.py): when set, every ResNet-18 conv sees
+# OPERAND_HOOK(activation) and OPERAND_HOOK(weight) instead of the exact fp32 operands (straight-
+# through: the hook's result carries the operand's gradient).  None = the pinned fp32 restatement.
+OPERAND_HOOK = None
+
+
+def _conv(x: Tensor, w: Tensor, stride: int, pad: int) -> Tensor:
+    if OPERAND_HOOK is not None:
+        x, w = OPERAND_HOOK(x), OPERAND_HOOK(w)
+    return F.conv2d(x, w, None, stride, pad)
+
+
 def resnet18_forward(st: Dict[str, Tensor], x: Tensor, train: bool, prefix: str = 'base_model'
                      ) -> Tensor:
     """torchvision resnet18 forward with the 2-channel conv1 and num_class fc of
     code/dmcnet/model.py:283-294."""
     p = prefix
-    x = F.conv2d(x, st[p + '.conv1.weight'], None, 2, 3)
+    x = _conv(x, st[p + '.conv1.weight'], 2, 3)
     x = F.relu(_bn(x, st, p + '.bn1', train, 1e-5))
     x = F.max_pool2d(x, 3, 2, 1)
     for li, (width, stride) in enumerate(RESNET18_STAGES, start=1):
         for b in range(2):
             q = '%s.layer%d.%d' % (p, li, b)
             s = stride if b == 0 else 1
-            out = F.conv2d(x, st[q + '.conv1.weight'], None, s, 1)
+            out = _conv(x, st[q + '.conv1.weight'], s, 1)
             out = F.relu(_bn(out, st, q + '.bn1', train, 1e-5))
-            out = F.conv2d(out, st[q + '.conv2.weight'], None, 1, 1)
+            out = _conv(out, st[q + '.conv2.weight'], 1, 1)
             out = _bn(out, st, q + '.bn2', train, 1e-5)
             if (q + '.downsample.0.weight') in st:
-                idt = F.conv2d(x, st[q + '.downsample.0.weight'], None, s, 0)
+                idt = _conv(x, st[q + '.downsample.0.weight'], s, 0)
                 idt = _bn(idt, st, q + '.downsample.1', train, 1e-5)
             else:
                 idt = x

@@ -433,3 +433,149 @@ def test_fused_adam_matches_torch_adam():
             n = p.numel()
             assert rel(flat[offs[ti]:offs[ti] + n], p.detach().reshape(-1)) < 1e-6, (it, ti)
     assert int(step) == 3
+
+
+# ------------------------------------------------------------------ full-size tensor-core GEMMs
+# The layer shapes of BASELINE config 2 (192 frames): thousands of M tiles per launch, so the
+# persistent loop of tap_gemm_ws_kernel (TMEM accumulator ping-pong over ~33 tiles per CTA, the
+# statistics flush at every change of the output-channel block) and the multi-split wgrad plans
+# run exactly as in the bench.  Reference: torch fp64 on the same device (checker only).
+def _pixel_cuda(x):      # [N,C,H,W] cuda -> padded pixel-major [N*Hp*Wp, C] fp32 cuda
+    n, c, h, w = x.shape
+    p = torch.zeros(n, ops.padded(h), ops.padded(w), c, device=x.device)
+    p[:, 1:h + 1, 1:w + 1, :] = x.permute(0, 2, 3, 1).float()
+    return p.reshape(-1, c).contiguous()
+
+
+def _from_pixel_cuda(flat, n, c, h, w):
+    return flat.reshape(n, ops.padded(h), ops.padded(w), c)[:, 1:h + 1, 1:w + 1, :].permute(0, 3, 1, 2)
+
+
+FULL_CASES = [(192, 64, 64, 56, 1), (192, 128, 128, 28, 1), (192, 256, 512, 14, 2), (192, 512, 512, 7, 1),
+              (192, 64, 128, 56, 2)]
+
+
+@pytest.mark.parametrize('n,cin,cout,h,stride', FULL_CASES)
+def test_tap_gemm_full_size_layers_vs_fp64(n, cin, cout, h, stride):
+    from dmcnet_b200.engine import _taps_s1, _taps_s2
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn(n, cin, h, h, generator=g, device=dev)
+    w = torch.randn(cout, cin, 3, 3, generator=g, device=dev) * 0.05
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    y = F.conv2d(xd, wd, None, stride, 1)
+    dy = torch.randn(y.shape, generator=g, device=dev)
+    y.backward(dy.double())
+    ho = h // stride
+    Hp = Wp = ops.padded(ho)
+    P = n * Hp * Wp
+    assert P // 128 >= 100
+    W_hi = torch.zeros(9, cout, cin, dtype=torch.bfloat16, device=dev)
+    W_lo, Wt_hi, Wt_lo = (torch.zeros_like(W_hi) for _ in range(3))
+    ops.weight_prep(w.contiguous(), cout, cin, 9, W_hi, W_lo, Wt_hi.view(9, cin, cout), Wt_lo.view(9, cin, cout))
+    hi_, lo_ = split(_pixel_cuda(x))
+    if stride == 1:
+        A_hi, A_lo, phases = hi_, lo_, 1
+        shift, phase, bsel = _taps_s1(Wp)
+    else:
+        A_hi = torch.zeros(4, P, cin, dtype=torch.bfloat16, device=dev)
+        A_lo = torch.zeros_like(A_hi)
+        ops.phase_split(hi_, lo_, n, h, h, cin, A_hi, A_lo)
+        shift, phase, bsel = _taps_s2(Wp)
+        phases = 4
+    D = torch.full((P, cout), float('nan'), device=dev)
+    stats = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+    ops.tap_gemm(A_hi, A_lo, W_hi, W_lo, D, a_phases=phases, a_rows=P, K=cin, b_slices=9, N=cout, M=P,
+                 ldD=cout, Hp=Hp, Wp=Wp, shift=shift, phase=phase, bsel=bsel, stats=stats)
+    yd = y.detach()
+    assert rel(_from_pixel_cuda(D, n, cout, ho, ho), yd) < 5e-5
+    assert rel(stats[0], yd.sum((0, 2, 3))) < 5e-5 * (n * ho * ho) ** 0.5
+    assert rel(stats[1], (yd * yd).sum((0, 2, 3))) < 5e-5
+    ring = D.view(n, Hp, Wp, cout).clone()
+    ring[:, 1:ho + 1, 1:ho + 1] = 0
+    assert float(ring.abs().max()) == 0.0
+    # weight gradient: split-K workspace + fixed-order reduction, straight into OIHW
+    G_hi, G_lo = split(_pixel_cuda(dy))
+    ws = torch.empty(ops.wgrad_workspace_floats(P, cout, cin, 9), device=dev)
+    assert ws.numel() >= 2 * 9 * cout * cin            # more than one split
+    gw = torch.zeros(cout, cin, 3, 3, device=dev)
+    ops.wgrad_gemm(G_hi, G_lo, A_hi, A_lo, gw, P=P, Cout=cout, x_phases=phases, Cin=cin, shift=shift,
+                   phase=phase, bsel=bsel, oihw_taps=9, workspace=ws)
+    assert rel(gw, wd.grad) < 5e-5
+    # data gradient
+    if stride == 1:
+        dX = torch.full((P, cin), float('nan'), device=dev)
+        ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dX, a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin, M=P,
+                     ldD=cin, Hp=Hp, Wp=Wp, shift=[-s for s in shift], phase=phase, bsel=bsel)
+    else:
+        dxp = torch.zeros(4, P, cin, device=dev)
+        for ph in range(4):
+            sh = [-shift[t] for t in range(9) if phase[t] == ph]
+            bs = [bsel[t] for t in range(9) if phase[t] == ph]
+            ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, dxp[ph], a_phases=1, a_rows=P, K=cout, b_slices=9, N=cin,
+                         M=P, ldD=cin, Hp=Hp, Wp=Wp, shift=sh, phase=[0] * len(sh), bsel=bs)
+        dX = torch.empty(n * ops.padded(h) * ops.padded(h), cin, device=dev)
+        ops.phase_unsplit(dxp, n, h, h, cin, dX)
+    assert rel(_from_pixel_cuda(dX, n, cin, h, h), xd.grad) < 5e-5
+
+
+@pytest.mark.parametrize('n,c,h', [(192, 64, 56), (192, 512, 7), (6, 128, 28)])
+@pytest.mark.parametrize('with_residual', [False, True])
+def test_tap_gemm_fused_bn_backward_epilogue(n, c, h, with_residual):
+    """BwFuse epilogue of the data-gradient GEMM (csrc/gemm_tc.cu): D = dz = (dX + gb) * [act > 0] and
+    the two BatchNorm-backward reductions sum(dz), sum(dz * xhat), against torch fp64 on identical
+    inputs.  Shapes: the first and the last residual stage of BASELINE config 2 at full size."""
+    from dmcnet_b200.engine import _taps_s1
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(12)
+    dy = torch.randn(n, c, h, h, generator=g, device=dev)               # gradient of the conv OUTPUT
+    w = torch.randn(c, c, 3, 3, generator=g, device=dev) * 0.05         # conv whose data gradient is taken
+    Yn = torch.randn(n, c, h, h, generator=g, device=dev) * 1.5 + 0.3   # raw output of the BN'd conv upstream
+    gbn = torch.randn(n, c, h, h, generator=g, device=dev) if with_residual else None
+    mean = Yn.double().mean((0, 2, 3))
+    var = Yn.double().var((0, 2, 3), unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    act = torch.relu((Yn.double() - mean.view(1, c, 1, 1)) * invstd.view(1, c, 1, 1)
+                     + 0.1 * torch.randn(n, c, h, h, generator=g, device=dev).double())
+    # reference
+    dX = torch.nn.grad.conv2d_input((n, c, h, h), w.double(), dy.double(), 1, 1)
+    dz_ref = (dX + (gbn.double() if with_residual else 0.0)) * (act.to(torch.bfloat16).float() > 0)
+    xhat = (Yn.double() - mean.view(1, c, 1, 1)) * invstd.view(1, c, 1, 1)
+    s1_ref, s2_ref = dz_ref.sum((0, 2, 3)), (dz_ref * xhat).sum((0, 2, 3))
+    # kernel
+    Hp = Wp = ops.padded(h)
+    P = n * Hp * Wp
+    W_hi = torch.zeros(9, c, c, dtype=torch.bfloat16, device=dev)
+    W_lo, Wt_hi, Wt_lo = (torch.zeros_like(W_hi) for _ in range(3))
+    ops.weight_prep(w.contiguous(), c, c, 9, W_hi, W_lo, Wt_hi, Wt_lo)
+    G_hi, G_lo = split(_pixel_cuda(dy))
+    act_hi, _ = split(_pixel_cuda(act))
+    Yp = _pixel_cuda(Yn)
+    gb = _pixel_cuda(gbn) if with_residual else None
+    shift, phase, bsel = _taps_s1(Wp)
+    D = torch.full((P, c), float('nan'), device=dev)
+    sums2 = torch.zeros(2, c, dtype=torch.float64, device=dev)
+    ops.tap_gemm(G_hi, G_lo, Wt_hi, Wt_lo, D, a_phases=1, a_rows=P, K=c, b_slices=9, N=c, M=P, ldD=c,
+                 Hp=Hp, Wp=Wp, shift=[-s for s in shift], phase=phase, bsel=bsel, stats=sums2,
+                 bw=(Yp, act_hi, gb, mean.float().contiguous(), invstd.float().contiguous()))
+    assert rel(_from_pixel_cuda(D, n, c, h, h), dz_ref) < 5e-5
+    ring = D.view(n, Hp, Wp, c).clone()
+    ring[:, 1:h + 1, 1:h + 1] = 0
+    assert float(ring.abs().max()) == 0.0
+    # sums of ~n*h*h terms of mixed sign: bar relative to the L2 size of the summands
+    cnt = float(n * h * h)
+    scale1 = float(dz_ref.abs().max()) * cnt ** 0.5
+    assert float((sums2[0] - s1_ref).abs().max()) < 5e-5 * scale1
+    scale2 = float((dz_ref * xhat).abs().max()) * cnt ** 0.5
+    assert float((sums2[1] - s2_ref).abs().max()) < 5e-5 * scale2
+    # and the BatchNorm backward completed from those sums equals autograd through batch_norm
+    gamma = torch.rand(c, generator=g, device=dev) + 0.5
+    Yg = Yn.double().requires_grad_(True)
+    out = F.batch_norm(Yg, None, None, gamma.double(), None, True, 0.1, 1e-5)
+    out.backward(dz_ref)
+    Gh = torch.zeros(P, c, dtype=torch.bfloat16, device=dev)
+    Gl = torch.zeros_like(Gh)
+    dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    ops.bn_bwd_apply(D, None, None, Yp, mean.float().contiguous(), invstd.float().contiguous(), gamma, sums2,
+                     cnt, P, c, Hp, Wp, Gh, Gl, None, dgam, dbet)
+    assert rel(_from_pixel_cuda(Gh.float() + Gl.float(), n, c, h, h), Yg.grad) < 5e-5

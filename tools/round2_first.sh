@@ -6,8 +6,8 @@
 # 3. an ncu capture of the two input-stage kernels (achieved HBM GB/s vs 35 B/pixel algorithmic).
 set -x
 mkdir -p gpurun_out
-DMC_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_z_extensions.py -v -p no:cacheprovider 2>&1 | tee gpurun_out/r02_ext_tests.log | tail -40
-python examples/train_synthetic.py --epochs 2 --batch-size 8 --model-prefix gpurun_out/r02_example/hmdb51 \
+python -m pytest tests/test_gpu_z_extensions.py -v -p no:cacheprovider 2>&1 | tee gpurun_out/r02_ext_tests.log | tail -40
+python examples/train_synthetic.py --epochs 2 --batch-size 8 --model-prefix /tmp/r02_example/hmdb51 \
     > gpurun_out/r02_example.log 2>&1; tail -5 gpurun_out/r02_example.log
 python bench.py --steps 10 --warmup 3 --input u8 --no-cpu-baseline > gpurun_out/r02_bench_u8.json 2> gpurun_out/r02_bench_u8.err
 tail -c 600 gpurun_out/r02_bench_u8.json
