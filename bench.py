@@ -3,21 +3,31 @@
 224x224, 3 segments, DMC generator + ResNet-18, train step).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--config dmcnet|gan]
+                    [--scaling weak|strong] [--no-extras]
 
 N>1 is launched by the driver through torch.distributed.run (one rank per GPU,
-NCCL); rank 0 prints ONE JSON line.  Workload at every N: BASELINE config 2
-("dmcnet (no GAN) train step, synthetic HMDB-51-shaped batch=64 per GPU, 3
-segments, flow-MSE + CE loss"), weak scaling (64 clips per rank, one sum
-all-reduce of the gradient bucket per step).
+NCCL); rank 0 prints ONE JSON line.
+
+Headline (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE config 2 -- "dmcnet (no GAN) train
+step, synthetic HMDB-51-shaped batch=64 per GPU, 3 segments, flow-MSE + CE loss" -- weak scaling
+(64 clips per rank, one sum all-reduce of the gradient bucket per step).
+
+The same line carries, under `configs`, the other single-node configurations BASELINE.json names,
+measured in the same process right after the headline with the same W / K:
+
+  configs.config3        dmcnet_GAN step pair (D-step + G-step, Discriminator3, 101 classes), B=64 per GPU
+  configs.config4_strong dmcnet_GAN, 51 classes, GLOBAL batch 512 fixed and sharded 512/N per GPU
+                         (strong scaling; one GPU holds all 512 clips at N=1)
 
   value      clips/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e        clips/s through FusedTrainStep.step() with HOST (pinned) input tensors:
-             H2D copy of flow/mv/residual/target and D2H read of the metrics inside
-             the timed region
+  e2e        clips/s through FusedTrainStep.step_pipelined_u8() with HOST (pinned) input: the uint8
+             sample stack [B,S,H,W,7] (the format CoviarDataSet's augmentation produces) crosses PCIe
+             every step, is split / normalised on the device, and the metric record is read back
   roofline   the dominant kernel family, timed live with CUDA events on the launch stream
   cpu_baseline / --impl reference
-             the CPU restatement of the reference step (oracle/, torch CPU fp32, all
-             host threads) on a bounded sample of the same workload
+             the reference's OWN Model (oracle/_ref, byte-compiled from /root/reference by
+             oracle/make_ref.py) inside the restated step of its train.py (oracle/ref_step.py), torch
+             CPU fp32, all host threads: kind "reference"; if oracle/_ref is absent, the oracle port
 """
 import argparse
 import json
@@ -32,14 +42,18 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     'dmcnet': dict(gan=False, arch_d=None, num_class=51,
                    workload='dmcnet train step (BASELINE config 2): DenseNetTiny generator + ResNet-18, '
-                            'flow-MSE + CE, Adam, B=64 clips x 3 segments x 224x224 per GPU, 51 classes'),
+                            'flow-MSE + CE, Adam, B=%d clips x 3 segments x 224x224 per GPU, 51 classes'),
     'gan': dict(gan=True, arch_d='Discriminator3', num_class=101,
                 workload='dmcnet_GAN train step (BASELINE config 3): mean of one D-step and one G-step, '
-                         'Discriminator3, B=64 clips x 3 segments x 224x224 per GPU, 101 classes'),
+                         'Discriminator3, B=%d clips x 3 segments x 224x224 per GPU, 101 classes'),
+    'gan51': dict(gan=True, arch_d='Discriminator3', num_class=51,
+                  workload='dmcnet_GAN data-parallel (BASELINE config 4): D-step + G-step pair, Discriminator3, '
+                           'HMDB-51 shape (51 classes), B=%d clips x 3 segments x 224x224 per GPU'),
 }
 
-# algorithmic FLOPs per frame: 1 MAC = 2 FLOP
-GFLOP_PER_CLIP = {'dmcnet': 35.2, 'gan': 35.6}
+# algorithmic FLOPs per clip (dead work removed): 1 MAC = 2 FLOP
+GFLOP_PER_CLIP = {'dmcnet': 35.2, 'gan': 35.6, 'gan51': 35.6}
+STRONG_GLOBAL_BATCH = 512
 
 
 def dist_env():
@@ -83,24 +97,50 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons)}
 
 
+# ---------------------------------------------------------------------------- CPU reference arm
+def cpu_sample_batch(requested):
+    """B=64 when the host has the memory for it (saved activations ~20 MB/frame), else 16."""
+    if requested:
+        return requested
+    try:
+        import psutil
+        return 64 if psutil.virtual_memory().available > 48 * (1 << 30) else 16
+    except Exception:  # noqa: BLE001
+        return 16
+
+
 def cpu_reference_rate(cfg_name, steps, warmup, sample_batch):
-    """Reference CPU path: oracle restatement of the step, torch CPU fp32, all host threads."""
+    """The reference's CPU implementation of the step on all host threads: `warmup` untimed + `steps`
+    timed iterations (GAN: D+G pairs) of B=sample_batch clips; returns the MEDIAN step rate."""
     import torch
     from oracle import dmc_oracle as O
+    from oracle import ref_loader as R
     cfg = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = O.build_state(cfg['num_class'], cfg['arch_d'], seed=1)
-    tr = O.OracleTrainer(sd, O.HParams(), gan=cfg['gan'], arch_d=cfg['arch_d'])
+    if R.reference_available():
+        from oracle.ref_step import ReferenceTrainer
+        tr, kind = ReferenceTrainer(cfg['num_class'], O.HParams(), gan=cfg['gan'], arch_d=cfg['arch_d'], state=sd), \
+            'reference'
+    else:
+        tr, kind = O.OracleTrainer(sd, O.HParams(), gan=cfg['gan'], arch_d=cfg['arch_d']), 'port'
     flow, mv, res, target = O.make_inputs(sample_batch, 3, cfg['num_class'], seed=0)
     per = 2 if cfg['gan'] else 1
     for _ in range(warmup * per):
         tr.step(flow, mv, res, target)
-    t0 = time.perf_counter()
-    for _ in range(steps * per):
-        tr.step(flow, mv, res, target)
-    dt = (time.perf_counter() - t0) / (steps * per)
-    return sample_batch / dt, dt * 1e3, cores
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        for _ in range(per):
+            tr.step(flow, mv, res, target)
+        times.append((time.perf_counter() - t0) / per)
+    times.sort()
+    dt = times[len(times) // 2]
+    sample = ('median of %d timed steps after %d warm-up, B=%d clips x 3 segments of the same workload, '
+              'torch CPU fp32, %d threads' % (steps, warmup, sample_batch, cores))
+    return {'value': sample_batch / dt, 'unit': 'clips/s', 'cores': cores, 'kind': kind, 'sample': sample,
+            'ms_per_step': dt * 1e3, 'batch': sample_batch}
 
 
 def run_reference(args):
@@ -108,16 +148,18 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    sb = args.cpu_sample_batch
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    rate, ms, cores = cpu_reference_rate(args.config, steps, warmup, sb)
-    sample = '%d timed + %d warm-up steps of B=%d clips (x3 segments) of the same workload' % (steps, warmup, sb)
+    sb = cpu_sample_batch(args.cpu_sample_batch)
+    steps, warmup = max(5, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    base = cpu_reference_rate(args.config, steps, warmup, sb)
+    rate = base['value']
     line = {
         'impl': 'reference', 'metric': 'clips/sec', 'value': rate, 'unit': 'clips/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': cfg['workload'], 'note': 'CPU, torch fp32, oracle restatement of the reference step'},
-        'cpu_baseline': {'value': rate, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'steps': steps, 'warmup': warmup, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'] % sb, 'clips_per_gpu': sb, 'global_batch': sb, 'segments': 3,
+                   'note': 'CPU, torch fp32: the reference Model (oracle/_ref) inside the restated train.py step'
+                   if base['kind'] == 'reference' else 'CPU, torch fp32, oracle restatement of the reference step'},
+        'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': rate, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -140,56 +182,30 @@ def protect_stdout():
     os.dup2(2, 1)
 
 
-def main():
-    protect_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='dmcnet', choices=list(CONFIGS))
-    ap.add_argument('--batch', type=int, default=64, help='clips per GPU')
-    ap.add_argument('--cpu-sample-batch', type=int, default=4)
-    ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--input', default='fp32', choices=['fp32', 'u8'],
-                    help="host format of the e2e leg: three normalised fp32 tensors (default, the measured "
-                         "path) or the uint8 [B,S,H,W,7] sample stack normalised on the device")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
-    if args.impl == 'reference':
-        return run_reference(args)
-
+# ---------------------------------------------------------------------------- one measured configuration
+def measure(cfg_name, B, args, *, rank, local_rank, world, clocks=False, roofline=False):
+    """W warm-up + K timed steps of one configuration at B clips per rank: resident throughput,
+    end-to-end throughput from pinned host memory, optional per-family breakdown."""
     import torch
     import torch.distributed as dist
     from dmcnet_b200 import ops
     from dmcnet_b200.engine import DmcEngine
+    from dmcnet_b200.model import build_state
     from dmcnet_b200.trainer import FusedTrainStep, HParams
 
-    rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        import datetime
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
-                                timeout=datetime.timedelta(seconds=180))
-    cfg = CONFIGS[args.config]
-    B, S, H, W = args.batch, 3, 224, 224
+    cfg = CONFIGS[cfg_name]
+    S, H, W = 3, 224, 224
     per = 2 if cfg['gan'] else 1                      # GAN: one "step" = D-step + G-step pair / 2
 
-    # synthetic inputs with the CoviarDataSet value model (uint8 -> normalised fp32), seeded per rank
+    # synthetic inputs with the CoviarDataSet value model (uint8 -> normalised fp32), seeded per rank.
+    # Drawn once as the uint8 stack [B,S,H,W,7] (flow | mv | residual), normalised as dataset.py:251-263.
     g = torch.Generator().manual_seed(1234 + rank)
 
-    def u8(shape, sigma):
-        return torch.clamp(torch.round(128.0 + sigma * torch.randn(shape, generator=g)), 0, 255)
-    std = torch.tensor((0.229, 0.224, 0.225))
-    mv = ((u8((B, S, 2, H, W), 25.0) / 255.0 - 0.5) / std.mean()).float().pin_memory()
-    res = ((u8((B, S, 3, H, W), 20.0) / 255.0 - 0.5) / std.view(1, 1, 3, 1, 1)).float().pin_memory()
-    flow = ((u8((B, S, 2, H, W), 30.0) / 255.0 - 0.5) / std.mean()).float().pin_memory()
+    def u8(ch, sigma):
+        return torch.clamp(torch.round(128.0 + sigma * torch.randn((B, S, H, W, ch), generator=g)), 0, 255)
+    stack_u8 = torch.cat((u8(2, 30.0), u8(2, 25.0), u8(3, 20.0)), 4).to(torch.uint8).contiguous().pin_memory()
     target = torch.randint(0, cfg['num_class'], (B,), generator=g).pin_memory()
 
-    # random-init weights of the reference architecture (torchvision resnet18 + reference conv inits)
-    from dmcnet_b200.model import build_state
     sd = build_state(cfg['num_class'], cfg['arch_d'], seed=1)
     eng = DmcEngine(cfg['num_class'], S, B * S, gan=cfg['gan'], arch_d=cfg['arch_d'])
     eng.load_state(sd)
@@ -209,7 +225,7 @@ def main():
         return float(t[0])
 
     # ---------------- device-resident throughput
-    tr.load_inputs(flow, mv, res, target)
+    tr.load_inputs_u8(stack_u8, target)               # split + normalise on the device, once
     masks_d = eng.draw_dropout_masks(2 * B * S) if cfg['gan'] else None
     masks_g = eng.draw_dropout_masks(B * S) if cfg['gan'] else None
 
@@ -224,8 +240,10 @@ def main():
     for _ in range(args.warmup * per + 2 * per):      # +2: graph warm-up and capture
         resident_step()
     ops.reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = None
+    if clocks:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -237,22 +255,12 @@ def main():
     launches = ops.launch_count() if not tr.use_graph else tr.launches_per_step * args.steps * per
 
     # ---------------- end to end through the public API with host inputs
-    # FusedTrainStep.step_pipelined: every step copies ITS batch from pinned host memory
-    # (on a copy stream, overlapping the previous step's compute) and reads back the metrics
-    # of the step that just finished; flush() inside the timed region collects the last one.
-    stack_u8 = None
-    if args.input == 'u8':
-        # the same sample values as one interleaved uint8 stack (flow | mv | residual channels)
-        denorm = lambda t, d: torch.round((t * d + 0.5) * 255.0).clamp_(0, 255)
-        stack_u8 = torch.cat((denorm(flow, std.mean()), denorm(mv, std.mean()),
-                              denorm(res, std.view(1, 1, 3, 1, 1))), 2).permute(0, 1, 3, 4, 2)
-        stack_u8 = stack_u8.to(torch.uint8).contiguous().pin_memory()
-
+    # every step copies ITS batch from pinned host memory (copy stream, overlapping the previous
+    # step's compute), runs the input kernels + the step, and reads back the metric record of the
+    # step that just finished; flush() inside the timed region collects the last one.
     def e2e_step():
         mk = masks_d if tr._mode() == 'D' else masks_g
-        if stack_u8 is not None:
-            return tr.step_pipelined_u8(stack_u8, target, masks=mk)
-        return tr.step_pipelined(flow, mv, res, target, masks=mk)
+        return tr.step_pipelined_u8(stack_u8, target, masks=mk)
     for _ in range(2 * per):
         e2e_step()
     tr.flush()
@@ -266,48 +274,123 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps / per)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    h2d = (flow.numel() + mv.numel() + res.numel()) * 4 + target.numel() * 8
-    if stack_u8 is not None:
-        h2d = stack_u8.numel() + target.numel() * 8
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    h2d = stack_u8.numel() + target.numel() * 8
     d2h = 16 * 8                                     # one pinned 16-double stats record per step
 
-    # ---------------- roofline of the dominant kernel family (instrumented eager pass)
-    # every rank runs it (the steps contain the gradient all-reduce); rank 0 reports
-    from dmcnet_b200.profiling import measure_roofline
-    roof = measure_roofline(resident_step, per, min(args.steps, 3), tr)
-    barrier()
+    roof = None
+    if roofline:
+        # every rank runs it (the steps contain the gradient all-reduce); rank 0 reports
+        from dmcnet_b200.profiling import measure_roofline
+        roof = measure_roofline(resident_step, per, min(args.steps, 3), tr)
+        barrier()
+
+    clips = B * world
+    out = {
+        'workload': cfg['workload'] % B, 'clips_per_gpu': B, 'global_batch': clips,
+        'value': clips / (ms_step * 1e-3), 'unit': 'clips/s', 'ms_per_step': ms_step,
+        'e2e': {'value': clips / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
+        'gpu_launches': int(launches),
+        'algorithmic_tflops': GFLOP_PER_CLIP[cfg_name] * clips / ms_step,
+        'last_metrics': last, 'cuda_graph': bool(tr.use_graph),
+    }
+    if sampler is not None:
+        out['clocks'] = sampler.summary()
+    if roof:
+        out['roofline'] = roof['roofline']
+        out['kernel_breakdown_ms_per_step'] = roof['breakdown']
+    del tr, eng, stack_u8
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    protect_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='dmcnet', choices=list(CONFIGS), help='headline configuration')
+    ap.add_argument('--batch', type=int, default=64, help='clips per GPU (weak) ')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help="headline scaling mode; 'strong' fixes the GLOBAL batch at 512 (512/N per GPU)")
+    ap.add_argument('--cpu-sample-batch', type=int, default=0, help='0 = 64 if host memory allows, else 16')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='headline only (skip configs.config3 / config4_strong)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                timeout=datetime.timedelta(seconds=300))
+    kw = dict(rank=rank, local_rank=local_rank, world=world)
+    B = args.batch
+    if args.scaling == 'strong':
+        if STRONG_GLOBAL_BATCH % world:
+            raise SystemExit('strong scaling needs a world size dividing %d' % STRONG_GLOBAL_BATCH)
+        B = STRONG_GLOBAL_BATCH // world
+    head = measure(args.config, B, args, clocks=True, roofline=True, **kw)
+
+    extras = {}
+    if not args.no_extras:
+        plan = []
+        if args.config != 'gan':
+            plan.append(('config3', 'gan', args.batch, 'weak'))
+        if STRONG_GLOBAL_BATCH % world == 0:
+            plan.append(('config4_strong', 'gan51', STRONG_GLOBAL_BATCH // world, 'strong'))
+        for key, cfg_name, b, mode in plan:
+            try:
+                r = measure(cfg_name, b, args, roofline=(key == 'config3'), **kw)
+                r['scaling'] = mode
+                extras[key] = r
+            except Exception as e:  # noqa: BLE001  (an extra must never take the headline down)
+                extras[key] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    clips = B * world
     line = {
-        'metric': 'clips/sec', 'value': clips / (ms_step * 1e-3), 'unit': 'clips/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (bf16x3 split on tensor cores, fp32 accumulate)',
-        'data': 'synthetic',
-        'config': {'workload': cfg['workload'], 'clips_per_gpu': B, 'global_batch': clips, 'segments': S,
-                   'parallelism': 'dp%d' % world,
+        'metric': 'clips/sec', 'value': head['value'], 'unit': 'clips/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': head['ms_per_step'], 'higher_is_better': True,
+        'scaling': args.scaling, 'vs_baseline': None,
+        'dtype': 'f32 (bf16x3 split on tensor cores, fp32 accumulate)', 'data': 'synthetic',
+        'config': {'workload': head['workload'], 'clips_per_gpu': head['clips_per_gpu'],
+                   'global_batch': head['global_batch'], 'segments': 3, 'parallelism': 'dp%d' % world,
                    'l2_policy': 'inputs+activations per step (>2 GB) far exceed the 126 MB L2',
-                   'cuda_graph': bool(tr.use_graph), 'e2e_input': args.input},
-        'e2e': {'value': clips / (ms_e2e * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
-        'gpu_launches': int(launches),
-        'clocks': sampler.summary(),
-        'algorithmic_tflops': GFLOP_PER_CLIP[args.config] * clips / ms_step,
-        'last_metrics': last,
+                   'cuda_graph': head['cuda_graph'], 'e2e_input': 'uint8 sample stack [B,S,H,W,7], pinned'},
+        'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'], 'clocks': head.get('clocks'),
+        'algorithmic_tflops': head['algorithmic_tflops'], 'last_metrics': head['last_metrics'],
     }
-    if roof:
-        line['roofline'] = roof.pop('roofline')
-        line['kernel_breakdown_ms_per_step'] = roof['breakdown']
-    if not args.no_cpu_baseline and world >= 1:
-        rate, ms, cores = cpu_reference_rate(args.config, 2, 1, args.cpu_sample_batch)
-        line['cpu_baseline'] = {'value': rate, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
-                                'sample': '2 timed + 1 warm-up steps of B=%d clips (x3 segments) of the same '
-                                          'workload, torch CPU fp32, oracle restatement' % args.cpu_sample_batch}
+    if 'roofline' in head:
+        line['roofline'] = head['roofline']
+        line['kernel_breakdown_ms_per_step'] = head['kernel_breakdown_ms_per_step']
+    if extras:
+        line['configs'] = extras
+    if not args.no_cpu_baseline and world == 1:
+        sb = cpu_sample_batch(args.cpu_sample_batch)
+        base = cpu_reference_rate(args.config, 5, 1, sb)
+        line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        if 'config3' in extras and 'error' not in extras['config3']:
+            b3 = cpu_reference_rate('gan', 5, 1, 16)
+            extras['config3']['cpu_baseline'] = {k: b3[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

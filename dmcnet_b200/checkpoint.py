@@ -123,7 +123,8 @@ def merge_non_strict(current: Dict[str, torch.Tensor], loaded: Dict[str, torch.T
             merged[k] = loaded[k]
         else:
             merged[k] = v
-    missing = [k for k in current if k not in loaded]
+    # torch's own loader does not report a missing num_batches_tracked (BN version < 2 checkpoints)
+    missing = [k for k in current if k not in loaded and not k.endswith('.num_batches_tracked')]
     unexpected = [k for k in loaded if k not in current]
     return merged, missing, unexpected
 

@@ -104,7 +104,8 @@ class DmcEngine:
     def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
-                 grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH):
+                 grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH,
+                 share_from: Optional['DmcEngine'] = None):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -127,11 +128,22 @@ class DmcEngine:
         # per-layer rounding noise (~1e-3) random-walks to 7e-3 relative at the stem/generator
         # gradients, so it is opt-in; the default keeps every GEMM at the fp32-equivalent split.
         self.grad_bf16 = grad_bf16
+        # share_from: alias another engine's parameter / gradient / Adam buckets and BatchNorm buffers
+        # (a second execution plan for a different frame count over the SAME model state)
+        self._share_from = share_from
         self._build_param_table()
         self._alloc_generator()
         self._alloc_classifier()
         if self.gan:
             self._alloc_discriminator()
+
+    def sibling(self, frames: int) -> 'DmcEngine':
+        """A second execution plan for `frames` frames over the SAME model state (shared parameter,
+        gradient, Adam buckets and BatchNorm buffers) -- the short last batch of an epoch."""
+        return DmcEngine(self.num_class, self.S, frames, gan=self.gan, arch_d=self.arch_d,
+                         gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
+                         device=self.device, gemm_engine=self.gemm_engine, grad_bf16=self.grad_bf16,
+                         gen_growth=self.gen_growth, share_from=self)
 
     def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
@@ -215,6 +227,13 @@ class DmcEngine:
                 off += (n + 63) // 64 * 64
             self.group_range[tag] = (start, off)
         self.total = off
+        if getattr(self, '_share_from', None) is not None:
+            o = self._share_from
+            if list(o.specs.items()) != list(self.specs.items()):
+                raise ValueError('share_from: the two engines describe different models')
+            self.params, self.grads, self.exp_avg, self.exp_avg_sq = o.params, o.grads, o.exp_avg, o.exp_avg_sq
+            self.buffers = o.buffers
+            return
         z = lambda: torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
         # BatchNorm buffers (state_dict entries that are not parameters)
@@ -260,6 +279,10 @@ class DmcEngine:
         for k in self.specs:
             self.p(k).copy_(sd[k].detach().reshape(-1).to(self.device, torch.float32))
         for k, b in self.buffers.items():
+            if k not in sd and k.endswith('.num_batches_tracked'):
+                # checkpoints written by torch < 0.4.1 (the reference trained with 0.3.1, README.md:28)
+                # have no such key; torch's own loader keeps the current value (BN version check)
+                continue
             b.copy_(sd[k].detach().to(self.device))
 
     def state_dict(self) -> "OrderedDict[str, torch.Tensor]":

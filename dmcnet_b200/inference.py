@@ -147,7 +147,9 @@ class VideoScorer:
         self.eng = DmcEngine(num_class, test_segments, self.per_launch, gan=arch_d is not None,
                              arch_d=arch_d, gen_flow_or_delta=gen_flow_or_delta, height=height,
                              width=width, device=device)
-        missing = [k for k in list(self.eng.specs) + list(self.eng.buffers) if k not in state]
+        # num_batches_tracked is absent from torch < 0.4.1 checkpoints (the reference's, README.md:28)
+        missing = [k for k in list(self.eng.specs) + list(self.eng.buffers)
+                   if k not in state and not k.endswith('.num_batches_tracked')]
         if missing:
             raise KeyError('state_dict lacks %d tensors of the scoring path, e.g. %s'
                            % (len(missing), missing[0]))

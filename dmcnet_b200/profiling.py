@@ -41,52 +41,94 @@ class FamilyTimer:
         e0.record()
         yield
         e1.record()
-        self.events.append((name, e0, e1, _flops(name, args)))
+        self.events.append((name, e0, e1) + _work(name, args))
 
     def totals(self):
         torch.cuda.synchronize()
-        ms, fl, cnt = defaultdict(float), defaultdict(float), defaultdict(int)
-        for name, e0, e1, f in self.events:
+        ms, fl, by, cnt = defaultdict(float), defaultdict(float), defaultdict(float), defaultdict(int)
+        for name, e0, e1, f, b in self.events:
             ms[name] += e0.elapsed_time(e1)
             fl[name] += f
+            by[name] += b
             cnt[name] += 1
-        return ms, fl, cnt
+        return ms, fl, by, cnt
 
 
 def _v(a):
     return a.value if hasattr(a, 'value') else a
 
 
+def _interior_fraction(Hp, Wp):
+    ph = ops.pad_hi()
+    return ((Hp - 1 - ph) * (Wp - 1 - ph)) / float(Hp * Wp) if Hp else 1.0
+
+
 def _flops(name, args):
     """Algorithmic FLOPs of one call (0 for bandwidth kernels)."""
+    return _work(name, args)[0]
+
+
+def _work(name, args):
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one call; bytes = every operand touched once."""
     if name in ('dmc_tc_tap_gemm', 'dmc_simt_tap_gemm'):
         K, N, M, Hp, Wp, ntaps = _v(args[4]), _v(args[8]), _v(args[10]), _v(args[12]), _v(args[13]), _v(args[14])
-        ph = ops.pad_hi()
-        valid = M * ((Hp - 1 - ph) * (Wp - 1 - ph)) / float(Hp * Wp) if Hp else M
-        return 2.0 * valid * N * K * ntaps
+        valid = M * _interior_fraction(Hp, Wp)
+        return 2.0 * valid * N * K * ntaps, M * (K * 4.0 + N * 4.0)
     if name in ('dmc_tc_wgrad', 'dmc_simt_wgrad'):
         P, Cout, Cin, ntaps = _v(args[2]), _v(args[3]), _v(args[7]), _v(args[9])
-        return 2.0 * P * Cout * Cin * ntaps            # upper bound: ring rows are zero work
+        # ring rows of dY are zero: only interior pixels are algorithmic work.  The call carries no
+        # geometry, so the fraction comes from the square frame the row count implies (set by the hook)
+        return 2.0 * P * _WGRAD_INTERIOR.get(int(P), 1.0) * Cout * Cin * ntaps, P * (Cout + Cin) * 4.0
     if name in ('dmc_conv_fwd',):
         Cin, H, W, Cout, ks, stride, N = (_v(args[i]) for i in (2, 3, 4, 7, 8, 9, 17))
-        return 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * ks * ks
+        ho, wo = H // stride, W // stride
+        return 2.0 * N * ho * wo * Cin * Cout * ks * ks, 4.0 * N * (Cin * H * W + Cout * ho * wo)
     if name in ('dmc_conv_wgrad',):
         Cin, H, W, Cout, ks, stride, N = (_v(args[i]) for i in (2, 3, 4, 7, 8, 9, 12))
-        return 2.0 * N * (H // stride) * (W // stride) * Cin * Cout * ks * ks
+        ho, wo = H // stride, W // stride
+        return 2.0 * N * ho * wo * Cin * Cout * ks * ks, 4.0 * N * (Cin * H * W + Cout * ho * wo)
     if name in ('dmc_conv_dgrad',):
         Cout, cic, ks, stride, H, W, N = (_v(args[i]) for i in (2, 5, 6, 7, 10, 11, 13))
-        return 2.0 * N * (H // stride) * (W // stride) * cic * Cout * ks * ks
-    return 0.0
+        ho, wo = H // stride, W // stride
+        return 2.0 * N * ho * wo * cic * Cout * ks * ks, 4.0 * N * (cic * H * W + Cout * ho * wo)
+    if name in ('dmc_conv3x3_dgrad_fused',):
+        Cy, H, W, Cx, N = (_v(args[i]) for i in (2, 3, 4, 6, 14))
+        return 2.0 * N * H * W * Cy * Cx * 9, 4.0 * N * H * W * (Cy + 2 * Cx)
+    if name in ('dmc_conv3x3_taps2',):
+        Cin, H, W, Cout, N = (_v(args[i]) for i in (2, 3, 4, 7, 13))
+        return 2.0 * N * H * W * Cin * Cout * 4, 4.0 * N * H * W * (Cin + Cout)
+    return 0.0, 0.0
+
+
+_WGRAD_INTERIOR = {}          # rows P of a pixel-major tensor -> interior fraction (filled by register_geometry)
+
+
+def register_geometry(frames, H, W):
+    """Tell the FLOP model which padded row counts belong to which frame geometry, so that the
+    weight-gradient count excludes the zero ring like the tap-GEMM count does."""
+    Hp, Wp = ops.padded(H), ops.padded(W)
+    _WGRAD_INTERIOR[int(frames * Hp * Wp)] = _interior_fraction(Hp, Wp)
 
 
 def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r01_tap_gemm_traffic.json), or None."""
-    p = os.path.join(ROOT, 'profiles', 'r01_tap_gemm_traffic.json')
-    if os.path.isfile(p):
-        with open(p) as f:
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full capture
+    (profiles/rNN_tap_gemm_traffic.json), or None."""
+    d = os.path.join(ROOT, 'profiles')
+    cands = sorted(f for f in os.listdir(d) if f.endswith('_tap_gemm_traffic.json')) if os.path.isdir(d) else []
+    if cands:
+        with open(os.path.join(d, cands[-1])) as f:
             return json.load(f).get('dram_bytes_per_launch_avg')
     return None
+
+
+def fma_peak_tflops():
+    """fp32 FMA peak: 128 FMA/clk/SM (tools/ubench/pipes.cu) x 148 SMs x max SM clock."""
+    mhz = 1965.0
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        with open(p) as f:
+            mhz = float(json.load(f).get('sm_max_mhz', mhz))
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12
 
 
 def measure_roofline(resident_step, per, steps, trainer):
@@ -96,6 +138,9 @@ def measure_roofline(resident_step, per, steps, trainer):
     was_graph = trainer.use_graph
     trainer.use_graph = False
     timer = FamilyTimer()
+    eng = trainer.eng
+    for blk in getattr(eng, 'blocks', []):
+        register_geometry(eng.N, blk['geo'].H, blk['geo'].W)
     resident_step()                                   # eager warm-up outside the hook
     if per == 2:
         resident_step()
@@ -106,11 +151,11 @@ def measure_roofline(resident_step, per, steps, trainer):
     finally:
         ops.set_call_hook(None)
         trainer.use_graph = was_graph
-    ms, fl, cnt = timer.totals()
+    ms, fl, by, cnt = timer.totals()
     if os.environ.get('DMC_DUMP_CALLS'):            # per-call times of one family, in launch order
         fam_dump = os.environ['DMC_DUMP_CALLS']
         import sys
-        for name, e0, e1, f in timer.events:
+        for name, e0, e1, f, _b in timer.events:
             if fam_dump in name:
                 print('CALL %s %.1f us %.1f GFLOP' % (name, e0.elapsed_time(e1) * 1e3, f / 1e9), file=sys.stderr)
     denom = float(steps * per)
@@ -130,9 +175,20 @@ def measure_roofline(resident_step, per, steps, trainer):
         'note': 'algorithmic FLOPs (padding ring excluded); bf16x3 split issues 3 MMAs per MAC -> ceiling 1/3; '
                 'traffic = DRAM bytes per launch (bytes) from the committed ncu capture',
     }
+    # the CUDA-core conv families of the generator / discriminator (north star: report achieved HBM
+    # GB/s; they are FMA-bound, so the fp32-FMA-pipe fraction is given alongside) and the wgrad GEMM
     others = {}
+    fma = fma_peak_tflops()
     for k in ms:
         if fl[k] > 0 and k != fam:
-            others[k.replace('dmc_', '')] = {'tflops': fl[k] / (ms[k] * 1e-3) / 1e12, 'ms_per_step': ms[k] / denom}
+            tf = fl[k] / (ms[k] * 1e-3) / 1e12
+            o = {'tflops': tf, 'ms_per_step': ms[k] / denom,
+                 'algorithmic_gbs': by[k] / (ms[k] * 1e-3) / 1e9,
+                 'hbm_frac': by[k] / (ms[k] * 1e-3) / 1e9 / peaks['hbm_gbs']}
+            if 'tc_' in k:
+                o['tensor_frac'] = tf / peaks['tensor_tflops']
+            else:
+                o['fma_frac'] = tf / fma
+            others[k.replace('dmc_', '')] = o
     out['roofline']['other_families'] = others
     return out

@@ -118,8 +118,9 @@ class FusedTrainStep:
         self.iteration = 0
         self.flow_kind = flow_loss_kind(hp.loss_mse)
         self._build_adam_tables()
-        self.set_epoch(0, epoch_thre=0)
         self._graphs: Dict[str, object] = {}
+        self._tails: Dict[int, 'FusedTrainStep'] = {}
+        self.set_epoch(0, epoch_thre=0)
         self._u8_stages: Dict[int, object] = {}
         self.launches_per_step = 0
         # pipelined input staging: H2D of batch k+1 overlaps the compute of batch k
@@ -171,7 +172,11 @@ class FusedTrainStep:
                 lr, wd = 0.0, 0.0
             rows.append((lr * mults[gi], wd * (0.0 if 'bias' in k else 1.0)))
         self.hyper.copy_(torch.tensor(rows, dtype=torch.float32))
-        self._graphs = {}
+        # the captured graphs read `hyper` from device memory and 'full' / 'freeze' are separate graph
+        # keys, so nothing is re-captured at an epoch boundary.
+        # code/dmcnet_GAN/train.py:261,331 alternate D / G on the loader index of the CURRENT epoch
+        # (`i % 2`): every epoch starts with a D-step, whatever the length of the previous one
+        self.iteration = 0
 
     # ------------------------------------------------------------------ checkpoint / resume
     def _hyper_rows(self) -> Dict[str, Tuple[float, float]]:
@@ -325,8 +330,6 @@ class FusedTrainStep:
             with torch.cuda.stream(s):
                 with torch.cuda.graph(ga, stream=s, capture_error_mode='thread_local'):
                     self._fwd_bwd(mode)
-                if apply:
-                    self._allreduce(groups)
                 with torch.cuda.graph(gb, stream=s, capture_error_mode='thread_local'):
                     self._adam(groups)
             torch.cuda.current_stream().wait_stream(s)
@@ -377,8 +380,41 @@ class FusedTrainStep:
     def step(self, input_flow, input_mv, input_residual, target,
              masks: Optional[Sequence[torch.Tensor]] = None, apply: bool = True,
              metrics: bool = True) -> Dict[str, float]:
+        b = int(target.shape[0])
+        if b != self.B:
+            return self._tail(b).step_from(self, input_flow, input_mv, input_residual, target, masks, apply,
+                                           metrics)
         self.load_inputs(input_flow, input_mv, input_residual, target)
         return self._step_staged(masks, apply, metrics)
+
+    # ------------------------------------------------------------------ short final batch
+    def _tail(self, b: int) -> 'FusedTrainStep':
+        """The reference DataLoaders have no drop_last (code/dmcnet/train.py:72-114), so every epoch
+        ends with a smaller batch (HMDB-51 split 1: 3570 clips at batch 45 leave 15).  Such a batch
+        runs on a second execution plan sized for it that SHARES this step's parameter, gradient and
+        Adam buckets, BatchNorm buffers, hyper table and step counters; losses are means over the
+        actual batch, as in the reference.  Plans are cached per size; eager launches (no graph)."""
+        if b < 1 or b > self.B:
+            raise ValueError('batch of %d clips: this step was built for at most %d' % (b, self.B))
+        if self.world > 1:
+            raise ValueError('short final batches are not sharded: use drop_last=True with world_size > 1 '
+                             '(every rank must see the same number of clips)')
+        t = self._tails.get(b)
+        if t is None:
+            eng = self.eng.sibling(b * self.S)
+            t = FusedTrainStep(eng, self.hp, b, use_graph=False)
+            t.hyper, t.steps = self.hyper, self.steps
+            self._tails[b] = t
+        return t
+
+    def step_from(self, parent: 'FusedTrainStep', input_flow, input_mv, input_residual, target, masks, apply,
+                  metrics) -> Dict[str, float]:
+        """One iteration on behalf of `parent` (see ``_tail``): same mode, same counters."""
+        self.freeze, self.iteration = parent.freeze, parent.iteration
+        self.load_inputs(input_flow, input_mv, input_residual, target)
+        out = self._step_staged(masks, apply, metrics)
+        parent.iteration = self.iteration
+        return out
 
     def _step_staged(self, masks, apply: bool, metrics: bool) -> Dict[str, float]:
         """One iteration on the batch already in the static input buffers."""
@@ -396,6 +432,8 @@ class FusedTrainStep:
         code/dmcnet_GAN/train.py:414-459): eval-mode forward (BatchNorm running statistics, no
         dropout), consensus + CE + top-k, the flow criterion and -- GAN -- the adversarial CE of the
         generated maps against "valid".  No gradients, no parameter or statistic is modified."""
+        if int(target.shape[0]) != self.B:                 # last validation batch (no drop_last)
+            return self._tail(int(target.shape[0])).validate_batch(input_flow, input_mv, input_residual, target)
         eng, hp, B, n = self.eng, self.hp, self.B, self.eng.N
         self.load_inputs(input_flow, input_mv, input_residual, target)
         eng.forward(self.in_mv, self.in_res, None, train=False)

@@ -254,29 +254,41 @@ def _conv(x: Tensor, w: Tensor, stride: int, pad: int) -> Tensor:
     return F.conv2d(x, w, None, stride, pad)
 
 
-def resnet18_forward(st: Dict[str, Tensor], x: Tensor, train: bool, prefix: str = 'base_model'
-                     ) -> Tensor:
+def resnet18_forward(st: Dict[str, Tensor], x: Tensor, train: bool, prefix: str = 'base_model',
+                     capture: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """torchvision resnet18 forward with the 2-channel conv1 and num_class fc of
-    code/dmcnet/model.py:283-294."""
+    code/dmcnet/model.py:283-294.  ``capture`` (tests only) receives the intermediate tensors:
+    raw conv outputs ('<unit>.conv'), block activations and the max-pool argmax."""
     p = prefix
+    cap = (lambda k, t: capture.__setitem__(k, t.detach())) if capture is not None else (lambda k, t: None)
     x = _conv(x, st[p + '.conv1.weight'], 2, 3)
+    cap('conv1', x)
     x = F.relu(_bn(x, st, p + '.bn1', train, 1e-5))
+    if capture is not None:
+        cap('pool_idx', F.max_pool2d(x.detach(), 3, 2, 1, return_indices=True)[1])
     x = F.max_pool2d(x, 3, 2, 1)
+    cap('pool', x)
     for li, (width, stride) in enumerate(RESNET18_STAGES, start=1):
         for b in range(2):
             q = '%s.layer%d.%d' % (p, li, b)
             s = stride if b == 0 else 1
             out = _conv(x, st[q + '.conv1.weight'], s, 1)
+            cap(q + '.conv1', out)
             out = F.relu(_bn(out, st, q + '.bn1', train, 1e-5))
+            cap(q + '.act1', out)
             out = _conv(out, st[q + '.conv2.weight'], 1, 1)
+            cap(q + '.conv2', out)
             out = _bn(out, st, q + '.bn2', train, 1e-5)
             if (q + '.downsample.0.weight') in st:
                 idt = _conv(x, st[q + '.downsample.0.weight'], s, 0)
+                cap(q + '.downsample.0', idt)
                 idt = _bn(idt, st, q + '.downsample.1', train, 1e-5)
             else:
                 idt = x
             x = F.relu(out + idt)
+            cap(q + '.out', x)
     x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+    cap('pooled', x)
     return F.linear(x, st[p + '.fc.weight'], st[p + '.fc.bias'])
 
 

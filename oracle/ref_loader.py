@@ -1,5 +1,6 @@
-"""Import the *reference's own* ``model.py`` from /root/reference (build container
-only -- the GPU box has no /root/reference).  TEST INFRASTRUCTURE ONLY.
+"""Import the *reference's own* ``model.py`` from /root/reference (build container) or from the
+sourceless byte-compiled copy staged under oracle/_ref by oracle/make_ref.py (the GPU box has no /root/reference).
+TEST / BASELINE INFRASTRUCTURE ONLY.
 
 Used by ``oracle/pin_against_reference.py`` and ``tests/golden/make_golden.py``.
 Both reference variants define top-level modules ``model`` and ``transforms``
@@ -15,11 +16,25 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get('DMC_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')       # oracle/make_ref.py
+
+
+def _pick_root() -> str:
+    """/root/reference in the build container, else the copy staged by oracle/make_ref.py."""
+    env = os.environ.get('DMC_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isfile(os.path.join('/root/reference', 'code', 'dmcnet', 'model.py')):
+        return '/root/reference'
+    return _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'code', 'dmcnet', 'model.py'))
+    d = os.path.join(REFERENCE_ROOT, 'code', 'dmcnet')
+    return os.path.isfile(os.path.join(d, 'model.py')) or os.path.isfile(os.path.join(d, 'model.pyc'))
 
 
 def load_reference_model_module(variant: str):
@@ -35,7 +50,10 @@ def load_reference_model_module(variant: str):
     try:
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')          # SyntaxWarning: `is 'ContextNetwork'`
-            spec = importlib.util.spec_from_file_location(name, os.path.join(d, 'model.py'))
+            path = os.path.join(d, 'model.py')
+            if not os.path.isfile(path):                   # staged, sourceless (oracle/make_ref.py)
+                path = os.path.join(d, 'model.pyc')
+            spec = importlib.util.spec_from_file_location(name, path)
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
     finally:

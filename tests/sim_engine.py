@@ -21,8 +21,9 @@ from oracle import dmc_oracle as O
 
 class SimEngine(DmcEngine):
     def __init__(self, num_class, num_segments, frames, *, gan=False, arch_d=None, gen_flow_or_delta=1,
-                 height=224, width=224, gen_growth=(8, 8, 6, 4, 2)):
+                 height=224, width=224, gen_growth=(8, 8, 6, 4, 2), share_from=None):
         self.device = torch.device('cpu')
+        self._share_from = share_from
         self.num_class, self.S, self.N = num_class, num_segments, frames
         self.gan, self.arch_d = gan, (arch_d if gan else None)
         self.gen_flow_or_delta = gen_flow_or_delta
@@ -37,6 +38,11 @@ class SimEngine(DmcEngine):
         self.logits, self.d_logits = torch.zeros(N, num_class), torch.zeros(N, num_class)
         self.validity, self.d_validity = torch.zeros(2 * N, 2), torch.zeros(2 * N, 2)
         self._masks, self._m, self._graph = None, N, None
+
+    def sibling(self, frames):
+        return SimEngine(self.num_class, self.S, frames, gan=self.gan, arch_d=self.arch_d,
+                         gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
+                         gen_growth=self.gen_growth, share_from=self)
 
     # -- kernels replaced by autograd on the oracle's functional model
     def forward(self, input_mv, input_residual, input_flow=None, *, train=True, masks=None, use_dropout=True):

@@ -469,7 +469,7 @@ def test_tap_gemm_full_size_layers_vs_fp64(n, cin, cout, h, stride):
     ho = h // stride
     Hp = Wp = ops.padded(ho)
     P = n * Hp * Wp
-    assert P // 128 >= 100
+    assert (P // 128) * (cout // 128 if cout >= 128 else 1) > 148     # more tiles than CTAs: persistent loop
     W_hi = torch.zeros(9, cout, cin, dtype=torch.bfloat16, device=dev)
     W_lo, Wt_hi, Wt_lo = (torch.zeros_like(W_hi) for _ in range(3))
     ops.weight_prep(w.contiguous(), cout, cin, 9, W_hi, W_lo, Wt_hi.view(9, cin, cout), Wt_lo.view(9, cin, cout))
