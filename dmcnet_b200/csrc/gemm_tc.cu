@@ -121,6 +121,17 @@ struct BwFuse {
   const float* invstd;
 };
 
+// Optional fused activation epilogue of a forward GEMM (discriminator blocks, code/dmcnet_GAN/
+// model.py:254-279: Conv(bias) -> LeakyReLU -> Dropout2d): D = mask[frame][n] * lrelu(D + bias[n]),
+// and the fused column statistics are then those of the activated, masked value (the BatchNorm that
+// follows the dropout).  frame = q / frame_rows.  mask may be null (eval mode / no dropout).
+struct ActFuse {
+  const float* bias;     // [N]; null = off
+  const float* mask;     // [frames][N] or null
+  float slope;
+  unsigned frame_rows;   // Hp * Wp
+};
+
 template <int BN, int STAGES>
 struct TapGemmWsSmem {
   static constexpr int A_BYTES = 128 * 128;
@@ -138,7 +149,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
-                   const BwFuse bw, int a_lo_on) {
+                   const BwFuse bw, int a_lo_on, const ActFuse act) {
   using S = TapGemmWsSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -303,14 +314,37 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * a);
         }
+        if (act.bias != nullptr) {
+          // bias + LeakyReLU + per-(frame, channel) dropout scale on this thread's row
+          const float* mrow = (act.mask && keep)
+                                  ? act.mask + (long)((unsigned)q / act.frame_rows) * N + n0 + c : nullptr;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float4 v;
-          v.x = keep ? __uint_as_float(r[4 * g + 0]) : 0.f;
-          v.y = keep ? __uint_as_float(r[4 * g + 1]) : 0.f;
-          v.z = keep ? __uint_as_float(r[4 * g + 2]) : 0.f;
-          v.w = keep ? __uint_as_float(r[4 * g + 3]) : 0.f;
-          *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(act.bias + n0 + c + 4 * g));
+            float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (mrow) m4 = __ldg(reinterpret_cast<const float4*>(mrow + 4 * g));
+            float4 v;
+            v.x = __uint_as_float(r[4 * g + 0]) + b4.x;
+            v.y = __uint_as_float(r[4 * g + 1]) + b4.y;
+            v.z = __uint_as_float(r[4 * g + 2]) + b4.z;
+            v.w = __uint_as_float(r[4 * g + 3]) + b4.w;
+            v.x = (v.x > 0.f ? v.x : v.x * act.slope) * m4.x;
+            v.y = (v.y > 0.f ? v.y : v.y * act.slope) * m4.y;
+            v.z = (v.z > 0.f ? v.z : v.z * act.slope) * m4.z;
+            v.w = (v.w > 0.f ? v.w : v.w * act.slope) * m4.w;
+            if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 v;
+            v.x = keep ? __uint_as_float(r[4 * g + 0]) : 0.f;
+            v.y = keep ? __uint_as_float(r[4 * g + 1]) : 0.f;
+            v.z = keep ? __uint_as_float(r[4 * g + 2]) : 0.f;
+            v.w = keep ? __uint_as_float(r[4 * g + 3]) : 0.f;
+            *reinterpret_cast<float4*>(stage + lane * S::EPI_PITCH + 4 * g) = v;
+          }
         }
         __syncwarp();
         if (stats && !bwd) {
@@ -355,10 +389,10 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                 const long off = gq * (long)ldD + n0 + c + c4;
                 yv[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
                 gv[ii] = yv[ii];
-                hv[ii] = make_uint2(0u, 0u);
+                hv[ii] = make_uint2(0x3f803f80u, 0x3f803f80u);      // act_hi == null: no ReLU mask (all "> 0")
                 if (gq < M) {
                   yv[ii] = __ldg(reinterpret_cast<const float4*>(bw.Y + off));
-                  hv[ii] = __ldg(reinterpret_cast<const uint2*>(bw.act_hi + off));
+                  if (bw.act_hi) hv[ii] = __ldg(reinterpret_cast<const uint2*>(bw.act_hi + off));
                   if (bw.gb) gv[ii] = __ldg(reinterpret_cast<const float4*>(bw.gb + off));
                 }
               }
@@ -402,7 +436,7 @@ template <int BN, int STAGES>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
-                              const BwFuse& bw, int a_lo_on, cudaStream_t stream) {
+                              const BwFuse& bw, int a_lo_on, const ActFuse& act, cudaStream_t stream) {
   using S = TapGemmWsSmem<BN, STAGES>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -416,7 +450,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n, stats, bw, a_lo_on);
+                                                  tiles_m, tiles_n, stats, bw, a_lo_on, act);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -897,22 +931,15 @@ static int sm_count() {
 
 using namespace dmc;
 
-// D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
-// stats (nullable, zeroed by the caller): double [2][N], += per-column sum and sum of squares of D
-// (the BatchNorm batch statistics of a convolution output, fused into the epilogue).
-// bw_Y != null switches the epilogue to the fused BatchNorm-backward reduction (see BwFuse):
-// D receives dz = (D + bw_gb) * [bw_act_hi > 0] and stats[0]/[1] += sum dz / sum dz * xhat.
-// A_lo == NULL: A is taken at bf16 precision (A_hi only, two MMAs per k-step instead of three).
-extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
-                               const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
-                               long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
-                               const int* phase, const int* bsel, double* stats, const float* bw_Y,
-                               const void* bw_act_hi, const float* bw_gb, const float* bw_mean,
-                               const float* bw_invstd, void* stream) {
-  DMC_REQUIRE(bw_Y == nullptr || (stats && bw_act_hi && bw_mean && bw_invstd && ldD == N),
-              "tap_gemm: fused BN backward needs stats, act, mean, invstd and ldD == N");
-  BwFuse bw;
-  bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
+static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                         const void* B_hi, const void* B_lo, int b_slices, int N, float* D, long M,
+                         int ldD, int Hp, int Wp, int ntaps, const int* shift, const int* phase,
+                         const int* bsel, double* stats, const BwFuse& bw, const ActFuse& act,
+                         void* stream) {
+  DMC_REQUIRE(bw.Y == nullptr || (stats && bw.mean && bw.invstd && ldD == N),
+              "tap_gemm: fused BN backward needs stats, mean, invstd and ldD == N");
+  DMC_REQUIRE(act.bias == nullptr || (bw.Y == nullptr && Hp > 0 && Wp > 0 && ldD == N),
+              "tap_gemm: fused activation needs a frame geometry, ldD == N and no BN-backward fusion");
   DMC_REQUIRE(K > 0 && K % 64 == 0, "tap_gemm: K=%d must be a positive multiple of 64", K);
   DMC_REQUIRE(N > 0 && N % 32 == 0, "tap_gemm: N=%d must be a multiple of 32", N);
   DMC_REQUIRE(ldD % 4 == 0 && ldD >= N, "tap_gemm: ldD=%d", ldD);
@@ -933,10 +960,48 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
   if (BN == 64)
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
+}
+
+// D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
+// stats (nullable, zeroed by the caller): double [2][N], += per-column sum and sum of squares of D
+// (the BatchNorm batch statistics of a convolution output, fused into the epilogue).
+// bw_Y != null switches the epilogue to the fused BatchNorm-backward reduction (see BwFuse):
+// D receives dz = (D + bw_gb) * [bw_act_hi > 0] and stats[0]/[1] += sum dz / sum dz * xhat
+// (bw_act_hi == NULL: no ReLU mask -- the BatchNorm being differentiated follows no ReLU).
+// A_lo == NULL: A is taken at bf16 precision (A_hi only, two MMAs per k-step instead of three).
+extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                               const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
+                               long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
+                               const int* phase, const int* bsel, double* stats, const float* bw_Y,
+                               const void* bw_act_hi, const float* bw_gb, const float* bw_mean,
+                               const float* bw_invstd, void* stream) {
+  BwFuse bw;
+  bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
+  ActFuse act;
+  act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
+  return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
+                       shift, phase, bsel, stats, bw, act, stream);
+}
+
+// The forward GEMM of a discriminator block (code/dmcnet_GAN/model.py:254-279): same contraction, the
+// epilogue applies D = mask[frame][n] * LeakyReLU_slope(D + bias[n]) (ActFuse) before the zero-ring
+// mask, the store and the column statistics.  bias [N]; mask [frames][N] or NULL.
+extern "C" int dmc_tc_tap_gemm_act(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                                   const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
+                                   long M, int ldD, int Hp, int Wp, int ntaps, const int* shift,
+                                   const int* phase, const int* bsel, double* stats, const float* bias,
+                                   const float* mask, float slope, void* stream) {
+  DMC_REQUIRE(bias != nullptr, "tap_gemm_act: bias is required");
+  BwFuse bw;
+  bw.Y = nullptr; bw.act_hi = nullptr; bw.gb = nullptr; bw.mean = nullptr; bw.invstd = nullptr;
+  ActFuse act;
+  act.bias = bias; act.mask = mask; act.slope = slope; act.frame_rows = (unsigned)(Hp * Wp);
+  return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
+                       shift, phase, bsel, stats, bw, act, stream);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).

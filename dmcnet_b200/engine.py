@@ -105,7 +105,7 @@ class DmcEngine:
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
                  grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH,
-                 share_from: Optional['DmcEngine'] = None):
+                 share_from: Optional['DmcEngine'] = None, disc_engine: Optional[str] = None):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -131,11 +131,22 @@ class DmcEngine:
         # share_from: alias another engine's parameter / gradient / Adam buckets and BatchNorm buffers
         # (a second execution plan for a different frame count over the SAME model state)
         self._share_from = share_from
+        # discriminator execution plan: 'tc' = every conv as a tcgen05 tap GEMM on pixel-major /
+        # space-to-depth operands (disc_plan.py, csrc/disc_pm.cu); 'planar' = the CUDA-core NCHW kernels
+        # (Discriminator4, odd sizes, and the cross-check of the tensor-core plan)
+        if disc_engine is None:
+            from . import disc_plan as DP
+            disc_engine = 'tc' if (gan and gemm_engine == 'tc' and DP.supported(arch_d, height, width)) \
+                else 'planar'
+        self.disc_engine = disc_engine if gan else None
         self._build_param_table()
         self._alloc_generator()
         self._alloc_classifier()
         if self.gan:
-            self._alloc_discriminator()
+            if self.disc_engine == 'tc':
+                self._alloc_discriminator_tc()
+            else:
+                self._alloc_discriminator()
 
     def sibling(self, frames: int) -> 'DmcEngine':
         """A second execution plan for `frames` frames over the SAME model state (shared parameter,
@@ -143,7 +154,7 @@ class DmcEngine:
         return DmcEngine(self.num_class, self.S, frames, gan=self.gan, arch_d=self.arch_d,
                          gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
                          device=self.device, gemm_engine=self.gemm_engine, grad_bf16=self.grad_bf16,
-                         gen_growth=self.gen_growth, share_from=self)
+                         gen_growth=self.gen_growth, share_from=self, disc_engine=self.disc_engine)
 
     def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
@@ -870,6 +881,195 @@ class DmcEngine:
                                self.dD.view(-1), self.dD.shape[1] * h * w, h, w, d_input_rows,
                                accumulate=True)
 
+
+    # ------------------------------------------------------------------ discriminator, tensor-core plan
+    def _alloc_discriminator_tc(self):
+        """Buffers and tables of the tensor-core discriminator plan (disc_plan.py): per block the index
+        tables, bf16 hi/lo operands, the saved post-dropout activation A (fp32) and the block output Z
+        (hi/lo, what the next GEMM reads); statistics, bias-gradient and GEMM-space weight-gradient
+        pools that one memset clears."""
+        from . import disc_plan as DP
+        dev, H, W = self.device, self.H, self.W
+        M = 2 * self.N
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        i32 = lambda a: torch.from_numpy(a.astype('int32')).contiguous().to(dev)
+        plans = DP.plan(disc_blocks(self.arch_d), H, W)
+        ncol = sum(lp['Np'] for lp in plans)
+        self._dsums = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
+        self._dsums2 = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
+        self._dbias = torch.zeros(ncol, dtype=torch.float64, device=dev)
+        self._dwg = torch.zeros(sum(lp['gmap'].size for lp in plans), **f32)
+        g0 = _Geo(M, H // 4, W // 4)
+        self.d_s4_hi = torch.zeros(g0.P, 64, **bf)            # 4x4 space-to-depth input, hi / lo
+        self.d_s4_lo = torch.zeros(g0.P, 64, **bf)
+        self.d_layers = []
+        col = wg = 0
+        max_pn = g0.P * 64
+        max_xp = max_ws = 0
+        for lp in plans:
+            Hg, Wg = lp['grid']
+            geo = _Geo(M, Hg, Wg)
+            T, Np, Kp = lp['gmap'].shape
+            L = {'name': 'discriminator.discriminator_block_%s' % lp['name'], 'kind': lp['kind'], 'bn': lp['bn'],
+                 'cin': lp['cin'], 'cout': lp['cout'], 'T': T, 'Np': Np, 'Kp': Kp, 'geo': geo,
+                 'Ho': lp['out_hw'][0], 'Wo': lp['out_hw'][1], 'form_out': lp['form_out'],
+                 'gmap': i32(lp['gmap'].reshape(-1)), 'inv': i32(lp['inv'].reshape(-1)),
+                 'cmap': i32(lp['cmap']), 'binv': i32(lp['binv'].reshape(-1)), 'R': lp['inv'].shape[1]}
+            if lp['kind'] == 'P2':
+                L['taps'], L['phases'] = _taps_s2(geo.Wp), 4
+                max_xp = max(max_xp, 4 * geo.P * Kp)
+                # phase-split copy of the block input: kept for the weight gradient
+                L['xp_hi'], L['xp_lo'] = torch.zeros(4 * geo.P * Kp, **bf), torch.zeros(4 * geo.P * Kp, **bf)
+            else:
+                sh = [di * geo.Wp + dj for di, dj in lp['offsets']]
+                L['taps'], L['phases'] = (sh, [0] * T, list(range(T))), 1
+            L['W_hi'], L['W_lo'] = torch.zeros(T, Np, Kp, **bf), torch.zeros(T, Np, Kp, **bf)
+            L['Wt_hi'], L['Wt_lo'] = torch.zeros(T, Kp, Np, **bf), torch.zeros(T, Kp, Np, **bf)
+            L['bias_exp'] = torch.zeros(Np, **f32)
+            L['mask'] = torch.ones(M, Np, **f32)
+            L['mask_idx'] = torch.from_numpy(lp['cmap'].clip(min=0).astype('int64')).to(dev)
+            L['A'] = torch.zeros(geo.P, Np, **f32)
+            L['Z_hi'], L['Z_lo'] = torch.zeros(geo.P, Np, **bf), torch.zeros(geo.P, Np, **bf)
+            L['sums'] = self._dsums[2 * col:2 * col + 2 * Np].view(2, Np)
+            L['sums2'] = self._dsums2[2 * col:2 * col + 2 * Np].view(2, Np)
+            L['dbias_exp'] = self._dbias[col:col + Np]
+            L['dWg'] = self._dwg[wg:wg + T * Np * Kp]
+            for k in ('scale', 'shift', 'mean', 'invstd'):
+                L[k] = torch.zeros(Np, **f32)
+            L['coef'] = torch.zeros(3, Np, **f32)
+            col += Np
+            wg += T * Np * Kp
+            max_pn = max(max_pn, geo.P * Np, geo.P * Kp)
+            max_ws = max(max_ws, ops.wgrad_workspace_floats(geo.P, Np, Kp, T))
+            self.d_layers.append(L)
+        self.d_dz = [torch.zeros(max_pn, **f32) for _ in range(2)]      # gradient ping-pong (w.r.t. Z)
+        self.d_G_hi, self.d_G_lo = torch.zeros(max_pn, **bf), torch.zeros(max_pn, **bf)
+        if max_xp:
+            self.d_dxp = torch.zeros(max_xp, **f32)
+        self.d_wgrad_ws = torch.empty(max_ws, **f32)
+        self.d_in = torch.zeros(M, 2, H, W, **f32)
+        self.validity = torch.zeros(M, 2, **f32)
+        self.d_validity = torch.zeros(M, 2, **f32)
+
+    def _disc_input_tc(self, li: int, m: int):
+        """(hi, lo, phases, rows) of the GEMM A operand of block li for m frames."""
+        L = self.d_layers[li]
+        rows = m * L['geo'].Hp * L['geo'].Wp
+        if li == 0:
+            return self.d_s4_hi, self.d_s4_lo, 1, rows
+        if L['phases'] == 4:
+            n = 4 * rows * L['Kp']
+            return L['xp_hi'][:n].view(4, rows, L['Kp']), L['xp_lo'][:n].view(4, rows, L['Kp']), 4, rows
+        prev = self.d_layers[li - 1]
+        return prev['Z_hi'], prev['Z_lo'], 1, rows
+
+    def _disc_forward_tc(self, x: torch.Tensor, m: int, train: bool, use_masks: bool):
+        """Discriminator*.forward on planar x [m,2,H,W] -> self.validity[:m]; every conv is a tap GEMM
+        whose epilogue applies bias + LeakyReLU(0.2) + Dropout2d and accumulates the statistics of the
+        BatchNorm2d(eps 0.8) that follows (code/dmcnet_GAN/model.py:254-279)."""
+        H, W = self.H, self.W
+        ops.planar_to_s2d4(x.view(-1), 2 * H * W, H, W, m, self.d_s4_hi, self.d_s4_lo)
+        if train:
+            ops.memset_zero(self._dsums)
+        for li, L in enumerate(self.d_layers):
+            p, geo, Np, Kp, T = L['name'], L['geo'], L['Np'], L['Kp'], L['T']
+            ops.weight_gather_prep(self.p(p + '.0.weight'), L['gmap'], T, Np, Kp, L['W_hi'], L['W_lo'],
+                                   L['Wt_hi'], L['Wt_lo'], self.p(p + '.0.bias'), L['cmap'], L['bias_exp'])
+            if L['phases'] == 4:
+                prev = self.d_layers[li - 1]
+                a_hi, a_lo, ph, rows = self._disc_input_tc(li, m)
+                ops.phase_split(prev['Z_hi'], prev['Z_lo'], m, prev['geo'].H, prev['geo'].W, Kp, a_hi, a_lo)
+            else:
+                a_hi, a_lo, ph, rows = self._disc_input_tc(li, m)
+            shift, phase, bsel = L['taps']
+            ops.tap_gemm_act(a_hi, a_lo, L['W_hi'], L['W_lo'], L['A'], a_phases=ph, a_rows=rows, K=Kp,
+                             b_slices=T, N=Np, M=rows, ldD=Np, Hp=geo.Hp, Wp=geo.Wp, shift=shift, phase=phase,
+                             bsel=bsel, bias=L['bias_exp'], mask=(L['mask'] if (train and use_masks) else None),
+                             slope=0.2, stats=(L['sums'] if (train and L['bn']) else None))
+            if L['bn']:
+                ops.pm_bn_finalize(L['sums'] if train else None, L['cmap'], Np, L['cout'],
+                                   float(m * L['Ho'] * L['Wo']), self.p(p + '.3.weight'), self.p(p + '.3.bias'),
+                                   self.buffers[p + '.3.running_mean'], self.buffers[p + '.3.running_var'],
+                                   self.buffers[p + '.3.num_batches_tracked'] if train else None, BN_MOMENTUM,
+                                   0.8, L['scale'], L['shift'], L['mean'], L['invstd'])
+                ops.bn_apply(L['A'], L['scale'], L['shift'], rows, Np, geo.Hp, geo.Wp, False, L['Z_hi'], L['Z_lo'])
+            else:
+                ops.split_planes(L['A'], rows, Np, geo.Hp, geo.Wp, L['Z_hi'], L['Z_lo'])
+        last = self.d_layers[-1]
+        ops.pm_linear_fwd(last['Z_hi'], last['Z_lo'], self.p('discriminator.adv_layer.weight'),
+                          self.p('discriminator.adv_layer.bias'), m, last['Np'], last['geo'].H, last['geo'].W,
+                          self.validity)
+
+    def _disc_backward_tc(self, m: int, need_wgrad: bool, use_masks: bool, to_input: bool, input_rows: int):
+        """Backward from self.d_validity[:m].  Per block: BatchNorm-backward coefficients from the two
+        reductions (accumulated by the epilogue of the data-gradient GEMM above it), ONE pass producing
+        the hi/lo gradient of the pre-activation (BN backward + Dropout2d + LeakyReLU'), then the
+        weight-gradient and data-gradient GEMMs.  to_input: accumulate d(loss)/d(x[:input_rows]) into the
+        generator's gradient buffer (GAN G-step)."""
+        H, W = self.H, self.W
+        last = self.d_layers[-1]
+        ops.memset_zero(self._dsums2)
+        ops.memset_zero(self._dbias)
+        if need_wgrad:
+            ops.memset_zero(self._dwg)
+        g = self.d_dz[0]
+        ops.pm_linear_bwd(self.d_validity, last['Z_hi'], last['Z_lo'], self.p('discriminator.adv_layer.weight'),
+                          m, last['Np'], last['geo'].H, last['geo'].W, g,
+                          self.g('discriminator.adv_layer.weight') if need_wgrad else None,
+                          self.g('discriminator.adv_layer.bias') if need_wgrad else None)
+        if last['bn']:
+            rows = m * last['geo'].Hp * last['geo'].Wp
+            ops.bn_bwd_reduce(g, None, None, last['A'], last['mean'], last['invstd'], rows, last['Np'],
+                              last['geo'].Hp, last['geo'].Wp, last['sums2'])
+        cur = 0
+        for li in reversed(range(len(self.d_layers))):
+            L = self.d_layers[li]
+            p, geo, Np, Kp, T = L['name'], L['geo'], L['Np'], L['Kp'], L['T']
+            rows = m * geo.Hp * geo.Wp
+            G_hi, G_lo = self.d_G_hi[:rows * Np], self.d_G_lo[:rows * Np]
+            if L['bn']:
+                ops.pm_bn_bwd_fold(L['sums2'], L['cmap'], Np, L['cout'], float(m * L['Ho'] * L['Wo']),
+                                   self.p(p + '.3.weight'), L['invstd'], L['coef'],
+                                   self.g(p + '.3.weight') if need_wgrad else None,
+                                   self.g(p + '.3.bias') if need_wgrad else None)
+            ops.pm_act_bwd(g, L['A'], L['mean'] if L['bn'] else None, L['invstd'] if L['bn'] else None,
+                           L['coef'] if L['bn'] else None, L['mask'] if use_masks else None, 0.2, rows, Np,
+                           geo.Hp, geo.Wp, G_hi, G_lo, L['dbias_exp'] if need_wgrad else None)
+            a_hi, a_lo, ph, _ = self._disc_input_tc(li, m)
+            shift, phase, bsel = L['taps']
+            if need_wgrad:
+                ops.wgrad_gemm(G_hi, G_lo, a_hi, a_lo, L['dWg'], P=rows, Cout=Np, x_phases=ph, Cin=Kp, shift=shift,
+                               phase=phase, bsel=bsel, oihw_taps=0, workspace=self.d_wgrad_ws)
+                ops.weight_grad_gather(L['dWg'], L['inv'], L['cout'] * L['cin'] * 9, L['R'], self.g(p + '.0.weight'),
+                                       L['dbias_exp'], L['binv'], L['cout'], self.g(p + '.0.bias'))
+            if li == 0 and not to_input:
+                break
+            prev = self.d_layers[li - 1] if li > 0 else None
+            nxt = self.d_dz[1 - cur]
+            fuse = prev is not None and prev['bn']
+            if L['phases'] == 1:
+                bw = (prev['A'], None, None, prev['mean'], prev['invstd']) if fuse else None
+                ops.tap_gemm(G_hi, G_lo, L['Wt_hi'], L['Wt_lo'], nxt, a_phases=1, a_rows=rows, K=Np, b_slices=T,
+                             N=Kp, M=rows, ldD=Kp, Hp=geo.Hp, Wp=geo.Wp, shift=[-s for s in shift],
+                             phase=phase, bsel=bsel, stats=(prev['sums2'] if fuse else None), bw=bw)
+            else:
+                dxp = self.d_dxp[:4 * rows * Kp].view(4, rows, Kp)
+                for q in range(4):
+                    sh = [-shift[t] for t in range(T) if phase[t] == q]
+                    bs = [bsel[t] for t in range(T) if phase[t] == q]
+                    ops.tap_gemm(G_hi, G_lo, L['Wt_hi'], L['Wt_lo'], dxp[q], a_phases=1, a_rows=rows, K=Np,
+                                 b_slices=T, N=Kp, M=rows, ldD=Kp, Hp=geo.Hp, Wp=geo.Wp, shift=sh,
+                                 phase=[0] * len(sh), bsel=bs)
+                pg = prev['geo']
+                ops.phase_unsplit(dxp, m, pg.H, pg.W, Kp, nxt)
+                if fuse:
+                    ops.bn_bwd_reduce(nxt, None, None, prev['A'], prev['mean'], prev['invstd'],
+                                      m * pg.Hp * pg.Wp, Kp, pg.Hp, pg.Wp, prev['sums2'])
+            g, cur = nxt, 1 - cur
+        if to_input:
+            ops.s2d4_to_planar(g, H, W, input_rows, self.dD.view(-1), self.dD.shape[1] * H * W, accumulate=True)
+
     # ------------------------------------------------------------------ public passes
     def forward(self, input_mv: torch.Tensor, input_residual: torch.Tensor,
                 input_flow: Optional[torch.Tensor] = None, *, train: bool = True,
@@ -894,14 +1094,23 @@ class DmcEngine:
         self._use_masks = bool(train and use_dropout)
         if self._use_masks and not (isinstance(masks, str) and masks == 'preloaded'):
             self.set_masks(masks if masks is not None else self.draw_dropout_masks(m), m)
-        self._disc_forward(self.d_in, m, train, self._use_masks)
+        if self.disc_engine == 'tc':
+            self._disc_forward_tc(self.d_in, m, train, self._use_masks)
+        else:
+            self._disc_forward(self.d_in, m, train, self._use_masks)
         self._m = m
         return self.logits[:n], self.validity[:m], self.gen_flow[:n]
 
     def set_masks(self, masks: Sequence[torch.Tensor], m: int):
         """Stage Dropout2d masks ([m, C] per block) into the static device buffers."""
         for L, mk in zip(self.d_layers, masks):
-            L['mask'][:m].copy_(mk.reshape(m, -1).to(torch.float32), non_blocking=True)
+            mk = mk.reshape(m, -1).to(torch.float32)
+            if self.disc_engine == 'tc':
+                # one value per (frame, true channel) -> one per GEMM column (space-to-depth columns
+                # repeat the channel's value, padding columns are irrelevant: their activation is 0)
+                L['mask'][:m].copy_(mk.to(self.device, non_blocking=True)[:, L['mask_idx']], non_blocking=True)
+            else:
+                L['mask'][:m].copy_(mk, non_blocking=True)
 
     def draw_dropout_masks(self, m: int, generator: Optional[torch.Generator] = None):
         """Dropout2d(0.25) feature masks drawn with the same ATen calls, shapes and
@@ -924,7 +1133,9 @@ class DmcEngine:
         produced (dead-work elimination)."""
         if cls:
             self._cls_backward(self.gen_flow, n, cls_wgrad, cls_to_gen, self.d_gen_flow)
-        if disc:
+        if disc and self.disc_engine == 'tc':
+            self._disc_backward_tc(self._m, disc_wgrad, self._use_masks, disc_to_gen, n)
+        elif disc:
             self._disc_backward(self.d_in, self._m, disc_wgrad, self._use_masks,
                                 self.d_gen_flow if disc_to_gen else None, n)
         if gen_grad:

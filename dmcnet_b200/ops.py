@@ -394,3 +394,68 @@ def adam_step(p, g, m, v, chunks, nchunks, hyper, step, beta1, beta2, eps, grad_
     _call('dmc_adam_step', _ptr(p, F32), _ptr(g, F32), _ptr(m, F32), _ptr(v, F32),
           _ptr(chunks, torch.int32), c_int(nchunks), _ptr(hyper, F32), _ptr(step, torch.int32),
           c_float(beta1), c_float(beta2), c_float(eps), c_float(grad_scale), _stream())
+
+
+# ---------------------------------------------------------------- discriminator on the tensor-core path
+I32 = torch.int32
+
+
+def tap_gemm_act(A_hi, A_lo, B_hi, B_lo, D, *, a_phases, a_rows, K, b_slices, N, M, ldD, Hp, Wp,
+                 shift, phase, bsel, bias, mask=None, slope=0.2, stats=None):
+    """tap_gemm whose epilogue applies D = mask[frame][n] * LeakyReLU(D + bias[n]) (csrc/gemm_tc.cu ActFuse)."""
+    _call('dmc_tc_tap_gemm_act', _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(a_phases), c_long(a_rows), c_int(K),
+          _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M),
+          c_int(ldD), c_int(Hp), c_int(Wp), c_int(len(shift)), _iarr(shift), _iarr(phase), _iarr(bsel),
+          _ptr(stats, F64), _ptr(bias, F32), _ptr(mask, F32), c_float(slope), _stream())
+
+
+def weight_gather_prep(w, gmap, T, N, K, W_hi, W_lo, Wt_hi=None, Wt_lo=None, bias=None, bmap=None,
+                       bias_exp=None):
+    _call('dmc_weight_gather_prep', _ptr(w, F32), _ptr(gmap, I32), c_int(T), c_int(N), c_int(K),
+          _ptr(W_hi, BF16), _ptr(W_lo, BF16), _ptr(Wt_hi, BF16), _ptr(Wt_lo, BF16), _ptr(bias, F32),
+          _ptr(bmap, I32), _ptr(bias_exp, F32), _stream())
+
+
+def weight_grad_gather(dWg, inv, n_w, R, dW, dbias_exp=None, binv=None, C=0, dbias=None):
+    _call('dmc_weight_grad_gather', _ptr(dWg, F32), _ptr(inv, I32), c_int(n_w), c_int(R), _ptr(dW, F32),
+          _ptr(dbias_exp, F64), _ptr(binv, I32), c_int(C), _ptr(dbias, F32), _stream())
+
+
+def pm_bn_finalize(sums, cmap, Cp, C, count, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift,
+                   mean=None, invstd=None):
+    _call('dmc_pm_bn_finalize', _ptr(sums, F64), _ptr(cmap, I32), c_int(Cp), c_int(C), c_double(count),
+          _ptr(gamma, F32), _ptr(beta, F32), _ptr(rmean, F32), _ptr(rvar, F32), _ptr(nbt, I64),
+          c_float(momentum), c_float(eps), _ptr(scale, F32), _ptr(shift, F32), _ptr(mean, F32),
+          _ptr(invstd, F32), _stream())
+
+
+def pm_bn_bwd_fold(sums2, cmap, Cp, C, count, gamma, invstd, coef, dgamma=None, dbeta=None):
+    _call('dmc_pm_bn_bwd_fold', _ptr(sums2, F64), _ptr(cmap, I32), c_int(Cp), c_int(C), c_double(count),
+          _ptr(gamma, F32), _ptr(invstd, F32), _ptr(coef, F32), _ptr(dgamma, F32), _ptr(dbeta, F32),
+          _stream())
+
+
+def pm_act_bwd(dZ, A, mean, invstd, coef, mask, slope, P, C, Hp, Wp, G_hi, G_lo, dbias_exp=None):
+    _call('dmc_pm_act_bwd', _ptr(dZ, F32), _ptr(A, F32), _ptr(mean, F32), _ptr(invstd, F32),
+          _ptr(coef, F32), _ptr(mask, F32), c_float(slope), c_long(P), c_int(C), c_int(Hp), c_int(Wp),
+          _ptr(G_hi, BF16), _ptr(G_lo, BF16), _ptr(dbias_exp, F64), _stream())
+
+
+def planar_to_s2d4(x, x_ns, H, W, M, out_hi, out_lo):
+    _call('dmc_planar_to_s2d4', _ptr(x, F32), c_long(x_ns), c_int(H), c_int(W), c_int(M), _ptr(out_hi, BF16),
+          _ptr(out_lo, BF16), _stream())
+
+
+def s2d4_to_planar(dS, H, W, M, dX, dx_ns, accumulate=False):
+    _call('dmc_s2d4_to_planar', _ptr(dS, F32), c_int(H), c_int(W), c_int(M), _ptr(dX, F32), c_long(dx_ns),
+          c_int(1 if accumulate else 0), _stream())
+
+
+def pm_linear_fwd(Z_hi, Z_lo, Wl, b, M, C, H, W, out):
+    _call('dmc_pm_linear_fwd', _ptr(Z_hi, BF16), _ptr(Z_lo, BF16), _ptr(Wl, F32), _ptr(b, F32), c_int(M),
+          c_int(C), c_int(H), c_int(W), _ptr(out, F32), _stream())
+
+
+def pm_linear_bwd(dv, Z_hi, Z_lo, Wl, M, C, H, W, dZ, dWl=None, db=None):
+    _call('dmc_pm_linear_bwd', _ptr(dv, F32), _ptr(Z_hi, BF16), _ptr(Z_lo, BF16), _ptr(Wl, F32), c_int(M),
+          c_int(C), c_int(H), c_int(W), _ptr(dZ, F32), _ptr(dWl, F32), _ptr(db, F32), _stream())

@@ -7,7 +7,8 @@ TEST / BASELINE INFRASTRUCTURE ONLY.  The reference is pure Python for this path
     code/dmcnet/model.py      code/dmcnet/transforms.py
     code/dmcnet_GAN/model.py  code/dmcnet_GAN/transforms.py
 
-into sourceless ``oracle/_ref/code/<variant>/<module>.pyc`` (same relative layout, so
+into sourceless bytecode ``oracle/_ref/code/<variant>/<module>.bc`` (a .pyc under another suffix:
+snapshots drop ``*.pyc``; same relative layout, so
 ``oracle/ref_loader.py`` loads either root; the GPU box runs the same image, hence the same CPython
 bytecode version).  No reference source text is copied anywhere; ``oracle/_ref/`` is git-ignored but not
 gpurun-ignored, like the product's own built ``.so``.  ``__graft_entry__.build()`` runs this when ``/root/reference`` is present.  It is what
@@ -35,7 +36,7 @@ def make(verbose: bool = False) -> bool:
     for parts in FILES:
         src, dst = os.path.join(SRC_ROOT, *parts), os.path.join(DST_ROOT, *parts)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        dst = dst[:-3] + '.pyc'
+        dst = dst[:-3] + '.bc'
         py_compile.compile(src, cfile=dst, doraise=True, optimize=0)
         with open(dst, 'rb') as f:
             manifest['/'.join(parts)] = hashlib.sha256(f.read()).hexdigest()

@@ -34,7 +34,7 @@ REFERENCE_ROOT = _pick_root()
 
 def reference_available() -> bool:
     d = os.path.join(REFERENCE_ROOT, 'code', 'dmcnet')
-    return os.path.isfile(os.path.join(d, 'model.py')) or os.path.isfile(os.path.join(d, 'model.pyc'))
+    return os.path.isfile(os.path.join(d, 'model.py')) or os.path.isfile(os.path.join(d, 'model.bc'))
 
 
 def load_reference_model_module(variant: str):
@@ -51,9 +51,19 @@ def load_reference_model_module(variant: str):
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')          # SyntaxWarning: `is 'ContextNetwork'`
             path = os.path.join(d, 'model.py')
-            if not os.path.isfile(path):                   # staged, sourceless (oracle/make_ref.py)
-                path = os.path.join(d, 'model.pyc')
-            spec = importlib.util.spec_from_file_location(name, path)
+            if os.path.isfile(path):
+                spec = importlib.util.spec_from_file_location(name, path)
+            else:
+                # staged, sourceless bytecode (oracle/make_ref.py): model.bc imports `transforms`,
+                # which is loaded the same way first
+                from importlib.machinery import SourcelessFileLoader
+                tf_loader = SourcelessFileLoader('transforms', os.path.join(d, 'transforms.bc'))
+                tf_spec = importlib.util.spec_from_loader('transforms', tf_loader)
+                tf = importlib.util.module_from_spec(tf_spec)
+                tf_loader.exec_module(tf)
+                sys.modules['transforms'] = tf
+                loader = SourcelessFileLoader(name, os.path.join(d, 'model.bc'))
+                spec = importlib.util.spec_from_loader(name, loader)
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
     finally:

@@ -1,0 +1,123 @@
+"""GPU: the discriminators on the tensor-core plan (dmcnet_b200/disc_plan.py, csrc/disc_pm.cu, the
+ActFuse / BwFuse epilogues of csrc/gemm_tc.cu) against autograd of the oracle's discriminator
+evaluated in float64 on identical inputs: validity, every parameter gradient, the gradient w.r.t. the
+input maps (what the generator receives in a G-step) and the BatchNorm running statistics.
+Bars: 5e-5 relative for the forward (bf16x3 GEMMs).  Gradients: the BatchNorm(eps 0.8) backward of
+block_3 cancels ~500:1 (dA = dZ - mean(dZ) - ...), so the 2^-17 operand rounding of the bf16 hi/lo
+split, ~1e-5 after each data-gradient GEMM, reaches 4e-3 .. 5e-3 in every block upstream of it while
+the blocks downstream stay at 1e-5 -- tests/test_grad_sensitivity.py reproduces exactly these
+figures on the CPU by rounding the ORACLE's own conv operands (4.7e-3 / 1e-5), and the fp32 oracle
+itself is 1e-3 .. 2.7e-3 away from its float64 evaluation at 384 frames.  Bar: 1e-2 per tensor
+(measured <= 5e-3), 1e-4 for the blocks after block_3 and for the planar fp32 plan."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dmc_oracle as O          # noqa: E402  (checker only)
+
+if torch.cuda.is_available():
+    from dmcnet_b200 import ops
+    from dmcnet_b200.engine import DmcEngine
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel2(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _oracle64(sd, arch_d, x, masks, dval, train):
+    st = {}
+    for k, v in sd.items():
+        if k.startswith('discriminator'):
+            t = v.double() if v.is_floating_point() else v.clone()
+            st[k] = t.requires_grad_(True) if (v.is_floating_point() and not O.is_buffer(k)) else t
+    xd = x.double().requires_grad_(True)
+    val = O.disc_forward(st, xd, arch_d, train, [m.double() for m in masks] if masks is not None else None)
+    if dval is not None:
+        val.backward(dval.double())
+    return val.detach(), st, xd.grad
+
+
+@pytest.mark.parametrize('arch_d,m', [('Discriminator3', 4), ('Discriminator', 3), ('Discriminator2', 2),
+                                      ('Discriminator5', 2)])
+@pytest.mark.parametrize('use_masks', [True, False])
+def test_tensor_core_discriminator_forward_backward_vs_fp64_oracle(arch_d, m, use_masks):
+    sd = O.build_state(51, arch_d, seed=1)
+    g = torch.Generator().manual_seed(3)
+    # make the BatchNorm parameters non-trivial
+    for k in sd:
+        if k.startswith('discriminator') and k.endswith('.3.weight'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+        if k.startswith('discriminator') and k.endswith('.3.bias'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.3
+    x = torch.randn(m, 2, 224, 224, generator=g)
+    dval = torch.randn(m, 2, generator=g)
+    torch.manual_seed(7)
+    masks = O.draw_dropout_masks(arch_d, m) if use_masks else None
+    val_ref, st, gx_ref = _oracle64(sd, arch_d, x, masks, dval, True)
+
+    eng = DmcEngine(51, 1, m, gan=True, arch_d=arch_d)          # frames = m, buffers for 2m
+    assert eng.disc_engine == 'tc'
+    eng.load_state(sd)
+    if use_masks:
+        eng.set_masks(masks, m)
+    xd = x.cuda()
+    eng._disc_forward_tc(xd, m, True, use_masks)
+    assert rel(eng.validity[:m], val_ref) < 5e-5
+    eng.d_validity[:m].copy_(dval.cuda())
+    eng.zero_grads()
+    ops.memset_zero(eng.dD)
+    eng._disc_backward_tc(m, True, use_masks, True, m)
+    torch.cuda.synchronize()
+    late = ('block_3_', 'block_4', 'adv_layer')               # downstream of block_3's BatchNorm
+    for k in eng.specs:
+        if k.startswith('discriminator'):
+            e = rel2(eng.grad_view(k), st[k].grad)
+            assert e < (1e-4 if any(t in k for t in late) else 1e-2), (k, e)
+    assert rel2(eng.dD[:, 0:2], gx_ref) < 1e-2
+    # running statistics (momentum 0.1, unbiased variance) and the batch counter
+    for k, v in st.items():
+        if k.endswith(('running_mean', 'running_var')):
+            assert rel(eng.buffers[k], v) < 1e-5, k
+        if k.endswith('num_batches_tracked'):
+            assert int(eng.buffers[k]) == int(v) == 1
+    # weight gradients are deterministic (split-K workspace + fixed-order gather)
+    first = eng.grads.clone()
+    eng.zero_grads()
+    eng._disc_backward_tc(m, True, use_masks, False, m)
+    lo, hi = eng.group_range['discriminator']
+    assert torch.equal(first[lo:hi], eng.grads[lo:hi])
+
+
+def test_tensor_core_discriminator_eval_mode_and_planar_twin_agree():
+    """Eval mode (running statistics, no dropout) on both execution plans."""
+    arch_d, m = 'Discriminator3', 2
+    sd = O.build_state(51, arch_d, seed=1)
+    g = torch.Generator().manual_seed(4)
+    for k in sd:
+        if k.endswith('running_mean') and k.startswith('discriminator'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        if k.endswith('running_var') and k.startswith('discriminator'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    x = torch.randn(m, 2, 224, 224, generator=g)
+    val_ref, _, _ = _oracle64(sd, arch_d, x, None, None, False)
+    for plan in ('tc', 'planar'):
+        eng = DmcEngine(51, 1, m, gan=True, arch_d=arch_d, disc_engine=plan)
+        eng.load_state(sd)
+        if plan == 'tc':
+            eng._disc_forward_tc(x.cuda(), m, False, False)
+        else:
+            eng._disc_forward(x.cuda(), m, False, False)
+        assert rel(eng.validity[:m], val_ref) < 5e-5, plan
+
+
+def test_discriminator4_stays_on_the_planar_plan():
+    eng = DmcEngine(51, 1, 1, gan=True, arch_d='Discriminator4')
+    assert eng.disc_engine == 'planar'

@@ -44,12 +44,12 @@ def rel2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _run(num_class, arch_d, batch, steps=2, gemm='tc'):
+def _run(num_class, arch_d, batch, steps=2, gemm='tc', disc_engine=None):
     gan = arch_d is not None
     sd = O.build_state(num_class, arch_d, seed=1)
     flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
     ref = O.OracleTrainer(sd, O.HParams(), gan=gan, arch_d=arch_d)
-    eng = DmcEngine(num_class, 3, batch * 3, gan=gan, arch_d=arch_d, gemm_engine=gemm)
+    eng = DmcEngine(num_class, 3, batch * 3, gan=gan, arch_d=arch_d, gemm_engine=gemm, disc_engine=disc_engine)
     eng.load_state(sd)
     tr = FusedTrainStep(eng, HParams(), batch)
     assert list(eng.state_keys()) == list(sd.keys())
@@ -77,7 +77,7 @@ def _check_forward(ref, eng, tr, mo, mg, gan):
         assert rel(eng.validity[:m], ref.last_validity) < 1e-3
 
 
-def _check_grads(ref, eng, groups, tight_groups=()):
+def _check_grads(ref, eng, groups, tight_groups=(), tight_tol=1e-4):
     og = ref.grads()
     l2 = []
     for k in eng.specs:
@@ -87,7 +87,7 @@ def _check_grads(ref, eng, groups, tight_groups=()):
             continue
         e = rel2(eng.grad_view(k), og[k])
         if any(k.startswith(g) for g in tight_groups):
-            assert e < 1e-4, (k, e)
+            assert e < tight_tol, (k, e)
         else:
             assert e < 1.2e-1, (k, e)
             l2.append(e)
@@ -115,12 +115,20 @@ def test_dmcnet_cuda_core_gemm_engine_agrees():
         _check_forward(ref, eng, tr, mo, mg, False)
 
 
-@pytest.mark.parametrize('num_class,arch_d,batch', [(101, 'Discriminator3', 2), (51, 'Discriminator', 1)])
-def test_gan_d_step_then_g_step_vs_oracle(num_class, arch_d, batch):
-    for it, ref, eng, tr, mo, mg in _run(num_class, arch_d, batch):
+@pytest.mark.parametrize('num_class,arch_d,batch,plan', [(101, 'Discriminator3', 2, 'tc'), (51, 'Discriminator', 1, 'tc'),
+                                                         (101, 'Discriminator3', 1, 'planar'),
+                                                         (51, 'Discriminator2', 1, 'tc'), (51, 'Discriminator5', 1, 'tc'),
+                                                         (51, 'Discriminator4', 1, 'planar')])
+def test_gan_d_step_then_g_step_vs_oracle(num_class, arch_d, batch, plan):
+    """Every discriminator of code/dmcnet_GAN/model.py:282-438, on the plan that runs it."""
+    for it, ref, eng, tr, mo, mg in _run(num_class, arch_d, batch, disc_engine=plan):
+        assert eng.disc_engine == plan
         _check_forward(ref, eng, tr, mo, mg, True)
         if it == 0:      # D-step: classifier + discriminator step; D grads do not depend on ResNet
-            _check_grads(ref, eng, ['base_model', 'discriminator'], tight_groups=['discriminator'])
+            # planar plan: fp32 kernels, 1e-4; tensor-core plan: 1e-2 (the 2^-17 operand rounding is
+            # amplified by block_3's BatchNorm backward, see tests/test_gpu_disc_tc.py)
+            _check_grads(ref, eng, ['base_model', 'discriminator'], tight_groups=['discriminator'],
+                         tight_tol=(1e-4 if plan == 'planar' else 1e-2))
         else:            # G-step: generator gradient arrives through ResNet-18 and D
             _check_grads(ref, eng, ['gen_flow_model'])
 

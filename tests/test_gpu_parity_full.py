@@ -96,7 +96,7 @@ def _disc_grads_fp64(ref, eng, arch_d, masks, n):
         if k.startswith('discriminator'):
             t = v.double() if v.is_floating_point() else v.clone()
             st[k] = t.requires_grad_(True) if (v.is_floating_point() and not O.is_buffer(k)) else t
-    x = eng.d_in.detach().double().cpu()
+    x = eng.d_in.detach().double().cpu()                 # [fake (generated) | real] as the product staged it
     validity = O.disc_forward(st, x, arch_d, True, [m.double() for m in masks])
     tgt = torch.cat((torch.zeros(n, dtype=torch.int64), torch.ones(n, dtype=torch.int64)))
     (F.cross_entropy(validity, tgt) * O.HParams().lr_adv_d).backward()
@@ -141,14 +141,14 @@ def test_config3_b64_gan_d_and_g_step_vs_oracle():
         errs = _forward_checks(ref, eng, tr, mo, mg, True)
         if it == 0:       # D-step: discriminator gradients do not depend on the ResNet backward
             d = _grad_errors(ref, eng, 'discriminator')
-            # At 384 frames the fp32 ORACLE is the noisy side: torch's CPU BatchNorm backward sums
-            # 1.2 M fp32 terms per channel at block_2 and everything upstream of it inherits ~1e-3
-            # (the same oracle evaluated in fp64 differs from its fp32 self by 1e-3 there, 1e-6 after it).
-            # So: 5e-3 against the fp32 oracle, 1e-4 against the fp64 evaluation of the same functions.
-            assert max(d.values()) < 5e-3, d
+            # 1e-2 against both evaluations of the oracle: at 384 frames the fp32 oracle is itself 1e-3 ..
+            # 2.7e-3 away from its float64 evaluation upstream of block_2 (torch's CPU BatchNorm backward
+            # sums 1.2 M fp32 terms per channel), and the tensor-core plan carries 4e-3 .. 5e-3 there
+            # (2^-17 operand rounding amplified by block_3's BatchNorm backward; tests/test_gpu_disc_tc.py)
+            assert max(d.values()) < 1e-2, d
             d64 = _disc_grads_fp64(ref, eng, arch_d, masks, B * 3)
             e64 = {k: rel2(eng.grad_view(k), d64[k]) for k in d64}
-            assert max(e64.values()) < 1e-4, e64
+            assert max(e64.values()) < 1e-2, e64
             rec['D'] = {'forward': errs, 'disc_grad_worst_vs_fp32_oracle': max(d.values()),
                         'disc_grad_worst_vs_fp64_oracle': max(e64.values()), 'metrics': mg}
         else:             # G-step: generator gradient = MSE + adversarial (through D) + CE (through ResNet-18)
@@ -196,14 +196,25 @@ def test_twenty_step_trajectory_vs_oracle():
             assert mg[k] == pytest.approx(mo[k], rel=2e-3, abs=1e-6), (it, k)
         assert mg['prec1'] == mo['prec1'] and mg['prec5'] == mo['prec5'], it
     osd, gsd = ref.state_dict(), eng.state_dict()
-    worst = {}
+    init = O.build_state(51, None, seed=1)
+    hp = HParams()
+    worst_w, worst_travel = {}, {}
     for k in osd:
         if k.endswith('num_batches_tracked'):
             assert int(gsd[k]) == steps == int(osd[k])
             continue
-        # parameters move by lr * O(1) per Adam step: compare the DISPLACEMENT from the initial state
-        worst[k] = rel(gsd[k].float(), osd[k].float())
-    bad = max(worst, key=worst.get)
-    _record('trajectory_20_steps', {'history': hist, 'worst_state_rel': worst[bad], 'worst_key': bad})
-    assert worst[bad] < 1e-2, (bad, worst[bad])
+        a, b = gsd[k].double().cpu(), osd[k].double().cpu()
+        worst_w[k] = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        if not O.is_buffer(k):
+            # Adam(eps 1e-3) moves an element by at most ~lr per step whatever the gradient size, so
+            # elements whose gradient is near zero follow the gradient NOISE: measure the distance
+            # between the two trajectories in units of the distance travelled, lr * steps
+            lr = hp.lr * (hp.lr_cls_mult if k.startswith('base_model') else hp.lr_mse_mult)
+            worst_travel[k] = float((a - b).abs().max() / (lr * steps))
+    nz = {k: v for k, v in worst_w.items() if float(init[k].double().abs().max()) > 0}      # not zero-initialised
+    bad, far = max(nz, key=nz.get), max(worst_travel, key=worst_travel.get)
+    _record('trajectory_20_steps', {'history': hist, 'worst_state_rel': nz[bad], 'worst_key': bad,
+                                    'worst_fraction_of_travel': worst_travel[far], 'worst_travel_key': far})
+    assert nz[bad] < 1e-2, (bad, nz[bad])                       # weights, BN weights, running statistics
+    assert worst_travel[far] < 0.5, (far, worst_travel[far])   # measured 0.18 (a zero-initialised BN bias)
     assert hist[-1]['loss'][1] < hist[0]['loss'][1]
