@@ -493,3 +493,103 @@ extern "C" int dmc_pm_linear_bwd(const float* dv, const void* Z_hi, const void* 
   }
   return DMC_OK;
 }
+
+// ------------------------------------------------------------------ stem data gradient on the tensor cores
+// d(loss)/d(gen_flow) through the classifier's 7x7/2 stem conv (GAN G-step; code/dmcnet_GAN/model.py:560:
+// the classifier input is NOT detached).  With Y = 2u + a, X = 2v + b the gradient of input pixel
+// (Y, X) reads dZ at (u + di, v + dj), di, dj in {-1, 0, 1, 2}, through kernel row r = a + 3 - 2 di:
+// a 16-tap GEMM over the 112x112 grid with K = 64 output channels and N = (a, b, c) = 8 columns
+// (padded to 32), operands from dmc_weight_gather_prep.  The two kernels below move the data:
+// planar dZ -> pixel-major hi/lo with a ring of TWO zero rows / columns (offset +2 must not reach
+// the next frame), and the GEMM result -> planar input gradient.
+namespace dmc {
+
+// in  [N][C][H][W] fp32 (frame stride in_ns)  ->  out hi/lo [N][H+2][W+2][C], pixel (h, w) at (h+2, w+2),
+// rows 0-1 and columns 0-1 zero.  Block = one output row of one frame; 32-pixel x C tiles through smem.
+__global__ void __launch_bounds__(256)
+planar_to_pm_ring2_kernel(const float* __restrict__ in, long in_ns, int C, int H, int W,
+                          bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+  extern __shared__ float tile[];                       // [C][33]
+  const int hp = blockIdx.x, n = blockIdx.y;
+  const int Wp = W + 2;
+  const long row_base = (((long)n * (H + 2) + hp) * Wp) * C;
+  if (hp < 2) {                                         // ring rows
+    for (long i = threadIdx.x; i < (long)Wp * C / 8; i += blockDim.x) {
+      reinterpret_cast<uint4*>(out_hi + row_base)[i] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(out_lo + row_base)[i] = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+  const int h = hp - 2;
+  for (int i = threadIdx.x; i < 2 * C / 8; i += blockDim.x) {        // ring columns 0, 1
+    reinterpret_cast<uint4*>(out_hi + row_base)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(out_lo + row_base)[i] = make_uint4(0, 0, 0, 0);
+  }
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+      const int c = i >> 5, dw = i & 31;
+      tile[c * 33 + dw] = (w0 + dw < W) ? in[(long)n * in_ns + ((long)c * H + h) * W + w0 + dw] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * C / 4; i += blockDim.x) {
+      const int c = (i % (C / 4)) * 4, dw = i / (C / 4);
+      if (w0 + dw < W) {
+        bf16 hh[4], ll[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16(tile[(c + k) * 33 + dw], hh[k], ll[k]);
+        const long o = row_base + (long)(w0 + dw + 2) * C + c;
+        *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(ll);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dX[n][c][2u+a][2v+b] (+)= D[n][u+2][v+2][(a*2+b)*2 + c]   (D fp32 with ldD columns, ring 2)
+__global__ void __launch_bounds__(256)
+s2d2_ring2_to_planar_kernel(const float* __restrict__ D, int ldD, int H, int W, int N, float* __restrict__ dX,
+                            long dx_ns, int accumulate) {
+  const int Hg = H / 2, Wg = W / 2, Wp = Wg + 2;
+  const long total = (long)N * 2 * H * Wg;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % Wg);
+    long r = i / Wg;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r & 1);
+    const int n = (int)(r >> 1);
+    const float* s = D + (((long)n * (Hg + 2) + (y >> 1) + 2) * Wp + v + 2) * ldD + (y & 1) * 4 + c;
+    float2 o = make_float2(s[0], s[2]);                 // b = 0, 1
+    float* d = dX + (long)n * dx_ns + ((long)c * H + y) * W + 2 * v;
+    if (accumulate) {
+      const float2 p = *reinterpret_cast<const float2*>(d);
+      o.x += p.x; o.y += p.y;
+    }
+    *reinterpret_cast<float2*>(d) = o;
+  }
+}
+
+}  // namespace dmc
+
+// planar fp32 [N][C][H][W] (frame stride in_ns) -> pixel-major bf16 hi/lo [N][H+2][W+2][C] with a
+// two-pixel zero ring on the low sides (the A operand of the stem data-gradient GEMM).
+extern "C" int dmc_planar_to_pm_ring2(const float* in, long in_ns, int C, int H, int W, int N, void* out_hi,
+                                      void* out_lo, void* stream) {
+  DMC_REQUIRE(in && out_hi && out_lo && N > 0, "planar_to_pm_ring2: null argument");
+  DMC_REQUIRE(C % 8 == 0 && C <= 256 && H > 0 && W > 0, "planar_to_pm_ring2: C=%d", C);
+  dim3 grid((unsigned)(H + 2), (unsigned)N);
+  planar_to_pm_ring2_kernel<<<grid, 256, C * 33 * sizeof(float), (cudaStream_t)stream>>>(
+      in, in_ns, C, H, W, (bf16*)out_hi, (bf16*)out_lo);
+  return dmc_check_launch("planar_to_pm_ring2_kernel");
+}
+
+// Result of the stem data-gradient GEMM (2x2 space-to-depth columns (a*2+b)*2+c on the H/2 x W/2 grid,
+// ring 2, ldD columns per pixel) -> planar dX [N][2][H][W] (frame stride dx_ns), optionally accumulating.
+extern "C" int dmc_s2d2_ring2_to_planar(const float* D, int ldD, int H, int W, int N, float* dX, long dx_ns,
+                                        int accumulate, void* stream) {
+  DMC_REQUIRE(D && dX && N > 0 && ldD >= 8, "s2d2_ring2_to_planar: bad arguments");
+  DMC_REQUIRE(H % 2 == 0 && W % 2 == 0 && dx_ns % 2 == 0, "s2d2_ring2_to_planar: H=%d W=%d", H, W);
+  s2d2_ring2_to_planar_kernel<<<grid_for((long)N * 2 * H * (W / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+      D, ldD, H, W, N, dX, dx_ns, accumulate);
+  return dmc_check_launch("s2d2_ring2_to_planar_kernel");
+}

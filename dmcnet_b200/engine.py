@@ -354,6 +354,31 @@ class DmcEngine:
         self.stem_wb = torch.zeros(128 * 128, dtype=torch.bfloat16, device=dev)
         self.stem_ws = torch.empty(ops.stem_wgrad_workspace_floats(), **f32) if self.stem_tc else None
         self.stem_dZ = torch.zeros(N, 64, H2, W2, **f32)
+        # data gradient of the stem conv (GAN G-step: the classifier input is not detached) as a 16-tap
+        # tensor-core GEMM over the H/2 x W/2 grid: input pixel (2u+a, 2v+b) reads dZ at (u+di, v+dj),
+        # di, dj in {-1..2}, through kernel row r = a + 3 - 2*di (csrc/disc_pm.cu, "stem data gradient")
+        self.stem_dgrad_tc = self.stem_tc and self.gan
+        if self.stem_dgrad_tc:
+            import numpy as np
+            offs = [(di, dj) for di in (-1, 0, 1, 2) for dj in (-1, 0, 1, 2)]
+            gmap = -np.ones((16, 32, 64), np.int32)
+            co = np.arange(64)
+            for t, (di, dj) in enumerate(offs):
+                for a in range(2):
+                    for b in range(2):
+                        r, q = a + 3 - 2 * di, b + 3 - 2 * dj
+                        if 0 <= r <= 6 and 0 <= q <= 6:
+                            for c in range(2):
+                                gmap[t, (a * 2 + b) * 2 + c, :] = ((co * 2 + c) * 7 + r) * 7 + q
+            wp2 = W2 + 2
+            self.stem_dg = {
+                'gmap': torch.from_numpy(gmap.reshape(-1)).to(dev),
+                'shift': [di * wp2 + dj for di, dj in offs],
+                'hi': torch.zeros(N * (H2 + 2) * wp2, 64, dtype=torch.bfloat16, device=dev),
+                'lo': torch.zeros(N * (H2 + 2) * wp2, 64, dtype=torch.bfloat16, device=dev),
+                'W_hi': torch.zeros(16, 32, 64, dtype=torch.bfloat16, device=dev),
+                'W_lo': torch.zeros(16, 32, 64, dtype=torch.bfloat16, device=dev),
+                'out': torch.zeros(N * (H2 + 2) * wp2, 32, **f32)}
         self.stem = {k: torch.zeros(64, **f32) for k in ('scale', 'shift', 'mean', 'invstd')}
         self.stem['sums'] = torch.zeros(2, 64, dtype=torch.float64, device=dev)
         self.stem['sums2'] = torch.zeros(2, 64, dtype=torch.float64, device=dev)
@@ -764,7 +789,18 @@ class DmcEngine:
             else:
                 ops.conv_wgrad(x_planar, 2 * H * W, 2, H, W, self.stem_dZ, ns, 64, 7, 2,
                                self.g('base_model.conv1.weight'), None, n)
-        if need_input_grad:
+        if need_input_grad and self.stem_dgrad_tc:
+            sd = self.stem_dg
+            rows = n * (H2 + 2) * (W2 + 2)
+            ops.planar_to_pm_ring2(self.stem_dZ.view(-1), ns, 64, H2, W2, n, sd['hi'], sd['lo'])
+            ops.weight_gather_prep(self.p('base_model.conv1.weight'), sd['gmap'], 16, 32, 64, sd['W_hi'],
+                                   sd['W_lo'])
+            ops.tap_gemm(sd['hi'], sd['lo'], sd['W_hi'], sd['W_lo'], sd['out'], a_phases=1, a_rows=rows, K=64,
+                         b_slices=16, N=32, M=rows, ldD=32, Hp=H2 + 2, Wp=W2 + 2, shift=sd['shift'],
+                         phase=[0] * 16, bsel=list(range(16)), engine='tc')
+            ops.s2d2_ring2_to_planar(sd['out'], 32, H, W, n, self.dD.view(-1), self.dD.shape[1] * H * W,
+                                     accumulate=True)
+        elif need_input_grad:
             ops.conv_dgrad(self.stem_dZ, ns, 64, self.p('base_model.conv1.weight'), 2, 2, 7, 2,
                            self.dD.view(-1), self.dD.shape[1] * H * W, H, W, n, accumulate=True)
 

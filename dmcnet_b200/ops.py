@@ -459,3 +459,13 @@ def pm_linear_fwd(Z_hi, Z_lo, Wl, b, M, C, H, W, out):
 def pm_linear_bwd(dv, Z_hi, Z_lo, Wl, M, C, H, W, dZ, dWl=None, db=None):
     _call('dmc_pm_linear_bwd', _ptr(dv, F32), _ptr(Z_hi, BF16), _ptr(Z_lo, BF16), _ptr(Wl, F32), c_int(M),
           c_int(C), c_int(H), c_int(W), _ptr(dZ, F32), _ptr(dWl, F32), _ptr(db, F32), _stream())
+
+
+def planar_to_pm_ring2(x, in_ns, C, H, W, N, out_hi, out_lo):
+    _call('dmc_planar_to_pm_ring2', _ptr(x, F32), c_long(in_ns), c_int(C), c_int(H), c_int(W), c_int(N),
+          _ptr(out_hi, BF16), _ptr(out_lo, BF16), _stream())
+
+
+def s2d2_ring2_to_planar(D, ldD, H, W, N, dX, dx_ns, accumulate=False):
+    _call('dmc_s2d2_ring2_to_planar', _ptr(D, F32), c_int(ldD), c_int(H), c_int(W), c_int(N), _ptr(dX, F32),
+          c_long(dx_ns), c_int(1 if accumulate else 0), _stream())

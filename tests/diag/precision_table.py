@@ -11,7 +11,7 @@ the classifier gradients (median / worst).  Candidates per k-step, cost in bf16-
   bf16x2w  hi*hi + hi*lo           2        weights split, activations bf16 (2^-9)
   bf16x1   hi*hi                   1        both bf16
 
-    python tools/precision_table.py [batch]      -> profiles/r02_precision_table.json
+    python tests/diag/precision_table.py [batch]      -> profiles/r02_precision_table.json
 """
 import json
 import os
@@ -20,7 +20,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import dmc_oracle as O          # noqa: E402  (diagnostic: the oracle is the subject)
 
