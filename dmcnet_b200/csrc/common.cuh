@@ -219,6 +219,16 @@ __host__ __device__ inline bool interior(long q, int Hp, int Wp) {
   return wp >= 1u && wp + DMC_PAD_HI < uw && hp >= 1u && hp + DMC_PAD_HI < uh;
 }
 
+// Same layout with a zero ring of R rows / columns (dilated convolutions: R >= dilation), pixel (h, w)
+// at (h + R, w + R); R = 1 is `interior` above.
+__host__ __device__ inline bool interior_r(long q, int Hp, int Wp, int R) {
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp;
+  const unsigned row = uq / uw;
+  const unsigned wp = uq - row * uw;
+  const unsigned hp = row % uh;
+  return wp >= (unsigned)R && hp >= (unsigned)R;
+}
+
 // i -> (i / d, i % d) for 32-bit i; shift/mask when d is a power of two (channel counts)
 struct FastDiv {
   unsigned d, shift, pow2;

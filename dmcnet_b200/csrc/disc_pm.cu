@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256)
 pm_act_bwd_kernel(const float* __restrict__ dZ, const float* __restrict__ A, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef,
                   const float* __restrict__ mask, float slope, long P, int C, int Hp, int Wp,
-                  bf16* __restrict__ G_hi, bf16* __restrict__ G_lo, double* __restrict__ dbias) {
+                  bf16* __restrict__ G_hi, bf16* __restrict__ G_lo, double* __restrict__ dbias, int ring) {
   const int c4n = C / 4;
   const int rows_per_iter = blockDim.x / c4n;
   const int c = (threadIdx.x % c4n) * 4;
@@ -184,7 +184,7 @@ pm_act_bwd_kernel(const float* __restrict__ dZ, const float* __restrict__ A, con
   for (unsigned q = blockIdx.x * rows_per_iter + r; q < (unsigned)P; q += step) {
     const long off = (long)q * C + c;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (interior(q, Hp, Wp)) {
+    if (interior_r(q, Hp, Wp, ring)) {
       const float4 dz = *reinterpret_cast<const float4*>(dZ + off);
       const float4 a = *reinterpret_cast<const float4*>(A + off);
       float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -437,7 +437,23 @@ extern "C" int dmc_pm_act_bwd(const float* dZ, const float* A, const float* mean
   const int rows_per_iter = 256 / (C / 4);
   pm_act_bwd_kernel<<<grid_for(cdiv(P, rows_per_iter), 1, 148L * 8), 256, 256 * 4 * sizeof(double),
                       (cudaStream_t)stream>>>(dZ, A, mean, invstd, coef, mask, slope, P, C, Hp, Wp,
-                                              (bf16*)G_hi, (bf16*)G_lo, dbias_exp);
+                                              (bf16*)G_hi, (bf16*)G_lo, dbias_exp, 1);
+  return dmc_check_launch("pm_act_bwd_kernel");
+}
+
+// BatchNorm backward alone, from the folded coefficients, on a layout with a `ring`-wide zero ring:
+// G = k1 * (dz - k2 - (Y - mean) * invstd * k3) as bf16 hi/lo (ContextNetwork blocks, where the
+// activation gradient was already applied to dz by the data-gradient GEMM's epilogue).
+extern "C" int dmc_pm_bn_bwd_apply(const float* dz, const float* Y, const float* mean, const float* invstd,
+                                   const float* coef, long P, int C, int Hp, int Wp, int ring, void* G_hi,
+                                   void* G_lo, void* stream) {
+  DMC_REQUIRE(dz && Y && mean && invstd && coef && G_hi && G_lo, "pm_bn_bwd_apply: null argument");
+  DMC_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024 && 256 % (C / 4) == 0, "pm_bn_bwd_apply: C=%d", C);
+  DMC_REQUIRE(P > 0 && P < (1L << 31) && ring >= 1 && ring < Hp && ring < Wp, "pm_bn_bwd_apply: bad geometry");
+  const int rows_per_iter = 256 / (C / 4);
+  pm_act_bwd_kernel<<<grid_for(cdiv(P, rows_per_iter), 1, 148L * 8), 256, 256 * 4 * sizeof(double),
+                      (cudaStream_t)stream>>>(dz, Y, mean, invstd, coef, nullptr, 1.f, P, C, Hp, Wp,
+                                              (bf16*)G_hi, (bf16*)G_lo, nullptr, ring);
   return dmc_check_launch("pm_act_bwd_kernel");
 }
 
@@ -504,45 +520,77 @@ extern "C" int dmc_pm_linear_bwd(const float* dv, const void* Z_hi, const void* 
 // the next frame), and the GEMM result -> planar input gradient.
 namespace dmc {
 
-// in  [N][C][H][W] fp32 (frame stride in_ns)  ->  out hi/lo [N][H+2][W+2][C], pixel (h, w) at (h+2, w+2),
-// rows 0-1 and columns 0-1 zero.  Block = one output row of one frame; 32-pixel x C tiles through smem.
+// in  [N][C][H][W] fp32 (frame stride in_ns)  ->  out [N][H+R][W+R][Cp], pixel (h, w) at (h+R, w+R),
+// rows / columns < R and channels >= C zero.  Output either bf16 hi/lo planes (out_f32 == null) or one
+// fp32 plane; act_hi != null multiplies by the LeakyReLU derivative (act > 0 ? 1 : slope) of a saved
+// activation in the OUTPUT layout (the gradient entering the last ContextNetwork block).
+// Block = one output row of one frame; 32-pixel x C tiles through shared memory.
 __global__ void __launch_bounds__(256)
-planar_to_pm_ring2_kernel(const float* __restrict__ in, long in_ns, int C, int H, int W,
-                          bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+planar_to_pm_ring_kernel(const float* __restrict__ in, long in_ns, int C, int Cp, int H, int W, int R,
+                         bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, float* __restrict__ out_f32,
+                         const bf16* __restrict__ act_hi, float slope) {
   extern __shared__ float tile[];                       // [C][33]
   const int hp = blockIdx.x, n = blockIdx.y;
-  const int Wp = W + 2;
-  const long row_base = (((long)n * (H + 2) + hp) * Wp) * C;
-  if (hp < 2) {                                         // ring rows
-    for (long i = threadIdx.x; i < (long)Wp * C / 8; i += blockDim.x) {
+  const int Wp = W + R;
+  const long row_base = (((long)n * (H + R) + hp) * Wp) * Cp;
+  const int zero_px = hp < R ? Wp : R;                  // whole ring row, or the ring columns of a data row
+  if (out_f32) {
+    for (long i = threadIdx.x; i < (long)zero_px * Cp / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(out_f32 + row_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (long i = threadIdx.x; i < (long)zero_px * Cp / 8; i += blockDim.x) {
       reinterpret_cast<uint4*>(out_hi + row_base)[i] = make_uint4(0, 0, 0, 0);
       reinterpret_cast<uint4*>(out_lo + row_base)[i] = make_uint4(0, 0, 0, 0);
     }
-    return;
   }
-  const int h = hp - 2;
-  for (int i = threadIdx.x; i < 2 * C / 8; i += blockDim.x) {        // ring columns 0, 1
-    reinterpret_cast<uint4*>(out_hi + row_base)[i] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(out_lo + row_base)[i] = make_uint4(0, 0, 0, 0);
-  }
+  if (hp < R) return;
+  const int h = hp - R;
   for (int w0 = 0; w0 < W; w0 += 32) {
     for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
       const int c = i >> 5, dw = i & 31;
       tile[c * 33 + dw] = (w0 + dw < W) ? in[(long)n * in_ns + ((long)c * H + h) * W + w0 + dw] : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * C / 4; i += blockDim.x) {
-      const int c = (i % (C / 4)) * 4, dw = i / (C / 4);
+    for (int i = threadIdx.x; i < 32 * Cp / 4; i += blockDim.x) {
+      const int c = (i % (Cp / 4)) * 4, dw = i / (Cp / 4);
       if (w0 + dw < W) {
-        bf16 hh[4], ll[4];
+        const long o = row_base + (long)(w0 + dw + R) * Cp + c;
+        float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) split_bf16(tile[(c + k) * 33 + dw], hh[k], ll[k]);
-        const long o = row_base + (long)(w0 + dw + 2) * C + c;
-        *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hh);
-        *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(ll);
+        for (int k = 0; k < 4; ++k) v[k] = (c + k < C) ? tile[(c + k) * 33 + dw] : 0.f;
+        if (act_hi) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (!(__bfloat162float(act_hi[o + k]) > 0.f)) v[k] *= slope;
+        }
+        if (out_f32) {
+          *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          bf16 hh[4], ll[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split_bf16(v[k], hh[k], ll[k]);
+          *reinterpret_cast<uint2*>(out_hi + o) = *reinterpret_cast<uint2*>(hh);
+          *reinterpret_cast<uint2*>(out_lo + o) = *reinterpret_cast<uint2*>(ll);
+        }
       }
     }
     __syncthreads();
+  }
+}
+
+// out[n][c][h][w] = Z[n][h+R][w+R][c] (+ add[n][c][h][w]),  Z = hi + lo with Cp columns, c < C.
+// Block = one row of one frame.
+__global__ void __launch_bounds__(256)
+pm_ring_to_planar_kernel(const bf16* __restrict__ Z_hi, const bf16* __restrict__ Z_lo, int Cp, int C, int H,
+                         int W, int R, const float* __restrict__ add, long add_ns, float* __restrict__ out,
+                         long out_ns) {
+  const int h = blockIdx.x, n = blockIdx.y;
+  const long row = (((long)n * (H + R) + h + R) * (W + R) + R) * Cp;
+  for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+    const int c = i / W, w = i - c * W;
+    float v = join_bf16(Z_hi[row + (long)w * Cp + c], Z_lo[row + (long)w * Cp + c]);
+    if (add) v += add[(long)n * add_ns + ((long)c * H + h) * W + w];
+    out[(long)n * out_ns + ((long)c * H + h) * W + w] = v;
   }
 }
 
@@ -578,9 +626,37 @@ extern "C" int dmc_planar_to_pm_ring2(const float* in, long in_ns, int C, int H,
   DMC_REQUIRE(in && out_hi && out_lo && N > 0, "planar_to_pm_ring2: null argument");
   DMC_REQUIRE(C % 8 == 0 && C <= 256 && H > 0 && W > 0, "planar_to_pm_ring2: C=%d", C);
   dim3 grid((unsigned)(H + 2), (unsigned)N);
-  planar_to_pm_ring2_kernel<<<grid, 256, C * 33 * sizeof(float), (cudaStream_t)stream>>>(
-      in, in_ns, C, H, W, (bf16*)out_hi, (bf16*)out_lo);
-  return dmc_check_launch("planar_to_pm_ring2_kernel");
+  planar_to_pm_ring_kernel<<<grid, 256, C * 33 * sizeof(float), (cudaStream_t)stream>>>(
+      in, in_ns, C, C, H, W, 2, (bf16*)out_hi, (bf16*)out_lo, nullptr, nullptr, 1.f);
+  return dmc_check_launch("planar_to_pm_ring_kernel");
+}
+
+// planar fp32 [N][C][H][W] (frame stride in_ns) -> pixel-major [N][H+R][W+R][Cp] with an R-wide zero
+// ring and channels C..Cp-1 zero: bf16 hi/lo planes, or (out_f32 != NULL) one fp32 plane.
+// act_hi != NULL (same layout as the output): values are multiplied by (act > 0 ? 1 : slope), the
+// LeakyReLU derivative -- the loss gradient entering ContextNetwork's last block.
+extern "C" int dmc_planar_to_pm_ring(const float* in, long in_ns, int C, int Cp, int H, int W, int R, int N,
+                                     void* out_hi, void* out_lo, float* out_f32, const void* act_hi,
+                                     float slope, void* stream) {
+  DMC_REQUIRE(in && N > 0 && ((out_hi && out_lo) || out_f32), "planar_to_pm_ring: null argument");
+  DMC_REQUIRE(C >= 1 && C <= Cp && Cp % 8 == 0 && C <= 256 && R >= 1 && H > 0 && W > 0,
+              "planar_to_pm_ring: C=%d Cp=%d R=%d", C, Cp, R);
+  dim3 grid((unsigned)(H + R), (unsigned)N);
+  planar_to_pm_ring_kernel<<<grid, 256, C * 33 * sizeof(float), (cudaStream_t)stream>>>(
+      in, in_ns, C, Cp, H, W, R, (bf16*)out_hi, (bf16*)out_lo, out_f32, (const bf16*)act_hi, slope);
+  return dmc_check_launch("planar_to_pm_ring_kernel");
+}
+
+// Inverse for activations: out[n][c][h][w] = (hi + lo)[n][h+R][w+R][c] (+ add[n][c][h][w]) for c < C
+// (ContextNetwork output -> planar gen_flow, "+ input_mv" of code/dmcnet/model.py:346 fused).
+extern "C" int dmc_pm_ring_to_planar(const void* Z_hi, const void* Z_lo, int Cp, int C, int H, int W, int R,
+                                     int N, const float* add, long add_ns, float* out, long out_ns,
+                                     void* stream) {
+  DMC_REQUIRE(Z_hi && Z_lo && out && N > 0 && C >= 1 && C <= Cp && R >= 1, "pm_ring_to_planar: bad arguments");
+  dim3 grid((unsigned)H, (unsigned)N);
+  pm_ring_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)Z_hi, (const bf16*)Z_lo, Cp, C,
+                                                                   H, W, R, add, add_ns, out, out_ns);
+  return dmc_check_launch("pm_ring_to_planar_kernel");
 }
 
 // Result of the stem data-gradient GEMM (2x2 space-to-depth columns (a*2+b)*2+c on the H/2 x W/2 grid,

@@ -119,6 +119,7 @@ struct BwFuse {
   const float* gb;       // second gradient source (residual branch) or null
   const float* mean;
   const float* invstd;
+  float slope;           // LeakyReLU slope of the activation (0 = ReLU): dz = D * (act > 0 ? 1 : slope)
 };
 
 // Optional fused activation epilogue of a forward GEMM (discriminator blocks, code/dmcnet_GAN/
@@ -149,7 +150,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
-                   const BwFuse bw, int a_lo_on, const ActFuse act) {
+                   const BwFuse bw, int a_lo_on, const ActFuse act, int ring) {
   using S = TapGemmWsSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -302,7 +303,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       mbar_wait(bar_tfull + 8 * a, aph);
       tc_fence_after();
       const long q = m0 + wq * 32 + lane;
-      const bool keep = q < M && (Hp == 0 || interior(q, Hp, Wp));
+      const bool keep = q < M && (Hp == 0 || interior_r(q, Hp, Wp, ring));
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * 32;
@@ -406,10 +407,10 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                   v.x += gv[ii].x; v.y += gv[ii].y; v.z += gv[ii].z; v.w += gv[ii].w;
                   const uint2 hraw = hv[ii];
                   // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  v.x = ((hraw.x & 0x8000u) == 0 && (hraw.x & 0x7fffu) != 0) ? v.x : 0.f;
-                  v.y = ((hraw.x & 0x80000000u) == 0 && (hraw.x & 0x7fff0000u) != 0) ? v.y : 0.f;
-                  v.z = ((hraw.y & 0x8000u) == 0 && (hraw.y & 0x7fffu) != 0) ? v.z : 0.f;
-                  v.w = ((hraw.y & 0x80000000u) == 0 && (hraw.y & 0x7fff0000u) != 0) ? v.w : 0.f;
+                  v.x = ((hraw.x & 0x8000u) == 0 && (hraw.x & 0x7fffu) != 0) ? v.x : v.x * bw.slope;
+                  v.y = ((hraw.x & 0x80000000u) == 0 && (hraw.x & 0x7fff0000u) != 0) ? v.y : v.y * bw.slope;
+                  v.z = ((hraw.y & 0x8000u) == 0 && (hraw.y & 0x7fffu) != 0) ? v.z : v.z * bw.slope;
+                  v.w = ((hraw.y & 0x80000000u) == 0 && (hraw.y & 0x7fff0000u) != 0) ? v.w : v.w * bw.slope;
                   const float4 y = yv[ii];
                   bs1[ci][0] += v.x; bs1[ci][1] += v.y; bs1[ci][2] += v.z; bs1[ci][3] += v.w;
                   bs2[ci][0] = fmaf(v.x, (y.x - mu.x) * is.x, bs2[ci][0]);
@@ -436,7 +437,8 @@ template <int BN, int STAGES>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
-                              const BwFuse& bw, int a_lo_on, const ActFuse& act, cudaStream_t stream) {
+                              const BwFuse& bw, int a_lo_on, const ActFuse& act, int ring,
+                              cudaStream_t stream) {
   using S = TapGemmWsSmem<BN, STAGES>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -450,7 +452,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n, stats, bw, a_lo_on, act);
+                                                  tiles_m, tiles_n, stats, bw, a_lo_on, act, ring);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -934,8 +936,9 @@ using namespace dmc;
 static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
                          const void* B_hi, const void* B_lo, int b_slices, int N, float* D, long M,
                          int ldD, int Hp, int Wp, int ntaps, const int* shift, const int* phase,
-                         const int* bsel, double* stats, const BwFuse& bw, const ActFuse& act,
+                         const int* bsel, double* stats, const BwFuse& bw, const ActFuse& act, int ring,
                          void* stream) {
+  DMC_REQUIRE(ring >= 1 && (Hp == 0 || (ring < Hp && ring < Wp)), "tap_gemm: ring=%d", ring);
   DMC_REQUIRE(bw.Y == nullptr || (stats && bw.mean && bw.invstd && ldD == N),
               "tap_gemm: fused BN backward needs stats, mean, invstd and ldD == N");
   DMC_REQUIRE(act.bias == nullptr || (bw.Y == nullptr && Hp > 0 && Wp > 0 && ldD == N),
@@ -960,10 +963,10 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
   if (BN == 64)
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
 }
 
 // D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
@@ -981,10 +984,30 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
                                const float* bw_invstd, void* stream) {
   BwFuse bw;
   bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
+  bw.slope = 0.f;
   ActFuse act;
   act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
-                       shift, phase, bsel, stats, bw, act, stream);
+                       shift, phase, bsel, stats, bw, act, 1, stream);
+}
+
+// dmc_tc_tap_gemm on a layout whose zero ring is `ring` rows / columns wide (pixel (h, w) at
+// (h + ring, w + ring); dilated convolutions of ContextNetwork, code/dmcnet/model.py:31-71, need
+// ring >= dilation), with a LeakyReLU slope in the fused BatchNorm-backward epilogue:
+// dz = (D + bw_gb) * (bw_act_hi > 0 ? 1 : bw_slope).
+extern "C" int dmc_tc_tap_gemm_ring(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                                    const void* B_hi, const void* B_lo, int b_slices, int N, float* D,
+                                    long M, int ldD, int Hp, int Wp, int ring, int ntaps, const int* shift,
+                                    const int* phase, const int* bsel, double* stats, const float* bw_Y,
+                                    const void* bw_act_hi, const float* bw_gb, const float* bw_mean,
+                                    const float* bw_invstd, float bw_slope, void* stream) {
+  BwFuse bw;
+  bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
+  bw.slope = bw_slope;
+  ActFuse act;
+  act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
+  return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
+                       shift, phase, bsel, stats, bw, act, ring, stream);
 }
 
 // The forward GEMM of a discriminator block (code/dmcnet_GAN/model.py:254-279): same contraction, the
@@ -998,10 +1021,11 @@ extern "C" int dmc_tc_tap_gemm_act(const void* A_hi, const void* A_lo, int a_pha
   DMC_REQUIRE(bias != nullptr, "tap_gemm_act: bias is required");
   BwFuse bw;
   bw.Y = nullptr; bw.act_hi = nullptr; bw.gb = nullptr; bw.mean = nullptr; bw.invstd = nullptr;
+  bw.slope = 0.f;
   ActFuse act;
   act.bias = bias; act.mask = mask; act.slope = slope; act.frame_rows = (unsigned)(Hp * Wp);
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
-                       shift, phase, bsel, stats, bw, act, stream);
+                       shift, phase, bsel, stats, bw, act, 1, stream);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).

@@ -237,7 +237,7 @@ bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
                 const bf16* __restrict__ res_hi, const bf16* __restrict__ res_lo,
                 const float* __restrict__ resY, const float* __restrict__ res_scale,
                 const float* __restrict__ res_shift, bf16* __restrict__ out_hi,
-                bf16* __restrict__ out_lo) {
+                bf16* __restrict__ out_lo, float slope, int ring) {
   const FastDiv fd((unsigned)(C / 4));
   const unsigned n = (unsigned)(P * (C / 4));
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -245,7 +245,7 @@ bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
     const int c = (int)fd.mod(i) * 4;
     const long off = (long)q * C + c;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (interior(q, Hp, Wp)) {
+    if (interior_r(q, Hp, Wp, ring)) {
       const float4 y = *reinterpret_cast<const float4*>(Y + off);
       const float4 sc = *reinterpret_cast<const float4*>(scale + c);
       const float4 sh = *reinterpret_cast<const float4*>(shift + c);
@@ -263,9 +263,9 @@ bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
         o[0] += fmaf(y2.x, s2.x, h2.x); o[1] += fmaf(y2.y, s2.y, h2.y);
         o[2] += fmaf(y2.z, s2.z, h2.z); o[3] += fmaf(y2.w, s2.w, h2.w);
       }
-      if (relu) {
+      if (relu) {                       // slope 0: ReLU; otherwise LeakyReLU(slope)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+        for (int k = 0; k < 4; ++k) o[k] = o[k] > 0.f ? o[k] : o[k] * slope;
       }
     }
     store_split4(out_hi, out_lo, off, o);
@@ -547,7 +547,20 @@ extern "C" int dmc_bn_apply(const float* Y, const float* scale, const float* shi
   DMC_REQUIRE(C % 4 == 0, "bn_apply: C=%d", C);
   bn_apply_kernel<<<grid_for(P * (C / 4), 256), 256, 0, ST(stream)>>>(
       Y, scale, shift, P, C, Hp, Wp, relu, (const bf16*)res_hi, (const bf16*)res_lo, resY, res_scale,
-      res_shift, (bf16*)out_hi, (bf16*)out_lo);
+      res_shift, (bf16*)out_hi, (bf16*)out_lo, 0.f, 1);
+  return dmc_check_launch("bn_apply_kernel");
+}
+
+// out = LeakyReLU_slope(Y*scale + shift) as bf16 hi/lo planes on a layout with a zero ring of `ring`
+// rows / columns (ContextNetwork blocks: dilated conv -> BatchNorm -> LeakyReLU(0.1),
+// code/dmcnet/model.py:31-42).  slope = 1 applies no activation.
+extern "C" int dmc_bn_apply_lrelu(const float* Y, const float* scale, const float* shift, long P, int C,
+                                  int Hp, int Wp, int ring, float slope, void* out_hi, void* out_lo,
+                                  void* stream) {
+  DMC_REQUIRE(C % 4 == 0 && ring >= 1 && ring < Hp && ring < Wp, "bn_apply_lrelu: C=%d ring=%d", C, ring);
+  bn_apply_kernel<<<grid_for(P * (C / 4), 256), 256, 0, ST(stream)>>>(
+      Y, scale, shift, P, C, Hp, Wp, 1, nullptr, nullptr, nullptr, nullptr, nullptr, (bf16*)out_hi,
+      (bf16*)out_lo, slope, ring);
   return dmc_check_launch("bn_apply_kernel");
 }
 
