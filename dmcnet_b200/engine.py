@@ -29,6 +29,10 @@ from . import ops
 GEN_GROWTH = (8, 8, 6, 4, 2)          # code/dmcnet/model.py:175-183
 GEN_IN = 5
 BN_MOMENTUM = 0.1
+# ContextNetwork (code/dmcnet/model.py:45-71): (cout, dilation) of its seven dilated 3x3 convs, each
+# followed by BatchNorm2d and LeakyReLU(0.1) -- the last one (-> 2 channels) included
+CONTEXT_LAYERS = ((32, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1), (2, 1))
+CONTEXT_RING = 16                     # zero ring of the pixel-major layout >= the largest dilation
 
 
 def disc_blocks(arch_d: str) -> List[Tuple[str, int, int, int, bool]]:
@@ -105,7 +109,8 @@ class DmcEngine:
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
                  grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH,
-                 share_from: Optional['DmcEngine'] = None, disc_engine: Optional[str] = None):
+                 share_from: Optional['DmcEngine'] = None, disc_engine: Optional[str] = None,
+                 arch_estimator: Optional[str] = None):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -122,6 +127,11 @@ class DmcEngine:
             raise ValueError('gen_growth must list the widths of the five dense layers')
         self.H, self.W = height, width
         self.gemm_engine = gemm_engine
+        # generator: the dense-concat family (growth table, CUDA-core kernels) or ContextNetwork, the
+        # reference's default --arch_estimator (dilated convs as tcgen05 tap GEMMs)
+        self.gen_arch = 'context' if arch_estimator == 'ContextNetwork' else 'dense'
+        if self.gen_arch == 'context' and gemm_engine != 'tc':
+            raise ValueError('ContextNetwork runs on the tensor-core GEMM engine only')
         # grad_bf16=True: the backward GEMMs (data and weight gradients of the ResNet convs) read
         # the incoming gradient dY rounded to bf16 (2 MMAs per k-step, no dY_lo plane; weights and
         # saved activations keep the full hi/lo split).  Measured on B200: 5% faster step, but the
@@ -140,7 +150,10 @@ class DmcEngine:
                 else 'planar'
         self.disc_engine = disc_engine if gan else None
         self._build_param_table()
-        self._alloc_generator()
+        if self.gen_arch == 'context':
+            self._alloc_context()
+        else:
+            self._alloc_generator()
         self._alloc_classifier()
         if self.gan:
             if self.disc_engine == 'tc':
@@ -154,7 +167,8 @@ class DmcEngine:
         return DmcEngine(self.num_class, self.S, frames, gan=self.gan, arch_d=self.arch_d,
                          gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
                          device=self.device, gemm_engine=self.gemm_engine, grad_bf16=self.grad_bf16,
-                         gen_growth=self.gen_growth, share_from=self, disc_engine=self.disc_engine)
+                         gen_growth=self.gen_growth, share_from=self, disc_engine=self.disc_engine,
+                         arch_estimator=('ContextNetwork' if self.gen_arch == 'context' else None))
 
     def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
@@ -200,12 +214,20 @@ class DmcEngine:
         specs['base_model.fc.weight'] = (C, 512)
         specs['base_model.fc.bias'] = (C,)
         cin = GEN_IN
-        for k, g in enumerate(self.gen_growth):
-            specs['gen_flow_model.conv_%d.0.weight' % k] = (g, cin, 3, 3)
-            specs['gen_flow_model.conv_%d.0.bias' % k] = (g,)
-            cin += g
-        specs['gen_flow_model.predict_flow.weight'] = (2, cin, 3, 3)
-        specs['gen_flow_model.predict_flow.bias'] = (2,)
+        if self.gen_arch == 'context':
+            for i, (co, _) in enumerate(CONTEXT_LAYERS):
+                q = 'gen_flow_model.conv_context.%d' % i
+                specs[q + '.0.weight'] = (co, cin, 3, 3)
+                specs[q + '.1.weight'] = (co,)
+                specs[q + '.1.bias'] = (co,)
+                cin = co
+        else:
+            for k, g in enumerate(self.gen_growth):
+                specs['gen_flow_model.conv_%d.0.weight' % k] = (g, cin, 3, 3)
+                specs['gen_flow_model.conv_%d.0.bias' % k] = (g,)
+                cin += g
+            specs['gen_flow_model.predict_flow.weight'] = (2, cin, 3, 3)
+            specs['gen_flow_model.predict_flow.bias'] = (2,)
         if self.gan:
             for name, ci, co, stride, bn in disc_blocks(self.arch_d):
                 p = 'discriminator.discriminator_block_%s' % name
@@ -918,6 +940,138 @@ class DmcEngine:
                                accumulate=True)
 
 
+
+    # ------------------------------------------------------------------ ContextNetwork generator
+    def _alloc_context(self):
+        """ContextNetwork (code/dmcnet/model.py:45-71) on the tensor-core path: pixel-major bf16 hi/lo maps
+        with a 16-pixel shared zero ring (dilations 1..16 become flat row shifts d*(dr*Wp + ds)),
+        channels zero-padded to 64 / 128 GEMM columns, weights through the same gather tables as the
+        discriminator plan (disc_plan.layer_plan('P1')), BatchNorm statistics / backward reductions in the
+        GEMM epilogues."""
+        from . import disc_plan as DP
+        dev, N, H, W, R = self.device, self.N, self.H, self.W, CONTEXT_RING
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        i32 = lambda a: torch.from_numpy(a.astype('int32')).contiguous().to(dev)
+        self.gen_ctot = GEN_IN
+        self.ctx_geo = (H + R, W + R)
+        Hp, Wp = self.ctx_geo
+        P = N * Hp * Wp
+        if P >= (1 << 31) // 128:
+            raise ValueError('ContextNetwork plan: %d frames of %dx%d exceed the 32-bit tile index range' % (N, H, W))
+        self.ctx_P = P
+        self.dD = torch.zeros(N, 2, H, W, **f32)                  # gradient w.r.t. gen_flow (planar)
+        self.d_gen_flow = self.dD
+        self.gen_flow = torch.zeros(N, 2, H, W, **f32)
+        self.ctx_in = torch.zeros(N, GEN_IN, H, W, **f32)          # cat(mv, residual), planar staging
+        self.ctx_in_hi, self.ctx_in_lo = torch.zeros(P, 64, **bf), torch.zeros(P, 64, **bf)
+        ncol = sum(DP.pad64(co) for co, _ in CONTEXT_LAYERS)
+        self._csums = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
+        self._csums2 = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
+        self.ctx_layers = []
+        cin, col, wg_total, max_np, max_ws = GEN_IN, 0, 0, 64, 0
+        for i, (co, d) in enumerate(CONTEXT_LAYERS):
+            lp = DP.layer_plan('P1', cin, co)
+            T, Np, Kp = lp['gmap'].shape
+            L = {'name': 'gen_flow_model.conv_context.%d' % i, 'cin': cin, 'cout': co, 'dil': d, 'Np': Np, 'Kp': Kp,
+                 'gmap': i32(lp['gmap'].reshape(-1)), 'inv': i32(lp['inv'].reshape(-1)), 'cmap': i32(lp['cmap']),
+                 'R': lp['inv'].shape[1],
+                 'shift': [(r - 1) * d * Wp + (s2 - 1) * d for r in range(3) for s2 in range(3)],
+                 'W_hi': torch.zeros(9, Np, Kp, **bf), 'W_lo': torch.zeros(9, Np, Kp, **bf),
+                 'Wt_hi': torch.zeros(9, Kp, Np, **bf), 'Wt_lo': torch.zeros(9, Kp, Np, **bf),
+                 'Y': torch.zeros(P, Np, **f32),
+                 'act_hi': torch.zeros(P, Np, **bf), 'act_lo': torch.zeros(P, Np, **bf),
+                 'sums': self._csums[2 * col:2 * col + 2 * Np].view(2, Np),
+                 'sums2': self._csums2[2 * col:2 * col + 2 * Np].view(2, Np),
+                 'coef': torch.zeros(3, Np, **f32), 'wg_off': wg_total}
+            for k in ('scale', 'shift_', 'mean', 'invstd'):
+                L[k] = torch.zeros(Np, **f32)
+            col += Np
+            wg_total += 9 * Np * Kp
+            max_np = max(max_np, Np, Kp)
+            max_ws = max(max_ws, ops.wgrad_workspace_floats(P, Np, Kp, 9))
+            self.ctx_layers.append(L)
+            cin = co
+        self._cwg = torch.zeros(wg_total, **f32)                   # GEMM-space weight gradients
+        for L in self.ctx_layers:
+            L['dWg'] = self._cwg[L['wg_off']:L['wg_off'] + 9 * L['Np'] * L['Kp']]
+        self.ctx_dz = [torch.zeros(P * max_np, **f32) for _ in range(2)]
+        self.ctx_G_hi, self.ctx_G_lo = torch.zeros(P * max_np, **bf), torch.zeros(P * max_np, **bf)
+        self.ctx_ws = torch.empty(max_ws, **f32)
+
+    def _ctx_forward(self, mv: torch.Tensor, res: torch.Tensor, n: int, train: bool):
+        """ContextNetwork.forward (+ input_mv when gen_flow_or_delta == 1): every block is dilated
+        Conv3x3(bias=False) -> BatchNorm2d(eps 1e-5) -> LeakyReLU(0.1) (code/dmcnet/model.py:31-42, :69-71)."""
+        H, W, R = self.H, self.W, CONTEXT_RING
+        Hp, Wp = self.ctx_geo
+        HW = H * W
+        rows = n * Hp * Wp
+        ops.copy_planar(mv, 2 * HW, self.ctx_in.view(-1), GEN_IN * HW, 2 * HW, n)
+        ops.copy_planar(res, 3 * HW, self.ctx_in.view(-1)[2 * HW:], GEN_IN * HW, 3 * HW, n)
+        ops.planar_to_pm_ring(self.ctx_in.view(-1), GEN_IN * HW, GEN_IN, 64, H, W, R, n, self.ctx_in_hi,
+                              self.ctx_in_lo)
+        if train:
+            ops.memset_zero(self._csums)
+        a_hi, a_lo = self.ctx_in_hi, self.ctx_in_lo
+        for L in self.ctx_layers:
+            p, Np, Kp = L['name'], L['Np'], L['Kp']
+            ops.weight_gather_prep(self.p(p + '.0.weight'), L['gmap'], 9, Np, Kp, L['W_hi'], L['W_lo'], L['Wt_hi'],
+                                   L['Wt_lo'])
+            ops.tap_gemm_ring(a_hi, a_lo, L['W_hi'], L['W_lo'], L['Y'], a_rows=rows, K=Kp, b_slices=9, N=Np,
+                              M=rows, ldD=Np, Hp=Hp, Wp=Wp, ring=R, shift=L['shift'],
+                              stats=(L['sums'] if train else None))
+            ops.pm_bn_finalize(L['sums'] if train else None, L['cmap'], Np, L['cout'], float(n * HW),
+                               self.p(p + '.1.weight'), self.p(p + '.1.bias'), self.buffers[p + '.1.running_mean'],
+                               self.buffers[p + '.1.running_var'],
+                               self.buffers[p + '.1.num_batches_tracked'] if train else None, BN_MOMENTUM, 1e-5,
+                               L['scale'], L['shift_'], L['mean'], L['invstd'])
+            ops.bn_apply_lrelu(L['Y'], L['scale'], L['shift_'], rows, Np, Hp, Wp, R, 0.1, L['act_hi'], L['act_lo'])
+            a_hi, a_lo = L['act_hi'], L['act_lo']
+        last = self.ctx_layers[-1]
+        ops.pm_ring_to_planar(last['act_hi'], last['act_lo'], last['Np'], 2, H, W, R, n,
+                              mv if self.gen_flow_or_delta == 1 else None, 2 * HW, self.gen_flow.view(-1), 2 * HW)
+
+    def _ctx_backward(self, n: int):
+        """Gradients of every ContextNetwork parameter from self.dD (= d loss / d gen_flow)."""
+        H, W, R = self.H, self.W, CONTEXT_RING
+        Hp, Wp = self.ctx_geo
+        HW = H * W
+        rows = n * Hp * Wp
+        count = float(n * HW)
+        ops.memset_zero(self._csums2)
+        ops.memset_zero(self._cwg)
+        last = self.ctx_layers[-1]
+        g = self.ctx_dz[0]
+        # loss gradient -> pixel-major, through the LeakyReLU of the last block; its two BN reductions
+        ops.planar_to_pm_ring(self.dD.view(-1), 2 * HW, 2, last['Np'], H, W, R, n, None, None, out_f32=g,
+                              act_hi=last['act_hi'], slope=0.1)
+        ops.bn_bwd_reduce(g, None, None, last['Y'], last['mean'], last['invstd'], rows, last['Np'], Hp, Wp,
+                          last['sums2'])
+        cur = 0
+        for li in reversed(range(len(self.ctx_layers))):
+            L = self.ctx_layers[li]
+            p, Np, Kp = L['name'], L['Np'], L['Kp']
+            G_hi, G_lo = self.ctx_G_hi[:rows * Np], self.ctx_G_lo[:rows * Np]
+            ops.pm_bn_bwd_fold(L['sums2'], L['cmap'], Np, L['cout'], count, self.p(p + '.1.weight'), L['invstd'],
+                               L['coef'], self.g(p + '.1.weight'), self.g(p + '.1.bias'))
+            ops.pm_bn_bwd_apply(g, L['Y'], L['mean'], L['invstd'], L['coef'], rows, Np, Hp, Wp, R, G_hi, G_lo)
+            if li > 0:
+                prev = self.ctx_layers[li - 1]
+                x_hi, x_lo = prev['act_hi'], prev['act_lo']
+            else:
+                x_hi, x_lo = self.ctx_in_hi, self.ctx_in_lo
+            nine = list(range(9))
+            ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, L['dWg'], P=rows, Cout=Np, x_phases=1, Cin=Kp, shift=L['shift'],
+                           phase=[0] * 9, bsel=nine, oihw_taps=0, workspace=self.ctx_ws)
+            ops.weight_grad_gather(L['dWg'], L['inv'], L['cout'] * L['cin'] * 9, L['R'], self.g(p + '.0.weight'))
+            if li == 0:
+                break
+            nxt = self.ctx_dz[1 - cur]
+            ops.tap_gemm_ring(G_hi, G_lo, L['Wt_hi'], L['Wt_lo'], nxt, a_rows=rows, K=Np, b_slices=9, N=Kp, M=rows,
+                              ldD=Kp, Hp=Hp, Wp=Wp, ring=R, shift=[-s2 for s2 in L['shift']], stats=prev['sums2'],
+                              bw=(prev['Y'], prev['act_hi'], None, prev['mean'], prev['invstd']), bw_slope=0.1)
+            g, cur = nxt, 1 - cur
+
     # ------------------------------------------------------------------ discriminator, tensor-core plan
     def _alloc_discriminator_tc(self):
         """Buffers and tables of the tensor-core discriminator plan (disc_plan.py): per block the index
@@ -1116,7 +1270,10 @@ class DmcEngine:
         mv = input_mv.reshape(-1, 2, H, W)
         res = input_residual.reshape(-1, 3, H, W)
         n = mv.shape[0]
-        self._gen_forward(mv, res, n)
+        if self.gen_arch == 'context':
+            self._ctx_forward(mv, res, n, train)
+        else:
+            self._gen_forward(mv, res, n)
         self._cls_forward(self.gen_flow, n, train)
         if not self.gan:
             return self.logits[:n], self.gen_flow[:n]
@@ -1174,5 +1331,7 @@ class DmcEngine:
         elif disc:
             self._disc_backward(self.d_in, self._m, disc_wgrad, self._use_masks,
                                 self.d_gen_flow if disc_to_gen else None, n)
-        if gen_grad:
+        if gen_grad and self.gen_arch == 'context':
+            self._ctx_backward(n)
+        elif gen_grad:
             self._gen_backward(n)

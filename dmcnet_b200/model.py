@@ -333,7 +333,8 @@ Initializing model:
 
     # -- engine plumbing
     def _native_supported(self) -> bool:
-        return (self._base_name == 'resnet18' and self.arch_estimator in DENSE_GROWTH
+        return (self._base_name == 'resnet18'
+                and (self.arch_estimator in DENSE_GROWTH or self.arch_estimator == 'ContextNetwork')
                 and self._representation == 'mv' and self.new_length == 1 and self.att == 0
                 and self.gen_flow_ds_factor == 0)
 
@@ -342,8 +343,8 @@ Initializing model:
             raise AttributeError("'%s' object has no attribute 'gen_flow_model'" % type(self).__name__)
         if not self._native_supported():
             raise NotImplementedError(
-                'dmcnet_b200 runs base_model=resnet18, arch_estimator=DenseNetTiny (also DenseNetSmall / '
-                'DenseNet, same kernels), representation=mv, att=0, gen_flow_ds_factor=0 natively; this '
+                'dmcnet_b200 runs base_model=resnet18, arch_estimator=ContextNetwork | DenseNetTiny | '
+                'DenseNetSmall | DenseNet, representation=mv, att=0, gen_flow_ds_factor=0 natively; this '
                 'configuration has no kernels (and there is no PyTorch fallback)')
         if not input_mv.is_cuda:
             raise RuntimeError('dmcnet_b200: inputs must be CUDA tensors (no CPU path exists)')
@@ -354,7 +355,9 @@ Initializing model:
             gan = getattr(self, 'discriminator', None) is not None
             eng = DmcEngine(self._num_class, self.num_segments, n, gan=gan, arch_d=self.arch_d,
                             gen_flow_or_delta=self.gen_flow_or_delta, height=H, width=W,
-                            device=input_mv.device, gen_growth=DENSE_GROWTH[self.arch_estimator])
+                            device=input_mv.device,
+                            gen_growth=DENSE_GROWTH.get(self.arch_estimator, DENSE_GROWTH['DenseNetTiny']),
+                            arch_estimator=self.arch_estimator)
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith('data_bn')}
             eng.load_state(sd)
             # parameters and buffers become views of the engine's storage

@@ -469,3 +469,39 @@ def planar_to_pm_ring2(x, in_ns, C, H, W, N, out_hi, out_lo):
 def s2d2_ring2_to_planar(D, ldD, H, W, N, dX, dx_ns, accumulate=False):
     _call('dmc_s2d2_ring2_to_planar', _ptr(D, F32), c_int(ldD), c_int(H), c_int(W), c_int(N), _ptr(dX, F32),
           c_long(dx_ns), c_int(1 if accumulate else 0), _stream())
+
+
+# ---------------------------------------------------------------- ContextNetwork (ring-R layouts, LeakyReLU)
+def tap_gemm_ring(A_hi, A_lo, B_hi, B_lo, D, *, a_rows, K, b_slices, N, M, ldD, Hp, Wp, ring, shift,
+                  stats=None, bw=None, bw_slope=0.0, phase=None, bsel=None, a_phases=1):
+    """tap_gemm on a layout with a `ring`-wide zero ring; bw = (Y, act_hi, gb_or_None, mean, invstd) with the
+    LeakyReLU slope bw_slope in the fused BatchNorm-backward epilogue."""
+    bY, bact, bgb, bmean, binv = bw if bw is not None else (None, None, None, None, None)
+    phase = phase if phase is not None else [0] * len(shift)
+    bsel = bsel if bsel is not None else list(range(len(shift)))
+    _call('dmc_tc_tap_gemm_ring', _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(a_phases), c_long(a_rows), c_int(K),
+          _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M), c_int(ldD),
+          c_int(Hp), c_int(Wp), c_int(ring), c_int(len(shift)), _iarr(shift), _iarr(phase), _iarr(bsel),
+          _ptr(stats, F64), _ptr(bY, F32), _ptr(bact, BF16), _ptr(bgb, F32), _ptr(bmean, F32), _ptr(binv, F32),
+          c_float(bw_slope), _stream())
+
+
+def bn_apply_lrelu(Y, scale, shift, P, C, Hp, Wp, ring, slope, out_hi, out_lo):
+    _call('dmc_bn_apply_lrelu', _ptr(Y, F32), _ptr(scale, F32), _ptr(shift, F32), c_long(P), c_int(C), c_int(Hp),
+          c_int(Wp), c_int(ring), c_float(slope), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _stream())
+
+
+def pm_bn_bwd_apply(dz, Y, mean, invstd, coef, P, C, Hp, Wp, ring, G_hi, G_lo):
+    _call('dmc_pm_bn_bwd_apply', _ptr(dz, F32), _ptr(Y, F32), _ptr(mean, F32), _ptr(invstd, F32), _ptr(coef, F32),
+          c_long(P), c_int(C), c_int(Hp), c_int(Wp), c_int(ring), _ptr(G_hi, BF16), _ptr(G_lo, BF16), _stream())
+
+
+def planar_to_pm_ring(x, in_ns, C, Cp, H, W, R, N, out_hi, out_lo, out_f32=None, act_hi=None, slope=1.0):
+    _call('dmc_planar_to_pm_ring', _ptr(x, F32), c_long(in_ns), c_int(C), c_int(Cp), c_int(H), c_int(W), c_int(R),
+          c_int(N), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(out_f32, F32), _ptr(act_hi, BF16), c_float(slope),
+          _stream())
+
+
+def pm_ring_to_planar(Z_hi, Z_lo, Cp, C, H, W, R, N, add, add_ns, out, out_ns):
+    _call('dmc_pm_ring_to_planar', _ptr(Z_hi, BF16), _ptr(Z_lo, BF16), c_int(Cp), c_int(C), c_int(H), c_int(W),
+          c_int(R), c_int(N), _ptr(add, F32), c_long(add_ns), _ptr(out, F32), c_long(out_ns), _stream())

@@ -1,0 +1,125 @@
+"""GPU: the reference's DEFAULT generator, ContextNetwork (code/dmcnet/model.py:45-71: seven dilated
+3x3 convs, dilations 1,2,4,8,16,1,1, each with BatchNorm2d + LeakyReLU(0.1)), on the tensor-core
+path -- against the oracle and against the fixture the REFERENCE itself produced
+(tests/golden/train_context_b1.npz, tests/golden/make_golden.py).
+
+Bars: forward outputs / losses / running statistics 1e-3 (north star), argmax exact; generator
+gradients (dmcnet: the MSE path only, through seven BatchNorm backwards on bf16x3 GEMMs) 2e-3
+per-tensor relative L2; classifier gradients as in tests/test_gpu_parity_full.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dmc_oracle as O          # noqa: E402  (checker only)
+from oracle.digest import digest_close      # noqa: E402
+
+if torch.cuda.is_available():
+    from dmcnet_b200.engine import DmcEngine
+    from dmcnet_b200.trainer import FusedTrainStep, HParams
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel2(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _pair(batch, arch_d=None, num_class=51):
+    gan = arch_d is not None
+    sd = O.build_state(num_class, arch_d, seed=1, arch_estimator='ContextNetwork')
+    ref = O.OracleTrainer(sd, O.HParams(), gan=gan, arch_d=arch_d, arch_estimator='ContextNetwork')
+    eng = DmcEngine(num_class, 3, batch * 3, gan=gan, arch_d=arch_d, arch_estimator='ContextNetwork')
+    eng.load_state(sd)
+    assert list(eng.state_keys()) == list(sd.keys())
+    return sd, ref, eng, FusedTrainStep(eng, HParams(), batch)
+
+
+@pytest.mark.parametrize('batch', [1, 2])
+def test_context_network_two_train_steps_vs_oracle(batch):
+    sd, ref, eng, tr = _pair(batch)
+    flow, mv, res, target = O.make_inputs(batch, 3, 51, seed=0)
+    for it in range(2):
+        mo = ref.step(flow, mv, res, target)
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+        for k in mo:
+            if k in ('prec1', 'prec5'):
+                assert mg[k] == mo[k], k
+            else:
+                assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+        assert rel(eng.gen_flow, ref.last_gen_flow) < 1e-3
+        assert rel(tr.consensus, ref.last_output) < 1e-3
+        assert torch.equal(tr.consensus.argmax(1).cpu(), ref.last_output.argmax(1))
+        if it == 0:
+            og = ref.grads()
+            for k in eng.specs:
+                if k.startswith('gen_flow_model'):
+                    assert rel2(eng.grad_view(k), og[k]) < 2e-3, k
+            osd, gsd = ref.state_dict(), eng.state_dict()
+            for k in osd:
+                if k.startswith('gen_flow_model') and not k.endswith('num_batches_tracked'):
+                    assert rel(gsd[k].float(), osd[k].float()) < 1e-3, k
+                if k.endswith('num_batches_tracked'):
+                    assert int(gsd[k]) == int(osd[k])
+
+
+def test_context_network_against_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'train_context_b1.npz'))
+    sd, ref, eng, tr = _pair(1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    for it in range(2):
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+        for k in ('loss', 'loss_cls', 'loss_mse'):
+            assert mg[k] == pytest.approx(float(g['s%d_%s' % (it, k)]), rel=1e-3)
+        np.testing.assert_allclose(tr.consensus.cpu().numpy(), g['s%d_output' % it], rtol=1e-3,
+                                   atol=1e-3 * np.abs(g['s%d_output' % it]).max())
+        digest_close(g['s%d_gen_flow' % it], eng.gen_flow.cpu(), 1e-3, 'gen_flow')
+
+
+def test_context_network_eval_forward_and_gan_g_step():
+    """Eval mode (running statistics) and the GAN G-step, where the generator gradient also arrives
+    through ResNet-18's stem data gradient and the discriminator."""
+    arch_d = 'Discriminator'
+    sd, ref, eng, tr = _pair(1, arch_d=arch_d)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    st = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        out = O.model_forward(st, mv, res, None, gan=True, arch_d=arch_d, train=False, arch_estimator='ContextNetwork')
+    logits, validity, gen_flow = eng.forward(mv.cuda(), res.cuda(), None, train=False)
+    assert rel(gen_flow, out[2]) < 1e-3 and rel(logits, out[0]) < 1e-3 and rel(validity, out[1]) < 1e-3
+    for it in range(2):
+        torch.manual_seed(100 + it)
+        masks = O.draw_dropout_masks(arch_d, 3 * (2 if it == 0 else 1))
+        mo = ref.step(flow, mv, res, target, masks=masks)
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), masks=masks)
+        for k in mo:
+            if k not in ('prec1', 'prec5', 'acc_adv'):
+                assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), (it, k)
+        if it == 1:
+            og = ref.grads()
+            errs = [rel2(eng.grad_view(k), og[k]) for k in eng.specs if k.startswith('gen_flow_model')]
+            assert float(np.median(errs)) < 3e-2 and max(errs) < 1e-1, errs
+
+
+def test_dropin_model_with_reference_default_generator_runs():
+    """``Model(num_class, S, 'mv', base_model='resnet18')`` with the reference's default
+    --arch_estimator constructs AND runs natively (round 1 raised NotImplementedError)."""
+    import contextlib, io
+    from dmcnet_b200.model import Model
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Model(51, 3, 'mv', base_model='resnet18', use_databn=0, gen_flow_or_delta=1)
+    assert m.arch_estimator == 'ContextNetwork'
+    m.cuda().train()
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    out, gen_flow = m(mv.cuda(), res.cuda())
+    loss = torch.nn.functional.cross_entropy(out.view(-1, 3, 51).mean(1), target.cuda()) + \
+        10.0 * torch.nn.functional.mse_loss(gen_flow, flow.cuda().view(-1, 2, 224, 224))
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
