@@ -105,12 +105,15 @@ class _ConvBN:
 
 
 class DmcEngine:
+    # defaults for subclasses that build only the parameter table (tests/sim_engine.py)
+    gen_arch, gen_fusion, gen_ds, _arch_estimator = 'dense', None, 0, None
+
     def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
                  grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH,
                  share_from: Optional['DmcEngine'] = None, disc_engine: Optional[str] = None,
-                 arch_estimator: Optional[str] = None):
+                 arch_estimator: Optional[str] = None, gen_flow_ds_factor: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -129,9 +132,20 @@ class DmcEngine:
         self.gemm_engine = gemm_engine
         # generator: the dense-concat family (growth table, CUDA-core kernels) or ContextNetwork, the
         # reference's default --arch_estimator (dilated convs as tcgen05 tap GEMMs)
+        self._arch_estimator = arch_estimator
         self.gen_arch = 'context' if arch_estimator == 'ContextNetwork' else 'dense'
         if self.gen_arch == 'context' and gemm_engine != 'tc':
             raise ValueError('ContextNetwork runs on the tensor-core GEMM engine only')
+        # EstimatorDenseNetTinyEarlyFusionSum / ...Stack (code/dmcnet/model.py:197-250): separate first convs
+        # for the motion vectors and the residual, summed or concatenated, then four dense layers
+        self.gen_fusion = {'DenseNetTinyEarlyFusionSum': 'sum', 'DenseNetTinyEarlyFusionStack': 'stack'}.get(
+            arch_estimator or '')
+        # --gen_flow_ds_factor f: AvgPool2d(f) in, f x f tiling out (model.py:326-327, :335-337, :347-348)
+        self.gen_ds = int(gen_flow_ds_factor)
+        if self.gen_ds < 0 or (self.gen_ds and (height % self.gen_ds or width % self.gen_ds)):
+            raise ValueError('gen_flow_ds_factor must divide the frame size')
+        if self.gen_ds and self.gen_arch == 'context':
+            raise NotImplementedError('ContextNetwork with gen_flow_ds_factor != 0 has no kernels')
         # grad_bf16=True: the backward GEMMs (data and weight gradients of the ResNet convs) read
         # the incoming gradient dY rounded to bf16 (2 MMAs per k-step, no dY_lo plane; weights and
         # saved activations keep the full hi/lo split).  Measured on B200: 5% faster step, but the
@@ -168,7 +182,7 @@ class DmcEngine:
                          gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
                          device=self.device, gemm_engine=self.gemm_engine, grad_bf16=self.grad_bf16,
                          gen_growth=self.gen_growth, share_from=self, disc_engine=self.disc_engine,
-                         arch_estimator=('ContextNetwork' if self.gen_arch == 'context' else None))
+                         arch_estimator=self._arch_estimator, gen_flow_ds_factor=self.gen_ds)
 
     def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
@@ -222,9 +236,16 @@ class DmcEngine:
                 specs[q + '.1.bias'] = (co,)
                 cin = co
         else:
-            for k, g in enumerate(self.gen_growth):
-                specs['gen_flow_model.conv_%d.0.weight' % k] = (g, cin, 3, 3)
-                specs['gen_flow_model.conv_%d.0.bias' % k] = (g,)
+            names, growth, base = self._dense_layout()
+            if self.gen_fusion:
+                specs['gen_flow_model.conv_0_mv.0.weight'] = (8, 2, 3, 3)
+                specs['gen_flow_model.conv_0_mv.0.bias'] = (8,)
+                specs['gen_flow_model.conv_0_r.0.weight'] = (8, 3, 3, 3)
+                specs['gen_flow_model.conv_0_r.0.bias'] = (8,)
+            cin = base
+            for name, g in zip(names, growth):
+                specs[name + '.weight'] = (g, cin, 3, 3)
+                specs[name + '.bias'] = (g,)
                 cin += g
             specs['gen_flow_model.predict_flow.weight'] = (2, cin, 3, 3)
             specs['gen_flow_model.predict_flow.bias'] = (2,)
@@ -325,35 +346,60 @@ class DmcEngine:
         return out
 
     # ------------------------------------------------------------------ allocation
+    def _dense_layout(self):
+        """(parameter prefixes of the dense layers, their growth, width of the base block).  The base is
+        the raw input (mv | residual, 5 channels) for EstimatorDenseNet*, or the fused first-layer
+        features for the EarlyFusion variants (8 summed / 16 stacked channels)."""
+        if self.gen_fusion:
+            return (['gen_flow_model.conv_%d.0' % k for k in (1, 2, 3, 4)], self.gen_growth[1:],
+                    16 if self.gen_fusion == 'stack' else 8)
+        return ['gen_flow_model.conv_%d.0' % k for k in range(5)], self.gen_growth, GEN_IN
+
     def _alloc_generator(self):
         dev, N, H, W = self.device, self.N, self.H, self.W
-        self.gen_ctot = GEN_IN + sum(self.gen_growth)                      # 33
-        self.X = torch.zeros(N, self.gen_ctot, H, W, dtype=torch.float32, device=dev)
-        # gradient buffer of the dense block: [d gen_flow (2) | new4 new3 new2 new1 new0 (28)];
+        f32 = dict(dtype=torch.float32, device=dev)
+        f = self.gen_ds or 1
+        self.gH, self.gW = H // f, W // f                       # resolution the estimator runs at
+        gH, gW = self.gH, self.gW
+        names, growth, base = self._dense_layout()
+        self.gen_names, self.gen_dense, self.gen_base = names, tuple(growth), base
+        self.gen_ctot = base + sum(growth)                      # 33 for DenseNetTiny
+        self.gen_base_off = self.gen_ctot - base                # X channel of the base block (28)
+        base_grad = self.gen_fusion is not None                 # the raw input needs no gradient
+        self.X = torch.zeros(N, self.gen_ctot, gH, gW, **f32)
+        # gradient buffer of the dense block: [d out (2) | d new_last .. d new_first | d base (fusion only)];
         # the gradient of one slice is a single convolution over ALL channels in front of it
-        self.dD = torch.zeros(N, 2 + self.gen_ctot - GEN_IN, H, W, dtype=torch.float32, device=dev)
-        self.d_gen_flow = self.dD[:, 0:2]                         # strided view (frame stride 30*H*W)
-        self.gen_flow = torch.zeros(N, 2, H, W, dtype=torch.float32, device=dev)
+        self.gD = torch.zeros(N, 2 + self.gen_base_off + (base if base_grad else 0), gH, gW, **f32)
+        if self.gen_ds:
+            self.dD = torch.zeros(N, 2, H, W, **f32)            # d loss / d gen_flow at frame resolution
+            self.gen_small = torch.zeros(N, 2, gH, gW, **f32)   # estimator output (+ pooled mv)
+            self.in_small = torch.zeros(N, GEN_IN, gH, gW, **f32)     # pooled mv | residual
+        else:
+            self.dD = self.gD
+        self.d_gen_flow = self.dD[:, 0:2]                       # strided view (frame stride 30*H*W for Tiny)
+        self.gen_flow = torch.zeros(N, 2, H, W, **f32)
+        if self.gen_fusion == 'sum':
+            self.ef = [torch.zeros(N, 8, gH, gW, **f32) for _ in range(3)]      # lrelu(conv_mv), lrelu(conv_r), scratch
         # channel offset of each layer's OUTPUT inside X: new channels are prepended
-        outs, off = [], self.gen_ctot - GEN_IN
-        for g in self.gen_growth:
+        outs, off = [], self.gen_base_off
+        for g in growth:
             off -= g
             outs.append(off)
         self.gen_out_off = outs                                          # [20, 12, 6, 2, 0]
-        self.gen_in_off = [o + g for o, g in zip(outs, self.gen_growth)]      # [28, 20, 12, 6, 2]
-        self.mv_off = self.gen_ctot - GEN_IN                             # 28
-        self.wflip = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=dev)   # dgrad weight scratch
-        # combined (flipped, transposed) dgrad weights of the generator slices, see _gen_backward
-        table, off = [len(self.gen_growth)], 0
+        self.gen_in_off = [o + g for o, g in zip(outs, growth)]          # [28, 20, 12, 6, 2]
+        self.wflip = torch.zeros(128 * 128 * 9, **f32)                   # dgrad weight scratch
+        # combined (flipped, transposed) dgrad weights of the slices, see _gen_backward
+        L = len(growth)
+        slices = [(growth[k], outs[k], k) for k in reversed(range(L))]   # (width, X channel, producing layer)
+        if base_grad:
+            slices.append((base, self.gen_base_off, -1))
+        table, off = [len(slices)], 0
         self.gen_wc_off = []
-        L = len(self.gen_growth)
-        for k in reversed(range(L)):                    # slices new4 .. new0
-            gk, xk = self.gen_growth[k], self.gen_out_off[k]
+        for gk, xk, k in slices:
             cin_s = 2 + xk
             segs = [(0, 2, self.offsets['gen_flow_model.predict_flow.weight'], self.gen_ctot, xk)]
-            for j in range(L - 1, k, -1):               # later dense layers j > k
-                segs.append((2 + self.gen_out_off[j], self.gen_growth[j],
-                             self.offsets['gen_flow_model.conv_%d.0.weight' % j],
+            for j in range(L - 1, k, -1):               # later dense layers j > k (all of them for the base)
+                segs.append((2 + outs[j], growth[j], self.offsets[names[j] + '.weight'],
                              self.gen_ctot - self.gen_in_off[j], xk - self.gen_in_off[j]))
             row = [off, gk, cin_s, len(segs)]
             for g in range(6):
@@ -361,8 +407,9 @@ class DmcEngine:
             table += row
             self.gen_wc_off.append(off)
             off += gk * cin_s * 9
+        self.gen_slices = slices
         self.gen_wc_table = table
-        self.gen_wc = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.gen_wc = torch.zeros(off, **f32)
 
     def _alloc_classifier(self):
         dev, N = self.device, self.N
@@ -503,46 +550,86 @@ class DmcEngine:
 
     # ------------------------------------------------------------------ generator
     def _gen_forward(self, mv: torch.Tensor, res: torch.Tensor, n: int):
-        """EstimatorDenseNetTiny.forward (+ input_mv when gen_flow_or_delta == 1)."""
-        H, W = self.H, self.W
+        """EstimatorDenseNet* / ...EarlyFusion*.forward (+ input_mv when gen_flow_or_delta == 1), at 1/f
+        resolution between an average pool and a tiling when gen_flow_ds_factor = f
+        (code/dmcnet/model.py:172-250, :330-348)."""
+        H, W = self.gH, self.gW
         HW = H * W
         X = self.X.view(-1)
         ns = self.gen_ctot * HW
-        ops.copy_planar(mv, 2 * HW, X[self.mv_off * HW:], ns, 2 * HW, n)
-        ops.copy_planar(res, 3 * HW, X[(self.mv_off + 2) * HW:], ns, 3 * HW, n)
-        for k, g in enumerate(self.gen_growth):
+        bo = self.gen_base_off
+        if self.gen_ds:
+            f, FHW = self.gen_ds, self.H * self.W
+            ops.avgpool_planar(mv, n * 2, self.H, self.W, f, self.in_small.view(-1)[:n * 2 * HW])
+            ops.avgpool_planar(res, n * 3, self.H, self.W, f, self.in_small.view(-1)[self.N * 2 * HW:])
+            mv = self.in_small.view(-1)[:self.N * 2 * HW]
+            res = self.in_small.view(-1)[self.N * 2 * HW:]
+        self._gen_in = (mv, res)
+        q = 'gen_flow_model.'
+        if self.gen_fusion is None:
+            ops.copy_planar(mv, 2 * HW, X[bo * HW:], ns, 2 * HW, n)
+            ops.copy_planar(res, 3 * HW, X[(bo + 2) * HW:], ns, 3 * HW, n)
+        elif self.gen_fusion == 'stack':            # x = cat(lrelu(conv_mv(mv)), lrelu(conv_r(res)))
+            ops.conv_fwd(mv, 2 * HW, 2, H, W, self.p(q + 'conv_0_mv.0.weight'), self.p(q + 'conv_0_mv.0.bias'), 8, 3, 1,
+                         X[bo * HW:], ns, n, slope=0.1)
+            ops.conv_fwd(res, 3 * HW, 3, H, W, self.p(q + 'conv_0_r.0.weight'), self.p(q + 'conv_0_r.0.bias'), 8, 3, 1,
+                         X[(bo + 8) * HW:], ns, n, slope=0.1)
+        else:                                       # x = lrelu(conv_mv(mv)) + lrelu(conv_r(res)); both kept for the backward
+            a, b = self.ef[0].view(-1), self.ef[1].view(-1)
+            ops.conv_fwd(mv, 2 * HW, 2, H, W, self.p(q + 'conv_0_mv.0.weight'), self.p(q + 'conv_0_mv.0.bias'), 8, 3, 1,
+                         a, 8 * HW, n, slope=0.1)
+            ops.conv_fwd(res, 3 * HW, 3, H, W, self.p(q + 'conv_0_r.0.weight'), self.p(q + 'conv_0_r.0.bias'), 8, 3, 1,
+                         b, 8 * HW, n, slope=0.1)
+            ops.conv_fwd(res, 3 * HW, 3, H, W, self.p(q + 'conv_0_r.0.weight'), self.p(q + 'conv_0_r.0.bias'), 8, 3, 1,
+                         X[bo * HW:], ns, n, slope=0.1, add=a, add_ns=8 * HW)
+        for k, g in enumerate(self.gen_dense):
             cin = self.gen_ctot - self.gen_in_off[k]
-            ops.conv_fwd(X[self.gen_in_off[k] * HW:], ns, cin, H, W,
-                         self.p('gen_flow_model.conv_%d.0.weight' % k),
-                         self.p('gen_flow_model.conv_%d.0.bias' % k), g, 3, 1,
-                         X[self.gen_out_off[k] * HW:], ns, n, slope=0.1)
-        ops.conv_fwd(X, ns, self.gen_ctot, H, W, self.p('gen_flow_model.predict_flow.weight'),
-                     self.p('gen_flow_model.predict_flow.bias'), 2, 3, 1, self.gen_flow.view(-1),
-                     2 * HW, n, slope=1.0,
+            ops.conv_fwd(X[self.gen_in_off[k] * HW:], ns, cin, H, W, self.p(self.gen_names[k] + '.weight'),
+                         self.p(self.gen_names[k] + '.bias'), g, 3, 1, X[self.gen_out_off[k] * HW:], ns, n, slope=0.1)
+        out = self.gen_small if self.gen_ds else self.gen_flow
+        ops.conv_fwd(X, ns, self.gen_ctot, H, W, self.p(q + 'predict_flow.weight'), self.p(q + 'predict_flow.bias'), 2,
+                     3, 1, out.view(-1), 2 * HW, n, slope=1.0,
                      add=(mv if self.gen_flow_or_delta == 1 else None), add_ns=2 * HW)
+        if self.gen_ds:
+            ops.tile_repeat(self.gen_small.view(-1), n * 2, H, W, self.gen_ds, self.gen_flow.view(-1))
 
     def _gen_backward(self, n: int):
-        """Gradients of all generator parameters from ``self.d_gen_flow`` (= dD[:, 0:2])."""
-        H, W = self.H, self.W
+        """Gradients of all generator parameters from d loss / d gen_flow (self.dD[:, 0:2])."""
+        H, W = self.gH, self.gW
         HW = H * W
-        X, dD = self.X.view(-1), self.dD.view(-1)
-        ns, dns = self.gen_ctot * HW, self.dD.shape[1] * HW
-        L = len(self.gen_growth)
+        X, dD = self.X.view(-1), self.gD.view(-1)
+        ns, dns = self.gen_ctot * HW, self.gD.shape[1] * HW
+        q = 'gen_flow_model.'
+        if self.gen_ds:                              # backward of the tiling: sum of the f*f tiles
+            ops.tile_sum(self.dD.view(-1), 2 * self.H * self.W, 2, H, W, self.gen_ds, n, dD, dns)
         ops.dense_dgrad_weights(self.params, self.gen_wc_table, self.gen_wc)
-        wk, bk = 'gen_flow_model.predict_flow.weight', 'gen_flow_model.predict_flow.bias'
-        ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dD, dns, 2, 3, 1, self.g(wk), self.g(bk), n)
-        for idx, k in enumerate(reversed(range(L))):
-            g = self.gen_growth[k]
-            oo, io = self.gen_out_off[k], self.gen_in_off[k]
-            cin_s = 2 + oo                                   # d gen_flow + every later slice
+        ops.conv_wgrad(X, ns, self.gen_ctot, H, W, dD, dns, 2, 3, 1, self.g(q + 'predict_flow.weight'),
+                       self.g(q + 'predict_flow.bias'), n)
+        mv, res = self._gen_in
+        for idx, (g, oo, k) in enumerate(self.gen_slices):
+            cin_s = 2 + oo                                   # d out + every later slice
             wc = self.gen_wc[self.gen_wc_off[idx]:self.gen_wc_off[idx] + g * cin_s * 9]
-            # slice gradient in ONE launch (no read-modify-write), LeakyReLU(0.1)' fused
-            ops.conv3x3_dgrad_fused(dD, dns, cin_s, H, W, wc, g, dD[(2 + oo) * HW:], dns, n,
-                                    accumulate=False, act_src=X[oo * HW:], act_ns=ns, act_c1=g,
-                                    act_slope=0.1)
-            wk, bk = 'gen_flow_model.conv_%d.0.weight' % k, 'gen_flow_model.conv_%d.0.bias' % k
-            ops.conv_wgrad(X[io * HW:], ns, self.gen_ctot - io, H, W, dD[(2 + oo) * HW:], dns, g, 3, 1,
-                           self.g(wk), self.g(bk), n)
+            masked = k >= 0 or self.gen_fusion == 'stack'    # slice = LeakyReLU(0.1) of ONE conv's output
+            # slice gradient in ONE launch (no read-modify-write), LeakyReLU' fused where it applies
+            ops.conv3x3_dgrad_fused(dD, dns, cin_s, H, W, wc, g, dD[(2 + oo) * HW:], dns, n, accumulate=False,
+                                    act_src=(X[oo * HW:] if masked else None), act_ns=ns,
+                                    act_c1=(g if masked else 0), act_slope=0.1)
+            if k >= 0:
+                io = self.gen_in_off[k]
+                ops.conv_wgrad(X[io * HW:], ns, self.gen_ctot - io, H, W, dD[(2 + oo) * HW:], dns, g, 3, 1,
+                               self.g(self.gen_names[k] + '.weight'), self.g(self.gen_names[k] + '.bias'), n)
+            elif self.gen_fusion == 'stack':
+                ops.conv_wgrad(mv, 2 * HW, 2, H, W, dD[(2 + oo) * HW:], dns, 8, 3, 1,
+                               self.g(q + 'conv_0_mv.0.weight'), self.g(q + 'conv_0_mv.0.bias'), n)
+                ops.conv_wgrad(res, 3 * HW, 3, H, W, dD[(2 + oo + 8) * HW:], dns, 8, 3, 1,
+                               self.g(q + 'conv_0_r.0.weight'), self.g(q + 'conv_0_r.0.bias'), n)
+            else:                                            # sum: the same dx through each branch's LeakyReLU
+                dpre = self.ef[2].view(-1)
+                for branch, src, cin_b, key in ((self.ef[0], mv, 2, 'conv_0_mv.0'), (self.ef[1], res, 3, 'conv_0_r.0')):
+                    ops.act_bwd_planar(dD[(2 + oo) * HW:], dns, branch.view(-1), 8 * HW, None, 0.1, 8, HW, n, dpre,
+                                       8 * HW)
+                    ops.conv_wgrad(src, cin_b * HW, cin_b, H, W, dpre, 8 * HW, 8, 3, 1, self.g(q + key + '.weight'),
+                                   self.g(q + key + '.bias'), n)
 
     def _dgrad_s1(self, dY, dy_ns, cout, wkey, cin, ci_count, dX, dx_ns, H, W, n, accumulate, act=None):
         """3x3 stride-1 data gradient = forward convolution of dY with the flipped, transposed weight;

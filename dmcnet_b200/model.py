@@ -333,19 +333,21 @@ Initializing model:
 
     # -- engine plumbing
     def _native_supported(self) -> bool:
-        return (self._base_name == 'resnet18'
-                and (self.arch_estimator in DENSE_GROWTH or self.arch_estimator == 'ContextNetwork')
-                and self._representation == 'mv' and self.new_length == 1 and self.att == 0
-                and self.gen_flow_ds_factor == 0)
+        dense = self.arch_estimator in DENSE_GROWTH or self.arch_estimator in (
+            'DenseNetTinyEarlyFusionSum', 'DenseNetTinyEarlyFusionStack')
+        context = self.arch_estimator == 'ContextNetwork' and self.att == 0 and self.gen_flow_ds_factor == 0
+        return (self._base_name == 'resnet18' and (dense or context)
+                and self._representation == 'mv' and self.new_length == 1)
 
     def _engine_for(self, input_mv) -> DmcEngine:
         if not hasattr(self, 'gen_flow_model'):
             raise AttributeError("'%s' object has no attribute 'gen_flow_model'" % type(self).__name__)
         if not self._native_supported():
             raise NotImplementedError(
-                'dmcnet_b200 runs base_model=resnet18, arch_estimator=ContextNetwork | DenseNetTiny | '
-                'DenseNetSmall | DenseNet, representation=mv, att=0, gen_flow_ds_factor=0 natively; this '
-                'configuration has no kernels (and there is no PyTorch fallback)')
+                'dmcnet_b200 runs base_model=resnet18, representation=mv with arch_estimator=DenseNetTiny | '
+                'DenseNetSmall | DenseNet | DenseNetTinyEarlyFusionSum | DenseNetTinyEarlyFusionStack (any '
+                'gen_flow_ds_factor) or ContextNetwork (att=0, gen_flow_ds_factor=0) natively; this configuration '
+                'has no kernels (and there is no PyTorch fallback)')
         if not input_mv.is_cuda:
             raise RuntimeError('dmcnet_b200: inputs must be CUDA tensors (no CPU path exists)')
         H, W = input_mv.shape[-2], input_mv.shape[-1]
@@ -357,7 +359,7 @@ Initializing model:
                             gen_flow_or_delta=self.gen_flow_or_delta, height=H, width=W,
                             device=input_mv.device,
                             gen_growth=DENSE_GROWTH.get(self.arch_estimator, DENSE_GROWTH['DenseNetTiny']),
-                            arch_estimator=self.arch_estimator)
+                            arch_estimator=self.arch_estimator, gen_flow_ds_factor=self.gen_flow_ds_factor)
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith('data_bn')}
             eng.load_state(sd)
             # parameters and buffers become views of the engine's storage

@@ -505,3 +505,17 @@ def planar_to_pm_ring(x, in_ns, C, Cp, H, W, R, N, out_hi, out_lo, out_f32=None,
 def pm_ring_to_planar(Z_hi, Z_lo, Cp, C, H, W, R, N, add, add_ns, out, out_ns):
     _call('dmc_pm_ring_to_planar', _ptr(Z_hi, BF16), _ptr(Z_lo, BF16), c_int(Cp), c_int(C), c_int(H), c_int(W),
           c_int(R), c_int(N), _ptr(add, F32), c_long(add_ns), _ptr(out, F32), c_long(out_ns), _stream())
+
+
+# ---------------------------------------------------------------- gen_flow_ds_factor helpers
+def avgpool_planar(x, planes, H, W, f, out):
+    _call('dmc_avgpool_planar', _ptr(x, F32), c_int(planes), c_int(H), c_int(W), c_int(f), _ptr(out, F32), _stream())
+
+
+def tile_repeat(x, planes, h, w, f, out):
+    _call('dmc_tile_repeat', _ptr(x, F32), c_int(planes), c_int(h), c_int(w), c_int(f), _ptr(out, F32), _stream())
+
+
+def tile_sum(d_out, do_ns, C, h, w, f, N, d_in, di_ns, accumulate=False):
+    _call('dmc_tile_sum', _ptr(d_out, F32), c_long(do_ns), c_int(C), c_int(h), c_int(w), c_int(f), c_int(N),
+          _ptr(d_in, F32), c_long(di_ns), c_int(1 if accumulate else 0), _stream())

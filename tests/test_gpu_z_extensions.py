@@ -511,3 +511,58 @@ def test_video_scorer_from_decoded_uint8_frames_ten_crops():
     r = V.forward_video(sd, mv, res, segs, 10)
     np.testing.assert_allclose(s, r, rtol=1e-3, atol=1e-3 * np.abs(r).max())
     assert int(s.argmax()) == int(r.argmax())
+
+
+# ------------------------------------------------------------------ the remaining generator choices
+@pytest.mark.parametrize('arch,ds', [('DenseNetTinyEarlyFusionSum', 0), ('DenseNetTinyEarlyFusionStack', 0),
+                                     ('DenseNetTiny', 4), ('DenseNetTinyEarlyFusionStack', 4)])
+def test_early_fusion_and_downsampled_generators_train_step_vs_oracle(arch, ds):
+    """EstimatorDenseNetTinyEarlyFusionSum / ...Stack (code/dmcnet/model.py:197-250) and
+    --gen_flow_ds_factor (AvgPool2d in, f x f tiling out; model.py:326-327, :335-337, :347-348) on the
+    dense-generator kernels: forward, losses, generator gradients (1e-4) and post-Adam state vs the oracle."""
+    num_class, batch = 51, 2
+    sd = O.build_state(num_class, None, seed=1, arch_estimator=arch, gen_flow_ds_factor=ds)
+    flow, mv, res, target = O.make_inputs(batch, 3, num_class, seed=0)
+    ref = O.OracleTrainer(sd, O.HParams(), gan=False, arch_estimator=arch, gen_flow_ds_factor=ds)
+    eng = DmcEngine(num_class, 3, batch * 3, arch_estimator=arch, gen_flow_ds_factor=ds)
+    eng.load_state(sd)
+    assert list(eng.state_keys()) == list(sd.keys())
+    tr = FusedTrainStep(eng, HParams(), batch)
+    for it in range(2):
+        mo = ref.step(flow, mv, res, target)
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+        for k in ('loss', 'loss_cls', 'loss_mse'):
+            assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), (it, k)
+        assert rel(eng.gen_flow, ref.last_gen_flow) < 1e-3
+        assert torch.equal(tr.consensus.argmax(1).cpu(), ref.last_output.argmax(1))
+        if it == 0:
+            og = ref.grads()
+            for k in eng.specs:
+                if k.startswith('gen_flow_model'):
+                    assert rel2(eng.grad_view(k), og[k]) < 1e-4, k
+    osd, gsd = ref.state_dict(), eng.state_dict()
+    for k in osd:
+        if k.startswith('gen_flow_model'):
+            assert rel(gsd[k], osd[k]) < 1e-3, k
+
+
+def test_gan_step_with_downsampled_generator_routes_gradients_through_the_tiling():
+    """GAN G-step with gen_flow_ds_factor = 4: classifier and discriminator gradients arrive at frame
+    resolution and are folded back through the tiling."""
+    arch_d, ds = 'Discriminator', 4
+    sd = O.build_state(51, arch_d, seed=1, gen_flow_ds_factor=ds)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    ref = O.OracleTrainer(sd, O.HParams(), gan=True, arch_d=arch_d, gen_flow_ds_factor=ds)
+    eng = DmcEngine(51, 3, 3, gan=True, arch_d=arch_d, gen_flow_ds_factor=ds)
+    eng.load_state(sd)
+    tr = FusedTrainStep(eng, HParams(), 1)
+    for it in range(2):
+        torch.manual_seed(100 + it)
+        masks = O.draw_dropout_masks(arch_d, 3 * (2 if it == 0 else 1))
+        mo = ref.step(flow, mv, res, target, masks=masks, apply=False)
+        mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), masks=masks, apply=False)
+        for k in ('loss', 'loss_cls', 'loss_adv'):
+            assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), (it, k)
+    og = ref.grads()
+    errs = [rel2(eng.grad_view(k), og[k]) for k in eng.specs if k.startswith('gen_flow_model')]
+    assert float(np.median(errs)) < 5e-2 and max(errs) < 1.2e-1, errs
