@@ -209,7 +209,8 @@ def measure(cfg_name, B, args, *, rank, local_rank, world, clocks=False, rooflin
     sd = build_state(cfg['num_class'], cfg['arch_d'], seed=1)
     eng = DmcEngine(cfg['num_class'], S, B * S, gan=cfg['gan'], arch_d=cfg['arch_d'])
     eng.load_state(sd)
-    tr = FusedTrainStep(eng, HParams(), B, world_size=world, use_graph=not args.no_graph, pipelined=True)
+    tr = FusedTrainStep(eng, HParams(), B, world_size=world, use_graph=not args.no_graph, pipelined=True,
+                        graph_allreduce=args.graph_allreduce)
 
     def barrier():
         torch.cuda.synchronize()
@@ -322,6 +323,8 @@ def main():
                     help="headline scaling mode; 'strong' fixes the GLOBAL batch at 512 (512/N per GPU)")
     ap.add_argument('--cpu-sample-batch', type=int, default=0, help='0 = 64 if host memory allows, else 16')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--graph-allreduce', action='store_true',
+                    help='capture the NCCL gradient all-reduce inside the step graph (N > 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='headline only (skip configs.config3 / config4_strong)')
     args = ap.parse_args()

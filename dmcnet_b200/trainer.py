@@ -91,7 +91,8 @@ def allreduce_groups(flat: torch.Tensor, group_range: Dict[str, Tuple[int, int]]
 
 class FusedTrainStep:
     def __init__(self, engine: DmcEngine, hp: HParams, batch: int, *, world_size: int = 1,
-                 process_group=None, use_graph: bool = False, pipelined: bool = False):
+                 process_group=None, use_graph: bool = False, pipelined: bool = False,
+                 graph_allreduce: bool = False):
         self.eng, self.hp, self.B = engine, hp, batch
         self.S = hp.num_segments
         if batch * self.S != engine.N:
@@ -100,6 +101,10 @@ class FusedTrainStep:
         self.world = world_size
         self.pg = process_group
         self.use_graph = use_graph
+        # graph_allreduce: capture the NCCL all-reduce INSIDE the step's CUDA graph (one graph = forward +
+        # backward + all-reduce + Adam, no host round trip between them) instead of issuing it eagerly
+        # between two graphs
+        self.graph_allreduce = bool(graph_allreduce and world_size > 1)
         dev = engine.device
         H, W, n = engine.H, engine.W, engine.N
         f32 = dict(dtype=torch.float32, device=dev)
@@ -328,21 +333,23 @@ class FusedTrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                with torch.cuda.graph(ga, stream=s, capture_error_mode='thread_local'):
-                    self._fwd_bwd(mode)
-                with torch.cuda.graph(gb, stream=s, capture_error_mode='thread_local'):
-                    self._adam(groups)
+                if self.graph_allreduce and apply:
+                    with torch.cuda.graph(ga, stream=s, capture_error_mode='thread_local'):
+                        self._fwd_bwd(mode)
+                        self._allreduce(groups)
+                        self._adam(groups)
+                    gb = None
+                else:
+                    with torch.cuda.graph(ga, stream=s, capture_error_mode='thread_local'):
+                        self._fwd_bwd(mode)
+                    with torch.cuda.graph(gb, stream=s, capture_error_mode='thread_local'):
+                        self._adam(groups)
             torch.cuda.current_stream().wait_stream(s)
             self._graphs[key] = ('ready', ga, gb)
-            # capture does not execute: run the step now
-            ga.replay()
-            if apply:
-                self._allreduce(groups)
-                gb.replay()
-            return
+            entry = self._graphs[key]          # capture does not execute: fall through and run the step now
         _, ga, gb = entry
         ga.replay()
-        if apply:
+        if apply and gb is not None:
             self._allreduce(groups)
             gb.replay()
 
