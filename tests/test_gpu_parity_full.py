@@ -194,7 +194,18 @@ def test_twenty_step_trajectory_vs_oracle():
         hist.append({k: (mo[k], mg[k]) for k in ('loss', 'loss_cls', 'loss_mse')})
         for k in ('loss_cls', 'loss_mse', 'loss'):
             assert mg[k] == pytest.approx(mo[k], rel=2e-3, abs=1e-6), (it, k)
-        assert mg['prec1'] == mo['prec1'] and mg['prec5'] == mo['prec5'], it
+        # top-k can only be compared while the oracle's own decision is not a near-tie: late in the
+        # trajectory two logits of one clip come within the accumulated difference of the two runs
+        lo = ref.last_output
+        top = lo.topk(6, 1).values
+        margin = float((top[:, :-1] - top[:, 1:]).min() / lo.abs().max())
+        dist = rel(tr.consensus, lo)
+        if margin > 3 * dist:
+            assert mg['prec1'] == mo['prec1'] and mg['prec5'] == mo['prec5'], (it, margin, dist)
+        # the two runs drift apart as the ~1e-2 gradient difference passes through Adam step after step
+        # (6 frames per BatchNorm batch); recorded per step in profiles/r02_parity_full.json
+        assert dist < (1e-3 if it == 0 else 1e-1), (it, dist)
+        hist[-1]['consensus_rel_err'] = dist
     osd, gsd = ref.state_dict(), eng.state_dict()
     init = O.build_state(51, None, seed=1)
     hp = HParams()
