@@ -198,6 +198,46 @@ flow_loss_head_kernel(const float* __restrict__ gen, const float* __restrict__ f
   }
 }
 
+// Attention-weighted flow criterion, criterion(att * gen, att * flow) of code/dmcnet/train.py:244-247
+// (--att 1): with u = att * (gen - flow), loss += crit(u), d/dgen = att * crit'(u),
+// d/datt = (gen - flow) * crit'(u).  gen, flow, att, datt are dense [numel]; dgen may be strided.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+att_flow_loss_head_kernel(const float* __restrict__ gen, const float* __restrict__ flow,
+                          const float* __restrict__ att, long n4, float gscale, float* __restrict__ dgen,
+                          long frame4, long dgen_ns4, float* __restrict__ datt, double* __restrict__ loss_sum) {
+  float s = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(gen)[i];
+    const float4 b = reinterpret_cast<const float4*>(flow)[i];
+    const float4 w = reinterpret_cast<const float4*>(att)[i];
+    const float d[4] = {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w};
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+    float gg[4], ga[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v, g;
+      flow_loss_term<KIND>(ww[k] * d[k], v, g);
+      s += v;
+      gg[k] = gscale * ww[k] * g;
+      ga[k] = gscale * d[k] * g;
+    }
+    if (dgen) {
+      const long o = frame4 == dgen_ns4 ? i : (i / frame4) * dgen_ns4 + (i % frame4);
+      reinterpret_cast<float4*>(dgen)[o] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      reinterpret_cast<float4*>(datt)[i] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+    }
+  }
+  __shared__ double red[8];
+  double sd = warp_sum_d((double)s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) sd += red[i];
+    atomicAdd(loss_sum, sd);
+  }
+}
+
 }  // namespace dmc
 
 using namespace dmc;
@@ -275,4 +315,29 @@ extern "C" int dmc_flow_loss_head(int kind, const float* gen, const float* flow,
   else
     flow_loss_head_kernel<2><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, n4, gscale, dgen, f4, d4, loss_sum);
   return dmc_check_launch("flow_loss_head_kernel");
+}
+
+// --att 1 (code/dmcnet/train.py:244-247, GAN :349-352): criterion(att * gen, att * flow), same kinds.
+// dgen (strided like dmc_flow_loss_head) = gscale * att * crit'(u), datt [numel] = gscale * (gen - flow) *
+// crit'(u), u = att * (gen - flow); both NULL for evaluation.
+extern "C" int dmc_att_flow_loss_head(int kind, const float* gen, const float* flow, const float* att,
+                                      long numel, float gscale, float* dgen, long frame_elems, long dgen_ns,
+                                      float* datt, double* loss_sum, void* stream) {
+  DMC_REQUIRE(kind >= 0 && kind <= 2, "att_flow_loss_head: kind must be 0 (MSE), 1 (SmoothL1) or 2 (L1)");
+  DMC_REQUIRE(numel % 4 == 0 && frame_elems % 4 == 0 && dgen_ns % 4 == 0 && frame_elems > 0,
+              "att_flow_loss_head: sizes must be multiples of 4");
+  DMC_REQUIRE(att != nullptr && (dgen == nullptr) == (datt == nullptr), "att_flow_loss_head: att / dgen / datt");
+  if (cudaMemsetAsync(loss_sum, 0, sizeof(double), ST_(stream)) != cudaSuccess)
+    return dmc_check_launch("att_flow_loss_head memset");
+  long blocks = cdiv(numel / 4, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  const long n4 = numel / 4, f4 = frame_elems / 4, d4 = dgen_ns / 4;
+  if (kind == 0)
+    att_flow_loss_head_kernel<0><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, att, n4, gscale, dgen, f4, d4, datt, loss_sum);
+  else if (kind == 1)
+    att_flow_loss_head_kernel<1><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, att, n4, gscale, dgen, f4, d4, datt, loss_sum);
+  else
+    att_flow_loss_head_kernel<2><<<(int)blocks, 256, 0, ST_(stream)>>>(gen, flow, att, n4, gscale, dgen, f4, d4, datt, loss_sum);
+  return dmc_check_launch("att_flow_loss_head_kernel");
 }
