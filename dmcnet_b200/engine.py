@@ -106,14 +106,14 @@ class _ConvBN:
 
 class DmcEngine:
     # defaults for subclasses that build only the parameter table (tests/sim_engine.py)
-    gen_arch, gen_fusion, gen_ds, _arch_estimator = 'dense', None, 0, None
+    gen_arch, gen_fusion, gen_ds, _arch_estimator, att = 'dense', None, 0, None, 0
 
     def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, device: Optional[torch.device] = None, gemm_engine: str = 'tc',
                  grad_bf16: bool = False, gen_growth: Sequence[int] = GEN_GROWTH,
                  share_from: Optional['DmcEngine'] = None, disc_engine: Optional[str] = None,
-                 arch_estimator: Optional[str] = None, gen_flow_ds_factor: int = 0):
+                 arch_estimator: Optional[str] = None, gen_flow_ds_factor: int = 0, att: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError('dmcnet_b200: a CUDA device is required (no CPU path exists)')
         if height % 32 or width % 32:
@@ -144,8 +144,11 @@ class DmcEngine:
         self.gen_ds = int(gen_flow_ds_factor)
         if self.gen_ds < 0 or (self.gen_ds and (height % self.gen_ds or width % self.gen_ds)):
             raise ValueError('gen_flow_ds_factor must divide the frame size')
-        if self.gen_ds and self.gen_arch == 'context':
-            raise NotImplementedError('ContextNetwork with gen_flow_ds_factor != 0 has no kernels')
+        # --att 1: ContextNetworkAtt (model.py:74-104) -- six context layers, then a flow head and an
+        # attention head (+ReLU); the flow criterion is weighted by the attention map (train.py:244-247).
+        # The reference ignores --att for every other estimator's constructor but still unpacks two
+        # outputs, so att is only meaningful with ContextNetwork
+        self.att = int(att == 1 and self.gen_arch == 'context')
         # grad_bf16=True: the backward GEMMs (data and weight gradients of the ResNet convs) read
         # the incoming gradient dY rounded to bf16 (2 MMAs per k-step, no dY_lo plane; weights and
         # saved activations keep the full hi/lo split).  Measured on B200: 5% faster step, but the
@@ -182,7 +185,7 @@ class DmcEngine:
                          gen_flow_or_delta=self.gen_flow_or_delta, height=self.H, width=self.W,
                          device=self.device, gemm_engine=self.gemm_engine, grad_bf16=self.grad_bf16,
                          gen_growth=self.gen_growth, share_from=self, disc_engine=self.disc_engine,
-                         arch_estimator=self._arch_estimator, gen_flow_ds_factor=self.gen_ds)
+                         arch_estimator=self._arch_estimator, gen_flow_ds_factor=self.gen_ds, att=self.att)
 
     def _alloc_sums(self, cout: int, bwd: bool = False) -> torch.Tensor:
         """[2][cout] double view inside one pool, so all BN statistics are zeroed by one memset."""
@@ -229,12 +232,10 @@ class DmcEngine:
         specs['base_model.fc.bias'] = (C,)
         cin = GEN_IN
         if self.gen_arch == 'context':
-            for i, (co, _) in enumerate(CONTEXT_LAYERS):
-                q = 'gen_flow_model.conv_context.%d' % i
-                specs[q + '.0.weight'] = (co, cin, 3, 3)
-                specs[q + '.1.weight'] = (co,)
-                specs[q + '.1.bias'] = (co,)
-                cin = co
+            for name, ci, co, _ in self._context_layout():
+                specs[name + '.0.weight'] = (co, ci, 3, 3)
+                specs[name + '.1.weight'] = (co,)
+                specs[name + '.1.bias'] = (co,)
         else:
             names, growth, base = self._dense_layout()
             if self.gen_fusion:
@@ -1029,38 +1030,68 @@ class DmcEngine:
 
 
     # ------------------------------------------------------------------ ContextNetwork generator
+    def _context_layout(self):
+        """[(parameter prefix, cin, cout, dilation)]: the trunk (code/dmcnet/model.py:45-71; the fifth
+        dilation is 1 instead of 16 when gen_flow_ds_factor != 0, :58-66 / :85-93) and, with --att 1, the
+        two heads of ContextNetworkAtt (:94-98) instead of the trunk's last layer."""
+        trunk = list(CONTEXT_LAYERS)
+        if self.gen_ds:
+            trunk[4] = (64, 1)
+        if self.att:
+            trunk = trunk[:6]
+        out, cin = [], GEN_IN
+        for i, (co, d) in enumerate(trunk):
+            out.append(('gen_flow_model.conv_context.%d' % i, cin, co, d))
+            cin = co
+        if self.att:
+            out.append(('gen_flow_model.predict_flow', 32, 2, 1))
+            out.append(('gen_flow_model.predict_att.0', 32, 2, 1))
+        return out
+
     def _alloc_context(self):
-        """ContextNetwork (code/dmcnet/model.py:45-71) on the tensor-core path: pixel-major bf16 hi/lo maps
-        with a 16-pixel shared zero ring (dilations 1..16 become flat row shifts d*(dr*Wp + ds)),
-        channels zero-padded to 64 / 128 GEMM columns, weights through the same gather tables as the
-        discriminator plan (disc_plan.layer_plan('P1')), BatchNorm statistics / backward reductions in the
-        GEMM epilogues."""
+        """ContextNetwork[Att] on the tensor-core path: pixel-major bf16 hi/lo maps with a shared zero ring
+        as wide as the largest dilation (a dilated tap is a flat row shift d*(dr*Wp + ds)), channels
+        zero-padded to 64 / 128 GEMM columns, weights through the gather tables of
+        disc_plan.layer_plan('P1'), BatchNorm statistics / backward reductions in the GEMM epilogues."""
         from . import disc_plan as DP
-        dev, N, H, W, R = self.device, self.N, self.H, self.W, CONTEXT_RING
+        dev, N, H, W = self.device, self.N, self.H, self.W
         f32 = dict(dtype=torch.float32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
         i32 = lambda a: torch.from_numpy(a.astype('int32')).contiguous().to(dev)
+        f = self.gen_ds or 1
+        self.gH, self.gW = H // f, W // f                       # resolution the estimator runs at
+        gH, gW = self.gH, self.gW
+        layout = self._context_layout()
+        R = self.ctx_ring = max(d for _, _, _, d in layout)
         self.gen_ctot = GEN_IN
-        self.ctx_geo = (H + R, W + R)
+        self.ctx_geo = (gH + R, gW + R)
         Hp, Wp = self.ctx_geo
         P = N * Hp * Wp
         if P >= (1 << 31) // 128:
             raise ValueError('ContextNetwork plan: %d frames of %dx%d exceed the 32-bit tile index range' % (N, H, W))
         self.ctx_P = P
-        self.dD = torch.zeros(N, 2, H, W, **f32)                  # gradient w.r.t. gen_flow (planar)
+        self.dD = torch.zeros(N, 2, H, W, **f32)                  # gradient w.r.t. gen_flow (planar, frame size)
         self.d_gen_flow = self.dD
         self.gen_flow = torch.zeros(N, 2, H, W, **f32)
-        self.ctx_in = torch.zeros(N, GEN_IN, H, W, **f32)          # cat(mv, residual), planar staging
+        self.ctx_in = torch.zeros(N, GEN_IN, gH, gW, **f32)        # cat(mv, residual) (pooled), planar staging
         self.ctx_in_hi, self.ctx_in_lo = torch.zeros(P, 64, **bf), torch.zeros(P, 64, **bf)
-        ncol = sum(DP.pad64(co) for co, _ in CONTEXT_LAYERS)
+        if self.gen_ds:
+            self.gen_small = torch.zeros(N, 2, gH, gW, **f32)
+            self.gD = torch.zeros(N, 2, gH, gW, **f32)             # d loss / d (estimator output)
+        else:
+            self.gD = self.dD
+        if self.att:
+            self.att_flow = torch.zeros(N, 2, gH, gW, **f32)       # attention map (estimator resolution, :341-357)
+            self.d_att = torch.zeros(N, 2, gH, gW, **f32)
+        ncol = sum(DP.pad64(co) for _, _, co, _ in layout)
         self._csums = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
         self._csums2 = torch.zeros(2 * ncol, dtype=torch.float64, device=dev)
         self.ctx_layers = []
-        cin, col, wg_total, max_np, max_ws = GEN_IN, 0, 0, 64, 0
-        for i, (co, d) in enumerate(CONTEXT_LAYERS):
+        col, wg_total, max_np, max_ws = 0, 0, 64, 0
+        for name, cin, co, d in layout:
             lp = DP.layer_plan('P1', cin, co)
             T, Np, Kp = lp['gmap'].shape
-            L = {'name': 'gen_flow_model.conv_context.%d' % i, 'cin': cin, 'cout': co, 'dil': d, 'Np': Np, 'Kp': Kp,
+            L = {'name': name, 'cin': cin, 'cout': co, 'dil': d, 'Np': Np, 'Kp': Kp,
                  'gmap': i32(lp['gmap'].reshape(-1)), 'inv': i32(lp['inv'].reshape(-1)), 'cmap': i32(lp['cmap']),
                  'R': lp['inv'].shape[1],
                  'shift': [(r - 1) * d * Wp + (s2 - 1) * d for r in range(3) for s2 in range(3)],
@@ -1070,7 +1101,7 @@ class DmcEngine:
                  'act_hi': torch.zeros(P, Np, **bf), 'act_lo': torch.zeros(P, Np, **bf),
                  'sums': self._csums[2 * col:2 * col + 2 * Np].view(2, Np),
                  'sums2': self._csums2[2 * col:2 * col + 2 * Np].view(2, Np),
-                 'coef': torch.zeros(3, Np, **f32), 'wg_off': wg_total}
+                 'coef': torch.zeros(3, Np, **f32), 'wg_off': wg_total, 'slope': 0.1}
             for k in ('scale', 'shift_', 'mean', 'invstd'):
                 L[k] = torch.zeros(Np, **f32)
             col += Np
@@ -1078,85 +1109,141 @@ class DmcEngine:
             max_np = max(max_np, Np, Kp)
             max_ws = max(max_ws, ops.wgrad_workspace_floats(P, Np, Kp, 9))
             self.ctx_layers.append(L)
-            cin = co
+        if self.att:
+            self.ctx_layers[-1]['slope'] = 0.0                     # ReLU(LeakyReLU(x)) = ReLU(x): the attention head
+        self.ctx_trunk = self.ctx_layers[:-2] if self.att else self.ctx_layers
         self._cwg = torch.zeros(wg_total, **f32)                   # GEMM-space weight gradients
         for L in self.ctx_layers:
             L['dWg'] = self._cwg[L['wg_off']:L['wg_off'] + 9 * L['Np'] * L['Kp']]
-        self.ctx_dz = [torch.zeros(P * max_np, **f32) for _ in range(2)]
+        self.ctx_dz = [torch.zeros(P * max_np, **f32) for _ in range(3 if self.att else 2)]
         self.ctx_G_hi, self.ctx_G_lo = torch.zeros(P * max_np, **bf), torch.zeros(P * max_np, **bf)
         self.ctx_ws = torch.empty(max_ws, **f32)
 
+    def _ctx_layer_fwd(self, L, a_hi, a_lo, rows: int, count: float, train: bool):
+        """dilated Conv3x3(bias=False) -> BatchNorm2d(eps 1e-5) -> LeakyReLU (code/dmcnet/model.py:31-42)."""
+        p, Np, Kp, R = L['name'], L['Np'], L['Kp'], self.ctx_ring
+        Hp, Wp = self.ctx_geo
+        ops.weight_gather_prep(self.p(p + '.0.weight'), L['gmap'], 9, Np, Kp, L['W_hi'], L['W_lo'], L['Wt_hi'],
+                               L['Wt_lo'])
+        ops.tap_gemm_ring(a_hi, a_lo, L['W_hi'], L['W_lo'], L['Y'], a_rows=rows, K=Kp, b_slices=9, N=Np,
+                          M=rows, ldD=Np, Hp=Hp, Wp=Wp, ring=R, shift=L['shift'],
+                          stats=(L['sums'] if train else None))
+        ops.pm_bn_finalize(L['sums'] if train else None, L['cmap'], Np, L['cout'], count,
+                           self.p(p + '.1.weight'), self.p(p + '.1.bias'), self.buffers[p + '.1.running_mean'],
+                           self.buffers[p + '.1.running_var'],
+                           self.buffers[p + '.1.num_batches_tracked'] if train else None, BN_MOMENTUM, 1e-5,
+                           L['scale'], L['shift_'], L['mean'], L['invstd'])
+        ops.bn_apply_lrelu(L['Y'], L['scale'], L['shift_'], rows, Np, Hp, Wp, R, L['slope'], L['act_hi'], L['act_lo'])
+
     def _ctx_forward(self, mv: torch.Tensor, res: torch.Tensor, n: int, train: bool):
-        """ContextNetwork.forward (+ input_mv when gen_flow_or_delta == 1): every block is dilated
-        Conv3x3(bias=False) -> BatchNorm2d(eps 1e-5) -> LeakyReLU(0.1) (code/dmcnet/model.py:31-42, :69-71)."""
-        H, W, R = self.H, self.W, CONTEXT_RING
+        """ContextNetwork[Att].forward (+ input_mv when gen_flow_or_delta == 1), at 1/f resolution between an
+        average pool and a tiling when gen_flow_ds_factor = f (code/dmcnet/model.py:330-357)."""
+        H, W, R = self.gH, self.gW, self.ctx_ring
         Hp, Wp = self.ctx_geo
         HW = H * W
-        rows = n * Hp * Wp
-        ops.copy_planar(mv, 2 * HW, self.ctx_in.view(-1), GEN_IN * HW, 2 * HW, n)
-        ops.copy_planar(res, 3 * HW, self.ctx_in.view(-1)[2 * HW:], GEN_IN * HW, 3 * HW, n)
-        ops.planar_to_pm_ring(self.ctx_in.view(-1), GEN_IN * HW, GEN_IN, 64, H, W, R, n, self.ctx_in_hi,
-                              self.ctx_in_lo)
+        rows, count = n * Hp * Wp, float(n * HW)
+        cin = self.ctx_in.view(-1)
+        if self.gen_ds:
+            ops.avgpool_planar(mv, n * 2, self.H, self.W, self.gen_ds, self.ctx_dz[0][:n * 2 * HW])
+            ops.avgpool_planar(res, n * 3, self.H, self.W, self.gen_ds, self.ctx_dz[1][:n * 3 * HW])
+            mv, res = self.ctx_dz[0][:n * 2 * HW], self.ctx_dz[1][:n * 3 * HW]
+        ops.copy_planar(mv, 2 * HW, cin, GEN_IN * HW, 2 * HW, n)
+        ops.copy_planar(res, 3 * HW, cin[2 * HW:], GEN_IN * HW, 3 * HW, n)
+        ops.planar_to_pm_ring(cin, GEN_IN * HW, GEN_IN, 64, H, W, R, n, self.ctx_in_hi, self.ctx_in_lo)
         if train:
             ops.memset_zero(self._csums)
         a_hi, a_lo = self.ctx_in_hi, self.ctx_in_lo
-        for L in self.ctx_layers:
-            p, Np, Kp = L['name'], L['Np'], L['Kp']
-            ops.weight_gather_prep(self.p(p + '.0.weight'), L['gmap'], 9, Np, Kp, L['W_hi'], L['W_lo'], L['Wt_hi'],
-                                   L['Wt_lo'])
-            ops.tap_gemm_ring(a_hi, a_lo, L['W_hi'], L['W_lo'], L['Y'], a_rows=rows, K=Kp, b_slices=9, N=Np,
-                              M=rows, ldD=Np, Hp=Hp, Wp=Wp, ring=R, shift=L['shift'],
-                              stats=(L['sums'] if train else None))
-            ops.pm_bn_finalize(L['sums'] if train else None, L['cmap'], Np, L['cout'], float(n * HW),
-                               self.p(p + '.1.weight'), self.p(p + '.1.bias'), self.buffers[p + '.1.running_mean'],
-                               self.buffers[p + '.1.running_var'],
-                               self.buffers[p + '.1.num_batches_tracked'] if train else None, BN_MOMENTUM, 1e-5,
-                               L['scale'], L['shift_'], L['mean'], L['invstd'])
-            ops.bn_apply_lrelu(L['Y'], L['scale'], L['shift_'], rows, Np, Hp, Wp, R, 0.1, L['act_hi'], L['act_lo'])
+        for L in self.ctx_trunk:
+            self._ctx_layer_fwd(L, a_hi, a_lo, rows, count, train)
             a_hi, a_lo = L['act_hi'], L['act_lo']
-        last = self.ctx_layers[-1]
-        ops.pm_ring_to_planar(last['act_hi'], last['act_lo'], last['Np'], 2, H, W, R, n,
-                              mv if self.gen_flow_or_delta == 1 else None, 2 * HW, self.gen_flow.view(-1), 2 * HW)
+        if self.att:
+            head_f, head_a = self.ctx_layers[-2], self.ctx_layers[-1]
+            self._ctx_layer_fwd(head_f, a_hi, a_lo, rows, count, train)
+            self._ctx_layer_fwd(head_a, a_hi, a_lo, rows, count, train)
+            ops.pm_ring_to_planar(head_a['act_hi'], head_a['act_lo'], head_a['Np'], 2, H, W, R, n, None, 0,
+                                  self.att_flow.view(-1), 2 * HW)
+            out = head_f
+        else:
+            out = self.ctx_trunk[-1]
+        # "+ input_mv" (model.py:344-345) uses the POOLED mv when the estimator runs at reduced resolution
+        add = cin if self.gen_flow_or_delta == 1 else None          # channels 0:2 of the staged input = mv
+        dst = self.gen_small if self.gen_ds else self.gen_flow
+        ops.pm_ring_to_planar(out['act_hi'], out['act_lo'], out['Np'], 2, H, W, R, n, add, GEN_IN * HW,
+                              dst.view(-1), 2 * HW)
+        if self.gen_ds:
+            ops.tile_repeat(self.gen_small.view(-1), n * 2, H, W, self.gen_ds, self.gen_flow.view(-1))
+
+    def _ctx_layer_bwd(self, L, g, x_hi, x_lo, rows: int, count: float):
+        """BatchNorm backward of one block from dz (already through its activation) and its two
+        reductions, then the weight gradient; returns the hi/lo gradient of the conv output."""
+        p, Np, Kp, R = L['name'], L['Np'], L['Kp'], self.ctx_ring
+        Hp, Wp = self.ctx_geo
+        G_hi, G_lo = self.ctx_G_hi[:rows * Np], self.ctx_G_lo[:rows * Np]
+        ops.pm_bn_bwd_fold(L['sums2'], L['cmap'], Np, L['cout'], count, self.p(p + '.1.weight'), L['invstd'],
+                           L['coef'], self.g(p + '.1.weight'), self.g(p + '.1.bias'))
+        ops.pm_bn_bwd_apply(g, L['Y'], L['mean'], L['invstd'], L['coef'], rows, Np, Hp, Wp, R, G_hi, G_lo)
+        ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, L['dWg'], P=rows, Cout=Np, x_phases=1, Cin=Kp, shift=L['shift'],
+                       phase=[0] * 9, bsel=list(range(9)), oihw_taps=0, workspace=self.ctx_ws)
+        ops.weight_grad_gather(L['dWg'], L['inv'], L['cout'] * L['cin'] * 9, L['R'], self.g(p + '.0.weight'))
+        return G_hi, G_lo
+
+    def _ctx_head_dz(self, L, d_planar, g, n: int, rows: int):
+        """planar loss gradient -> pixel-major dz of block L (through its activation) + its BN reductions."""
+        H, W, R = self.gH, self.gW, self.ctx_ring
+        Hp, Wp = self.ctx_geo
+        ops.planar_to_pm_ring(d_planar.view(-1), 2 * H * W, 2, L['Np'], H, W, R, n, None, None, out_f32=g,
+                              act_hi=L['act_hi'], slope=L['slope'])
+        ops.bn_bwd_reduce(g, None, None, L['Y'], L['mean'], L['invstd'], rows, L['Np'], Hp, Wp, L['sums2'])
 
     def _ctx_backward(self, n: int):
-        """Gradients of every ContextNetwork parameter from self.dD (= d loss / d gen_flow)."""
-        H, W, R = self.H, self.W, CONTEXT_RING
+        """Gradients of every ContextNetwork[Att] parameter from self.dD (= d loss / d gen_flow) and, with
+        --att 1, self.d_att (= d loss / d att_flow)."""
+        H, W, R = self.gH, self.gW, self.ctx_ring
         Hp, Wp = self.ctx_geo
-        HW = H * W
-        rows = n * Hp * Wp
-        count = float(n * HW)
+        rows, count = n * Hp * Wp, float(n * H * W)
         ops.memset_zero(self._csums2)
         ops.memset_zero(self._cwg)
-        last = self.ctx_layers[-1]
+        if self.gen_ds:                              # backward of the tiling: sum of the f*f tiles
+            ops.tile_sum(self.dD.view(-1), 2 * self.H * self.W, 2, H, W, self.gen_ds, n, self.gD.view(-1), 2 * H * W)
+        trunk = self.ctx_trunk
         g = self.ctx_dz[0]
-        # loss gradient -> pixel-major, through the LeakyReLU of the last block; its two BN reductions
-        ops.planar_to_pm_ring(self.dD.view(-1), 2 * HW, 2, last['Np'], H, W, R, n, None, None, out_f32=g,
-                              act_hi=last['act_hi'], slope=0.1)
-        ops.bn_bwd_reduce(g, None, None, last['Y'], last['mean'], last['invstd'], rows, last['Np'], Hp, Wp,
-                          last['sums2'])
-        cur = 0
-        for li in reversed(range(len(self.ctx_layers))):
-            L = self.ctx_layers[li]
-            p, Np, Kp = L['name'], L['Np'], L['Kp']
-            G_hi, G_lo = self.ctx_G_hi[:rows * Np], self.ctx_G_lo[:rows * Np]
-            ops.pm_bn_bwd_fold(L['sums2'], L['cmap'], Np, L['cout'], count, self.p(p + '.1.weight'), L['invstd'],
-                               L['coef'], self.g(p + '.1.weight'), self.g(p + '.1.bias'))
-            ops.pm_bn_bwd_apply(g, L['Y'], L['mean'], L['invstd'], L['coef'], rows, Np, Hp, Wp, R, G_hi, G_lo)
+        if self.att:
+            head_f, head_a, top = self.ctx_layers[-2], self.ctx_layers[-1], trunk[-1]
+            # flow head: its data gradient (raw) goes to a side buffer ...
+            self._ctx_head_dz(head_f, self.gD, g, n, rows)
+            G_hi, G_lo = self._ctx_layer_bwd(head_f, g, top['act_hi'], top['act_lo'], rows, count)
+            side = self.ctx_dz[2]
+            ops.tap_gemm_ring(G_hi, G_lo, head_f['Wt_hi'], head_f['Wt_lo'], side, a_rows=rows, K=head_f['Np'],
+                              b_slices=9, N=head_f['Kp'], M=rows, ldD=head_f['Kp'], Hp=Hp, Wp=Wp, ring=R,
+                              shift=[-s2 for s2 in head_f['shift']])
+            # ... and joins the attention head's in the fused epilogue (gb), which also applies the trunk's
+            # LeakyReLU' and reduces for its BatchNorm
+            self._ctx_head_dz(head_a, self.d_att, g, n, rows)
+            G_hi, G_lo = self._ctx_layer_bwd(head_a, g, top['act_hi'], top['act_lo'], rows, count)
+            nxt = self.ctx_dz[1]
+            ops.tap_gemm_ring(G_hi, G_lo, head_a['Wt_hi'], head_a['Wt_lo'], nxt, a_rows=rows, K=head_a['Np'],
+                              b_slices=9, N=head_a['Kp'], M=rows, ldD=head_a['Kp'], Hp=Hp, Wp=Wp, ring=R,
+                              shift=[-s2 for s2 in head_a['shift']], stats=top['sums2'],
+                              bw=(top['Y'], top['act_hi'], side, top['mean'], top['invstd']), bw_slope=top['slope'])
+            g, cur = nxt, 1
+        else:
+            self._ctx_head_dz(trunk[-1], self.gD, g, n, rows)
+            cur = 0
+        for li in reversed(range(len(trunk))):
+            L = trunk[li]
             if li > 0:
-                prev = self.ctx_layers[li - 1]
+                prev = trunk[li - 1]
                 x_hi, x_lo = prev['act_hi'], prev['act_lo']
             else:
                 x_hi, x_lo = self.ctx_in_hi, self.ctx_in_lo
-            nine = list(range(9))
-            ops.wgrad_gemm(G_hi, G_lo, x_hi, x_lo, L['dWg'], P=rows, Cout=Np, x_phases=1, Cin=Kp, shift=L['shift'],
-                           phase=[0] * 9, bsel=nine, oihw_taps=0, workspace=self.ctx_ws)
-            ops.weight_grad_gather(L['dWg'], L['inv'], L['cout'] * L['cin'] * 9, L['R'], self.g(p + '.0.weight'))
+            G_hi, G_lo = self._ctx_layer_bwd(L, g, x_hi, x_lo, rows, count)
             if li == 0:
                 break
             nxt = self.ctx_dz[1 - cur]
-            ops.tap_gemm_ring(G_hi, G_lo, L['Wt_hi'], L['Wt_lo'], nxt, a_rows=rows, K=Np, b_slices=9, N=Kp, M=rows,
-                              ldD=Kp, Hp=Hp, Wp=Wp, ring=R, shift=[-s2 for s2 in L['shift']], stats=prev['sums2'],
-                              bw=(prev['Y'], prev['act_hi'], None, prev['mean'], prev['invstd']), bw_slope=0.1)
+            ops.tap_gemm_ring(G_hi, G_lo, L['Wt_hi'], L['Wt_lo'], nxt, a_rows=rows, K=L['Np'], b_slices=9,
+                              N=L['Kp'], M=rows, ldD=L['Kp'], Hp=Hp, Wp=Wp, ring=R, shift=[-s2 for s2 in L['shift']],
+                              stats=prev['sums2'], bw=(prev['Y'], prev['act_hi'], None, prev['mean'], prev['invstd']),
+                              bw_slope=prev['slope'])
             g, cur = nxt, 1 - cur
 
     # ------------------------------------------------------------------ discriminator, tensor-core plan
@@ -1362,8 +1449,9 @@ class DmcEngine:
         else:
             self._gen_forward(mv, res, n)
         self._cls_forward(self.gen_flow, n, train)
+        extra = (self.att_flow[:n],) if self.att else ()        # (base_out, [validity,] gen_flow, att_flow), model.py:354-357
         if not self.gan:
-            return self.logits[:n], self.gen_flow[:n]
+            return (self.logits[:n], self.gen_flow[:n]) + extra
         HW2 = 2 * H * W
         ops.copy_planar(self.gen_flow, HW2, self.d_in.view(-1), HW2, HW2, n)     # "first fake then real"
         m = n
@@ -1379,7 +1467,7 @@ class DmcEngine:
         else:
             self._disc_forward(self.d_in, m, train, self._use_masks)
         self._m = m
-        return self.logits[:n], self.validity[:m], self.gen_flow[:n]
+        return (self.logits[:n], self.validity[:m], self.gen_flow[:n]) + extra
 
     def set_masks(self, masks: Sequence[torch.Tensor], m: int):
         """Stage Dropout2d masks ([m, C] per block) into the static device buffers."""

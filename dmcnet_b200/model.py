@@ -254,6 +254,9 @@ class _DmcFunction(torch.autograd.Function):
     def backward(ctx, *grads):
         eng, model, n = ctx.eng, ctx.model, ctx.n
         from . import ops
+        d_att = None
+        if eng.att:
+            grads, d_att = grads[:-1], grads[-1]
         if eng.gan:
             d_logits, d_validity, d_gen = grads
         else:
@@ -261,6 +264,8 @@ class _DmcFunction(torch.autograd.Function):
         z = lambda t, g: t.copy_(g) if g is not None else t.zero_()
         z(eng.d_logits[:n], d_logits)
         z(eng.d_gen_flow[:n], d_gen)
+        if eng.att:
+            z(eng.d_att[:n], d_att)
         if eng.gan:
             z(eng.d_validity[:eng._m], d_validity)
         eng.zero_grads()
@@ -335,8 +340,9 @@ Initializing model:
     def _native_supported(self) -> bool:
         dense = self.arch_estimator in DENSE_GROWTH or self.arch_estimator in (
             'DenseNetTinyEarlyFusionSum', 'DenseNetTinyEarlyFusionStack')
-        context = self.arch_estimator == 'ContextNetwork' and self.att == 0 and self.gen_flow_ds_factor == 0
-        return (self._base_name == 'resnet18' and (dense or context)
+        context = self.arch_estimator == 'ContextNetwork' and self.att in (0, 1)
+        # (--att 1 with any other estimator unpacks ONE tensor into two in the reference, model.py:341-342)
+        return (self._base_name == 'resnet18' and ((dense and self.att == 0) or context)
                 and self._representation == 'mv' and self.new_length == 1)
 
     def _engine_for(self, input_mv) -> DmcEngine:
@@ -346,8 +352,8 @@ Initializing model:
             raise NotImplementedError(
                 'dmcnet_b200 runs base_model=resnet18, representation=mv with arch_estimator=DenseNetTiny | '
                 'DenseNetSmall | DenseNet | DenseNetTinyEarlyFusionSum | DenseNetTinyEarlyFusionStack (any '
-                'gen_flow_ds_factor) or ContextNetwork (att=0, gen_flow_ds_factor=0) natively; this configuration '
-                'has no kernels (and there is no PyTorch fallback)')
+                'gen_flow_ds_factor) or ContextNetwork (att 0 / 1, any gen_flow_ds_factor) natively; this '
+                'configuration has no kernels (and there is no PyTorch fallback)')
         if not input_mv.is_cuda:
             raise RuntimeError('dmcnet_b200: inputs must be CUDA tensors (no CPU path exists)')
         H, W = input_mv.shape[-2], input_mv.shape[-1]
@@ -359,7 +365,8 @@ Initializing model:
                             gen_flow_or_delta=self.gen_flow_or_delta, height=H, width=W,
                             device=input_mv.device,
                             gen_growth=DENSE_GROWTH.get(self.arch_estimator, DENSE_GROWTH['DenseNetTiny']),
-                            arch_estimator=self.arch_estimator, gen_flow_ds_factor=self.gen_flow_ds_factor)
+                            arch_estimator=self.arch_estimator, gen_flow_ds_factor=self.gen_flow_ds_factor,
+                            att=self.att)
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith('data_bn')}
             eng.load_state(sd)
             # parameters and buffers become views of the engine's storage

@@ -519,3 +519,11 @@ def tile_repeat(x, planes, h, w, f, out):
 def tile_sum(d_out, do_ns, C, h, w, f, N, d_in, di_ns, accumulate=False):
     _call('dmc_tile_sum', _ptr(d_out, F32), c_long(do_ns), c_int(C), c_int(h), c_int(w), c_int(f), c_int(N),
           _ptr(d_in, F32), c_long(di_ns), c_int(1 if accumulate else 0), _stream())
+
+
+def att_flow_loss_head(kind, gen, flow, att, numel, gscale, dgen, datt, loss_sum, frame_elems=None, dgen_ns=None):
+    """criterion(att * gen, att * flow) of --att 1 (code/dmcnet/train.py:246-247); kinds as flow_loss_head."""
+    fe = frame_elems if frame_elems is not None else numel
+    _call('dmc_att_flow_loss_head', c_int(kind), _ptr(gen, F32), _ptr(flow, F32), _ptr(att, F32), c_long(numel),
+          c_float(gscale), _ptr(dgen, F32), c_long(fe), c_long(dgen_ns if dgen_ns is not None else fe),
+          _ptr(datt, F32), _ptr(loss_sum, F64), _stream())

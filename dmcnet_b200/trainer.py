@@ -286,17 +286,28 @@ class FusedTrainStep:
             eng.backward(n, cls=True, cls_wgrad=False, gen_grad=True, cls_to_gen=True, disc=True,
                          disc_wgrad=False, disc_to_gen=True)
 
-    def _flow_head(self, sc):
+    def _flow_head(self, sc, grads: bool = True):
         """criterion_mse(gen_flow, input_flow) and its gradient into the generator's
-        gradient buffer (code/dmcnet/train.py:245; GAN/train.py:350)."""
+        gradient buffer (code/dmcnet/train.py:245; GAN/train.py:350); with --att 1 both sides are weighted
+        by the attention map (train.py:246-247) and the map receives a gradient too."""
         eng = self.eng
         numel, frame = eng.N * 2 * eng.H * eng.W, 2 * eng.H * eng.W
-        dgen_ns = eng.dD.shape[1] * eng.H * eng.W
-        if self.flow_kind == 0:
-            ops.mse_head(eng.gen_flow, self.in_flow, numel, sc['mse'], eng.dD, self.mse_sum,
+        dgen_ns = eng.dD.shape[1] * eng.H * eng.W if grads else frame
+        dD = eng.dD if grads else None
+        if getattr(eng, 'att', 0):
+            if eng.gen_ds:
+                # the reference multiplies a 1/f-resolution attention map with the tiled flow: a shape error
+                raise RuntimeError('The size of tensor a (%d) must match the size of tensor b (%d): --att 1 with '
+                                   '--gen_flow_ds_factor != 0 cannot evaluate its flow loss (reference behaviour, '
+                                   'code/dmcnet/train.py:246)' % (eng.gW, eng.W))
+            ops.att_flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, eng.att_flow, numel,
+                                   sc['flow'] if grads else 0.0, dD, eng.d_att if grads else None, self.mse_sum,
+                                   frame_elems=frame, dgen_ns=dgen_ns)
+        elif self.flow_kind == 0:
+            ops.mse_head(eng.gen_flow, self.in_flow, numel, sc['mse'] if grads else 0.0, dD, self.mse_sum,
                          frame_elems=frame, dgen_ns=dgen_ns)
         else:
-            ops.flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, numel, sc['flow'], eng.dD,
+            ops.flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, numel, sc['flow'] if grads else 0.0, dD,
                                self.mse_sum, frame_elems=frame, dgen_ns=dgen_ns)
 
     def _step_groups(self, mode: str) -> List[str]:
@@ -446,13 +457,7 @@ class FusedTrainStep:
         eng.forward(self.in_mv, self.in_res, None, train=False)
         ops.ce_head(eng.logits, B, self.S, eng.num_class, self.target, 0.0, self.consensus, None,
                     self.ce_stats)
-        numel, frame = n * 2 * eng.H * eng.W, 2 * eng.H * eng.W
-        if self.flow_kind == 0:
-            ops.mse_head(eng.gen_flow, self.in_flow, numel, 0.0, None, self.mse_sum, frame_elems=frame,
-                         dgen_ns=frame)
-        else:
-            ops.flow_loss_head(self.flow_kind, eng.gen_flow, self.in_flow, numel, 0.0, None, self.mse_sum,
-                               frame_elems=frame, dgen_ns=frame)
+        self._flow_head(None, grads=False)
         if eng.gan:
             ops.ce_head(eng.validity, n, 1, 2, self.adv_t_g, 0.0, None, None, self.adv_stats)
         return self.read_metrics('G' if eng.gan else 'full')

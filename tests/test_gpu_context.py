@@ -144,3 +144,62 @@ def test_dropin_model_with_reference_default_generator_runs():
         10.0 * torch.nn.functional.mse_loss(gen_flow, flow.cuda().view(-1, 2, 224, 224))
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+# ------------------------------------------------------------------ ContextNetworkAtt, reduced resolution
+def _pair_kw(batch, **kw):
+    sd = O.build_state(51, None, seed=1, arch_estimator='ContextNetwork', **kw)
+    ref = O.OracleTrainer(sd, O.HParams(), arch_estimator='ContextNetwork', **kw)
+    eng = DmcEngine(51, 3, batch * 3, arch_estimator='ContextNetwork', **kw)
+    eng.load_state(sd)
+    assert list(eng.state_keys()) == list(sd.keys())
+    return sd, ref, eng, FusedTrainStep(eng, HParams(), batch)
+
+
+def test_context_network_att_train_step_vs_oracle():
+    """--att 1 (ContextNetworkAtt, code/dmcnet/model.py:74-104): flow head + attention head (ReLU), the
+    flow loss weighted by the attention map (train.py:246-247).  The reference's own class cannot
+    run backward on torch >= 1.x (two in-place activations), so the gradients are held to the oracle."""
+    sd, ref, eng, tr = _pair_kw(1, att=1)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    mo = ref.step(flow, mv, res, target, apply=False)
+    mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), apply=False)
+    for k in ('loss', 'loss_cls', 'loss_mse'):
+        assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+    assert rel(eng.gen_flow, ref.last_gen_flow) < 1e-3
+    st = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        out = O.model_forward(st, mv, res, train=True, arch_estimator='ContextNetwork', att=1)
+    assert rel(eng.att_flow, out[2]) < 1e-3 and float(eng.att_flow.min()) >= 0.0
+    og = ref.grads()
+    for k in eng.specs:
+        if k.startswith('gen_flow_model'):
+            assert rel2(eng.grad_view(k), og[k]) < 2e-2, k
+
+
+@pytest.mark.parametrize('att', [0, 1])
+def test_context_network_at_reduced_resolution(att):
+    """--gen_flow_ds_factor 4 with ContextNetwork: the fifth dilation becomes 1 (model.py:58-66), AvgPool2d in,
+    4 x 4 tiling out.  With --att 1 the reference returns the attention map at the REDUCED resolution and its
+    flow loss then fails on the shape mismatch (train.py:246): forwards only, and the same error."""
+    sd, ref, eng, tr = _pair_kw(1, att=att, gen_flow_ds_factor=4)
+    flow, mv, res, target = O.make_inputs(1, 3, 51, seed=0)
+    st = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        out = O.model_forward(st, mv, res, train=True, arch_estimator='ContextNetwork', att=att, gen_flow_ds_factor=4)
+    got = eng.forward(mv.cuda(), res.cuda(), train=True)
+    assert rel(got[1], out[1]) < 1e-3 and rel(got[0], out[0]) < 1e-3
+    if att:
+        assert tuple(got[2].shape) == tuple(out[2].shape) == (3, 2, 56, 56) and rel(got[2], out[2]) < 1e-3
+        with pytest.raises(RuntimeError, match='must match the size'):
+            tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda())
+        return
+    eng.load_state(sd)
+    mo = ref.step(flow, mv, res, target, apply=False)
+    mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), apply=False)
+    for k in ('loss', 'loss_cls', 'loss_mse'):
+        assert mg[k] == pytest.approx(mo[k], rel=1e-3, abs=1e-6), k
+    og = ref.grads()
+    for k in eng.specs:
+        if k.startswith('gen_flow_model'):
+            assert rel2(eng.grad_view(k), og[k]) < 2e-2, k
