@@ -30,10 +30,18 @@ def pad64(c: int) -> int:
 
 
 def supported(arch_d: str, height: int, width: int) -> bool:
-    """The tensor-core plan covers the four 16/32/64/128-channel discriminators at sizes whose last map
-    is at least 1x1 on every grid (Discriminator4's 8/16/32 plan stays on the planar kernels)."""
+    """Whether the plan can express this discriminator: the four 16/32/64/128-channel ones, at sizes that
+    are multiples of 16 (Discriminator4's 8/16/32 channels have no space-to-depth form here)."""
     return arch_d in ('Discriminator', 'Discriminator2', 'Discriminator3', 'Discriminator5') \
         and height % 16 == 0 and width % 16 == 0
+
+
+def preferred(arch_d: str, height: int, width: int) -> bool:
+    """Whether the engine picks the tensor-core plan by default.  Discriminator5 (20 BatchNorm'd blocks) is
+    left on the fp32 planar kernels: each BatchNorm backward amplifies the 2^-17 operand rounding of the
+    bf16 hi/lo GEMMs, and through five blocks per stage the gradients of its early blocks were measured
+    3e-2 .. 2e-1 away from the float64 oracle (1e-2 for Discriminator3); `disc_engine='tc'` still forces it."""
+    return supported(arch_d, height, width) and arch_d != 'Discriminator5'
 
 
 def _split2(v: int) -> Tuple[int, int]:

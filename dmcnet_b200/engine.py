@@ -163,7 +163,7 @@ class DmcEngine:
         # (Discriminator4, odd sizes, and the cross-check of the tensor-core plan)
         if disc_engine is None:
             from . import disc_plan as DP
-            disc_engine = 'tc' if (gan and gemm_engine == 'tc' and DP.supported(arch_d, height, width)) \
+            disc_engine = 'tc' if (gan and gemm_engine == 'tc' and DP.preferred(arch_d, height, width)) \
                 else 'planar'
         self.disc_engine = disc_engine if gan else None
         self._build_param_table()

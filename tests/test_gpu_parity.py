@@ -117,12 +117,12 @@ def test_dmcnet_cuda_core_gemm_engine_agrees():
 
 @pytest.mark.parametrize('num_class,arch_d,batch,plan', [(101, 'Discriminator3', 2, 'tc'), (51, 'Discriminator', 1, 'tc'),
                                                          (101, 'Discriminator3', 1, 'planar'),
-                                                         (51, 'Discriminator2', 1, 'tc'), (51, 'Discriminator5', 1, 'tc'),
+                                                         (51, 'Discriminator2', 1, 'tc'), (51, 'Discriminator5', 1, 'planar'),
                                                          (51, 'Discriminator4', 1, 'planar')])
 def test_gan_d_step_then_g_step_vs_oracle(num_class, arch_d, batch, plan):
     """Every discriminator of code/dmcnet_GAN/model.py:282-438, on the plan that runs it."""
-    for it, ref, eng, tr, mo, mg in _run(num_class, arch_d, batch, disc_engine=plan):
-        assert eng.disc_engine == plan
+    for it, ref, eng, tr, mo, mg in _run(num_class, arch_d, batch, disc_engine=(None if arch_d != 'Discriminator3' else plan)):
+        assert eng.disc_engine == plan          # None = the engine's own choice
         _check_forward(ref, eng, tr, mo, mg, True)
         if it == 0:      # D-step: classifier + discriminator step; D grads do not depend on ResNet
             # planar plan: fp32 kernels, 1e-4; tensor-core plan: 1e-2 (the 2^-17 operand rounding is
