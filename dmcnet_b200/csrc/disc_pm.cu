@@ -47,6 +47,26 @@ weight_gather_prep_kernel(const float* __restrict__ w, const int* __restrict__ m
     for (int j = threadIdx.x; j < N; j += blockDim.x) bias_exp[j] = bmap[j] >= 0 ? bias[bmap[j]] : 0.f;
 }
 
+// Inference: BatchNorm folded into the conv operand.  W[t][co][ci] = w_oihw[co][ci][t] * scale[co] as bf16
+// hi/lo, zero-padded to [T][Np][Kp]; bias_out[co] = shift[co] (0 on padding columns).
+__global__ void __launch_bounds__(256)
+weight_fold_prep_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int Cout, int Cin, int T, int Np, int Kp,
+                        bf16* __restrict__ W_hi, bf16* __restrict__ W_lo, float* __restrict__ bias_out) {
+  const int total = T * Np * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Kp, n = (i / Kp) % Np, t = i / (Kp * Np);
+    float v = 0.f;
+    if (n < Cout && k < Cin) v = w[((long)n * Cin + k) * T + t] * scale[n];
+    bf16 h, l;
+    split_bf16(v, h, l);
+    W_hi[i] = h;
+    W_lo[i] = l;
+  }
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < Np; j += blockDim.x) bias_out[j] = j < Cout ? shift[j] : 0.f;
+}
+
 // dW[e] += sum_r dWg[inv[e][r]] (inv < 0: no entry), dbias[c] += sum_r dbias_exp[binv[c][r]].
 // Fixed summation order: deterministic.
 __global__ void __launch_bounds__(256)
@@ -377,6 +397,19 @@ extern "C" int dmc_weight_gather_prep(const float* w, const int* map, int T, int
   weight_gather_prep_kernel<<<grid_for((long)T * N * K, 256), 256, 0, (cudaStream_t)stream>>>(
       w, map, T, N, K, (bf16*)W_hi, (bf16*)W_lo, (bf16*)Wt_hi, (bf16*)Wt_lo, bias, bmap, bias_exp);
   return dmc_check_launch("weight_gather_prep_kernel");
+}
+
+// Inference operands with eval-mode BatchNorm folded in: W_hi/lo [T][Np][Kp] = bf16 split of
+// w_oihw[co][ci][t] * scale[co] (zero padding beyond Cout / Cin), bias_out [Np] = shift (0 on padding).
+// scale / shift are the eval coefficients (dmc_bn_eval_coeffs / dmc_pm_bn_finalize in eval mode).
+extern "C" int dmc_weight_fold_prep(const float* w_oihw, const float* scale, const float* shift, int Cout,
+                                    int Cin, int T, int Np, int Kp, void* W_hi, void* W_lo, float* bias_out,
+                                    void* stream) {
+  DMC_REQUIRE(w_oihw && scale && shift && W_hi && W_lo && bias_out, "weight_fold_prep: null argument");
+  DMC_REQUIRE(Cout >= 1 && Cin >= 1 && T >= 1 && Np >= Cout && Kp >= Cin, "weight_fold_prep: bad shape");
+  weight_fold_prep_kernel<<<grid_for((long)T * Np * Kp, 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, scale, shift, Cout, Cin, T, Np, Kp, (bf16*)W_hi, (bf16*)W_lo, bias_out);
+  return dmc_check_launch("weight_fold_prep_kernel");
 }
 
 // OIHW gradient from the GEMM-space gradient: dW[e] += sum_{r<R} dWg[inv[e*R + r]] (entries < 0

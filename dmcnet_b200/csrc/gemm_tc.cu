@@ -131,6 +131,14 @@ struct ActFuse {
   const float* mask;     // [frames][N] or null
   float slope;
   unsigned frame_rows;   // Hp * Wp
+  // inference with BatchNorm folded into the weights (bias = folded shift): optional residual added
+  // BEFORE the activation (fp32 [M][N], or a bf16 hi/lo activation), and the result written as bf16
+  // hi/lo planes instead of fp32 D -- the operand of the next GEMM, with no elementwise pass in between
+  const float* res_f32;
+  const bf16* res_hi;
+  const bf16* res_lo;
+  bf16* out_hi;
+  bf16* out_lo;
 };
 
 template <int BN, int STAGES>
@@ -319,6 +327,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           // bias + LeakyReLU + per-(frame, channel) dropout scale on this thread's row
           const float* mrow = (act.mask && keep)
                                   ? act.mask + (long)((unsigned)q / act.frame_rows) * N + n0 + c : nullptr;
+          const long roff = q * (long)ldD + n0 + c;        // this thread's row in a [M][ldD] residual
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(act.bias + n0 + c + 4 * g));
@@ -329,6 +338,17 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
             v.y = __uint_as_float(r[4 * g + 1]) + b4.y;
             v.z = __uint_as_float(r[4 * g + 2]) + b4.z;
             v.w = __uint_as_float(r[4 * g + 3]) + b4.w;
+            if (keep && act.res_f32) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(act.res_f32 + roff + 4 * g));
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            } else if (keep && act.res_hi) {
+              const uint2 h = __ldg(reinterpret_cast<const uint2*>(act.res_hi + roff + 4 * g));
+              const uint2 l = __ldg(reinterpret_cast<const uint2*>(act.res_lo + roff + 4 * g));
+              v.x += __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+              v.y += __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+              v.z += __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+              v.w += __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+            }
             v.x = (v.x > 0.f ? v.x : v.x * act.slope) * m4.x;
             v.y = (v.y > 0.f ? v.y : v.y * act.slope) * m4.y;
             v.z = (v.z > 0.f ? v.z : v.z * act.slope) * m4.z;
@@ -373,7 +393,16 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
               const long gq = m0 + wq * 32 + row;
               if (gq < M) {
                 const float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
-                *reinterpret_cast<float4*>(D + gq * (long)ldD + n0 + c + c4) = v;
+                const long o = gq * (long)ldD + n0 + c + c4;
+                if (act.out_hi) {
+                  bf16 hh[4], ll[4];
+                  split_bf16(v.x, hh[0], ll[0]); split_bf16(v.y, hh[1], ll[1]);
+                  split_bf16(v.z, hh[2], ll[2]); split_bf16(v.w, hh[3], ll[3]);
+                  *reinterpret_cast<uint2*>(act.out_hi + o) = *reinterpret_cast<uint2*>(hh);
+                  *reinterpret_cast<uint2*>(act.out_lo + o) = *reinterpret_cast<uint2*>(ll);
+                } else {
+                  *reinterpret_cast<float4*>(D + o) = v;
+                }
               }
             }
           } else {
@@ -987,6 +1016,7 @@ extern "C" int dmc_tc_tap_gemm(const void* A_hi, const void* A_lo, int a_phases,
   bw.slope = 0.f;
   ActFuse act;
   act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
+  act.res_f32 = nullptr; act.res_hi = nullptr; act.res_lo = nullptr; act.out_hi = nullptr; act.out_lo = nullptr;
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
                        shift, phase, bsel, stats, bw, act, 1, stream);
 }
@@ -1006,6 +1036,7 @@ extern "C" int dmc_tc_tap_gemm_ring(const void* A_hi, const void* A_lo, int a_ph
   bw.slope = bw_slope;
   ActFuse act;
   act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
+  act.res_f32 = nullptr; act.res_hi = nullptr; act.res_lo = nullptr; act.out_hi = nullptr; act.out_lo = nullptr;
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
                        shift, phase, bsel, stats, bw, act, ring, stream);
 }
@@ -1024,8 +1055,34 @@ extern "C" int dmc_tc_tap_gemm_act(const void* A_hi, const void* A_lo, int a_pha
   bw.slope = 0.f;
   ActFuse act;
   act.bias = bias; act.mask = mask; act.slope = slope; act.frame_rows = (unsigned)(Hp * Wp);
+  act.res_f32 = nullptr; act.res_hi = nullptr; act.res_lo = nullptr; act.out_hi = nullptr; act.out_lo = nullptr;
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
                        shift, phase, bsel, stats, bw, act, 1, stream);
+}
+
+// Inference GEMM with BatchNorm folded into the operands (test.py scoring path, code/dmcnet/test.py:139-151):
+// out = act( A * B' + bias [+ residual] ) where B' = W * bn_scale (dmc_weight_fold_prep), bias = bn_shift,
+// act = LeakyReLU(slope) (0: ReLU, 1: none), residual = res_f32 [M][N] or res_hi/res_lo (bf16 planes) or
+// none.  The result goes to out_hi / out_lo (bf16 planes, the operand of the next GEMM) when given,
+// else to D (fp32).  Zero ring of width `ring` preserved.
+extern "C" int dmc_tc_tap_gemm_fold(const void* A_hi, const void* A_lo, int a_phases, long a_rows, int K,
+                                    const void* B_hi, const void* B_lo, int b_slices, int N, float* D, long M,
+                                    int Hp, int Wp, int ring, int ntaps, const int* shift, const int* phase,
+                                    const int* bsel, const float* bias, float slope, const float* res_f32,
+                                    const void* res_hi, const void* res_lo, void* out_hi, void* out_lo,
+                                    void* stream) {
+  DMC_REQUIRE(bias != nullptr, "tap_gemm_fold: bias is required");
+  DMC_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && (out_hi || D), "tap_gemm_fold: output");
+  DMC_REQUIRE((res_hi == nullptr) == (res_lo == nullptr) && !(res_f32 && res_hi), "tap_gemm_fold: residual");
+  BwFuse bw;
+  bw.Y = nullptr; bw.act_hi = nullptr; bw.gb = nullptr; bw.mean = nullptr; bw.invstd = nullptr;
+  bw.slope = 0.f;
+  ActFuse act;
+  act.bias = bias; act.mask = nullptr; act.slope = slope; act.frame_rows = (unsigned)(Hp * Wp);
+  act.res_f32 = res_f32; act.res_hi = (const bf16*)res_hi; act.res_lo = (const bf16*)res_lo;
+  act.out_hi = (bf16*)out_hi; act.out_lo = (bf16*)out_lo;
+  return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, N, Hp, Wp, ntaps,
+                       shift, phase, bsel, nullptr, bw, act, ring, stream);
 }
 
 // dW[bsel_t][Cout][Cin] += sum_q G[q][Cout] * X[phase_t][q + shift_t][Cin]   (caller zeroes dW).

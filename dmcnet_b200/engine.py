@@ -102,11 +102,12 @@ class _ConvBN:
         self.shift = torch.zeros(cout, **f32)
         self.mean = torch.zeros(cout, **f32)
         self.invstd = torch.ones(cout, **f32)
+        self.fbias = torch.zeros(cout, **f32)      # folded BatchNorm shift (eval-mode GEMM bias)
 
 
 class DmcEngine:
     # defaults for subclasses that build only the parameter table (tests/sim_engine.py)
-    gen_arch, gen_fusion, gen_ds, _arch_estimator, att = 'dense', None, 0, None, 0
+    gen_arch, gen_fusion, gen_ds, _arch_estimator, att, fold_bn = 'dense', None, 0, None, 0, True
 
     def __init__(self, num_class: int, num_segments: int, frames: int, *, gan: bool = False,
                  arch_d: Optional[str] = None, gen_flow_or_delta: int = 1, height: int = 224,
@@ -149,6 +150,10 @@ class DmcEngine:
         # The reference ignores --att for every other estimator's constructor but still unpacks two
         # outputs, so att is only meaningful with ContextNetwork
         self.att = int(att == 1 and self.gen_arch == 'context')
+        # eval-mode forwards (validate(), test.py scoring) fold BatchNorm into the conv operands: the GEMM
+        # epilogue adds the folded shift and the residual, applies the activation and writes the next
+        # GEMM's bf16 hi/lo operand directly -- no bn_apply pass, no fp32 conv output
+        self.fold_bn = True
         # grad_bf16=True: the backward GEMMs (data and weight gradients of the ResNet convs) read
         # the incoming gradient dY rounded to bf16 (2 MMAs per k-step, no dY_lo plane; weights and
         # saved activations keep the full hi/lo split).  Measured on B200: 5% faster step, but the
@@ -695,7 +700,9 @@ class DmcEngine:
         H, W = self.H, self.W
         if n != self.N:
             raise RuntimeError('engine was built for %d frames, got %d' % (self.N, n))
-        self._prep_weights()
+        folded = not train and self.fold_bn and self.gemm_engine == 'tc'
+        if not folded:
+            self._prep_weights()
         if train:
             ops.memset_zero(self._sums_pool[:self._sums_used])
         # stem: 7x7/2 conv (planar) -> BN -> ReLU -> maxpool -> pixel-major hi/lo
@@ -722,7 +729,9 @@ class DmcEngine:
         ops.stem_pool_fwd(self.stem_Y, st['scale'], st['shift'], n, 64, H2, W2, self.A0_hi, self.A0_lo,
                           self.pool_idx)
         x_hi, x_lo = self.A0_hi, self.A0_lo
-        for blk in self.blocks:
+        if folded:
+            x_hi, x_lo = self._cls_blocks_folded(x_hi, x_lo, n)
+        for blk in ([] if folded else self.blocks):
             c1, c2, geo = blk['c1'], blk['c2'], blk['geo']
             if 'ds' in blk:
                 gi = blk['geo_in']
@@ -749,6 +758,47 @@ class DmcEngine:
         ops.avgpool(x_hi, x_lo, n, gl.Hp, gl.Wp, 512, self.pooled)
         ops.linear_fwd(self.pooled, self.p('base_model.fc.weight'), self.p('base_model.fc.bias'), n,
                        512, self.num_class, self.logits)
+
+    def _fold_unit(self, u: _ConvBN):
+        """Eval-mode BatchNorm of unit u folded into its GEMM operand: W' = W * scale, bias = shift."""
+        wk = u.name_bn
+        ops.bn_eval_coeffs(self.p(wk + '.weight'), self.p(wk + '.bias'), self.buffers[wk + '.running_mean'],
+                           self.buffers[wk + '.running_var'], 1e-5, u.cout, u.scale, u.shift)
+        ops.weight_fold_prep(self.p(u.name_conv + '.weight'), u.scale, u.shift, u.cout, u.cin, u.taps, u.cout, u.cin,
+                             u.W_hi, u.W_lo, u.fbias)
+
+    def _conv_fold(self, u: _ConvBN, a_hi, a_lo, a_phases: int, slope: float, **out):
+        geo = u.geo
+        if u.ks == 1:
+            shift, phase, bsel = [0], [0], [0]
+        elif u.stride == 1:
+            shift, phase, bsel = _taps_s1(geo.Wp)
+        else:
+            shift, phase, bsel = _taps_s2(geo.Wp)
+        ops.tap_gemm_fold(a_hi, a_lo, u.W_hi, u.W_lo, a_phases=a_phases, a_rows=geo.P, K=u.cin, b_slices=u.taps,
+                          N=u.cout, M=geo.P, Hp=geo.Hp, Wp=geo.Wp, shift=shift, phase=phase, bsel=bsel,
+                          bias=u.fbias, slope=slope, **out)
+
+    def _cls_blocks_folded(self, x_hi, x_lo, n: int):
+        """The eight BasicBlocks in eval mode with BatchNorm folded: two (three) GEMMs per block, each
+        writing the hi/lo activation the next one reads; relu(bn2(conv2) + identity) in conv2's epilogue."""
+        for blk in self.blocks:
+            c1, c2 = blk['c1'], blk['c2']
+            self._fold_unit(c1)
+            self._fold_unit(c2)
+            if 'ds' in blk:
+                ds, gi = blk['ds'], blk['geo_in']
+                self._fold_unit(ds)
+                ops.phase_split(x_hi, x_lo, n, gi.H, gi.W, blk['cin'], blk['xp_hi'], blk['xp_lo'])
+                self._conv_fold(c1, blk['xp_hi'], blk['xp_lo'], 4, 0.0, out_hi=c1.act_hi, out_lo=c1.act_lo)
+                self._conv_fold(ds, blk['xp_hi'], blk['xp_lo'], 4, 1.0, D=ds.Y)
+                self._conv_fold(c2, c1.act_hi, c1.act_lo, 1, 0.0, res_f32=ds.Y, out_hi=c2.act_hi, out_lo=c2.act_lo)
+            else:
+                self._conv_fold(c1, x_hi, x_lo, 1, 0.0, out_hi=c1.act_hi, out_lo=c1.act_lo)
+                self._conv_fold(c2, c1.act_hi, c1.act_lo, 1, 0.0, res_hi=x_hi, res_lo=x_lo, out_hi=c2.act_hi,
+                                out_lo=c2.act_lo)
+            x_hi, x_lo = c2.act_hi, c2.act_lo
+        return x_hi, x_lo
 
     def _unit_bn_bwd(self, u: _ConvBN, g_a, g_b, act_hi, G_hi, G_lo, dz_out):
         geo, wk = u.geo, u.name_bn
@@ -1123,6 +1173,17 @@ class DmcEngine:
         """dilated Conv3x3(bias=False) -> BatchNorm2d(eps 1e-5) -> LeakyReLU (code/dmcnet/model.py:31-42)."""
         p, Np, Kp, R = L['name'], L['Np'], L['Kp'], self.ctx_ring
         Hp, Wp = self.ctx_geo
+        if not train and self.fold_bn:
+            # eval: BatchNorm folded into the operand, activation in the epilogue, hi/lo written directly
+            ops.pm_bn_finalize(None, L['cmap'], Np, L['cout'], count, self.p(p + '.1.weight'), self.p(p + '.1.bias'),
+                               self.buffers[p + '.1.running_mean'], self.buffers[p + '.1.running_var'], None,
+                               BN_MOMENTUM, 1e-5, L['scale'], L['shift_'], L['mean'], L['invstd'])
+            ops.weight_fold_prep(self.p(p + '.0.weight'), L['scale'], L['shift_'], L['cout'], L['cin'], 9, Np, Kp,
+                                 L['W_hi'], L['W_lo'], L['coef'].view(-1)[:Np])
+            ops.tap_gemm_fold(a_hi, a_lo, L['W_hi'], L['W_lo'], a_phases=1, a_rows=rows, K=Kp, b_slices=9, N=Np,
+                              M=rows, Hp=Hp, Wp=Wp, ring=R, shift=L['shift'], phase=[0] * 9, bsel=list(range(9)),
+                              bias=L['coef'].view(-1)[:Np], slope=L['slope'], out_hi=L['act_hi'], out_lo=L['act_lo'])
+            return
         ops.weight_gather_prep(self.p(p + '.0.weight'), L['gmap'], 9, Np, Kp, L['W_hi'], L['W_lo'], L['Wt_hi'],
                                L['Wt_lo'])
         ops.tap_gemm_ring(a_hi, a_lo, L['W_hi'], L['W_lo'], L['Y'], a_rows=rows, K=Kp, b_slices=9, N=Np,

@@ -527,3 +527,19 @@ def att_flow_loss_head(kind, gen, flow, att, numel, gscale, dgen, datt, loss_sum
     _call('dmc_att_flow_loss_head', c_int(kind), _ptr(gen, F32), _ptr(flow, F32), _ptr(att, F32), c_long(numel),
           c_float(gscale), _ptr(dgen, F32), c_long(fe), c_long(dgen_ns if dgen_ns is not None else fe),
           _ptr(datt, F32), _ptr(loss_sum, F64), _stream())
+
+
+# ---------------------------------------------------------------- inference with BatchNorm folded in
+def weight_fold_prep(w, scale, shift, Cout, Cin, T, Np, Kp, W_hi, W_lo, bias_out):
+    _call('dmc_weight_fold_prep', _ptr(w, F32), _ptr(scale, F32), _ptr(shift, F32), c_int(Cout), c_int(Cin),
+          c_int(T), c_int(Np), c_int(Kp), _ptr(W_hi, BF16), _ptr(W_lo, BF16), _ptr(bias_out, F32), _stream())
+
+
+def tap_gemm_fold(A_hi, A_lo, B_hi, B_lo, *, a_phases, a_rows, K, b_slices, N, M, Hp, Wp, shift, phase, bsel,
+                  bias, slope, ring=1, D=None, res_f32=None, res_hi=None, res_lo=None, out_hi=None, out_lo=None):
+    """out = LeakyReLU_slope(A * B + bias [+ residual]) -> bf16 hi/lo planes (or fp32 D); csrc/gemm_tc.cu."""
+    _call('dmc_tc_tap_gemm_fold', _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(a_phases), c_long(a_rows), c_int(K),
+          _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M), c_int(Hp),
+          c_int(Wp), c_int(ring), c_int(len(shift)), _iarr(shift), _iarr(phase), _iarr(bsel), _ptr(bias, F32),
+          c_float(slope), _ptr(res_f32, F32), _ptr(res_hi, BF16), _ptr(res_lo, BF16), _ptr(out_hi, BF16),
+          _ptr(out_lo, BF16), _stream())

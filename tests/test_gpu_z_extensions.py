@@ -566,3 +566,50 @@ def test_gan_step_with_downsampled_generator_routes_gradients_through_the_tiling
     og = ref.grads()
     errs = [rel2(eng.grad_view(k), og[k]) for k in eng.specs if k.startswith('gen_flow_model')]
     assert float(np.median(errs)) < 5e-2 and max(errs) < 1.2e-1, errs
+
+
+# ------------------------------------------------------------------ eval-mode BatchNorm folding
+@pytest.mark.parametrize('arch', ['DenseNetTiny', 'ContextNetwork'])
+def test_eval_forward_with_folded_batchnorm_matches_oracle_and_unfolded_path(arch):
+    """validate() / test.py forwards fold BatchNorm into the GEMM operands (W' = W * scale, shift and the
+    residual added in the epilogue, activation applied there, hi/lo written directly):
+    same outputs as the oracle's eval-mode forward and as the unfolded kernels, argmax exact."""
+    num_class, n = 51, 6
+    sd = O.build_state(num_class, None, seed=1, arch_estimator=arch)
+    g = torch.Generator().manual_seed(9)
+    for k in sd:                                   # non-trivial running statistics and affine parameters
+        if k.endswith('running_mean'):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.2
+        elif k.endswith('running_var'):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+        elif k.endswith(('bn1.weight', 'bn2.weight', 'downsample.1.weight')) or ('.1.weight' in k and 'context' in k):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+        elif k.endswith(('bn1.bias', 'bn2.bias', 'downsample.1.bias')) or ('.1.bias' in k and 'context' in k):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.2
+    flow, mv, res, target = O.make_inputs(2, 3, num_class, seed=0)
+    st = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        ref_logits, ref_gen = O.model_forward(st, mv, res, train=False, arch_estimator=arch)
+    outs = {}
+    for fold in (True, False):
+        eng = DmcEngine(num_class, 3, n, arch_estimator=arch)
+        eng.fold_bn = fold
+        eng.load_state(sd)
+        before = eng.state_dict()
+        logits, gen_flow = eng.forward(mv.cuda(), res.cuda(), train=False)
+        outs[fold] = (logits.clone(), gen_flow.clone())
+        assert rel(logits, ref_logits) < 1e-3 and rel(gen_flow, ref_gen) < 1e-3, fold
+        assert torch.equal(logits.view(2, 3, num_class).mean(1).argmax(1).cpu(),
+                           ref_logits.view(2, 3, num_class).mean(1).argmax(1))
+        after = eng.state_dict()
+        assert all(torch.equal(before[k], after[k]) for k in before)          # eval changes no state
+    assert rel(outs[True][0], outs[False][0]) < 1e-4
+    # ... and a train step after an eval forward still sees un-folded operands
+    eng = DmcEngine(num_class, 3, n, arch_estimator=arch)
+    eng.load_state(sd)
+    eng.forward(mv.cuda(), res.cuda(), train=False)
+    tr = FusedTrainStep(eng, HParams(), 2)
+    ref = O.OracleTrainer(sd, O.HParams(), arch_estimator=arch)
+    mo = ref.step(flow, mv, res, target, apply=False)
+    mg = tr.step(flow.cuda(), mv.cuda(), res.cuda(), target.cuda(), apply=False)
+    assert mg['loss'] == pytest.approx(mo['loss'], rel=1e-3)
