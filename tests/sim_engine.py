@@ -21,9 +21,18 @@ from oracle import dmc_oracle as O
 
 class SimEngine(DmcEngine):
     def __init__(self, num_class, num_segments, frames, *, gan=False, arch_d=None, gen_flow_or_delta=1,
-                 height=224, width=224, gen_growth=(8, 8, 6, 4, 2), share_from=None):
+                 height=224, width=224, gen_growth=(8, 8, 6, 4, 2), share_from=None, arch_estimator=None,
+                 att=0, gen_flow_ds_factor=0):
         self.device = torch.device('cpu')
         self._share_from = share_from
+        # generator selection, as DmcEngine.__init__ (parameter table only; the simulated forward below
+        # implements the dense family)
+        self._arch_estimator = arch_estimator
+        self.gen_arch = 'context' if arch_estimator == 'ContextNetwork' else 'dense'
+        self.gen_fusion = {'DenseNetTinyEarlyFusionSum': 'sum', 'DenseNetTinyEarlyFusionStack': 'stack'}.get(
+            arch_estimator or '')
+        self.gen_ds = int(gen_flow_ds_factor)
+        self.att = int(att == 1 and self.gen_arch == 'context')
         self.num_class, self.S, self.N = num_class, num_segments, frames
         self.gan, self.arch_d = gan, (arch_d if gan else None)
         self.gen_flow_or_delta = gen_flow_or_delta

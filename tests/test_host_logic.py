@@ -285,3 +285,24 @@ def test_dense_block_gradient_plan_matches_autograd(growth):
         dD[:, 2 + oo:2 + oo + gk] = d_pre
         ref = pre[k].grad
         assert float((d_pre - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), (growth, k)
+
+
+@pytest.mark.parametrize('arch,att,ds', [('DenseNetTiny', 0, 0), ('DenseNetSmall', 0, 0), ('DenseNet', 0, 4),
+                                         ('DenseNetTinyEarlyFusionSum', 0, 0), ('DenseNetTinyEarlyFusionStack', 0, 4),
+                                         ('ContextNetwork', 0, 0), ('ContextNetwork', 1, 0), ('ContextNetwork', 0, 4),
+                                         ('ContextNetwork', 1, 4)])
+def test_engine_parameter_table_matches_the_reference_state_dict_for_every_generator(arch, att, ds):
+    """Keys, order and shapes of the engine's parameter / buffer table against the state_dict the
+    oracle builds (itself bit-pinned on the reference constructors, oracle/pin_against_reference.py)."""
+    from sim_engine import SimEngine
+    from oracle import dmc_oracle as O
+    sd = O.build_state(11, 'Discriminator', seed=1, arch_estimator=arch, att=att, gen_flow_ds_factor=ds)
+    growth = O.DENSE_GROWTH.get(arch, O.GEN_TINY_GROWTH)
+    eng = SimEngine(11, 3, 3, gan=True, arch_d='Discriminator', height=32, width=32, gen_growth=growth,
+                    arch_estimator=arch, att=att, gen_flow_ds_factor=ds)
+    keys = eng.state_keys()
+    want = [k for k in sd if not k.startswith('discriminator.adv_layer')]       # fc_in depends on the frame size
+    assert [k for k in keys if not k.startswith('discriminator.adv_layer')] == want
+    for k in want:
+        shp = eng.specs[k] if k in eng.specs else tuple(eng.buffers[k].shape)
+        assert tuple(shp) == tuple(sd[k].shape), k
