@@ -31,6 +31,20 @@ struct TapTable {
   int bsel[MAX_TAPS];    // which weight slice
 };
 
+// "Row window" schedule of a K = 64 tap GEMM: taps whose row shifts differ by a few rows (the three
+// columns of one kernel row) read almost the same 128 activation rows, so the producer loads ONE
+// window of 136 rows per group and the MMAs of each tap start their A descriptor `rowoff` rows into
+// it (a SWIZZLE_128B descriptor may start at any 128-byte row of a 1024-byte aligned tile):
+// the L2 -> shared traffic of the A operand, which bounds 64-channel layers, drops ~3x.
+static constexpr int RW_GROUPS = 8, RW_GT = 3, RW_ROWS = 136;
+struct RwTable {
+  int ngroups;
+  int gshift[RW_GROUPS];          // window start = m0 + gshift
+  int gcount[RW_GROUPS];          // taps in the group (<= RW_GT)
+  int rowoff[RW_GROUPS][RW_GT];   // tap's first row inside the window (0 .. RW_ROWS - 128)
+  int bsel[RW_GROUPS][RW_GT];
+};
+
 // ------------------------------------------------------------------ tensor maps
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
@@ -141,25 +155,26 @@ struct ActFuse {
   bf16* out_lo;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RW = false>
 struct TapGemmWsSmem {
-  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int A_BYTES = (RW ? RW_ROWS : 128) * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + (RW ? RW_GT : 1) * 2 * B_BYTES;
   static constexpr int EPI_PITCH = 36;                         // floats; STS.128 conflict-free
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
   static constexpr int RED_BYTES = 4 * 2 * BN * 4;             // per-warp column sums (BN statistics)
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + RED_BYTES + 1024 + 256;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RW = false>
 __global__ void __launch_bounds__(192, 1)
 tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
-                   const BwFuse bw, int a_lo_on, const ActFuse act, int ring) {
-  using S = TapGemmWsSmem<BN, STAGES>;
+                   const BwFuse bw, int a_lo_on, const ActFuse act, int ring,
+                   const __grid_constant__ RwTable rw) {
+  using S = TapGemmWsSmem<BN, STAGES, RW>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -174,7 +189,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / 64;
-  const int iters = taps.ntaps * kblocks;
+  const int iters = RW ? rw.ngroups : taps.ntaps * kblocks;     // pipeline stages per tile
   const int total_tiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
@@ -207,9 +222,23 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         for (int i = 0; i < iters; ++i, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const int t = i / kblocks, kb = i - t * kblocks;
           const uint32_t full = bar_full + 8 * s;
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
+          if constexpr (RW) {
+            // one 136-row window of A (hi [+ lo]) and the weight tiles of the group's taps
+            const int cnt = rw.gcount[i];
+            mbar_expect_tx(full, (uint32_t)((a_lo_on ? 2 : 1) * S::A_BYTES + cnt * 2 * S::B_BYTES));
+            const int row = (int)(m0 + rw.gshift[i]);
+            tma_load_3d(st, &mapAh, full, 0, row, 0);
+            if (a_lo_on) tma_load_3d(st + S::A_BYTES, &mapAl, full, 0, row, 0);
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t bt = st + 2 * S::A_BYTES + j * 2 * S::B_BYTES;
+              tma_load_3d(bt, &mapBh, full, 0, n0, rw.bsel[i][j]);
+              tma_load_3d(bt + S::B_BYTES, &mapBl, full, 0, n0, rw.bsel[i][j]);
+            }
+            continue;
+          }
+          const int t = i / kblocks, kb = i - t * kblocks;
           mbar_expect_tx(full, a_lo_on ? S::STAGE_BYTES : S::STAGE_BYTES - S::A_BYTES);
           const int row = (int)(m0 + taps.shift[t]);
           tma_load_3d(st, &mapAh, full, kb * 64, row, taps.phase[t]);
@@ -233,6 +262,26 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
+          if constexpr (RW) {
+            const int cnt = rw.gcount[i];
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t a0 = st + (uint32_t)rw.rowoff[i][j] * 128u;
+              const uint32_t bt = st + 2 * S::A_BYTES + j * 2 * S::B_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = umma_desc_sw128(a0 + ks * 32, 16, 1024);
+                const uint64_t al = umma_desc_sw128(a0 + S::A_BYTES + ks * 32, 16, 1024);
+                const uint64_t bh = umma_desc_sw128(bt + ks * 32, 16, 1024);
+                const uint64_t bl = umma_desc_sw128(bt + S::B_BYTES + ks * 32, 16, 1024);
+                const uint32_t first = (uint32_t)((i | j | ks) != 0);
+                if (a_lo_on) umma_bf16(acc, al, bh, idesc, first);
+                umma_bf16(acc, ah, bl, idesc, a_lo_on ? 1u : first);
+                umma_bf16(acc, ah, bh, idesc, 1);
+              }
+            }
+            umma_commit(bar_empty + 8 * s);
+            continue;
+          }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ah = umma_desc_sw128(st + ks * 32, 16, 1024);
@@ -462,14 +511,14 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RW = false>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
                               const BwFuse& bw, int a_lo_on, const ActFuse& act, int ring,
-                              cudaStream_t stream) {
-  using S = TapGemmWsSmem<BN, STAGES>;
-  auto kern = tap_gemm_ws_kernel<BN, STAGES>;
+                              cudaStream_t stream, const RwTable* rw = nullptr) {
+  using S = TapGemmWsSmem<BN, STAGES, RW>;
+  auto kern = tap_gemm_ws_kernel<BN, STAGES, RW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
@@ -480,9 +529,42 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(N, BN);
   long grid = (long)tiles_m * tiles_n;
   if (grid > sms) grid = sms;
+  RwTable none;
+  none.ngroups = 0;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
-                                                  tiles_m, tiles_n, stats, bw, a_lo_on, act, ring);
+                                                  tiles_m, tiles_n, stats, bw, a_lo_on, act, ring,
+                                                  rw ? *rw : none);
   return dmc_check_launch("tap_gemm_ws_kernel");
+}
+
+// Groups the taps of a K = 64, single-phase tap GEMM into row windows (see RwTable); false when the tap
+// set does not fit (more than RW_GROUPS groups).
+static bool build_row_windows(const TapTable& tt, RwTable& rw) {
+  int order[MAX_TAPS];
+  for (int i = 0; i < tt.ntaps; ++i) order[i] = i;
+  for (int i = 1; i < tt.ntaps; ++i)                      // insertion sort by shift
+    for (int j = i; j > 0 && tt.shift[order[j]] < tt.shift[order[j - 1]]; --j) {
+      const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+    }
+  rw.ngroups = 0;
+  for (int g = 0; g < RW_GROUPS; ++g) {
+    rw.gshift[g] = 0; rw.gcount[g] = 0;
+    for (int j = 0; j < RW_GT; ++j) { rw.rowoff[g][j] = 0; rw.bsel[g][j] = 0; }
+  }
+  int i = 0;
+  while (i < tt.ntaps) {
+    if (rw.ngroups == RW_GROUPS) return false;
+    const int g = rw.ngroups++;
+    const int base = tt.shift[order[i]];
+    rw.gshift[g] = base;
+    while (i < tt.ntaps && rw.gcount[g] < RW_GT && tt.shift[order[i]] - base <= RW_ROWS - 128) {
+      const int j = rw.gcount[g]++;
+      rw.rowoff[g][j] = tt.shift[order[i]] - base;
+      rw.bsel[g][j] = tt.bsel[order[i]];
+      ++i;
+    }
+  }
+  return true;
 }
 
 // ------------------------------------------------------------------ wgrad (split-K, tap groups)
@@ -993,8 +1075,21 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
   const int sms = sm_count();
   if (BN == 128)
     return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
-  if (BN == 64)
+  if (BN == 64) {
+    // K = 64 layers are bounded by the L2 -> shared traffic of the A operand: row-window schedule
+    static const bool rw_off = getenv("DMC_NO_ROW_WINDOW") != nullptr;
+    RwTable rw;
+    bool single_phase = a_phases == 1;
+    for (int i = 0; i < ntaps; ++i) single_phase = single_phase && phase[i] == 0;
+    if (!rw_off && K == 64 && single_phase && ntaps >= 2 && build_row_windows(tt, rw)) {
+      CUtensorMap wAh, wAl;
+      if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS))) return rc;
+      if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS))) return rc;
+      return launch_tap_gemm_ws<64, 2, true>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
+                                             a_lo_on, act, ring, st, &rw);
+    }
     return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
+  }
   return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
 }
 
