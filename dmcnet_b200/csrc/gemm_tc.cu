@@ -175,7 +175,12 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const BwFuse bw, int a_lo_on, const ActFuse act, int ring,
                    const __grid_constant__ RwTable rw) {
   using S = TapGemmWsSmem<BN, STAGES, RW>;
-  constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+  // Two accumulators of 2*BN columns each: columns [0, BN) collect hi*hi + lo*hi, columns [BN, 2BN) the
+  // hi*lo term, because A_hi is multiplied with the STACKED operand [B_hi ; B_lo] (adjacent in the stage) in
+  // ONE N = 2*BN MMA: two MMAs per k-step instead of three, and 20 KB instead of 24 KB of shared-memory
+  // operand reads per k-step of a 128-wide tile (the MMA unit's limiter here).  The epilogue adds the halves.
+  constexpr uint32_t ACC_COLS = 2 * BN;
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -250,13 +255,14 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);            // A_lo * B_hi            -> columns [0, BN)
+      const uint32_t idesc2 = umma_idesc_bf16(2 * BN, 0, 0);       // A_hi * [B_hi ; B_lo]   -> columns [0, 2BN)
       uint32_t it = 0, j = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
         const uint32_t a = j & 1, aph = (j >> 1) & 1;
         mbar_wait(bar_tempty + 8 * a, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t acc = tmem_d + a * BN;
+        const uint32_t acc = tmem_d + a * ACC_COLS;
         for (int i = 0; i < iters; ++i, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
@@ -271,12 +277,9 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ah = umma_desc_sw128(a0 + ks * 32, 16, 1024);
                 const uint64_t al = umma_desc_sw128(a0 + S::A_BYTES + ks * 32, 16, 1024);
-                const uint64_t bh = umma_desc_sw128(bt + ks * 32, 16, 1024);
-                const uint64_t bl = umma_desc_sw128(bt + S::B_BYTES + ks * 32, 16, 1024);
-                const uint32_t first = (uint32_t)((i | j | ks) != 0);
-                if (a_lo_on) umma_bf16(acc, al, bh, idesc, first);
-                umma_bf16(acc, ah, bl, idesc, a_lo_on ? 1u : first);
-                umma_bf16(acc, ah, bh, idesc, 1);
+                const uint64_t bh = umma_desc_sw128(bt + ks * 32, 16, 1024);     // B_lo follows B_hi in the stage
+                umma_bf16(acc, ah, bh, idesc2, (uint32_t)((i | j | ks) != 0));
+                if (a_lo_on) umma_bf16(acc, al, bh, idesc, 1);
               }
             }
             umma_commit(bar_empty + 8 * s);
@@ -286,11 +289,9 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ah = umma_desc_sw128(st + ks * 32, 16, 1024);
             const uint64_t al = umma_desc_sw128(st + S::A_BYTES + ks * 32, 16, 1024);
-            const uint64_t bh = umma_desc_sw128(st + 2 * S::A_BYTES + ks * 32, 16, 1024);
-            const uint64_t bl = umma_desc_sw128(st + 2 * S::A_BYTES + S::B_BYTES + ks * 32, 16, 1024);
-            if (a_lo_on) umma_bf16(acc, al, bh, idesc, (i | ks) != 0);
-            umma_bf16(acc, ah, bl, idesc, a_lo_on ? 1u : (uint32_t)((i | ks) != 0));
-            umma_bf16(acc, ah, bh, idesc, 1);
+            const uint64_t bh = umma_desc_sw128(st + 2 * S::A_BYTES + ks * 32, 16, 1024);   // [B_hi ; B_lo]
+            umma_bf16(acc, ah, bh, idesc2, (uint32_t)((i | ks) != 0));
+            if (a_lo_on) umma_bf16(acc, al, bh, idesc, 1);
           }
           umma_commit(bar_empty + 8 * s);
         }
@@ -364,9 +365,12 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = ci * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_d + a * BN + ((uint32_t)(wq * 32) << 16) + c, r);
+        uint32_t r[32], r2[32];
+        tmem_ld32(tmem_d + a * ACC_COLS + ((uint32_t)(wq * 32) << 16) + c, r);
+        tmem_ld32(tmem_d + a * ACC_COLS + ((uint32_t)(wq * 32) << 16) + BN + c, r2);
         tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
         if (ci == NCH - 1) {                      // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
