@@ -582,8 +582,12 @@ struct WgradSmem {
   static constexpr int X_BYTES = (BN / 64) * BOX_BYTES;   // one tap, one plane
   static constexpr int STAGE_BYTES = 2 * G_BYTES + TG * 2 * X_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr uint32_t TMEM_COLS = (TG * BN) <= 32 ? 32 : (TG * BN) <= 64 ? 64 : (TG * BN) <= 128 ? 128
-                                        : (TG * BN) <= 256 ? 256 : 512;
+  // STACK: G_hi is multiplied with the stacked operand [X_hi | X_lo] (adjacent boxes of the stage) in one
+  // N = 2*BN MMA, as in tap_gemm_ws_kernel; needs 2*BN accumulator columns per tap
+  static constexpr bool STACK = TG * 2 * BN <= 512;
+  static constexpr int ACC = STACK ? 2 * BN : BN;
+  static constexpr uint32_t TMEM_COLS = (TG * ACC) <= 32 ? 32 : (TG * ACC) <= 64 ? 64 : (TG * ACC) <= 128 ? 128
+                                        : (TG * ACC) <= 256 ? 256 : 512;
 };
 
 template <int BN, int TG, int BKP, int STAGES>
@@ -594,7 +598,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
                   long P, int kb_per_split, int n_tiles, int oihw_taps, int g_lo_on,
                   float* __restrict__ ws) {
   using S = WgradSmem<BN, TG, BKP, STAGES>;
-  static_assert(TG * BN <= 512, "tap group does not fit TMEM");
+  static_assert(TG * S::ACC <= 512, "tap group does not fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES;
@@ -663,6 +667,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
     }
   } else if (warp == 1 && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(BN, 1, 1);
+    const uint32_t idesc2 = umma_idesc_bf16(2 * BN, 1, 1);
     for (int i = 0; i < iters; ++i) {
       const int s = i % STAGES;
       mbar_wait(bar_base + 8 * s, (i / STAGES) & 1);
@@ -670,17 +675,23 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
       const uint32_t st = smem_base + s * S::STAGE_BYTES;
       for (int g = 0; g < nt_g; ++g) {
         const uint32_t xs = st + 2 * S::G_BYTES + g * 2 * S::X_BYTES;
-        const uint32_t acc = tmem_d + g * BN;
+        const uint32_t acc = tmem_d + g * S::ACC;
 #pragma unroll
         for (int ks = 0; ks < BKP / 16; ++ks) {   // 16 pixels per MMA = two 8-row swizzle atoms
           const uint32_t koff = ks * 2048;
           const uint64_t gh = umma_desc_sw128(st + koff, S::BOX_BYTES, 1024);
           const uint64_t gl = umma_desc_sw128(st + S::G_BYTES + koff, S::BOX_BYTES, 1024);
           const uint64_t xh = umma_desc_sw128(xs + koff, S::BOX_BYTES, 1024);
-          const uint64_t xl = umma_desc_sw128(xs + S::X_BYTES + koff, S::BOX_BYTES, 1024);
-          if (g_lo_on) umma_bf16(acc, gl, xh, idesc, (i | ks) != 0);
-          umma_bf16(acc, gh, xl, idesc, g_lo_on ? 1u : (uint32_t)((i | ks) != 0));
-          umma_bf16(acc, gh, xh, idesc, 1);
+          if constexpr (S::STACK) {
+            // G_hi * [X_hi | X_lo] (the lo boxes follow the hi boxes at the same box pitch), then G_lo * X_hi
+            umma_bf16(acc, gh, xh, idesc2, (uint32_t)((i | ks) != 0));
+            if (g_lo_on) umma_bf16(acc, gl, xh, idesc, 1);
+          } else {
+            const uint64_t xl = umma_desc_sw128(xs + S::X_BYTES + koff, S::BOX_BYTES, 1024);
+            if (g_lo_on) umma_bf16(acc, gl, xh, idesc, (i | ks) != 0);
+            umma_bf16(acc, gh, xl, idesc, g_lo_on ? 1u : (uint32_t)((i | ks) != 0));
+            umma_bf16(acc, gh, xh, idesc, 1);
+          }
         }
       }
       umma_commit(bar_base + 8 * (STAGES + s));
@@ -702,7 +713,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * BN + c, r);
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * S::ACC + c, r);
+        if constexpr (S::STACK) {
+          uint32_t r2[32];
+          tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * S::ACC + BN + c, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+        }
         tmem_ld_wait();
         if (co < Cout) {
 #pragma unroll
@@ -723,7 +741,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
-      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * BN + c, r);
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * S::ACC + c, r);
+      if constexpr (S::STACK) {
+        uint32_t r2[32];
+        tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + g * S::ACC + BN + c, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + __uint_as_float(r2[k]));
+      }
       tmem_ld_wait();
       if (co < Cout) {
 #pragma unroll
