@@ -126,7 +126,7 @@ def test_context_network_eval_forward_and_gan_g_step():
             errs = [rel2(eng.grad_view(k), og[k]) for k in eng.specs if k.startswith('gen_flow_model')]
             print('ContextNetwork G-step generator gradient error: median %.3e worst %.3e'
                   % (float(np.median(errs)), max(errs)))
-            assert float(np.median(errs)) < 8e-2 and max(errs) < 1.5e-1, errs
+            assert float(np.median(errs)) < 6e-2 and max(errs) < 1e-1, errs          # measured 3.1e-2 / 3.5e-2
 
 
 def test_dropin_model_with_reference_default_generator_runs():

@@ -8,15 +8,14 @@ Tolerances
   * generator and discriminator gradients in steps where no classifier gradient
     flows into them: 1e-4 relative (they are plain fp32 kernels);
   * everything downstream of the ResNet-18 backward: the gradient is a
-    discontinuous function of the forward activations (ReLU / max-pool switches
-    times BatchNorm's mean-subtraction over tiny test batches), so ANY forward that
-    is not bit-identical -- ours carries ~1e-5 relative error from the bf16x3
-    tensor-core split -- moves a handful of switches and changes per-tensor
-    gradients by ~1e-2 in L2.  oracle-side evidence: rounding the oracle's own
-    activations to 2^-17 reproduces the same 1.3e-2 (DESIGN.md "Parity").  The
-    bar used here is per-tensor relative L2 <= 1.2e-1 and a median <= 5e-2 (measured: worst
-    6.6e-2, medians 1.5e-2 .. 3.1e-2), with the
-    kernels themselves checked to 1e-5 on identical inputs in test_gpu_kernels.py.
+    discontinuous function of the forward activations (ReLU / max-pool switches), so ANY forward
+    that is not bit-identical moves a fraction of the switches.  tests/test_grad_sensitivity.py
+    measures this on the ORACLE itself: one fp32 ulp of operand noise moves its per-tensor
+    gradients by 5e-3, the 2^-17 rounding of the bf16 hi/lo split by 1.2e-2 (1.6e-2 worst), at
+    every batch size; tests/test_gpu_backward_exact.py shows the product's backward agrees with
+    autograd to 5e-5 once the forward state is identical.  The bar used here is per-tensor
+    relative L2: median <= 3e-2, worst <= 6e-2 (measured on B200 at B = 1 / 2: medians
+    5e-3 .. 1.9e-2, worst 3.1e-2; round 1 used 5e-2 / 1.2e-1).
 """
 import os
 
@@ -89,12 +88,12 @@ def _check_grads(ref, eng, groups, tight_groups=(), tight_tol=1e-4):
         if any(k.startswith(g) for g in tight_groups):
             assert e < tight_tol, (k, e)
         else:
-            assert e < 1.2e-1, (k, e)
+            assert e < 6e-2, (k, e)
             l2.append(e)
     if l2:
-        print('MARGIN end-to-end gradient rel L2: median %.3e (bar 5e-2) worst %.3e (bar 1.2e-1) over %d tensors'
+        print('MARGIN end-to-end gradient rel L2: median %.3e (bar 3e-2) worst %.3e (bar 6e-2) over %d tensors'
               % (float(np.median(l2)), max(l2), len(l2)))
-        assert float(np.median(l2)) < 5e-2
+        assert float(np.median(l2)) < 3e-2
 
 
 def test_dmcnet_two_train_steps_vs_oracle():
