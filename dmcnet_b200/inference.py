@@ -135,7 +135,8 @@ class VideoScorer:
     def __init__(self, state: Dict[str, torch.Tensor], num_class: int, test_segments: int = 25,
                  test_crops: int = 10, *, gen_flow_or_delta: int = 1, height: int = 224,
                  width: int = 224, max_frames_per_launch: Optional[int] = None,
-                 arch_d: Optional[str] = None, device: Optional[torch.device] = None):
+                 arch_d: Optional[str] = None, device: Optional[torch.device] = None,
+                 arch_estimator: str = 'DenseNetTiny', att: int = 0, gen_flow_ds_factor: int = 0):
         from .engine import DmcEngine
         self.num_class = num_class
         self.arch_d = arch_d
@@ -144,9 +145,13 @@ class VideoScorer:
         self.per_launch, self.launches = plan_launches(self.frames, max_frames_per_launch)
         # arch_d: also run the discriminator on the generated map (code/dmcnet_GAN/test.py:91,
         # validity [frames, 2] per video); the class scores do not depend on it
+        # --arch_estimator / --att / --gen_flow_ds_factor of test.py (test_options mirrors train_options)
+        from .model import DENSE_GROWTH
         self.eng = DmcEngine(num_class, test_segments, self.per_launch, gan=arch_d is not None,
                              arch_d=arch_d, gen_flow_or_delta=gen_flow_or_delta, height=height,
-                             width=width, device=device)
+                             width=width, device=device, arch_estimator=arch_estimator, att=att,
+                             gen_flow_ds_factor=gen_flow_ds_factor,
+                             gen_growth=DENSE_GROWTH.get(arch_estimator, DENSE_GROWTH['DenseNetTiny']))
         # num_batches_tracked is absent from torch < 0.4.1 checkpoints (the reference's, README.md:28)
         missing = [k for k in list(self.eng.specs) + list(self.eng.buffers)
                    if k not in state and not k.endswith('.num_batches_tracked')]
