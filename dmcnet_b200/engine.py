@@ -1373,7 +1373,6 @@ class DmcEngine:
         if max_xp:
             self.d_dxp = torch.zeros(max_xp, **f32)
         self.d_wgrad_ws = torch.empty(max_ws, **f32)
-        self.d_in = torch.zeros(M, 2, H, W, **f32)
         self.validity = torch.zeros(M, 2, **f32)
         self.d_validity = torch.zeros(M, 2, **f32)
 
@@ -1394,7 +1393,8 @@ class DmcEngine:
         whose epilogue applies bias + LeakyReLU(0.2) + Dropout2d and accumulates the statistics of the
         BatchNorm2d(eps 0.8) that follows (code/dmcnet_GAN/model.py:254-279)."""
         H, W = self.H, self.W
-        ops.planar_to_s2d4(x.view(-1), 2 * H * W, H, W, m, self.d_s4_hi, self.d_s4_lo)
+        if x is not None:          # planar input; None = the caller already filled the space-to-depth operand
+            ops.planar_to_s2d4(x.view(-1), 2 * H * W, H, W, m, self.d_s4_hi, self.d_s4_lo)
         if train:
             ops.memset_zero(self._dsums)
         for li, L in enumerate(self.d_layers):
@@ -1514,18 +1514,23 @@ class DmcEngine:
         if not self.gan:
             return (self.logits[:n], self.gen_flow[:n]) + extra
         HW2 = 2 * H * W
-        ops.copy_planar(self.gen_flow, HW2, self.d_in.view(-1), HW2, HW2, n)     # "first fake then real"
-        m = n
-        if input_flow is not None:
-            flow = input_flow.reshape(-1, 2, H, W)
-            ops.copy_planar(flow, HW2, self.d_in.view(-1)[n * HW2:], HW2, HW2, n)
-            m = 2 * n
+        m = n if input_flow is None else 2 * n
+        flow = None if input_flow is None else input_flow.reshape(-1, 2, H, W)
         self._use_masks = bool(train and use_dropout)
         if self._use_masks and not (isinstance(masks, str) and masks == 'preloaded'):
             self.set_masks(masks if masks is not None else self.draw_dropout_masks(m), m)
         if self.disc_engine == 'tc':
-            self._disc_forward_tc(self.d_in, m, train, self._use_masks)
+            # "first fake then real" (GAN/model.py:546-548): the two halves are converted straight into
+            # the 4x4 space-to-depth operand, no planar concatenation
+            rows = n * ops.padded(H // 4) * ops.padded(W // 4)
+            ops.planar_to_s2d4(self.gen_flow.view(-1), HW2, H, W, n, self.d_s4_hi, self.d_s4_lo)
+            if flow is not None:
+                ops.planar_to_s2d4(flow, HW2, H, W, n, self.d_s4_hi[rows:], self.d_s4_lo[rows:])
+            self._disc_forward_tc(None, m, train, self._use_masks)
         else:
+            ops.copy_planar(self.gen_flow, HW2, self.d_in.view(-1), HW2, HW2, n)
+            if flow is not None:
+                ops.copy_planar(flow, HW2, self.d_in.view(-1)[n * HW2:], HW2, HW2, n)
             self._disc_forward(self.d_in, m, train, self._use_masks)
         self._m = m
         return (self.logits[:n], self.validity[:m], self.gen_flow[:n]) + extra

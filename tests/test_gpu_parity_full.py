@@ -86,7 +86,7 @@ def _grad_errors(ref, eng, prefix):
             if k.startswith(prefix) and float(og[k].abs().max()) > 0}
 
 
-def _disc_grads_fp64(ref, eng, arch_d, masks, n):
+def _disc_grads_fp64(ref, eng, arch_d, masks, n, ref_flow):
     """d(lr_adv_d * CE(validity, [fake, real]))/d(discriminator parameters) from the oracle's
     functions evaluated in float64 on the D input the product saw (first fake, then real)."""
     import torch.nn.functional as F
@@ -96,7 +96,7 @@ def _disc_grads_fp64(ref, eng, arch_d, masks, n):
         if k.startswith('discriminator'):
             t = v.double() if v.is_floating_point() else v.clone()
             st[k] = t.requires_grad_(True) if (v.is_floating_point() and not O.is_buffer(k)) else t
-    x = eng.d_in.detach().double().cpu()                 # [fake (generated) | real] as the product staged it
+    x = torch.cat((eng.gen_flow.detach(), ref_flow.reshape(-1, 2, eng.H, eng.W).cuda()), 0).double().cpu()   # [fake | real]
     validity = O.disc_forward(st, x, arch_d, True, [m.double() for m in masks])
     tgt = torch.cat((torch.zeros(n, dtype=torch.int64), torch.ones(n, dtype=torch.int64)))
     (F.cross_entropy(validity, tgt) * O.HParams().lr_adv_d).backward()
@@ -146,7 +146,7 @@ def test_config3_b64_gan_d_and_g_step_vs_oracle():
             # sums 1.2 M fp32 terms per channel), and the tensor-core plan carries 4e-3 .. 5e-3 there
             # (2^-17 operand rounding amplified by block_3's BatchNorm backward; tests/test_gpu_disc_tc.py)
             assert max(d.values()) < 1e-2, d
-            d64 = _disc_grads_fp64(ref, eng, arch_d, masks, B * 3)
+            d64 = _disc_grads_fp64(ref, eng, arch_d, masks, B * 3, flow)
             e64 = {k: rel2(eng.grad_view(k), d64[k]) for k in d64}
             assert max(e64.values()) < 1e-2, e64
             rec['D'] = {'forward': errs, 'disc_grad_worst_vs_fp32_oracle': max(d.values()),
