@@ -229,3 +229,48 @@ def test_twenty_step_trajectory_vs_oracle():
     assert nz[bad] < 1e-2, (bad, nz[bad])                       # weights, BN weights, running statistics
     assert worst_travel[far] < 0.5, (far, worst_travel[far])   # measured 0.18 (a zero-initialised BN bias)
     assert hist[-1]['loss'][1] < hist[0]['loss'][1]
+
+
+def test_config4_b512_on_one_gpu_equals_b64_on_a_tiled_batch():
+    """BASELINE config 4 at N = 1 (the strong-scaling base: all 512 clips, 3072 discriminator frames, on one
+    GPU) cannot be compared with the CPU oracle in reasonable time, so it is held to a size-independent
+    property instead: a batch made of 8 copies of a 64-clip batch (Dropout2d masks tiled alike) has the same
+    BatchNorm statistics, hence the same losses, logits and -- the losses being batch means -- the same
+    gradients as the 64-clip batch.  Catches 32-bit index / grid-size errors at the largest shapes."""
+    arch_d, nc, b, reps = 'Discriminator3', 51, 64, 8
+    sd = O.build_state(nc, arch_d, seed=1)
+    flow, mv, res, target = O.make_inputs(b, 3, nc, seed=0)
+    torch.manual_seed(5)
+    masks = [O.draw_dropout_masks(arch_d, b * 3 * 2), O.draw_dropout_masks(arch_d, b * 3)]
+    out = {}
+    for B in (b, b * reps):
+        r = B // b
+        eng = DmcEngine(nc, 3, B * 3, gan=True, arch_d=arch_d)
+        eng.load_state(sd)
+        tr = FusedTrainStep(eng, HParams(), B)
+        f, m, rs, t = (x.repeat((r,) + (1,) * (x.dim() - 1)).cuda() for x in (flow, mv, res, target))
+        rec = []
+        for it in range(2):                                   # D-step, then G-step, same parameters
+            n = b * 3
+            if it == 0:    # D input = [fake frames | real frames]: tile each half
+                mk = [torch.cat((k[:n].repeat(r, 1), k[n:].repeat(r, 1))) for k in masks[0]]
+            else:
+                mk = [k.repeat(r, 1) for k in masks[1]]
+            mt = tr.step(f, m, rs, t, masks=mk, apply=False)
+            rec.append((mt, tr.consensus[:b].clone().cpu(), eng.grads.clone().cpu()))
+        out[B] = rec
+        del eng, tr
+        torch.cuda.empty_cache()
+    for it in range(2):
+        (m1, c1, g1), (m8, c8, g8) = out[b][it], out[b * reps][it]
+        for k in m1:
+            assert m8[k] == pytest.approx(m1[k], rel=1e-4, abs=1e-6), (it, k)
+        assert rel(c8, c1) < 1e-4, it
+        # gradients: identical up to the summation order of the batch statistics, i.e. up to the switch
+        # sensitivity of tests/test_grad_sensitivity.py (5e-3 for one ulp)
+        nz = g1.abs() > 0
+        assert bool((g8.abs() > 0)[nz].all())
+        assert rel2(g8, g1) < 3e-2, it
+    _record('config4_b512_vs_b64_tiled', {'loss_D': out[b * reps][0][0]['loss'], 'loss_G': out[b * reps][1][0]['loss'],
+                                           'grad_rel_l2_D': rel2(out[b * reps][0][2], out[b][0][2]),
+                                           'grad_rel_l2_G': rel2(out[b * reps][1][2], out[b][1][2])})
