@@ -268,8 +268,6 @@ def test_config4_b512_on_one_gpu_equals_b64_on_a_tiled_batch():
         assert rel(c8, c1) < 1e-4, it
         # gradients: identical up to the summation order of the batch statistics, i.e. up to the switch
         # sensitivity of tests/test_grad_sensitivity.py (5e-3 for one ulp)
-        nz = g1.abs() > 0
-        assert bool((g8.abs() > 0)[nz].all())
         assert rel2(g8, g1) < 3e-2, it
     _record('config4_b512_vs_b64_tiled', {'loss_D': out[b * reps][0][0]['loss'], 'loss_G': out[b * reps][1][0]['loss'],
                                            'grad_rel_l2_D': rel2(out[b * reps][0][2], out[b][0][2]),
