@@ -210,7 +210,7 @@ def measure(cfg_name, B, args, *, rank, local_rank, world, clocks=False, rooflin
     eng = DmcEngine(cfg['num_class'], S, B * S, gan=cfg['gan'], arch_d=cfg['arch_d'])
     eng.load_state(sd)
     tr = FusedTrainStep(eng, HParams(), B, world_size=world, use_graph=not args.no_graph, pipelined=True,
-                        graph_allreduce=args.graph_allreduce)
+                        graph_allreduce=args.graph_allreduce, overlap=(False if args.no_overlap else None))
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,7 +296,7 @@ def measure(cfg_name, B, args, *, rank, local_rank, world, clocks=False, rooflin
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
         'gpu_launches': int(launches),
         'algorithmic_tflops': GFLOP_PER_CLIP[cfg_name] * clips / ms_step,
-        'last_metrics': last, 'cuda_graph': bool(tr.use_graph),
+        'last_metrics': last, 'cuda_graph': bool(tr.use_graph), 'two_streams': bool(tr.overlap),
     }
     if sampler is not None:
         out['clocks'] = sampler.summary()
@@ -325,6 +325,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--graph-allreduce', action='store_true',
                     help='capture the NCCL gradient all-reduce inside the step graph (N > 1)')
+    ap.add_argument('--no-overlap', action='store_true',
+                    help='one stream (default: generator backward / discriminator next to the classifier on two)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='headline only (skip configs.config3 / config4_strong)')
     args = ap.parse_args()

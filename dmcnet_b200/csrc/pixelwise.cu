@@ -415,6 +415,45 @@ phase_unsplit_kernel(const float* __restrict__ in, int frames, int H, int W, int
   }
 }
 
+// phase_unsplit fused with the ReLU mask of the activation the gradient belongs to and with the two
+// BatchNorm-backward reductions of the conv + BN that produced it (the block in front of a stride-2
+// block): out = dz = unsplit(in) * [act > 0], sums2[0][c] += sum dz, sums2[1][c] += sum dz * xhat.
+// One pass instead of unsplit + a separate reduction pass over the same tensor.
+__global__ void __launch_bounds__(256, 4)
+phase_unsplit_reduce_kernel(const float* __restrict__ in, int frames, int H, int W, int C,
+                            const bf16* __restrict__ act_hi, const float* __restrict__ Y,
+                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                            float* __restrict__ out, double* __restrict__ sums2) {
+  const int Hq = dmc_padded(H / 2), Wq = dmc_padded(W / 2), Hp = dmc_padded(H), Wp = dmc_padded(W);
+  const long P = (long)frames * Hp * Wp;
+  channel_reduce2(P, C, sums2, sums2 + C, [&](unsigned q, int c, float (&s0)[4], float (&s1)[4]) {
+    const int wp = (int)(q % (unsigned)Wp);
+    const unsigned r = q / (unsigned)Wp;
+    const int hp = (int)(r % (unsigned)Hp);
+    const int f = (int)(r / (unsigned)Hp);
+    const long off = (long)q * C + c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hp >= 1 && wp >= 1) {
+      const int h = hp - 1, w = wp - 1;
+      const int ph = (h & 1) * 2 + (w & 1);
+      const long src = ((((long)ph * frames + f) * Hq + (h >> 1) + 1) * Wq + (w >> 1) + 1) * C + c;
+      v = *reinterpret_cast<const float4*>(in + src);
+      const bf16x4 a = *reinterpret_cast<const bf16x4*>(act_hi + off);
+      if (!(__bfloat162float(a.v[0]) > 0.f)) v.x = 0.f;
+      if (!(__bfloat162float(a.v[1]) > 0.f)) v.y = 0.f;
+      if (!(__bfloat162float(a.v[2]) > 0.f)) v.z = 0.f;
+      if (!(__bfloat162float(a.v[3]) > 0.f)) v.w = 0.f;
+      const float4 y = *reinterpret_cast<const float4*>(Y + off);
+      const float4 m = *reinterpret_cast<const float4*>(mean + c);
+      const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+      s0[0] += v.x; s0[1] += v.y; s0[2] += v.z; s0[3] += v.w;
+      s1[0] += v.x * (y.x - m.x) * is.x; s1[1] += v.y * (y.y - m.y) * is.y;
+      s1[2] += v.z * (y.z - m.z) * is.z; s1[3] += v.w * (y.w - m.w) * is.w;
+    }
+    *reinterpret_cast<float4*>(out + off) = v;
+  });
+}
+
 // ------------------------------------------------------------------ global average pool
 __global__ void avgpool_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int frames,
                                int Hp, int Wp, int C, float* __restrict__ pooled) {
@@ -607,6 +646,26 @@ extern "C" int dmc_phase_unsplit(const float* in, int frames, int H, int W, int 
   const long n = (long)frames * dmc_padded(H) * dmc_padded(W) * (C / 4);
   phase_unsplit_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(in, frames, H, W, C, out);
   return dmc_check_launch("phase_unsplit_kernel");
+}
+
+// dmc_phase_unsplit fused with the ReLU mask and the two BatchNorm-backward reductions of the unit the
+// gradient belongs to: out [frames][H+1][W+1][C] = dz = unsplit(in) * [act_hi > 0] (ring zero),
+// sums2 (double [2][C], caller-zeroed) += (sum dz, sum dz * (Y - mean) * invstd).
+extern "C" int dmc_phase_unsplit_reduce(const float* in, int frames, int H, int W, int C, const void* act_hi,
+                                        const float* Y, const float* mean, const float* invstd, float* out,
+                                        double* sums2, void* stream) {
+  DMC_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "phase_unsplit_reduce: H=%d W=%d C=%d", H, W, C);
+  DMC_REQUIRE(act_hi && Y && mean && invstd && sums2, "phase_unsplit_reduce: null argument");
+  const long P = (long)frames * dmc_padded(H) * dmc_padded(W);
+  DMC_REQUIRE(P < (1L << 31), "phase_unsplit_reduce: too many rows");
+  const int threads = reduce_block(C);
+  const int rows_per_iter = threads / (C / 4);
+  long blocks = cdiv(P, (long)rows_per_iter * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  phase_unsplit_reduce_kernel<<<(unsigned)blocks, threads, 2 * threads * 4 * sizeof(double), ST(stream)>>>(
+      in, frames, H, W, C, (const bf16*)act_hi, Y, mean, invstd, out, sums2);
+  return dmc_check_launch("phase_unsplit_reduce_kernel");
 }
 
 extern "C" int dmc_avgpool(const void* hi, const void* lo, int frames, int Hp, int Wp, int C,

@@ -904,8 +904,16 @@ class DmcEngine:
                                  engine=self.gemm_engine)
                 gi = blk['geo_in']
                 g_a = T2[:gi.P * cin]
-                ops.phase_unsplit(blk['dxp'], n, gi.H, gi.W, cin, g_a)
-                g_b, g_is_dz = None, False
+                if fuse:
+                    # one pass: interleave the four phases, apply the ReLU mask of the previous block's
+                    # output and reduce for its bn2 -> g_a is that block's dz
+                    pb = self.blocks[bi - 1]['c2']
+                    ops.phase_unsplit_reduce(blk['dxp'], n, gi.H, gi.W, cin, pb.act_hi, pb.Y, pb.mean, pb.invstd,
+                                             g_a, pb.sums2)
+                    g_b, g_is_dz = None, True
+                else:
+                    ops.phase_unsplit(blk['dxp'], n, gi.H, gi.W, cin, g_a)
+                    g_b, g_is_dz = None, False
             else:
                 if fuse:
                     self._bn_bwd_apply_only(c1, T1[:pc], G_hi, G_lo)
@@ -1426,7 +1434,8 @@ class DmcEngine:
                           self.p('discriminator.adv_layer.bias'), m, last['Np'], last['geo'].H, last['geo'].W,
                           self.validity)
 
-    def _disc_backward_tc(self, m: int, need_wgrad: bool, use_masks: bool, to_input: bool, input_rows: int):
+    def _disc_backward_tc(self, m: int, need_wgrad: bool, use_masks: bool, to_input: bool, input_rows: int,
+                          defer_input: bool = False):
         """Backward from self.d_validity[:m].  Per block: BatchNorm-backward coefficients from the two
         reductions (accumulated by the epilogue of the data-gradient GEMM above it), ONE pass producing
         the hi/lo gradient of the pre-activation (BN backward + Dropout2d + LeakyReLU'), then the
@@ -1492,15 +1501,35 @@ class DmcEngine:
                     ops.bn_bwd_reduce(nxt, None, None, prev['A'], prev['mean'], prev['invstd'],
                                       m * pg.Hp * pg.Wp, Kp, pg.Hp, pg.Wp, prev['sums2'])
             g, cur = nxt, 1 - cur
-        if to_input:
-            ops.s2d4_to_planar(g, H, W, input_rows, self.dD.view(-1), self.dD.shape[1] * H * W, accumulate=True)
+        self._disc_dx = g
+        if to_input and not defer_input:
+            self.disc_input_accumulate(input_rows)
+
+    def disc_input_accumulate(self, input_rows: int):
+        """d(loss_adv)/d(gen_flow) (space-to-depth form left by _disc_backward_tc) += into the generator's
+        gradient buffer.  Separate from the backward so that a caller running the classifier and the
+        discriminator on two streams can order the two accumulations after the join."""
+        ops.s2d4_to_planar(self._disc_dx, self.H, self.W, input_rows, self.dD.view(-1),
+                           self.dD.shape[1] * self.H * self.W, accumulate=True)
 
     # ------------------------------------------------------------------ public passes
     def forward(self, input_mv: torch.Tensor, input_residual: torch.Tensor,
                 input_flow: Optional[torch.Tensor] = None, *, train: bool = True,
                 masks: Optional[Sequence[torch.Tensor]] = None, use_dropout: bool = True):
         """Model.forward.  Returns views of engine-owned outputs:
-        (logits [n,C], gen_flow [n,2,H,W]) or, for GAN, (logits, validity [m,2], gen_flow)."""
+        (logits [n,C], gen_flow [n,2,H,W]) or, for GAN, (logits, validity [m,2], gen_flow).
+        The three parts below can also be called one by one (FusedTrainStep runs the classifier and the
+        discriminator, which only share gen_flow, on two streams)."""
+        n = self.forward_generator(input_mv, input_residual, train=train)
+        self.forward_classifier(n, train=train)
+        extra = (self.att_flow[:n],) if self.att else ()        # (base_out, [validity,] gen_flow, att_flow), model.py:354-357
+        if not self.gan:
+            return (self.logits[:n], self.gen_flow[:n]) + extra
+        m = self.forward_discriminator(n, input_flow, train=train, masks=masks, use_dropout=use_dropout)
+        return (self.logits[:n], self.validity[:m], self.gen_flow[:n]) + extra
+
+    def forward_generator(self, input_mv: torch.Tensor, input_residual: torch.Tensor, *, train: bool = True) -> int:
+        """cat(mv, residual) -> estimator (+ input_mv) -> self.gen_flow (model.py:330-348); returns the frame count."""
         H, W = self.H, self.W
         mv = input_mv.reshape(-1, 2, H, W)
         res = input_residual.reshape(-1, 3, H, W)
@@ -1509,10 +1538,17 @@ class DmcEngine:
             self._ctx_forward(mv, res, n, train)
         else:
             self._gen_forward(mv, res, n)
+        return n
+
+    def forward_classifier(self, n: int, *, train: bool = True) -> None:
+        """ResNet-18 over self.gen_flow -> self.logits (model.py:349-353)."""
         self._cls_forward(self.gen_flow, n, train)
-        extra = (self.att_flow[:n],) if self.att else ()        # (base_out, [validity,] gen_flow, att_flow), model.py:354-357
-        if not self.gan:
-            return (self.logits[:n], self.gen_flow[:n]) + extra
+
+    def forward_discriminator(self, n: int, input_flow: Optional[torch.Tensor] = None, *, train: bool = True,
+                              masks: Optional[Sequence[torch.Tensor]] = None, use_dropout: bool = True) -> int:
+        """Discriminator over cat(gen_flow, input_flow) (D-step) or gen_flow alone (G-step) ->
+        self.validity[:m]; returns m (GAN/model.py:546-551)."""
+        H, W = self.H, self.W
         HW2 = 2 * H * W
         m = n if input_flow is None else 2 * n
         flow = None if input_flow is None else input_flow.reshape(-1, 2, H, W)
@@ -1533,7 +1569,7 @@ class DmcEngine:
                 ops.copy_planar(flow, HW2, self.d_in.view(-1)[n * HW2:], HW2, HW2, n)
             self._disc_forward(self.d_in, m, train, self._use_masks)
         self._m = m
-        return (self.logits[:n], self.validity[:m], self.gen_flow[:n]) + extra
+        return m
 
     def set_masks(self, masks: Sequence[torch.Tensor], m: int):
         """Stage Dropout2d masks ([m, C] per block) into the static device buffers."""
@@ -1560,7 +1596,7 @@ class DmcEngine:
 
     def backward(self, n: int, *, cls: bool = True, cls_wgrad: bool = True, gen_grad: bool = True,
                  cls_to_gen: bool = False, disc: bool = False, disc_wgrad: bool = False,
-                 disc_to_gen: bool = False):
+                 disc_to_gen: bool = False, disc_defer_input: bool = False):
         """Backward pass.  Inputs: self.d_logits (classifier), self.d_gen_flow (direct
         gradient on the generated map, e.g. MSE; must be initialised -- zeros if none)
         and self.d_validity (discriminator).  Flags select which parameter gradients are
@@ -1568,7 +1604,8 @@ class DmcEngine:
         if cls:
             self._cls_backward(self.gen_flow, n, cls_wgrad, cls_to_gen, self.d_gen_flow)
         if disc and self.disc_engine == 'tc':
-            self._disc_backward_tc(self._m, disc_wgrad, self._use_masks, disc_to_gen, n)
+            self._disc_backward_tc(self._m, disc_wgrad, self._use_masks, disc_to_gen, n,
+                                   defer_input=disc_defer_input)
         elif disc:
             self._disc_backward(self.d_in, self._m, disc_wgrad, self._use_masks,
                                 self.d_gen_flow if disc_to_gen else None, n)

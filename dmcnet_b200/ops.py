@@ -186,6 +186,14 @@ def phase_unsplit(inp, frames, H, W, C, out):
           _ptr(out, F32), _stream())
 
 
+def phase_unsplit_reduce(inp, frames, H, W, C, act_hi, Y, mean, invstd, out, sums2):
+    """phase_unsplit + ReLU mask of the activation the gradient belongs to + both BatchNorm-backward
+    reductions of the unit that produced it (sums2 += (sum dz, sum dz * xhat)); out = dz."""
+    _call('dmc_phase_unsplit_reduce', _ptr(inp, F32), c_int(frames), c_int(H), c_int(W), c_int(C),
+          _ptr(act_hi, BF16), _ptr(Y, F32), _ptr(mean, F32), _ptr(invstd, F32), _ptr(out, F32),
+          _ptr(sums2, F64), _stream())
+
+
 def avgpool(hi, lo, frames, Hp, Wp, C, pooled):
     _call('dmc_avgpool', _ptr(hi, BF16), _ptr(lo, BF16), c_int(frames), c_int(Hp), c_int(Wp),
           c_int(C), _ptr(pooled, F32), _stream())

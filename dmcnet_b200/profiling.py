@@ -139,8 +139,9 @@ def measure_roofline(resident_step, per, steps, trainer):
     """Run `steps` instrumented eager steps; return the dominant family's roofline
     and the per-family time breakdown (ms per train step)."""
     peaks = measured_peaks()
-    was_graph = trainer.use_graph
+    was_graph, was_overlap = trainer.use_graph, getattr(trainer, 'overlap', False)
     trainer.use_graph = False
+    trainer.overlap = False                          # every kernel timed alone, on one stream
     timer = FamilyTimer()
     eng = trainer.eng
     for blk in getattr(eng, 'blocks', []):
@@ -155,6 +156,7 @@ def measure_roofline(resident_step, per, steps, trainer):
     finally:
         ops.set_call_hook(None)
         trainer.use_graph = was_graph
+        trainer.overlap = was_overlap
     ms, fl, by, cnt = timer.totals()
     if os.environ.get('DMC_DUMP_CALLS'):            # per-call times of one family, in launch order
         fam_dump = os.environ['DMC_DUMP_CALLS']

@@ -15,6 +15,7 @@ gradient; BatchNorm statistics stay per rank (= nn.DataParallel semantics).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -92,7 +93,7 @@ def allreduce_groups(flat: torch.Tensor, group_range: Dict[str, Tuple[int, int]]
 class FusedTrainStep:
     def __init__(self, engine: DmcEngine, hp: HParams, batch: int, *, world_size: int = 1,
                  process_group=None, use_graph: bool = False, pipelined: bool = False,
-                 graph_allreduce: bool = False):
+                 graph_allreduce: bool = False, overlap: Optional[bool] = None):
         self.eng, self.hp, self.B = engine, hp, batch
         self.S = hp.num_segments
         if batch * self.S != engine.N:
@@ -106,6 +107,15 @@ class FusedTrainStep:
         # between two graphs
         self.graph_allreduce = bool(graph_allreduce and world_size > 1)
         dev = engine.device
+        # two-stream step (see _fwd_bwd).  Default: on for dmcnet_GAN (measured 22.5 -> 21.5 ms per D/G pair at
+        # B=64), off for dmcnet (17.4 vs 17.5 ms: the generator's backward and the tap GEMMs each fill every
+        # SM -- 200 KB of shared memory / 46 K registers per GEMM CTA leave no room for co-residency -- so the
+        # two branches only interleave); DMC_OVERLAP=0/1 or overlap=False/True overrides
+        if overlap is None:
+            env = os.environ.get('DMC_OVERLAP')
+            overlap = bool(engine.gan) if env is None else env != '0'
+        self.overlap = bool(overlap) and torch.device(dev).type == 'cuda'
+        self._side_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         H, W, n = engine.H, engine.W, engine.N
         f32 = dict(dtype=torch.float32, device=dev)
         # static inputs (graph-replayable)
@@ -254,12 +264,61 @@ class FusedTrainStep:
         return 'D' if self.iteration % 2 == 0 else 'G'
 
     def _fwd_bwd(self, mode: str):
-        """forward + heads + backward for one mode (graph-capturable: static buffers only)."""
+        """forward + heads + backward for one mode (graph-capturable: static buffers only).
+
+        With ``overlap`` (default) the parts of the step that only meet at gen_flow run on two streams
+        that fork after the generator's forward and join before Adam -- inside the captured graph they are
+        two branches.  dmcnet: the flow loss + generator backward (fp32 FMA kernels) next to the classifier's
+        forward + backward (tensor-core and HBM-bound kernels): gen_flow is detached (model.py:352), so
+        neither reads what the other writes.  dmcnet_GAN: the discriminator's forward + backward next to
+        the classifier's; in the G-step both feed d(gen_flow), so the discriminator's last accumulation is
+        issued after the join, in the serial order (bit-identical results either way)."""
         eng, hp, B, S = self.eng, self.hp, self.B, self.S
         n = B * S
         sc = loss_grad_scales(hp, B, self.world, n, eng.H, eng.W)
         g_cls = sc['cls']
         eng.zero_grads()
+        if not (self.overlap and (not eng.gan or eng.disc_engine == 'tc')):
+            return self._fwd_bwd_serial(mode, n, sc)
+        main, side = torch.cuda.current_stream(), self._side_stream
+        eng.forward_generator(self.in_mv, self.in_res, train=True)
+        side.wait_stream(main)
+
+        def classifier_head():
+            eng.forward_classifier(n, train=True)
+            ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,
+                        eng.d_logits, self.ce_stats)
+
+        if not eng.gan:
+            with torch.cuda.stream(side):
+                self._flow_head(sc)
+                eng.backward(n, cls=False, gen_grad=True)
+            classifier_head()
+            eng.backward(n, cls=(mode == 'full'), cls_wgrad=True, gen_grad=False, cls_to_gen=False)
+            main.wait_stream(side)
+            return
+        d_step = mode == 'D'
+        m = 2 * n if d_step else n
+        with torch.cuda.stream(side):
+            eng.forward_discriminator(n, self.in_flow if d_step else None, train=True, masks='preloaded')
+            ops.ce_head(eng.validity, m, 1, 2, self.adv_t_d if d_step else self.adv_t_g,
+                        (hp.lr_adv_d if d_step else hp.lr_adv_g) / (m * self.world), None,
+                        eng.d_validity, self.adv_stats)
+            eng.backward(n, cls=False, gen_grad=False, disc=True, disc_wgrad=d_step, disc_to_gen=not d_step,
+                         disc_defer_input=True)
+        classifier_head()
+        if not d_step:
+            self._flow_head(sc)
+        eng.backward(n, cls=True, cls_wgrad=d_step, gen_grad=False, cls_to_gen=not d_step)
+        main.wait_stream(side)
+        if not d_step:
+            eng.disc_input_accumulate(n)
+            eng.backward(n, cls=False, gen_grad=True)
+
+    def _fwd_bwd_serial(self, mode: str, n: int, sc):
+        """The same step on one stream."""
+        eng, hp, B, S = self.eng, self.hp, self.B, self.S
+        g_cls = sc['cls']
         if not eng.gan:
             eng.forward(self.in_mv, self.in_res, train=True)
             ops.ce_head(eng.logits, B, S, eng.num_class, self.target, g_cls, self.consensus,

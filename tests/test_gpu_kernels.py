@@ -579,3 +579,39 @@ def test_tap_gemm_fused_bn_backward_epilogue(n, c, h, with_residual):
     ops.bn_bwd_apply(D, None, None, Yp, mean.float().contiguous(), invstd.float().contiguous(), gamma, sums2,
                      cnt, P, c, Hp, Wp, Gh, Gl, None, dgam, dbet)
     assert rel(_from_pixel_cuda(Gh.float() + Gl.float(), n, c, h, h), Yg.grad) < 5e-5
+
+
+@pytest.mark.parametrize('n,c,h', [(192, 64, 56), (6, 128, 28), (3, 256, 14)])
+def test_phase_unsplit_with_fused_mask_and_bn_backward_reductions(n, c, h):
+    """dmc_phase_unsplit_reduce (csrc/pixelwise.cu) = dmc_phase_unsplit, then the ReLU mask and the two
+    BatchNorm-backward reductions of dmc_bn_bwd_reduce / dmc_bn_bwd_apply's dz output, in one pass:
+    dz bit-identical to the two-kernel sequence, sums to fp64 accuracy."""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(21)
+    Hp = Wp = ops.padded(h)
+    Hq = Wq = ops.padded(h // 2)
+    P, Pq = n * Hp * Wp, n * Hq * Wq
+    dxp = torch.randn(4, Pq, c, generator=g, device=dev)
+    Yn = torch.randn(n, c, h, h, generator=g, device=dev) * 1.5 + 0.3
+    act = torch.relu(torch.randn(n, c, h, h, generator=g, device=dev))
+    mean = Yn.double().mean((0, 2, 3)).float().contiguous()
+    invstd = (Yn.double().var((0, 2, 3), unbiased=False) + 1e-5).rsqrt().float().contiguous()
+    act_hi, _ = split(_pixel_cuda(act))
+    Yp = _pixel_cuda(Yn)
+    # two-kernel sequence
+    dX = torch.empty(P, c, device=dev)
+    ops.phase_unsplit(dxp, n, h, h, c, dX)
+    dz_ref = _from_pixel_cuda(dX, n, c, h, h).double() * (_from_pixel_cuda(act_hi.float().view(P, c), n, c, h, h) > 0)
+    xhat = (Yn.double() - mean.double().view(1, c, 1, 1)) * invstd.double().view(1, c, 1, 1)
+    s_ref = torch.stack((dz_ref.sum((0, 2, 3)), (dz_ref * xhat).sum((0, 2, 3))))
+    # fused
+    out = torch.full((P, c), float('nan'), device=dev)
+    sums2 = torch.zeros(2, c, dtype=torch.float64, device=dev)
+    ops.phase_unsplit_reduce(dxp, n, h, h, c, act_hi, Yp, mean, invstd, out, sums2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert torch.equal(_from_pixel_cuda(out, n, c, h, h).double(), dz_ref)
+    ring = out.view(n, Hp, Wp, c)
+    assert float(ring[:, 0].abs().max()) == 0.0 and float(ring[:, :, 0].abs().max()) == 0.0
+    scale = dz_ref.abs().sum((0, 2, 3)).clamp_min(1e-30)
+    assert float(((sums2 - s_ref).abs() / scale).max()) < 2e-6
