@@ -210,23 +210,34 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int n, int a_mn_major, int b
 #define DMC_PAD_HI 0
 __host__ __device__ inline int dmc_padded(int h) { return h + 1 + DMC_PAD_HI; }
 __host__ __device__ inline int dmc_unpadded(int hp) { return hp - 1 - DMC_PAD_HI; }
+// 3-D maps (I3D, code/dmcnet_I3D/network/i3d.py): [clips][T+1][H+1][W+1][C] with the same shared zero ring
+// on the low side of EVERY dimension.  The kernels below keep their (Hp, Wp) signature: the padded
+// temporal extent travels in the high half of Hp (Hp_arg = Hp | Tp << 16, dmc_pack_hp), and a row is
+// interior when its (t, h, w) are all >= 1.  Tp = 0 (every 2-D caller) costs one uniform branch.
+__host__ __device__ inline int dmc_pack_hp(int Hp, int Tp) { return Hp | (Tp << 16); }
 __host__ __device__ inline bool interior(long q, int Hp, int Wp) {
   // q < 2^31 for every tensor this library builds: 32-bit unsigned division is ~5x cheaper
-  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp;
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu, ut = (unsigned)Hp >> 16;
   const unsigned row = uq / uw;
   const unsigned wp = uq - row * uw;
-  const unsigned hp = row % uh;
-  return wp >= 1u && wp + DMC_PAD_HI < uw && hp >= 1u && hp + DMC_PAD_HI < uh;
+  const unsigned fr = row / uh;
+  const unsigned hp = row - fr * uh;
+  bool ok = wp >= 1u && wp + DMC_PAD_HI < uw && hp >= 1u && hp + DMC_PAD_HI < uh;
+  if (ut) ok = ok && (fr % ut) >= 1u;
+  return ok;
 }
 
 // Same layout with a zero ring of R rows / columns (dilated convolutions: R >= dilation), pixel (h, w)
 // at (h + R, w + R); R = 1 is `interior` above.
 __host__ __device__ inline bool interior_r(long q, int Hp, int Wp, int R) {
-  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp;
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu, ut = (unsigned)Hp >> 16;
   const unsigned row = uq / uw;
   const unsigned wp = uq - row * uw;
-  const unsigned hp = row % uh;
-  return wp >= (unsigned)R && hp >= (unsigned)R;
+  const unsigned fr = row / uh;
+  const unsigned hp = row - fr * uh;
+  bool ok = wp >= (unsigned)R && hp >= (unsigned)R;
+  if (ut) ok = ok && (fr % ut) >= (unsigned)R;
+  return ok;
 }
 
 // i -> (i / d, i % d) for 32-bit i; shift/mask when d is a power of two (channel counts)

@@ -23,7 +23,7 @@
 
 namespace dmc {
 
-static constexpr int MAX_TAPS = 16;
+static constexpr int MAX_TAPS = 27;      // 3 x 3 x 3 (I3D)
 struct TapTable {
   int ntaps;
   int shift[MAX_TAPS];   // row shift applied to the A operand
@@ -62,15 +62,19 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][box1][64], SWIZZLE_128B.
+// pitch (elements, 0 = d0): row pitch of the tensor, so that a column sub-range [c0, c0 + d0) of a wider
+// [d1][pitch] matrix is an operand (base = its first element; the inception branches of I3D read and write
+// slices of the concatenated maps).
 static int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                       uint32_t box0, uint32_t box1) {
+                       uint32_t box0, uint32_t box1, uint64_t pitch = 0) {
+  if (pitch == 0) pitch = d0;
   auto enc = get_encode();
   if (!enc) {
     dmc_set_error("cuTensorMapEncodeTiled entry point not available");
     return DMC_ERR_CUDA;
   }
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * sizeof(bf16), d0 * d1 * sizeof(bf16)};
+  cuuint64_t strides[2] = {pitch * sizeof(bf16), pitch * d1 * sizeof(bf16)};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
@@ -173,7 +177,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
                    const BwFuse bw, int a_lo_on, const ActFuse act, int ring,
-                   const __grid_constant__ RwTable rw) {
+                   const __grid_constant__ RwTable rw, int stats_ld) {
   using S = TapGemmWsSmem<BN, STAGES, RW>;
   // Two accumulators of 2*BN columns each: columns [0, BN) collect hi*hi + lo*hi, columns [BN, 2BN) the
   // hi*lo term, because A_hi is multiplied with the STACKED operand [B_hi ; B_lo] (adjacent in the stage) in
@@ -345,7 +349,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       for (int c = wq * 32 + lane; c < 2 * BN; c += 128) {
         const float v = red[c] + red[2 * BN + c] + red[4 * BN + c] + red[6 * BN + c];
         const int col = c < BN ? c : c - BN;
-        if (n0f + col < N) atomicAdd(stats + (c < BN ? 0 : N) + n0f + col, (double)v);
+        if (n0f + col < N) atomicAdd(stats + (c < BN ? 0 : stats_ld) + n0f + col, (double)v);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -445,8 +449,12 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
               const int row = i * 4 + (lane >> 3);
               const long gq = m0 + wq * 32 + row;
               if (gq < M) {
-                const float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
+                float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
                 const long o = gq * (long)ldD + n0 + c + c4;
+                if (bw.gb) {          // plain data gradient + a second gradient source (no mask, no reduction)
+                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(bw.gb + o));
+                  v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w;
+                }
                 if (act.out_hi) {
                   bf16 hh[4], ll[4];
                   split_bf16(v.x, hh[0], ll[0]); split_bf16(v.y, hh[1], ll[1]);
@@ -520,7 +528,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
                               const BwFuse& bw, int a_lo_on, const ActFuse& act, int ring,
-                              cudaStream_t stream, const RwTable* rw = nullptr) {
+                              cudaStream_t stream, const RwTable* rw = nullptr, int stats_ld = 0) {
   using S = TapGemmWsSmem<BN, STAGES, RW>;
   auto kern = tap_gemm_ws_kernel<BN, STAGES, RW>;
   static bool attr_set = false;
@@ -537,7 +545,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   none.ngroups = 0;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
                                                   tiles_m, tiles_n, stats, bw, a_lo_on, act, ring,
-                                                  rw ? *rw : none);
+                                                  rw ? *rw : none, stats_ld > 0 ? stats_ld : N);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
@@ -966,15 +974,16 @@ static void wgrad_plan(int BN, int BKP, int Cout, int Cin, int ntaps, long P, in
 template <int BN, int TG, int BKP, int STAGES>
 static int launch_wgrad(const void* G_hi, const void* G_lo, const void* X_hi, const void* X_lo,
                         int x_phases, const TapTable& taps, float* dW, int Cout, int Cin, long P,
-                        int sm_count, int oihw_taps, float* ws, long ws_floats, cudaStream_t stream) {
+                        int sm_count, int oihw_taps, float* ws, long ws_floats, cudaStream_t stream,
+                        int ldg = 0, int ldx = 0) {
   using S = WgradSmem<BN, TG, BKP, STAGES>;
   CUtensorMap mGh, mGl, mXh, mXl;
   int rc;
-  if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mGh, G_hi, Cout, P, 1, 64, BKP, ldg))) return rc;
   const int g_lo_on = G_lo != nullptr;     // G_lo == NULL: dY is used at bf16 precision
-  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, Cout, P, 1, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, Cout, P, 1, 64, BKP, ldg))) return rc;
+  if ((rc = make_map_3d(&mXh, X_hi, Cin, P, x_phases, 64, BKP, ldx))) return rc;
+  if ((rc = make_map_3d(&mXl, X_lo, Cin, P, x_phases, 64, BKP, ldx))) return rc;
   auto kern = wgrad_gemm_kernel<BN, TG, BKP, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1014,15 +1023,16 @@ static void wgrad64_plan(int BKP, long P, int sm_count, long* kb_per_split, long
 template <int BKP, int STAGES>
 static int launch_wgrad64(const void* G_hi, const void* G_lo, const void* X_hi, const void* X_lo,
                           int x_phases, const TapTable& taps, float* dW, long P, int sm_count,
-                          int oihw_taps, float* ws, long ws_floats, cudaStream_t stream) {
+                          int oihw_taps, float* ws, long ws_floats, cudaStream_t stream, int ldg = 0,
+                          int ldx = 0) {
   using S = Wgrad64Smem<BKP, STAGES>;
   CUtensorMap mGh, mGl, mXh, mXl;
   int rc;
   const int g_lo_on = G_lo != nullptr;
-  if ((rc = make_map_3d(&mGh, G_hi, 64, P, 1, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, 64, P, 1, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mXh, X_hi, 64, P, x_phases, 64, BKP))) return rc;
-  if ((rc = make_map_3d(&mXl, X_lo, 64, P, x_phases, 64, BKP))) return rc;
+  if ((rc = make_map_3d(&mGh, G_hi, 64, P, 1, 64, BKP, ldg))) return rc;
+  if ((rc = make_map_3d(&mGl, g_lo_on ? G_lo : G_hi, 64, P, 1, 64, BKP, ldg))) return rc;
+  if ((rc = make_map_3d(&mXh, X_hi, 64, P, x_phases, 64, BKP, ldx))) return rc;
+  if ((rc = make_map_3d(&mXl, X_lo, 64, P, x_phases, 64, BKP, ldx))) return rc;
   auto kern = wgrad64_kernel<BKP, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1077,10 +1087,14 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
                          const void* B_hi, const void* B_lo, int b_slices, int N, float* D, long M,
                          int ldD, int Hp, int Wp, int ntaps, const int* shift, const int* phase,
                          const int* bsel, double* stats, const BwFuse& bw, const ActFuse& act, int ring,
-                         void* stream) {
-  DMC_REQUIRE(ring >= 1 && (Hp == 0 || (ring < Hp && ring < Wp)), "tap_gemm: ring=%d", ring);
-  DMC_REQUIRE(bw.Y == nullptr || (stats && bw.mean && bw.invstd && ldD == N),
-              "tap_gemm: fused BN backward needs stats, mean, invstd and ldD == N");
+                         void* stream, int lda = 0, int stats_ld = 0) {
+  DMC_REQUIRE(ring >= 1 && (Hp == 0 || (ring < (Hp & 0xffff) && ring < Wp)), "tap_gemm: ring=%d", ring);
+  // fused BN backward: Y / act_hi / gb are addressed like D (row pitch ldD); with ldD > N every pointer,
+  // mean / invstd and stats included, is the caller's column sub-range of a wider map
+  DMC_REQUIRE(bw.Y == nullptr || (stats && bw.mean && bw.invstd && (ldD == N || stats_ld >= N)),
+              "tap_gemm: fused BN backward needs stats, mean, invstd and ldD == N (or an explicit stats_ld)");
+  DMC_REQUIRE(lda == 0 || (lda >= K && lda % 8 == 0 && a_phases == 1), "tap_gemm: lda=%d", lda);
+  DMC_REQUIRE(stats_ld == 0 || stats_ld >= N, "tap_gemm: stats_ld=%d", stats_ld);
   DMC_REQUIRE(act.bias == nullptr || (bw.Y == nullptr && Hp > 0 && Wp > 0 && ldD == N),
               "tap_gemm: fused activation needs a frame geometry, ldD == N and no BN-backward fusion");
   DMC_REQUIRE(K > 0 && K % 64 == 0, "tap_gemm: K=%d must be a positive multiple of 64", K);
@@ -1095,15 +1109,16 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
   const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, 128))) return rc;
+  if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, 128, lda))) return rc;
   const int a_lo_on = A_lo != nullptr;     // A_lo == NULL: A is used at bf16 precision (two MMAs per k-step)
-  if ((rc = make_map_3d(&mAl, a_lo_on ? A_lo : A_hi, K, a_rows, a_phases, 64, 128))) return rc;
+  if ((rc = make_map_3d(&mAl, a_lo_on ? A_lo : A_hi, K, a_rows, a_phases, 64, 128, lda))) return rc;
   if ((rc = make_map_3d(&mBh, B_hi, K, N, b_slices, 64, BN))) return rc;
   if ((rc = make_map_3d(&mBl, B_lo, K, N, b_slices, 64, BN))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (BN == 128)
-    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
+    return launch_tap_gemm_ws<128, 3>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st,
+                                      nullptr, stats_ld);
   if (BN == 64) {
     // K = 64 layers are bounded by the L2 -> shared traffic of the A operand: row-window schedule
     static const bool rw_off = getenv("DMC_NO_ROW_WINDOW") != nullptr;
@@ -1112,14 +1127,16 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
     for (int i = 0; i < ntaps; ++i) single_phase = single_phase && phase[i] == 0;
     if (!rw_off && K == 64 && single_phase && ntaps >= 2 && build_row_windows(tt, rw)) {
       CUtensorMap wAh, wAl;
-      if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS))) return rc;
-      if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS))) return rc;
+      if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
+      if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
       return launch_tap_gemm_ws<64, 2, true>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
-                                             a_lo_on, act, ring, st, &rw);
+                                             a_lo_on, act, ring, st, &rw, stats_ld);
     }
-    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
+    return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st,
+                                     nullptr, stats_ld);
   }
-  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st);
+  return launch_tap_gemm_ws<32, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st,
+                                   nullptr, stats_ld);
 }
 
 // D[M][ldD] (cols n<N) = sum_t A[phase_t][q + shift_t][0:K] . B[bsel_t][n][0:K]
@@ -1163,6 +1180,31 @@ extern "C" int dmc_tc_tap_gemm_ring(const void* A_hi, const void* A_lo, int a_ph
   act.res_f32 = nullptr; act.res_hi = nullptr; act.res_lo = nullptr; act.out_hi = nullptr; act.out_lo = nullptr;
   return tap_gemm_impl(A_hi, A_lo, a_phases, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps,
                        shift, phase, bsel, stats, bw, act, ring, stream);
+}
+
+// dmc_tc_tap_gemm on COLUMN SUB-RANGES of wider maps (the inception blocks of I3D,
+// code/dmcnet_I3D/network/i3d.py:391-432: every branch reads a slice of one concatenated map and writes a
+// slice of the next).  A_hi / A_lo point at the first column of the slice, lda = row pitch of that map
+// (elements; 0 = K); D and -- with the fused BatchNorm backward -- bw_Y / bw_act_hi / bw_gb / bw_mean /
+// bw_invstd are the caller's slices with row pitch ldD; stats is double [2][stats_ld] (0 = N), again offset
+// to the slice.  bw_Y == NULL and bw_gb != NULL: D = result + bw_gb (plain sum of two data gradients).
+// Hp may carry a padded temporal extent (dmc_pack_hp, common.cuh): rows of the t-ring are masked as well.
+extern "C" int dmc_tc_tap_gemm_ex(const void* A_hi, const void* A_lo, int lda, long a_rows, int K,
+                                  const void* B_hi, const void* B_lo, int b_slices, int N, float* D, long M,
+                                  int ldD, int Hp, int Wp, int ntaps, const int* shift, const int* bsel,
+                                  double* stats, int stats_ld, const float* bw_Y, const void* bw_act_hi,
+                                  const float* bw_gb, const float* bw_mean, const float* bw_invstd,
+                                  void* stream) {
+  BwFuse bw;
+  bw.Y = bw_Y; bw.act_hi = (const bf16*)bw_act_hi; bw.gb = bw_gb; bw.mean = bw_mean; bw.invstd = bw_invstd;
+  bw.slope = 0.f;
+  ActFuse act;
+  act.bias = nullptr; act.mask = nullptr; act.slope = 1.f; act.frame_rows = 1u;
+  act.res_f32 = nullptr; act.res_hi = nullptr; act.res_lo = nullptr; act.out_hi = nullptr; act.out_lo = nullptr;
+  int phase[MAX_TAPS] = {0};
+  DMC_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS, "tap_gemm_ex: ntaps=%d", ntaps);
+  return tap_gemm_impl(A_hi, A_lo, 1, a_rows, K, B_hi, B_lo, b_slices, N, D, M, ldD, Hp, Wp, ntaps, shift,
+                       phase, bsel, stats, bw, act, 1, stream, lda, stats_ld);
 }
 
 // The forward GEMM of a discriminator block (code/dmcnet_GAN/model.py:254-279): same contraction, the
@@ -1214,13 +1256,15 @@ extern "C" int dmc_tc_tap_gemm_fold(const void* A_hi, const void* A_lo, int a_ph
 // G_lo == NULL: dY is taken at bf16 precision (G_hi only).
 // workspace != NULL (>= dmc_tc_wgrad_workspace() floats): split-K partial tiles go to the workspace
 // with plain stores and a second kernel sums them in a fixed order (deterministic, no atomics).
-extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
-                            const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
-                            const int* shift, const int* phase, const int* bsel, int oihw_taps,
-                            float* workspace, long workspace_floats, void* stream) {
+static int wgrad_impl(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
+                      const void* X_lo, int x_phases, int Cin, float* dW, int ntaps, const int* shift,
+                      const int* phase, const int* bsel, int oihw_taps, float* workspace,
+                      long workspace_floats, void* stream, int ldg, int ldx) {
   DMC_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0, "wgrad: Cout=%d Cin=%d must be multiples of 64", Cout,
               Cin);
   DMC_REQUIRE(P > 0 && P < (1L << 31), "wgrad: bad P");
+  DMC_REQUIRE((ldg == 0 || (ldg >= Cout && ldg % 8 == 0)) && (ldx == 0 || (ldx >= Cin && ldx % 8 == 0 && x_phases == 1)),
+              "wgrad: ldg=%d ldx=%d", ldg, ldx);
   TapTable tt;
   DMC_REQUIRE(fill_taps(tt, ntaps, shift, phase, bsel) == 0, "wgrad: ntaps=%d", ntaps);
   for (int i = 0; i < ntaps; ++i)
@@ -1230,12 +1274,31 @@ extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout
   // dY tile (always true) -- the activation tile is per tap.
   if (Cout == 64 && Cin == 64 && ntaps <= 10)      // layer1: two taps per M = 128 MMA
     return launch_wgrad64<32, 2>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, P, sm_count(), oihw_taps,
-                                 workspace, workspace_floats, st);
+                                 workspace, workspace_floats, st, ldg, ldx);
   if (Cin % 128 == 0)       // wide tiles: one tap per CTA, two CTAs per SM (32-pixel k-blocks)
     return launch_wgrad<128, 1, 32, 3>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P,
-                                       sm_count(), oihw_taps, workspace, workspace_floats, st);
+                                       sm_count(), oihw_taps, workspace, workspace_floats, st, ldg, ldx);
   return launch_wgrad<64, 5, 64, 2>(G_hi, G_lo, X_hi, X_lo, x_phases, tt, dW, Cout, Cin, P, sm_count(),
-                                    oihw_taps, workspace, workspace_floats, st);
+                                    oihw_taps, workspace, workspace_floats, st, ldg, ldx);
+}
+
+extern "C" int dmc_tc_wgrad(const void* G_hi, const void* G_lo, long P, int Cout, const void* X_hi,
+                            const void* X_lo, int x_phases, int Cin, float* dW, int ntaps,
+                            const int* shift, const int* phase, const int* bsel, int oihw_taps,
+                            float* workspace, long workspace_floats, void* stream) {
+  return wgrad_impl(G_hi, G_lo, P, Cout, X_hi, X_lo, x_phases, Cin, dW, ntaps, shift, phase, bsel, oihw_taps,
+                    workspace, workspace_floats, stream, 0, 0);
+}
+
+// dmc_tc_wgrad on column sub-ranges: G = Cout columns of a [P][ldg] map, X = Cin columns of a [P][ldx] map
+// (pointers at the first column of each slice), one phase, up to 27 taps (3 x 3 x 3 kernels of I3D).
+extern "C" int dmc_tc_wgrad_ex(const void* G_hi, const void* G_lo, int ldg, long P, int Cout, const void* X_hi,
+                               const void* X_lo, int ldx, int Cin, float* dW, int ntaps, const int* shift,
+                               const int* bsel, float* workspace, long workspace_floats, void* stream) {
+  int phase[MAX_TAPS] = {0};
+  DMC_REQUIRE(ntaps >= 1 && ntaps <= MAX_TAPS, "wgrad_ex: ntaps=%d", ntaps);
+  return wgrad_impl(G_hi, G_lo, P, Cout, X_hi, X_lo, 1, Cin, dW, ntaps, shift, phase, bsel, 0, workspace,
+                    workspace_floats, stream, ldg, ldx);
 }
 
 // Floats of split-K workspace dmc_tc_wgrad needs for this shape (0 is never returned; passing

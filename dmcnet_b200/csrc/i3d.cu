@@ -1,0 +1,479 @@
+// Kernels either side of the tap GEMMs of the I3D classifier (code/dmcnet_I3D/network/i3d.py:299-601).
+//
+// 3-D maps are pixel-major [clips][T+1][H+1][W+1][C] with the shared zero ring of common.cuh on the low
+// side of every dimension (Hp arguments of the pixelwise / GEMM kernels carry the temporal extent, see
+// dmc_pack_hp); activations are bf16 hi/lo plane pairs, raw conv outputs and gradients fp32.  A 3x3x3
+// "SAME" convolution is then a 27-tap GEMM with flat row shifts dt*Hp*Wp + dh*Wp + dw, a 1x1x1
+// convolution a one-tap GEMM (csrc/gemm_tc.cu).  What is left for this file:
+//   * the sample layout [B][7][T][H][W] -> per-frame planar mv / residual / flow,
+//   * the 7x7x7 stride-2 stem as an explicit im2col operand (K = 686 -> 704) and its transpose,
+//   * MaxPool3dTFPadding (TF "SAME": zeros appended on the HIGH side, ceil_mode) forward / backward,
+//   * AvgPool3d((2,7,7)) + the mean over the remaining temporal positions, folded into one weighted mean,
+//   * dropout mask multiply, SGD with Nesterov momentum over the flat bucket (train_model.py:129-142).
+#include "common.cuh"
+
+namespace dmc {
+
+static unsigned grid_1d(long n, int block, long cap = 148L * 16) {
+  long g = cdiv(n, block);
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// ------------------------------------------------------------------ sample layout
+// data [B][Cd][T][HW] (Cd = 5 or 7: mv 2 | residual 3 | flow 2, code/dmcnet_I3D/train/model.py:139-158)
+// -> mv [B*T][2][HW], res [B*T][3][HW], flow [B*T][2][HW] (flow may be NULL).
+__global__ void __launch_bounds__(256)
+i3d_unpack_kernel(const float* __restrict__ data, int B, int Cd, int T, int HW4, float* __restrict__ mv,
+                  float* __restrict__ res, float* __restrict__ flow) {
+  const long total = (long)B * Cd * T * HW4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW4);
+    long r = i / HW4;
+    const int t = (int)(r % T);
+    r /= T;
+    const int c = (int)(r % Cd);
+    const int b = (int)(r / Cd);
+    const float4 v = reinterpret_cast<const float4*>(data)[i];
+    const long f = (long)b * T + t;
+    float* dst;
+    if (c < 2) dst = mv + (f * 2 + c) * (long)HW4 * 4;
+    else if (c < 5) dst = res + (f * 3 + (c - 2)) * (long)HW4 * 4;
+    else if (flow) dst = flow + (f * 2 + (c - 5)) * (long)HW4 * 4;
+    else continue;
+    reinterpret_cast<float4*>(dst)[p] = v;
+  }
+}
+
+// ------------------------------------------------------------------ stem im2col
+// x planar [clips*T][2][H][W] (frame stride x_ns) -> A hi/lo [clips][To+1][Ho+1][Wo+1][KP] with
+// k = ((kt*7 + kh)*7 + kw)*2 + ci = x[ci][2to+kt-2][2ho+kh-2][2wo+kw-2] (TF "SAME" for kernel 7, stride 2:
+// 2 zeros in front, 3 behind, i3d.py:299-315), zero for k >= 686 and outside the clip.  Ring rows are
+// never written (the buffer is allocated zeroed).  One thread per (row, kt, kh): 14 values -> 7 bf16x2.
+__global__ void __launch_bounds__(256)
+i3d_stem_im2col_kernel(const float* __restrict__ x, long x_ns, int clips, int T, int H, int W, int KP,
+                       bf16* __restrict__ A_hi, bf16* __restrict__ A_lo) {
+  const int To = T / 2, Ho = H / 2, Wo = W / 2;
+  const int Tp = To + 1, Hp = Ho + 1, Wp = Wo + 1;
+  const long units = (long)clips * To * Ho * Wo * 49;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % 49);
+    long r = i / 49;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho); r /= Ho;
+    const int to = (int)(r % To);
+    const int n = (int)(r / To);
+    const int kt = kk / 7, kh = kk % 7;
+    const int t = 2 * to + kt - 2, h = 2 * ho + kh - 2;
+    const long row = (((long)n * Tp + to + 1) * Hp + ho + 1) * Wp + wo + 1;
+    bf16* oh = A_hi + row * KP + kk * 14;
+    bf16* ol = A_lo + row * KP + kk * 14;
+    const bool in_th = t >= 0 && t < T && h >= 0 && h < H;
+    const float* f0 = x + ((long)n * T + (in_th ? t : 0)) * x_ns + (long)(in_th ? h : 0) * W;
+    const float* f1 = f0 + (long)H * W;
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) {
+      const int w = 2 * wo + kw - 2;
+      float v0 = 0.f, v1 = 0.f;
+      if (in_th && w >= 0 && w < W) { v0 = __ldg(f0 + w); v1 = __ldg(f1 + w); }
+      bf16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      __nv_bfloat162 hh, ll;
+      hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
+      *reinterpret_cast<__nv_bfloat162*>(oh + 2 * kw) = hh;
+      *reinterpret_cast<__nv_bfloat162*>(ol + 2 * kw) = ll;
+    }
+  }
+}
+
+// Transpose of the im2col: dX[n*T + t][ci][h][w] (+)= sum over the (kt, kh, kw) whose output position
+// (to, ho, wo) = ((t+2-kt)/2, ...) is integral and inside the map of dA[row(to,ho,wo)][k].
+__global__ void __launch_bounds__(256)
+i3d_stem_col2im_kernel(const float* __restrict__ dA, int KP, int clips, int T, int H, int W,
+                       float* __restrict__ dX, long dx_ns, int accumulate) {
+  const int To = T / 2, Ho = H / 2, Wo = W / 2;
+  const int Tp = To + 1, Hp = Ho + 1, Wp = Wo + 1;
+  const long total = (long)clips * T * H * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % T);
+    const int n = (int)(r / T);
+    float a0 = 0.f, a1 = 0.f;
+    for (int kt = (t & 1); kt < 7; kt += 2) {            // t + 2 - kt even
+      const int to = (t + 2 - kt) / 2;
+      if (t + 2 - kt < 0 || to >= To) continue;
+      for (int kh = (h & 1); kh < 7; kh += 2) {
+        const int ho = (h + 2 - kh) / 2;
+        if (h + 2 - kh < 0 || ho >= Ho) continue;
+        for (int kw = (w & 1); kw < 7; kw += 2) {
+          const int wo = (w + 2 - kw) / 2;
+          if (w + 2 - kw < 0 || wo >= Wo) continue;
+          const long row = (((long)n * Tp + to + 1) * Hp + ho + 1) * Wp + wo + 1;
+          const float2 v = __ldg(reinterpret_cast<const float2*>(dA + row * KP + ((kt * 7 + kh) * 7 + kw) * 2));
+          a0 += v.x;
+          a1 += v.y;
+        }
+      }
+    }
+    float* o0 = dX + ((long)n * T + t) * dx_ns + (long)h * W + w;
+    float* o1 = o0 + (long)H * W;
+    if (accumulate) { *o0 += a0; *o1 += a1; } else { *o0 = a0; *o1 = a1; }
+  }
+}
+
+// ------------------------------------------------------------------ MaxPool3dTFPadding
+struct Pool3 {
+  int Ti, Hi, Wi, To, Ho, Wo;      // interior extents of the input / output maps
+  int kt, kh, kw, st, sh, sw;      // window, stride
+  int pt, ph, pw;                  // zeros in FRONT of each dimension (TF "SAME": pad_along / 2)
+};
+
+// in hi/lo [clips][Ti+1][Hi+1][Wi+1][C] -> out hi/lo [clips][To+1][Ho+1][Wo+1][C] (interior rows only; the
+// output buffers are allocated zeroed) and idx [rows_out][C] = window position (dt*kh + dh)*kw + dw of the
+// maximum, 255 when a padding zero wins.  Scan order and strict '>' as ATen's max_pool3d: the first
+// maximum wins.  Positions outside the map are the ConstantPad3d zeros of i3d.py:380-388.
+__global__ void __launch_bounds__(256)
+maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int clips, int C,
+                     const Pool3 g, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                     uint8_t* __restrict__ idx) {
+  const int C4 = C / 4;
+  const long units = (long)clips * g.To * g.Ho * g.Wo * C4;
+  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long r = i / C4;
+    const int wo = (int)(r % g.Wo); r /= g.Wo;
+    const int ho = (int)(r % g.Ho); r /= g.Ho;
+    const int to = (int)(r % g.To);
+    const int n = (int)(r / g.To);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    uint2 bh = make_uint2(0u, 0u), bl = make_uint2(0u, 0u);
+    bf16* bhp = reinterpret_cast<bf16*>(&bh);
+    bf16* blp = reinterpret_cast<bf16*>(&bl);
+    uint8_t bi[4] = {255, 255, 255, 255};
+    for (int dt = 0; dt < g.kt; ++dt) {
+      const int t = to * g.st + dt - g.pt;
+      for (int dh = 0; dh < g.kh; ++dh) {
+        const int h = ho * g.sh + dh - g.ph;
+        for (int dw = 0; dw < g.kw; ++dw) {
+          const int w = wo * g.sw + dw - g.pw;
+          const bool in = t >= 0 && t < g.Ti && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi;
+          uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
+          if (in) {
+            const long q = (((long)n * Tpi + t + 1) * Hpi + h + 1) * Wpi + w + 1;
+            vh = __ldg(reinterpret_cast<const uint2*>(in_hi + q * C + c));
+            vl = __ldg(reinterpret_cast<const uint2*>(in_lo + q * C + c));
+          }
+          const bf16* vhp = reinterpret_cast<const bf16*>(&vh);
+          const bf16* vlp = reinterpret_cast<const bf16*>(&vl);
+          const uint8_t code = in ? (uint8_t)((dt * g.kh + dh) * g.kw + dw) : (uint8_t)255;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float v = join_bf16(vhp[k], vlp[k]);
+            if (v > best[k]) { best[k] = v; bhp[k] = vhp[k]; blp[k] = vlp[k]; bi[k] = code; }
+          }
+        }
+      }
+    }
+    const long qo = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + wo + 1;
+    *reinterpret_cast<uint2*>(out_hi + qo * C + c) = bh;
+    *reinterpret_cast<uint2*>(out_lo + qo * C + c) = bl;
+    *reinterpret_cast<uchar4*>(idx + qo * C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
+// dX[row_in][c] = add[row_in][c] + sum over the windows containing the position whose idx points at it of
+// g[row_out][c]; every row of dX is written (ring rows: 0).
+__global__ void __launch_bounds__(256)
+maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ idx, int clips, int C,
+                     const Pool3 g, const float* __restrict__ add, float* __restrict__ dX) {
+  const int C4 = C / 4;
+  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
+  const long units = (long)clips * Tpi * Hpi * Wpi * C4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long q = i / C4;
+    long r = q;
+    const int wp = (int)(r % Wpi); r /= Wpi;
+    const int hp = (int)(r % Hpi); r /= Hpi;
+    const int tp = (int)(r % Tpi);
+    const int n = (int)(r / Tpi);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tp >= 1 && hp >= 1 && wp >= 1) {
+      const int t = tp - 1, h = hp - 1, w = wp - 1;
+      if (add) acc = __ldg(reinterpret_cast<const float4*>(add + q * C + c));
+      // windows: to * st - pt <= t <= to * st - pt + kt - 1
+      const int to_hi = (t + g.pt) / g.st, ho_hi = (h + g.ph) / g.sh, wo_hi = (w + g.pw) / g.sw;
+      for (int to = to_hi; to >= 0 && to * g.st - g.pt + g.kt - 1 >= t; --to) {
+        if (to >= g.To) continue;
+        const int dt = t + g.pt - to * g.st;
+        for (int ho = ho_hi; ho >= 0 && ho * g.sh - g.ph + g.kh - 1 >= h; --ho) {
+          if (ho >= g.Ho) continue;
+          const int dh = h + g.ph - ho * g.sh;
+          for (int wo = wo_hi; wo >= 0 && wo * g.sw - g.pw + g.kw - 1 >= w; --wo) {
+            if (wo >= g.Wo) continue;
+            const int dw = w + g.pw - wo * g.sw;
+            const uint8_t code = (uint8_t)((dt * g.kh + dh) * g.kw + dw);
+            const long qo = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + wo + 1;
+            const uchar4 id = *reinterpret_cast<const uchar4*>(idx + qo * C + c);
+            if (id.x == code || id.y == code || id.z == code || id.w == code) {
+              const float4 gv = __ldg(reinterpret_cast<const float4*>(gout + qo * C + c));
+              if (id.x == code) acc.x += gv.x;
+              if (id.y == code) acc.y += gv.y;
+              if (id.z == code) acc.z += gv.z;
+              if (id.w == code) acc.w += gv.w;
+            }
+          }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(dX + q * C + c) = acc;
+  }
+}
+
+// ------------------------------------------------------------------ head
+// AvgPool3d((2,7,7), stride 1) over a [T5][7][7] map leaves T5-1 temporal positions; the 1x1x1 logits
+// convolution and the mean over them are linear, so mean_t'(conv(avg_t')) = conv(weighted mean):
+// pooled[n][c] = sum_{t,h,w} wt(t) * x / ((T5-1) * 2 * H * W), wt(t) = number of windows containing t
+// (i3d.py:484,521-525 with Unit3Dpy's squeeze / mean).
+__device__ __forceinline__ float head_wt(int t, int T5) {
+  const int lo = t - 1 > 0 ? t - 1 : 0, hi = t < T5 - 2 ? t : T5 - 2;
+  return (float)(hi - lo + 1);
+}
+
+__global__ void __launch_bounds__(256)
+i3d_head_pool_fwd_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int T5, int H, int W,
+                         int C, float* __restrict__ pooled) {
+  const int n = blockIdx.x;
+  const int Hp = H + 1, Wp = W + 1, Tp = T5 + 1;
+  const float inv = 1.f / (float)((T5 - 1) * 2 * H * W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T5; ++t) {
+      float s = 0.f;
+      for (int h = 0; h < H; ++h)
+        for (int w = 0; w < W; ++w) {
+          const long q = (((long)n * Tp + t + 1) * Hp + h + 1) * Wp + w + 1;
+          s += join_bf16(hi[q * C + c], lo[q * C + c]);
+        }
+      acc += head_wt(t, T5) * s;
+    }
+    pooled[(long)n * C + c] = acc * inv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+i3d_head_pool_bwd_kernel(const float* __restrict__ dpooled, int clips, int T5, int H, int W, int C,
+                         float* __restrict__ dX) {
+  const int C4 = C / 4;
+  const int Hp = H + 1, Wp = W + 1, Tp = T5 + 1;
+  const long units = (long)clips * Tp * Hp * Wp * C4;
+  const float inv = 1.f / (float)((T5 - 1) * 2 * H * W);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long q = i / C4;
+    long r = q;
+    const int wp = (int)(r % Wp); r /= Wp;
+    const int hp = (int)(r % Hp); r /= Hp;
+    const int tp = (int)(r % Tp);
+    const int n = (int)(r / Tp);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tp >= 1 && hp >= 1 && wp >= 1) {
+      const float s = head_wt(tp - 1, T5) * inv;
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dpooled + (long)n * C + c));
+      v = make_float4(d.x * s, d.y * s, d.z * s, d.w * s);
+    }
+    *reinterpret_cast<float4*>(dX + q * C + c) = v;
+  }
+}
+
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ m, long n, float* __restrict__ out) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = a[i] * m[i];
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 yv = reinterpret_cast<float4*>(y)[i];
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    yv.x = fmaf(a, xv.x, yv.x); yv.y = fmaf(a, xv.y, yv.y); yv.z = fmaf(a, xv.z, yv.z); yv.w = fmaf(a, xv.w, yv.w);
+    reinterpret_cast<float4*>(y)[i] = yv;
+  }
+}
+
+__global__ void add_i64_kernel(long long* __restrict__ p, int n, long long v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += v;
+}
+
+// ------------------------------------------------------------------ SGD, Nesterov momentum
+struct SgdChunk { int offset, count, tensor, pad; };     // same table as dmc_adam_step
+
+// torch.optim.SGD(momentum, nesterov=True, dampening=0), `_single_tensor_sgd`:
+//   g += wd * p;  buf = momentum * buf + g  (first step: buf = g, identical with buf = 0);
+//   p -= lr * (g + momentum * buf)
+__global__ void __launch_bounds__(256)
+sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                    const SgdChunk* __restrict__ chunks, const float* __restrict__ hyper, float momentum,
+                    float grad_scale) {
+  const SgdChunk ch = chunks[blockIdx.x];
+  const float lr = hyper[2 * ch.tensor], wd = hyper[2 * ch.tensor + 1];
+  for (int i = threadIdx.x; i < ch.count; i += blockDim.x) {
+    const long o = (long)ch.offset + i;
+    float gk = fmaf(wd, p[o], g[o] * grad_scale);
+    const float b = momentum * buf[o] + gk;
+    buf[o] = b;
+    p[o] = p[o] - lr * (gk + momentum * b);
+  }
+}
+
+}  // namespace dmc
+
+using namespace dmc;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+// data [B][Cd][T][H*W] fp32 (Cd = 5 or 7) -> per-frame planar mv [B*T][2][HW], res [B*T][3][HW] and, with
+// Cd = 7, flow [B*T][2][HW] (code/dmcnet_I3D/train/model.py:139-158: input[:, :5] feeds the generator,
+// input[:, 5:7] is the flow target; i3d.py:504-506 folds T into the batch).
+extern "C" int dmc_i3d_unpack(const float* data, int B, int Cd, int T, long HW, float* mv, float* res,
+                              float* flow, void* stream) {
+  DMC_REQUIRE(data && mv && res && B > 0 && T > 0 && (Cd == 5 || Cd == 7) && HW % 4 == 0, "i3d_unpack: bad arguments");
+  const long total = (long)B * Cd * T * (HW / 4);
+  i3d_unpack_kernel<<<grid_1d(total, 256), 256, 0, ST(stream)>>>(data, B, Cd, T, (int)(HW / 4), mv, res,
+                                                                Cd == 7 ? flow : nullptr);
+  return dmc_check_launch("i3d_unpack_kernel");
+}
+
+// A_hi / A_lo [clips][T/2+1][H/2+1][W/2+1][KP] (zero-initialised by the caller once; ring rows and the
+// columns >= 686 are never written) = im2col of x [clips*T][2][H][W] for Conv3d(2, 64, 7, stride 2) with
+// TF "SAME" padding (2 in front, 3 behind); column k = ((kt*7 + kh)*7 + kw)*2 + ci.
+extern "C" int dmc_i3d_stem_im2col(const float* x, long x_ns, int clips, int T, int H, int W, int KP,
+                                   void* A_hi, void* A_lo, void* stream) {
+  DMC_REQUIRE(x && A_hi && A_lo && clips > 0, "i3d_stem_im2col: null argument");
+  DMC_REQUIRE(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && KP >= 686 && KP % 2 == 0, "i3d_stem_im2col: T=%d H=%d W=%d KP=%d", T, H, W, KP);
+  const long units = (long)clips * (T / 2) * (H / 2) * (W / 2) * 49;
+  i3d_stem_im2col_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(x, x_ns, clips, T, H, W, KP,
+                                                                                 (bf16*)A_hi, (bf16*)A_lo);
+  return dmc_check_launch("i3d_stem_im2col_kernel");
+}
+
+// Transpose of dmc_i3d_stem_im2col for the data gradient: dX [clips*T][2][H][W] (frame stride dx_ns)
+// (+)= col2im(dA [rows][KP] fp32).
+extern "C" int dmc_i3d_stem_col2im(const float* dA, int KP, int clips, int T, int H, int W, float* dX,
+                                   long dx_ns, int accumulate, void* stream) {
+  DMC_REQUIRE(dA && dX && clips > 0 && T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && KP >= 686, "i3d_stem_col2im: bad arguments");
+  const long total = (long)clips * T * H * W;
+  i3d_stem_col2im_kernel<<<grid_1d(total, 256, 148L * 32), 256, 0, ST(stream)>>>(dA, KP, clips, T, H, W, dX,
+                                                                                 dx_ns, accumulate);
+  return dmc_check_launch("i3d_stem_col2im_kernel");
+}
+
+static int fill_pool(Pool3& g, const int* in_thw, const int* kernel, const int* stride) {
+  g.Ti = in_thw[0]; g.Hi = in_thw[1]; g.Wi = in_thw[2];
+  g.kt = kernel[0]; g.kh = kernel[1]; g.kw = kernel[2];
+  g.st = stride[0]; g.sh = stride[1]; g.sw = stride[2];
+  const int k[3] = {g.kt, g.kh, g.kw}, s[3] = {g.st, g.sh, g.sw}, in[3] = {g.Ti, g.Hi, g.Wi};
+  int out[3], pf[3];
+  for (int d = 0; d < 3; ++d) {
+    if (k[d] < 1 || s[d] < 1 || in[d] < 1 || k[d] > 3) return -1;
+    const int pad = k[d] - s[d] > 0 ? k[d] - s[d] : 0;            // get_padding_shape, i3d.py:299-315
+    pf[d] = pad / 2;
+    // MaxPool3d(kernel, stride, ceil_mode=True) on the padded extent
+    const int ext = in[d] + pad;
+    int o = (ext - k[d] + s[d] - 1) / s[d] + 1;
+    if ((o - 1) * s[d] >= ext) --o;                               // last window must start inside the input
+    out[d] = o;
+  }
+  g.pt = pf[0]; g.ph = pf[1]; g.pw = pf[2];
+  g.To = out[0]; g.Ho = out[1]; g.Wo = out[2];
+  return 0;
+}
+
+// Output extents of MaxPool3dTFPadding(kernel, stride) on a [T][H][W] map (i3d.py:375-388).
+extern "C" int dmc_maxpool3d_out_shape(const int* in_thw, const int* kernel, const int* stride, int* out_thw) {
+  Pool3 g;
+  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride) == 0, "maxpool3d: bad geometry");
+  out_thw[0] = g.To; out_thw[1] = g.Ho; out_thw[2] = g.Wo;
+  return DMC_OK;
+}
+
+// MaxPool3dTFPadding forward on pixel-major hi/lo maps (see the kernel); idx is uint8 [rows_out][C].
+extern "C" int dmc_maxpool3d_fwd(const void* in_hi, const void* in_lo, int clips, int C, const int* in_thw,
+                                 const int* kernel, const int* stride, void* out_hi, void* out_lo, void* idx,
+                                 void* stream) {
+  Pool3 g;
+  DMC_REQUIRE(in_hi && in_lo && out_hi && out_lo && idx && clips > 0 && C % 4 == 0, "maxpool3d_fwd: bad arguments");
+  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride) == 0, "maxpool3d_fwd: bad geometry");
+  const long units = (long)clips * g.To * g.Ho * g.Wo * (C / 4);
+  maxpool3d_fwd_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(
+      (const bf16*)in_hi, (const bf16*)in_lo, clips, C, g, (bf16*)out_hi, (bf16*)out_lo, (uint8_t*)idx);
+  return dmc_check_launch("maxpool3d_fwd_kernel");
+}
+
+// Backward: dX [rows_in][C] = add (may be NULL) + routed gradient; every row written (ring rows zero).
+extern "C" int dmc_maxpool3d_bwd(const float* gout, const void* idx, int clips, int C, const int* in_thw,
+                                 const int* kernel, const int* stride, const float* add, float* dX,
+                                 void* stream) {
+  Pool3 g;
+  DMC_REQUIRE(gout && idx && dX && clips > 0 && C % 4 == 0, "maxpool3d_bwd: bad arguments");
+  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride) == 0, "maxpool3d_bwd: bad geometry");
+  const long units = (long)clips * (g.Ti + 1) * (g.Hi + 1) * (g.Wi + 1) * (C / 4);
+  maxpool3d_bwd_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips,
+                                                                              C, g, add, dX);
+  return dmc_check_launch("maxpool3d_bwd_kernel");
+}
+
+// pooled [clips][C] = AvgPool3d((2,7,7)) followed by the mean over the remaining temporal positions of
+// the hi/lo map [clips][T5+1][H+1][W+1][C] (see head_wt).
+extern "C" int dmc_i3d_head_pool_fwd(const void* hi, const void* lo, int clips, int T5, int H, int W, int C,
+                                     float* pooled, void* stream) {
+  DMC_REQUIRE(hi && lo && pooled && clips > 0 && T5 >= 2 && H >= 1 && W >= 1, "i3d_head_pool_fwd: bad arguments");
+  i3d_head_pool_fwd_kernel<<<clips, 256, 0, ST(stream)>>>((const bf16*)hi, (const bf16*)lo, T5, H, W, C, pooled);
+  return dmc_check_launch("i3d_head_pool_fwd_kernel");
+}
+
+extern "C" int dmc_i3d_head_pool_bwd(const float* dpooled, int clips, int T5, int H, int W, int C, float* dX,
+                                     void* stream) {
+  DMC_REQUIRE(dpooled && dX && clips > 0 && T5 >= 2 && C % 4 == 0, "i3d_head_pool_bwd: bad arguments");
+  const long units = (long)clips * (T5 + 1) * (H + 1) * (W + 1) * (C / 4);
+  i3d_head_pool_bwd_kernel<<<grid_1d(units, 256), 256, 0, ST(stream)>>>(dpooled, clips, T5, H, W, C, dX);
+  return dmc_check_launch("i3d_head_pool_bwd_kernel");
+}
+
+// out = a * m elementwise (dropout mask of i3d.py:526, forward and backward).
+extern "C" int dmc_mul(const float* a, const float* m, long n, float* out, void* stream) {
+  DMC_REQUIRE(a && m && out && n > 0, "mul: bad arguments");
+  mul_kernel<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(a, m, n, out);
+  return dmc_check_launch("mul_kernel");
+}
+
+// y += a * x over n floats (n a multiple of 4): gradient accumulation over the iter_size micro-batches of
+// code/dmcnet_I3D/train/model.py:377-396 (loss.backward() adds into .grad).
+extern "C" int dmc_axpy(float* y, const float* x, float a, long n, void* stream) {
+  DMC_REQUIRE(y && x && n > 0 && n % 4 == 0, "axpy: bad arguments");
+  axpy_kernel<<<grid_1d(n / 4, 256), 256, 0, ST(stream)>>>(y, x, a, n / 4);
+  return dmc_check_launch("axpy_kernel");
+}
+
+// p[i] += v for an int64 array (the num_batches_tracked counters of every BatchNorm3d, kept contiguous).
+extern "C" int dmc_add_i64(void* p, int n, long long v, void* stream) {
+  DMC_REQUIRE(p && n > 0, "add_i64: bad arguments");
+  add_i64_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ST(stream)>>>((long long*)p, n, v);
+  return dmc_check_launch("add_i64_kernel");
+}
+
+// One torch.optim.SGD(momentum, nesterov=True) step over `nchunks` chunks of the flat bucket (the chunk /
+// hyper tables of dmc_adam_step); grad_scale multiplies the gradient first (1 / iter_size,
+// code/dmcnet_I3D/train/model.py:387-396).
+extern "C" int dmc_sgd_nesterov_step(float* p, const float* g, float* buf, const void* chunks, int nchunks,
+                                     const float* hyper, float momentum, float grad_scale, void* stream) {
+  if (nchunks <= 0) return DMC_OK;
+  DMC_REQUIRE(p && g && buf && chunks && hyper, "sgd_nesterov_step: null argument");
+  sgd_nesterov_kernel<<<nchunks, 256, 0, ST(stream)>>>(p, g, buf, reinterpret_cast<const SgdChunk*>(chunks), hyper,
+                                                       momentum, grad_scale);
+  return dmc_check_launch("sgd_nesterov_kernel");
+}

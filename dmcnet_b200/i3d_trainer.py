@@ -1,0 +1,172 @@
+"""One iteration of the I3D trainer (code/dmcnet_I3D/train/model.py:286-446, train_model.py:20-272) on the
+I3DEngine: the non-adversarial branch of ``model.fit`` for modality 'flow+mp4' -- forward
+``node='flow+logit'``, CE + MSE, one backward, the classifier's optimizer (``optimizer``: base layers with
+``lr_mult``, new layers) and the generator's (``optimizer_mse``), gradients accumulated over ``iter_size``
+batches and divided by it before the step (:423-432), the two-stage learning-rate rule of
+``adjust_learning_rate`` (:268-283) with fresh optimizers at ``epoch_thre`` (:351-356).
+
+Optimizers over the flat buckets: Adam (``dmc_adam_step``; eps 1e-8, the generator's stage-two Adam 1e-3,
+train_model.py:122-176) or SGD with Nesterov momentum 0.9 (``dmc_sgd_nesterov_step``), weight decay 1e-4 on
+every tensor (train_model.py:112-113).  The adversarial branch (``--adv``, ``optimizer_3``) is not built.
+Data parallel: clips sharded over ranks, BatchNorm3d statistics per rank (nn.DataParallel, train_model.py:119),
+loss gradients pre-scaled by the global batch, one sum all-reduce of the flat gradient bucket per optimizer step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .i3d_engine import I3DEngine
+
+
+@dataclass
+class I3DHParams:
+    """Defaults of train_hmdb51.py:20-110 (``--optimizer sgd``, ``--fine_tune 1``, ``--drop-out 0.5``)."""
+    optim: str = 'sgd'
+    lr_base: float = 0.005
+    lr_base2: float = 0.002
+    weight_decay: float = 1e-4
+    iter_size: int = 1
+    epoch_thre: int = 1
+    fine_tune: bool = True
+    detach: bool = False
+    dropout: float = 0.5
+    momentum: float = 0.9
+    betas: tuple = (0.9, 0.999)
+
+
+def lr_mult_rule(lr_mult: float, epoch: int, epoch_thre: int) -> float:
+    """model.adjust_learning_rate (train/model.py:268-283): groups with lr_mult 0.2 / 0.5 (the convolutional
+    part of I3D) get 0 during stage one; 0.5 becomes 1.0 afterwards."""
+    if lr_mult in (0.2, 0.5):
+        if epoch_thre > 0 and epoch + 1 <= epoch_thre:
+            return 0.0
+        if lr_mult == 0.5:
+            return 1.0
+    return lr_mult
+
+
+def param_group_of(key: str) -> str:
+    """train_model.py:62-86 with modality 'flow+mp4'."""
+    if key.startswith('gen_flow_model'):
+        return 'gf'
+    if key.startswith('conv3d_0c_1x1') or key.startswith('classifier'):
+        return 'new'
+    return 'base'
+
+
+class I3DTrainStep:
+    def __init__(self, engine: I3DEngine, hp: I3DHParams, *, world_size: int = 1, process_group=None):
+        if hp.optim not in ('sgd', 'adam'):
+            raise ValueError("optimizer must be 'sgd' or 'adam' (train_hmdb51.py:80-82)")
+        self.eng, self.hp, self.world, self.pg = engine, hp, world_size, process_group
+        dev = engine.device
+        self.B = engine.clips
+        self.target = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.consensus = torch.zeros(self.B, engine.num_class, dtype=torch.float32, device=dev)
+        self.ce_stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.mse_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.acc = torch.zeros_like(engine.grads) if hp.iter_size > 1 else None
+        self.lr_mul = 0.2 if hp.fine_tune else 0.5                      # train_model.py:100-105
+        self.keys: List[str] = list(engine.specs.keys())
+        self.group: List[str] = [param_group_of(k) for k in self.keys]
+        chunks = {'cls': [], 'gf': []}
+        for ti, (k, g) in enumerate(zip(self.keys, self.group)):
+            off, n = engine.offsets[k], engine.numel(k)
+            for c0 in range(0, n, 1024):
+                chunks['gf' if g == 'gf' else 'cls'].append((off + c0, min(1024, n - c0), ti, 0))
+        self.chunks = {}
+        for g, rows in chunks.items():
+            t = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).contiguous().to(dev)
+            self.chunks[g] = (t, len(rows))
+        self.hyper = torch.zeros(len(self.keys), 2, dtype=torch.float32, device=dev)
+        self.steps = torch.zeros(2, dtype=torch.int32, device=dev)        # Adam step counts: classifier, generator
+        self.i = 0
+        self.epoch = -1
+        self.stage2 = False
+        self.set_epoch(0)
+
+    # ------------------------------------------------------------------ schedule
+    def set_epoch(self, epoch: int, lr: Optional[float] = None, lr2: Optional[float] = None):
+        """Learning rates for `epoch` (lr / lr2: the MultiFactorScheduler values of the two stages, default
+        their base rates).  Entering stage two replaces both optimizers by fresh ones (train/model.py:351-356):
+        moments and step counts restart."""
+        hp = self.hp
+        stage2 = epoch >= hp.epoch_thre
+        if stage2 and not self.stage2:
+            ops.memset_zero(self.eng.exp_avg)
+            ops.memset_zero(self.eng.exp_avg_sq)
+            ops.memset_zero(self.steps)
+        self.stage2, self.epoch = stage2, epoch
+        if not stage2:
+            lr_g = hp.lr_base if lr is None else lr
+            lr_c = 0.0 if hp.detach else lr_g                               # :405-411
+        else:
+            lr_g = lr_c = hp.lr_base2 if lr2 is None else lr2
+        rows = []
+        for g in self.group:
+            if g == 'gf':
+                rows.append((lr_g, hp.weight_decay))
+            else:
+                mult = lr_mult_rule(self.lr_mul if g == 'base' else 1.0, epoch, hp.epoch_thre)
+                rows.append((lr_c * mult, hp.weight_decay))
+        self.hyper.copy_(torch.tensor(rows, dtype=torch.float32))
+
+    # ------------------------------------------------------------------ step
+    def _optimizers(self, src: torch.Tensor, scale: float):
+        eng, hp = self.eng, self.hp
+        for gi, g in enumerate(('cls', 'gf')):
+            t, n = self.chunks[g]
+            if hp.optim == 'adam':
+                eps = 1e-3 if (g == 'gf' and self.stage2) else 1e-8
+                ops.adam_step(eng.params, src, eng.exp_avg, eng.exp_avg_sq, t, n, self.hyper.view(-1),
+                              self.steps[gi:gi + 1], hp.betas[0], hp.betas[1], eps, scale)
+            else:
+                ops.sgd_nesterov_step(eng.params, src, eng.exp_avg, t, n, self.hyper.view(-1), hp.momentum, scale)
+
+    def step(self, data: torch.Tensor, target: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
+             metrics: bool = True) -> Dict[str, float]:
+        """data [B, 7, T, H, W] (device or pinned host), target [B].  dropout_mask [B, 400] replaces the draw of
+        nn.Dropout(hp.dropout) (None: drawn here with the same ATen call)."""
+        eng, hp, B = self.eng, self.hp, self.B
+        dev = eng.device
+        if not data.is_cuda:
+            data = data.to(dev, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        if hp.dropout > 0.0:
+            eng.set_dropout(hp.dropout, dropout_mask if dropout_mask is not None else eng.draw_dropout_mask(hp.dropout))
+        else:
+            eng.set_dropout(0.0)
+        eng.zero_grads()
+        eng.forward_data(data, train=True)
+        ops.ce_head(eng.logits, B, 1, eng.num_class, self.target, 1.0 / (B * self.world), self.consensus,
+                    eng.d_logits, self.ce_stats)
+        H, W = eng.H, eng.W
+        numel = eng.N * 2 * H * W
+        ops.mse_head(eng.gen_flow, eng.in_flow, numel, 2.0 / (numel * self.world), eng.dD, self.mse_sum,
+                     frame_elems=2 * H * W, dgen_ns=eng.dD.shape[1] * H * W)
+        # I3D.forward is never called with detach=True by fit (train/model.py:139-147): the classifier's
+        # gradient reaches the generator through the stem
+        eng.backward(eng.N, cls=True, cls_wgrad=True, gen_grad=True, cls_to_gen=True)
+        self.i += 1
+        stepped = False
+        if hp.iter_size > 1:
+            ops.axpy(self.acc, eng.grads, 1.0)
+        if self.i % hp.iter_size == 0:
+            src = self.acc if hp.iter_size > 1 else eng.grads
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.pg)
+            self._optimizers(src, 1.0 / hp.iter_size)
+            if hp.iter_size > 1:
+                ops.memset_zero(self.acc)
+            self.i = 0
+            stepped = True
+        if not metrics:
+            return {'stepped': stepped}
+        ce = self.ce_stats.cpu().tolist()
+        return {'loss_ce': ce[0] / B, 'top1': ce[1] * 100.0 / B, 'top5': ce[2] * 100.0 / B,
+                'loss_mse': float(self.mse_sum.cpu()[0]) / numel, 'stepped': stepped}

@@ -551,3 +551,87 @@ def tap_gemm_fold(A_hi, A_lo, B_hi, B_lo, *, a_phases, a_rows, K, b_slices, N, M
           c_int(Wp), c_int(ring), c_int(len(shift)), _iarr(shift), _iarr(phase), _iarr(bsel), _ptr(bias, F32),
           c_float(slope), _ptr(res_f32, F32), _ptr(res_hi, BF16), _ptr(res_lo, BF16), _ptr(out_hi, BF16),
           _ptr(out_lo, BF16), _stream())
+
+
+# ---------------------------------------------------------------- I3D (csrc/i3d.cu, column sub-range GEMMs)
+def pack_hp(Hp: int, Tp: int) -> int:
+    """Hp argument of the pixelwise / GEMM kernels for a 3-D map with padded temporal extent Tp."""
+    return int(Hp) | (int(Tp) << 16)
+
+
+def tap_gemm_ex(A_hi, A_lo, B_hi, B_lo, D, *, lda, a_rows, K, b_slices, N, M, ldD, Hp, Wp, shift, bsel,
+                stats=None, stats_ld=0, bw=None, gb=None):
+    """Tap GEMM on column sub-ranges (dmc_tc_tap_gemm_ex).  bw = (Y, act_hi, gb, mean, invstd) fuses the
+    BatchNorm-backward reductions; gb alone adds a second gradient source to a plain result."""
+    bY, bact, bgb, bmean, binv = bw if bw is not None else (None, None, gb, None, None)
+    _call('dmc_tc_tap_gemm_ex', _ptr(A_hi, BF16), _ptr(A_lo, BF16), c_int(lda), c_long(a_rows), c_int(K),
+          _ptr(B_hi, BF16), _ptr(B_lo, BF16), c_int(b_slices), c_int(N), _ptr(D, F32), c_long(M), c_int(ldD),
+          c_int(Hp), c_int(Wp), c_int(len(shift)), _iarr(shift), _iarr(bsel), _ptr(stats, F64), c_int(stats_ld),
+          _ptr(bY, F32), _ptr(bact, BF16), _ptr(bgb, F32), _ptr(bmean, F32), _ptr(binv, F32), _stream())
+
+
+def wgrad_gemm_ex(G_hi, G_lo, X_hi, X_lo, dW, *, ldg, ldx, P, Cout, Cin, shift, bsel, workspace=None):
+    _call('dmc_tc_wgrad_ex', _ptr(G_hi, BF16), _ptr(G_lo, BF16), c_int(ldg), c_long(P), c_int(Cout),
+          _ptr(X_hi, BF16), _ptr(X_lo, BF16), c_int(ldx), c_int(Cin), _ptr(dW, F32), c_int(len(shift)),
+          _iarr(shift), _iarr(bsel), _ptr(workspace, F32),
+          c_long(0 if workspace is None else workspace.numel()), _stream())
+
+
+def i3d_unpack(data, B, Cd, T, HW, mv, res, flow):
+    _call('dmc_i3d_unpack', _ptr(data, F32), c_int(B), c_int(Cd), c_int(T), c_long(HW), _ptr(mv, F32),
+          _ptr(res, F32), _ptr(flow, F32), _stream())
+
+
+def i3d_stem_im2col(x, x_ns, clips, T, H, W, KP, A_hi, A_lo):
+    _call('dmc_i3d_stem_im2col', _ptr(x, F32), c_long(x_ns), c_int(clips), c_int(T), c_int(H), c_int(W),
+          c_int(KP), _ptr(A_hi, BF16), _ptr(A_lo, BF16), _stream())
+
+
+def i3d_stem_col2im(dA, KP, clips, T, H, W, dX, dx_ns, accumulate):
+    _call('dmc_i3d_stem_col2im', _ptr(dA, F32), c_int(KP), c_int(clips), c_int(T), c_int(H), c_int(W),
+          _ptr(dX, F32), c_long(dx_ns), c_int(1 if accumulate else 0), _stream())
+
+
+def maxpool3d_out_shape(in_thw, kernel, stride):
+    out = (c_int * 3)()
+    fn = _native.lib().dmc_maxpool3d_out_shape
+    fn.restype = c_int
+    _native.check(fn(_iarr(in_thw), _iarr(kernel), _iarr(stride), out), 'dmc_maxpool3d_out_shape')
+    return tuple(int(v) for v in out)
+
+
+def maxpool3d_fwd(in_hi, in_lo, clips, C, in_thw, kernel, stride, out_hi, out_lo, idx):
+    _call('dmc_maxpool3d_fwd', _ptr(in_hi, BF16), _ptr(in_lo, BF16), c_int(clips), c_int(C), _iarr(in_thw),
+          _iarr(kernel), _iarr(stride), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8), _stream())
+
+
+def maxpool3d_bwd(gout, idx, clips, C, in_thw, kernel, stride, add, dX):
+    _call('dmc_maxpool3d_bwd', _ptr(gout, F32), _ptr(idx, U8), c_int(clips), c_int(C), _iarr(in_thw),
+          _iarr(kernel), _iarr(stride), _ptr(add, F32), _ptr(dX, F32), _stream())
+
+
+def i3d_head_pool_fwd(hi, lo, clips, T5, H, W, C, pooled):
+    _call('dmc_i3d_head_pool_fwd', _ptr(hi, BF16), _ptr(lo, BF16), c_int(clips), c_int(T5), c_int(H), c_int(W),
+          c_int(C), _ptr(pooled, F32), _stream())
+
+
+def i3d_head_pool_bwd(dpooled, clips, T5, H, W, C, dX):
+    _call('dmc_i3d_head_pool_bwd', _ptr(dpooled, F32), c_int(clips), c_int(T5), c_int(H), c_int(W), c_int(C),
+          _ptr(dX, F32), _stream())
+
+
+def mul(a, m, out):
+    _call('dmc_mul', _ptr(a, F32), _ptr(m, F32), c_long(a.numel()), _ptr(out, F32), _stream())
+
+
+def add_i64(p, v=1):
+    _call('dmc_add_i64', _ptr(p, I64), c_int(p.numel()), ctypes.c_longlong(v), _stream())
+
+
+def sgd_nesterov_step(p, g, buf, chunks, nchunks, hyper, momentum, grad_scale=1.0):
+    _call('dmc_sgd_nesterov_step', _ptr(p, F32), _ptr(g, F32), _ptr(buf, F32), _ptr(chunks), c_int(nchunks),
+          _ptr(hyper, F32), c_float(momentum), c_float(grad_scale), _stream())
+
+
+def axpy(y, x, a=1.0):
+    _call('dmc_axpy', _ptr(y, F32), _ptr(x, F32), c_float(a), c_long(y.numel()), _stream())

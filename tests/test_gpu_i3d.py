@@ -1,0 +1,417 @@
+"""I3D path on the B200: the new kernels of csrc/i3d.cu against torch on identical inputs, and the I3DEngine
+forward / backward / train step against the oracle (oracle/i3d_oracle.py, pinned bit-exactly on the
+reference's i3d.py) and the reference-generated fixture tests/golden/i3d_b1.npz."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from dmcnet_b200 import ops
+from oracle import i3d_oracle as O          # checker only
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'i3d_b1.npz')
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def split(x):
+    hi = x.to(torch.bfloat16)
+    return hi.contiguous(), (x - hi.float()).to(torch.bfloat16).contiguous()
+
+
+def to_ring(x):          # [B,C,T,H,W] -> [B*(T+1)*(H+1)*(W+1), C] on x's device
+    b, c, t, h, w = x.shape
+    p = torch.zeros(b, t + 1, h + 1, w + 1, c, device=x.device, dtype=x.dtype)
+    p[:, 1:, 1:, 1:, :] = x.permute(0, 2, 3, 4, 1)
+    return p.reshape(-1, c).contiguous()
+
+
+def from_ring(flat, b, c, t, h, w):
+    return flat.reshape(b, t + 1, h + 1, w + 1, -1)[:, 1:, 1:, 1:, :c].permute(0, 4, 1, 2, 3)
+
+
+@pytest.mark.parametrize('kernel,stride,thw', [((1, 3, 3), (1, 2, 2), (4, 12, 12)), ((3, 3, 3), (2, 2, 2), (8, 28, 28)),
+                                               ((2, 2, 2), (2, 2, 2), (4, 14, 14)), ((3, 3, 3), (1, 1, 1), (4, 7, 7))])
+def test_maxpool3d_tf_padding_forward_backward(kernel, stride, thw):
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(5)
+    B, C = 2, 64
+    T, H, W = thw
+    x = torch.relu(torch.randn(B, C, T, H, W, generator=g, device=dev)).requires_grad_(True)
+    ref = F.max_pool3d(F.pad(x, O.tf_same_pad(kernel, stride)), kernel, stride, ceil_mode=True)
+    To, Ho, Wo = ops.maxpool3d_out_shape(thw, kernel, stride)
+    assert tuple(ref.shape[2:]) == (To, Ho, Wo)
+    x_hi, x_lo = split(to_ring(x.detach()))
+    Po = B * (To + 1) * (Ho + 1) * (Wo + 1)
+    o_hi = torch.zeros(Po * C, dtype=torch.bfloat16, device=dev)
+    o_lo = torch.zeros_like(o_hi)
+    idx = torch.zeros(Po * C, dtype=torch.uint8, device=dev)
+    ops.maxpool3d_fwd(x_hi, x_lo, B, C, thw, kernel, stride, o_hi, o_lo, idx)
+    got = from_ring((o_hi.float() + o_lo.float()).view(Po, C), B, C, To, Ho, Wo)
+    xr = from_ring((x_hi.float() + x_lo.float()), B, C, T, H, W)
+    ref_r = F.max_pool3d(F.pad(xr, O.tf_same_pad(kernel, stride)), kernel, stride, ceil_mode=True)
+    assert torch.equal(got, ref_r)
+    go = torch.randn(B, C, To, Ho, Wo, generator=g, device=dev)
+    ref.backward(go)
+    add = torch.randn(B * (T + 1) * (H + 1) * (W + 1), C, generator=g, device=dev)
+    dX = torch.full_like(add, float('nan'))
+    ops.maxpool3d_bwd(to_ring(go), idx, B, C, thw, kernel, stride, add, dX)
+    assert torch.isfinite(dX).all()
+    want = x.grad * (x.detach() > 0) + from_ring(add, B, C, T, H, W) * (x.detach() > 0)
+    got_g = from_ring(dX, B, C, T, H, W) * (x.detach() > 0)          # ties at exactly 0 are killed by the ReLU mask
+    assert rel(got_g, want) < 1e-6
+    ring = dX.view(B, T + 1, H + 1, W + 1, C)
+    assert float(ring[:, 0].abs().max()) == 0 and float(ring[:, :, 0].abs().max()) == 0 and float(ring[:, :, :, 0].abs().max()) == 0
+
+
+def test_stem_im2col_gemm_and_col2im():
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(6)
+    B, T, H, W, KP = 2, 4, 16, 24, 704
+    x = torch.randn(B, 2, T, H, W, generator=g, device=dev).requires_grad_(True)
+    w = (torch.randn(64, 2, 7, 7, 7, generator=g, device=dev) * 0.05)
+    xd = x.detach().double().requires_grad_(True)            # fp64 reference (cuDNN fp32 convs default to TF32)
+    ref = F.conv3d(F.pad(xd, O.tf_same_pad((7, 7, 7), (2, 2, 2))), w.double(), None, 2)
+    To, Ho, Wo = T // 2, H // 2, W // 2
+    P = B * (To + 1) * (Ho + 1) * (Wo + 1)
+    A_hi = torch.zeros(P * KP, dtype=torch.bfloat16, device=dev)
+    A_lo = torch.zeros_like(A_hi)
+    planar = x.detach().permute(0, 2, 1, 3, 4).contiguous()           # [B*T][2][H][W]
+    ops.i3d_stem_im2col(planar, 2 * H * W, B, T, H, W, KP, A_hi, A_lo)
+    A = (A_hi.float() + A_lo.float()).view(P, KP)
+    Wg = torch.zeros(64, KP, device=dev)
+    Wg[:, :686] = w.permute(0, 2, 3, 4, 1).reshape(64, 686)           # k = ((kt*7+kh)*7+kw)*2 + ci
+    got = from_ring(A.double() @ Wg.double().t(), B, 64, To, Ho, Wo)
+    assert rel(got, ref.detach()) < 1e-5
+    ring = A.view(B, To + 1, Ho + 1, Wo + 1, KP)
+    assert float(ring[:, 0].abs().max()) == 0 and float(ring[:, :, 0].abs().max()) == 0
+    go = torch.randn(ref.shape, generator=g, device=dev)
+    ref.backward(go.double())
+    dA = (to_ring(go).double() @ Wg.double()).float().contiguous()    # [P][KP]
+    dX = torch.zeros(B * T, 2, H, W, device=dev)
+    ops.i3d_stem_col2im(dA, KP, B, T, H, W, dX.view(-1), 2 * H * W, False)
+    assert rel(dX.view(B, T, 2, H, W).permute(0, 2, 1, 3, 4), xd.grad) < 1e-5
+
+
+def test_head_pool_and_sgd_nesterov_and_unpack():
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(7)
+    B, C, T5 = 3, 1024, 4
+    x = torch.relu(torch.randn(B, C, T5, 7, 7, generator=g, device=dev)).requires_grad_(True)
+    ref = F.avg_pool3d(x, (2, 7, 7), (1, 1, 1)).squeeze(3).squeeze(3).mean(2)
+    hi, lo = split(to_ring(x.detach()))
+    pooled = torch.zeros(B, C, device=dev)
+    ops.i3d_head_pool_fwd(hi, lo, B, T5, 7, 7, C, pooled)
+    assert rel(pooled, ref) < 1e-5
+    go = torch.randn(B, C, generator=g, device=dev)
+    ref.backward(go)
+    dX = torch.full((B * (T5 + 1) * 8 * 8, C), float('nan'), device=dev)
+    ops.i3d_head_pool_bwd(go, B, T5, 7, 7, C, dX)
+    assert rel(from_ring(dX, B, C, T5, 7, 7), x.grad) < 1e-6
+    # SGD with Nesterov momentum vs torch.optim.SGD, three steps, two hyper rows, grad scale
+    n = 5000
+    p0 = torch.randn(n, generator=g, device=dev)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([{'params': [p_ref]}], lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    p, buf = p0.clone(), torch.zeros(n, device=dev)
+    chunks = torch.tensor([[c0, min(1024, n - c0), 0, 0] for c0 in range(0, n, 1024)], dtype=torch.int32, device=dev)
+    hyper = torch.tensor([[0.01, 1e-4]], device=dev)
+    for _ in range(3):
+        gr = torch.randn(n, generator=g, device=dev)
+        p_ref.grad = gr / 4
+        opt.step()
+        ops.sgd_nesterov_step(p, gr, buf, chunks, chunks.shape[0], hyper.view(-1), 0.9, 0.25)
+    assert rel(p, p_ref.detach()) < 1e-6
+    # sample layout
+    data = torch.randn(2, 7, 4, 8, 8, generator=g, device=dev)
+    mv, res, flow = (torch.zeros(8, c, 8, 8, device=dev) for c in (2, 3, 2))
+    ops.i3d_unpack(data, 2, 7, 4, 64, mv, res, flow)
+    fr = data.transpose(1, 2).reshape(8, 7, 8, 8)
+    assert torch.equal(mv, fr[:, 0:2]) and torch.equal(res, fr[:, 2:5]) and torch.equal(flow, fr[:, 5:7])
+
+
+def test_tap_gemm_on_column_slices_of_3d_maps():
+    """dmc_tc_tap_gemm_ex: 27 taps, A = a column slice of a wider map, D = a column slice, statistics with a
+    row pitch, temporal ring masked; and the fused BatchNorm-backward epilogue on a slice."""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(8)
+    B, T, H, W = 2, 4, 7, 7
+    Cw, c0, K, N, Dw, d0 = 192, 64, 128, 64, 256, 128
+    x = torch.randn(B, K, T, H, W, generator=g, device=dev)
+    w = torch.randn(N, K, 3, 3, 3, generator=g, device=dev) * 0.05
+    ref = F.conv3d(x.double(), w.double(), None, 1, 1)
+    Tp, Hp, Wp = T + 1, H + 1, W + 1
+    P = B * Tp * Hp * Wp
+    Awide = torch.randn(P, Cw, generator=g, device=dev)
+    Awide[:, c0:c0 + K] = to_ring(x)
+    A_hi, A_lo = split(Awide)
+    Wg = w.permute(2, 3, 4, 0, 1).reshape(27, N, K).contiguous()
+    W_hi, W_lo = split(Wg)
+    shift = [(kt - 1) * Hp * Wp + (kh - 1) * Wp + (kw - 1) for kt in range(3) for kh in range(3) for kw in range(3)]
+    D = torch.full((P, Dw), 7.0, device=dev)
+    stats = torch.zeros(2, Dw, dtype=torch.float64, device=dev)
+    ops.tap_gemm_ex(A_hi.view(-1)[c0:], A_lo.view(-1)[c0:], W_hi, W_lo, D.view(-1)[d0:], lda=Cw, a_rows=P, K=K,
+                    b_slices=27, N=N, M=P, ldD=Dw, Hp=ops.pack_hp(Hp, Tp), Wp=Wp, shift=shift, bsel=list(range(27)),
+                    stats=stats.view(-1)[d0:], stats_ld=Dw)
+    torch.cuda.synchronize()
+    got = from_ring(D[:, d0:d0 + N], B, N, T, H, W)
+    assert rel(got, ref) < 5e-5
+    assert float((D[:, :d0] - 7.0).abs().max()) == 0 and float((D[:, d0 + N:] - 7.0).abs().max()) == 0
+    ring = D.view(B, Tp, Hp, Wp, Dw)[..., d0:d0 + N]
+    assert float(ring[:, 0].abs().max()) == 0 and float(ring[:, :, 0].abs().max()) == 0 and float(ring[:, :, :, 0].abs().max()) == 0
+    assert rel(stats[0, d0:d0 + N], ref.double().sum((0, 2, 3, 4))) < 1e-4
+    assert rel(stats[1, d0:d0 + N], (ref.double() ** 2).sum((0, 2, 3, 4))) < 1e-4
+    assert float(stats[:, :d0].abs().max()) == 0
+    # plain sum of two gradient sources
+    gb = torch.randn(P, Dw, generator=g, device=dev)
+    D2 = torch.zeros(P, Dw, device=dev)
+    ops.tap_gemm_ex(A_hi.view(-1)[c0:], A_lo.view(-1)[c0:], W_hi, W_lo, D2.view(-1)[d0:], lda=Cw, a_rows=P, K=K,
+                    b_slices=27, N=N, M=P, ldD=Dw, Hp=ops.pack_hp(Hp, Tp), Wp=Wp, shift=shift, bsel=list(range(27)),
+                    gb=gb.view(-1)[d0:])
+    assert rel(D2[:, d0:d0 + N], D[:, d0:d0 + N] + gb[:, d0:d0 + N]) < 1e-6
+
+
+def _engine_and_oracle(clips=1, T=16, seed=1):
+    from dmcnet_b200.i3d_engine import I3DEngine
+    sd = O.build_state(51, 'DenseNetTiny', seed=seed)
+    eng = I3DEngine(51, clips, T)
+    eng.load_state(sd)
+    return eng, sd
+
+
+def test_i3d_forward_vs_oracle_and_reference_fixture():
+    eng, sd = _engine_and_oracle()
+    data, target = O.make_inputs(1, 16, 51, seed=0)
+    st = {k: v.clone() for k, v in sd.items()}
+    rec = {}
+    with torch.no_grad():
+        logits_o, flow_o = O.i3d_forward(st, data[:, :5], train=True, record=rec)
+    logits, gen_flow = eng.forward_data(data.cuda(), train=True)
+    torch.cuda.synchronize()
+    flow_e = gen_flow.view(1, 16, 2, 224, 224).transpose(1, 2)
+    assert rel(flow_e, flow_o) < 1e-5
+    # per-stage activations (which stage breaks first, if any)
+    stages = [('conv3d_1a_7x7', eng.m_stem, list(range(64))), ('conv3d_2b_1x1', eng.m_2b, list(range(64))),
+              ('conv3d_2c_3x3', eng.m_2c, list(range(192)))]
+    for i, M in enumerate(eng.mixed):
+        cols = eng.mixed[i + 1]['b0'].in_cols if i + 1 < len(eng.mixed) else list(range(1024))
+        stages.append((M['name'], M['m_cat'], cols))
+    errs = {}
+    for name, m, cols in stages:
+        geo = m['geo']
+        a = (m['hi'].float() + m['lo'].float()).view(geo.P, m['width'])[:, cols]
+        errs[name] = rel(from_ring(a, 1, len(cols), geo.T, geo.H, geo.W), rec[name])
+    print('I3D per-stage activation errors:', {k: '%.1e' % v for k, v in errs.items()})
+    assert max(errs.values()) < 1e-3, errs
+    assert rel(logits, logits_o) < 1e-3
+    assert torch.equal(logits.argmax(1).cpu(), logits_o.argmax(1))
+    gold = np.load(GOLD)
+    assert rel(logits, torch.from_numpy(gold['logits'])) < 1e-3
+    # running statistics and counters
+    out = eng.state_dict()
+    for k in ('conv3d_1a_7x7.batch3d.running_mean', 'mixed_5c.branch_3.1.batch3d.running_var'):
+        assert rel(out[k], torch.from_numpy(gold['buf/' + k])) < 1e-3, k
+    assert int(out['mixed_4d.branch_1.1.batch3d.num_batches_tracked']) == 1
+    # eval-mode forward on the updated statistics
+    with torch.no_grad():
+        le_o, _ = O.i3d_forward(st, data[:, :5], train=False)
+    le, _ = eng.forward_data(data.cuda(), train=False)
+    assert rel(le, le_o) < 1e-3
+
+
+def _record(name, rec):
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, 'r02_i3d_parity.json')
+    data = {}
+    if os.path.isfile(path):
+        try:
+            data = json.load(open(path))
+        except ValueError:
+            data = {}
+    data[name] = rec
+    json.dump(data, open(path, 'w'), indent=1, sort_keys=True)
+
+
+def test_i3d_backward_vs_oracle_calibrated_by_fp64():
+    """Whole-network gradients (CE + MSE, the classifier's gradient reaching the generator through the stem)
+    at B = 2.  The I3D gradient is ill conditioned -- 57 BatchNorm'd ReLU layers and four max-pools, a head
+    whose gradient is constant over positions so that every BatchNorm backward cancels most of it -- to
+    the point that the reference's own fp32 arithmetic is 1.2e-2 (median) / 3.8e-2 (worst) away from the
+    float64 evaluation of the same step.  The bf16x3 tensor-core path measures 4.4e-2 / 7.6e-2: the
+    square-root law of DESIGN.md section 5 allows a factor sqrt(2^-17 / 2^-24) = 11 over fp32, measured 3.8.
+    Bars: tight on the head (no switch in between), 6x the fp32 oracle's own distance from float64 elsewhere."""
+    B = 2
+    eng, sd = _engine_and_oracle(clips=B)
+    data, target = O.make_inputs(B, 16, 51, seed=0)
+
+    def oracle_grads(dtype):
+        st = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        for k in st:
+            if not O.is_buffer(k):
+                st[k].requires_grad_(True)
+        lo, fo = O.i3d_forward(st, data[:, :5].to(dtype), train=True)
+        (F.cross_entropy(lo, target) + F.mse_loss(fo, data[:, 5:7].to(dtype))).backward()
+        return {k: v.grad for k, v in st.items() if not O.is_buffer(k)}
+    g32, g64 = oracle_grads(torch.float32), oracle_grads(torch.float64)
+    dev = eng.device
+    eng.zero_grads()
+    eng.forward_data(data.cuda(), train=True)
+    ops.ce_head(eng.logits, B, 1, 51, target.cuda(), 1.0 / B, torch.zeros(B, 51, device=dev), eng.d_logits,
+                torch.zeros(4, device=dev))
+    numel = eng.N * 2 * 224 * 224
+    ops.mse_head(eng.gen_flow, eng.in_flow, numel, 2.0 / numel, eng.dD, torch.zeros(1, dtype=torch.float64, device=dev),
+                 frame_elems=2 * 224 * 224, dgen_ns=eng.dD.shape[1] * 224 * 224)
+    eng.backward(eng.N, cls=True, cls_wgrad=True, gen_grad=True, cls_to_gen=True)
+    torch.cuda.synchronize()
+    e_o = {k: rel_l2(eng.grad_view(k), g32[k]) for k in eng.specs}
+    e_64 = sorted(rel_l2(eng.grad_view(k), g64[k]) for k in eng.specs)
+    o_64 = sorted(rel_l2(g32[k], g64[k]) for k in eng.specs)
+    med = lambda v: v[len(v) // 2]
+    eo = sorted(e_o.values())
+    rec = {'batch': B, 'engine_vs_oracle': [med(eo), eo[-1]], 'engine_vs_fp64': [med(e_64), e_64[-1]],
+           'fp32_oracle_vs_fp64': [med(o_64), o_64[-1]]}
+    print('I3D gradients (median, worst):', rec)
+    _record('backward_b2', rec)
+    for k in ('classifier.weight', 'classifier.bias', 'conv3d_0c_1x1.conv3d.weight', 'conv3d_0c_1x1.conv3d.bias'):
+        assert e_o[k] < 1e-3, (k, e_o[k])
+    assert med(e_64) < 6 * med(o_64) and e_64[-1] < 6 * o_64[-1], rec
+    assert med(eo) < 1e-1 and eo[-1] < 3e-1, rec
+
+
+@pytest.mark.parametrize('optim,iter_size', [('sgd', 1), ('sgd', 2), ('adam', 1)])
+def test_i3d_train_step_vs_oracle(optim, iter_size):
+    """model.fit's non-adversarial iteration (CE + MSE, optimizer + optimizer_mse, iter_size accumulation,
+    stage-two learning rates) for ONE optimizer step (iter_size batches) at B = 1: losses and metrics of every
+    batch, the parameter movement per group.  One step only: the step moves the weights by ~1 %, the two
+    sides then differ by ~7e-4 of that, and by the square-root law of the switch noise the gradients of a
+    second step are no longer comparable element by element."""
+    from dmcnet_b200.i3d_engine import I3DEngine
+    from dmcnet_b200.i3d_trainer import I3DHParams, I3DTrainStep
+    sd = O.build_state(51, 'DenseNetTiny', seed=1)
+    hp_kw = dict(optim=optim, iter_size=iter_size, epoch_thre=0, dropout=0.5)      # stage two: every group moves
+    ref = O.I3DOracleTrainer(sd, O.I3DHParams(**hp_kw))
+    eng = I3DEngine(51, 1, 16)
+    eng.load_state(sd)
+    tr = I3DTrainStep(eng, I3DHParams(**hp_kw))
+    gen = torch.Generator().manual_seed(5)
+    for it in range(iter_size):
+        data, target = O.make_inputs(1, 16, 51, seed=10 + it)
+        mask = eng.draw_dropout_mask(0.5, gen)
+        m_ref = ref.step(data, target, dropout_mask=mask)
+        m = tr.step(data.cuda(), target.cuda(), dropout_mask=mask)
+        assert m['stepped'] == m_ref['stepped'] == (it == iter_size - 1)
+        assert abs(m['loss_ce'] - m_ref['loss_ce']) < 2e-3 * max(1.0, m_ref['loss_ce']), (it, m, m_ref)
+        assert m['top1'] == m_ref['top1'] and m['top5'] == m_ref['top5']
+        assert abs(m['loss_mse'] - m_ref['loss_mse']) < 1e-3 * max(1.0, m_ref['loss_mse'])
+    torch.cuda.synchronize()
+    out, want = eng.state_dict(), ref.state_dict()
+    moved = {}
+    for grp in ('gf', 'base', 'new'):
+        num = den = 0.0
+        for k in eng.specs:
+            from dmcnet_b200.i3d_trainer import param_group_of
+            if param_group_of(k) != grp:
+                continue
+            d_e = out[k].double().cpu() - sd[k].double()
+            d_o = want[k].double() - sd[k].double()
+            num += float((d_e - d_o).norm() ** 2)
+            den += float(d_o.norm() ** 2)
+        moved[grp] = (num / max(den, 1e-300)) ** 0.5
+    print('I3D train step %s iter_size %d: relative error of the parameter movement' % (optim, iter_size), moved)
+    _record('train_step_%s_%d' % (optim, iter_size), moved)
+    assert den > 0
+    # SGD moves a parameter by lr * gradient: the movement inherits the gradient's error; Adam normalises
+    # every element, so elements whose gradient changes sign move the other way (looser)
+    bar = 0.25 if optim == 'sgd' else 0.6
+    assert moved['new'] < (2e-3 if optim == 'sgd' else 5e-2) and moved['base'] < bar and moved['gf'] < bar, moved
+    for k in ('conv3d_1a_7x7.batch3d.running_mean', 'mixed_5c.branch_3.1.batch3d.running_var'):
+        assert rel(out[k], want[k]) < 5e-3, k
+    assert int(out['mixed_4d.branch_1.1.batch3d.num_batches_tracked']) == iter_size
+
+
+@pytest.mark.parametrize('beta_shift,bar', [(4.0, 1e-2), (0.0, 1e-2)])
+def test_two_inception_blocks_forward_backward_vs_fp64(beta_shift, bar):
+    """The intricate part of the plan in isolation and well conditioned: mixed_4c -> mixed_4d on a random input
+    map with a random upstream gradient, against torch fp64 autograd of the oracle's blocks.  Covers the
+    column-slice GEMMs, the merged 1x1x1 pair, the branch max-pool, BatchNorm over a concatenated map, the
+    fused BatchNorm-backward epilogue on slices (mid maps) and on a whole map (previous block), the weight
+    gradients through row pitches and the gather tables.
+    beta_shift = 0: ordinary statistics; a forward error of ~5e-5 flips a ~2e-5 fraction of the ReLU
+    switches and the relative L2 error of a gradient is the square root of that fraction (DESIGN.md section
+    5) -- measured worst 4.6e-3.  beta_shift = 4: every pre-activation sits four standard deviations above
+    the switch (no flips), but every conv input then has mean 4 and unit spread: the products' bf16x3 rounding
+    is relative to the mean while BatchNorm removes it, a ~100-fold amplification of the 1e-5 arithmetic
+    error -- measured worst 3.5e-3, on other tensors.  A plumbing error (a wrong slice, tap or table) is O(1)
+    on the tensors it touches; bar 1e-2."""
+    from dmcnet_b200.i3d_engine import I3DEngine, MIXED
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(11)
+    clips = 2
+    sd = O.build_state(51, 'DenseNetTiny', seed=3)
+    for k in sd:                                    # non-trivial BatchNorm affine parameters
+        if k.endswith('batch3d.weight'):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+        elif k.endswith('batch3d.bias'):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g) + beta_shift
+    eng = I3DEngine(51, clips, 16)
+    eng.load_state(sd)
+    A, Bk = eng.mixed[3], eng.mixed[4]              # mixed_4c, mixed_4d
+    geo = A['geo']
+    T, H, W = geo.thw
+    cin = MIXED[3][1]
+    x = torch.relu(torch.randn(clips, cin, T, H, W, generator=g))
+    go = torch.randn(clips, MIXED[5][1], T, H, W, generator=g)
+    # reference: fp64 autograd
+    st = {k: (v.double().requires_grad_(True) if v.is_floating_point() and not O.is_buffer(k) else
+              (v.double() if v.is_floating_point() else v.clone())) for k, v in sd.items()}
+    xd = x.double().requires_grad_(True)
+    ya = O._mixed(st, 'mixed_4c', xd, True)
+    yb = O._mixed(st, 'mixed_4d', ya, True)
+    yb.backward(go.double())
+    # engine
+    cols_in = torch.tensor(A['b0'].in_cols)
+    xin = torch.zeros(geo.P, A['Kin'])
+    xin[:, cols_in] = to_ring(x)
+    x_hi, x_lo = split(xin.to(dev))
+    x_hi, x_lo = x_hi.view(-1), x_lo.view(-1)
+    eng._prep_weights()
+    ops.memset_zero(eng._sums)
+    a_hi, a_lo = eng._mixed_fwd(A, x_hi, x_lo, True)
+    b_hi, b_lo = eng._mixed_fwd(Bk, a_hi, a_lo, True)
+    torch.cuda.synchronize()
+    cols_a, cols_b = torch.tensor(Bk['b0'].in_cols), torch.tensor(eng.mixed[5]['b0'].in_cols)
+    ya_e = from_ring((a_hi.float() + a_lo.float()).view(geo.P, -1)[:, cols_a.to(dev)], clips, len(cols_a), T, H, W)
+    yb_e = from_ring((b_hi.float() + b_lo.float()).view(geo.P, -1)[:, cols_b.to(dev)], clips, len(cols_b), T, H, W)
+    assert rel(ya_e, ya.detach()) < 5e-5 and rel(yb_e, yb.detach()) < 1e-4
+    gin = torch.zeros(geo.P, Bk['cat'].width)
+    gin[:, cols_b] = to_ring(go)
+    eng.zero_grads()
+    ops.memset_zero(eng._sums2)
+    ops.memset_zero(eng._dwg)
+    eng.gbuf[0][:gin.numel()].copy_(gin.view(-1).to(dev))
+    cur = eng._mixed_bwd(Bk, a_hi, a_lo, 0, None, False, True, (A['cat'], A['m_cat'], 0))
+    cur = eng._mixed_bwd(A, x_hi, x_lo, cur, None, True, True, None)
+    torch.cuda.synchronize()
+    dX = eng.gbuf[cur][:geo.P * A['Kin']].view(geo.P, A['Kin'])[:, cols_in.to(dev)]
+    errs = {'dX': rel_l2(from_ring(dX, clips, cin, T, H, W) * (x > 0).to(dev), xd.grad * (x > 0))}
+    for blk in ('mixed_4c', 'mixed_4d'):
+        for k in eng.specs:
+            if k.startswith(blk):
+                errs[k] = rel_l2(eng.grad_view(k), st[k].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print('two-block backward (beta shift %g): worst' % beta_shift, [(k, '%.1e' % v) for k, v in worst])
+    assert worst[0][1] < bar, worst
