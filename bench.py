@@ -18,6 +18,8 @@ measured in the same process right after the headline with the same W / K:
   configs.config3        dmcnet_GAN step pair (D-step + G-step, Discriminator3, 101 classes), B=64 per GPU
   configs.config4_strong dmcnet_GAN, 51 classes, GLOBAL batch 512 fixed and sharded 512/N per GPU
                          (strong scaling; one GPU holds all 512 clips at N=1)
+  configs.config5_i3d    dmcnet_I3D (DenseNetTiny estimator + I3D), 16-frame clips, GLOBAL batch 32 sharded 32/N
+                         per GPU (the reference's nn.DataParallel split of --batch-size 32), SGD-Nesterov
 
   value      clips/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e        clips/s through FusedTrainStep.step_pipelined_u8() with HOST (pinned) input: the uint8
@@ -310,6 +312,99 @@ def measure(cfg_name, B, args, *, rank, local_rank, world, clocks=False, rooflin
     return out
 
 
+# ---------------------------------------------------------------------------- BASELINE config 5 (I3D)
+I3D_GLOBAL_BATCH, I3D_CLIP_LEN = 32, 16
+# forward 7.31 (estimator, 16 frames) + 51.17 (I3D) GFLOP per clip; a train step is
+# counted as 3x the forward (data + weight gradients; the input layers' data gradients are small)
+I3D_GFLOP_PER_CLIP = 3.0 * (7.31 + 51.17)
+
+
+def measure_i3d(B, args, *, rank, local_rank, world):
+    """dmcnet_I3D train step (DenseNetTiny estimator + I3D, CE + MSE, SGD-Nesterov, fit()'s non-adversarial
+    iteration) at B clips of 16 frames per rank: resident and end-to-end (pinned fp32 sample tensor) rates."""
+    import torch
+    import torch.distributed as dist
+    from dmcnet_b200 import ops
+    from dmcnet_b200.i3d_engine import I3DEngine
+    from dmcnet_b200.i3d_trainer import I3DHParams, I3DTrainStep
+    from dmcnet_b200.i3d_model import build_i3d_state
+    T, H, W = I3D_CLIP_LEN, 224, 224
+    g = torch.Generator().manual_seed(4321 + rank)
+    data = torch.empty(B, 7, T, H, W).normal_(generator=g).pin_memory()
+    target = torch.randint(0, 51, (B,), generator=g).pin_memory()
+    eng = I3DEngine(51, B, T)
+    eng.load_state(build_i3d_state(51, 'DenseNetTiny', seed=1))
+    tr = I3DTrainStep(eng, I3DHParams(epoch_thre=0), world_size=world)
+    mask = eng.draw_dropout_mask(0.5, g)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+    d_data, d_target = data.cuda(), target.cuda()
+    steps = max(2, min(args.steps, 5))
+    out = {}
+    for key, dd, tt, met in (('resident', d_data, d_target, False), ('e2e', data, target, True)):
+        for _ in range(2):
+            tr.step(dd, tt, dropout_mask=mask, metrics=met)
+        ops.reset_launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = tr.step(dd, tt, dropout_mask=mask, metrics=met)
+        e1.record()
+        barrier()
+        out[key] = max_over_ranks(e0.elapsed_time(e1) / steps)
+        if key == 'resident':
+            launches = ops.launch_count()
+    clips = B * world
+    res = {'workload': 'dmcnet_I3D train step (BASELINE config 5): DenseNetTiny estimator + I3D (Inception-3D), CE + MSE, '
+                       'SGD-Nesterov, B=%d clips x 16 frames x 224x224 per GPU, 51 classes' % B,
+           'clips_per_gpu': B, 'global_batch': clips, 'value': clips / (out['resident'] * 1e-3), 'unit': 'clips/s',
+           'ms_per_step': out['resident'], 'steps': steps,
+           'e2e': {'value': clips / (out['e2e'] * 1e-3), 'unit': 'clips/s', 'ms_per_step': out['e2e'],
+                   'h2d_bytes_per_step': data.numel() * 4 + target.numel() * 8, 'd2h_bytes_per_step': 4 * 4 + 8},
+           'gpu_launches': int(launches), 'algorithmic_tflops': I3D_GFLOP_PER_CLIP * clips / out['resident'],
+           'last_metrics': last, 'cuda_graph': False}
+    del tr, eng, d_data
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_i3d_rate(steps, warmup, sample_batch):
+    """The oracle's restatement of the I3D iteration (pinned bit-exactly on the reference's i3d.py) on all host
+    threads; median step rate."""
+    import torch
+    from oracle import i3d_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = O.I3DOracleTrainer(O.build_state(51, 'DenseNetTiny', seed=1), O.I3DHParams(epoch_thre=0))
+    data, target = O.make_inputs(sample_batch, I3D_CLIP_LEN, 51, seed=0)
+    for _ in range(warmup):
+        tr.step(data, target)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.step(data, target)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
+    return {'value': sample_batch / dt, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+            'sample': 'median of %d timed steps after %d warm-up, B=%d clips x 16 frames of the same workload, torch CPU '
+                      'fp32, %d threads' % (steps, warmup, sample_batch, cores)}
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
@@ -359,9 +454,14 @@ def main():
             plan.append(('config3', 'gan', args.batch, 'weak'))
         if STRONG_GLOBAL_BATCH % world == 0:
             plan.append(('config4_strong', 'gan51', STRONG_GLOBAL_BATCH // world, 'strong'))
+        if I3D_GLOBAL_BATCH % world == 0:
+            plan.append(('config5_i3d', 'i3d', I3D_GLOBAL_BATCH // world, 'strong'))
         for key, cfg_name, b, mode in plan:
             try:
-                r = measure(cfg_name, b, args, roofline=(key == 'config3'), **kw)
+                if cfg_name == 'i3d':
+                    r = measure_i3d(b, args, **kw)
+                else:
+                    r = measure(cfg_name, b, args, roofline=(key == 'config3'), **kw)
                 r['scaling'] = mode
                 extras[key] = r
             except Exception as e:  # noqa: BLE001  (an extra must never take the headline down)
@@ -396,6 +496,8 @@ def main():
         if 'config3' in extras and 'error' not in extras['config3']:
             b3 = cpu_reference_rate('gan', 5, 1, 16)
             extras['config3']['cpu_baseline'] = {k: b3[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        if 'config5_i3d' in extras and 'error' not in extras['config5_i3d']:
+            extras['config5_i3d']['cpu_baseline'] = cpu_i3d_rate(3, 1, 2)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -415,3 +415,41 @@ def test_two_inception_blocks_forward_backward_vs_fp64(beta_shift, bar):
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
     print('two-block backward (beta shift %g): worst' % beta_shift, [(k, '%.1e' % v) for k, v in worst])
     assert worst[0][1] < bar, worst
+
+
+def test_dropin_i3d_module_with_torch_autograd_and_optimizer():
+    """``from network.i3d import I3D`` as a reference user drives it: nn.Module forward(node='flow+logit'),
+    criterion, loss.backward(), a torch optimizer on its parameters."""
+    from dmcnet_b200.dropin.dmcnet_I3D.network.i3d import I3D
+    torch.manual_seed(1)
+    net = I3D(51, modality='flow+mp4', dropout_prob=0, arch_estimator='DenseNetTiny')
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ref_sd = O.build_state(51, 'DenseNetTiny', seed=1)
+    assert all(torch.equal(sd[k], ref_sd[k]) for k in ref_sd)
+    net.cuda().train()
+    data, target = O.make_inputs(1, 16, 51, seed=0)
+    st = {k: (v.clone() if O.is_buffer(k) else v.clone().requires_grad_(True)) for k, v in ref_sd.items()}
+    lo, fo = O.i3d_forward(st, data[:, :5], train=True)
+    (F.cross_entropy(lo, target) + F.mse_loss(fo, data[:, 5:7])).backward()
+    d = data.cuda()
+    logits, flow = net(d[:, :5].contiguous(), node='flow+logit')
+    assert tuple(flow.shape) == (1, 2, 16, 224, 224)
+    assert rel(logits, lo) < 1e-3 and rel(flow, fo) < 1e-5
+    loss = F.cross_entropy(logits, target.cuda()) + F.mse_loss(flow, d[:, 5:7])
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    opt.zero_grad()
+    loss.backward()
+    named = dict(net.named_parameters())
+    assert rel_l2(named['classifier.weight'].grad, st['classifier.weight'].grad) < 1e-3
+    assert rel_l2(named['gen_flow_model.predict_flow.weight'].grad, st['gen_flow_model.predict_flow.weight'].grad) < 0.3
+    before = named['classifier.weight'].detach().clone()
+    opt.step()
+    assert float((named['classifier.weight'].detach() - before).abs().max()) > 0
+    # the engine sees the optimizer's update (parameters are views of its bucket); eval forward, logits only
+    net.eval()
+    with torch.no_grad():
+        out = net(d[:, :5].contiguous())
+    assert tuple(out.shape) == (1, 51) and torch.isfinite(out).all()
+    assert int(net.state_dict()['conv3d_2b_1x1.batch3d.num_batches_tracked']) == 1
+    with pytest.raises(NotImplementedError):
+        net(d[:, :5].contiguous(), node='D')
