@@ -212,31 +212,41 @@ __host__ __device__ inline int dmc_padded(int h) { return h + 1 + DMC_PAD_HI; }
 __host__ __device__ inline int dmc_unpadded(int hp) { return hp - 1 - DMC_PAD_HI; }
 // 3-D maps (I3D, code/dmcnet_I3D/network/i3d.py): [clips][T+1][H+1][W+1][C] with the same shared zero ring
 // on the low side of EVERY dimension.  The kernels below keep their (Hp, Wp) signature: the padded
-// temporal extent travels in the high half of Hp (Hp_arg = Hp | Tp << 16, dmc_pack_hp), and a row is
-// interior when its (t, h, w) are all >= 1.  Tp = 0 (every 2-D caller) costs one uniform branch.
-__host__ __device__ inline int dmc_pack_hp(int Hp, int Tp) { return Hp | (Tp << 16); }
+// temporal extent travels in the high half of Hp (Hp_arg = Hp | Tp << 16 | t_hi << 30, dmc_pack_hp), and a
+// row is interior when its (t, h, w) are all >= 1 -- and, with t_hi = 1, its frame is not the LAST of the
+// Tp either (the I3D stem map keeps one zero frame behind each clip as well, csrc/i3d.cu).  Tp = 0 (every
+// 2-D caller) costs one uniform branch.
+__host__ __device__ inline int dmc_pack_hp(int Hp, int Tp, int t_hi = 0) { return Hp | (Tp << 16) | (t_hi << 30); }
 __host__ __device__ inline bool interior(long q, int Hp, int Wp) {
   // q < 2^31 for every tensor this library builds: 32-bit unsigned division is ~5x cheaper
-  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu, ut = (unsigned)Hp >> 16;
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu;
+  const unsigned ut = ((unsigned)Hp >> 16) & 0x3fffu, thi = ((unsigned)Hp >> 30) & 1u;
   const unsigned row = uq / uw;
   const unsigned wp = uq - row * uw;
   const unsigned fr = row / uh;
   const unsigned hp = row - fr * uh;
   bool ok = wp >= 1u && wp + DMC_PAD_HI < uw && hp >= 1u && hp + DMC_PAD_HI < uh;
-  if (ut) ok = ok && (fr % ut) >= 1u;
+  if (ut) {
+    const unsigned tp = fr % ut;
+    ok = ok && tp >= 1u && tp + thi < ut;
+  }
   return ok;
 }
 
 // Same layout with a zero ring of R rows / columns (dilated convolutions: R >= dilation), pixel (h, w)
 // at (h + R, w + R); R = 1 is `interior` above.
 __host__ __device__ inline bool interior_r(long q, int Hp, int Wp, int R) {
-  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu, ut = (unsigned)Hp >> 16;
+  const unsigned uq = (unsigned)q, uw = (unsigned)Wp, uh = (unsigned)Hp & 0xffffu;
+  const unsigned ut = ((unsigned)Hp >> 16) & 0x3fffu, thi = ((unsigned)Hp >> 30) & 1u;
   const unsigned row = uq / uw;
   const unsigned wp = uq - row * uw;
   const unsigned fr = row / uh;
   const unsigned hp = row - fr * uh;
   bool ok = wp >= (unsigned)R && hp >= (unsigned)R;
-  if (ut) ok = ok && (fr % ut) >= (unsigned)R;
+  if (ut) {
+    const unsigned tp = fr % ut;
+    ok = ok && tp >= (unsigned)R && tp + thi < ut;
+  }
   return ok;
 }
 

@@ -6,7 +6,8 @@
 // "SAME" convolution is then a 27-tap GEMM with flat row shifts dt*Hp*Wp + dh*Wp + dw, a 1x1x1
 // convolution a one-tap GEMM (csrc/gemm_tc.cu).  What is left for this file:
 //   * the sample layout [B][7][T][H][W] -> per-frame planar mv / residual / flow,
-//   * the 7x7x7 stride-2 stem as an explicit im2col operand (K = 686 -> 704) and its transpose,
+//   * the 7x7x7 stride-2 stem: spatial patches of every frame (K = 98 -> 128) for a 7-tap temporal GEMM, and
+//     the transpose of that gather,
 //   * MaxPool3dTFPadding (TF "SAME": zeros appended on the HIGH side, ceil_mode) forward / backward,
 //   * AvgPool3d((2,7,7)) + the mean over the remaining temporal positions, folded into one weighted mean,
 //   * dropout mask multiply, SGD with Nesterov momentum over the flat bucket (train_model.py:129-142).
@@ -46,80 +47,74 @@ i3d_unpack_kernel(const float* __restrict__ data, int B, int Cd, int T, int HW4,
   }
 }
 
-// ------------------------------------------------------------------ stem im2col
-// x planar [clips*T][2][H][W] (frame stride x_ns) -> A hi/lo [clips][To+1][Ho+1][Wo+1][KP] with
-// k = ((kt*7 + kh)*7 + kw)*2 + ci = x[ci][2to+kt-2][2ho+kh-2][2wo+kw-2] (TF "SAME" for kernel 7, stride 2:
-// 2 zeros in front, 3 behind, i3d.py:299-315), zero for k >= 686 and outside the clip.  Ring rows are
-// never written (the buffer is allocated zeroed).  One thread per (row, kt, kh): 14 values -> 7 bf16x2.
+// ------------------------------------------------------------------ stem operand
+// Conv3d(2, 64, 7, stride 2) with TF "SAME" padding (2 zeros in front, 3 behind, i3d.py:299-315) as a
+// 7-tap GEMM over the temporal kernel index: the spatial 7x7x2 patch of every INPUT frame at the output's
+// spatial positions is the K dimension (98 -> 128 columns), and output frame `to` reads input frames
+// 2*to + kt - 2.  Frames are split by parity into two phases so that the stride-2 walk becomes a unit
+// frame shift:  A2[phase][clip][tp][ho+1][wo+1][(kh*7+kw)*2+ci] = x[ci][t = 2*(tp-1)+phase][2ho+kh-2][2wo+kw-2],
+// tp in 1..T/2; frames tp = 0 and tp = T/2+1 stay zero (the taps reach one frame back and two ahead).
+// 3x less operand traffic than a full 686-column im2col, and the data gradient comes back in the same form.
 __global__ void __launch_bounds__(256)
-i3d_stem_im2col_kernel(const float* __restrict__ x, long x_ns, int clips, int T, int H, int W, int KP,
-                       bf16* __restrict__ A_hi, bf16* __restrict__ A_lo) {
-  const int To = T / 2, Ho = H / 2, Wo = W / 2;
-  const int Tp = To + 1, Hp = Ho + 1, Wp = Wo + 1;
-  const long units = (long)clips * To * Ho * Wo * 49;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % 49);
-    long r = i / 49;
-    const int wo = (int)(r % Wo); r /= Wo;
-    const int ho = (int)(r % Ho); r /= Ho;
-    const int to = (int)(r % To);
-    const int n = (int)(r / To);
-    const int kt = kk / 7, kh = kk % 7;
-    const int t = 2 * to + kt - 2, h = 2 * ho + kh - 2;
-    const long row = (((long)n * Tp + to + 1) * Hp + ho + 1) * Wp + wo + 1;
-    bf16* oh = A_hi + row * KP + kk * 14;
-    bf16* ol = A_lo + row * KP + kk * 14;
-    const bool in_th = t >= 0 && t < T && h >= 0 && h < H;
-    const float* f0 = x + ((long)n * T + (in_th ? t : 0)) * x_ns + (long)(in_th ? h : 0) * W;
-    const float* f1 = f0 + (long)H * W;
-#pragma unroll
-    for (int kw = 0; kw < 7; ++kw) {
-      const int w = 2 * wo + kw - 2;
-      float v0 = 0.f, v1 = 0.f;
-      if (in_th && w >= 0 && w < W) { v0 = __ldg(f0 + w); v1 = __ldg(f1 + w); }
-      bf16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      __nv_bfloat162 hh, ll;
-      hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
-      *reinterpret_cast<__nv_bfloat162*>(oh + 2 * kw) = hh;
-      *reinterpret_cast<__nv_bfloat162*>(ol + 2 * kw) = ll;
+i3d_stem_patches_kernel(const float* __restrict__ x, long x_ns, int clips, int T, int H, int W,
+                        bf16* __restrict__ A_hi, bf16* __restrict__ A_lo) {
+  const int Tq = T / 2, Ho = H / 2, Wo = W / 2;
+  const int Tp = Tq + 2, Hp = Ho + 1, Wp = Wo + 1;
+  const unsigned rows = (unsigned)(clips * T * Ho * Wo);        // (input frame, ho, wo)
+  const long phase_rows = (long)clips * Tp * Hp * Wp;
+  const int kk = threadIdx.x & 63, sub = threadIdx.x >> 6;      // 49 of 64 lanes: (kh, kw); 4 rows per block
+  if (kk >= 49) return;
+  const int kh = kk / 7, kw = kk % 7;
+  for (unsigned r = blockIdx.x * 4 + sub; r < rows; r += gridDim.x * 4) {
+    const unsigned wo = r % (unsigned)Wo, r1 = r / (unsigned)Wo;
+    const unsigned ho = r1 % (unsigned)Ho, f = r1 / (unsigned)Ho;      // f = clip * T + t
+    const unsigned t = f % (unsigned)T, n = f / (unsigned)T;
+    const int h = 2 * (int)ho + kh - 2, w = 2 * (int)wo + kw - 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* f0 = x + (long)f * x_ns + (long)h * W + w;
+      v0 = __ldg(f0);
+      v1 = __ldg(f0 + (long)H * W);
     }
+    bf16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    __nv_bfloat162 hh, ll;
+    hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
+    const long row = (t & 1u) * phase_rows + (((long)n * Tp + (t >> 1) + 1) * Hp + ho + 1) * Wp + wo + 1;
+    *reinterpret_cast<__nv_bfloat162*>(A_hi + row * 128 + kk * 2) = hh;
+    *reinterpret_cast<__nv_bfloat162*>(A_lo + row * 128 + kk * 2) = ll;
   }
 }
 
-// Transpose of the im2col: dX[n*T + t][ci][h][w] (+)= sum over the (kt, kh, kw) whose output position
-// (to, ho, wo) = ((t+2-kt)/2, ...) is integral and inside the map of dA[row(to,ho,wo)][k].
+// Transpose for the data gradient: dX[clip*T + t][ci][h][w] (+)= sum over the (kh, kw) whose output position
+// ((h+2-kh)/2, (w+2-kw)/2) is integral and inside the map of dA2[t & 1][row(clip, t/2+1, ho+1, wo+1)][(kh*7+kw)*2+ci].
 __global__ void __launch_bounds__(256)
-i3d_stem_col2im_kernel(const float* __restrict__ dA, int KP, int clips, int T, int H, int W,
-                       float* __restrict__ dX, long dx_ns, int accumulate) {
-  const int To = T / 2, Ho = H / 2, Wo = W / 2;
-  const int Tp = To + 1, Hp = Ho + 1, Wp = Wo + 1;
-  const long total = (long)clips * T * H * W;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    long r = i / W;
-    const int h = (int)(r % H); r /= H;
-    const int t = (int)(r % T);
-    const int n = (int)(r / T);
+i3d_stem_patches_bwd_kernel(const float* __restrict__ dA, int clips, int T, int H, int W, float* __restrict__ dX,
+                            long dx_ns, int accumulate) {
+  const int Tq = T / 2, Ho = H / 2, Wo = W / 2;
+  const int Tp = Tq + 2, Hp = Ho + 1, Wp = Wo + 1;
+  const long phase_rows = (long)clips * Tp * Hp * Wp;
+  const unsigned total = (unsigned)(clips * T * H * W);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned w = i % (unsigned)W, r1 = i / (unsigned)W;
+    const unsigned h = r1 % (unsigned)H, f = r1 / (unsigned)H;
+    const unsigned t = f % (unsigned)T, n = f / (unsigned)T;
+    const long base = (t & 1u) * phase_rows + (((long)n * Tp + (t >> 1) + 1) * Hp) * Wp;
     float a0 = 0.f, a1 = 0.f;
-    for (int kt = (t & 1); kt < 7; kt += 2) {            // t + 2 - kt even
-      const int to = (t + 2 - kt) / 2;
-      if (t + 2 - kt < 0 || to >= To) continue;
-      for (int kh = (h & 1); kh < 7; kh += 2) {
-        const int ho = (h + 2 - kh) / 2;
-        if (h + 2 - kh < 0 || ho >= Ho) continue;
-        for (int kw = (w & 1); kw < 7; kw += 2) {
-          const int wo = (w + 2 - kw) / 2;
-          if (w + 2 - kw < 0 || wo >= Wo) continue;
-          const long row = (((long)n * Tp + to + 1) * Hp + ho + 1) * Wp + wo + 1;
-          const float2 v = __ldg(reinterpret_cast<const float2*>(dA + row * KP + ((kt * 7 + kh) * 7 + kw) * 2));
-          a0 += v.x;
-          a1 += v.y;
-        }
+    for (int kh = (int)(h & 1u); kh < 7; kh += 2) {
+      const int ho = ((int)h + 2 - kh) / 2;
+      if ((int)h + 2 - kh < 0 || ho >= Ho) continue;
+      for (int kw = (int)(w & 1u); kw < 7; kw += 2) {
+        const int wo = ((int)w + 2 - kw) / 2;
+        if ((int)w + 2 - kw < 0 || wo >= Wo) continue;
+        const long row = base + (long)(ho + 1) * Wp + wo + 1;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(dA + row * 128 + (kh * 7 + kw) * 2));
+        a0 += v.x;
+        a1 += v.y;
       }
     }
-    float* o0 = dX + ((long)n * T + t) * dx_ns + (long)h * W + w;
+    float* o0 = dX + (long)f * dx_ns + (long)h * W + w;
     float* o1 = o0 + (long)H * W;
     if (accumulate) { *o0 += a0; *o1 += a1; } else { *o0 = a0; *o1 = a1; }
   }
@@ -130,108 +125,157 @@ struct Pool3 {
   int Ti, Hi, Wi, To, Ho, Wo;      // interior extents of the input / output maps
   int kt, kh, kw, st, sh, sw;      // window, stride
   int pt, ph, pw;                  // zeros in FRONT of each dimension (TF "SAME": pad_along / 2)
+  int t_hi;                        // extra zero frames behind each clip of the INPUT map (the stem map has one)
 };
 
 // in hi/lo [clips][Ti+1][Hi+1][Wi+1][C] -> out hi/lo [clips][To+1][Ho+1][Wo+1][C] (interior rows only; the
 // output buffers are allocated zeroed) and idx [rows_out][C] = window position (dt*kh + dh)*kw + dw of the
 // maximum, 255 when a padding zero wins.  Scan order and strict '>' as ATen's max_pool3d: the first
 // maximum wins.  Positions outside the map are the ConstantPad3d zeros of i3d.py:380-388.
+// One thread = 4 channels x WB consecutive outputs of a row: every input of the union of their windows is
+// loaded once (WB + 2 instead of 3 * WB positions per (dt, dh) at stride 1) -- the kernel is bound by L2 reads.
+template <int WB>
 __global__ void __launch_bounds__(256)
 maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int clips, int C,
                      const Pool3 g, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
                      uint8_t* __restrict__ idx) {
   const int C4 = C / 4;
-  const long units = (long)clips * g.To * g.Ho * g.Wo * C4;
-  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
+  const int wblocks = (g.Wo + WB - 1) / WB;
+  const long units = (long)clips * g.To * g.Ho * wblocks * C4;
+  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     long r = i / C4;
-    const int wo = (int)(r % g.Wo); r /= g.Wo;
+    const int wo0 = (int)(r % wblocks) * WB; r /= wblocks;
     const int ho = (int)(r % g.Ho); r /= g.Ho;
     const int to = (int)(r % g.To);
     const int n = (int)(r / g.To);
-    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    uint2 bh = make_uint2(0u, 0u), bl = make_uint2(0u, 0u);
-    bf16* bhp = reinterpret_cast<bf16*>(&bh);
-    bf16* blp = reinterpret_cast<bf16*>(&bl);
-    uint8_t bi[4] = {255, 255, 255, 255};
+    float best[WB][4];
+    uint2 bh[WB], bl[WB];
+    uint32_t bi[WB];                         // four window codes, one byte per channel
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      best[j][0] = best[j][1] = best[j][2] = best[j][3] = -INFINITY;
+      bh[j] = make_uint2(0u, 0u); bl[j] = make_uint2(0u, 0u); bi[j] = 0xffffffffu;
+    }
+    const int w_lo = wo0 * g.sw - g.pw, w_hi = (wo0 + WB - 1) * g.sw - g.pw + g.kw - 1;
     for (int dt = 0; dt < g.kt; ++dt) {
       const int t = to * g.st + dt - g.pt;
       for (int dh = 0; dh < g.kh; ++dh) {
         const int h = ho * g.sh + dh - g.ph;
-        for (int dw = 0; dw < g.kw; ++dw) {
-          const int w = wo * g.sw + dw - g.pw;
-          const bool in = t >= 0 && t < g.Ti && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi;
+        const bool in_th = t >= 0 && t < g.Ti && h >= 0 && h < g.Hi;
+        const long qrow = (((long)n * Tpi + t + 1) * Hpi + h + 1) * Wpi + 1;
+        for (int w = w_lo; w <= w_hi; ++w) {
+          const bool in = in_th && w >= 0 && w < g.Wi;
           uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
           if (in) {
-            const long q = (((long)n * Tpi + t + 1) * Hpi + h + 1) * Wpi + w + 1;
-            vh = __ldg(reinterpret_cast<const uint2*>(in_hi + q * C + c));
-            vl = __ldg(reinterpret_cast<const uint2*>(in_lo + q * C + c));
+            vh = __ldg(reinterpret_cast<const uint2*>(in_hi + (qrow + w) * C + c));
+            vl = __ldg(reinterpret_cast<const uint2*>(in_lo + (qrow + w) * C + c));
           }
           const bf16* vhp = reinterpret_cast<const bf16*>(&vh);
           const bf16* vlp = reinterpret_cast<const bf16*>(&vl);
-          const uint8_t code = in ? (uint8_t)((dt * g.kh + dh) * g.kw + dw) : (uint8_t)255;
+          float v[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float v = join_bf16(vhp[k], vlp[k]);
-            if (v > best[k]) { best[k] = v; bhp[k] = vhp[k]; blp[k] = vlp[k]; bi[k] = code; }
+          for (int k = 0; k < 4; ++k) v[k] = join_bf16(vhp[k], vlp[k]);
+#pragma unroll
+          for (int j = 0; j < WB; ++j) {
+            const int dw = w - ((wo0 + j) * g.sw - g.pw);
+            if (dw < 0 || dw >= g.kw) continue;
+            const uint32_t code = in ? (uint32_t)((dt * g.kh + dh) * g.kw + dw) : 255u;
+            bf16* bhp = reinterpret_cast<bf16*>(&bh[j]);
+            bf16* blp = reinterpret_cast<bf16*>(&bl[j]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (v[k] > best[j][k]) {
+                best[j][k] = v[k]; bhp[k] = vhp[k]; blp[k] = vlp[k];
+                bi[j] = (bi[j] & ~(0xffu << (8 * k))) | (code << (8 * k));
+              }
           }
         }
       }
     }
-    const long qo = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + wo + 1;
-    *reinterpret_cast<uint2*>(out_hi + qo * C + c) = bh;
-    *reinterpret_cast<uint2*>(out_lo + qo * C + c) = bl;
-    *reinterpret_cast<uchar4*>(idx + qo * C + c) = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+    const long qo = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + wo0 + 1;
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      if (wo0 + j >= g.Wo) break;
+      *reinterpret_cast<uint2*>(out_hi + (qo + j) * C + c) = bh[j];
+      *reinterpret_cast<uint2*>(out_lo + (qo + j) * C + c) = bl[j];
+      *reinterpret_cast<uint32_t*>(idx + (qo + j) * C + c) = bi[j];
+    }
   }
 }
 
 // dX[row_in][c] = add[row_in][c] + sum over the windows containing the position whose idx points at it of
-// g[row_out][c]; every row of dX is written (ring rows: 0).
+// g[row_out][c]; every row of dX is written (ring rows: 0).  One thread = 4 channels x WB consecutive input
+// columns: the idx words of the union of their windows are loaded once.
+template <int WB>
 __global__ void __launch_bounds__(256)
 maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ idx, int clips, int C,
                      const Pool3 g, const float* __restrict__ add, float* __restrict__ dX) {
   const int C4 = C / 4;
-  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
-  const long units = (long)clips * Tpi * Hpi * Wpi * C4;
+  const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
+  const int wblocks = (Wpi + WB - 1) / WB;
+  const long units = (long)clips * Tpi * Hpi * wblocks * C4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
-    const long q = i / C4;
-    long r = q;
-    const int wp = (int)(r % Wpi); r /= Wpi;
+    long r = i / C4;
+    const int wp0 = (int)(r % wblocks) * WB; r /= wblocks;
     const int hp = (int)(r % Hpi); r /= Hpi;
     const int tp = (int)(r % Tpi);
     const int n = (int)(r / Tpi);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tp >= 1 && hp >= 1 && wp >= 1) {
-      const int t = tp - 1, h = hp - 1, w = wp - 1;
-      if (add) acc = __ldg(reinterpret_cast<const float4*>(add + q * C + c));
-      // windows: to * st - pt <= t <= to * st - pt + kt - 1
-      const int to_hi = (t + g.pt) / g.st, ho_hi = (h + g.ph) / g.sh, wo_hi = (w + g.pw) / g.sw;
+    const long q0 = (((long)n * Tpi + tp) * Hpi + hp) * Wpi + wp0;
+    float4 acc[WB];
+#pragma unroll
+    for (int j = 0; j < WB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tp >= 1 && tp <= g.Ti && hp >= 1) {
+      const int t = tp - 1, h = hp - 1;
+      if (add) {
+#pragma unroll
+        for (int j = 0; j < WB; ++j)
+          if (wp0 + j >= 1 && wp0 + j < Wpi) acc[j] = __ldg(reinterpret_cast<const float4*>(add + (q0 + j) * C + c));
+      }
+      // windows along w of the WB columns w0 .. w0 + WB - 1 (w = wp - 1): wo * sw - pw <= w <= wo * sw - pw + kw - 1
+      const int w0 = wp0 - 1;
+      int wo_lo = (w0 + g.pw - g.kw + 1 + g.sw - 1);
+      wo_lo = wo_lo <= 0 ? 0 : wo_lo / g.sw;
+      int wo_hi = (w0 + WB - 1 + g.pw) / g.sw;
+      if (wo_hi >= g.Wo) wo_hi = g.Wo - 1;
+      const int to_hi = (t + g.pt) / g.st, ho_hi = (h + g.ph) / g.sh;
       for (int to = to_hi; to >= 0 && to * g.st - g.pt + g.kt - 1 >= t; --to) {
         if (to >= g.To) continue;
         const int dt = t + g.pt - to * g.st;
         for (int ho = ho_hi; ho >= 0 && ho * g.sh - g.ph + g.kh - 1 >= h; --ho) {
           if (ho >= g.Ho) continue;
           const int dh = h + g.ph - ho * g.sh;
-          for (int wo = wo_hi; wo >= 0 && wo * g.sw - g.pw + g.kw - 1 >= w; --wo) {
-            if (wo >= g.Wo) continue;
-            const int dw = w + g.pw - wo * g.sw;
-            const uint8_t code = (uint8_t)((dt * g.kh + dh) * g.kw + dw);
-            const long qo = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + wo + 1;
-            const uchar4 id = *reinterpret_cast<const uchar4*>(idx + qo * C + c);
-            if (id.x == code || id.y == code || id.z == code || id.w == code) {
-              const float4 gv = __ldg(reinterpret_cast<const float4*>(gout + qo * C + c));
-              if (id.x == code) acc.x += gv.x;
-              if (id.y == code) acc.y += gv.y;
-              if (id.z == code) acc.z += gv.z;
-              if (id.w == code) acc.w += gv.w;
+          const int cbase = (dt * g.kh + dh) * g.kw;
+          const long qorow = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + 1;
+          for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+            const uint32_t id = __ldg(reinterpret_cast<const uint32_t*>(idx + (qorow + wo) * C + c));
+            // the codes this output can hold for our columns: cbase + dw, dw = w - (wo * sw - pw) in [0, kw)
+            const uint32_t d0 = (id & 0xffu) - cbase, d1 = ((id >> 8) & 0xffu) - cbase,
+                           d2 = ((id >> 16) & 0xffu) - cbase, d3 = (id >> 24) - cbase;
+            const uint32_t kwu = (uint32_t)g.kw;
+            if (d0 >= kwu && d1 >= kwu && d2 >= kwu && d3 >= kwu) continue;
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(gout + (qorow + wo) * C + c));
+            const int wbase = wo * g.sw - g.pw - w0;          // column index j of dw = 0
+#pragma unroll
+            for (int j = 0; j < WB; ++j) {
+              const uint32_t dw = (uint32_t)(j - wbase);
+              if (dw >= kwu || wp0 + j < 1 || wp0 + j >= Wpi) continue;
+              if (d0 == dw) acc[j].x += gv.x;
+              if (d1 == dw) acc[j].y += gv.y;
+              if (d2 == dw) acc[j].z += gv.z;
+              if (d3 == dw) acc[j].w += gv.w;
             }
           }
         }
       }
     }
-    *reinterpret_cast<float4*>(dX + q * C + c) = acc;
+#pragma unroll
+    for (int j = 0; j < WB; ++j) {
+      if (wp0 + j >= Wpi) break;
+      *reinterpret_cast<float4*>(dX + (q0 + j) * C + c) = (wp0 + j >= 1) ? acc[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -348,31 +392,34 @@ extern "C" int dmc_i3d_unpack(const float* data, int B, int Cd, int T, long HW, 
   return dmc_check_launch("i3d_unpack_kernel");
 }
 
-// A_hi / A_lo [clips][T/2+1][H/2+1][W/2+1][KP] (zero-initialised by the caller once; ring rows and the
-// columns >= 686 are never written) = im2col of x [clips*T][2][H][W] for Conv3d(2, 64, 7, stride 2) with
-// TF "SAME" padding (2 in front, 3 behind); column k = ((kt*7 + kh)*7 + kw)*2 + ci.
-extern "C" int dmc_i3d_stem_im2col(const float* x, long x_ns, int clips, int T, int H, int W, int KP,
-                                   void* A_hi, void* A_lo, void* stream) {
-  DMC_REQUIRE(x && A_hi && A_lo && clips > 0, "i3d_stem_im2col: null argument");
-  DMC_REQUIRE(T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && KP >= 686 && KP % 2 == 0, "i3d_stem_im2col: T=%d H=%d W=%d KP=%d", T, H, W, KP);
-  const long units = (long)clips * (T / 2) * (H / 2) * (W / 2) * 49;
-  i3d_stem_im2col_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(x, x_ns, clips, T, H, W, KP,
-                                                                                 (bf16*)A_hi, (bf16*)A_lo);
-  return dmc_check_launch("i3d_stem_im2col_kernel");
+// A_hi / A_lo [2][clips][T/2+2][H/2+1][W/2+1][128] (zero-initialised by the caller once; ring rows, the two
+// zero frames of every clip and columns >= 98 are never written): the spatial 7x7x2 patches of every frame of
+// x [clips*T][2][H][W] at the stride-2 output positions, frames split by parity (see the kernel).
+extern "C" int dmc_i3d_stem_patches(const float* x, long x_ns, int clips, int T, int H, int W, void* A_hi,
+                                    void* A_lo, void* stream) {
+  DMC_REQUIRE(x && A_hi && A_lo && clips > 0, "i3d_stem_patches: null argument");
+  DMC_REQUIRE(T % 2 == 0 && H % 2 == 0 && W % 2 == 0, "i3d_stem_patches: T=%d H=%d W=%d", T, H, W);
+  const long rows = (long)clips * T * (H / 2) * (W / 2);
+  DMC_REQUIRE(rows < (1L << 31), "i3d_stem_patches: too many rows");
+  i3d_stem_patches_kernel<<<grid_1d(rows, 4, 148L * 16), 256, 0, ST(stream)>>>(x, x_ns, clips, T, H, W, (bf16*)A_hi,
+                                                                              (bf16*)A_lo);
+  return dmc_check_launch("i3d_stem_patches_kernel");
 }
 
-// Transpose of dmc_i3d_stem_im2col for the data gradient: dX [clips*T][2][H][W] (frame stride dx_ns)
-// (+)= col2im(dA [rows][KP] fp32).
-extern "C" int dmc_i3d_stem_col2im(const float* dA, int KP, int clips, int T, int H, int W, float* dX,
-                                   long dx_ns, int accumulate, void* stream) {
-  DMC_REQUIRE(dA && dX && clips > 0 && T % 2 == 0 && H % 2 == 0 && W % 2 == 0 && KP >= 686, "i3d_stem_col2im: bad arguments");
+// Transpose of dmc_i3d_stem_patches for the data gradient: dX [clips*T][2][H][W] (frame stride dx_ns)
+// (+)= gather(dA [2][rows][128] fp32).
+extern "C" int dmc_i3d_stem_patches_bwd(const float* dA, int clips, int T, int H, int W, float* dX, long dx_ns,
+                                        int accumulate, void* stream) {
+  DMC_REQUIRE(dA && dX && clips > 0 && T % 2 == 0 && H % 2 == 0 && W % 2 == 0, "i3d_stem_patches_bwd: bad arguments");
   const long total = (long)clips * T * H * W;
-  i3d_stem_col2im_kernel<<<grid_1d(total, 256, 148L * 32), 256, 0, ST(stream)>>>(dA, KP, clips, T, H, W, dX,
-                                                                                 dx_ns, accumulate);
-  return dmc_check_launch("i3d_stem_col2im_kernel");
+  DMC_REQUIRE(total < (1L << 32), "i3d_stem_patches_bwd: too many elements");
+  i3d_stem_patches_bwd_kernel<<<grid_1d(total, 256, 148L * 32), 256, 0, ST(stream)>>>(dA, clips, T, H, W, dX, dx_ns,
+                                                                                     accumulate);
+  return dmc_check_launch("i3d_stem_patches_bwd_kernel");
 }
 
-static int fill_pool(Pool3& g, const int* in_thw, const int* kernel, const int* stride) {
+static int fill_pool(Pool3& g, const int* in_thw, const int* kernel, const int* stride, int t_hi = 0) {
+  g.t_hi = t_hi;
   g.Ti = in_thw[0]; g.Hi = in_thw[1]; g.Wi = in_thw[2];
   g.kt = kernel[0]; g.kh = kernel[1]; g.kw = kernel[2];
   g.st = stride[0]; g.sh = stride[1]; g.sw = stride[2];
@@ -402,27 +449,28 @@ extern "C" int dmc_maxpool3d_out_shape(const int* in_thw, const int* kernel, con
 }
 
 // MaxPool3dTFPadding forward on pixel-major hi/lo maps (see the kernel); idx is uint8 [rows_out][C].
+// in_t_hi: zero frames BEHIND each clip of the input map (0, or 1 for the stem map).
 extern "C" int dmc_maxpool3d_fwd(const void* in_hi, const void* in_lo, int clips, int C, const int* in_thw,
-                                 const int* kernel, const int* stride, void* out_hi, void* out_lo, void* idx,
-                                 void* stream) {
+                                 int in_t_hi, const int* kernel, const int* stride, void* out_hi, void* out_lo,
+                                 void* idx, void* stream) {
   Pool3 g;
   DMC_REQUIRE(in_hi && in_lo && out_hi && out_lo && idx && clips > 0 && C % 4 == 0, "maxpool3d_fwd: bad arguments");
-  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride) == 0, "maxpool3d_fwd: bad geometry");
-  const long units = (long)clips * g.To * g.Ho * g.Wo * (C / 4);
-  maxpool3d_fwd_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(
+  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_fwd: bad geometry");
+  const long units = (long)clips * g.To * g.Ho * cdiv(g.Wo, 4) * (C / 4);
+  maxpool3d_fwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(
       (const bf16*)in_hi, (const bf16*)in_lo, clips, C, g, (bf16*)out_hi, (bf16*)out_lo, (uint8_t*)idx);
   return dmc_check_launch("maxpool3d_fwd_kernel");
 }
 
 // Backward: dX [rows_in][C] = add (may be NULL) + routed gradient; every row written (ring rows zero).
 extern "C" int dmc_maxpool3d_bwd(const float* gout, const void* idx, int clips, int C, const int* in_thw,
-                                 const int* kernel, const int* stride, const float* add, float* dX,
+                                 int in_t_hi, const int* kernel, const int* stride, const float* add, float* dX,
                                  void* stream) {
   Pool3 g;
   DMC_REQUIRE(gout && idx && dX && clips > 0 && C % 4 == 0, "maxpool3d_bwd: bad arguments");
-  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride) == 0, "maxpool3d_bwd: bad geometry");
-  const long units = (long)clips * (g.Ti + 1) * (g.Hi + 1) * (g.Wi + 1) * (C / 4);
-  maxpool3d_bwd_kernel<<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips,
+  DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_bwd: bad geometry");
+  const long units = (long)clips * (g.Ti + 1 + g.t_hi) * (g.Hi + 1) * cdiv(g.Wi + 1, 4) * (C / 4);
+  maxpool3d_bwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips,
                                                                               C, g, add, dX);
   return dmc_check_launch("maxpool3d_bwd_kernel");
 }

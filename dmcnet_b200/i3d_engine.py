@@ -14,7 +14,8 @@ block reads the whole map as its K dimension (weights of padding columns are zer
 
   * 3x3x3 "SAME" conv  = 27-tap GEMM, row shifts dt*Hp*Wp + dh*Wp + dw (csrc/gemm_tc.cu, dmc_tc_tap_gemm_ex)
   * 1x1x1 conv          = one-tap GEMM; the two 1x1x1 convs in front of the 3x3x3 branches are ONE GEMM
-  * 7x7x7 / 2 stem      = one-tap GEMM on an explicit im2col operand (K = 686 -> 704, csrc/i3d.cu)
+  * 7x7x7 / 2 stem      = 7-tap GEMM over the temporal kernel index on per-frame 7x7x2 patches (K = 98 -> 128),
+                          even / odd input frames as two phases (csrc/i3d.cu)
   * MaxPool3dTFPadding  = csrc/i3d.cu (argmax kept as a window code for the backward)
   * BatchNorm3d (train) = statistics in the GEMM epilogue, dmc_bn_finalize over a whole column group,
                           dmc_bn_apply; backward reductions in the epilogue of the data-gradient GEMM
@@ -31,7 +32,7 @@ from . import ops
 from .engine import DmcEngine, GEN_GROWTH
 
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5
-STEM_K, STEM_KP = 686, 704
+STEM_KP = 128          # 7 x 7 x 2 spatial patch (98) padded; the temporal kernel index is the tap
 
 # (name, in_channels, [b0, b1a, b1b, b2a, b2b, b3]) -- i3d.py:471-489
 MIXED = [('mixed_3b', 192, [64, 96, 128, 16, 32, 32]), ('mixed_3c', 256, [128, 128, 192, 32, 96, 64]),
@@ -73,12 +74,15 @@ def i3d_param_specs(num_class: int) -> "OrderedDict[str, Tuple[int, ...]]":
 
 
 class _Geo3:
-    def __init__(self, clips: int, T: int, H: int, W: int):
-        self.clips, self.T, self.H, self.W = clips, T, H, W
-        self.Tp, self.Hp, self.Wp = T + 1, H + 1, W + 1
+    """[clips][T+1(+t_hi)][H+1][W+1] map: zero ring in front of every dimension; t_hi = 1 (the stem's map)
+    keeps one more zero frame behind each clip (its temporal taps reach two frames ahead)."""
+
+    def __init__(self, clips: int, T: int, H: int, W: int, t_hi: int = 0):
+        self.clips, self.T, self.H, self.W, self.t_hi = clips, T, H, W, t_hi
+        self.Tp, self.Hp, self.Wp = T + 1 + t_hi, H + 1, W + 1
         self.P = clips * self.Tp * self.Hp * self.Wp
         self.count = float(clips * T * H * W)
-        self.hp = ops.pack_hp(self.Hp, self.Tp)
+        self.hp = ops.pack_hp(self.Hp, self.Tp, t_hi)
         self.thw = (T, H, W)
 
     def taps(self, k: int):
@@ -109,7 +113,7 @@ class _Unit:
         self.name, self.cin, self.cout, self.k = name, cin, cout, k
         self.cop = pad64(cout)
         self.in_cols, self.Kp = list(in_cols), Kp
-        self.T = k ** 3 if k <= 3 else 1
+        self.T = k ** 3 if k <= 3 else 7          # taps of its GEMM (the 7x7x7 stem: temporal index only)
         self.group: Optional[_Group] = None
         self.col0 = 0
 
@@ -139,7 +143,7 @@ class I3DEngine(DmcEngine):
 
     # ------------------------------------------------------------------ plan
     def _plan_trunk(self, clips: int, T: int, H: int, W: int):
-        g1 = _Geo3(clips, T // 2, H // 2, W // 2)
+        g1 = _Geo3(clips, T // 2, H // 2, W // 2, t_hi=1)
         t2 = ops.maxpool3d_out_shape(g1.thw, (1, 3, 3), (1, 2, 2))
         g2 = _Geo3(clips, *t2)
         t3 = ops.maxpool3d_out_shape(g2.thw, (1, 3, 3), (1, 2, 2))
@@ -278,12 +282,13 @@ class I3DEngine(DmcEngine):
         gmap[i] = absolute offset of the parameter element (or -1), inv[e] = i for every element e."""
         T, Kp = u.T, u.Kp
         base = self.offsets[u.name + '.conv3d.weight']
-        if u.k == 7:                                           # stem: column k = ((kt*7+kh)*7+kw)*2 + ci
-            co = torch.arange(64).view(64, 1, 1)
-            ci = torch.arange(2).view(1, 2, 1)
-            t = torch.arange(343).view(1, 1, 343)
-            e = (co * 2 + ci) * 343 + t
-            i = (n0 + co) * Kp + t * 2 + ci
+        if u.k == 7:                                           # stem: slice kt, column (kh*7+kw)*2 + ci
+            co = torch.arange(64).view(64, 1, 1, 1)
+            ci = torch.arange(2).view(1, 2, 1, 1)
+            kt = torch.arange(7).view(1, 1, 7, 1)
+            sp = torch.arange(49).view(1, 1, 1, 49)
+            e = ((co * 2 + ci) * 7 + kt) * 49 + sp
+            i = (kt * n_total + n0 + co) * Kp + sp * 2 + ci
         else:
             co = torch.arange(u.cout).view(-1, 1, 1)
             ci = torch.arange(u.cin).view(1, -1, 1)
@@ -313,7 +318,15 @@ class I3DEngine(DmcEngine):
         G = {'units': list(units), 'N': n_total, 'Kp': Kp, 'T': T, 'gmap': gmap.to(dev), 'inv': invs,
              'W_hi': torch.zeros(T * n_total * Kp, **bf), 'W_lo': torch.zeros(T * n_total * Kp, **bf),
              'Wt_hi': torch.zeros(T * n_total * Kp, **bf), 'Wt_lo': torch.zeros(T * n_total * Kp, **bf)}
-        G['shift'], G['bsel'] = geo.taps(u0.k if u0.k <= 3 else 1)
+        if u0.k == 7:
+            # output frame `to` reads input frame 2*to + kt - 2: even kt -> phase 0 (even frames) shifted by
+            # kt/2 - 1 frames, odd kt -> phase 1 shifted by (kt - 3)/2
+            fr = geo.Hp * geo.Wp
+            G['shift'] = [((kt // 2 - 1) if kt % 2 == 0 else (kt - 3) // 2) * fr for kt in range(7)]
+            G['phase'] = [kt % 2 for kt in range(7)]
+            G['bsel'] = list(range(7))
+        else:
+            G['shift'], G['bsel'] = geo.taps(u0.k)
         self._n_dwg = getattr(self, '_n_dwg', 0)
         G['dwg_off'] = self._n_dwg
         self._n_dwg += T * n_total * Kp
@@ -347,9 +360,9 @@ class I3DEngine(DmcEngine):
             return {'Y': torch.zeros(geo.P * width, **f32), 'hi': torch.zeros(geo.P * width, **bf),
                     'lo': torch.zeros(geo.P * width, **bf), 'geo': geo, 'width': width}
 
-        # stem: im2col operand, conv output, activation; pool 2a
-        self.s_A_hi = torch.zeros(g1.P * STEM_KP, **bf)
-        self.s_A_lo = torch.zeros(g1.P * STEM_KP, **bf)
+        # stem: patch operand (two frame-parity phases), conv output, activation; pool 2a
+        self.s_A_hi = torch.zeros(2 * g1.P * STEM_KP, **bf)
+        self.s_A_lo = torch.zeros(2 * g1.P * STEM_KP, **bf)
         self.m_stem = act(g1, 64)
         self.g_stem = self._make_gemm([self.stem], g1)
         self.p2a = {'hi': torch.zeros(g2.P * 64, **bf), 'lo': torch.zeros(g2.P * 64, **bf),
@@ -393,7 +406,7 @@ class I3DEngine(DmcEngine):
             geo = self._gemm_geo[id(G)]
             ws = max(ws, ops.wgrad_workspace_floats(geo.P, G['N'], G['Kp'], G['T']))
         self.wgrad_ws = torch.zeros(ws, **f32)
-        self.stem_dA = None                                   # [P1][704] fp32, allocated on first use (data gradient)
+        self.stem_dA = None                                   # [2][P1][128] fp32, allocated on first use (data gradient)
         # head
         nc = self.num_class
         self.pooled = torch.zeros(clips, 1024, **f32)
@@ -430,10 +443,12 @@ class I3DEngine(DmcEngine):
         ops.bn_apply(m['Y'], gr.scale, gr.shift, geo.P, w, geo.hp, geo.Wp, True, m['hi'], m['lo'])
 
     def _pool_fwd(self, p: dict, x_hi, x_lo):
-        ops.maxpool3d_fwd(x_hi, x_lo, self.clips, p['C'], p['gin'].thw, p['k'], p['s'], p['hi'], p['lo'], p['idx'])
+        ops.maxpool3d_fwd(x_hi, x_lo, self.clips, p['C'], p['gin'].thw, p['k'], p['s'], p['hi'], p['lo'], p['idx'],
+                          in_t_hi=p['gin'].t_hi)
 
     def _pool_bwd(self, p: dict, gout, add, dX):
-        ops.maxpool3d_bwd(gout, p['idx'], self.clips, p['C'], p['gin'].thw, p['k'], p['s'], add, dX)
+        ops.maxpool3d_bwd(gout, p['idx'], self.clips, p['C'], p['gin'].thw, p['k'], p['s'], add, dX,
+                          in_t_hi=p['gin'].t_hi)
 
     def _mixed_fwd(self, M: dict, x_hi, x_lo, train: bool):
         geo, mid, cat = M['geo'], M['mid'], M['cat']
@@ -462,9 +477,11 @@ class I3DEngine(DmcEngine):
         if train:
             ops.memset_zero(self._sums)
             ops.add_i64(self._nbt, 1)
-        ops.i3d_stem_im2col(x_planar, 2 * H * W, clips, T, H, W, STEM_KP, self.s_A_hi, self.s_A_lo)
-        gs = self.stem.group
-        self._gemm_fwd(self.g_stem, self.s_A_hi, self.s_A_lo, STEM_KP, g1, self.m_stem['Y'], 64, gs, 0, train)
+        ops.i3d_stem_patches(x_planar, 2 * H * W, clips, T, H, W, self.s_A_hi, self.s_A_lo)
+        gs, G = self.stem.group, self.g_stem
+        ops.tap_gemm(self.s_A_hi, self.s_A_lo, G['W_hi'], G['W_lo'], self.m_stem['Y'], a_phases=2, a_rows=g1.P,
+                     K=STEM_KP, b_slices=7, N=64, M=g1.P, ldD=64, Hp=g1.hp, Wp=g1.Wp, shift=G['shift'],
+                     phase=G['phase'], bsel=G['bsel'], stats=(gs.sums if train else None))
         self._bn_fwd(gs, self.m_stem, train)
         self._pool_fwd(self.p2a, self.m_stem['hi'], self.m_stem['lo'])
         self._gemm_fwd(self.g_2b, self.p2a['hi'], self.p2a['lo'], 64, g2, self.m_2b['Y'], 64, self.u2b.group, 0, train)
@@ -633,15 +650,24 @@ class I3DEngine(DmcEngine):
         P1 = g1.P
         G_hi, G_lo = self.G_hi[:P1 * 64], self.G_lo[:P1 * 64]
         self._bn_bwd(self.stem.group, self.m_stem, self.gbuf[o3][:P1 * 64], None, False, G_hi, G_lo)
+        G = self.g_stem
         if need_wgrad:
-            self._wgrad(self.g_stem, G_hi, G_lo, 64, self.s_A_hi, self.s_A_lo, STEM_KP, g1)
+            dW = self._dwg[G['dwg_off']:G['dwg_off'] + 7 * 64 * STEM_KP]
+            ops.wgrad_gemm(G_hi, G_lo, self.s_A_hi, self.s_A_lo, dW, P=P1, Cout=64, x_phases=2, Cin=STEM_KP,
+                           shift=G['shift'], phase=G['phase'], bsel=G['bsel'], oihw_taps=0, workspace=self.wgrad_ws)
+            for u, inv in G['inv']:
+                ops.weight_grad_gather(dW, inv, inv.numel(), 1, self.g(u.name + '.conv3d.weight'))
         if need_input_grad:
             if self.stem_dA is None:
-                self.stem_dA = torch.zeros(P1 * STEM_KP, dtype=torch.float32, device=self.device)
-            self._dgrad(self.g_stem, G_hi, G_lo, 64, g1, self.stem_dA, STEM_KP)
+                self.stem_dA = torch.zeros(2 * P1 * STEM_KP, dtype=torch.float32, device=self.device)
+            for ph in range(2):                  # gradient of each phase's patches: the taps that read it
+                kts = [kt for kt in range(7) if G['phase'][kt] == ph]
+                ops.tap_gemm_ex(G_hi, G_lo, G['Wt_hi'], G['Wt_lo'], self.stem_dA[ph * P1 * STEM_KP:], lda=64, a_rows=P1,
+                                K=64, b_slices=7, N=STEM_KP, M=P1, ldD=STEM_KP, Hp=g1.hp, Wp=g1.Wp,
+                                shift=[-G['shift'][kt] for kt in kts], bsel=kts)
             H, W = self.H, self.W
-            ops.i3d_stem_col2im(self.stem_dA, STEM_KP, clips, self.clip_len, H, W, self.dD.view(-1),
-                                self.dD.shape[1] * H * W, True)
+            ops.i3d_stem_patches_bwd(self.stem_dA, clips, self.clip_len, H, W, self.dD.view(-1),
+                                     self.dD.shape[1] * H * W, True)
 
     # ------------------------------------------------------------------ public passes
     def forward_data(self, data: torch.Tensor, *, train: bool = True):

@@ -554,9 +554,10 @@ def tap_gemm_fold(A_hi, A_lo, B_hi, B_lo, *, a_phases, a_rows, K, b_slices, N, M
 
 
 # ---------------------------------------------------------------- I3D (csrc/i3d.cu, column sub-range GEMMs)
-def pack_hp(Hp: int, Tp: int) -> int:
-    """Hp argument of the pixelwise / GEMM kernels for a 3-D map with padded temporal extent Tp."""
-    return int(Hp) | (int(Tp) << 16)
+def pack_hp(Hp: int, Tp: int, t_hi: int = 0) -> int:
+    """Hp argument of the pixelwise / GEMM kernels for a 3-D map with padded temporal extent Tp (t_hi = 1: the
+    last of the Tp frames of each clip is a zero frame as well)."""
+    return int(Hp) | (int(Tp) << 16) | (int(t_hi) << 30)
 
 
 def tap_gemm_ex(A_hi, A_lo, B_hi, B_lo, D, *, lda, a_rows, K, b_slices, N, M, ldD, Hp, Wp, shift, bsel,
@@ -582,14 +583,14 @@ def i3d_unpack(data, B, Cd, T, HW, mv, res, flow):
           _ptr(res, F32), _ptr(flow, F32), _stream())
 
 
-def i3d_stem_im2col(x, x_ns, clips, T, H, W, KP, A_hi, A_lo):
-    _call('dmc_i3d_stem_im2col', _ptr(x, F32), c_long(x_ns), c_int(clips), c_int(T), c_int(H), c_int(W),
-          c_int(KP), _ptr(A_hi, BF16), _ptr(A_lo, BF16), _stream())
+def i3d_stem_patches(x, x_ns, clips, T, H, W, A_hi, A_lo):
+    _call('dmc_i3d_stem_patches', _ptr(x, F32), c_long(x_ns), c_int(clips), c_int(T), c_int(H), c_int(W),
+          _ptr(A_hi, BF16), _ptr(A_lo, BF16), _stream())
 
 
-def i3d_stem_col2im(dA, KP, clips, T, H, W, dX, dx_ns, accumulate):
-    _call('dmc_i3d_stem_col2im', _ptr(dA, F32), c_int(KP), c_int(clips), c_int(T), c_int(H), c_int(W),
-          _ptr(dX, F32), c_long(dx_ns), c_int(1 if accumulate else 0), _stream())
+def i3d_stem_patches_bwd(dA, clips, T, H, W, dX, dx_ns, accumulate):
+    _call('dmc_i3d_stem_patches_bwd', _ptr(dA, F32), c_int(clips), c_int(T), c_int(H), c_int(W), _ptr(dX, F32),
+          c_long(dx_ns), c_int(1 if accumulate else 0), _stream())
 
 
 def maxpool3d_out_shape(in_thw, kernel, stride):
@@ -600,14 +601,15 @@ def maxpool3d_out_shape(in_thw, kernel, stride):
     return tuple(int(v) for v in out)
 
 
-def maxpool3d_fwd(in_hi, in_lo, clips, C, in_thw, kernel, stride, out_hi, out_lo, idx):
+def maxpool3d_fwd(in_hi, in_lo, clips, C, in_thw, kernel, stride, out_hi, out_lo, idx, in_t_hi=0):
     _call('dmc_maxpool3d_fwd', _ptr(in_hi, BF16), _ptr(in_lo, BF16), c_int(clips), c_int(C), _iarr(in_thw),
-          _iarr(kernel), _iarr(stride), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8), _stream())
+          c_int(in_t_hi), _iarr(kernel), _iarr(stride), _ptr(out_hi, BF16), _ptr(out_lo, BF16), _ptr(idx, U8),
+          _stream())
 
 
-def maxpool3d_bwd(gout, idx, clips, C, in_thw, kernel, stride, add, dX):
+def maxpool3d_bwd(gout, idx, clips, C, in_thw, kernel, stride, add, dX, in_t_hi=0):
     _call('dmc_maxpool3d_bwd', _ptr(gout, F32), _ptr(idx, U8), c_int(clips), c_int(C), _iarr(in_thw),
-          _iarr(kernel), _iarr(stride), _ptr(add, F32), _ptr(dX, F32), _stream())
+          c_int(in_t_hi), _iarr(kernel), _iarr(stride), _ptr(add, F32), _ptr(dX, F32), _stream())
 
 
 def i3d_head_pool_fwd(hi, lo, clips, T5, H, W, C, pooled):

@@ -58,7 +58,7 @@ def main():
     for name, m, cols in stages:
         geo = m['geo']
         a = (m['hi'].float() + m['lo'].float()).view(geo.P, m['width'])[:, cols]
-        a = a.reshape(B, geo.Tp, geo.Hp, geo.Wp, -1)[:, 1:, 1:, 1:].permute(0, 4, 1, 2, 3)
+        a = a.reshape(B, geo.Tp, geo.Hp, geo.Wp, -1)[:, 1:1 + geo.T, 1:, 1:].permute(0, 4, 1, 2, 3)
         flips = float(((a.cpu() > 0) != (rec[name] > 0)).float().mean())
         print('act  %-16s rel %.2e  relu-switch flips %.2e' % (name, rel_l2(a, rec[name]), flips))
     e1 = sorted(rel_l2(eng.grad_view(k), st[k].grad) for k in eng.specs)

@@ -76,33 +76,36 @@ def test_maxpool3d_tf_padding_forward_backward(kernel, stride, thw):
     assert float(ring[:, 0].abs().max()) == 0 and float(ring[:, :, 0].abs().max()) == 0 and float(ring[:, :, :, 0].abs().max()) == 0
 
 
-def test_stem_im2col_gemm_and_col2im():
+def test_stem_patches_and_their_transpose():
+    """dmc_i3d_stem_patches: per-frame 7x7x2 patches at the stride-2 positions, two frame-parity phases, zero
+    frames at both ends of a clip; dmc_i3d_stem_patches_bwd is its transpose (checked through autograd of a
+    torch restatement of the gather)."""
     dev = torch.device('cuda')
     g = torch.Generator(device='cuda').manual_seed(6)
-    B, T, H, W, KP = 2, 4, 16, 24, 704
-    x = torch.randn(B, 2, T, H, W, generator=g, device=dev).requires_grad_(True)
-    w = (torch.randn(64, 2, 7, 7, 7, generator=g, device=dev) * 0.05)
-    xd = x.detach().double().requires_grad_(True)            # fp64 reference (cuDNN fp32 convs default to TF32)
-    ref = F.conv3d(F.pad(xd, O.tf_same_pad((7, 7, 7), (2, 2, 2))), w.double(), None, 2)
-    To, Ho, Wo = T // 2, H // 2, W // 2
-    P = B * (To + 1) * (Ho + 1) * (Wo + 1)
-    A_hi = torch.zeros(P * KP, dtype=torch.bfloat16, device=dev)
+    B, T, H, W, KP = 2, 4, 16, 24, 128
+    x = torch.randn(B * T, 2, H, W, generator=g, device=dev)
+    Tq, Ho, Wo = T // 2, H // 2, W // 2
+    Tp, Hp, Wp = Tq + 2, Ho + 1, Wo + 1
+    P = B * Tp * Hp * Wp
+    A_hi = torch.zeros(2 * P * KP, dtype=torch.bfloat16, device=dev)
     A_lo = torch.zeros_like(A_hi)
-    planar = x.detach().permute(0, 2, 1, 3, 4).contiguous()           # [B*T][2][H][W]
-    ops.i3d_stem_im2col(planar, 2 * H * W, B, T, H, W, KP, A_hi, A_lo)
-    A = (A_hi.float() + A_lo.float()).view(P, KP)
-    Wg = torch.zeros(64, KP, device=dev)
-    Wg[:, :686] = w.permute(0, 2, 3, 4, 1).reshape(64, 686)           # k = ((kt*7+kh)*7+kw)*2 + ci
-    got = from_ring(A.double() @ Wg.double().t(), B, 64, To, Ho, Wo)
-    assert rel(got, ref.detach()) < 1e-5
-    ring = A.view(B, To + 1, Ho + 1, Wo + 1, KP)
-    assert float(ring[:, 0].abs().max()) == 0 and float(ring[:, :, 0].abs().max()) == 0
-    go = torch.randn(ref.shape, generator=g, device=dev)
-    ref.backward(go.double())
-    dA = (to_ring(go).double() @ Wg.double()).float().contiguous()    # [P][KP]
+    ops.i3d_stem_patches(x, 2 * H * W, B, T, H, W, A_hi, A_lo)
+
+    def patches(xx):              # [B*T,2,H,W] -> [2][B][Tp][Hp][Wp][128]
+        cols = F.unfold(F.pad(xx, (2, 3, 2, 3)), 7, stride=2)            # [B*T, 2*49, Ho*Wo], rows ci*49 + kh*7 + kw
+        cols = cols.view(B, T, 2, 49, Ho, Wo).permute(0, 1, 4, 5, 3, 2).reshape(B, T, Ho, Wo, 98)
+        out = torch.zeros(2, B, Tp, Hp, Wp, KP, dtype=xx.dtype, device=xx.device)
+        out[0, :, 1:1 + Tq, 1:, 1:, :98] = cols[:, 0::2]
+        out[1, :, 1:1 + Tq, 1:, 1:, :98] = cols[:, 1::2]
+        return out
+    got = (A_hi.float() + A_lo.float()).view(2, B, Tp, Hp, Wp, KP)
+    assert rel(got, patches(x)) < 1e-5
+    xd = x.double().requires_grad_(True)
+    dA = torch.randn(2, B, Tp, Hp, Wp, KP, generator=g, device=dev)
+    (patches(xd) * dA.double()).sum().backward()
     dX = torch.zeros(B * T, 2, H, W, device=dev)
-    ops.i3d_stem_col2im(dA, KP, B, T, H, W, dX.view(-1), 2 * H * W, False)
-    assert rel(dX.view(B, T, 2, H, W).permute(0, 2, 1, 3, 4), xd.grad) < 1e-5
+    ops.i3d_stem_patches_bwd(dA.contiguous(), B, T, H, W, dX.view(-1), 2 * H * W, False)
+    assert rel(dX, xd.grad) < 1e-5
 
 
 def test_head_pool_and_sgd_nesterov_and_unpack():
@@ -212,7 +215,8 @@ def test_i3d_forward_vs_oracle_and_reference_fixture():
     for name, m, cols in stages:
         geo = m['geo']
         a = (m['hi'].float() + m['lo'].float()).view(geo.P, m['width'])[:, cols]
-        errs[name] = rel(from_ring(a, 1, len(cols), geo.T, geo.H, geo.W), rec[name])
+        a5 = a.reshape(1, geo.Tp, geo.Hp, geo.Wp, -1)[:, 1:1 + geo.T, 1:, 1:].permute(0, 4, 1, 2, 3)
+        errs[name] = rel(a5, rec[name])
     print('I3D per-stage activation errors:', {k: '%.1e' % v for k, v in errs.items()})
     assert max(errs.values()) < 1e-3, errs
     assert rel(logits, logits_o) < 1e-3
@@ -453,3 +457,32 @@ def test_dropin_i3d_module_with_torch_autograd_and_optimizer():
     assert int(net.state_dict()['conv3d_2b_1x1.batch3d.num_batches_tracked']) == 1
     with pytest.raises(NotImplementedError):
         net(d[:, :5].contiguous(), node='D')
+
+
+def test_maxpool3d_on_a_map_with_a_zero_frame_behind_each_clip():
+    """The stem map keeps one zero frame behind every clip (in_t_hi = 1): pool 2a reads and differentiates it."""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(9)
+    B, C, T, H, W = 2, 64, 4, 12, 12
+    kernel, stride = (1, 3, 3), (1, 2, 2)
+    x = torch.relu(torch.randn(B, C, T, H, W, generator=g, device=dev)).requires_grad_(True)
+    ref = F.max_pool3d(F.pad(x, O.tf_same_pad(kernel, stride)), kernel, stride, ceil_mode=True)
+    To, Ho, Wo = ops.maxpool3d_out_shape((T, H, W), kernel, stride)
+    p = torch.zeros(B, T + 2, H + 1, W + 1, C, device=dev)
+    p[:, 1:T + 1, 1:, 1:, :] = x.detach().permute(0, 2, 3, 4, 1)
+    x_hi, x_lo = split(p.reshape(-1, C).contiguous())
+    Po = B * (To + 1) * (Ho + 1) * (Wo + 1)
+    o_hi = torch.zeros(Po * C, dtype=torch.bfloat16, device=dev)
+    o_lo = torch.zeros_like(o_hi)
+    idx = torch.zeros(Po * C, dtype=torch.uint8, device=dev)
+    ops.maxpool3d_fwd(x_hi, x_lo, B, C, (T, H, W), kernel, stride, o_hi, o_lo, idx, in_t_hi=1)
+    got = from_ring((o_hi.float() + o_lo.float()).view(Po, C), B, C, To, Ho, Wo)
+    assert rel(got, ref.detach()) < 1e-5
+    go = torch.randn(B, C, To, Ho, Wo, generator=g, device=dev)
+    ref.backward(go)
+    dX = torch.full((B * (T + 2) * (H + 1) * (W + 1), C), float('nan'), device=dev)
+    ops.maxpool3d_bwd(to_ring(go), idx, B, C, (T, H, W), kernel, stride, None, dX, in_t_hi=1)
+    d5 = dX.view(B, T + 2, H + 1, W + 1, C)
+    assert float(d5[:, 0].abs().max()) == 0 and float(d5[:, T + 1].abs().max()) == 0
+    got_g = d5[:, 1:T + 1, 1:, 1:].permute(0, 4, 1, 2, 3) * (x.detach() > 0)
+    assert rel(got_g, x.grad * (x.detach() > 0)) < 1e-6

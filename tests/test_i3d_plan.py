@@ -146,30 +146,39 @@ def test_inception_block_as_column_slice_gemms(block):
         assert eng.mixed[block + 1]['b0'].in_cols == nxt_cols
 
 
-def test_stem_im2col_column_order_and_tf_same_padding():
+def test_stem_as_seven_temporal_taps_over_frame_patches():
+    """Conv3d(2, 64, 7, stride 2), TF "SAME" (2 zeros in front, 3 behind): per-frame 7x7x2 patches at the
+    output's spatial positions, even / odd frames as two phases, one tap per temporal kernel index."""
     torch.manual_seed(4)
     eng = cpu_engine()
     sd = O.build_state(51, 'DenseNetTiny', seed=2)
     eng.load_state(sd)
     params = eng.params.double()
-    T, H, W = 4, 6, 8
-    x = torch.randn(1, 2, T, H, W, dtype=torch.float64)
+    clips, T, H, W = 2, 8, 6, 8
+    x = torch.randn(clips, 2, T, H, W, dtype=torch.float64)
     w = sd['conv3d_1a_7x7.conv3d.weight'].double()
     ref = F.conv3d(F.pad(x, O.tf_same_pad((7, 7, 7), (2, 2, 2))), w, None, 2)
-    Wg = gemm_weights(eng, [eng.stem], params)[0]                      # [64][704]
-    To, Ho, Wo = T // 2, H // 2, W // 2
-    A = torch.zeros(To, Ho, Wo, E.STEM_KP, dtype=torch.float64)
+    Wg = gemm_weights(eng, [eng.stem], params)                        # [7][64][128]
+    geo = E._Geo3(clips, T // 2, H // 2, W // 2, t_hi=1)
+    A2 = torch.zeros(2, clips, geo.Tp, geo.Hp, geo.Wp, E.STEM_KP, dtype=torch.float64)
+    for n in range(clips):
+        for t in range(T):
+            for ho in range(geo.H):
+                for wo in range(geo.W):
+                    for kh in range(7):
+                        for kw in range(7):
+                            h, ww = 2 * ho + kh - 2, 2 * wo + kw - 2
+                            if 0 <= h < H and 0 <= ww < W:
+                                A2[t % 2, n, t // 2 + 1, ho + 1, wo + 1, (kh * 7 + kw) * 2:(kh * 7 + kw) * 2 + 2] = x[n, :, t, h, ww]
+    fr = geo.Hp * geo.Wp
+    shift = [((kt // 2 - 1) if kt % 2 == 0 else (kt - 3) // 2) * fr for kt in range(7)]
+    P = geo.P
+    out = torch.zeros(P, 64, dtype=torch.float64)
+    pad = 3 * fr
     for kt in range(7):
-        for kh in range(7):
-            for kw in range(7):
-                for ci in range(2):
-                    k = ((kt * 7 + kh) * 7 + kw) * 2 + ci
-                    for to in range(To):
-                        for ho in range(Ho):
-                            for wo in range(Wo):
-                                t, h, ww = 2 * to + kt - 2, 2 * ho + kh - 2, 2 * wo + kw - 2
-                                if 0 <= t < T and 0 <= h < H and 0 <= ww < W:
-                                    A[to, ho, wo, k] = x[0, ci, t, h, ww]
-    got = (A.reshape(-1, E.STEM_KP) @ Wg.t()).reshape(To, Ho, Wo, 64).permute(3, 0, 1, 2)
-    assert tuple(ref.shape[2:]) == (To, Ho, Wo)
-    assert float((got - ref[0]).abs().max()) < 1e-9
+        Ap = torch.zeros(P + 2 * pad, E.STEM_KP, dtype=torch.float64)
+        Ap[pad:pad + P] = A2[kt % 2].reshape(P, E.STEM_KP)
+        out += Ap[pad + shift[kt]:pad + shift[kt] + P] @ Wg[kt].t()
+    got = out.reshape(clips, geo.Tp, geo.Hp, geo.Wp, 64)[:, 1:1 + geo.T, 1:, 1:].permute(0, 4, 1, 2, 3)
+    assert tuple(ref.shape[2:]) == geo.thw
+    assert float((got - ref).abs().max()) < 1e-9
