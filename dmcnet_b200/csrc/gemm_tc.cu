@@ -1106,7 +1106,10 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
   for (int i = 0; i < ntaps; ++i)
     DMC_REQUIRE(phase[i] >= 0 && phase[i] < a_phases && bsel[i] >= 0 && bsel[i] < b_slices,
                 "tap_gemm: tap %d out of range", i);
-  const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+  // 128-wide tiles whenever N exceeds one: a partial last tile (N = 192, 320, 576, 832: the inception maps of
+  // I3D) reads zero-filled weight rows and skips the stores, which costs less than 64-wide tiles whose MMAs
+  // are bounded by shared-memory operand reads (tensor pipe 35-48 % vs 75-80 %)
+  const int BN = (N % 128 == 0 || (N > 128 && N % 64 == 0)) ? 128 : (N % 64 == 0 ? 64 : 32);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map_3d(&mAh, A_hi, K, a_rows, a_phases, 64, 128, lda))) return rc;
