@@ -143,13 +143,14 @@ maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in
   const int wblocks = (g.Wo + WB - 1) / WB;
   const long units = (long)clips * g.To * g.Ho * wblocks * C4;
   const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    long r = i / C4;
-    const int wo0 = (int)(r % wblocks) * WB; r /= wblocks;
-    const int ho = (int)(r % g.Ho); r /= g.Ho;
-    const int to = (int)(r % g.To);
-    const int n = (int)(r / g.To);
+  // 32-bit index arithmetic (the host checks units < 2^32): 64-bit divisions cost more than the loads
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)units; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)C4) * 4;
+    unsigned r = i / (unsigned)C4;
+    const int wo0 = (int)(r % (unsigned)wblocks) * WB; r /= (unsigned)wblocks;
+    const int ho = (int)(r % (unsigned)g.Ho); r /= (unsigned)g.Ho;
+    const int to = (int)(r % (unsigned)g.To);
+    const int n = (int)(r / (unsigned)g.To);
     float best[WB][4];
     uint2 bh[WB], bl[WB];
     uint32_t bi[WB];                         // four window codes, one byte per channel
@@ -216,13 +217,13 @@ maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__
   const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
   const int wblocks = (Wpi + WB - 1) / WB;
   const long units = (long)clips * Tpi * Hpi * wblocks * C4;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    long r = i / C4;
-    const int wp0 = (int)(r % wblocks) * WB; r /= wblocks;
-    const int hp = (int)(r % Hpi); r /= Hpi;
-    const int tp = (int)(r % Tpi);
-    const int n = (int)(r / Tpi);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)units; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)C4) * 4;
+    unsigned r = i / (unsigned)C4;
+    const int wp0 = (int)(r % (unsigned)wblocks) * WB; r /= (unsigned)wblocks;
+    const int hp = (int)(r % (unsigned)Hpi); r /= (unsigned)Hpi;
+    const int tp = (int)(r % (unsigned)Tpi);
+    const int n = (int)(r / (unsigned)Tpi);
     const long q0 = (((long)n * Tpi + tp) * Hpi + hp) * Wpi + wp0;
     float4 acc[WB];
 #pragma unroll
@@ -457,6 +458,7 @@ extern "C" int dmc_maxpool3d_fwd(const void* in_hi, const void* in_lo, int clips
   DMC_REQUIRE(in_hi && in_lo && out_hi && out_lo && idx && clips > 0 && C % 4 == 0, "maxpool3d_fwd: bad arguments");
   DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_fwd: bad geometry");
   const long units = (long)clips * g.To * g.Ho * cdiv(g.Wo, 4) * (C / 4);
+  DMC_REQUIRE(units < (1L << 32), "maxpool3d_fwd: map too large");
   maxpool3d_fwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(
       (const bf16*)in_hi, (const bf16*)in_lo, clips, C, g, (bf16*)out_hi, (bf16*)out_lo, (uint8_t*)idx);
   return dmc_check_launch("maxpool3d_fwd_kernel");
@@ -470,6 +472,7 @@ extern "C" int dmc_maxpool3d_bwd(const float* gout, const void* idx, int clips, 
   DMC_REQUIRE(gout && idx && dX && clips > 0 && C % 4 == 0, "maxpool3d_bwd: bad arguments");
   DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_bwd: bad geometry");
   const long units = (long)clips * (g.Ti + 1 + g.t_hi) * (g.Hi + 1) * cdiv(g.Wi + 1, 4) * (C / 4);
+  DMC_REQUIRE(units < (1L << 32), "maxpool3d_bwd: map too large");
   maxpool3d_bwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips,
                                                                               C, g, add, dX);
   return dmc_check_launch("maxpool3d_bwd_kernel");

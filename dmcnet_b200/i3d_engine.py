@@ -123,8 +123,8 @@ class I3DEngine(DmcEngine):
     `clip_len` frames.  ``arch_estimator=None`` is the plain two-channel I3D (modality 'flow' / 'mv')."""
 
     def __init__(self, num_class: int, clips: int, clip_len: int = 16, *, arch_estimator: Optional[str] = 'DenseNetTiny',
-                 height: int = 224, width: int = 224, device: Optional[torch.device] = None,
-                 share_from: Optional['I3DEngine'] = None):
+                 arch_d: Optional[str] = None, height: int = 224, width: int = 224,
+                 device: Optional[torch.device] = None, share_from: Optional['I3DEngine'] = None):
         if arch_estimator is not None and arch_estimator not in GEN_TABLE:
             # i3d.py:460-465 builds no estimator for any other string and forward() then feeds the 5-channel
             # input to a 2-channel convolution
@@ -133,13 +133,17 @@ class I3DEngine(DmcEngine):
             raise ValueError('I3D: clip_len must be a multiple of 8, at least 16 (AvgPool3d((2,7,7)) needs T/8 >= 2)')
         if height != 224 or width != 224:
             raise ValueError('I3D: AvgPool3d((2,7,7)) + squeeze (i3d.py:484,352-354) fix the frame size at 224 x 224')
+        if arch_d is not None and arch_estimator is None:
+            raise ValueError('I3D: a discriminator (arch_d) judges generated maps; it needs an estimator')
         self.clips, self.clip_len = clips, clip_len
         self.has_gen = arch_estimator is not None
         self.i3d_arch_estimator = arch_estimator
         self._plan_trunk(clips, clip_len, height, width)
-        super().__init__(num_class, clip_len, clips * clip_len, gan=False, gen_flow_or_delta=0, height=height,
-                         width=width, device=device, gemm_engine='tc', share_from=share_from,
-                         gen_growth=GEN_TABLE.get(arch_estimator or 'DenseNetTiny'))
+        # arch_d: the frame discriminator of the adversarial stages (i3d.py:466-476, node='D'): the 2-D plans of
+        # DmcEngine over the clips*T generated frames [+ as many real ones]
+        super().__init__(num_class, clip_len, clips * clip_len, gan=arch_d is not None, arch_d=arch_d,
+                         gen_flow_or_delta=0, height=height, width=width, device=device, gemm_engine='tc',
+                         share_from=share_from, gen_growth=GEN_TABLE.get(arch_estimator or 'DenseNetTiny'))
 
     # ------------------------------------------------------------------ plan
     def _plan_trunk(self, clips: int, T: int, H: int, W: int):
@@ -199,8 +203,8 @@ class I3DEngine(DmcEngine):
     def _param_specs(self):
         specs: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
         if self.has_gen:
-            for k, v in super()._param_specs().items():
-                if k.startswith('gen_flow_model'):
+            for k, v in super()._param_specs().items():          # reference order: generator, discriminator, trunk
+                if k.startswith('gen_flow_model') or k.startswith('discriminator'):
                     specs[k] = v
         specs.update(i3d_param_specs(self.num_class))
         return specs
@@ -215,15 +219,16 @@ class I3DEngine(DmcEngine):
         self.group_range: Dict[str, Tuple[int, int]] = {}
         off = 0
         al = lambda n: (n + 63) // 64 * 64
-        start = off
-        for k, shp in self.specs.items():                       # generator first (its own optimizer)
-            if k.startswith('gen_flow_model'):
-                self.offsets[k] = off
-                off += al(self._numel(shp))
-        self.group_range['gen_flow_model'] = (start, off)
+        for tag in ('gen_flow_model', 'discriminator'):         # each with its own optimizer
+            start = off
+            for k, shp in self.specs.items():
+                if k.startswith(tag):
+                    self.offsets[k] = off
+                    off += al(self._numel(shp))
+            self.group_range[tag] = (start, off)
         start = off
         for k, shp in self.specs.items():
-            if not k.startswith('gen_flow_model') and 'batch3d' not in k:
+            if not k.startswith(('gen_flow_model', 'discriminator')) and 'batch3d' not in k:
                 self.offsets[k] = off
                 off += al(self._numel(shp))
         for gr in self.groups:
@@ -254,6 +259,12 @@ class I3DEngine(DmcEngine):
         for gr in self.groups:
             gr.rm_off = col
             col += gr.width
+        for k, shp in self.specs.items():                       # BatchNorm2d of the discriminator blocks
+            if k.startswith('discriminator') and k.endswith('.weight') and len(shp) == 1:
+                base = k[:-len('.weight')]
+                self.buffers[base + '.running_mean'] = torch.zeros(shp, dtype=torch.float32, device=dev)
+                self.buffers[base + '.running_var'] = torch.ones(shp, dtype=torch.float32, device=dev)
+                self.buffers[base + '.num_batches_tracked'] = torch.zeros((), dtype=torch.int64, device=dev)
         for i, u in enumerate(self.units.values()):
             a = u.group.rm_off + u.col0
             self.buffers[u.name + '.batch3d.running_mean'] = self._rm[a:a + u.cout]
@@ -327,9 +338,9 @@ class I3DEngine(DmcEngine):
             G['bsel'] = list(range(7))
         else:
             G['shift'], G['bsel'] = geo.taps(u0.k)
-        self._n_dwg = getattr(self, '_n_dwg', 0)
-        G['dwg_off'] = self._n_dwg
-        self._n_dwg += T * n_total * Kp
+        self._i3d_n_dwg = getattr(self, '_i3d_n_dwg', 0)
+        G['dwg_off'] = self._i3d_n_dwg
+        self._i3d_n_dwg += T * n_total * Kp
         self._gemms.append(G)
         return G
 
@@ -396,7 +407,7 @@ class I3DEngine(DmcEngine):
         big_mid = max(M['geo'].P * M['mid'].width for M in self.mixed)
         self.dz_mid = torch.zeros(big_mid, **f32)
         self.Gm_hi, self.Gm_lo = torch.zeros(big_mid, **bf), torch.zeros(big_mid, **bf)
-        self._dwg = torch.zeros(self._n_dwg, **f32)
+        self._i3d_dwg = torch.zeros(self._i3d_n_dwg, **f32)
         ws = 0
         self._gemm_geo = {id(self.g_stem): g1, id(self.g_2b): g2, id(self.g_2c): g2}
         for M in self.mixed:
@@ -415,8 +426,8 @@ class I3DEngine(DmcEngine):
         self.drop_mask = torch.ones(clips, 400, **f32)
         self.logits = torch.zeros(clips, nc, **f32)
         self.d_logits = torch.zeros(clips, nc, **f32)
-        self.d_featd = torch.zeros(clips, 400, **f32)
-        self.d_feat = torch.zeros(clips, 400, **f32)
+        self.d_h400d = torch.zeros(clips, 400, **f32)
+        self.d_h400 = torch.zeros(clips, 400, **f32)
         self.d_pooled = torch.zeros(clips, 1024, **f32)
         self.dropout_p = 0.0
 
@@ -537,7 +548,7 @@ class I3DEngine(DmcEngine):
                              geo.hp, geo.Wp, G_hi, G_lo, None, gr.dgamma, gr.dbeta)
 
     def _wgrad(self, G: dict, g_hi, g_lo, ldg, x_hi, x_lo, ldx, geo):
-        dW = self._dwg[G['dwg_off']:G['dwg_off'] + G['T'] * G['N'] * G['Kp']]
+        dW = self._i3d_dwg[G['dwg_off']:G['dwg_off'] + G['T'] * G['N'] * G['Kp']]
         sh, bs = G['shift'], G['bsel']
         ops.wgrad_gemm_ex(g_hi, g_lo, x_hi, x_lo, dW, ldg=ldg, ldx=ldx, P=geo.P, Cout=G['N'], Cin=G['Kp'],
                           shift=sh, bsel=bs, workspace=self.wgrad_ws)
@@ -595,17 +606,17 @@ class I3DEngine(DmcEngine):
         g1, g2, g3, g4, g5 = self.geos
         clips, nc = self.clips, self.num_class
         gw = (lambda k: self.g(k)) if need_wgrad else (lambda k: None)
-        ops.linear_bwd(self.d_logits, self._head_in, self.p('classifier.weight'), clips, 400, nc, self.d_featd,
+        ops.linear_bwd(self.d_logits, self._head_in, self.p('classifier.weight'), clips, 400, nc, self.d_h400d,
                        gw('classifier.weight'), gw('classifier.bias'))
-        d_feat = self.d_featd
+        d_feat = self.d_h400d
         if self._used_drop:
-            ops.mul(self.d_featd, self.drop_mask, self.d_feat)
-            d_feat = self.d_feat
+            ops.mul(self.d_h400d, self.drop_mask, self.d_h400)
+            d_feat = self.d_h400
         ops.linear_bwd(d_feat, self.pooled, self.p('conv3d_0c_1x1.conv3d.weight'), clips, 1024, 400, self.d_pooled,
                        gw('conv3d_0c_1x1.conv3d.weight'), gw('conv3d_0c_1x1.conv3d.bias'))
         ops.memset_zero(self._sums2)
         if need_wgrad:
-            ops.memset_zero(self._dwg)
+            ops.memset_zero(self._i3d_dwg)
         cur = 0
         ops.i3d_head_pool_bwd(self.d_pooled, clips, g5.T, g5.H, g5.W, 1024, self.gbuf[cur][:g5.P * 1024])
         g_is_dz = False
@@ -652,7 +663,7 @@ class I3DEngine(DmcEngine):
         self._bn_bwd(self.stem.group, self.m_stem, self.gbuf[o3][:P1 * 64], None, False, G_hi, G_lo)
         G = self.g_stem
         if need_wgrad:
-            dW = self._dwg[G['dwg_off']:G['dwg_off'] + 7 * 64 * STEM_KP]
+            dW = self._i3d_dwg[G['dwg_off']:G['dwg_off'] + 7 * 64 * STEM_KP]
             ops.wgrad_gemm(G_hi, G_lo, self.s_A_hi, self.s_A_lo, dW, P=P1, Cout=64, x_phases=2, Cin=STEM_KP,
                            shift=G['shift'], phase=G['phase'], bsel=G['bsel'], oihw_taps=0, workspace=self.wgrad_ws)
             for u, inv in G['inv']:

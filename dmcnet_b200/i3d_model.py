@@ -144,17 +144,18 @@ class I3D(nn.Module):
         self._param_keys = None
 
     def _engine_for(self, inp) -> I3DEngine:
-        if self._in_channels != 2 or getattr(self, 'discriminator', None) is not None:
-            raise NotImplementedError('dmcnet_b200 runs I3D on two-channel stacks (modality flow | mv | flow+mp4) '
-                                      'without a discriminator; this configuration has no kernels')
+        if self._in_channels != 2:
+            raise NotImplementedError('dmcnet_b200 runs I3D on two-channel stacks (modality flow | mv | flow+mp4); '
+                                      'this configuration has no kernels')
         if not inp.is_cuda:
             raise RuntimeError('dmcnet_b200: inputs must be CUDA tensors (no CPU path exists)')
         B, T, H, W = int(inp.shape[0]), int(inp.shape[2]), int(inp.shape[3]), int(inp.shape[4])
         eng = self._engine
         if eng is None or (eng.clips, eng.clip_len) != (B, T):
             gen = self.arch_estimator if self.arch_estimator in GEN_TABLE else None
-            new = I3DEngine(self.num_classes, B, T, arch_estimator=gen, height=H, width=W, device=inp.device,
-                            share_from=eng)
+            arch_d = self.arch_d if getattr(self, 'discriminator', None) is not None else None
+            new = I3DEngine(self.num_classes, B, T, arch_estimator=gen, arch_d=arch_d, height=H, width=W,
+                            device=inp.device, share_from=eng)
             if eng is None:
                 new.load_state(self.state_dict())
                 named_p = dict(self.named_parameters())
@@ -170,7 +171,8 @@ class I3D(nn.Module):
 
     def forward(self, inp, node='logit', detach=False):
         if node == 'D':
-            raise NotImplementedError('I3D(node="D"): the discriminator branch of dmcnet_I3D is not built')
+            raise NotImplementedError('I3D(node="D") as a separate autograd call is not built: the adversarial stages '
+                                      'run inside dmcnet_b200.i3d_trainer.I3DTrainStep (adv > 0)')
         self._engine_for(inp)
         named_p = dict(self.named_parameters())
         params = [named_p[k] for k in self._param_keys]

@@ -7,7 +7,14 @@ batches and divided by it before the step (:423-432), the two-stage learning-rat
 
 Optimizers over the flat buckets: Adam (``dmc_adam_step``; eps 1e-8, the generator's stage-two Adam 1e-3,
 train_model.py:122-176) or SGD with Nesterov momentum 0.9 (``dmc_sgd_nesterov_step``), weight decay 1e-4 on
-every tensor (train_model.py:112-113).  The adversarial branch (``--adv``, ``optimizer_3``) is not built.
+every tensor (train_model.py:112-113).
+
+With ``adv > 0`` (``--adv``, ``--arch-d``: ``optimizer_3``, :357-446) batches alternate in runs of ``iter_size``:
+a D stage (loss = CE + adv * adversarial CE of the frame discriminator on [generated | real] frames, steps the
+classifier's optimizer and the discriminator's Adam(eps 1e-3)) and a G stage (loss = [0 during epoch 0] * CE
++ MSE + adv * the same adversarial CE, steps the generator's optimizer only).  As in the reference every
+backward adds into every parameter's gradient and a stage zeroes only what it steps, so the generator's
+gradient of a D stage is part of the next G step and vice versa.
 Data parallel: clips sharded over ranks, BatchNorm3d statistics per rank (nn.DataParallel, train_model.py:119),
 loss gradients pre-scaled by the global batch, one sum all-reduce of the flat gradient bucket per optimizer step.
 """
@@ -36,6 +43,8 @@ class I3DHParams:
     dropout: float = 0.5
     momentum: float = 0.9
     betas: tuple = (0.9, 0.999)
+    adv: float = 0.0              # --adv: weight of the adversarial loss; > 0 needs an engine built with arch_d
+    lr_d: Optional[float] = None  # --lr-d (train_model.py:249-258); None = lr_base
 
 
 def lr_mult_rule(lr_mult: float, epoch: int, epoch_thre: int) -> float:
@@ -53,6 +62,8 @@ def param_group_of(key: str) -> str:
     """train_model.py:62-86 with modality 'flow+mp4'."""
     if key.startswith('gen_flow_model'):
         return 'gf'
+    if key.startswith('discriminator'):
+        return 'd'
     if key.startswith('conv3d_0c_1x1') or key.startswith('classifier'):
         return 'new'
     return 'base'
@@ -69,22 +80,30 @@ class I3DTrainStep:
         self.consensus = torch.zeros(self.B, engine.num_class, dtype=torch.float32, device=dev)
         self.ce_stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self.mse_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.acc = torch.zeros_like(engine.grads) if hp.iter_size > 1 else None
+        self.adv = hp.adv > 0
+        if self.adv and not engine.gan:
+            raise ValueError('adv > 0 needs I3DEngine(..., arch_d=...) (train_hmdb51.py --arch-d)')
+        self.acc = torch.zeros_like(engine.grads) if (hp.iter_size > 1 or self.adv) else None
+        if self.adv:
+            n = engine.N
+            self.adv_t = torch.cat((torch.zeros(n, dtype=torch.int64), torch.ones(n, dtype=torch.int64))).to(dev)
+            self.adv_stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self.lr_mul = 0.2 if hp.fine_tune else 0.5                      # train_model.py:100-105
         self.keys: List[str] = list(engine.specs.keys())
         self.group: List[str] = [param_group_of(k) for k in self.keys]
-        chunks = {'cls': [], 'gf': []}
+        chunks = {'cls': [], 'gf': [], 'd': []}
         for ti, (k, g) in enumerate(zip(self.keys, self.group)):
             off, n = engine.offsets[k], engine.numel(k)
             for c0 in range(0, n, 1024):
-                chunks['gf' if g == 'gf' else 'cls'].append((off + c0, min(1024, n - c0), ti, 0))
+                chunks[g if g in ('gf', 'd') else 'cls'].append((off + c0, min(1024, n - c0), ti, 0))
         self.chunks = {}
         for g, rows in chunks.items():
             t = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).contiguous().to(dev)
             self.chunks[g] = (t, len(rows))
         self.hyper = torch.zeros(len(self.keys), 2, dtype=torch.float32, device=dev)
-        self.steps = torch.zeros(2, dtype=torch.int32, device=dev)        # Adam step counts: classifier, generator
+        self.steps = torch.zeros(3, dtype=torch.int32, device=dev)        # Adam step counts: classifier, generator, D
         self.i = 0
+        self.i_batch = 0
         self.epoch = -1
         self.stage2 = False
         self.set_epoch(0)
@@ -96,11 +115,14 @@ class I3DTrainStep:
         moments and step counts restart."""
         hp = self.hp
         stage2 = epoch >= hp.epoch_thre
-        if stage2 and not self.stage2:
-            ops.memset_zero(self.eng.exp_avg)
-            ops.memset_zero(self.eng.exp_avg_sq)
-            ops.memset_zero(self.steps)
-        self.stage2, self.epoch = stage2, epoch
+        if stage2 and not self.stage2:                  # optimizer_3 is NOT replaced: the discriminator's state stays
+            for tag in ('gen_flow_model', 'i3d'):
+                lo, hi = self.eng.group_range[tag]
+                if hi > lo:
+                    ops.memset_zero(self.eng.exp_avg[lo:hi])
+                    ops.memset_zero(self.eng.exp_avg_sq[lo:hi])
+            ops.memset_zero(self.steps[0:2])
+        self.stage2, self.epoch, self.i_batch = stage2, epoch, 0
         if not stage2:
             lr_g = hp.lr_base if lr is None else lr
             lr_c = 0.0 if hp.detach else lr_g                               # :405-411
@@ -110,27 +132,40 @@ class I3DTrainStep:
         for g in self.group:
             if g == 'gf':
                 rows.append((lr_g, hp.weight_decay))
+            elif g == 'd':
+                rows.append((hp.lr_base if hp.lr_d is None else hp.lr_d, hp.weight_decay))
             else:
                 mult = lr_mult_rule(self.lr_mul if g == 'base' else 1.0, epoch, hp.epoch_thre)
                 rows.append((lr_c * mult, hp.weight_decay))
         self.hyper.copy_(torch.tensor(rows, dtype=torch.float32))
 
     # ------------------------------------------------------------------ step
-    def _optimizers(self, src: torch.Tensor, scale: float):
+    def _optimizers(self, which, src: torch.Tensor, scale: float):
         eng, hp = self.eng, self.hp
-        for gi, g in enumerate(('cls', 'gf')):
+        for g in which:
             t, n = self.chunks[g]
-            if hp.optim == 'adam':
-                eps = 1e-3 if (g == 'gf' and self.stage2) else 1e-8
+            gi = ('cls', 'gf', 'd').index(g)
+            if hp.optim == 'adam' or g == 'd':                  # optimizer_3 is Adam whatever --optimizer says
+                eps = 1e-3 if (g == 'd' or (g == 'gf' and self.stage2)) else 1e-8
                 ops.adam_step(eng.params, src, eng.exp_avg, eng.exp_avg_sq, t, n, self.hyper.view(-1),
                               self.steps[gi:gi + 1], hp.betas[0], hp.betas[1], eps, scale)
             else:
                 ops.sgd_nesterov_step(eng.params, src, eng.exp_avg, t, n, self.hyper.view(-1), hp.momentum, scale)
 
+    def _ranges(self, which):
+        gr = self.eng.group_range
+        out = []
+        for g in which:
+            lo, hi = gr[{'cls': 'i3d', 'gf': 'gen_flow_model', 'd': 'discriminator'}[g]]
+            if hi > lo:
+                out.append((lo, hi))
+        return out
+
     def step(self, data: torch.Tensor, target: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
-             metrics: bool = True) -> Dict[str, float]:
+             metrics: bool = True, disc_masks=None) -> Dict[str, float]:
         """data [B, 7, T, H, W] (device or pinned host), target [B].  dropout_mask [B, 400] replaces the draw of
-        nn.Dropout(hp.dropout) (None: drawn here with the same ATen call)."""
+        nn.Dropout(hp.dropout) (None: drawn here with the same ATen call); disc_masks: the Dropout2d masks of the
+        discriminator blocks (adv > 0; None: drawn)."""
         eng, hp, B = self.eng, self.hp, self.B
         dev = eng.device
         if not data.is_cuda:
@@ -140,33 +175,55 @@ class I3DTrainStep:
             eng.set_dropout(hp.dropout, dropout_mask if dropout_mask is not None else eng.draw_dropout_mask(hp.dropout))
         else:
             eng.set_dropout(0.0)
+        d_stage = self.adv and self.i_batch % (2 * hp.iter_size) < hp.iter_size
+        self.i_batch += 1
+        w_ce = 1.0 if (d_stage or not self.adv or self.epoch >= 1) else 0.0          # train/model.py:397-402
         eng.zero_grads()
         eng.forward_data(data, train=True)
-        ops.ce_head(eng.logits, B, 1, eng.num_class, self.target, 1.0 / (B * self.world), self.consensus,
+        n = eng.N
+        ops.ce_head(eng.logits, B, 1, eng.num_class, self.target, w_ce / (B * self.world), self.consensus,
                     eng.d_logits, self.ce_stats)
         H, W = eng.H, eng.W
-        numel = eng.N * 2 * H * W
-        ops.mse_head(eng.gen_flow, eng.in_flow, numel, 2.0 / (numel * self.world), eng.dD, self.mse_sum,
-                     frame_elems=2 * H * W, dgen_ns=eng.dD.shape[1] * H * W)
+        numel = n * 2 * H * W
+        # the D stage's loss has no MSE term (:362-369); the kernel still evaluates it for the metrics
+        ops.mse_head(eng.gen_flow, eng.in_flow, numel, 0.0 if d_stage else 2.0 / (numel * self.world), eng.dD,
+                     self.mse_sum, frame_elems=2 * H * W, dgen_ns=eng.dD.shape[1] * H * W)
+        if self.adv:
+            # validity of [generated | real] frames against [0 | 1], in BOTH stages (static_model.forward :148-160)
+            eng.forward_discriminator(n, eng.in_flow, train=True,
+                                      masks=disc_masks if disc_masks is not None else eng.draw_dropout_masks(2 * n))
+            ops.ce_head(eng.validity, 2 * n, 1, 2, self.adv_t, hp.adv / (2 * n * self.world), None, eng.d_validity,
+                        self.adv_stats)
         # I3D.forward is never called with detach=True by fit (train/model.py:139-147): the classifier's
-        # gradient reaches the generator through the stem
-        eng.backward(eng.N, cls=True, cls_wgrad=True, gen_grad=True, cls_to_gen=True)
+        # gradient reaches the generator through the stem.  A zero-weighted CE (G stage of epoch 0) is dead work
+        eng.backward(n, cls=w_ce != 0.0, cls_wgrad=True, gen_grad=True, cls_to_gen=True, disc=self.adv,
+                     disc_wgrad=self.adv, disc_to_gen=self.adv)
         self.i += 1
         stepped = False
-        if hp.iter_size > 1:
+        if self.acc is not None:
             ops.axpy(self.acc, eng.grads, 1.0)
         if self.i % hp.iter_size == 0:
-            src = self.acc if hp.iter_size > 1 else eng.grads
+            src = self.acc if self.acc is not None else eng.grads
+            which = ('cls', 'gf') if not self.adv else (('cls', 'd') if d_stage else ('gf',))
             if self.world > 1:
                 import torch.distributed as dist
-                dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.pg)
-            self._optimizers(src, 1.0 / hp.iter_size)
-            if hp.iter_size > 1:
-                ops.memset_zero(self.acc)
+                rs = self._ranges(which)
+                lo, hi = min(r[0] for r in rs), max(r[1] for r in rs)
+                if self.adv and d_stage:
+                    assert len(rs) == 1 or rs[0][1] == rs[1][0] or rs[1][1] == rs[0][0]    # adjacent: one collective
+                dist.all_reduce(src[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self._optimizers(which, src, 1.0 / hp.iter_size)
+            if self.acc is not None:
+                for lo, hi in self._ranges(which):
+                    ops.memset_zero(self.acc[lo:hi])
             self.i = 0
             stepped = True
         if not metrics:
             return {'stepped': stepped}
         ce = self.ce_stats.cpu().tolist()
-        return {'loss_ce': ce[0] / B, 'top1': ce[1] * 100.0 / B, 'top5': ce[2] * 100.0 / B,
-                'loss_mse': float(self.mse_sum.cpu()[0]) / numel, 'stepped': stepped}
+        out = {'loss_ce': ce[0] / B, 'top1': ce[1] * 100.0 / B, 'top5': ce[2] * 100.0 / B,
+               'loss_mse': float(self.mse_sum.cpu()[0]) / numel, 'stepped': stepped,
+               'stage': 'D' if d_stage else 'G'}
+        if self.adv:
+            out['loss_adv'] = self.adv_stats.cpu().tolist()[0] / (2 * n)
+        return out

@@ -1,9 +1,10 @@
 """CPU oracle for the I3D classifier behind the DMC generator  --  TEST INFRASTRUCTURE ONLY.
 
 Plain torch-CPU fp32 restatement of ``I3D.forward`` (code/dmcnet_I3D/network/i3d.py:435-533) on a
-functional ``state_dict`` and of the non-adversarial iteration of ``model.fit``
-(code/dmcnet_I3D/train/model.py:286-446: CE + MSE, two optimizers, gradient accumulation over
-``iter_size`` batches, the two-stage learning-rate rule of ``adjust_learning_rate`` :268-283).  Only
+functional ``state_dict`` and of one iteration of ``model.fit`` (code/dmcnet_I3D/train/model.py:286-446:
+CE + MSE [+ the adversarial CE of ``--adv``], the classifier's / generator's / discriminator's optimizers,
+the alternating D / G stages, gradient accumulation over ``iter_size`` batches, the two-stage learning-rate
+rule of ``adjust_learning_rate`` :268-283).  Only
 ``tests/``, ``__graft_entry__`` and ``bench.py``'s CPU-baseline legs may import it.
 
 Parity pin: the reference has no tests or golden vectors for this path; this restatement is pinned
@@ -42,8 +43,8 @@ def tf_same_pad(kernel: Sequence[int], stride: Sequence[int]) -> Tuple[int, ...]
     return tuple(out[2:] + out[:2])
 
 
-def build_state(num_class: int, arch_estimator: Optional[str] = 'DenseNetTiny', seed: Optional[int] = 1
-                ) -> "OrderedDict[str, Tensor]":
+def build_state(num_class: int, arch_estimator: Optional[str] = 'DenseNetTiny', seed: Optional[int] = 1,
+                arch_d: Optional[str] = None) -> "OrderedDict[str, Tensor]":
     """state_dict of ``I3D(num_class, 'flow+mp4', arch_estimator=...)`` with the constructors' random
     init, in the reference's construction order (generator first, i3d.py:457-465)."""
     from torch import nn
@@ -56,6 +57,15 @@ def build_state(num_class: int, arch_estimator: Optional[str] = 'DenseNetTiny', 
             mods['gen_flow_model.conv_%d.0' % k] = nn.Conv2d(cin, g, 3, 1, 1, bias=True)
             cin += g
         mods['gen_flow_model.predict_flow'] = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)
+    if arch_d is not None:                                     # i3d.py:466-476, blocks :112-137 (same as dmcnet_GAN)
+        from oracle.dmc_oracle import disc_blocks, disc_fc_in
+        for name, ci, co, stride, bn in disc_blocks(arch_d):
+            if bn:
+                nn.Conv2d(ci, co, 3, stride, 1)              # the bn-less block built first and discarded
+            mods['discriminator.discriminator_block_%s.0' % name] = nn.Conv2d(ci, co, 3, stride, 1)
+            if bn:
+                mods['discriminator.discriminator_block_%s.3' % name] = nn.BatchNorm2d(co, 0.8)
+        mods['discriminator.adv_layer'] = nn.Linear(disc_fc_in(arch_d), 2)
 
     def unit(name, cin, cout, k, stride=1):
         pad = tf_same_pad((k,) * 3, (stride,) * 3)
@@ -179,9 +189,10 @@ class I3DHParams:
 
     def __init__(self, optim: str = 'sgd', lr_base: float = 0.005, lr_base2: float = 0.002, weight_decay: float = 1e-4,
                  iter_size: int = 1, epoch_thre: int = 1, fine_tune: bool = True, detach: bool = False,
-                 dropout: float = 0.5):
+                 dropout: float = 0.5, adv: float = 0.0, lr_d: Optional[float] = None):
         self.optim, self.lr_base, self.lr_base2, self.weight_decay = optim, lr_base, lr_base2, weight_decay
         self.iter_size, self.epoch_thre, self.fine_tune, self.detach, self.dropout = iter_size, epoch_thre, fine_tune, detach, dropout
+        self.adv, self.lr_d = adv, (lr_base if lr_d is None else lr_d)
 
 
 def param_groups(keys: Sequence[str]):
@@ -204,16 +215,23 @@ def lr_mult_rule(lr_mult: float, epoch: int, epoch_thre: int) -> float:
 
 
 class I3DOracleTrainer:
-    """``model.fit`` without a discriminator (optimizer_3 is None), one call = one batch."""
+    """``model.fit``, one call = one batch of the epoch.  Without a discriminator (hp.adv == 0, optimizer_3 is
+    None) every batch is a classifier + generator iteration; with one, batches alternate in runs of
+    ``iter_size``: D stage (loss CE + adv * adversarial CE; steps ``optimizer`` and ``optimizer_3``), G stage
+    (loss [0 in epoch 0] * CE + MSE + adv * the SAME adversarial CE; steps ``optimizer_mse`` only).  Gradients
+    are those of autograd's .grad accumulation: a stage zeroes only the optimizers it steps, so the other
+    groups' gradients carry over into their next step -- reference behaviour, train/model.py:344-446."""
 
-    def __init__(self, state: Dict[str, Tensor], hp: I3DHParams, arch_estimator: str = 'DenseNetTiny'):
-        self.hp, self.arch = hp, arch_estimator
+    def __init__(self, state: Dict[str, Tensor], hp: I3DHParams, arch_estimator: str = 'DenseNetTiny',
+                 arch_d: Optional[str] = None):
+        self.hp, self.arch, self.arch_d = hp, arch_estimator, arch_d
         self.st: "OrderedDict[str, Tensor]" = OrderedDict()
         for k, v in state.items():
             self.st[k] = v.detach().clone() if is_buffer(k) else v.detach().clone().requires_grad_(True)
         keys = [k for k in self.st if not is_buffer(k)]
         gf, base, new = param_groups(keys)
-        self.keys = {'gf': gf, 'base': base, 'new': new}
+        dk = [k for k in keys if k.startswith('discriminator')]
+        self.keys = {'gf': gf, 'base': base, 'new': new, 'd': dk}
         lr_mul = 0.2 if hp.fine_tune else 0.5                           # train_model.py:100-105
         self.lr_mul = lr_mul
         P = lambda ks: [self.st[k] for k in ks]
@@ -226,46 +244,93 @@ class I3DOracleTrainer:
         # stage one / stage two optimizers (train_model.py:122-176); the generator's stage-two Adam has eps 1e-3
         self.opt = [make(hp.lr_base, grp()), make(hp.lr_base2, grp())]
         self.opt_mse = [make(hp.lr_base, [{'params': P(gf)}]), make(hp.lr_base2, [{'params': P(gf)}], eps=1e-3)]
+        self.opt_d = None
+        if hp.adv > 0:
+            assert arch_d is not None
+            self.opt_d = torch.optim.Adam(P(dk), lr=hp.lr_base, weight_decay=hp.weight_decay, eps=1e-3)   # :143-149
         self.i = 0
+        self.i_batch = 0
         self.epoch = 0
+
+    def set_epoch(self, epoch: int):
+        self.epoch, self.i_batch = epoch, 0
 
     def _adjust(self, optimizer, lr, epoch=0, epoch_thre=0):
         for g in optimizer.param_groups:
             g['lr'] = lr * lr_mult_rule(g.get('lr_mult', 1.0), epoch, epoch_thre)
 
-    def step(self, data: Tensor, target: Tensor, dropout_mask: Optional[Tensor] = None) -> Dict[str, float]:
-        hp = self.hp
-        stage2 = self.epoch >= hp.epoch_thre
-        opt, opt_mse = self.opt[1 if stage2 else 0], self.opt_mse[1 if stage2 else 0]
+    def _forward(self, data, target, dropout_mask, disc_masks):
         logits, flow = i3d_forward(self.st, data[:, :5], arch_estimator=self.arch, train=True,
                                    dropout_mask=dropout_mask)
         loss = F.cross_entropy(logits, target)
         mse = F.mse_loss(flow, data[:, 5:7])
-        (loss + mse).backward()                                          # train/model.py:392-396
+        adv = None
+        if self.opt_d is not None:                                       # static_model.forward, :148-160
+            from oracle.dmc_oracle import disc_forward
+            b, _, t, h, w = flow.shape
+            x = torch.cat((torch.reshape(torch.transpose(flow, 1, 2), (-1, 2, h, w)),
+                           torch.reshape(torch.transpose(data[:, 5:7], 1, 2), (-1, 2, h, w))), 0)
+            validity = disc_forward(self.st, x, self.arch_d, True, disc_masks)
+            labels = torch.cat((torch.zeros(b * t, dtype=torch.int64), torch.ones(b * t, dtype=torch.int64)))
+            adv = F.cross_entropy(validity, labels)
+            self.last_validity = validity.detach()
+        self.last_logits, self.last_flow = logits.detach(), flow.detach()
+        return logits, loss, mse, adv
+
+    def _div(self, opts):
+        if self.hp.iter_size != 1:
+            for o in opts:
+                for g in o.param_groups:
+                    for p in g['params']:
+                        if p.grad is not None:
+                            p.grad /= self.hp.iter_size
+
+    def step(self, data: Tensor, target: Tensor, dropout_mask: Optional[Tensor] = None,
+             disc_masks: Optional[Sequence[Tensor]] = None) -> Dict[str, float]:
+        hp = self.hp
+        stage2 = self.epoch >= hp.epoch_thre
+        opt, opt_mse = self.opt[1 if stage2 else 0], self.opt_mse[1 if stage2 else 0]
+        d_stage = self.opt_d is not None and self.i_batch % (2 * hp.iter_size) < hp.iter_size
+        self.i_batch += 1
+        logits, loss, mse, adv = self._forward(data, target, dropout_mask, disc_masks)
         if not stage2:
             lr = hp.lr_base
             lr1 = 0.0 if hp.detach else lr                               # :405-411
         else:
             lr = lr1 = hp.lr_base2
-        self._adjust(opt, lr1, self.epoch, hp.epoch_thre)
-        self._adjust(opt_mse, lr)
-        self.i += 1
         stepped = False
-        if self.i % hp.iter_size == 0:
-            if hp.iter_size != 1:
-                for o in (opt, opt_mse):
-                    for g in o.param_groups:
-                        for p in g['params']:
-                            p.grad /= hp.iter_size
-            opt.step(); opt.zero_grad()
-            opt_mse.step(); opt_mse.zero_grad()
-            self.i = 0
-            stepped = True
-        self.last_logits, self.last_flow = logits.detach(), flow.detach()
+        if d_stage:
+            (loss + hp.adv * adv).backward()                             # :362-369
+            self._adjust(opt, lr1, self.epoch, hp.epoch_thre)
+            self._adjust(self.opt_d, hp.lr_d)
+            self.i += 1
+            if self.i % hp.iter_size == 0:
+                self._div((opt, self.opt_d))
+                opt.step(); opt.zero_grad()
+                self.opt_d.step(); self.opt_d.zero_grad()
+                self.i, stepped = 0, True
+        else:
+            if self.opt_d is None:
+                (loss + mse).backward()                                  # :392-396
+                self._adjust(opt, lr1, self.epoch, hp.epoch_thre)
+            else:
+                ((0.0 if self.epoch < 1 else 1.0) * loss + mse + hp.adv * adv).backward()    # :397-402
+            self._adjust(opt_mse, lr)
+            self.i += 1
+            if self.i % hp.iter_size == 0:
+                self._div(((opt, opt_mse) if self.opt_d is None else (opt_mse,)))
+                if self.opt_d is None:
+                    opt.step(); opt.zero_grad()
+                opt_mse.step(); opt_mse.zero_grad()
+                self.i, stepped = 0, True
         top = logits.detach().topk(min(5, logits.shape[1]), 1).indices
-        return {'loss_ce': float(loss), 'loss_mse': float(mse), 'stepped': stepped,
-                'top1': float((top[:, :1] == target.view(-1, 1)).any(1).float().mean() * 100),
-                'top5': float((top == target.view(-1, 1)).any(1).float().mean() * 100)}
+        out = {'loss_ce': float(loss.detach()), 'loss_mse': float(mse.detach()), 'stepped': stepped,
+               'stage': 'D' if d_stage else 'G',
+               'top1': float((top[:, :1] == target.view(-1, 1)).any(1).float().mean() * 100),
+               'top5': float((top == target.view(-1, 1)).any(1).float().mean() * 100)}
+        if adv is not None:
+            out['loss_adv'] = float(adv.detach())
+        return out
 
     def grads(self) -> Dict[str, Tensor]:
         return {k: v.grad.detach().clone() for k, v in self.st.items() if not is_buffer(k) and v.grad is not None}

@@ -66,6 +66,18 @@ def run(write: bool = False, clip_len: int = 16, num_class: int = 51):
         le_r, _ = net(data[:, :5], node='flow+logit')
         le, _ = O.i3d_forward(st, data[:, :5], arch_estimator='DenseNetTiny', train=False)
     assert torch.equal(le, le_r), 'eval forward differs'
+    # with a discriminator: construction order / init, and I3D.forward(x, node='D')
+    from oracle.dmc_oracle import disc_forward
+    torch.manual_seed(1)
+    netd = ref.I3D(num_class, modality='flow+mp4', dropout_prob=0, arch_estimator='DenseNetTiny', arch_d='Discriminator')
+    sdd = O.build_state(num_class, 'DenseNetTiny', seed=1, arch_d='Discriminator')
+    assert list(sdd.keys()) == list(netd.state_dict().keys())
+    for k, v in netd.state_dict().items():
+        assert torch.equal(sdd[k], v), k
+    netd.eval()
+    xs = torch.randn(3, 2, 224, 224)
+    with torch.no_grad():
+        assert torch.equal(netd(xs, node='D'), disc_forward({k: v.clone() for k, v in sdd.items()}, xs, 'Discriminator', False))
     if write:
         import numpy as np
         out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'i3d_b1.npz')

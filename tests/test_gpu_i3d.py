@@ -405,7 +405,7 @@ def test_two_inception_blocks_forward_backward_vs_fp64(beta_shift, bar):
     gin[:, cols_b] = to_ring(go)
     eng.zero_grads()
     ops.memset_zero(eng._sums2)
-    ops.memset_zero(eng._dwg)
+    ops.memset_zero(eng._i3d_dwg)
     eng.gbuf[0][:gin.numel()].copy_(gin.view(-1).to(dev))
     cur = eng._mixed_bwd(Bk, a_hi, a_lo, 0, None, False, True, (A['cat'], A['m_cat'], 0))
     cur = eng._mixed_bwd(A, x_hi, x_lo, cur, None, True, True, None)
@@ -486,3 +486,73 @@ def test_maxpool3d_on_a_map_with_a_zero_frame_behind_each_clip():
     assert float(d5[:, 0].abs().max()) == 0 and float(d5[:, T + 1].abs().max()) == 0
     got_g = d5[:, 1:T + 1, 1:, 1:].permute(0, 4, 1, 2, 3) * (x.detach() > 0)
     assert rel(got_g, x.grad * (x.detach() > 0)) < 1e-6
+
+
+def _movement(eng, before_e, after_ref, before_ref, param_group_of):
+    out = eng.state_dict()
+    moved = {}
+    for grp in ('gf', 'd', 'base', 'new'):
+        num = den = mine = 0.0
+        for k in eng.specs:
+            if param_group_of(k) != grp:
+                continue
+            d_e = out[k].double().cpu() - before_e[k].double().cpu()
+            d_o = after_ref[k].double() - before_ref[k].double()
+            num += float((d_e - d_o).norm() ** 2)
+            den += float(d_o.norm() ** 2)
+            mine += float(d_e.norm() ** 2)
+        moved[grp] = {'rel_err': (num / den) ** 0.5 if den > 0 else None, 'ref': den ** 0.5, 'engine': mine ** 0.5}
+    return moved
+
+
+@pytest.mark.parametrize('frozen_d_stage', [False, True])
+def test_i3d_adversarial_stages_vs_oracle(frozen_d_stage):
+    """--adv 1 --arch-d Discriminator: a D stage and a G stage of model.fit (train/model.py:357-446): the three
+    losses of both batches and the parameter movement of every group.
+    frozen_d_stage=False: the D stage steps the classifier (SGD) and the discriminator (Adam) -- compared;
+    the generator must not move.  frozen_d_stage=True (stage one with --detach 1 and --lr-d 0: both learning
+    rates of the D stage are 0, so the G stage runs on identical weights on both sides): the generator's G
+    step, whose gradient is the sum of what the D stage's backward left in .grad and the G stage's own."""
+    from dmcnet_b200.i3d_engine import I3DEngine
+    from dmcnet_b200.i3d_trainer import I3DHParams, I3DTrainStep, param_group_of
+    from oracle import dmc_oracle as O2
+    arch_d = 'Discriminator'
+    sd = O.build_state(51, 'DenseNetTiny', seed=1, arch_d=arch_d)
+    if frozen_d_stage:
+        hp_kw = dict(optim='sgd', iter_size=1, epoch_thre=5, detach=True, dropout=0.5, adv=1.0, lr_d=0.0)
+    else:
+        hp_kw = dict(optim='sgd', iter_size=1, epoch_thre=0, dropout=0.5, adv=1.0, lr_d=0.002)
+    ref = O.I3DOracleTrainer(sd, O.I3DHParams(**hp_kw), arch_d=arch_d)
+    ref.set_epoch(1)                                    # epoch >= 1: the G stage's CE counts
+    eng = I3DEngine(51, 1, 16, arch_d=arch_d)
+    eng.load_state(sd)
+    tr = I3DTrainStep(eng, I3DHParams(**hp_kw))
+    tr.set_epoch(1)
+    gen = torch.Generator().manual_seed(5)
+    for it in range(2):
+        data, target = O.make_inputs(1, 16, 51, seed=20 + it)
+        mask = eng.draw_dropout_mask(0.5, gen)
+        dmasks = O2.draw_dropout_masks(arch_d, 32, gen)
+        before_ref, before_e = ref.state_dict(), eng.state_dict()
+        m_ref = ref.step(data, target, dropout_mask=mask, disc_masks=dmasks)
+        m = tr.step(data.cuda(), target.cuda(), dropout_mask=mask, disc_masks=dmasks)
+        torch.cuda.synchronize()
+        assert m['stage'] == m_ref['stage'] == ('D', 'G')[it] and m['stepped'] and m_ref['stepped']
+        tol = 2e-3 if (it == 0 or frozen_d_stage) else 3e-2        # else the second batch runs on moved weights
+        for k in ('loss_ce', 'loss_mse', 'loss_adv'):
+            assert abs(m[k] - m_ref[k]) < tol * max(1.0, abs(m_ref[k])), (it, k, m, m_ref)
+        if it == 0:
+            assert rel(eng.validity[:32], ref.last_validity) < 1e-3
+        moved = _movement(eng, before_e, ref.state_dict(), before_ref, param_group_of)
+        print('I3D adversarial %s stage (frozen D stage: %s):' % (m['stage'], frozen_d_stage), moved)
+        _record('adv_%s_stage%s' % (m['stage'], '_frozen' if frozen_d_stage else ''), moved)
+        if it == 0:
+            assert moved['gf']['ref'] == 0.0 and moved['gf']['engine'] == 0.0        # D stage: the generator stays
+            if frozen_d_stage:
+                assert all(moved[g]['engine'] == 0.0 and moved[g]['ref'] == 0.0 for g in ('d', 'base', 'new'))
+            else:
+                assert moved['new']['rel_err'] < 2e-3 and moved['base']['rel_err'] < 0.25 and moved['d']['rel_err'] < 0.35, moved
+        else:                                                                         # G stage: only the generator moves
+            assert all(moved[g]['engine'] == 0.0 and moved[g]['ref'] == 0.0 for g in ('d', 'base', 'new')), moved
+            if frozen_d_stage:
+                assert moved['gf']['rel_err'] < 0.3, moved

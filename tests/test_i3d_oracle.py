@@ -58,3 +58,30 @@ def test_dropin_module_state_dict_and_groups():
         assert lr_mult_rule(a_, b_, 2) == O.lr_mult_rule(a_, b_, 2)
     with pytest.raises(RuntimeError):
         plain(torch.zeros(1, 2, 16, 224, 224))          # CPU tensor: there is no CPU path
+
+
+def test_oracle_adversarial_stages_keep_the_other_groups_gradients():
+    """fit() zeroes only the optimizers a stage steps (train/model.py:387-446): after a D stage the generator's
+    gradient is still in .grad (and becomes part of the G step), after the G stage the classifier's and the
+    discriminator's are."""
+    from oracle import dmc_oracle as O2
+    sd = O.build_state(51, 'DenseNetTiny', seed=1, arch_d='Discriminator')
+    assert len(sd) == 383
+    tr = O.I3DOracleTrainer(sd, O.I3DHParams(optim='sgd', epoch_thre=0, dropout=0.0, adv=1.0), arch_d='Discriminator')
+    tr.set_epoch(1)
+    g = torch.Generator().manual_seed(3)
+    data, target = O.make_inputs(1, 16, 51, seed=3)
+    m = tr.step(data, target, disc_masks=O2.draw_dropout_masks('Discriminator', 32, g))
+    assert m['stage'] == 'D' and m['stepped'] and 0.3 < m['loss_adv'] < 2.0
+    gr = tr.grads()
+    assert all(k.startswith('gen_flow_model') for k in gr) and len(gr) == 12
+    before = {k: v.clone() for k, v in tr.state_dict().items()}
+    m = tr.step(data, target, disc_masks=O2.draw_dropout_masks('Discriminator', 32, g))
+    assert m['stage'] == 'G' and m['stepped']
+    gr = tr.grads()
+    assert not any(k.startswith('gen_flow_model') for k in gr) and 'classifier.weight' in gr \
+        and 'discriminator.adv_layer.weight' in gr
+    after = tr.state_dict()
+    assert not torch.equal(after['gen_flow_model.conv_0.0.weight'], before['gen_flow_model.conv_0.0.weight'])
+    assert torch.equal(after['classifier.weight'], before['classifier.weight'])
+    assert torch.equal(after['discriminator.adv_layer.weight'], before['discriminator.adv_layer.weight'])
