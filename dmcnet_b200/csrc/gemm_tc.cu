@@ -444,25 +444,35 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
             is = *reinterpret_cast<const float4*>(bw.invstd + n0 + c + c4);
           }
           if (!bwd) {
+            // two batches of four rows; the loads of a second gradient source (bw.gb) are all issued before
+            // the first use -- one dependent load per row made this path latency-bound (20 us per tile)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + (lane >> 3);
-              const long gq = m0 + wq * 32 + row;
-              if (gq < M) {
-                float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
-                const long o = gq * (long)ldD + n0 + c + c4;
-                if (bw.gb) {          // plain data gradient + a second gradient source (no mask, no reduction)
-                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(bw.gb + o));
-                  v.x += g4.x; v.y += g4.y; v.z += g4.z; v.w += g4.w;
-                }
-                if (act.out_hi) {
-                  bf16 hh[4], ll[4];
-                  split_bf16(v.x, hh[0], ll[0]); split_bf16(v.y, hh[1], ll[1]);
-                  split_bf16(v.z, hh[2], ll[2]); split_bf16(v.w, hh[3], ll[3]);
-                  *reinterpret_cast<uint2*>(act.out_hi + o) = *reinterpret_cast<uint2*>(hh);
-                  *reinterpret_cast<uint2*>(act.out_lo + o) = *reinterpret_cast<uint2*>(ll);
-                } else {
-                  *reinterpret_cast<float4*>(D + o) = v;
+            for (int hb = 0; hb < 2; ++hb) {
+              float4 g4[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int row = (hb * 4 + ii) * 4 + (lane >> 3);
+                const long gq = m0 + wq * 32 + row;
+                g4[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bw.gb && gq < M) g4[ii] = __ldg(reinterpret_cast<const float4*>(bw.gb + gq * (long)ldD + n0 + c + c4));
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int row = (hb * 4 + ii) * 4 + (lane >> 3);
+                const long gq = m0 + wq * 32 + row;
+                if (gq < M) {
+                  float4 v = *reinterpret_cast<const float4*>(stage + row * S::EPI_PITCH + c4);
+                  const long o = gq * (long)ldD + n0 + c + c4;
+                  v.x += g4[ii].x; v.y += g4[ii].y; v.z += g4[ii].z; v.w += g4[ii].w;
+                  if (act.out_hi) {
+                    bf16 hh[4], ll[4];
+                    split_bf16(v.x, hh[0], ll[0]); split_bf16(v.y, hh[1], ll[1]);
+                    split_bf16(v.z, hh[2], ll[2]); split_bf16(v.w, hh[3], ll[3]);
+                    *reinterpret_cast<uint2*>(act.out_hi + o) = *reinterpret_cast<uint2*>(hh);
+                    *reinterpret_cast<uint2*>(act.out_lo + o) = *reinterpret_cast<uint2*>(ll);
+                  } else {
+                    *reinterpret_cast<float4*>(D + o) = v;
+                  }
                 }
               }
             }

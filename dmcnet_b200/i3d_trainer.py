@@ -227,3 +227,49 @@ class I3DTrainStep:
         if self.adv:
             out['loss_adv'] = self.adv_stats.cpu().tolist()[0] / (2 * n)
         return out
+
+    # ------------------------------------------------------------------ pipelined host input
+    def step_pipelined(self, data: torch.Tensor, target: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
+                       disc_masks=None) -> Dict[str, float]:
+        """``step`` for pinned HOST batches: the host->device copy of THIS batch runs on a copy stream while the
+        previous batch computes, and the call returns the metrics of the PREVIOUS batch (``{}`` first;
+        ``flush()`` returns the last).  Same arithmetic as ``step``."""
+        dev = self.eng.device
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty(data.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._stage_t = [torch.empty(target.shape, dtype=torch.int64, device=dev) for _ in range(2)]
+            self._ev_copied = [torch.cuda.Event() for _ in range(2)]
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]
+            self._host_stats = torch.zeros(8, dtype=torch.float64).pin_memory()
+            self._k, self._pending = 0, None
+        s = self._k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if self._k >= 2:
+                self._copy_stream.wait_event(self._ev_free[s])          # the step that read this slot is done
+            self._stage[s].copy_(data, non_blocking=True)
+            self._stage_t[s].copy_(target, non_blocking=True)
+            self._ev_copied[s].record(self._copy_stream)
+        prev = self._collect()
+        main.wait_event(self._ev_copied[s])
+        out = self.step(self._stage[s], self._stage_t[s], dropout_mask=dropout_mask, metrics=False,
+                        disc_masks=disc_masks)
+        self._ev_free[s].record(main)
+        self._pending = out
+        self._k += 1
+        return prev
+
+    def _collect(self) -> Dict[str, float]:
+        if getattr(self, '_pending', None) is None:
+            return {}
+        B, numel = self.B, self.eng.N * 2 * self.eng.H * self.eng.W
+        ce = self.ce_stats.cpu().tolist()                               # synchronises with the previous step only
+        out = dict(self._pending)
+        out.update({'loss_ce': ce[0] / B, 'top1': ce[1] * 100.0 / B, 'top5': ce[2] * 100.0 / B,
+                    'loss_mse': float(self.mse_sum.cpu()[0]) / numel})
+        self._pending = None
+        return out
+
+    def flush(self) -> Dict[str, float]:
+        return self._collect()

@@ -39,7 +39,8 @@ class Timer:
                 fl = 2.0 * P * Cout * Cin * nt
             shape = ''
             if name == 'dmc_tc_tap_gemm_ex':
-                shape = 'M=%d N=%d K=%d' % (M, N, K)
+                shape = 'M=%d N=%d K=%d ldD=%d lda=%d%s%s' % (M, N, K, v(args[11]), v(args[2]),
+                                                            ' stats' if v(args[17]) else '', ' gb' if v(args[21]) else '')
             elif name == 'dmc_tc_wgrad_ex':
                 shape = 'P=%d Cout=%d Cin=%d' % (P, Cout, Cin)
             self.ev.append((key, e0, e1, fl, shape))
@@ -78,9 +79,13 @@ def main():
     for k in sorted(ms, key=lambda k: -ms[k]):
         extra = '  %.0f TFLOP/s issued' % (fl[k] / ms[k] / 1e9) if fl[k] else ''
         print('  %-34s %8.3f ms  %5.1f %%  x%d%s' % (k, ms[k], 100 * ms[k] / tot, cnt[k] // steps, extra))
+    ncall = defaultdict(int)
+    for k, e0, e1, f, shape in t.ev:
+        if shape:
+            ncall[(k, shape)] += 1
     print('slowest GEMM shapes (ms per step, all calls of the shape):')
-    for (k, shape), v in sorted(calls.items(), key=lambda kv: -kv[1])[:24]:
-        print('  %-28s %-34s %7.3f ms' % (k, shape, v))
+    for (k, shape), v in sorted(calls.items(), key=lambda kv: -kv[1])[:40]:
+        print('  %-28s %-58s %7.3f ms  x%d' % (k, shape, v, ncall[(k, shape)] // steps))
 
 
 if __name__ == '__main__':
