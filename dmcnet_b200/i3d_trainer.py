@@ -70,10 +70,17 @@ def param_group_of(key: str) -> str:
 
 
 class I3DTrainStep:
-    def __init__(self, engine: I3DEngine, hp: I3DHParams, *, world_size: int = 1, process_group=None):
+    def __init__(self, engine: I3DEngine, hp: I3DHParams, *, world_size: int = 1, process_group=None,
+                 use_graph: bool = False):
         if hp.optim not in ('sgd', 'adam'):
             raise ValueError("optimizer must be 'sgd' or 'adam' (train_hmdb51.py:80-82)")
         self.eng, self.hp, self.world, self.pg = engine, hp, world_size, process_group
+        # use_graph: forward + heads + backward (+ accumulation) of a batch is one CUDA graph per stage, the
+        # optimizer step another (the gradient all-reduce of N > 1 sits between them): ~400 launches per step,
+        # which bound the step once a rank holds only a few clips (strong scaling of BASELINE config 5)
+        self.use_graph = use_graph
+        self._graphs: Dict[object, object] = {}
+        self.in_data = None
         dev = engine.device
         self.B = engine.clips
         self.target = torch.zeros(self.B, dtype=torch.int64, device=dev)
@@ -161,6 +168,57 @@ class I3DTrainStep:
                 out.append((lo, hi))
         return out
 
+    def _fwd_bwd(self, data: torch.Tensor, d_stage: bool, w_ce: float):
+        """zero_grad -> forward -> losses -> backward -> accumulate; static buffers only (graph-capturable)."""
+        eng, hp, B = self.eng, self.hp, self.B
+        n, H, W = eng.N, eng.H, eng.W
+        numel = n * 2 * H * W
+        eng.zero_grads()
+        eng.forward_data(data, train=True)
+        ops.ce_head(eng.logits, B, 1, eng.num_class, self.target, w_ce / (B * self.world), self.consensus,
+                    eng.d_logits, self.ce_stats)
+        # the D stage's loss has no MSE term (:362-369); the kernel still evaluates it for the metrics
+        ops.mse_head(eng.gen_flow, eng.in_flow, numel, 0.0 if d_stage else 2.0 / (numel * self.world), eng.dD,
+                     self.mse_sum, frame_elems=2 * H * W, dgen_ns=eng.dD.shape[1] * H * W)
+        if self.adv:
+            # validity of [generated | real] frames against [0 | 1], in BOTH stages (static_model.forward :148-160)
+            eng.forward_discriminator(n, eng.in_flow, train=True, masks='preloaded')
+            ops.ce_head(eng.validity, 2 * n, 1, 2, self.adv_t, hp.adv / (2 * n * self.world), None, eng.d_validity,
+                        self.adv_stats)
+        # I3D.forward is never called with detach=True by fit (train/model.py:139-147): the classifier's
+        # gradient reaches the generator through the stem.  A zero-weighted CE (G stage of epoch 0) is dead work
+        eng.backward(n, cls=w_ce != 0.0, cls_wgrad=True, gen_grad=True, cls_to_gen=True, disc=self.adv,
+                     disc_wgrad=self.adv, disc_to_gen=self.adv)
+        if self.acc is not None:
+            ops.axpy(self.acc, eng.grads, 1.0)
+
+    def _apply(self, which, src: torch.Tensor):
+        self._optimizers(which, src, 1.0 / self.hp.iter_size)
+        if self.acc is not None:
+            for lo, hi in self._ranges(which):
+                ops.memset_zero(self.acc[lo:hi])
+
+    def _graphed(self, key, fn):
+        """Run fn eagerly (use_graph off, or the first call of a key: warm-up), else capture it once and replay."""
+        if not self.use_graph:
+            return fn()
+        st = self._graphs.get(key)
+        if st is None:
+            fn()
+            self._graphs[key] = 'warm'
+            return
+        if st == 'warm':
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            self._graphs[key] = st = g
+        st.replay()
+
     def step(self, data: torch.Tensor, target: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
              metrics: bool = True, disc_masks=None) -> Dict[str, float]:
         """data [B, 7, T, H, W] (device or pinned host), target [B].  dropout_mask [B, 400] replaces the draw of
@@ -168,7 +226,7 @@ class I3DTrainStep:
         discriminator blocks (adv > 0; None: drawn)."""
         eng, hp, B = self.eng, self.hp, self.B
         dev = eng.device
-        if not data.is_cuda:
+        if not data.is_cuda and not self.use_graph:
             data = data.to(dev, non_blocking=True)
         self.target.copy_(target, non_blocking=True)
         if hp.dropout > 0.0:
@@ -178,30 +236,19 @@ class I3DTrainStep:
         d_stage = self.adv and self.i_batch % (2 * hp.iter_size) < hp.iter_size
         self.i_batch += 1
         w_ce = 1.0 if (d_stage or not self.adv or self.epoch >= 1) else 0.0          # train/model.py:397-402
-        eng.zero_grads()
-        eng.forward_data(data, train=True)
         n = eng.N
-        ops.ce_head(eng.logits, B, 1, eng.num_class, self.target, w_ce / (B * self.world), self.consensus,
-                    eng.d_logits, self.ce_stats)
         H, W = eng.H, eng.W
         numel = n * 2 * H * W
-        # the D stage's loss has no MSE term (:362-369); the kernel still evaluates it for the metrics
-        ops.mse_head(eng.gen_flow, eng.in_flow, numel, 0.0 if d_stage else 2.0 / (numel * self.world), eng.dD,
-                     self.mse_sum, frame_elems=2 * H * W, dgen_ns=eng.dD.shape[1] * H * W)
         if self.adv:
-            # validity of [generated | real] frames against [0 | 1], in BOTH stages (static_model.forward :148-160)
-            eng.forward_discriminator(n, eng.in_flow, train=True,
-                                      masks=disc_masks if disc_masks is not None else eng.draw_dropout_masks(2 * n))
-            ops.ce_head(eng.validity, 2 * n, 1, 2, self.adv_t, hp.adv / (2 * n * self.world), None, eng.d_validity,
-                        self.adv_stats)
-        # I3D.forward is never called with detach=True by fit (train/model.py:139-147): the classifier's
-        # gradient reaches the generator through the stem.  A zero-weighted CE (G stage of epoch 0) is dead work
-        eng.backward(n, cls=w_ce != 0.0, cls_wgrad=True, gen_grad=True, cls_to_gen=True, disc=self.adv,
-                     disc_wgrad=self.adv, disc_to_gen=self.adv)
+            eng.set_masks(disc_masks if disc_masks is not None else eng.draw_dropout_masks(2 * n), 2 * n)
+        if self.use_graph:
+            if self.in_data is None or self.in_data.shape != data.shape:
+                self.in_data = torch.empty(data.shape, dtype=torch.float32, device=dev)
+            self.in_data.copy_(data, non_blocking=True)
+            data = self.in_data
+        self._graphed(('fb', bool(d_stage), w_ce), lambda: self._fwd_bwd(data, d_stage, w_ce))
         self.i += 1
         stepped = False
-        if self.acc is not None:
-            ops.axpy(self.acc, eng.grads, 1.0)
         if self.i % hp.iter_size == 0:
             src = self.acc if self.acc is not None else eng.grads
             which = ('cls', 'gf') if not self.adv else (('cls', 'd') if d_stage else ('gf',))
@@ -209,13 +256,8 @@ class I3DTrainStep:
                 import torch.distributed as dist
                 rs = self._ranges(which)
                 lo, hi = min(r[0] for r in rs), max(r[1] for r in rs)
-                if self.adv and d_stage:
-                    assert len(rs) == 1 or rs[0][1] == rs[1][0] or rs[1][1] == rs[0][0]    # adjacent: one collective
                 dist.all_reduce(src[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-            self._optimizers(which, src, 1.0 / hp.iter_size)
-            if self.acc is not None:
-                for lo, hi in self._ranges(which):
-                    ops.memset_zero(self.acc[lo:hi])
+            self._graphed(('apply', which, self.stage2), lambda: self._apply(which, src))
             self.i = 0
             stepped = True
         if not metrics:

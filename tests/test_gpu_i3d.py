@@ -556,3 +556,35 @@ def test_i3d_adversarial_stages_vs_oracle(frozen_d_stage):
             assert all(moved[g]['engine'] == 0.0 and moved[g]['ref'] == 0.0 for g in ('d', 'base', 'new')), moved
             if frozen_d_stage:
                 assert moved['gf']['rel_err'] < 0.3, moved
+
+
+def test_i3d_step_in_cuda_graphs_matches_eager():
+    """I3DTrainStep(use_graph=True): forward + backward of a batch and the optimizer step replayed from CUDA
+    graphs give the losses of the eager step on every batch (a stale buffer or a missed copy would not) and
+    move the head the same way."""
+    from dmcnet_b200.i3d_engine import I3DEngine
+    from dmcnet_b200.i3d_trainer import I3DHParams, I3DTrainStep
+    sd = O.build_state(51, 'DenseNetTiny', seed=1)
+    runs = []
+    for use_graph in (False, True):
+        eng = I3DEngine(51, 1, 16)
+        eng.load_state(sd)
+        tr = I3DTrainStep(eng, I3DHParams(optim='sgd', epoch_thre=0, dropout=0.5, iter_size=2), use_graph=use_graph)
+        gen = torch.Generator().manual_seed(5)
+        ms = []
+        for it in range(6):                      # warm-up, capture, then four replayed batches (two optimizer steps)
+            data, target = O.make_inputs(1, 16, 51, seed=30 + it)
+            mask = eng.draw_dropout_mask(0.5, gen)
+            ms.append(tr.step(data.pin_memory() if it % 2 else data.cuda(), target.cuda(), dropout_mask=mask))
+        torch.cuda.synchronize()
+        runs.append((ms, eng.state_dict()))
+    (m_e, s_e), (m_g, s_g) = runs
+    for it, (a, b) in enumerate(zip(m_e, m_g)):
+        assert a['stepped'] == b['stepped'] == (it % 2 == 1)
+        tol = 1e-5 if it < 2 else 2e-2           # after the first optimizer step: switch noise, not graph effects
+        assert abs(a['loss_ce'] - b['loss_ce']) < tol * max(1.0, a['loss_ce']), (it, a, b)
+        assert abs(a['loss_mse'] - b['loss_mse']) < 1e-4 * max(1.0, a['loss_mse']), (it, a, b)
+    d_e = s_e['classifier.weight'] - sd['classifier.weight'].cuda()
+    d_g = s_g['classifier.weight'] - sd['classifier.weight'].cuda()
+    assert rel_l2(d_g, d_e) < 5e-2
+    assert int(s_g['conv3d_2b_1x1.batch3d.num_batches_tracked']) == 6

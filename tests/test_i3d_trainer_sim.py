@@ -65,7 +65,12 @@ class SimI3DEngine(E.I3DEngine):
     def draw_dropout_masks(self, m, generator=None):
         return O2.draw_dropout_masks(self.arch_d, m, generator)
 
+    def set_masks(self, masks, m):
+        self._dmasks = [mk.clone() for mk in masks]
+
     def forward_discriminator(self, n, input_flow=None, *, train=True, masks=None, use_dropout=True):
+        if isinstance(masks, str) and masks == 'preloaded':
+            masks = self._dmasks
         st, logits, flow, _ = self._graph
         x = torch.cat((torch.reshape(torch.transpose(flow, 1, 2), (-1, 2, 224, 224)), input_flow), 0)
         with torch.enable_grad():
