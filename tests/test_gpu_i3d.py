@@ -588,3 +588,31 @@ def test_i3d_step_in_cuda_graphs_matches_eager():
     d_g = s_g['classifier.weight'] - sd['classifier.weight'].cuda()
     assert rel_l2(d_g, d_e) < 5e-2
     assert int(s_g['conv3d_2b_1x1.batch3d.num_batches_tracked']) == 6
+
+
+def test_plain_two_channel_i3d_at_32_frames():
+    """modality 'flow' (no estimator) and a 32-frame clip: the drop-in module against the oracle -- the head's
+    AvgPool3d((2,7,7)) then leaves three temporal positions whose mean is folded into one weighted mean, and
+    every pool / geometry runs at a second set of extents."""
+    from dmcnet_b200.i3d_model import I3D
+    torch.manual_seed(4)
+    net = I3D(51, modality='flow', dropout_prob=0)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ref_sd = O.build_state(51, None, seed=4)
+    assert list(sd.keys()) == list(ref_sd.keys()) and all(torch.equal(sd[k], ref_sd[k]) for k in sd)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 2, 32, 224, 224, generator=g)
+    target = torch.tensor([7])
+    st = {k: (v.clone() if O.is_buffer(k) else v.clone().requires_grad_(True)) for k, v in ref_sd.items()}
+    lo, _ = O.i3d_forward(st, x, arch_estimator=None, train=True)
+    F.cross_entropy(lo, target).backward()
+    net.cuda().train()
+    logits = net(x.cuda())
+    assert rel(logits, lo) < 1e-3 and torch.equal(logits.argmax(1).cpu(), lo.argmax(1))
+    F.cross_entropy(logits, target.cuda()).backward()
+    named = dict(net.named_parameters())
+    for k in ('classifier.weight', 'conv3d_0c_1x1.conv3d.weight'):
+        assert rel_l2(named[k].grad, st[k].grad) < 1e-3, k
+    errs = sorted(rel_l2(named[k].grad, st[k].grad) for k in named)
+    print('plain I3D, 32 frames: gradient errors median %.2e worst %.2e' % (errs[len(errs) // 2], errs[-1]))
+    assert errs[len(errs) // 2] < 1e-1 and errs[-1] < 3e-1
