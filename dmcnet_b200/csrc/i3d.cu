@@ -128,21 +128,54 @@ struct Pool3 {
   int t_hi;                        // extra zero frames behind each clip of the INPUT map (the stem map has one)
 };
 
+// 8-byte read-only load under a predicate (zeros otherwise) without a branch around it
+__device__ __forceinline__ uint2 ldg_u2_if(const void* p, bool on) {
+  uint2 v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\t"
+               "@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+               : "=r"(v.x), "=r"(v.y) : "l"(p), "r"((int)on));
+  return v;
+}
+
+// Pool geometry: compile-time for the four pools I3D uses (i3d.py:452-476 and the inception branch), so the
+// window loops unroll and every window code is an immediate; the Pool3 fields otherwise (KT = 0).
+template <int KT, int KH, int KW, int ST, int SH, int SW>
+struct PoolGeo {
+  static constexpr bool FIXED = KT > 0;
+  const Pool3& g;
+  __device__ __forceinline__ int kt() const { return FIXED ? KT : g.kt; }
+  __device__ __forceinline__ int kh() const { return FIXED ? KH : g.kh; }
+  __device__ __forceinline__ int kw() const { return FIXED ? KW : g.kw; }
+  __device__ __forceinline__ int st() const { return FIXED ? ST : g.st; }
+  __device__ __forceinline__ int sh() const { return FIXED ? SH : g.sh; }
+  __device__ __forceinline__ int sw() const { return FIXED ? SW : g.sw; }
+  __device__ __forceinline__ int pt() const { return FIXED ? (KT > ST ? (KT - ST) / 2 : 0) : g.pt; }
+  __device__ __forceinline__ int ph() const { return FIXED ? (KH > SH ? (KH - SH) / 2 : 0) : g.ph; }
+  __device__ __forceinline__ int pw() const { return FIXED ? (KW > SW ? (KW - SW) / 2 : 0) : g.pw; }
+};
+
 // in hi/lo [clips][Ti+1][Hi+1][Wi+1][C] -> out hi/lo [clips][To+1][Ho+1][Wo+1][C] (interior rows only; the
 // output buffers are allocated zeroed) and idx [rows_out][C] = window position (dt*kh + dh)*kw + dw of the
 // maximum, 255 when a padding zero wins.  Scan order and strict '>' as ATen's max_pool3d: the first
 // maximum wins.  Positions outside the map are the ConstantPad3d zeros of i3d.py:380-388.
 // One thread = 4 channels x WB consecutive outputs of a row: every input of the union of their windows is
-// loaded once (WB + 2 instead of 3 * WB positions per (dt, dh) at stride 1) -- the kernel is bound by L2 reads.
-template <int WB>
+// loaded once (WB + 2 instead of 3 * WB positions per (dt, dh) at stride 1).  The kernel is bound by
+// instruction issue (ncu: sm 70 %, DRAM 3 %), so the running maximum of a (output, channel) is three
+// registers -- value, the hi/lo bf16 pair packed in one word, window code -- and an update is one compare
+// and three selects.
+template <int WB, int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, int clips, int C,
                      const Pool3 g, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
                      uint8_t* __restrict__ idx) {
+  const PoolGeo<KT, KH, KW, ST, SH, SW> q{g};
+  const int kt = q.kt(), kh = q.kh(), kw = q.kw(), st = q.st(), sh = q.sh(), sw = q.sw();
+  const int pt = q.pt(), ph = q.ph(), pw = q.pw();
   const int C4 = C / 4;
   const int wblocks = (g.Wo + WB - 1) / WB;
   const long units = (long)clips * g.To * g.Ho * wblocks * C4;
   const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
+  const int nw = (WB - 1) * sw + kw;          // input columns under the WB windows
   // 32-bit index arithmetic (the host checks units < 2^32): 64-bit divisions cost more than the loads
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)units; i += gridDim.x * blockDim.x) {
     const int c = (int)(i % (unsigned)C4) * 4;
@@ -152,45 +185,47 @@ maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in
     const int to = (int)(r % (unsigned)g.To);
     const int n = (int)(r / (unsigned)g.To);
     float best[WB][4];
-    uint2 bh[WB], bl[WB];
-    uint32_t bi[WB];                         // four window codes, one byte per channel
+    uint32_t bhl[WB][4];                     // (hi bits << 16) | lo bits of the running maximum
+    uint32_t bcode[WB][4];
 #pragma unroll
-    for (int j = 0; j < WB; ++j) {
-      best[j][0] = best[j][1] = best[j][2] = best[j][3] = -INFINITY;
-      bh[j] = make_uint2(0u, 0u); bl[j] = make_uint2(0u, 0u); bi[j] = 0xffffffffu;
-    }
-    const int w_lo = wo0 * g.sw - g.pw, w_hi = (wo0 + WB - 1) * g.sw - g.pw + g.kw - 1;
-    for (int dt = 0; dt < g.kt; ++dt) {
-      const int t = to * g.st + dt - g.pt;
-      for (int dh = 0; dh < g.kh; ++dh) {
-        const int h = ho * g.sh + dh - g.ph;
+    for (int j = 0; j < WB; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { best[j][k] = -INFINITY; bhl[j][k] = 0u; bcode[j][k] = 255u; }
+    const int w_lo = wo0 * sw - pw;
+#pragma unroll
+    for (int dt = 0; dt < kt; ++dt) {
+      const int t = to * st + dt - pt;
+#pragma unroll
+      for (int dh = 0; dh < kh; ++dh) {
+        const int h = ho * sh + dh - ph;
         const bool in_th = t >= 0 && t < g.Ti && h >= 0 && h < g.Hi;
-        const long qrow = (((long)n * Tpi + t + 1) * Hpi + h + 1) * Wpi + 1;
-        for (int w = w_lo; w <= w_hi; ++w) {
+        // element offset of column w_lo of the row; 32-bit (the host checks rows * C < 2^30) so that an
+        // address is one multiply-add, not a rematerialised 64-bit product per load
+        const int e0 = (((n * Tpi + t + 1) * Hpi + h + 1) * Wpi + 1 + w_lo) * C + c;
+        const uint32_t cbase = (uint32_t)((dt * kh + dh) * kw);
+#pragma unroll
+        for (int iw = 0; iw < nw; ++iw) {
+          const int w = w_lo + iw;
           const bool in = in_th && w >= 0 && w < g.Wi;
-          uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
-          if (in) {
-            vh = __ldg(reinterpret_cast<const uint2*>(in_hi + (qrow + w) * C + c));
-            vl = __ldg(reinterpret_cast<const uint2*>(in_lo + (qrow + w) * C + c));
-          }
-          const bf16* vhp = reinterpret_cast<const bf16*>(&vh);
-          const bf16* vlp = reinterpret_cast<const bf16*>(&vl);
+          const uint2 vh = ldg_u2_if(in_hi + (e0 + iw * C), in);
+          const uint2 vl = ldg_u2_if(in_lo + (e0 + iw * C), in);
+          const uint32_t p[4] = {__byte_perm(vl.x, vh.x, 0x5410), __byte_perm(vl.x, vh.x, 0x7632),
+                                 __byte_perm(vl.y, vh.y, 0x5410), __byte_perm(vl.y, vh.y, 0x7632)};
           float v[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = join_bf16(vhp[k], vlp[k]);
+          for (int k = 0; k < 4; ++k) v[k] = __uint_as_float(p[k] & 0xffff0000u) + __uint_as_float(p[k] << 16);
 #pragma unroll
           for (int j = 0; j < WB; ++j) {
-            const int dw = w - ((wo0 + j) * g.sw - g.pw);
-            if (dw < 0 || dw >= g.kw) continue;
-            const uint32_t code = in ? (uint32_t)((dt * g.kh + dh) * g.kw + dw) : 255u;
-            bf16* bhp = reinterpret_cast<bf16*>(&bh[j]);
-            bf16* blp = reinterpret_cast<bf16*>(&bl[j]);
+            const int dw = iw - j * sw;
+            if (dw < 0 || dw >= kw) continue;
+            const uint32_t code = in ? cbase + (uint32_t)dw : 255u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (v[k] > best[j][k]) {
-                best[j][k] = v[k]; bhp[k] = vhp[k]; blp[k] = vlp[k];
-                bi[j] = (bi[j] & ~(0xffu << (8 * k))) | (code << (8 * k));
-              }
+            for (int k = 0; k < 4; ++k) {
+              const bool up = v[k] > best[j][k];
+              best[j][k] = up ? v[k] : best[j][k];
+              bhl[j][k] = up ? p[k] : bhl[j][k];
+              bcode[j][k] = up ? code : bcode[j][k];
+            }
           }
         }
       }
@@ -199,9 +234,12 @@ maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in
 #pragma unroll
     for (int j = 0; j < WB; ++j) {
       if (wo0 + j >= g.Wo) break;
-      *reinterpret_cast<uint2*>(out_hi + (qo + j) * C + c) = bh[j];
-      *reinterpret_cast<uint2*>(out_lo + (qo + j) * C + c) = bl[j];
-      *reinterpret_cast<uint32_t*>(idx + (qo + j) * C + c) = bi[j];
+      *reinterpret_cast<uint2*>(out_hi + (qo + j) * C + c) =
+          make_uint2(__byte_perm(bhl[j][0], bhl[j][1], 0x7632), __byte_perm(bhl[j][2], bhl[j][3], 0x7632));
+      *reinterpret_cast<uint2*>(out_lo + (qo + j) * C + c) =
+          make_uint2(__byte_perm(bhl[j][0], bhl[j][1], 0x5410), __byte_perm(bhl[j][2], bhl[j][3], 0x5410));
+      *reinterpret_cast<uint32_t*>(idx + (qo + j) * C + c) =
+          bcode[j][0] | (bcode[j][1] << 8) | (bcode[j][2] << 16) | (bcode[j][3] << 24);
     }
   }
 }
@@ -209,14 +247,20 @@ maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in
 // dX[row_in][c] = add[row_in][c] + sum over the windows containing the position whose idx points at it of
 // g[row_out][c]; every row of dX is written (ring rows: 0).  One thread = 4 channels x WB consecutive input
 // columns: the idx words of the union of their windows are loaded once.
-template <int WB>
+template <int WB, int KT, int KH, int KW, int ST, int SH, int SW>
 __global__ void __launch_bounds__(256)
 maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ idx, int clips, int C,
                      const Pool3 g, const float* __restrict__ add, float* __restrict__ dX) {
+  const PoolGeo<KT, KH, KW, ST, SH, SW> q{g};
+  const int kt = q.kt(), kh = q.kh(), kw = q.kw(), st = q.st(), sh = q.sh(), sw = q.sw();
+  const int pt = q.pt(), ph = q.ph(), pw = q.pw();
   const int C4 = C / 4;
   const int Hpi = g.Hi + 1, Wpi = g.Wi + 1, Tpi = g.Ti + 1 + g.t_hi, Hpo = g.Ho + 1, Wpo = g.Wo + 1, Tpo = g.To + 1;
   const int wblocks = (Wpi + WB - 1) / WB;
   const long units = (long)clips * Tpi * Hpi * wblocks * C4;
+  // at most this many windows contain a position / overlap the WB columns, per dimension
+  const int nto = (kt + st - 1) / st, nho = (kh + sh - 1) / sh, nwo = (WB + kw - 2) / sw + 1;
+  const uint32_t kwu = (uint32_t)kw;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)units; i += gridDim.x * blockDim.x) {
     const int c = (int)(i % (unsigned)C4) * 4;
     unsigned r = i / (unsigned)C4;
@@ -237,28 +281,35 @@ maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__
       }
       // windows along w of the WB columns w0 .. w0 + WB - 1 (w = wp - 1): wo * sw - pw <= w <= wo * sw - pw + kw - 1
       const int w0 = wp0 - 1;
-      int wo_lo = (w0 + g.pw - g.kw + 1 + g.sw - 1);
-      wo_lo = wo_lo <= 0 ? 0 : wo_lo / g.sw;
-      int wo_hi = (w0 + WB - 1 + g.pw) / g.sw;
+      int wo_lo = (w0 + pw - kw + 1 + sw - 1);
+      wo_lo = wo_lo <= 0 ? 0 : wo_lo / sw;
+      int wo_hi = (w0 + WB - 1 + pw) / sw;
       if (wo_hi >= g.Wo) wo_hi = g.Wo - 1;
-      const int to_hi = (t + g.pt) / g.st, ho_hi = (h + g.ph) / g.sh;
-      for (int to = to_hi; to >= 0 && to * g.st - g.pt + g.kt - 1 >= t; --to) {
-        if (to >= g.To) continue;
-        const int dt = t + g.pt - to * g.st;
-        for (int ho = ho_hi; ho >= 0 && ho * g.sh - g.ph + g.kh - 1 >= h; --ho) {
-          if (ho >= g.Ho) continue;
-          const int dh = h + g.ph - ho * g.sh;
-          const int cbase = (dt * g.kh + dh) * g.kw;
-          const long qorow = (((long)n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + 1;
-          for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-            const uint32_t id = __ldg(reinterpret_cast<const uint32_t*>(idx + (qorow + wo) * C + c));
+      const int to_hi = (t + pt) / st, ho_hi = (h + ph) / sh;
+#pragma unroll
+      for (int a = 0; a < nto; ++a) {
+        const int to = to_hi - a;
+        const int dt = t + pt - to * st;                    // grows with a: past kt - 1 no window reaches t
+        if (to < 0 || dt >= kt || to >= g.To) continue;
+#pragma unroll
+        for (int b = 0; b < nho; ++b) {
+          const int ho = ho_hi - b;
+          const int dh = h + ph - ho * sh;
+          if (ho < 0 || dh >= kh || ho >= g.Ho) continue;
+          const uint32_t cbase = (uint32_t)((dt * kh + dh) * kw);
+          // 32-bit element offsets (the host checks rows * C < 2^30)
+          const int eo = (((n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + 1 + wo_lo) * C + c;
+#pragma unroll
+          for (int e = 0; e < nwo; ++e) {
+            const int wo = wo_lo + e;
+            if (wo > wo_hi) continue;
+            const uint32_t id = __ldg(reinterpret_cast<const uint32_t*>(idx + (eo + e * C)));
             // the codes this output can hold for our columns: cbase + dw, dw = w - (wo * sw - pw) in [0, kw)
             const uint32_t d0 = (id & 0xffu) - cbase, d1 = ((id >> 8) & 0xffu) - cbase,
                            d2 = ((id >> 16) & 0xffu) - cbase, d3 = (id >> 24) - cbase;
-            const uint32_t kwu = (uint32_t)g.kw;
             if (d0 >= kwu && d1 >= kwu && d2 >= kwu && d3 >= kwu) continue;
-            const float4 gv = __ldg(reinterpret_cast<const float4*>(gout + (qorow + wo) * C + c));
-            const int wbase = wo * g.sw - g.pw - w0;          // column index j of dw = 0
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(gout + (eo + e * C)));
+            const int wbase = wo * sw - pw - w0;            // column index j of dw = 0
 #pragma unroll
             for (int j = 0; j < WB; ++j) {
               const uint32_t dw = (uint32_t)(j - wbase);
@@ -441,6 +492,17 @@ static int fill_pool(Pool3& g, const int* in_thw, const int* kernel, const int* 
   return 0;
 }
 
+// The four pools of I3D (i3d.py:452-476, Mixed branch 3) have kernels with the geometry compiled in;
+// 0 = the generic kernel.
+static int pool_variant(const Pool3& g) {
+  const int k = g.kt * 100 + g.kh * 10 + g.kw, s = g.st * 100 + g.sh * 10 + g.sw;
+  if (k == 133 && s == 122) return 1;
+  if (k == 333 && s == 222) return 2;
+  if (k == 222 && s == 222) return 3;
+  if (k == 333 && s == 111) return 4;
+  return 0;
+}
+
 // Output extents of MaxPool3dTFPadding(kernel, stride) on a [T][H][W] map (i3d.py:375-388).
 extern "C" int dmc_maxpool3d_out_shape(const int* in_thw, const int* kernel, const int* stride, int* out_thw) {
   Pool3 g;
@@ -459,8 +521,20 @@ extern "C" int dmc_maxpool3d_fwd(const void* in_hi, const void* in_lo, int clips
   DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_fwd: bad geometry");
   const long units = (long)clips * g.To * g.Ho * cdiv(g.Wo, 4) * (C / 4);
   DMC_REQUIRE(units < (1L << 32), "maxpool3d_fwd: map too large");
-  maxpool3d_fwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(
-      (const bf16*)in_hi, (const bf16*)in_lo, clips, C, g, (bf16*)out_hi, (bf16*)out_lo, (uint8_t*)idx);
+  DMC_REQUIRE((long)clips * (g.Ti + 2 + g.t_hi) * (g.Hi + 1) * (g.Wi + 1) * C < (1L << 30),
+              "maxpool3d_fwd: input map too large for 32-bit element offsets");
+  const unsigned grid = grid_1d(units, 256, 148L * 32);
+#define DMC_POOL_FWD(...)                                                                                   \
+  maxpool3d_fwd_kernel<4, __VA_ARGS__><<<grid, 256, 0, ST(stream)>>>(                                       \
+      (const bf16*)in_hi, (const bf16*)in_lo, clips, C, g, (bf16*)out_hi, (bf16*)out_lo, (uint8_t*)idx)
+  switch (pool_variant(g)) {
+    case 1: DMC_POOL_FWD(1, 3, 3, 1, 2, 2); break;
+    case 2: DMC_POOL_FWD(3, 3, 3, 2, 2, 2); break;
+    case 3: DMC_POOL_FWD(2, 2, 2, 2, 2, 2); break;
+    case 4: DMC_POOL_FWD(3, 3, 3, 1, 1, 1); break;
+    default: DMC_POOL_FWD(0, 0, 0, 0, 0, 0);
+  }
+#undef DMC_POOL_FWD
   return dmc_check_launch("maxpool3d_fwd_kernel");
 }
 
@@ -473,8 +547,20 @@ extern "C" int dmc_maxpool3d_bwd(const float* gout, const void* idx, int clips, 
   DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_bwd: bad geometry");
   const long units = (long)clips * (g.Ti + 1 + g.t_hi) * (g.Hi + 1) * cdiv(g.Wi + 1, 4) * (C / 4);
   DMC_REQUIRE(units < (1L << 32), "maxpool3d_bwd: map too large");
-  maxpool3d_bwd_kernel<4><<<grid_1d(units, 256, 148L * 32), 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips,
-                                                                              C, g, add, dX);
+  DMC_REQUIRE((long)clips * (g.To + 1) * (g.Ho + 1) * (g.Wo + 1) * C < (1L << 30),
+              "maxpool3d_bwd: output map too large for 32-bit element offsets");
+  const unsigned grid = grid_1d(units, 256, 148L * 32);
+#define DMC_POOL_BWD(...)                                                                                   \
+  maxpool3d_bwd_kernel<4, __VA_ARGS__><<<grid, 256, 0, ST(stream)>>>(gout, (const uint8_t*)idx, clips, C, g, \
+                                                                     add, dX)
+  switch (pool_variant(g)) {
+    case 1: DMC_POOL_BWD(1, 3, 3, 1, 2, 2); break;
+    case 2: DMC_POOL_BWD(3, 3, 3, 2, 2, 2); break;
+    case 3: DMC_POOL_BWD(2, 2, 2, 2, 2, 2); break;
+    case 4: DMC_POOL_BWD(3, 3, 3, 1, 1, 1); break;
+    default: DMC_POOL_BWD(0, 0, 0, 0, 0, 0);
+  }
+#undef DMC_POOL_BWD
   return dmc_check_launch("maxpool3d_bwd_kernel");
 }
 
