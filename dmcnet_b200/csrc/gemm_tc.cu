@@ -165,6 +165,7 @@ struct ActFuse {
 // pulls 104 KB instead of 251 KB per tile through the SM's L2 port, which is what bounded it (one 84 KB
 // stage of the RW = 1 schedule takes ~2000 cycles to arrive at ~42 B/clk, longer than its 36 MMAs run).
 static constexpr int RB_TAPS = 9;
+static constexpr bool RESIDENT_B_DEFAULT = false;
 template <int BN, int STAGES, int RW = 0>
 struct TapGemmWsSmem {
   static constexpr int A_BYTES = (RW ? RW_ROWS : 128) * 128;
@@ -1186,8 +1187,10 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
       if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
       if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
       // one 64-wide output block and at most nine taps: the weights stay resident in shared memory
-      static const bool rb_off = getenv("DMC_NO_RESIDENT_B") != nullptr;
-      if (!rb_off && N == 64 && ntaps <= RB_TAPS)
+      // (DMC_RESIDENT_B=0 / 1 overrides the default for A/B timing)
+      static const char* rb_env = getenv("DMC_RESIDENT_B");
+      static const bool rb_on = rb_env ? rb_env[0] == '1' : RESIDENT_B_DEFAULT;
+      if (rb_on && N == 64 && ntaps <= RB_TAPS)
         return launch_tap_gemm_ws<64, 3, 2>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
                                             a_lo_on, act, ring, st, &rw, stats_ld);
       return launch_tap_gemm_ws<64, 2, 1>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,

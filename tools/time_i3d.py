@@ -43,6 +43,8 @@ class Timer:
                                                             ' stats' if v(args[17]) else '', ' gb' if v(args[21]) else '')
             elif name == 'dmc_tc_wgrad_ex':
                 shape = 'P=%d Cout=%d Cin=%d' % (P, Cout, Cin)
+            elif name in ('dmc_maxpool3d_fwd', 'dmc_maxpool3d_bwd'):
+                shape = 'C=%d thw=%s k=%s s=%s' % (v(args[3]), list(args[4]), list(args[6]), list(args[7]))
             self.ev.append((key, e0, e1, fl, shape))
         return cm()
 
@@ -84,7 +86,7 @@ def main():
         if shape:
             ncall[(k, shape)] += 1
     print('slowest GEMM shapes (ms per step, all calls of the shape):')
-    for (k, shape), v in sorted(calls.items(), key=lambda kv: -kv[1])[:40]:
+    for (k, shape), v in sorted(calls.items(), key=lambda kv: -kv[1])[:48]:
         print('  %-28s %-58s %7.3f ms  x%d' % (k, shape, v, ncall[(k, shape)] // steps))
 
 
