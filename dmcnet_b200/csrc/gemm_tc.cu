@@ -159,27 +159,18 @@ struct ActFuse {
   bf16* out_lo;
 };
 
-// RW = 0: one (A tile, B tile) pair per stage; 1: row windows (RwTable); 2: row windows with RESIDENT
-// weights -- every tap's [B_hi ; B_lo] (<= RB_TAPS taps of a 64 x 64 slice) is loaded once per CTA and stays
-// in shared memory, and a stage is ONE plane (hi or lo) of one 136-row window.  A 64-channel 3x3 layer then
-// pulls 104 KB instead of 251 KB per tile through the SM's L2 port, which is what bounded it (one 84 KB
-// stage of the RW = 1 schedule takes ~2000 cycles to arrive at ~42 B/clk, longer than its 36 MMAs run).
-static constexpr int RB_TAPS = 9;
-static constexpr bool RESIDENT_B_DEFAULT = false;
-template <int BN, int STAGES, int RW = 0>
+template <int BN, int STAGES, bool RW = false>
 struct TapGemmWsSmem {
   static constexpr int A_BYTES = (RW ? RW_ROWS : 128) * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = RW == 2 ? A_BYTES : 2 * A_BYTES + (RW ? RW_GT : 1) * 2 * B_BYTES;
-  static constexpr int RES_BYTES = RW == 2 ? RB_TAPS * 2 * B_BYTES : 0;
-  static constexpr int PIPE_BYTES = RES_BYTES + STAGES * STAGE_BYTES;     // resident weights, then the ring
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + (RW ? RW_GT : 1) * 2 * B_BYTES;
   static constexpr int EPI_PITCH = 36;                         // floats; STS.128 conflict-free
   static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
   static constexpr int RED_BYTES = 4 * 2 * BN * 4;             // per-warp column sums (BN statistics)
-  static constexpr int TOTAL = PIPE_BYTES + EPI_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + RED_BYTES + 1024 + 256;
 };
 
-template <int BN, int STAGES, int RW = 0>
+template <int BN, int STAGES, bool RW = false>
 __global__ void __launch_bounds__(192, 1)
 tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
@@ -197,21 +188,17 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* epi = reinterpret_cast<float*>(smem_gen + S::PIPE_BYTES);
-  float* red = reinterpret_cast<float*>(smem_gen + S::PIPE_BYTES + S::EPI_BYTES);
-  const uint32_t ring_base = smem_base + S::RES_BYTES;           // stage ring (behind the resident weights)
-  const uint32_t bar_base = smem_base + S::PIPE_BYTES + S::EPI_BYTES + S::RED_BYTES;
+  float* epi = reinterpret_cast<float*>(smem_gen + STAGES * S::STAGE_BYTES);
+  float* red = reinterpret_cast<float*>(smem_gen + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
+  const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::RED_BYTES;
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * STAGES;
   const uint32_t bar_tfull = bar_base + 16 * STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t bar_res = tmem_slot + 8;                        // RW == 2: resident weights have landed
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / 64;
-  const int planes = a_lo_on ? 2 : 1;
-  // pipeline stages per tile
-  const int iters = RW == 2 ? rw.ngroups * planes : (RW ? rw.ngroups : taps.ntaps * kblocks);
+  const int iters = RW ? rw.ngroups : taps.ntaps * kblocks;     // pipeline stages per tile
   const int total_tiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
@@ -223,7 +210,6 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 4);
     }
-    mbar_init(bar_res, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapAh);
     tma_prefetch_desc(&mapAl);
@@ -239,17 +225,6 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      if constexpr (RW == 2) {
-        // every tap's [B_hi ; B_lo], in group order (the MMA warp enumerates the slots the same way)
-        mbar_expect_tx(bar_res, (uint32_t)(taps.ntaps * 2 * S::B_BYTES));
-        uint32_t slot = 0;
-        for (int g = 0; g < rw.ngroups; ++g)
-          for (int j = 0; j < rw.gcount[g]; ++j, ++slot) {
-            const uint32_t bt = smem_base + slot * 2 * S::B_BYTES;
-            tma_load_3d(bt, &mapBh, bar_res, 0, 0, rw.bsel[g][j]);
-            tma_load_3d(bt + S::B_BYTES, &mapBl, bar_res, 0, 0, rw.bsel[g][j]);
-          }
-      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long m0 = (long)(tile % tiles_m) * 128;
         const int n0 = (tile / tiles_m) * BN;
@@ -257,15 +232,8 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
-          const uint32_t st = ring_base + s * S::STAGE_BYTES;
-          if constexpr (RW == 2) {
-            // one plane of one 136-row window
-            const int g = i / planes, pl = i - g * planes;
-            mbar_expect_tx(full, (uint32_t)S::A_BYTES);
-            tma_load_3d(st, pl ? &mapAl : &mapAh, full, 0, (int)(m0 + rw.gshift[g]), 0);
-            continue;
-          }
-          if constexpr (RW == 1) {
+          const uint32_t st = smem_base + s * S::STAGE_BYTES;
+          if constexpr (RW) {
             // one 136-row window of A (hi [+ lo]) and the weight tiles of the group's taps
             const int cnt = rw.gcount[i];
             mbar_expect_tx(full, (uint32_t)((a_lo_on ? 2 : 1) * S::A_BYTES + cnt * 2 * S::B_BYTES));
@@ -294,41 +262,17 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);            // A_lo * B_hi            -> columns [0, BN)
       const uint32_t idesc2 = umma_idesc_bf16(2 * BN, 0, 0);       // A_hi * [B_hi ; B_lo]   -> columns [0, 2BN)
       uint32_t it = 0, j = 0;
-      if constexpr (RW == 2) {
-        mbar_wait(bar_res, 0);
-        tc_fence_after();
-      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
         const uint32_t a = j & 1, aph = (j >> 1) & 1;
         mbar_wait(bar_tempty + 8 * a, aph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_d + a * ACC_COLS;
-        int slot0 = 0;                                   // RW == 2: first resident slot of the current group
         for (int i = 0; i < iters; ++i, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t st = ring_base + s * S::STAGE_BYTES;
-          if constexpr (RW == 2) {
-            // hi plane: A_hi x [B_hi ; B_lo] (N = 2*BN), lo plane: A_lo x B_hi, weights from the resident slots
-            const int g = i / planes, pl = i - g * planes;
-            const int cnt = rw.gcount[g];
-            for (int jj = 0; jj < cnt; ++jj) {
-              const uint32_t a0 = st + (uint32_t)rw.rowoff[g][jj] * 128u;
-              const uint32_t bt = smem_base + (uint32_t)(slot0 + jj) * 2 * S::B_BYTES;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = umma_desc_sw128(a0 + ks * 32, 16, 1024);
-                const uint64_t bd = umma_desc_sw128(bt + ks * 32, 16, 1024);
-                if (pl == 0) umma_bf16(acc, ad, bd, idesc2, (uint32_t)((i | jj | ks) != 0));
-                else umma_bf16(acc, ad, bd, idesc, 1);
-              }
-            }
-            umma_commit(bar_empty + 8 * s);
-            if (pl == planes - 1) slot0 += cnt;
-            continue;
-          }
-          if constexpr (RW == 1) {
+          const uint32_t st = smem_base + s * S::STAGE_BYTES;
+          if constexpr (RW) {
             const int cnt = rw.gcount[i];
             for (int j = 0; j < cnt; ++j) {
               const uint32_t a0 = st + (uint32_t)rw.rowoff[i][j] * 128u;
@@ -589,7 +533,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <int BN, int STAGES, int RW = 0>
+template <int BN, int STAGES, bool RW = false>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
@@ -1186,15 +1130,8 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
       CUtensorMap wAh, wAl;
       if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
       if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
-      // one 64-wide output block and at most nine taps: the weights stay resident in shared memory
-      // (DMC_RESIDENT_B=0 / 1 overrides the default for A/B timing)
-      static const char* rb_env = getenv("DMC_RESIDENT_B");
-      static const bool rb_on = rb_env ? rb_env[0] == '1' : RESIDENT_B_DEFAULT;
-      if (rb_on && N == 64 && ntaps <= RB_TAPS)
-        return launch_tap_gemm_ws<64, 3, 2>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
-                                            a_lo_on, act, ring, st, &rw, stats_ld);
-      return launch_tap_gemm_ws<64, 2, 1>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
-                                          a_lo_on, act, ring, st, &rw, stats_ld);
+      return launch_tap_gemm_ws<64, 2, true>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
+                                             a_lo_on, act, ring, st, &rw, stats_ld);
     }
     return launch_tap_gemm_ws<64, 4>(mAh, mAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw, a_lo_on, act, ring, st,
                                      nullptr, stats_ld);
