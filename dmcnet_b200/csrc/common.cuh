@@ -100,6 +100,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
+// One lane of a converged warp (elect.sync).  Unlike `lane == 0` the compiler knows the region behind it is
+// executed by a single thread and keeps descriptors / barrier addresses in uniform registers instead of
+// wrapping every tcgen05.mma in a per-lane uniformisation loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // L2 prefetch of one box of a tiled tensor map (a hint: no shared memory, no mbarrier).  Issued a tile or two
 // ahead of the demand load it turns that load's HBM round trip into an L2 hit.
 __device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {

@@ -224,7 +224,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t it = 0;
       // pf > 0 (row-window and one-tap schedules): the activation boxes of the tile this CTA will reach `pf`
       // rounds from now are prefetched into L2.  These GEMMs are bound by the latency of their activation
@@ -282,7 +282,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(BN, 0, 0);            // A_lo * B_hi            -> columns [0, BN)
       const uint32_t idesc2 = umma_idesc_bf16(2 * BN, 0, 0);       // A_hi * [B_hi ; B_lo]   -> columns [0, 2BN)
       uint32_t it = 0, j = 0;
@@ -689,7 +689,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
     return;
   }
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     for (int i = 0; i < iters; ++i) {
       const int s = i % STAGES;
       if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
@@ -711,7 +711,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     const uint32_t idesc = umma_idesc_bf16(BN, 1, 1);
     const uint32_t idesc2 = umma_idesc_bf16(2 * BN, 1, 1);
     for (int i = 0; i < iters; ++i) {
@@ -870,7 +870,7 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant_
     return;
   }
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     for (int i = 0; i < iters; ++i) {
       const int s = i % STAGES;
       if (i >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((i / STAGES) - 1) & 1);
@@ -888,7 +888,7 @@ wgrad64_kernel(const __grid_constant__ CUtensorMap mapGh, const __grid_constant_
         tma_load_3d(xs + S::XP_BYTES, &mapXl, full, 0, xrow, ph);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one_sync()) {
     const uint32_t idesc = umma_idesc_bf16(64, 1, 1);
     for (int i = 0; i < iters; ++i) {
       const int s = i % STAGES;

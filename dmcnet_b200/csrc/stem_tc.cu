@@ -222,7 +222,7 @@ stem_conv_tc_fwd_kernel(const float* __restrict__ in, long in_ns, int H, int W,
     __syncthreads();
     // issued from a builder warp: tcgen05 operations of one warp execute in order, so an
     // epilogue warp that issued the MMAs would have its TMEM loads queue behind them
-    if (tid == 128) {
+    if (warp == 4 && elect_one_sync()) {
       tc_fence_after();
       const uint32_t acc = tmem_d + buf * 128;
       const uint32_t a_u32 = base + buf * ST_A_BYTES, b_u32 = base + 2 * ST_A_BYTES;
@@ -408,7 +408,7 @@ stem_conv_tc_wgrad_kernel(const float* __restrict__ in, long in_ns, int H, int W
     }
     tc_fence_before();
     __syncthreads();
-    if (tid == 128) {
+    if (warp == 4 && elect_one_sync()) {
       tc_fence_after();
       const uint32_t a_u32 = base + buf * ST_A_BYTES;
       const uint32_t g_u32 = base + 2 * ST_A_BYTES + buf * ST_G_BYTES;
