@@ -114,13 +114,6 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-// L2 prefetch of one box of a tiled tensor map (a hint: no shared memory, no mbarrier).  Issued a tile or two
-// ahead of the demand load it turns that load's HBM round trip into an L2 hit.
-__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0,
                                             int c1, int c2) {
   asm volatile(

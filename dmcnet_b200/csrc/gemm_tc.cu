@@ -37,7 +37,6 @@ struct TapTable {
 // it (a SWIZZLE_128B descriptor may start at any 128-byte row of a 1024-byte aligned tile):
 // the L2 -> shared traffic of the A operand, which bounds 64-channel layers, drops ~3x.
 static constexpr int RW_GROUPS = 8, RW_GT = 3, RW_ROWS = 136;
-static constexpr int TMA_PREFETCH_DEFAULT = 0;
 struct RwTable {
   int ngroups;
   int gshift[RW_GROUPS];          // window start = m0 + gshift
@@ -178,7 +177,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
                    const BwFuse bw, int a_lo_on, const ActFuse act, int ring,
-                   const __grid_constant__ RwTable rw, int stats_ld, int pf) {
+                   const __grid_constant__ RwTable rw, int stats_ld) {
   using S = TapGemmWsSmem<BN, STAGES, RW>;
   // Two accumulators of 2*BN columns each: columns [0, BN) collect hi*hi + lo*hi, columns [BN, 2BN) the
   // hi*lo term, because A_hi is multiplied with the STACKED operand [B_hi ; B_lo] (adjacent in the stage) in
@@ -226,32 +225,9 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   if (warp == 0) {
     if (elect_one_sync()) {
       uint32_t it = 0;
-      // pf > 0 (row-window and one-tap schedules): the activation boxes of the tile this CTA will reach `pf`
-      // rounds from now are prefetched into L2.  These GEMMs are bound by the latency of their activation
-      // loads (the operand was written by the previous elementwise pass and streams from HBM; the ring holds
-      // one or two stages in flight), not by bandwidth or the MMAs.
-      auto prefetch_tile = [&](long ptile) {
-        if (ptile >= total_tiles) return;
-        const long pm0 = (ptile % tiles_m) * 128;
-        if constexpr (RW) {
-          for (int g = 0; g < rw.ngroups; ++g) {
-            const int row = (int)(pm0 + rw.gshift[g]);
-            tma_prefetch_3d(&mapAh, 0, row, 0);
-            if (a_lo_on) tma_prefetch_3d(&mapAl, 0, row, 0);
-          }
-        } else {
-          const int row = (int)(pm0 + taps.shift[0]);
-          for (int kb = 0; kb < kblocks; ++kb) {
-            tma_prefetch_3d(&mapAh, kb * 64, row, taps.phase[0]);
-            if (a_lo_on) tma_prefetch_3d(&mapAl, kb * 64, row, taps.phase[0]);
-          }
-        }
-      };
-      if (pf > 1) prefetch_tile((long)blockIdx.x + gridDim.x);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long m0 = (long)(tile % tiles_m) * 128;
         const int n0 = (tile / tiles_m) * BN;
-        if (pf > 0) prefetch_tile((long)tile + (long)pf * gridDim.x);
         for (int i = 0; i < iters; ++i, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -577,13 +553,9 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   if (grid > sms) grid = sms;
   RwTable none;
   none.ngroups = 0;
-  // L2 prefetch distance (tiles of this CTA ahead): DMC_TMA_PREFETCH=<n> overrides, 0 = off
-  static const char* pf_env = getenv("DMC_TMA_PREFETCH");
-  static const int pf_dist = pf_env ? atoi(pf_env) : TMA_PREFETCH_DEFAULT;
-  const int pf = (RW || taps.ntaps == 1) ? pf_dist : 0;
   kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
                                                   tiles_m, tiles_n, stats, bw, a_lo_on, act, ring,
-                                                  rw ? *rw : none, stats_ld > 0 ? stats_ld : N, pf);
+                                                  rw ? *rw : none, stats_ld > 0 ? stats_ld : N);
   return dmc_check_launch("tap_gemm_ws_kernel");
 }
 
