@@ -37,6 +37,7 @@ struct TapTable {
 // it (a SWIZZLE_128B descriptor may start at any 128-byte row of a 1024-byte aligned tile):
 // the L2 -> shared traffic of the A operand, which bounds 64-channel layers, drops ~3x.
 static constexpr int RW_GROUPS = 8, RW_GT = 3, RW_ROWS = 136;
+static constexpr int EPILOGUE_WARPS_DEFAULT = 4;
 struct RwTable {
   int ngroups;
   int gshift[RW_GROUPS];          // window start = m0 + gshift
@@ -159,26 +160,31 @@ struct ActFuse {
   bf16* out_lo;
 };
 
-template <int BN, int STAGES, bool RW = false>
+template <int BN, int STAGES, bool RW = false, int EPW = 4>
 struct TapGemmWsSmem {
   static constexpr int A_BYTES = (RW ? RW_ROWS : 128) * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + (RW ? RW_GT : 1) * 2 * B_BYTES;
   static constexpr int EPI_PITCH = 36;                         // floats; STS.128 conflict-free
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+  static constexpr int EPI_BYTES = EPW * 32 * EPI_PITCH * 4;   // one staging tile per epilogue warp
   static constexpr int RED_BYTES = 4 * 2 * BN * 4;             // per-warp column sums (BN statistics)
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + RED_BYTES + 1024 + 256;
 };
 
-template <int BN, int STAGES, bool RW = false>
-__global__ void __launch_bounds__(192, 1)
+// EPW = 4 or 8 epilogue warps.  With 8, two warps share a TMEM lane quarter (warp % 4) and split the 32-column
+// chunks of a tile between them: the fused BN-backward epilogue of a 64-wide launch (three global loads per
+// element behind a 96-cycle k-step) is otherwise the critical path (ncu: 212 vs 144 us).
+template <int BN, int STAGES, bool RW = false, int EPW = 4>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
 tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const __grid_constant__ TapTable taps, float* __restrict__ D, long M, int N, int ldD,
                    int K, int Hp, int Wp, int tiles_m, int tiles_n, double* __restrict__ stats,
                    const BwFuse bw, int a_lo_on, const ActFuse act, int ring,
                    const __grid_constant__ RwTable rw, int stats_ld) {
-  using S = TapGemmWsSmem<BN, STAGES, RW>;
+  using S = TapGemmWsSmem<BN, STAGES, RW, EPW>;
+  static_assert(EPW == 4 || EPW == 8, "epilogue warps");
+  static_assert((BN / 32) % (EPW / 4) == 0, "chunks must divide between the warps of a lane quarter");
   // Two accumulators of 2*BN columns each: columns [0, BN) collect hi*hi + lo*hi, columns [BN, 2BN) the
   // hi*lo term, because A_hi is multiplied with the STACKED operand [B_hi ; B_lo] (adjacent in the stage) in
   // ONE N = 2*BN MMA: two MMAs per k-step instead of three, and 20 KB instead of 24 KB of shared-memory
@@ -208,7 +214,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, EPW);
     }
     fence_barrier_init();
     tma_prefetch_desc(&mapAh);
@@ -303,12 +309,16 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       }
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4
+    // ---- epilogue warps 2..(2 + EPW - 1): TMEM lane quarter = warp % 4; with EPW = 8 the warps ew and ew + 4
+    // share a quarter and take the chunks ci = cj * NH + half
     const int wq = warp & 3;
-    float* stage = epi + wq * 32 * S::EPI_PITCH;
+    const int ew = warp - 2;
+    constexpr int NH = EPW / 4;
+    const int half = ew >> 2;
+    float* stage = epi + ew * 32 * S::EPI_PITCH;
     // fused BatchNorm statistics: lane = one column of each 32-column chunk; partial sums
     // stay in registers while the CTA walks tiles of the same output-channel block
-    constexpr int NCH = BN / 32;
+    constexpr int NCH = (BN / 32) / NH;               // chunks of THIS warp
     float cs[NCH], css[NCH];          // forward statistics: lane = column of the chunk
     float bs1[NCH][4], bs2[NCH][4];   // fused BN backward: lane owns 4 columns ((lane & 7) * 4 ..)
 #pragma unroll
@@ -331,27 +341,27 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
             a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
             a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
             if (lane < 8) {
-              mine[i * 32 + lane * 4 + k] = a;
-              mine[BN + i * 32 + lane * 4 + k] = b;
+              mine[(i * NH + half) * 32 + lane * 4 + k] = a;
+              mine[BN + (i * NH + half) * 32 + lane * 4 + k] = b;
             }
             bs1[i][k] = 0.f; bs2[i][k] = 0.f;
           }
       } else {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          mine[i * 32 + lane] = cs[i];
-          mine[BN + i * 32 + lane] = css[i];
+          mine[(i * NH + half) * 32 + lane] = cs[i];
+          mine[BN + (i * NH + half) * 32 + lane] = css[i];
           cs[i] = 0.f;
           css[i] = 0.f;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = wq * 32 + lane; c < 2 * BN; c += 128) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPW) : "memory");
+      for (int c = ew * 32 + lane; c < 2 * BN; c += 32 * EPW) {
         const float v = red[c] + red[2 * BN + c] + red[4 * BN + c] + red[6 * BN + c];
         const int col = c < BN ? c : c - BN;
         if (n0f + col < N) atomicAdd(stats + (c < BN ? 0 : stats_ld) + n0f + col, (double)v);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPW) : "memory");
     };
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
@@ -368,7 +378,7 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       const bool keep = q < M && (Hp == 0 || interior_r(q, Hp, Wp, ring));
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
-        const int c = ci * 32;
+        const int c = (ci * NH + half) * 32;
         uint32_t r[32], r2[32];
         tmem_ld32(tmem_d + a * ACC_COLS + ((uint32_t)(wq * 32) << 16) + c, r);
         tmem_ld32(tmem_d + a * ACC_COLS + ((uint32_t)(wq * 32) << 16) + BN + c, r2);
@@ -533,14 +543,14 @@ tap_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <int BN, int STAGES, bool RW = false>
+template <int BN, int STAGES, bool RW = false, int EPW = 4>
 static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const TapTable& taps, float* D, long M, int N,
                               int ldD, int K, int Hp, int Wp, int sms, double* stats,
                               const BwFuse& bw, int a_lo_on, const ActFuse& act, int ring,
                               cudaStream_t stream, const RwTable* rw = nullptr, int stats_ld = 0) {
-  using S = TapGemmWsSmem<BN, STAGES, RW>;
-  auto kern = tap_gemm_ws_kernel<BN, STAGES, RW>;
+  using S = TapGemmWsSmem<BN, STAGES, RW, EPW>;
+  auto kern = tap_gemm_ws_kernel<BN, STAGES, RW, EPW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
@@ -553,7 +563,7 @@ static int launch_tap_gemm_ws(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   if (grid > sms) grid = sms;
   RwTable none;
   none.ngroups = 0;
-  kern<<<(unsigned)grid, 192, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
+  kern<<<(unsigned)grid, 64 + 32 * EPW, S::TOTAL, stream>>>(mAh, mAl, mBh, mBl, taps, D, M, N, ldD, K, Hp, Wp,
                                                   tiles_m, tiles_n, stats, bw, a_lo_on, act, ring,
                                                   rw ? *rw : none, stats_ld > 0 ? stats_ld : N);
   return dmc_check_launch("tap_gemm_ws_kernel");
@@ -1130,6 +1140,13 @@ static int tap_gemm_impl(const void* A_hi, const void* A_lo, int a_phases, long 
       CUtensorMap wAh, wAl;
       if ((rc = make_map_3d(&wAh, A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
       if ((rc = make_map_3d(&wAl, a_lo_on ? A_lo : A_hi, K, a_rows, 1, 64, RW_ROWS, lda))) return rc;
+      // eight epilogue warps where the epilogue reads global memory (fused BN backward, second gradient
+      // source, residual): DMC_EPILOGUE_WARPS=4 / 8 overrides for A/B timing
+      static const char* epw_env = getenv("DMC_EPILOGUE_WARPS");
+      static const int epw = epw_env ? atoi(epw_env) : EPILOGUE_WARPS_DEFAULT;
+      if (epw == 8)
+        return launch_tap_gemm_ws<64, 2, true, 8>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
+                                                  a_lo_on, act, ring, st, &rw, stats_ld);
       return launch_tap_gemm_ws<64, 2, true>(wAh, wAl, mBh, mBl, tt, D, M, N, ldD, K, Hp, Wp, sms, stats, bw,
                                              a_lo_on, act, ring, st, &rw, stats_ld);
     }
