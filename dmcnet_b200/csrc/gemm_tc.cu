@@ -37,7 +37,7 @@ struct TapTable {
 // it (a SWIZZLE_128B descriptor may start at any 128-byte row of a 1024-byte aligned tile):
 // the L2 -> shared traffic of the A operand, which bounds 64-channel layers, drops ~3x.
 static constexpr int RW_GROUPS = 8, RW_GT = 3, RW_ROWS = 136;
-static constexpr int EPILOGUE_WARPS_DEFAULT = 4;
+static constexpr int EPILOGUE_WARPS_DEFAULT = 8;
 struct RwTable {
   int ngroups;
   int gshift[RW_GROUPS];          // window start = m0 + gshift
