@@ -128,7 +128,8 @@ struct Pool3 {
   int t_hi;                        // extra zero frames behind each clip of the INPUT map (the stem map has one)
 };
 
-// Work decomposition of the pool kernels.  Thread index -> (channel quad, column block, row, frame, clip):
+// Work decomposition of the STRIDED forward pools (COMPACT in the kernel; the stride-1 pools and every backward
+// keep the linear order, channel quads fastest).  Thread index -> (channel quad, column block, row, frame, clip):
 // the low 8 bits (one CTA of 256 threads) are 16 channel quads x 2 column blocks x POOL_HT rows x POOL_TT
 // frames (every channel count of I3D is a multiple of 64, so no lane idles; a half-warp still moves whole
 // 128-byte lines).
