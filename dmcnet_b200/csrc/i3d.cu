@@ -238,7 +238,7 @@ maxpool3d_fwd_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in
       for (int dh = 0; dh < kh; ++dh) {
         const int h = ho * sh + dh - ph;
         const bool in_th = t >= 0 && t < g.Ti && h >= 0 && h < g.Hi;
-        // element offset of column w_lo of the row; 32-bit (the host checks rows * C < 2^30) so that an
+        // element offset of column w_lo of the row; 32-bit (the host checks rows * C < 2^31 - 2^24) so that an
         // address is one multiply-add, not a rematerialised 64-bit product per load
         const int e0 = (((n * Tpi + t + 1) * Hpi + h + 1) * Wpi + 1 + w_lo) * C + c;
         const uint32_t cbase = (uint32_t)((dt * kh + dh) * kw);
@@ -338,7 +338,7 @@ maxpool3d_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__
           const int dh = h + ph - ho * sh;
           if (ho < 0 || dh >= kh || ho >= g.Ho) continue;
           const uint32_t cbase = (uint32_t)((dt * kh + dh) * kw);
-          // 32-bit element offsets (the host checks rows * C < 2^30)
+          // 32-bit element offsets (the host checks rows * C < 2^31 - 2^24)
           const int eo = (((n * Tpo + to + 1) * Hpo + ho + 1) * Wpo + 1 + wo_lo) * C + c;
 #pragma unroll
           for (int e = 0; e < nwo; ++e) {
@@ -565,7 +565,7 @@ extern "C" int dmc_maxpool3d_fwd(const void* in_hi, const void* in_lo, int clips
   const long units = (variant != 0 && compact) ? pool_blocks(clips, C / 4, g.To, g.Ho, (int)cdiv(g.Wo, 4)).units
                                                : (long)clips * g.To * g.Ho * cdiv(g.Wo, 4) * (C / 4);
   DMC_REQUIRE(units < (1L << 32), "maxpool3d_fwd: map too large");
-  DMC_REQUIRE((long)clips * (g.Ti + 2 + g.t_hi) * (g.Hi + 1) * (g.Wi + 1) * C < (1L << 30),
+  DMC_REQUIRE((long)clips * (g.Ti + 2 + g.t_hi) * (g.Hi + 1) * (g.Wi + 1) * C < (1L << 31) - (1L << 24),
               "maxpool3d_fwd: input map too large for 32-bit element offsets");
   const unsigned grid = grid_1d(units, 256, 148L * 32);
 #define DMC_POOL_FWD(...)                                                                                   \
@@ -591,7 +591,7 @@ extern "C" int dmc_maxpool3d_bwd(const float* gout, const void* idx, int clips, 
   DMC_REQUIRE(fill_pool(g, in_thw, kernel, stride, in_t_hi) == 0 && in_t_hi >= 0, "maxpool3d_bwd: bad geometry");
   const long units = (long)clips * (g.Ti + 1 + g.t_hi) * (g.Hi + 1) * cdiv(g.Wi + 1, 4) * (C / 4);
   DMC_REQUIRE(units < (1L << 32), "maxpool3d_bwd: map too large");
-  DMC_REQUIRE((long)clips * (g.To + 1) * (g.Ho + 1) * (g.Wo + 1) * C < (1L << 30),
+  DMC_REQUIRE((long)clips * (g.To + 1) * (g.Ho + 1) * (g.Wo + 1) * C < (1L << 31) - (1L << 24),
               "maxpool3d_bwd: output map too large for 32-bit element offsets");
   const unsigned grid = grid_1d(units, 256, 148L * 32);
 #define DMC_POOL_BWD(...)                                                                                   \
